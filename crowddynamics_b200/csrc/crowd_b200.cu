@@ -1,0 +1,612 @@
+// crowd_b200.cu -- hand-written sm_100a CUDA implementation of the crowddynamics per-timestep agent update,
+// behind the C ABI declared in include/crowd_b200.h.
+//
+// Compiled with -fmad=false: the reference's numba/LLVM code never contracts a*b+c, and several quantities
+// (the time-to-collision discriminant b*b - a*c, skin distances d - r_tot) are differences of nearly equal numbers,
+// so the pair kernels keep the reference's exact operation order and rounding.  Division and sqrt are IEEE
+// correctly rounded in CUDA fp64, so per-pair results differ from the CPU only through hypot/exp/sin/cos (<= 1-2 ulp).
+//
+// File:line citations refer to /root/reference/crowddynamics/.
+#include "crowd_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CK(call)                                                                                              \
+    do {                                                                                                      \
+        cudaError_t e_ = (call);                                                                              \
+        if (e_ != cudaSuccess)                                                                                \
+            return fail(CDB_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+#define CKS(call)                    \
+    do {                             \
+        int s_ = (call);             \
+        if (s_ != CDB_OK) return s_; \
+    } while (0)
+
+template <typename T>
+int dev_alloc(T **p, size_t count) {
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+    if (count == 0) count = 1;
+    CK(cudaMalloc((void **)p, count * sizeof(T)));
+    return CDB_OK;
+}
+
+inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+}  // namespace
+
+struct cdb_sim {
+    int device = 0;
+    int model = 0;
+    int64_t itemsize = 0;
+    int n_planes = 0;
+    int64_t capacity = 0;   // agent slots allocated (incl. room for ghosts / migrants)
+    int64_t n = 0;          // agents currently held
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+
+    Soa cur{}, alt{};       // ping-pong SoA state; `cur` is authoritative
+    uint8_t *d_aos = nullptr;      // device image of the packed host records (n * itemsize)
+    int64_t aos_capacity = 0;
+    uint8_t *h_bounce = nullptr;   // pinned host bounce buffer for field-wise downloads
+    int64_t bounce_bytes = 0;
+
+    // block list
+    bool lattice_fixed = false;
+    Grid grid{};             // host copy
+    Grid *d_grid = nullptr;
+    double cell_size = 0.0;
+    bool tables_valid = false;
+    int64_t cell_capacity = 0;
+    int *d_cell_count = nullptr, *d_cell_start = nullptr, *d_cell_fill = nullptr;
+    int *d_cell_of_slot = nullptr;   // flat cell of each slot (of `cur`, valid after build)
+    int *d_order_tmp = nullptr, *d_order = nullptr;
+    int *d_scan_partials = nullptr;
+    long long *d_bbox = nullptr;     // min ix, max ix, min iy, max iy
+    long long *h_bbox = nullptr;     // pinned
+
+    // obstacles / navigation
+    double *d_obstacles = nullptr;
+    int64_t n_obstacles = 0;
+    std::vector<NavField> nav;       // host copy (device pointers inside)
+    NavField *d_nav = nullptr;
+    int n_nav = 0;
+
+    // reductions / time
+    unsigned long long *d_vmax = nullptr;   // ordered-uint64 encodings: [0] max |v|, [1] max v0
+    double *d_dt = nullptr;                 // [0] last dt, [1] time_tot
+    double *h_dt = nullptr;                 // pinned double[2]
+    int *d_error = nullptr;
+    int *h_error = nullptr;                 // pinned
+    unsigned long long *d_pair_count = nullptr;
+    int64_t iterations = 0;
+};
+
+namespace {
+
+int alloc_soa(Soa &s, int n_planes, int64_t capacity) {
+    s.stride = (capacity + 31) / 32 * 32;
+    CKS(dev_alloc(&s.p, (size_t)n_planes * s.stride));
+    CKS(dev_alloc(&s.id, s.stride));
+    CKS(dev_alloc(&s.target, s.stride));
+    return CDB_OK;
+}
+
+void free_soa(Soa &s) {
+    cudaFree(s.p); cudaFree(s.id); cudaFree(s.target);
+    s = Soa{};
+}
+
+int ensure_capacity(cdb_sim *sim, int64_t n) {
+    if (n <= sim->capacity && sim->cur.p) return CDB_OK;
+    int64_t cap = n < 1024 ? 1024 : n;
+    free_soa(sim->cur); free_soa(sim->alt);
+    CKS(alloc_soa(sim->cur, sim->n_planes, cap));
+    CKS(alloc_soa(sim->alt, sim->n_planes, cap));
+    CKS(dev_alloc(&sim->d_cell_of_slot, cap));
+    CKS(dev_alloc(&sim->d_order_tmp, cap));
+    CKS(dev_alloc(&sim->d_order, cap));
+    sim->capacity = cap;
+    return CDB_OK;
+}
+
+int ensure_cells(cdb_sim *sim, int64_t ncell) {
+    if (ncell <= sim->cell_capacity) return CDB_OK;
+    int64_t cap = ncell + ncell / 4 + 1024;
+    CKS(dev_alloc(&sim->d_cell_count, cap));
+    CKS(dev_alloc(&sim->d_cell_start, cap + 1));
+    CKS(dev_alloc(&sim->d_cell_fill, cap));
+    CKS(dev_alloc(&sim->d_scan_partials, cap / SCAN_TILE + 2));
+    sim->cell_capacity = cap;
+    return CDB_OK;
+}
+
+int check_device_error(cdb_sim *sim) {
+    CK(cudaMemcpyAsync(sim->h_error, sim->d_error, sizeof(int), cudaMemcpyDeviceToHost, sim->stream));
+    CK(cudaStreamSynchronize(sim->stream));
+    int e = *sim->h_error;
+    if (e == 0) return CDB_OK;
+    CK(cudaMemsetAsync(sim->d_error, 0, sizeof(int), sim->stream));
+    if (e == ERR_NONFINITE) return fail(CDB_ERR_INVALID_VALUE, "non-finite agent position encountered on device");
+    if (e == ERR_CELL_RANGE) return fail(CDB_ERR_CAPACITY, "cell lattice too large (more than 2^31 cells)");
+    return fail(CDB_ERR_CUDA, "device error flag %d", e);
+}
+
+// ---- block list --------------------------------------------------------------------------------------------------
+int build_block_list(cdb_sim *sim, double cell_size) {
+    if (!(cell_size > 0.0) || !std::isfinite(cell_size)) return fail(CDB_ERR_INVALID_VALUE, "cell_size must be > 0");
+    const int64_t n = sim->n;
+    sim->cell_size = cell_size;
+    sim->tables_valid = false;
+    cudaStream_t st = sim->stream;
+    if (n == 0) {
+        sim->grid = Grid{0, 0, 0, 0, 0};
+        CK(cudaMemcpyAsync(sim->d_grid, &sim->grid, sizeof(Grid), cudaMemcpyHostToDevice, st));
+        sim->tables_valid = true;
+        return CDB_OK;
+    }
+    const int T = 256;
+    if (!sim->lattice_fixed) {
+        k_bbox_init<<<1, 32, 0, st>>>(sim->d_bbox);
+        k_bbox<<<cdiv(n, T * 4) < 1184 ? cdiv(n, T * 4) : 1184, T, 0, st>>>(sim->cur, (int)n, cell_size, sim->d_bbox, sim->d_error);
+        CK(cudaMemcpyAsync(sim->h_bbox, sim->d_bbox, 4 * sizeof(long long), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        CKS(check_device_error(sim));
+        long long x0 = sim->h_bbox[0], x1 = sim->h_bbox[1], y0 = sim->h_bbox[2], y1 = sim->h_bbox[3];
+        long long nx = x1 - x0 + 1, ny = y1 - y0 + 1;
+        if (nx <= 0 || ny <= 0 || (double)nx * (double)ny > 2.0e9)
+            return fail(CDB_ERR_CAPACITY, "block list of %lld x %lld cells is too large", nx, ny);
+        sim->grid = Grid{x0, y0, nx, ny, nx * ny};
+        CK(cudaMemcpyAsync(sim->d_grid, &sim->grid, sizeof(Grid), cudaMemcpyHostToDevice, st));
+    }
+    const int64_t ncell = sim->grid.ncell;
+    CKS(ensure_cells(sim, ncell));
+    CK(cudaMemsetAsync(sim->d_cell_count, 0, ncell * sizeof(int), st));
+    CK(cudaMemsetAsync(sim->d_cell_fill, 0, ncell * sizeof(int), st));
+    k_cell_count<<<cdiv(n, T), T, 0, st>>>(sim->cur, (int)n, cell_size, sim->d_grid, sim->d_cell_of_slot, sim->d_cell_count, sim->d_error);
+    // exclusive scan count -> start
+    const int nblk = cdiv(ncell, SCAN_TILE);
+    k_scan_tiles<<<nblk, SCAN_THREADS, 0, st>>>(sim->d_cell_count, sim->d_cell_start, (int)ncell, sim->d_scan_partials);
+    k_scan_partials<<<1, 1024, 0, st>>>(sim->d_scan_partials, nblk);
+    k_scan_add<<<nblk, SCAN_THREADS, 0, st>>>(sim->d_cell_start, (int)ncell, sim->d_scan_partials, (int)n);
+    k_scatter<<<cdiv(n, T), T, 0, st>>>(sim->d_cell_of_slot, (int)n, sim->d_cell_start, sim->d_cell_fill, sim->d_order_tmp);
+    k_rank_fix<<<cdiv(n, T), T, 0, st>>>(sim->d_order_tmp, (int)n, sim->cur.id, sim->d_cell_of_slot, sim->d_cell_start,
+                                         sim->d_cell_count, sim->d_order);
+    k_gather<<<cdiv(n, T), T, 0, st>>>(sim->cur, sim->alt, (int)n, sim->n_planes, sim->d_order, sim->d_cell_of_slot, sim->d_order_tmp);
+    // d_order_tmp now holds the flat cell of every *sorted* slot
+    std::swap(sim->cur, sim->alt);
+    std::swap(sim->d_cell_of_slot, sim->d_order_tmp);
+    CK(cudaGetLastError());
+    sim->tables_valid = true;
+    return CDB_OK;
+}
+
+int launch_reduce_vmax(cdb_sim *sim) {
+    cudaStream_t st = sim->stream;
+    k_vmax_init<<<1, 32, 0, st>>>(sim->d_vmax);
+    if (sim->n > 0) {
+        int blocks = cdiv(sim->n, 256 * 4);
+        if (blocks > 1184) blocks = 1184;
+        k_vmax<<<blocks, 256, 0, st>>>(sim->cur, (int)sim->n, sim->d_vmax);
+    }
+    CK(cudaGetLastError());
+    return CDB_OK;
+}
+
+int node_reset(cdb_sim *sim) {
+    if (sim->n) k_reset<<<cdiv(sim->n, 256), 256, 0, sim->stream>>>(sim->cur, (int)sim->n, sim->model);
+    CK(cudaGetLastError());
+    return CDB_OK;
+}
+int node_navigation(cdb_sim *sim) {
+    if (sim->n && sim->n_nav) k_navigation<<<cdiv(sim->n, 256), 256, 0, sim->stream>>>(sim->cur, (int)sim->n, sim->d_nav, sim->n_nav);
+    CK(cudaGetLastError());
+    return CDB_OK;
+}
+int node_orientation(cdb_sim *sim) {
+    if (sim->n && sim->model == CDB_MODEL_THREE_CIRCLE) k_orientation<<<cdiv(sim->n, 256), 256, 0, sim->stream>>>(sim->cur, (int)sim->n);
+    CK(cudaGetLastError());
+    return CDB_OK;
+}
+int node_adjust(cdb_sim *sim) {
+    if (sim->n) k_adjust<<<cdiv(sim->n, 256), 256, 0, sim->stream>>>(sim->cur, (int)sim->n, sim->model);
+    CK(cudaGetLastError());
+    return CDB_OK;
+}
+int node_agent_agent(cdb_sim *sim, double cell_size) {
+    CKS(build_block_list(sim, cell_size));
+    if (sim->n == 0) return CDB_OK;
+    const int T = 128;
+    if (sim->model == CDB_MODEL_CIRCULAR)
+        k_agent_agent_circular_v1<<<cdiv(sim->n, T), T, 0, sim->stream>>>(sim->cur, (int)sim->n, sim->d_grid, sim->d_cell_of_slot,
+                                                                          sim->d_cell_start, sim->d_cell_count);
+    else
+        k_agent_agent_three_circle_v1<<<cdiv(sim->n, T), T, 0, sim->stream>>>(sim->cur, (int)sim->n, sim->d_grid, sim->d_cell_of_slot,
+                                                                              sim->d_cell_start, sim->d_cell_count);
+    CK(cudaGetLastError());
+    return CDB_OK;
+}
+int node_agent_obstacle(cdb_sim *sim) {
+    if (sim->n && sim->n_obstacles)
+        k_agent_obstacle<<<cdiv(sim->n, 128), 128, 0, sim->stream>>>(sim->cur, (int)sim->n, sim->model, sim->d_obstacles, (int)sim->n_obstacles);
+    CK(cudaGetLastError());
+    return CDB_OK;
+}
+int node_integrate(cdb_sim *sim, double dt_min, double dt_max) {
+    CKS(launch_reduce_vmax(sim));
+    k_integrate<<<sim->n ? cdiv(sim->n, 256) : 1, 256, 0, sim->stream>>>(sim->cur, (int)sim->n, sim->model, dt_min, dt_max, sim->d_vmax, sim->d_dt);
+    CK(cudaGetLastError());
+    sim->tables_valid = false;   // positions moved
+    return CDB_OK;
+}
+
+}  // namespace
+
+// =====================================================================================================================
+extern "C" {
+
+const char *cdb_last_error(void) { return g_err.c_str(); }
+int cdb_version(void) { return 100; }
+
+int cdb_device_count(int *count) {
+    if (!count) return fail(CDB_ERR_INVALID_VALUE, "count is NULL");
+    CK(cudaGetDeviceCount(count));
+    return CDB_OK;
+}
+
+int cdb_create(int device, int model, int64_t capacity, cdb_sim **out) {
+    if (!out) return fail(CDB_ERR_INVALID_VALUE, "out is NULL");
+    *out = nullptr;
+    if (model != CDB_MODEL_CIRCULAR && model != CDB_MODEL_THREE_CIRCLE) return fail(CDB_ERR_INVALID_TYPE, "unknown agent model %d", model);
+    if (capacity < 0) return fail(CDB_ERR_INVALID_VALUE, "negative capacity");
+    CK(cudaSetDevice(device));
+    cdb_sim *sim = new cdb_sim();
+    sim->device = device;
+    sim->model = model;
+    sim->itemsize = model == CDB_MODEL_CIRCULAR ? 228 : 316;
+    sim->n_planes = model == CDB_MODEL_CIRCULAR ? NP_CIRC : NP_THREE;
+    int rc = [&]() -> int {
+        CK(cudaStreamCreateWithFlags(&sim->stream, cudaStreamNonBlocking));
+        sim->own_stream = true;
+        CKS(ensure_capacity(sim, capacity));
+        CKS(dev_alloc(&sim->d_grid, 1));
+        CKS(dev_alloc(&sim->d_bbox, 4));
+        CKS(dev_alloc(&sim->d_vmax, 2));
+        CKS(dev_alloc(&sim->d_dt, 2));
+        CKS(dev_alloc(&sim->d_error, 1));
+        CKS(dev_alloc(&sim->d_pair_count, 1));
+        CKS(dev_alloc(&sim->d_nav, MAX_NAV_TARGETS));
+        CK(cudaMemset(sim->d_error, 0, sizeof(int)));
+        CK(cudaMemset(sim->d_dt, 0, 2 * sizeof(double)));
+        CK(cudaMallocHost((void **)&sim->h_bbox, 4 * sizeof(long long)));
+        CK(cudaMallocHost((void **)&sim->h_dt, 2 * sizeof(double)));
+        CK(cudaMallocHost((void **)&sim->h_error, sizeof(int)));
+        return CDB_OK;
+    }();
+    if (rc != CDB_OK) { cdb_destroy(sim); return rc; }
+    *out = sim;
+    return CDB_OK;
+}
+
+int cdb_destroy(cdb_sim *sim) {
+    if (!sim) return CDB_OK;
+    cudaSetDevice(sim->device);
+    if (sim->stream) cudaStreamSynchronize(sim->stream);
+    free_soa(sim->cur); free_soa(sim->alt);
+    cudaFree(sim->d_aos); cudaFreeHost(sim->h_bounce);
+    cudaFree(sim->d_grid); cudaFree(sim->d_cell_count); cudaFree(sim->d_cell_start); cudaFree(sim->d_cell_fill);
+    cudaFree(sim->d_cell_of_slot); cudaFree(sim->d_order_tmp); cudaFree(sim->d_order); cudaFree(sim->d_scan_partials);
+    cudaFree(sim->d_bbox); cudaFreeHost(sim->h_bbox);
+    cudaFree(sim->d_obstacles);
+    for (auto &f : sim->nav) { cudaFree((void *)f.U); cudaFree((void *)f.V); }
+    cudaFree(sim->d_nav); cudaFree(sim->d_vmax); cudaFree(sim->d_dt); cudaFreeHost(sim->h_dt);
+    cudaFree(sim->d_error); cudaFreeHost(sim->h_error); cudaFree(sim->d_pair_count);
+    if (sim->own_stream && sim->stream) cudaStreamDestroy(sim->stream);
+    delete sim;
+    return CDB_OK;
+}
+
+int cdb_set_stream(cdb_sim *sim, void *cuda_stream) {
+    if (!sim) return fail(CDB_ERR_INVALID_VALUE, "sim is NULL");
+    CK(cudaSetDevice(sim->device));
+    CK(cudaStreamSynchronize(sim->stream));
+    if (sim->own_stream) { cudaStreamDestroy(sim->stream); sim->own_stream = false; }
+    sim->stream = (cudaStream_t)cuda_stream;
+    return CDB_OK;
+}
+
+int cdb_synchronize(cdb_sim *sim) {
+    if (!sim) return fail(CDB_ERR_INVALID_VALUE, "sim is NULL");
+    CK(cudaSetDevice(sim->device));
+    CK(cudaStreamSynchronize(sim->stream));
+    return CDB_OK;
+}
+
+int64_t cdb_num_agents(const cdb_sim *sim) { return sim ? sim->n : -1; }
+
+int cdb_upload_agents_aos(cdb_sim *sim, const void *agents, int64_t n, int64_t itemsize) {
+    if (!sim) return fail(CDB_ERR_INVALID_VALUE, "sim is NULL");
+    if (itemsize != sim->itemsize) return fail(CDB_ERR_INVALID_TYPE, "agent itemsize %lld does not match the model (%lld)", (long long)itemsize, (long long)sim->itemsize);
+    if (n < 0 || (n > 0 && !agents)) return fail(CDB_ERR_INVALID_VALUE, "bad agents buffer");
+    if (n > 2000000000LL) return fail(CDB_ERR_CAPACITY, "too many agents");
+    CK(cudaSetDevice(sim->device));
+    CKS(ensure_capacity(sim, n));
+    if (n * itemsize > sim->aos_capacity) {
+        CKS(dev_alloc(&sim->d_aos, (size_t)(n * itemsize + 16)));
+        sim->aos_capacity = n * itemsize;
+    }
+    sim->n = n;
+    sim->tables_valid = false;
+    if (n == 0) return CDB_OK;
+    CK(cudaMemcpyAsync(sim->d_aos, agents, n * itemsize, cudaMemcpyHostToDevice, sim->stream));
+    const int smem = AOS_REC_PER_BLOCK * (int)itemsize;
+    if (sim->model == CDB_MODEL_CIRCULAR)
+        k_unpack_aos<0><<<cdiv(n, AOS_REC_PER_BLOCK), AOS_REC_PER_BLOCK, smem, sim->stream>>>(sim->d_aos, (int)n, sim->cur);
+    else
+        k_unpack_aos<1><<<cdiv(n, AOS_REC_PER_BLOCK), AOS_REC_PER_BLOCK, smem, sim->stream>>>(sim->d_aos, (int)n, sim->cur);
+    CK(cudaGetLastError());
+    // the host buffer may be pageable and reused by the caller right away
+    CK(cudaStreamSynchronize(sim->stream));
+    return CDB_OK;
+}
+
+int cdb_download_agents_aos(cdb_sim *sim, void *agents, int64_t n, int64_t itemsize, uint32_t field_mask) {
+    if (!sim) return fail(CDB_ERR_INVALID_VALUE, "sim is NULL");
+    if (itemsize != sim->itemsize) return fail(CDB_ERR_INVALID_TYPE, "agent itemsize %lld does not match the model (%lld)", (long long)itemsize, (long long)sim->itemsize);
+    if (n != sim->n) return fail(CDB_ERR_INVALID_VALUE, "host array has %lld agents, device holds %lld", (long long)n, (long long)sim->n);
+    if (n == 0) return CDB_OK;
+    if (!agents) return fail(CDB_ERR_INVALID_VALUE, "agents is NULL");
+    CK(cudaSetDevice(sim->device));
+    const uint32_t mask = field_mask & CDB_F_ALL_MUTABLE;
+    const uint32_t pack_mask = (field_mask & CDB_F_WHOLE_RECORD) ? (uint32_t)CDB_F_ALL_MUTABLE : mask;
+    if (sim->model == CDB_MODEL_CIRCULAR)
+        k_pack_aos<0><<<cdiv(n, 128), 128, 0, sim->stream>>>(sim->cur, (int)n, sim->d_aos, pack_mask);
+    else
+        k_pack_aos<1><<<cdiv(n, 128), 128, 0, sim->stream>>>(sim->cur, (int)n, sim->d_aos, pack_mask);
+    CK(cudaGetLastError());
+    if (field_mask & CDB_F_WHOLE_RECORD) {
+        CK(cudaMemcpyAsync(agents, sim->d_aos, n * itemsize, cudaMemcpyDeviceToHost, sim->stream));
+        CK(cudaStreamSynchronize(sim->stream));
+        return check_device_error(sim);
+    }
+    if (n * itemsize > sim->bounce_bytes) {
+        if (sim->h_bounce) cudaFreeHost(sim->h_bounce);
+        sim->h_bounce = nullptr;
+        CK(cudaMallocHost((void **)&sim->h_bounce, n * itemsize));
+        sim->bounce_bytes = n * itemsize;
+    }
+    CK(cudaMemcpyAsync(sim->h_bounce, sim->d_aos, n * itemsize, cudaMemcpyDeviceToHost, sim->stream));
+    CK(cudaStreamSynchronize(sim->stream));
+    // merge the selected fields into the caller's records (plumbing: byte copies only)
+    int nf = 0;
+    const FieldMap *fm = host_field_map(sim->model, &nf);
+    for (int f = 0; f < nf; ++f) {
+        if (!(fm[f].bit & mask)) continue;
+        const int off = fm[f].offset;
+        uint8_t *dst = (uint8_t *)agents + off;
+        const uint8_t *src = sim->h_bounce + off;
+        for (int64_t i = 0; i < n; ++i) memcpy(dst + i * itemsize, src + i * itemsize, 8);
+    }
+    return check_device_error(sim);
+}
+
+int cdb_set_obstacles(cdb_sim *sim, const double *segments, int64_t n_segments) {
+    if (!sim) return fail(CDB_ERR_INVALID_VALUE, "sim is NULL");
+    if (n_segments < 0 || (n_segments > 0 && !segments)) return fail(CDB_ERR_INVALID_VALUE, "bad obstacle buffer");
+    CK(cudaSetDevice(sim->device));
+    CK(cudaStreamSynchronize(sim->stream));
+    CKS(dev_alloc(&sim->d_obstacles, (size_t)n_segments * 4));
+    sim->n_obstacles = n_segments;
+    if (n_segments) CK(cudaMemcpy(sim->d_obstacles, segments, n_segments * 4 * sizeof(double), cudaMemcpyHostToDevice));
+    return CDB_OK;
+}
+
+int cdb_set_navigation_field(cdb_sim *sim, int64_t target, const double *U, const double *V, int64_t ny, int64_t nx,
+                             double minx, double miny, double step) {
+    if (!sim) return fail(CDB_ERR_INVALID_VALUE, "sim is NULL");
+    if (target < 0 || target >= MAX_NAV_TARGETS) return fail(CDB_ERR_INVALID_VALUE, "target index %lld out of range [0, %d)", (long long)target, MAX_NAV_TARGETS);
+    if (ny < 0 || nx < 0 || ((ny * nx) > 0 && (!U || !V))) return fail(CDB_ERR_INVALID_VALUE, "bad navigation field");
+    CK(cudaSetDevice(sim->device));
+    CK(cudaStreamSynchronize(sim->stream));
+    if ((int64_t)sim->nav.size() <= target) sim->nav.resize(target + 1, NavField{});
+    NavField &f = sim->nav[target];
+    cudaFree((void *)f.U); cudaFree((void *)f.V);
+    f = NavField{};
+    double *dU = nullptr, *dV = nullptr;
+    CKS(dev_alloc(&dU, (size_t)(ny * nx)));
+    CKS(dev_alloc(&dV, (size_t)(ny * nx)));
+    if (ny * nx > 0) {
+        CK(cudaMemcpy(dU, U, ny * nx * sizeof(double), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(dV, V, ny * nx * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    f.U = dU; f.V = dV; f.ny = ny; f.nx = nx; f.minx = minx; f.miny = miny; f.step = step; f.valid = 1;
+    sim->n_nav = (int)sim->nav.size();
+    CK(cudaMemcpy(sim->d_nav, sim->nav.data(), sim->nav.size() * sizeof(NavField), cudaMemcpyHostToDevice));
+    return CDB_OK;
+}
+
+int cdb_clear_navigation(cdb_sim *sim) {
+    if (!sim) return fail(CDB_ERR_INVALID_VALUE, "sim is NULL");
+    CK(cudaSetDevice(sim->device));
+    CK(cudaStreamSynchronize(sim->stream));
+    for (auto &f : sim->nav) { cudaFree((void *)f.U); cudaFree((void *)f.V); }
+    sim->nav.clear();
+    sim->n_nav = 0;
+    return CDB_OK;
+}
+
+#define SIM_ENTRY()                                               \
+    if (!sim) return fail(CDB_ERR_INVALID_VALUE, "sim is NULL"); \
+    CK(cudaSetDevice(sim->device))
+
+int cdb_reset(cdb_sim *sim) { SIM_ENTRY(); return node_reset(sim); }
+int cdb_navigation(cdb_sim *sim) { SIM_ENTRY(); return node_navigation(sim); }
+int cdb_orientation(cdb_sim *sim) { SIM_ENTRY(); return node_orientation(sim); }
+int cdb_adjust(cdb_sim *sim) { SIM_ENTRY(); return node_adjust(sim); }
+int cdb_agent_agent(cdb_sim *sim, double cell_size) { SIM_ENTRY(); return node_agent_agent(sim, cell_size); }
+int cdb_agent_obstacle(cdb_sim *sim) { SIM_ENTRY(); return node_agent_obstacle(sim); }
+
+int cdb_integrate(cdb_sim *sim, double dt_min, double dt_max, double *dt_out) {
+    SIM_ENTRY();
+    CKS(node_integrate(sim, dt_min, dt_max));
+    if (dt_out) {
+        CK(cudaMemcpyAsync(sim->h_dt, sim->d_dt, 2 * sizeof(double), cudaMemcpyDeviceToHost, sim->stream));
+        CK(cudaStreamSynchronize(sim->stream));
+        *dt_out = sim->h_dt[0];
+    }
+    return CDB_OK;
+}
+
+int cdb_step(cdb_sim *sim, uint32_t flags, double cell_size, double dt_min, double dt_max, int64_t n_steps, double *dt_out) {
+    SIM_ENTRY();
+    if (n_steps < 0) return fail(CDB_ERR_INVALID_VALUE, "negative n_steps");
+    for (int64_t k = 0; k < n_steps; ++k) {
+        if (flags & CDB_STEP_NAVIGATION) CKS(node_navigation(sim));
+        if (flags & CDB_STEP_ORIENTATION) CKS(node_orientation(sim));
+        if (flags & CDB_STEP_ADJUSTING) CKS(node_adjust(sim));
+        if (flags & CDB_STEP_AGENT_AGENT) CKS(node_agent_agent(sim, cell_size));
+        if (flags & CDB_STEP_AGENT_OBSTACLE) CKS(node_agent_obstacle(sim));
+        if (flags & CDB_STEP_INTEGRATOR) {
+            CKS(node_integrate(sim, dt_min, dt_max));
+            if (dt_out) {
+                CK(cudaMemcpyAsync(sim->h_dt, sim->d_dt, 2 * sizeof(double), cudaMemcpyDeviceToHost, sim->stream));
+                CK(cudaStreamSynchronize(sim->stream));
+                dt_out[k] = sim->h_dt[0];
+            }
+        }
+        if (flags & CDB_STEP_RESET) CKS(node_reset(sim));
+        sim->iterations++;
+    }
+    return CDB_OK;
+}
+
+int cdb_get_time(cdb_sim *sim, double *time_tot, int64_t *iterations) {
+    SIM_ENTRY();
+    CK(cudaMemcpyAsync(sim->h_dt, sim->d_dt, 2 * sizeof(double), cudaMemcpyDeviceToHost, sim->stream));
+    CK(cudaStreamSynchronize(sim->stream));
+    if (time_tot) *time_tot = sim->h_dt[1];
+    if (iterations) *iterations = sim->iterations;
+    return check_device_error(sim);
+}
+
+// ---- block list exports -------------------------------------------------------------------------------------------
+int cdb_build_block_list(cdb_sim *sim, double cell_size) { SIM_ENTRY(); return build_block_list(sim, cell_size); }
+
+int cdb_get_grid(cdb_sim *sim, int64_t grid[4]) {
+    SIM_ENTRY();
+    if (!sim->tables_valid) return fail(CDB_ERR_STATE, "no block list has been built for the current positions");
+    grid[0] = sim->grid.ix_min; grid[1] = sim->grid.iy_min; grid[2] = sim->grid.nx; grid[3] = sim->grid.ny;
+    return CDB_OK;
+}
+
+int cdb_get_cell_ids(cdb_sim *sim, int64_t *cell_of_agent, int64_t n) {
+    SIM_ENTRY();
+    if (!sim->tables_valid) return fail(CDB_ERR_STATE, "no block list has been built for the current positions");
+    if (n != sim->n) return fail(CDB_ERR_INVALID_VALUE, "size mismatch");
+    if (n == 0) return CDB_OK;
+    long long *d = nullptr;
+    CKS(dev_alloc(&d, (size_t)n));
+    k_export_cell_ids<<<cdiv(n, 256), 256, 0, sim->stream>>>(sim->cur.id, sim->d_cell_of_slot, (int)n, d);
+    CK(cudaMemcpyAsync(cell_of_agent, d, n * sizeof(long long), cudaMemcpyDeviceToHost, sim->stream));
+    CK(cudaStreamSynchronize(sim->stream));
+    cudaFree(d);
+    return CDB_OK;
+}
+
+int cdb_get_cell_tables(cdb_sim *sim, int64_t *points_indices, int64_t n, int64_t *cells_count, int64_t *cells_offset, int64_t n_cells) {
+    SIM_ENTRY();
+    if (!sim->tables_valid) return fail(CDB_ERR_STATE, "no block list has been built for the current positions");
+    if (n != sim->n || n_cells != sim->grid.ncell) return fail(CDB_ERR_INVALID_VALUE, "size mismatch (n %lld vs %lld, cells %lld vs %lld)", (long long)n, (long long)sim->n, (long long)n_cells, (long long)sim->grid.ncell);
+    if (n == 0) return CDB_OK;
+    long long *d = nullptr;
+    const int64_t m = n > n_cells ? n : n_cells;
+    CKS(dev_alloc(&d, (size_t)m));
+    k_widen<<<cdiv(n, 256), 256, 0, sim->stream>>>(sim->cur.id, (int)n, d);
+    CK(cudaMemcpyAsync(points_indices, d, n * sizeof(long long), cudaMemcpyDeviceToHost, sim->stream));
+    k_widen<<<cdiv(n_cells, 256), 256, 0, sim->stream>>>(sim->d_cell_count, (int)n_cells, d);
+    CK(cudaMemcpyAsync(cells_count, d, n_cells * sizeof(long long), cudaMemcpyDeviceToHost, sim->stream));
+    k_widen<<<cdiv(n_cells, 256), 256, 0, sim->stream>>>(sim->d_cell_start, (int)n_cells, d);
+    CK(cudaMemcpyAsync(cells_offset, d, n_cells * sizeof(long long), cudaMemcpyDeviceToHost, sim->stream));
+    CK(cudaStreamSynchronize(sim->stream));
+    cudaFree(d);
+    return CDB_OK;
+}
+
+int cdb_get_neighbor_pairs(cdb_sim *sim, int64_t *pairs, int64_t cap, int64_t *count) {
+    SIM_ENTRY();
+    if (!sim->tables_valid) return fail(CDB_ERR_STATE, "no block list has been built for the current positions");
+    if (!count) return fail(CDB_ERR_INVALID_VALUE, "count is NULL");
+    *count = 0;
+    if (sim->n == 0) return CDB_OK;
+    long long *d = nullptr;
+    CKS(dev_alloc(&d, (size_t)(cap > 0 ? 2 * cap : 1)));
+    CK(cudaMemsetAsync(sim->d_pair_count, 0, sizeof(unsigned long long), sim->stream));
+    k_export_pairs<<<cdiv(sim->n, 128), 128, 0, sim->stream>>>(sim->cur.id, (int)sim->n, sim->d_grid, sim->d_cell_of_slot, sim->d_cell_start,
+                                                             sim->d_cell_count, d, cap > 0 && pairs ? cap : 0, sim->d_pair_count);
+    unsigned long long c = 0;
+    CK(cudaMemcpyAsync(&c, sim->d_pair_count, sizeof(c), cudaMemcpyDeviceToHost, sim->stream));
+    CK(cudaStreamSynchronize(sim->stream));
+    *count = (int64_t)c;
+    if (pairs && cap > 0) {
+        int64_t m = (int64_t)c < cap ? (int64_t)c : cap;
+        CK(cudaMemcpy(pairs, d, 2 * m * sizeof(long long), cudaMemcpyDeviceToHost));
+    }
+    cudaFree(d);
+    return CDB_OK;
+}
+
+// ---- fixed lattice / strips -----------------------------------------------------------------------------------------
+int cdb_set_lattice(cdb_sim *sim, int64_t ix_min, int64_t iy_min, int64_t nx, int64_t ny) {
+    SIM_ENTRY();
+    if (nx <= 0 || ny <= 0 || (double)nx * (double)ny > 2.0e9) return fail(CDB_ERR_INVALID_VALUE, "bad lattice shape");
+    CK(cudaStreamSynchronize(sim->stream));
+    sim->grid = Grid{ix_min, iy_min, nx, ny, nx * ny};
+    sim->lattice_fixed = true;
+    sim->tables_valid = false;
+    CK(cudaMemcpy(sim->d_grid, &sim->grid, sizeof(Grid), cudaMemcpyHostToDevice));
+    return CDB_OK;
+}
+int cdb_clear_lattice(cdb_sim *sim) {
+    SIM_ENTRY();
+    sim->lattice_fixed = false;
+    sim->tables_valid = false;
+    return CDB_OK;
+}
+
+int cdb_set_strip(cdb_sim *sim, int64_t, int64_t, int, int) { SIM_ENTRY(); return fail(CDB_ERR_STATE, "strip decomposition not built yet"); }
+int64_t cdb_halo_record_doubles(const cdb_sim *sim) { return sim ? (sim->model == CDB_MODEL_CIRCULAR ? 6 : 14) : -1; }
+int64_t cdb_migrant_record_doubles(const cdb_sim *sim) { return sim ? sim->n_planes + 2 : -1; }
+int cdb_halo_pack(cdb_sim *sim, int, double *, int64_t) { SIM_ENTRY(); return fail(CDB_ERR_STATE, "strip decomposition not built yet"); }
+int cdb_halo_unpack(cdb_sim *sim, int, const double *, int64_t) { SIM_ENTRY(); return fail(CDB_ERR_STATE, "strip decomposition not built yet"); }
+int cdb_migrants_pack(cdb_sim *sim, int, double *, int64_t) { SIM_ENTRY(); return fail(CDB_ERR_STATE, "strip decomposition not built yet"); }
+int cdb_migrants_unpack(cdb_sim *sim, int, const double *, int64_t) { SIM_ENTRY(); return fail(CDB_ERR_STATE, "strip decomposition not built yet"); }
+int cdb_strip_step_begin(cdb_sim *sim, uint32_t, double) { SIM_ENTRY(); return fail(CDB_ERR_STATE, "strip decomposition not built yet"); }
+double *cdb_strip_vmax_ptr(cdb_sim *sim) { return sim ? (double *)sim->d_vmax : nullptr; }
+int cdb_strip_step_finish(cdb_sim *sim, uint32_t, double, double) { SIM_ENTRY(); return fail(CDB_ERR_STATE, "strip decomposition not built yet"); }
+int cdb_strip_absorb(cdb_sim *sim) { SIM_ENTRY(); return fail(CDB_ERR_STATE, "strip decomposition not built yet"); }
+
+}  // extern "C"

@@ -1,0 +1,744 @@
+// kernels.cuh -- device code of libcrowd_b200: data layout, pair / wall / integrator arithmetic and the kernels.
+// All arithmetic is fp64 and follows the reference's operation order (compiled with -fmad=false, see crowd_b200.cu).
+// File:line citations refer to /root/reference/crowddynamics/.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "crowd_b200.h"
+
+// ---- HBM layout: struct-of-arrays "planes" of doubles, plane k at p + k * stride ---------------------------------
+enum Plane {
+    PX, PY, VX, VY, E0X, E0Y, FX, FY, FPX, FPY,                 // position, velocity, target_direction, force, force_prev
+    RADIUS, MASS, V0, TAU_ADJ, K_SOC, TAU_0, MU, KAPPA, DAMPING,  // per-agent constants
+    NP_CIRC,
+    LSX = NP_CIRC, LSY, RSX, RSY,                               // position_ls, position_rs
+    R_T, R_S, R_TS, INERTIA, OMEGA0,                            // body constants (three-circle)
+    PHI, OMEGA, PHI0, TORQUE, TORQUE_PREV, TAU_ROT,             // orientation, angular_velocity, target_orientation, ...
+    NP_THREE
+};
+
+struct Soa {
+    double *p;
+    long long stride;
+    int *id;             // original agent index (row in the host array) of the agent in this slot
+    long long *target;   // States.target (simulation/agents.py:41-45)
+    __device__ __forceinline__ double &operator()(int plane, int i) const { return p[(long long)plane * stride + i]; }
+};
+
+struct Grid { long long ix_min, iy_min, nx, ny, ncell; };
+
+struct NavField { const double *U, *V; long long ny, nx; double minx, miny, step; int valid; };
+
+struct FieldMap { short plane; short offset; unsigned bit; };
+
+enum { ERR_NONE = 0, ERR_NONFINITE = 1, ERR_CELL_RANGE = 2 };
+constexpr int MAX_NAV_TARGETS = 64;
+constexpr int AOS_REC_PER_BLOCK = 128;
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+#define SIGTH_SOC 3.0    // core/interactions.py:45
+#define F_SOC_MAX 2e3    // core/motion/power_law.py:52
+#define TAU_MAX 30.0     // core/motion/power_law.py:243
+#define CDB_PI 3.141592653589793
+
+// Packed record layout (simulation/agents.py:447-457 via traits.py:158-219).  B = offset of the circular block
+// (0 for circular, 32 for three_circle whose position_ls/position_rs come first).
+#define CIRC_FIELDS(B)                                                                                         \
+    {RADIUS, B + 28, 0}, {MASS, B + 60, 0}, {V0, B + 76, 0},                                                   \
+    {PX, B + 92, CDB_F_POSITION}, {PY, B + 100, CDB_F_POSITION}, {VX, B + 108, CDB_F_VELOCITY}, {VY, B + 116, CDB_F_VELOCITY}, \
+    {E0X, B + 124, CDB_F_TARGET_DIRECTION}, {E0Y, B + 132, CDB_F_TARGET_DIRECTION}, {FX, B + 140, CDB_F_FORCE},   \
+    {FY, B + 148, CDB_F_FORCE}, {FPX, B + 156, CDB_F_FORCE_PREV}, {FPY, B + 164, CDB_F_FORCE_PREV},            \
+    {TAU_ADJ, B + 172, 0}, {K_SOC, B + 180, 0}, {TAU_0, B + 188, 0}, {MU, B + 196, 0}, {KAPPA, B + 204, 0},     \
+    {DAMPING, B + 212, 0}
+#define THREE_FIELDS                                                                                           \
+    {LSX, 0, CDB_F_SHOULDERS}, {LSY, 8, CDB_F_SHOULDERS}, {RSX, 16, CDB_F_SHOULDERS}, {RSY, 24, CDB_F_SHOULDERS}, \
+    {R_T, 32 + 36, 0}, {R_S, 32 + 44, 0}, {R_TS, 32 + 52, 0}, {INERTIA, 32 + 68, 0}, {OMEGA0, 32 + 84, 0},     \
+    {PHI, 260, CDB_F_ORIENTATION}, {OMEGA, 268, CDB_F_ANGULAR_VELOCITY}, {PHI0, 276, CDB_F_TARGET_ORIENTATION}, \
+    {TORQUE, 284, CDB_F_TORQUE}, {TORQUE_PREV, 292, CDB_F_TORQUE_PREV}, {TAU_ROT, 300, 0}
+
+__constant__ FieldMap c_fields_circ[] = {CIRC_FIELDS(0)};
+__constant__ FieldMap c_fields_three[] = {CIRC_FIELDS(32), THREE_FIELDS};
+static const FieldMap h_fields_circ[] = {CIRC_FIELDS(0)};
+static const FieldMap h_fields_three[] = {CIRC_FIELDS(32), THREE_FIELDS};
+constexpr int N_FIELDS_CIRC = 19;
+constexpr int N_FIELDS_THREE = 19 + 15;
+static_assert(sizeof(h_fields_circ) / sizeof(FieldMap) == N_FIELDS_CIRC, "field table");
+static_assert(sizeof(h_fields_three) / sizeof(FieldMap) == N_FIELDS_THREE, "field table");
+
+static inline const FieldMap *host_field_map(int model, int *count) {
+    *count = model == 0 ? N_FIELDS_CIRC : N_FIELDS_THREE;
+    return model == 0 ? h_fields_circ : h_fields_three;
+}
+
+// =====================================================================================================================
+// small helpers
+// =====================================================================================================================
+__device__ __forceinline__ unsigned long long ordered_bits(double x) {
+    unsigned long long b = (unsigned long long)__double_as_longlong(x);
+    return (b & 0x8000000000000000ULL) ? ~b : (b | 0x8000000000000000ULL);
+}
+__device__ __forceinline__ double from_ordered_bits(unsigned long long k) {
+    unsigned long long b = (k & 0x8000000000000000ULL) ? (k & 0x7fffffffffffffffULL) : ~k;
+    return __longlong_as_double((long long)b);
+}
+
+// Python float modulo as numba lowers `%` (CPython float_rem); vector2D.py:29
+__device__ __forceinline__ double py_mod(double x, double y) {
+    double m = fmod(x, y);
+    if (m != 0.0) { if ((y < 0) != (m < 0)) m += y; }
+    else m = copysign(0.0, y);
+    return m;
+}
+// vector2D.py:8-36
+__device__ __forceinline__ double wrap_to_pi(double rad) {
+    double rad_ = py_mod(rad, 2 * CDB_PI);
+    if (rad < 0 && rad_ == CDB_PI) return -CDB_PI;
+    else if (rad_ > CDB_PI) return rad_ - (2 * CDB_PI);
+    else return rad_;
+}
+
+// core/motion/contact.py:14-48:  -h (mu n - kappa (v.t) t) + damping (v.n) n
+__device__ __forceinline__ void force_contact(double h, double nx, double ny, double vx, double vy, double tx, double ty,
+                                              double mu, double kappa, double damping, double &fx, double &fy) {
+    double kvt = kappa * (vx * tx + vy * ty);
+    double dvn = damping * (vx * nx + vy * ny);
+    fx = -h * (mu * nx - kvt * tx) + dvn * nx;
+    fy = -h * (mu * ny - kvt * ty) + dvn * ny;
+}
+
+// core/motion/power_law.py:84-102
+__device__ __forceinline__ double magnitude(double tau, double tau_0) {
+    return (2.0 / tau + 1.0 / tau_0) * exp(-tau / tau_0) / (tau * tau);
+}
+
+// vector2D.py:167-187
+__device__ __forceinline__ void truncate2(double &x, double &y, double l) {
+    double vlen = hypot(x, y);
+    if (vlen > l) { double s = l / vlen; x *= s; y *= s; }
+}
+
+// ---- circular pair, evaluated for agent i against neighbour j (interactions.py:53-70, distance.py:19-47,
+//      power_law.py:215-259).  The reference's (i, j) -> (j, i) swap is an exact negation for circular agents, so
+//      every agent evaluates its neighbours as "i" and obtains bit-identical per-pair forces.
+struct CircMe { double px, py, vx, vy, r, mass, k_soc, tau_0, mu, kappa, damping; };
+
+__device__ __forceinline__ void pair_circular(const CircMe &me, double pxj, double pyj, double vxj, double vyj, double rj,
+                                              double &fx, double &fy) {
+    double x = me.px - pxj, y = me.py - pyj;
+    double d = hypot(x, y);
+    double r_tot = me.r + rj;
+    double h = d - r_tot;
+    if (h < SIGTH_SOC) {
+        double vx = me.vx - vxj, vy = me.vy - vyj;
+        double a = vx * vx + vy * vy;
+        double b = -(x * vx + y * vy);
+        double c = (x * x + y * y) - r_tot * r_tot;
+        double dd = sqrt(b * b - a * c);
+        double fsx = 0.0, fsy = 0.0;
+        if (!(isnan(dd) || dd == 0.0 || a == 0.0)) {
+            double tau = (b - dd) / a;
+            if (!(tau <= 0.0 || tau > TAU_MAX)) {
+                double gx = (vx - (vx * b + x * a) / dd) / a;   // power_law.py:107-126
+                double gy = (vy - (vy * b + y * a) / dd) / a;
+                double mag = magnitude(tau, me.tau_0);
+                double mk = -me.mass * me.k_soc;
+                fsx = mk * gx * mag;
+                fsy = mk * gy * mag;
+                truncate2(fsx, fsy, F_SOC_MAX);
+            }
+        }
+        if (h < 0.0) {
+            double nx = 0.0, ny = 0.0;
+            if (d != 0.0) { nx = x / d; ny = y / d; }
+            double cx, cy;
+            force_contact(h, nx, ny, vx, vy, ny, -nx, me.mu, me.kappa, me.damping, cx, cy);   // t = rotate270(n)
+            fsx += cx; fsy += cy;
+        }
+        fx += fsx; fy += fsy;
+    }
+}
+
+// ---- three-circle pair in the reference's (i, j) orientation (interactions.py:75-104, distance.py:55-105,
+//      power_law.py:264-363).  Not symmetric under swapping (distance.py:103 quirk, selection rule power_law.py:324),
+//      so the caller says which of the two agents "me" is and gets that side's force / torque.
+struct ThreeKin { double x[3][2]; double r[3]; double vx, vy, phi, r_ts; };
+struct ThreePar { double mass, k_soc, tau_0, mu, kappa, damping; };
+
+__device__ __forceinline__ void pair_three_circle(const ThreeKin &I, const ThreeKin &J, bool me_is_i, const ThreePar &me,
+                                                  double &fx, double &fy, double &torque) {
+    // distance_three_circles
+    double h_min = nan(""), nx = 0.0, ny = 0.0;
+    int i_min = 0, j_min = 0;
+#pragma unroll
+    for (int pi = 0; pi < 3; ++pi)
+#pragma unroll
+        for (int pj = 0; pj < 3; ++pj) {
+            double x = I.x[pi][0] - J.x[pj][0], y = I.x[pi][1] - J.x[pj][1];
+            double d = hypot(x, y);
+            double h = d - (I.r[pi] + J.r[pj]);
+            if (h < h_min || isnan(h_min)) {
+                h_min = h; i_min = pi; j_min = pj;
+                if (d == 0.0) { nx = 0.0; ny = 0.0; } else { nx = x / d; ny = y / d; }
+            }
+        }
+    if (!(h_min < SIGTH_SOC)) return;
+    double vx = I.vx - J.vx, vy = I.vy - J.vy;
+    double a = vx * vx + vy * vy;
+    double fsx = 0.0, fsy = 0.0;
+    if (a != 0.0) {
+        int contact_i = 0, contact_j = 0;
+        double tau = nan(""), b_min = nan(""), d_min = nan("");
+#pragma unroll
+        for (int pi = 0; pi < 3; ++pi)
+#pragma unroll
+            for (int pj = 0; pj < 3; ++pj) {
+                double x = I.x[pi][0] - J.x[pj][0], y = I.x[pi][1] - J.x[pj][1];
+                double r_tot = I.r[pi] + J.r[pj];
+                double b = -(x * vx + y * vy);
+                double c = (x * x + y * y) - r_tot * r_tot;
+                double dd = sqrt(b * b - a * c);
+                if (isnan(dd) || dd == 0.0) continue;
+                double tau_new = (b - dd) / a;
+                if (isnan(tau) || (0.0 < tau_new && tau_new < tau)) {
+                    contact_i = pi; contact_j = pj; tau = tau_new; b_min = b; d_min = dd;
+                }
+            }
+        if (!(isnan(tau) || tau <= 0.0)) {
+            double oix = 0.0, oiy = 0.0, ojx = 0.0, ojy = 0.0;   // shoulder displacement vectors, power_law.py:333-350
+            if (contact_i == 1) { oix += I.r_ts * sin(I.phi); oiy += I.r_ts * -cos(I.phi); }
+            else if (contact_i == 2) { oix -= I.r_ts * sin(I.phi); oiy -= I.r_ts * -cos(I.phi); }
+            if (contact_j == 1) { ojx += J.r_ts * sin(J.phi); ojy += J.r_ts * -cos(J.phi); }
+            else if (contact_j == 2) { ojx -= J.r_ts * sin(J.phi); ojy -= J.r_ts * -cos(J.phi); }
+            double xr = I.x[0][0] - J.x[0][0], yr = I.x[0][1] - J.x[0][1];
+            double ox = oix - ojx, oy = oiy - ojy;
+            double gx = (vx - (a * (xr + 2 * ox) + b_min * vx) / d_min) / a;   // power_law.py:131-149
+            double gy = (vy - (a * (yr + 2 * oy) + b_min * vy) / d_min) / a;
+            double mag = magnitude(tau, me.tau_0);
+            double mk = -me.mass * me.k_soc;
+            fsx = mk * gx * mag;
+            fsy = mk * gy * mag;
+            if (!me_is_i) { fsx = 0.0 - fsx; fsy = 0.0 - fsy; }   // force_j[:] -= ... (power_law.py:358)
+            truncate2(fsx, fsy, F_SOC_MAX);
+        }
+    }
+    if (h_min < 0.0) {
+        double cx, cy;
+        force_contact(h_min, nx, ny, vx, vy, ny, -nx, me.mu, me.kappa, me.damping, cx, cy);
+        if (me_is_i) { fsx += cx; fsy += cy; } else { fsx -= cx; fsy -= cy; }
+    }
+    double mx, my;   // moment arm, distance.py:102-103
+    if (me_is_i) {
+        mx = I.x[i_min][0] + I.r[i_min] * nx - I.x[0][0];
+        my = I.x[i_min][1] + I.r[i_min] * ny - I.x[0][1];
+    } else {
+        mx = I.x[j_min][0] - J.r[j_min] * nx - J.x[0][0];
+        my = I.x[j_min][1] - J.r[j_min] * ny - J.x[0][1];
+    }
+    fx += fsx; fy += fsy;
+    torque += mx * fsy - my * fsx;   // cross, vector2D.py:136-149
+}
+
+// ---- distance_circle_line, core/distance.py:110-146 ----------------------------------------------------------------
+__device__ __forceinline__ double distance_circle_line(double x, double y, double r, double p0x, double p0y, double p1x, double p1y,
+                                                       double &nx, double &ny) {
+    double dx = p1x - p0x, dy = p1y - p0y;
+    double l_w = hypot(dx, dy);
+    double twx = dx / l_w, twy = dy / l_w;
+    double nwx = -twy, nwy = twx;   // rotate90
+    double q0x = x - p0x, q0y = y - p0y, q1x = x - p1x, q1y = y - p1y;
+    double l_t = -(twx * q1x + twy * q1y) - (twx * q0x + twy * q0y);
+    double d_iw;
+    if (l_t > l_w) {
+        d_iw = hypot(q0x, q0y); nx = q0x / d_iw; ny = q0y / d_iw;
+    } else if (l_t < -l_w) {
+        d_iw = hypot(q1x, q1y); nx = q1x / d_iw; ny = q1y / d_iw;
+    } else {
+        double l_n = nwx * q0x + nwy * q0y;
+        d_iw = fabs(l_n);
+        double s = isnan(l_n) ? l_n : (double)((l_n > 0.0) - (l_n < 0.0));   // np.sign
+        nx = s * nwx; ny = s * nwy;
+    }
+    return d_iw - r;
+}
+
+// =====================================================================================================================
+// AoS <-> SoA
+// =====================================================================================================================
+template <int MODEL>
+__global__ void k_unpack_aos(const uint8_t *__restrict__ aos, int n, Soa s) {
+    constexpr int ITEM = MODEL == 0 ? 228 : 316;
+    constexpr int WORDS = ITEM / 4;
+    extern __shared__ uint32_t sm[];
+    const int rec0 = blockIdx.x * AOS_REC_PER_BLOCK;
+    const int nrec = min(AOS_REC_PER_BLOCK, n - rec0);
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(aos) + (size_t)rec0 * WORDS;
+    for (int w = threadIdx.x; w < nrec * WORDS; w += blockDim.x) sm[w] = src[w];   // coalesced 4-byte loads
+    __syncthreads();
+    const int t = threadIdx.x;
+    if (t >= nrec) return;
+    const int i = rec0 + t;
+    const uint32_t *rec = sm + t * WORDS;    // odd word stride: conflict-free
+    const FieldMap *fm = MODEL == 0 ? c_fields_circ : c_fields_three;
+    constexpr int NF = MODEL == 0 ? N_FIELDS_CIRC : N_FIELDS_THREE;
+#pragma unroll 1
+    for (int f = 0; f < NF; ++f) {
+        int w = fm[f].offset >> 2;
+        s(fm[f].plane, i) = __hiloint2double((int)rec[w + 1], (int)rec[w]);
+    }
+    // States.target: int64 at byte offset B + 2 (2-byte aligned)
+    const uint8_t *rb = reinterpret_cast<const uint8_t *>(rec) + (MODEL == 0 ? 2 : 34);
+    unsigned long long tv = 0;
+#pragma unroll
+    for (int b = 0; b < 8; ++b) tv |= (unsigned long long)rb[b] << (8 * b);
+    s.target[i] = (long long)tv;
+    s.id[i] = i;
+}
+
+template <int MODEL>
+__global__ void k_pack_aos(Soa s, int n, uint8_t *__restrict__ aos, unsigned mask) {
+    constexpr int ITEM = MODEL == 0 ? 228 : 316;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    uint32_t *rec = reinterpret_cast<uint32_t *>(aos + (size_t)s.id[t] * ITEM);
+    const FieldMap *fm = MODEL == 0 ? c_fields_circ : c_fields_three;
+    constexpr int NF = MODEL == 0 ? N_FIELDS_CIRC : N_FIELDS_THREE;
+#pragma unroll 1
+    for (int f = 0; f < NF; ++f) {
+        if (!(fm[f].bit & mask)) continue;
+        double v = s(fm[f].plane, t);
+        int w = fm[f].offset >> 2;
+        rec[w] = (uint32_t)__double2loint(v);
+        rec[w + 1] = (uint32_t)__double2hiint(v);
+    }
+}
+
+// =====================================================================================================================
+// block list: cell = floor(p / c) on the lattice anchored at multiples of c (spec core/block_list.py:28-52)
+// =====================================================================================================================
+__global__ void k_bbox_init(long long *bbox) {
+    if (threadIdx.x == 0) {
+        bbox[0] = 0x7fffffffffffffffLL; bbox[1] = -0x7fffffffffffffffLL - 1;
+        bbox[2] = 0x7fffffffffffffffLL; bbox[3] = -0x7fffffffffffffffLL - 1;
+    }
+}
+
+__device__ __forceinline__ long long warp_min(long long v) {
+    for (int o = 16; o; o >>= 1) { long long w = __shfl_xor_sync(0xffffffffu, v, o); v = w < v ? w : v; }
+    return v;
+}
+__device__ __forceinline__ long long warp_max(long long v) {
+    for (int o = 16; o; o >>= 1) { long long w = __shfl_xor_sync(0xffffffffu, v, o); v = w > v ? w : v; }
+    return v;
+}
+
+__global__ void k_bbox(Soa s, int n, double cell_size, long long *bbox, int *error) {
+    long long x0 = 0x7fffffffffffffffLL, x1 = -0x7fffffffffffffffLL - 1, y0 = x0, y1 = x1;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        double fx = floor(s(PX, i) / cell_size), fy = floor(s(PY, i) / cell_size);
+        if (!(fabs(fx) < 4.0e18) || !(fabs(fy) < 4.0e18)) { atomicExch(error, ERR_NONFINITE); continue; }
+        long long ix = (long long)fx, iy = (long long)fy;
+        x0 = ix < x0 ? ix : x0; x1 = ix > x1 ? ix : x1;
+        y0 = iy < y0 ? iy : y0; y1 = iy > y1 ? iy : y1;
+    }
+    x0 = warp_min(x0); x1 = warp_max(x1); y0 = warp_min(y0); y1 = warp_max(y1);
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(&bbox[0], x0); atomicMax(&bbox[1], x1);
+        atomicMin(&bbox[2], y0); atomicMax(&bbox[3], y1);
+    }
+}
+
+__device__ __forceinline__ int flat_cell(double px, double py, double cell_size, const Grid &g) {
+    double fx = floor(px / cell_size), fy = floor(py / cell_size);
+    // clamp into the lattice (no-op for a bounding-box lattice; border binning for a fixed one)
+    double rx = fx - (double)g.ix_min, ry = fy - (double)g.iy_min;
+    long long cx = rx < 0.0 ? 0 : (rx > (double)(g.nx - 1) ? g.nx - 1 : (long long)rx);
+    long long cy = ry < 0.0 ? 0 : (ry > (double)(g.ny - 1) ? g.ny - 1 : (long long)ry);
+    return (int)(cx * g.ny + cy);
+}
+
+__global__ void k_cell_count(Soa s, int n, double cell_size, const Grid *grid, int *cell_of_slot, int *cell_count, int *error) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const Grid g = *grid;
+    double px = s(PX, i), py = s(PY, i);
+    if (!isfinite(px) || !isfinite(py)) atomicExch(error, ERR_NONFINITE);
+    int c = flat_cell(px, py, cell_size, g);
+    cell_of_slot[i] = c;
+    atomicAdd(&cell_count[c], 1);
+}
+
+// exclusive scan of cell counts -> cell starts (three small kernels; the table is tiny next to the agent state)
+__global__ void k_scan_tiles(const int *__restrict__ in, int *__restrict__ out, int n, int *__restrict__ partials) {
+    __shared__ int warp_sums[SCAN_THREADS / 32];
+    const int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+    int v[SCAN_ITEMS], sum = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) { v[k] = (base + k < n) ? in[base + k] : 0; sum += v[k]; }
+    int incl = sum;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int o = 1; o < 32; o <<= 1) { int w = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += w; }
+    if (lane == 31) warp_sums[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        int ws = lane < SCAN_THREADS / 32 ? warp_sums[lane] : 0;
+        int wi = ws;
+        for (int o = 1; o < 32; o <<= 1) { int w = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += w; }
+        if (lane < SCAN_THREADS / 32) warp_sums[lane] = wi - ws;
+        if (lane == SCAN_THREADS / 32 - 1) partials[blockIdx.x] = wi;
+    }
+    __syncthreads();
+    int run = warp_sums[warp] + incl - sum;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) { if (base + k < n) out[base + k] = run; run += v[k]; }
+}
+
+__global__ void k_scan_partials(int *partials, int m) {
+    __shared__ int warp_sums[32];
+    __shared__ int carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int base = 0; base < m; base += blockDim.x) {
+        int i = base + threadIdx.x;
+        int v = i < m ? partials[i] : 0;
+        int incl = v;
+        for (int o = 1; o < 32; o <<= 1) { int w = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += w; }
+        if (lane == 31) warp_sums[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            int ws = warp_sums[lane], wi = ws;
+            for (int o = 1; o < 32; o <<= 1) { int w = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += w; }
+            warp_sums[lane] = wi - ws;
+        }
+        __syncthreads();
+        int carry = carry_s;
+        int excl = carry + warp_sums[warp] + incl - v;
+        if (i < m) partials[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) carry_s = excl + v;
+        __syncthreads();
+    }
+}
+
+__global__ void k_scan_add(int *out, int n, const int *__restrict__ partials, int total) {
+    const int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+    const int add = partials[blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) if (base + k < n) out[base + k] += add;
+    if (blockIdx.x == 0 && threadIdx.x == 0) out[n] = total;
+}
+
+__global__ void k_scatter(const int *__restrict__ cell_of_slot, int n, const int *__restrict__ cell_start, int *cell_fill, int *order_tmp) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int c = cell_of_slot[i];
+    order_tmp[cell_start[c] + atomicAdd(&cell_fill[c], 1)] = i;
+}
+
+// make the order inside every cell deterministic: ascending original agent index (== stable counting sort of the
+// reference block list, whatever order the atomics of k_scatter resolved in)
+__global__ void k_rank_fix(const int *__restrict__ order_tmp, int n, const int *__restrict__ id, const int *__restrict__ cell_of_slot,
+                           const int *__restrict__ cell_start, const int *__restrict__ cell_count, int *__restrict__ order) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const int src = order_tmp[t];
+    const int c = cell_of_slot[src];
+    const int b = cell_start[c], e = b + cell_count[c];
+    const int my = id[src];
+    int rank = 0;
+    for (int u = b; u < e; ++u) rank += id[order_tmp[u]] < my;
+    order[b + rank] = src;
+}
+
+__global__ void k_gather(Soa src, Soa dst, int n, int n_planes, const int *__restrict__ order, const int *__restrict__ cell_of_slot,
+                         int *__restrict__ cell_sorted) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const int o = order[t];
+    for (int k = 0; k < n_planes; ++k) dst(k, t) = src(k, o);
+    dst.id[t] = src.id[o];
+    dst.target[t] = src.target[o];
+    cell_sorted[t] = cell_of_slot[o];
+}
+
+__global__ void k_export_cell_ids(const int *__restrict__ id, const int *__restrict__ cell_sorted, int n, long long *out) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) out[id[t]] = cell_sorted[t];
+}
+__global__ void k_widen(const int *__restrict__ in, int n, long long *out) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) out[t] = in[t];
+}
+
+// candidate pairs of the block list, forward half stencil (0,0)+, (0,+1), (+1,-1), (+1,0), (+1,+1)
+__global__ void k_export_pairs(const int *__restrict__ id, int n, const Grid *grid, const int *__restrict__ cell_sorted,
+                               const int *__restrict__ cell_start, const int *__restrict__ cell_count, long long *pairs,
+                               long long cap, unsigned long long *count) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const Grid g = *grid;
+    const int c = cell_sorted[t];
+    const long long cx = c / g.ny, cy = c % g.ny;
+    const long long me = id[t];
+    const int sx[5] = {0, 0, 1, 1, 1}, sy[5] = {0, 1, -1, 0, 1};
+    for (int k = 0; k < 5; ++k) {
+        long long x2 = cx + sx[k], y2 = cy + sy[k];
+        if (x2 >= g.nx || y2 < 0 || y2 >= g.ny) continue;
+        int d = (int)(x2 * g.ny + y2);
+        int b = k == 0 ? t + 1 : cell_start[d], e = cell_start[d] + cell_count[d];
+        for (int u = b; u < e; ++u) {
+            unsigned long long slot = atomicAdd(count, 1ULL);
+            if ((long long)slot < cap) { pairs[2 * slot] = me; pairs[2 * slot + 1] = id[u]; }
+        }
+    }
+}
+
+// =====================================================================================================================
+// per-agent nodes
+// =====================================================================================================================
+__global__ void k_reset(Soa s, int n, int model) {   // logic.py:59-64
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    s(FX, i) = 0.0; s(FY, i) = 0.0;
+    if (model == CDB_MODEL_THREE_CIRCLE) s(TORQUE, i) = 0.0;
+}
+
+// logic.py:149-165: indices = trunc((pos - (minx, miny)) / step) (quickest_path.py:41-44), in-grid => e0 = (U, V)[iy, ix]
+__device__ __forceinline__ void navigation_sample(const NavField *nav, int n_nav, long long target, double px, double py,
+                                                  double &e0x, double &e0y) {
+    if (target < 0 || target >= n_nav) return;
+    const NavField f = nav[target];
+    if (!f.valid) return;
+    double fx = (px - f.minx) / f.step, fy = (py - f.miny) / f.step;
+    if (!(fabs(fx) < 9.0e18) || !(fabs(fy) < 9.0e18)) return;
+    long long jx = (long long)fx, jy = (long long)fy;   // toward zero, like ndarray.astype(int64)
+    if (0 <= jy && jy < f.ny && 0 <= jx && jx < f.nx) {
+        e0x = f.U[jy * f.nx + jx];
+        e0y = f.V[jy * f.nx + jx];
+    }
+}
+
+__global__ void k_navigation(Soa s, int n, const NavField *nav, int n_nav) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double ex = s(E0X, i), ey = s(E0Y, i);
+    navigation_sample(nav, n_nav, s.target[i], s(PX, i), s(PY, i), ex, ey);
+    s(E0X, i) = ex; s(E0Y, i) = ey;
+}
+
+__global__ void k_orientation(Soa s, int n) {   // steering/orientation.py:17-21
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    s(PHI0, i) = atan2(s(E0Y, i), s(E0X, i));
+}
+
+// motion/adjusting.py:18-51,56-95
+__device__ __forceinline__ void adjust_force(double mass, double tau_adj, double v0, double e0x, double e0y, double vx, double vy,
+                                             double &fx, double &fy) {
+    double sc = mass / tau_adj;
+    fx = sc * (v0 * e0x - vx);
+    fy = sc * (v0 * e0y - vy);
+}
+__device__ __forceinline__ double adjust_torque(double inertia, double tau_rot, double phi0, double phi, double omega0, double omega) {
+    return inertia / tau_rot * (wrap_to_pi(phi0 - phi) / CDB_PI * omega0 - omega);
+}
+
+__global__ void k_adjust(Soa s, int n, int model) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double fx, fy;
+    adjust_force(s(MASS, i), s(TAU_ADJ, i), s(V0, i), s(E0X, i), s(E0Y, i), s(VX, i), s(VY, i), fx, fy);
+    s(FX, i) += fx; s(FY, i) += fy;
+    if (model == CDB_MODEL_THREE_CIRCLE)
+        s(TORQUE, i) += adjust_torque(s(INERTIA, i), s(TAU_ROT, i), s(PHI0, i), s(PHI, i), s(OMEGA0, i), s(OMEGA, i));
+}
+
+// interactions.py:107-141,169-186
+__device__ __forceinline__ void walls_circular(double px, double py, double r, double vx, double vy, double mu, double kappa, double damping,
+                                               const double *__restrict__ obs, int n_obs, double &fx, double &fy) {
+    for (int w = 0; w < n_obs; ++w) {
+        double nx, ny;
+        double h = distance_circle_line(px, py, r, obs[4 * w], obs[4 * w + 1], obs[4 * w + 2], obs[4 * w + 3], nx, ny);
+        if (h < 0.0) {
+            double cx, cy;
+            force_contact(h, nx, ny, vx, vy, ny, -nx, mu, kappa, damping, cx, cy);
+            fx += cx; fy += cy;
+        }
+    }
+}
+
+__device__ __forceinline__ void walls_three_circle(const double x[3][2], const double r[3], double vx, double vy, double mu, double kappa,
+                                                   double damping, const double *__restrict__ obs, int n_obs, double &fx, double &fy,
+                                                   double &torque) {
+    for (int w = 0; w < n_obs; ++w) {
+        double h_min = nan(""), nx = 0.0, ny = 0.0;
+        int i_min = 0;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {   // distance.py:154-180
+            double ax, ay;
+            double h = distance_circle_line(x[k][0], x[k][1], r[k], obs[4 * w], obs[4 * w + 1], obs[4 * w + 2], obs[4 * w + 3], ax, ay);
+            if (h < h_min || isnan(h_min)) { h_min = h; nx = ax; ny = ay; i_min = k; }
+        }
+        if (h_min < 0.0) {
+            double mx = x[i_min][0] - r[i_min] * nx - x[0][0];
+            double my = x[i_min][1] - r[i_min] * ny - x[0][1];
+            double cx, cy;
+            force_contact(h_min, nx, ny, vx, vy, ny, -nx, mu, kappa, damping, cx, cy);
+            fx += cx; fy += cy;
+            torque += mx * cy - my * cx;
+        }
+    }
+}
+
+__global__ void k_agent_obstacle(Soa s, int n, int model, const double *__restrict__ obs, int n_obs) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double fx = s(FX, i), fy = s(FY, i);
+    if (model == CDB_MODEL_CIRCULAR) {
+        walls_circular(s(PX, i), s(PY, i), s(RADIUS, i), s(VX, i), s(VY, i), s(MU, i), s(KAPPA, i), s(DAMPING, i), obs, n_obs, fx, fy);
+    } else {
+        double x[3][2] = {{s(PX, i), s(PY, i)}, {s(LSX, i), s(LSY, i)}, {s(RSX, i), s(RSY, i)}};
+        double r[3] = {s(R_T, i), s(R_S, i), s(R_S, i)};
+        double tq = s(TORQUE, i);
+        walls_three_circle(x, r, s(VX, i), s(VY, i), s(MU, i), s(KAPPA, i), s(DAMPING, i), obs, n_obs, fx, fy, tq);
+        s(TORQUE, i) = tq;
+    }
+    s(FX, i) = fx; s(FY, i) = fy;
+}
+
+// ---- integrator: core/integrator.py:32-97,167-193,209-256 + shoulders simulation/agents.py:473-486 ---------------
+__global__ void k_vmax_init(unsigned long long *vmax) {
+    if (threadIdx.x == 0) { vmax[0] = ordered_bits(0.0); vmax[1] = ordered_bits(-__longlong_as_double(0x7ff0000000000000LL)); }
+}
+
+__device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long v) {
+    for (int o = 16; o; o >>= 1) { unsigned long long w = __shfl_xor_sync(0xffffffffu, v, o); v = w > v ? w : v; }
+    return v;
+}
+
+__global__ void k_vmax(Soa s, int n, unsigned long long *vmax) {
+    double v_max = 0.0;
+    unsigned long long v0 = ordered_bits(-__longlong_as_double(0x7ff0000000000000LL));
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        double l = hypot(s(VX, i), s(VY, i));
+        if (l > v_max) v_max = l;                    // NaN speeds are skipped, as in the reference loop
+        double t = s(V0, i);
+        unsigned long long tb = isnan(t) ? 0xffffffffffffffffULL : ordered_bits(t);   // np.max propagates NaN
+        v0 = tb > v0 ? tb : v0;
+    }
+    unsigned long long vm = warp_max_u64(ordered_bits(v_max));
+    v0 = warp_max_u64(v0);
+    if ((threadIdx.x & 31) == 0) { atomicMax(&vmax[0], vm); atomicMax(&vmax[1], v0); }
+}
+
+__device__ __forceinline__ double adaptive_timestep(const unsigned long long *vmax, double dt_min, double dt_max) {
+    double v_max = from_ordered_bits(vmax[0]);
+    double v0_max = vmax[1] == 0xffffffffffffffffULL ? nan("") : from_ordered_bits(vmax[1]);
+    if (v_max == 0.0) return dt_max;
+    double dx_max = 1.1 * v0_max * dt_max;
+    double dt = dx_max / v_max;
+    if (dt > dt_max) return dt_max;
+    else if (dt < dt_min) return dt_min;
+    else return dt;
+}
+
+__device__ __forceinline__ void verlet(double f, double f_prev, double inv_mass_num, double dt, double &v, double &x) {
+    // translational_verlet / rotational_verlet: a = f / m (division kept as in the reference)
+    double old_acc = f_prev / inv_mass_num;
+    double new_acc = f / inv_mass_num;
+    v += (old_acc + new_acc) / 2 * dt;
+    x += v * dt + new_acc / 2 * (dt * dt);
+}
+
+__global__ void k_integrate(Soa s, int n, int model, double dt_min, double dt_max, const unsigned long long *vmax, double *dt_out) {
+    const double dt = adaptive_timestep(vmax, dt_min, dt_max);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) { dt_out[0] = dt; dt_out[1] += dt; }
+    if (i >= n) return;
+    const double m = s(MASS, i);
+    double fx = s(FX, i), fy = s(FY, i);
+    double vx = s(VX, i), vy = s(VY, i), px = s(PX, i), py = s(PY, i);
+    verlet(fx, s(FPX, i), m, dt, vx, px);
+    verlet(fy, s(FPY, i), m, dt, vy, py);
+    s(FPX, i) = fx; s(FPY, i) = fy;
+    s(VX, i) = vx; s(VY, i) = vy; s(PX, i) = px; s(PY, i) = py;
+    if (model == CDB_MODEL_THREE_CIRCLE) {
+        double tq = s(TORQUE, i), w = s(OMEGA, i), phi = s(PHI, i);
+        verlet(tq, s(TORQUE_PREV, i), s(INERTIA, i), dt, w, phi);
+        phi = wrap_to_pi(phi);
+        s(TORQUE_PREV, i) = tq; s(OMEGA, i) = w; s(PHI, i) = phi;
+        double r_ts = s(R_TS, i);
+        double ox = sin(phi) * r_ts, oy = -cos(phi) * r_ts;   // rotate270(unit_vector(phi)) * r_ts
+        s(LSX, i) = px - ox; s(LSY, i) = py - oy;
+        s(RSX, i) = px + ox; s(RSY, i) = py + oy;
+    }
+}
+
+// =====================================================================================================================
+// agent-agent, v1: one thread per (cell-sorted) agent, full 3x3 stencil, immediate evaluation
+// =====================================================================================================================
+__global__ void __launch_bounds__(128)
+k_agent_agent_circular_v1(Soa s, int n, const Grid *grid, const int *__restrict__ cell_sorted, const int *__restrict__ cell_start,
+                          const int *__restrict__ cell_count) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const Grid g = *grid;
+    const int c = cell_sorted[t];
+    const long long cx = c / g.ny, cy = c % g.ny;
+    CircMe me = {s(PX, t), s(PY, t), s(VX, t), s(VY, t), s(RADIUS, t), s(MASS, t), s(K_SOC, t), s(TAU_0, t), s(MU, t), s(KAPPA, t), s(DAMPING, t)};
+    double fx = 0.0, fy = 0.0;
+    for (long long x2 = cx - 1; x2 <= cx + 1; ++x2) {
+        if (x2 < 0 || x2 >= g.nx) continue;
+        const long long ylo = cy > 0 ? cy - 1 : 0, yhi = cy + 1 < g.ny ? cy + 1 : g.ny - 1;
+        const int b = cell_start[x2 * g.ny + ylo];
+        const int e = cell_start[x2 * g.ny + yhi] + cell_count[x2 * g.ny + yhi];
+        for (int u = b; u < e; ++u) {
+            if (u == t) continue;
+            pair_circular(me, s(PX, u), s(PY, u), s(VX, u), s(VY, u), s(RADIUS, u), fx, fy);
+        }
+    }
+    s(FX, t) += fx; s(FY, t) += fy;
+}
+
+__device__ __forceinline__ void load_three_kin(const Soa &s, int u, ThreeKin &k) {
+    k.x[0][0] = s(PX, u); k.x[0][1] = s(PY, u);
+    k.x[1][0] = s(LSX, u); k.x[1][1] = s(LSY, u);
+    k.x[2][0] = s(RSX, u); k.x[2][1] = s(RSY, u);
+    k.r[0] = s(R_T, u); k.r[1] = s(R_S, u); k.r[2] = k.r[1];
+    k.vx = s(VX, u); k.vy = s(VY, u); k.phi = s(PHI, u); k.r_ts = s(R_TS, u);
+}
+
+__global__ void __launch_bounds__(128)
+k_agent_agent_three_circle_v1(Soa s, int n, const Grid *grid, const int *__restrict__ cell_sorted, const int *__restrict__ cell_start,
+                              const int *__restrict__ cell_count) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const Grid g = *grid;
+    const int c = cell_sorted[t];
+    const long long cx = c / g.ny, cy = c % g.ny;
+    ThreeKin me;
+    load_three_kin(s, t, me);
+    const ThreePar par = {s(MASS, t), s(K_SOC, t), s(TAU_0, t), s(MU, t), s(KAPPA, t), s(DAMPING, t)};
+    const int my_id = s.id[t];
+    double fx = 0.0, fy = 0.0, tq = 0.0;
+    for (long long x2 = cx - 1; x2 <= cx + 1; ++x2) {
+        if (x2 < 0 || x2 >= g.nx) continue;
+        const long long ylo = cy > 0 ? cy - 1 : 0, yhi = cy + 1 < g.ny ? cy + 1 : g.ny - 1;
+        const int b = cell_start[x2 * g.ny + ylo];
+        const int e = cell_start[x2 * g.ny + yhi] + cell_count[x2 * g.ny + yhi];
+        for (int u = b; u < e; ++u) {
+            if (u == t) continue;
+            ThreeKin other;
+            load_three_kin(s, u, other);
+            // reference pair orientation: i = lexicographically smaller (cell_x, cell_y, agent index)
+            const int oc = cell_sorted[u];
+            const bool me_is_i = c < oc || (c == oc && my_id < s.id[u]);
+            if (me_is_i) pair_three_circle(me, other, true, par, fx, fy, tq);
+            else pair_three_circle(other, me, false, par, fx, fy, tq);
+        }
+    }
+    s(FX, t) += fx; s(FY, t) += fy; s(TORQUE, t) += tq;
+}

@@ -1,0 +1,183 @@
+"""Device-resident mirror of ``simulation.agents.array`` (host side of the C ABI).
+
+``DeviceAgents`` owns one ``cdb_sim`` handle.  Two operating modes:
+
+* strict   -- every node: upload the host array, run the kernel(s), download the fields the node writes.  Used by the
+              functional API (``crowddynamics_b200.core.*``) and by logic nodes living in a tree with host-side nodes.
+* resident -- state stays on the device between nodes / steps; the host array is refreshed on demand (``sync_host``).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .structures import model_of, as_obstacles, MODEL_CIRCULAR
+from .exceptions import InvalidType, InvalidValue
+
+
+def _ptr(a):
+    return C.c_void_p(a.ctypes.data)
+
+
+def _check_agents(agents):
+    model = model_of(agents)
+    if agents.ndim != 1 or not agents.flags.c_contiguous:
+        raise InvalidValue('agents must be a 1-D C-contiguous structured array (reference agents.py:680)')
+    return model
+
+
+class DeviceAgents:
+    def __init__(self, model, capacity=0, device=0, stream=None):
+        self.lib = _lib.load()
+        self.model = int(model)
+        self.device = int(device)
+        self.itemsize = 228 if self.model == MODEL_CIRCULAR else 316
+        h = C.c_void_p()
+        _lib.check(self.lib.cdb_create(self.device, self.model, int(capacity), C.byref(h)))
+        self.handle = h
+        self.n = 0
+        if stream is not None:
+            self.set_stream(stream)
+
+    # -- lifetime -------------------------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, 'handle', None):
+            self.lib.cdb_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, stream):
+        """stream: raw cudaStream_t as int (``torch.cuda.current_stream().cuda_stream``)."""
+        _lib.check(self.lib.cdb_set_stream(self.handle, C.c_void_p(int(stream))))
+
+    def synchronize(self):
+        _lib.check(self.lib.cdb_synchronize(self.handle))
+
+    # -- data ------------------------------------------------------------------------------------------------------
+    def upload(self, agents):
+        if _check_agents(agents) != self.model:
+            raise InvalidType('agents dtype does not match the device model')
+        _lib.check(self.lib.cdb_upload_agents_aos(self.handle, _ptr(agents), len(agents), agents.dtype.itemsize))
+        self.n = len(agents)
+
+    def upload_raw(self, ptr, n):
+        """Upload from a raw host pointer (e.g. a pinned torch tensor holding packed records)."""
+        _lib.check(self.lib.cdb_upload_agents_aos(self.handle, C.c_void_p(int(ptr)), int(n), self.itemsize))
+        self.n = int(n)
+
+    def download(self, agents, mask=_lib.F_ALL_MUTABLE):
+        if _check_agents(agents) != self.model:
+            raise InvalidType('agents dtype does not match the device model')
+        _lib.check(self.lib.cdb_download_agents_aos(self.handle, _ptr(agents), len(agents), agents.dtype.itemsize, mask))
+
+    def download_raw(self, ptr, n, mask=_lib.F_WHOLE_RECORD):
+        _lib.check(self.lib.cdb_download_agents_aos(self.handle, C.c_void_p(int(ptr)), int(n), self.itemsize, mask))
+
+    def set_obstacles(self, obstacles):
+        seg = as_obstacles(obstacles)
+        _lib.check(self.lib.cdb_set_obstacles(self.handle, _ptr(seg) if len(seg) else None, len(seg)))
+
+    def set_navigation_field(self, target, mgrid, direction_map):
+        """(mgrid, (U, V)) as returned by Field.navigation_to_target (reference field.py:155-164)."""
+        U = np.ascontiguousarray(np.asarray(direction_map[0]), dtype=np.float64)
+        V = np.ascontiguousarray(np.asarray(direction_map[1]), dtype=np.float64)
+        if U.shape != V.shape or U.ndim != 2:
+            raise InvalidValue('direction map must be two (ny, nx) arrays')
+        minx, miny = mgrid.bounds[0], mgrid.bounds[1]
+        _lib.check(self.lib.cdb_set_navigation_field(self.handle, int(target), _ptr(U), _ptr(V), U.shape[0], U.shape[1],
+                                                     float(minx), float(miny), float(mgrid.step)))
+
+    def clear_navigation(self):
+        _lib.check(self.lib.cdb_clear_navigation(self.handle))
+
+    # -- nodes -----------------------------------------------------------------------------------------------------
+    def reset(self):
+        _lib.check(self.lib.cdb_reset(self.handle))
+
+    def navigation(self):
+        _lib.check(self.lib.cdb_navigation(self.handle))
+
+    def orientation(self):
+        _lib.check(self.lib.cdb_orientation(self.handle))
+
+    def adjust(self):
+        _lib.check(self.lib.cdb_adjust(self.handle))
+
+    def agent_agent(self, cell_size):
+        _lib.check(self.lib.cdb_agent_agent(self.handle, float(cell_size)))
+
+    def agent_obstacle(self):
+        _lib.check(self.lib.cdb_agent_obstacle(self.handle))
+
+    def integrate(self, dt_min, dt_max):
+        dt = C.c_double()
+        _lib.check(self.lib.cdb_integrate(self.handle, float(dt_min), float(dt_max), C.byref(dt)))
+        return dt.value
+
+    def step(self, n_steps=1, flags=_lib.STEP_ALL, cell_size=3.6, dt_min=0.01, dt_max=0.01, want_dt=True):
+        """n_steps fused iterations of the selected nodes on the device; returns the dt of every step (or None)."""
+        dts = np.zeros(int(n_steps), dtype=np.float64) if want_dt else None
+        _lib.check(self.lib.cdb_step(self.handle, int(flags), float(cell_size), float(dt_min), float(dt_max),
+                                     int(n_steps), _ptr(dts) if want_dt and n_steps else None))
+        return dts
+
+    def time(self):
+        t, it = C.c_double(), C.c_int64()
+        _lib.check(self.lib.cdb_get_time(self.handle, C.byref(t), C.byref(it)))
+        return t.value, it.value
+
+    # -- block list exports ------------------------------------------------------------------------------------------
+    def build_block_list(self, cell_size):
+        _lib.check(self.lib.cdb_build_block_list(self.handle, float(cell_size)))
+
+    def grid(self):
+        g = (C.c_int64 * 4)()
+        _lib.check(self.lib.cdb_get_grid(self.handle, g))
+        return tuple(int(x) for x in g)
+
+    def cell_ids(self):
+        out = np.empty(self.n, dtype=np.int64)
+        _lib.check(self.lib.cdb_get_cell_ids(self.handle, _ptr(out), self.n))
+        return out
+
+    def cell_tables(self):
+        """-> (points_indices, cells_count, cells_offset, grid_shape) like cell_lists.add_to_cells."""
+        g = self.grid()
+        nc = g[2] * g[3]
+        pi = np.empty(self.n, dtype=np.int64)
+        cc = np.empty(nc, dtype=np.int64)
+        co = np.empty(nc, dtype=np.int64)
+        _lib.check(self.lib.cdb_get_cell_tables(self.handle, _ptr(pi), self.n, _ptr(cc), _ptr(co), nc))
+        return pi, cc, co, np.array(g[2:], dtype=np.int64)
+
+    def neighbor_pairs(self):
+        cnt = C.c_int64()
+        _lib.check(self.lib.cdb_get_neighbor_pairs(self.handle, None, 0, C.byref(cnt)))
+        out = np.empty((cnt.value, 2), dtype=np.int64)
+        if cnt.value:
+            _lib.check(self.lib.cdb_get_neighbor_pairs(self.handle, _ptr(out), cnt.value, C.byref(cnt)))
+        return out
+
+    def set_lattice(self, ix_min, iy_min, nx, ny):
+        _lib.check(self.lib.cdb_set_lattice(self.handle, int(ix_min), int(iy_min), int(nx), int(ny)))
+
+    def clear_lattice(self):
+        _lib.check(self.lib.cdb_clear_lattice(self.handle))
+
+
+_CACHE = {}
+
+
+def device_agents_for(agents, device=0):
+    """Cached DeviceAgents for (device, model) -- used by the strict functional API."""
+    model = _check_agents(agents)
+    key = (device, model)
+    da = _CACHE.get(key)
+    if da is None:
+        da = _CACHE[key] = DeviceAgents(model, capacity=len(agents), device=device)
+    return da

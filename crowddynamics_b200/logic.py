@@ -1,0 +1,384 @@
+"""Drop-in logic nodes for the replaced sub-tree of ``MultiAgentSimulation`` (reference simulation/logic.py).
+
+Same class names, constructor ``Node(simulation, **params)``, ``update()`` without arguments, composition with ``<<``
+and lookup ``tree['Name']`` as the reference (simulation/base.py:27-84, logic.py:31-54).  The reference's base classes
+need traitlets + anytree, which are not installed in the build image; when they are importable (a real crowddynamics
+install) our nodes subclass the reference ``LogicNode`` so they can be mixed with its other nodes, otherwise a small
+duck-typed tree (``LogicNodeBase`` below) provides the same surface.
+
+State handling: all nodes of one simulation share a ``DeviceState`` that mirrors
+``simulation.agents.array`` on the GPU.
+
+* ``mode='strict'``   -- each ``update()`` uploads the host array, runs its kernel(s) and downloads the fields the
+  node writes: bit-for-bit the reference's contract (the host array is always coherent; host-side nodes such as
+  ``Fluctuation`` / ``InsideDomain`` / ``SaveSimulationData`` can sit anywhere in the tree).
+* ``mode='resident'`` -- the array is uploaded once; nodes only launch kernels; ``DeviceState.sync_host()`` refreshes
+  the host array on demand (call it before any host-side node reads agents).  ``FusedStep`` runs the whole replaced
+  sub-tree for many iterations in one C-ABI call.
+"""
+import numpy as np
+
+from . import _lib
+from .engine import DeviceAgents
+from .structures import is_model, model_of, as_obstacles, MODEL_THREE_CIRCLE
+
+try:  # pragma: no cover - reference package not installable here
+    from crowddynamics.simulation.logic import LogicNode as _RefLogicNode
+    from crowddynamics.core.geometry import geom_to_linear_obstacles as _geom_to_linear_obstacles
+    _HAVE_REFERENCE = True
+except Exception:  # noqa
+    _RefLogicNode = None
+    _geom_to_linear_obstacles = None
+    _HAVE_REFERENCE = False
+
+
+class LogicNodeBase:
+    """Minimal stand-in for reference simulation/base.py:27-84 (anytree NodeMixin + traitlets ``name``)."""
+
+    def __init__(self, *args, **kwargs):
+        self.name = kwargs.pop('name', self.__class__.__name__)
+        self._parent = None
+        self.children = ()
+
+    # -- tree ------------------------------------------------------------------------------------------------------
+    @property
+    def parent(self):
+        return self._parent
+
+    @parent.setter
+    def parent(self, node):
+        if self._parent is not None:
+            self._parent.children = tuple(c for c in self._parent.children if c is not self)
+        self._parent = node
+        if node is not None:
+            node.children = node.children + (self,)
+
+    @property
+    def root(self):
+        node = self
+        while node._parent is not None:
+            node = node._parent
+        return node
+
+    def inject_before(self, node):
+        parent = self.parent
+        self.parent = node
+        node.parent = parent
+
+    def inject_after(self, node):
+        for child in self.children:
+            child.parent = node
+        node.parent = self
+
+    def add_children(self, node):
+        node.parent = self
+        return self
+
+    def __lshift__(self, other):
+        if isinstance(other, LogicNodeBase) or hasattr(other, 'update'):
+            self.add_children(other)
+        else:
+            for _other in other:
+                self.add_children(_other)
+        return self
+
+    def __repr__(self):
+        return self.name
+
+    def __getitem__(self, item):
+        for node in pre_order_iter(self.root):
+            if node.name == item:
+                return node
+        raise KeyError('Key: "{}" not in the tree.'.format(item))
+
+    def update(self):
+        raise NotImplementedError
+
+
+def pre_order_iter(node):
+    yield node
+    for c in node.children:
+        yield from pre_order_iter(c)
+
+
+def post_order_iter(node):
+    for c in node.children:
+        yield from post_order_iter(c)
+    yield node
+
+
+class _Params:
+    """Poor man's traits: class-level defaults overridable by constructor keywords (reference nodes use traitlets)."""
+    _params = {}
+
+    def _init_params(self, kwargs):
+        for key, default in self._params.items():
+            setattr(self, key, kwargs.pop(key, default))
+
+
+class DeviceState:
+    """GPU mirror of ``simulation.agents.array`` shared by all nodes of one simulation."""
+
+    def __init__(self, simulation, mode='strict', device=0):
+        assert mode in ('strict', 'resident')
+        self.simulation = simulation
+        self.mode = mode
+        self.device = device
+        self.dev = None
+        self._host_id = None
+        self._obstacles_key = None
+        self._nav_key = None
+        self.dirty_host = False     # device is ahead of the host array (resident mode)
+
+    @classmethod
+    def of(cls, simulation, mode=None, device=0):
+        st = getattr(simulation, '_b200_state', None)
+        if st is None:
+            st = cls(simulation, mode or 'strict', device)
+            try:
+                simulation._b200_state = st
+            except Exception:  # traitlets HasTraits accept new attributes; be defensive anyway
+                object.__setattr__(simulation, '_b200_state', st)
+        elif mode is not None and mode != st.mode:
+            st.sync_host()
+            st.mode = mode
+        return st
+
+    @property
+    def agents(self):
+        return self.simulation.agents.array
+
+    def _ensure(self):
+        agents = self.agents
+        model = model_of(agents)      # raises InvalidType for an unknown dtype, like interactions.py:204-205
+        if self.dev is None or self.dev.model != model:
+            self.dev = DeviceAgents(model, capacity=len(agents), device=self.device)
+            self._host_id = None
+        return agents
+
+    def begin(self):
+        """Make the device state current before a node runs."""
+        agents = self._ensure()
+        if self.mode == 'strict' or self._host_id != (id(agents), len(agents)):
+            self.dev.upload(agents)
+            self._host_id = (id(agents), len(agents))
+            self.dirty_host = False
+        return self.dev
+
+    def end(self, mask):
+        """Publish what a node wrote."""
+        if self.mode == 'strict':
+            self.dev.download(self.agents, mask)
+        else:
+            self.dirty_host = True
+
+    def sync_host(self, mask=_lib.F_ALL_MUTABLE):
+        """Resident mode: refresh the host array from the device (before host-side nodes / IO read it)."""
+        if self.dev is not None and self.dirty_host:
+            self.dev.download(self.agents, mask)
+            self.dirty_host = False
+
+    def invalidate(self):
+        """Resident mode: the host array was modified by a host-side node; re-upload at the next node."""
+        self.sync_host()
+        self._host_id = None
+
+    # -- geometry / fields -------------------------------------------------------------------------------------------
+    def ensure_obstacles(self):
+        field = getattr(self.simulation, 'field', None)
+        obstacles = getattr(field, 'obstacles', None) if field is not None else None
+        if obstacles is None:
+            seg = np.zeros((0, 4))
+        elif isinstance(obstacles, np.ndarray):
+            seg = as_obstacles(obstacles)
+        elif _geom_to_linear_obstacles is not None:      # shapely geometry, as logic.py:126-129
+            seg = as_obstacles(_geom_to_linear_obstacles(obstacles))
+        else:
+            raise TypeError('field.obstacles must be an obstacle_type_linear array (shapely is not available)')
+        key = seg.tobytes()
+        if key != self._obstacles_key:
+            self.dev.set_obstacles(seg)
+            self._obstacles_key = key
+
+    def ensure_navigation(self, step, radius, strength):
+        field = self.simulation.field
+        n_targets = len(field.targets)
+        key = (id(field), n_targets, step, radius, strength)
+        if key != self._nav_key:
+            self.dev.clear_navigation()
+            for target in range(n_targets):
+                mgrid, distance_map, direction_map = field.navigation_to_target(target, step, radius, strength)
+                self.dev.set_navigation_field(target, mgrid, direction_map)
+            self._nav_key = key
+
+
+_Base = _RefLogicNode if _HAVE_REFERENCE else LogicNodeBase
+
+
+class LogicNode(_Base, _Params):
+    """Base of the GPU nodes: ``Node(simulation, mode='strict'|'resident', device=0, **params)``."""
+
+    def __init__(self, simulation, *args, **kwargs):
+        mode = kwargs.pop('mode', None)
+        device = kwargs.pop('device', 0)
+        self._init_params(kwargs)
+        if _HAVE_REFERENCE:
+            super().__init__(simulation, *args, **kwargs)
+        else:
+            super().__init__(*args, **kwargs)
+            self.simulation = simulation
+        self.state = DeviceState.of(simulation, mode, device)
+
+    def update(self):
+        raise NotImplementedError
+
+
+class Reset(LogicNode):
+    """logic.py:59-64"""
+
+    def update(self):
+        dev = self.state.begin()
+        dev.reset()
+        self.state.end(_lib.F_FORCE | _lib.F_TORQUE)
+
+
+class Integrator(LogicNode):
+    """logic.py:67-75"""
+    _params = dict(dt_min=0.01, dt_max=0.01)
+
+    def update(self):
+        dev = self.state.begin()
+        dt = dev.integrate(self.dt_min, self.dt_max)
+        self.state.end(_lib.F_POSITION | _lib.F_VELOCITY | _lib.F_FORCE_PREV | _lib.F_SHOULDERS | _lib.F_ORIENTATION |
+                       _lib.F_ANGULAR_VELOCITY | _lib.F_TORQUE_PREV)
+        self.simulation.data['dt'] = dt
+        self.simulation.data['time_tot'] += dt
+
+
+class Adjusting(LogicNode):
+    """logic.py:89-94"""
+
+    def update(self):
+        dev = self.state.begin()
+        dev.adjust()
+        self.state.end(_lib.F_FORCE | _lib.F_TORQUE)
+
+
+class AgentAgentInteractions(LogicNode):
+    """logic.py:97-119.  As in the reference, ``sight_soc`` / ``f_soc_max`` only size the cells; the kernels use the
+    module constants SIGTH_SOC = 3.0 (interactions.py:45) and F_SOC_MAX = 2e3 (power_law.py:52)."""
+    _params = dict(sight_soc=3.0, max_agent_radius=0.3, f_soc_max=2e3, cell_size=None)
+
+    def __init__(self, simulation, *args, **kwargs):
+        super().__init__(simulation, *args, **kwargs)
+        if self.cell_size is None:
+            self.cell_size = self.sight_soc + 2 * self.max_agent_radius
+
+    def update(self):
+        dev = self.state.begin()
+        dev.agent_agent(self.cell_size)
+        self.state.end(_lib.F_FORCE | _lib.F_TORQUE)
+
+
+class AgentObstacleInteractions(LogicNode):
+    """logic.py:122-130"""
+
+    def update(self):
+        dev = self.state.begin()
+        self.state.ensure_obstacles()
+        dev.agent_obstacle()
+        self.state.end(_lib.F_FORCE | _lib.F_TORQUE)
+
+
+class Navigation(LogicNode):
+    """logic.py:135-165 (sampling of the static direction field; the field itself is built by the host ``Field``)."""
+    _params = dict(step=0.1, radius=0.5, strength=0.3)
+
+    def update(self):
+        dev = self.state.begin()
+        self.state.ensure_navigation(self.step, self.radius, self.strength)
+        dev.navigation()
+        self.state.end(_lib.F_TARGET_DIRECTION)
+
+
+class Orientation(LogicNode):
+    """logic.py:258-261"""
+
+    def update(self):
+        if is_model(self.simulation.agents.array, 'three_circle'):
+            dev = self.state.begin()
+            dev.orientation()
+            self.state.end(_lib.F_TARGET_ORIENTATION)
+
+
+class FusedStep(LogicNode):
+    """The whole replaced sub-tree in one C-ABI call per ``update()``: navigation -> orientation -> adjusting ->
+    agent-agent -> agent-obstacle -> integrator -> reset (post-order of examples/simulations.py:123-136), resident on
+    the device.  ``steps_per_update`` > 1 advances several iterations per call."""
+    _params = dict(dt_min=0.01, dt_max=0.01, cell_size=3.6, step=0.1, radius=0.5, strength=0.3, steps_per_update=1,
+                   navigation=True, sync_every_update=False)
+
+    def __init__(self, simulation, *args, **kwargs):
+        kwargs.setdefault('mode', 'resident')
+        super().__init__(simulation, *args, **kwargs)
+
+    def update(self):
+        dev = self.state.begin()
+        self.state.ensure_obstacles()
+        flags = _lib.STEP_ALL
+        field = getattr(self.simulation, 'field', None)
+        if self.navigation and field is not None and getattr(field, 'targets', None) is not None and len(field.targets):
+            self.state.ensure_navigation(self.step, self.radius, self.strength)
+        else:
+            flags &= ~_lib.STEP_NAVIGATION
+        dts = dev.step(self.steps_per_update, flags, self.cell_size, self.dt_min, self.dt_max)
+        self.state.dirty_host = True
+        if len(dts):
+            self.simulation.data['dt'] = float(dts[-1])
+            self.simulation.data['time_tot'] += float(dts.sum())
+        if self.sync_every_update or self.state.mode == 'strict':
+            self.state.sync_host()
+
+
+class MultiAgentSimulation:
+    """Minimal host with the surface the nodes use (reference simulation/multiagent.py:23-55): ``agents.array``,
+    ``field`` (``obstacles``, ``targets``, ``navigation_to_target``), ``logic``, ``data`` and ``update()`` =
+    post-order traversal of the logic tree."""
+
+    class _Agents:
+        def __init__(self, array):
+            self.array = array
+
+    class ArrayField:
+        """Field given directly as arrays: obstacle segments + per-target (mgrid, (U, V))."""
+
+        def __init__(self, obstacles=None, fields=()):
+            self.obstacles = obstacles
+            self.targets = list(range(len(fields)))
+            self._fields = list(fields)
+
+        def navigation_to_target(self, target, step, radius, strength):
+            mgrid, direction_map = self._fields[target]
+            return mgrid, None, direction_map
+
+    def __init__(self, agents, obstacles=None, fields=(), logic=None):
+        self.agents = self._Agents(agents)
+        self.field = self.ArrayField(obstacles, fields)
+        self.logic = logic
+        self.data = {'iterations': 0, 'time_tot': 0.0, 'dt': 0.0}
+
+    def update(self):
+        for node in post_order_iter(self.logic.root):
+            node.update()
+        self.data['iterations'] += 1
+
+
+def hallway_logic(simulation, mode='strict', dt_min=0.01, dt_max=0.01, cell_size=None):
+    """The replaced part of the Hallway / RoomWithOneExit logic tree (examples/simulations.py:123-136), without the
+    host-side Fluctuation / InsideDomain nodes."""
+    aa = dict(cell_size=cell_size) if cell_size else {}
+    return Reset(simulation, mode=mode) << (
+        Integrator(simulation, dt_min=dt_min, dt_max=dt_max) << (
+            Adjusting(simulation) << (Navigation(simulation), Orientation(simulation)),
+            AgentAgentInteractions(simulation, **aa),
+            AgentObstacleInteractions(simulation)))

@@ -1,0 +1,156 @@
+/* crowd_b200.h -- C ABI of the B200-native crowddynamics agent update (libcrowd_b200.so).
+ *
+ * This is the drop-in boundary for the reference's per-timestep hot path.  Every entry point replaces one
+ * reference interface (cited as file:line under /root/reference/crowddynamics/); the Python logic nodes in
+ * crowddynamics_b200/logic.py bind them with ctypes exactly as INTEGRATION.md shows for the reference's own
+ * simulation/logic.py.  Plain pointers and sizes only: no torch, numpy or C++ types cross this boundary.
+ *
+ * Conventions
+ *   - every function returns a cdb_status (0 = ok); cdb_last_error() gives the message of the last failure on the
+ *     calling thread.  The Python side maps CDB_ERR_INVALID_TYPE -> InvalidType, everything else ->
+ *     CrowdDynamicsException subclasses (reference exceptions.py:10-22; interactions.py:204-205,213-214).
+ *   - agent records are the reference's packed structured dtypes: itemsize 228 (agent_type_circular) or 316
+ *     (agent_type_three_circle), simulation/agents.py:447-457.  Any other itemsize is CDB_ERR_INVALID_TYPE.
+ *   - all arithmetic is IEEE fp64 on the GPU; there is no CPU fallback anywhere behind this header.
+ *   - a cdb_sim is bound to one CUDA device and used from one host thread at a time (the reference is single
+ *     threaded, simulation/multiagent.py:51-55); the CUDA context is created lazily by cdb_create in the calling
+ *     process, so a forked MultiAgentProcess (multiagent.py:58-100) must create its own sim.
+ */
+#ifndef CROWD_B200_H
+#define CROWD_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct cdb_sim cdb_sim;
+
+typedef enum {
+    CDB_OK = 0,
+    CDB_ERR_INVALID_TYPE = 1,  /* unknown agent dtype / itemsize                 -> InvalidType */
+    CDB_ERR_INVALID_VALUE = 2, /* bad argument, non-finite positions, ...        -> InvalidValue */
+    CDB_ERR_CUDA = 3,          /* CUDA runtime error                             -> DeviceError */
+    CDB_ERR_CAPACITY = 4,      /* more agents / cells / halo entries than allocated */
+    CDB_ERR_STATE = 5          /* call order (e.g. tables requested before a block list was built) */
+} cdb_status;
+
+enum { CDB_MODEL_CIRCULAR = 0, CDB_MODEL_THREE_CIRCLE = 1 };
+
+/* Field mask bits for cdb_download_agents_aos: which record fields are written back to the host array. */
+enum {
+    CDB_F_POSITION = 1u << 0,
+    CDB_F_VELOCITY = 1u << 1,
+    CDB_F_TARGET_DIRECTION = 1u << 2,
+    CDB_F_FORCE = 1u << 3,
+    CDB_F_FORCE_PREV = 1u << 4,
+    CDB_F_SHOULDERS = 1u << 5,          /* position_ls, position_rs */
+    CDB_F_ORIENTATION = 1u << 6,
+    CDB_F_ANGULAR_VELOCITY = 1u << 7,
+    CDB_F_TARGET_ORIENTATION = 1u << 8,
+    CDB_F_TORQUE = 1u << 9,
+    CDB_F_TORQUE_PREV = 1u << 10,
+    CDB_F_ALL_MUTABLE = (1u << 11) - 1,
+    CDB_F_WHOLE_RECORD = 1u << 31       /* copy the full records (valid when the host did not touch the array since upload) */
+};
+
+/* Node selection bits for cdb_step -- one bit per replaced LogicNode, executed in the reference's post-order
+ * (examples/simulations.py:123-136): navigation, orientation, adjusting, agent-agent, agent-obstacle, integrator, reset. */
+enum {
+    CDB_STEP_NAVIGATION = 1u << 0,
+    CDB_STEP_ORIENTATION = 1u << 1,
+    CDB_STEP_ADJUSTING = 1u << 2,
+    CDB_STEP_AGENT_AGENT = 1u << 3,
+    CDB_STEP_AGENT_OBSTACLE = 1u << 4,
+    CDB_STEP_INTEGRATOR = 1u << 5,
+    CDB_STEP_RESET = 1u << 6,
+    CDB_STEP_ALL = (1u << 7) - 1
+};
+
+/* ---- library ---------------------------------------------------------------------------------------------------- */
+const char *cdb_last_error(void);
+int cdb_version(void);
+int cdb_device_count(int *count);
+
+/* ---- lifetime ---------------------------------------------------------------------------------------------------
+ * Replaces: nothing in the reference (its state is the host array simulation.agents.array, agents.py:605-680);
+ * the sim object is the device-resident mirror of that array in SoA layout. */
+int cdb_create(int device, int model, int64_t capacity, cdb_sim **out);
+int cdb_destroy(cdb_sim *sim);
+/* Run all work of this sim on an existing CUDA stream (cudaStream_t, e.g. torch.cuda.current_stream().cuda_stream). */
+int cdb_set_stream(cdb_sim *sim, void *cuda_stream);
+int cdb_synchronize(cdb_sim *sim);
+int64_t cdb_num_agents(const cdb_sim *sim);
+
+/* ---- host <-> device of the reference data contract ---------------------------------------------------------------
+ * agents: packed records exactly as simulation.agents.array (C-contiguous, asserted at agents.py:680).
+ * upload converts AoS -> device SoA; download writes the fields selected by field_mask back into the host records
+ * (in the original agent order, whatever the device-side cell ordering is). */
+int cdb_upload_agents_aos(cdb_sim *sim, const void *agents, int64_t n, int64_t itemsize);
+int cdb_download_agents_aos(cdb_sim *sim, void *agents, int64_t n, int64_t itemsize, uint32_t field_mask);
+
+/* obstacles: (W, 4) doubles p0x,p0y,p1x,p1y == obstacle_type_linear (core/structures.py:6-9), the output format of
+ * geom_to_linear_obstacles (core/geometry.py:99-102) that AgentObstacleInteractions.update builds (logic.py:122-130). */
+int cdb_set_obstacles(cdb_sim *sim, const double *segments, int64_t n_segments);
+
+/* Navigation field of one target: U, V of shape (ny, nx) indexed [iy, ix], origin (minx, miny), grid step -- the
+ * (mgrid, direction_map) pair returned by Field.navigation_to_target (simulation/field.py:155-164). */
+int cdb_set_navigation_field(cdb_sim *sim, int64_t target, const double *U, const double *V, int64_t ny, int64_t nx,
+                             double minx, double miny, double step);
+int cdb_clear_navigation(cdb_sim *sim);
+
+/* ---- per-node entry points (one per replaced LogicNode.update) ------------------------------------------------------ */
+int cdb_reset(cdb_sim *sim);                 /* Reset.update, logic.py:59-64 */
+int cdb_navigation(cdb_sim *sim);            /* Navigation.update sampling, logic.py:149-165 + navigation.py:60-78 + quickest_path.py:41-44 */
+int cdb_orientation(cdb_sim *sim);           /* Orientation.update, logic.py:258-261 + steering/orientation.py:17-21 */
+int cdb_adjust(cdb_sim *sim);                /* Adjusting.update, logic.py:89-94 + motion/adjusting.py:101-121 */
+int cdb_agent_agent(cdb_sim *sim, double cell_size);   /* AgentAgentInteractions.update, logic.py:118-119 -> core/interactions.py:191-205 */
+int cdb_agent_obstacle(cdb_sim *sim);        /* AgentObstacleInteractions.update, logic.py:122-130 -> core/interactions.py:208-214 */
+int cdb_integrate(cdb_sim *sim, double dt_min, double dt_max, double *dt_out);   /* Integrator.update, logic.py:71-75 -> core/integrator.py:209-256 */
+
+/* Fused resident step: n_steps iterations of the selected nodes without leaving the device (the body of
+ * MultiAgentSimulation.update, simulation/multiagent.py:51-55, restricted to the replaced sub-tree).
+ * dt_out (may be NULL) receives the n_steps time steps used; time_tot / iterations accumulate like simulation.data. */
+int cdb_step(cdb_sim *sim, uint32_t node_flags, double cell_size, double dt_min, double dt_max, int64_t n_steps,
+             double *dt_out);
+int cdb_get_time(cdb_sim *sim, double *time_tot, int64_t *iterations);
+
+/* ---- block list: debug / parity exports (cell_lists.add_to_cells & iter_nearest_neighbors, call sites
+ * core/interactions.py:191-205; spec core/block_list.py:28-52) ---------------------------------------------------- */
+int cdb_build_block_list(cdb_sim *sim, double cell_size);
+int cdb_get_grid(cdb_sim *sim, int64_t grid[4]);                       /* ix_min, iy_min, nx, ny */
+int cdb_get_cell_ids(cdb_sim *sim, int64_t *cell_of_agent, int64_t n); /* flat cell id per agent, original order */
+int cdb_get_cell_tables(cdb_sim *sim, int64_t *points_indices, int64_t n, int64_t *cells_count,
+                        int64_t *cells_offset, int64_t n_cells);
+/* Candidate pairs (same or adjacent cell), each unordered pair once as ordered (i, j) with i the agent that is
+ * lexicographically smaller in (cell_x, cell_y, agent_index); pairs[2*k], pairs[2*k+1]; *count may exceed cap. */
+int cdb_get_neighbor_pairs(cdb_sim *sim, int64_t *pairs, int64_t cap, int64_t *count);
+
+/* ---- fixed lattice + strip decomposition (multi-GPU; no reference counterpart) ------------- */
+/* Fix the cell lattice instead of deriving it from the bounding box every step (cells stay anchored at multiples of
+ * cell_size, so cell coordinates are identical; agents outside are binned into the border cells). */
+int cdb_set_lattice(cdb_sim *sim, int64_t ix_min, int64_t iy_min, int64_t nx, int64_t ny);
+int cdb_clear_lattice(cdb_sim *sim);
+/* Declare that this sim owns cell columns [ix_lo, ix_hi) of the lattice; columns ix_lo-1 and ix_hi hold ghosts. */
+int cdb_set_strip(cdb_sim *sim, int64_t ix_lo, int64_t ix_hi, int has_left, int has_right);
+/* Halo / migrant buffers are plain device memory owned by the caller (e.g. torch tensors given to NCCL send/recv). */
+int64_t cdb_halo_record_doubles(const cdb_sim *sim);
+int64_t cdb_migrant_record_doubles(const cdb_sim *sim);
+/* side: 0 = left neighbour, 1 = right.  Buffers start with a 4-double header (count, ...). */
+int cdb_halo_pack(cdb_sim *sim, int side, double *dev_buf, int64_t cap_records);
+int cdb_halo_unpack(cdb_sim *sim, int side, const double *dev_buf, int64_t cap_records);
+int cdb_migrants_pack(cdb_sim *sim, int side, double *dev_buf, int64_t cap_records);
+int cdb_migrants_unpack(cdb_sim *sim, int side, const double *dev_buf, int64_t cap_records);
+/* The strip step is split around the exchanges:  begin (sort, pack halos) | exchange | finish (forces, integrate,
+ * pack migrants) | exchange | absorb (append migrants).  v_max_inout / v0_max_inout are device doubles reduced by the
+ * caller across ranks (MAX) between begin and finish when dt_min != dt_max. */
+int cdb_strip_step_begin(cdb_sim *sim, uint32_t node_flags, double cell_size);
+double *cdb_strip_vmax_ptr(cdb_sim *sim);   /* device double[2]: max |v|, max target_velocity of owned agents */
+int cdb_strip_step_finish(cdb_sim *sim, uint32_t node_flags, double dt_min, double dt_max);
+int cdb_strip_absorb(cdb_sim *sim);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CROWD_B200_H */

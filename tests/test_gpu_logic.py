@@ -1,0 +1,67 @@
+"""The drop-in logic nodes (crowddynamics_b200.logic) driving a MultiAgentSimulation-like host, against the oracle."""
+import numpy as np
+import pytest
+
+from conftest import load_golden, rel_err_fields, vec_rel_err
+from crowddynamics_b200 import synthetic as S, logic as L
+from oracle import crowd_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize('model', ['circular', 'three_circle'])
+def test_strict_tree_matches_oracle_step_by_step(model):
+    agents, obstacles, fields = S.hallway(seed=1, model=model)
+    ref = agents.copy()
+    sim = L.MultiAgentSimulation(agents, obstacles, fields)
+    sim.logic = L.hallway_logic(sim, mode='strict', dt_min=0.001, dt_max=0.01)
+    assert [n.name for n in L.post_order_iter(sim.logic.root)] == [
+        'Navigation', 'Orientation', 'Adjusting', 'AgentAgentInteractions', 'AgentObstacleInteractions', 'Integrator',
+        'Reset']
+    assert sim.logic['Integrator'].dt_max == 0.01 and sim.logic['AgentAgentInteractions'].cell_size == 3.6
+    t = 0.0
+    for it in range(20):
+        sim.update()
+        t += O.step(ref, obstacles, fields, 3.6, 0.001, 0.01)
+        assert np.abs(agents['position'] - ref['position']).max() <= 1e-9
+    assert sim.data['iterations'] == 20
+    assert abs(sim.data['time_tot'] - t) <= 1e-12
+    assert (agents['force'] == 0).all()
+
+
+def test_hallway_reference_trajectory_resident():
+    """BASELINE config 1: 200 updates of the Hallway, fused + resident, against the reference's own trajectory."""
+    g = load_golden('hallway.npz')
+    agents, obstacles, fields = S.hallway(seed=0)
+    sim = L.MultiAgentSimulation(agents, obstacles, fields)
+    sim.logic = L.FusedStep(sim, dt_min=0.01, dt_max=0.01, steps_per_update=50)
+    traj = [agents['position'].copy()]
+    for _ in range(4):
+        sim.update()
+        sim.logic.state.sync_host()
+        traj.append(agents['position'].copy())
+    assert np.abs(np.stack(traj) - g['positions']).max() <= 1e-6
+    assert abs(sim.data['time_tot'] - 2.0) < 1e-9
+    # reference examples/tests/test_validation.py:13-38 flavour: the crowd actually walks
+    assert np.abs(agents['position'][:, 0] - traj[0][:, 0]).mean() > 1.0
+
+
+def test_resident_nodes_and_host_sync():
+    agents, obstacles, fields = S.hallway(seed=2, model='three_circle')
+    ref = agents.copy()
+    sim = L.MultiAgentSimulation(agents, obstacles, fields)
+    sim.logic = L.hallway_logic(sim, mode='resident')
+    for _ in range(10):
+        sim.update()
+        O.step(ref, obstacles, fields, 3.6, 0.01, 0.01)
+    assert (agents['position'] != ref['position']).any()      # host not refreshed yet
+    sim.logic.state.sync_host()
+    assert np.abs(agents['position'] - ref['position']).max() <= 1e-9
+    assert np.abs(agents['orientation'] - ref['orientation']).max() <= 1e-8
+    # a host-side node edits the array -> invalidate -> next node re-uploads
+    agents['velocity'] = 0.0
+    ref['velocity'] = 0.0
+    sim.logic.state.invalidate()
+    sim.update(); O.step(ref, obstacles, fields, 3.6, 0.01, 0.01)
+    sim.logic.state.sync_host()
+    assert np.abs(agents['position'] - ref['position']).max() <= 1e-9
