@@ -1,0 +1,319 @@
+#!/usr/bin/env python
+"""bench.py -- agent-steps/sec of the replaced crowddynamics sub-tree on B200 (BASELINE.json metric).
+
+One "step" = one MultiAgentSimulation.update() of the replaced nodes over the whole crowd:
+navigation sample -> orientation -> adjusting -> block list + agent-agent -> agent-obstacle -> adaptive-dt
+velocity Verlet -> reset.  Workload at N=1: synthetic 1M ThreeCircle agents (BASELINE.json configs[2], the
+configuration the metric is quoted on), uniform density 1 agent/m^2 in a walled square room, static direction field.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--model three_circle|circular] [--agents M] [--density R]
+    python bench.py --impl reference ...      # the CPU arm: the oracle port of the reference on the host cores
+
+Under torchrun (N > 1) every rank owns one strip of a domain N times as wide (weak scaling), exchanging halo agents and
+migrants with its strip neighbours over NCCL each step.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ALGO_BYTES = {'circular': 184 + 16, 'three_circle': 312 + 16}   # state bytes per agent-step + (U,V) sample
+CELL = 3.6
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index=0):
+        self.rows = []
+        self.proc = None
+        self.gpu_index = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.gpu_index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in self.rows:
+            c = [x.strip() for x in r.split(',')]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); smax.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(names, c[5:9]):
+                if v.lower() == 'active':
+                    reasons.add(name)
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(smax) if smax else None,
+                'samples': len(sm), 'reasons': sorted(reasons)}
+
+
+def make_crowd(model, n, density, seed, origin=(0.0, 0.0)):
+    from crowddynamics_b200 import synthetic as S
+    agents, obstacles, side = S.uniform_crowd(n, model, density=density, seed=seed, origin=origin)
+    return agents, obstacles, side
+
+
+def make_field(side, origin=(0.0, 0.0), step=1.0):
+    """Static direction field towards an exit in the middle of the right wall (synthetic, (ny, nx) [iy, ix] layout).
+    step = 1 m keeps the two maps at 2 x 8 MB for the 1000 m room (the reference default 0.1 m would be 2 x 800 MB)."""
+    from crowddynamics_b200 import synthetic as S
+    x0, y0 = origin
+    return S.direction_field(step, (x0, y0, x0 + side, y0 + side), 'exit', point=(x0 + side, y0 + side / 2))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def cpu_port_rate(model, n_sample, steps, density, threads=1):
+    """agent-steps/s of the C oracle port (serial algorithm, like the reference) on `threads` independent replicas."""
+    from oracle import crowd_oracle as O
+    from crowddynamics_b200 import synthetic as S
+    O.lib()
+    crowds = []
+    for t in range(threads):
+        a, obs, side = S.uniform_crowd(n_sample, model, density=density, seed=100 + t)
+        crowds.append((a, obs, [make_field(side)]))
+
+    def work(k):
+        a, obs, fields = crowds[k]
+        for _ in range(steps):
+            O.step(a, obs, fields, CELL, 0.01, 0.01)
+    for k in range(threads):       # warm-up: one step each
+        a, obs, fields = crowds[k]
+        O.step(a, obs, fields, CELL, 0.01, 0.01)
+    t0 = time.perf_counter()
+    if threads == 1:
+        work(0)
+    else:
+        th = [threading.Thread(target=work, args=(k,)) for k in range(threads)]
+        [x.start() for x in th]
+        [x.join() for x in th]
+    dt = time.perf_counter() - t0
+    return threads * n_sample * steps / dt, dt
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the CPU arm.  The reference is Python + numba and /root/reference does not exist on the GPU box,
+    so this times the oracle port (bit-identical to the numba code on the golden vectors) on all host threads: the
+    algorithm is serial, so the threads run independent replicas of a bounded sample of the same workload."""
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    n_sample = args.cpu_agents or (20000 if args.model == 'three_circle' else 100000)
+    # warm-up steps are run inside cpu_port_rate (1 per replica); `steps` timed steps per replica
+    steps = max(1, min(args.steps, 5))
+    rate, secs = cpu_port_rate(args.model, n_sample, steps, args.density, threads=cores)
+    sample = '%d independent replicas of %d %s agents (density %.3g /m^2) x %d steps, C port of the numba reference' % (
+        cores, n_sample, args.model, args.density, steps)
+    line = {
+        'impl': 'reference', 'metric': 'agent-steps/sec', 'value': rate, 'unit': 'agent-steps/s', 'n_gpus': args.gpus,
+        'steps': steps, 'warmup': 1, 'ms_per_step': 1e3 * secs / steps, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': workload_config(args, n_sample, args.gpus),
+        'cpu_baseline': {'value': rate, 'unit': 'agent-steps/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': rate, 'unit': 'agent-steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, n_per_gpu, world):
+    return {'workload': 'synthetic %d %s agents per GPU, uniform %.3g agents/m^2 in a walled square room, 4 wall '
+                        'segments, static exit direction field (step 1 m), cell 3.6 m, dt_min=dt_max=0.01'
+                        % (n_per_gpu, args.model, args.density),
+            'agents_per_gpu': n_per_gpu, 'agent_model': args.model, 'density': args.density,
+            'parallelism': 'strips%d' % world if world > 1 else 'single',
+            'l2_policy': 'inputs larger than L2 (%d MB of SoA state streamed per step)'
+                         % (n_per_gpu * (34 if args.model == 'three_circle' else 19) * 8 // 2 ** 20)}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--model', default='three_circle', choices=['circular', 'three_circle'])
+    ap.add_argument('--agents', type=int, default=1000000, help='agents per GPU')
+    ap.add_argument('--density', type=float, default=1.0)
+    ap.add_argument('--cpu-agents', type=int, default=0, help='agents in the CPU baseline sample')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--e2e-steps', type=int, default=3)
+    args = ap.parse_args()
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if args.impl == 'reference':
+        return run_reference(args, rank, world)
+
+    import torch
+    import torch.distributed as dist
+    from crowddynamics_b200 import _lib
+    from crowddynamics_b200.engine import DeviceAgents
+    from crowddynamics_b200.structures import MODEL_CIRCULAR, MODEL_THREE_CIRCLE
+
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm')
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    _lib.load()
+
+    n = args.agents
+    mid = MODEL_CIRCULAR if args.model == 'circular' else MODEL_THREE_CIRCLE
+    itemsize = 228 if args.model == 'circular' else 316
+
+    if world > 1:
+        from crowddynamics_b200.parallel import StripSimulation
+        sim = StripSimulation.synthetic(args.model, n, args.density, rank, world, local_rank, seed=rank)
+        step_fn, dev = sim.step, sim.dev
+        n_local = sim.n_owned
+    else:
+        agents, obstacles, side = make_crowd(args.model, n, args.density, seed=0)
+        dev = DeviceAgents(mid, capacity=n, device=local_rank)
+        dev.set_stream(torch.cuda.current_stream().cuda_stream)
+        dev.set_obstacles(obstacles)
+        dev.set_navigation_field(0, *make_field(side))
+        # pinned host image of simulation.agents.array (packed records), the e2e leg copies it every step
+        host = torch.empty(n * itemsize, dtype=torch.uint8).pin_memory()
+        host.numpy()[:] = agents.view(np.uint8).reshape(-1)
+        dev.upload_raw(host.data_ptr(), n)
+
+        def step_fn(k):
+            dev.step(k, _lib.STEP_ALL, CELL, 0.01, 0.01, want_dt=False)
+        n_local = lambda: n   # noqa: E731
+
+    def sync():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    step_fn(args.warmup)
+    sync()
+    dev.profile(True)
+    launches0 = dev.launch_count()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync()
+    ev0.record()
+    step_fn(args.steps)
+    ev1.record()
+    sync()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = ev0.elapsed_time(ev1)
+    launches = dev.launch_count() - launches0
+    prof = dev.profile_read()
+    dev.profile(False)
+    agents_total = n_local() if callable(n_local) else n_local
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device='cuda')
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        c = torch.tensor([float(agents_total), float(launches)], dtype=torch.float64, device='cuda')
+        dist.all_reduce(c, op=dist.ReduceOp.SUM)
+        agents_total, launches = int(c[0].item()), int(c[1].item())
+    value = agents_total * args.steps / (ms * 1e-3)
+
+    # ---- end to end through the public boundary with HOST buffers (rank-local, aggregated like `value`) -------------
+    e2e = None
+    if world == 1:
+        e2e_steps = max(1, args.e2e_steps)
+        for _ in range(1):    # warm-up
+            dev.upload_raw(host.data_ptr(), n); step_fn(1); dev.download_raw(host.data_ptr(), n)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            dev.upload_raw(host.data_ptr(), n)          # H2D of simulation.agents.array (pinned) + AoS -> SoA
+            step_fn(1)
+            dev.download_raw(host.data_ptr(), n)        # SoA -> AoS + D2H of the whole records
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
+        e2e = {'value': n * e2e_steps / e2e_s, 'unit': 'agent-steps/s', 'h2d_bytes_per_step': n * itemsize,
+               'd2h_bytes_per_step': n * itemsize, 'steps': e2e_steps,
+               'path': 'cdb_upload_agents_aos -> cdb_step(1) -> cdb_download_agents_aos on a pinned host array'}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = measured_peaks()
+    n_rank0 = agents_total // world if world > 1 else n
+    roofline = None
+    if prof[3] > 0:
+        k_ms = prof[1] / prof[3]                      # dominant kernel: agent-agent (+ fused epilogue)
+        algo_bytes = ALGO_BYTES[args.model] * n_rank0
+        achieved = algo_bytes / (k_ms * 1e-3) / 1e9
+        roofline = {'bound': 'hbm', 'kernel': 'agent_agent', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+                    'frac': achieved / peak, 'peak_source': peak_src, 'traffic': None,
+                    'kernel_ms': k_ms, 'algorithmic_bytes_per_launch': algo_bytes,
+                    'phase_ms_per_step': {'pre_and_block_list': prof[0] / prof[3], 'agent_agent': k_ms,
+                                          'post': prof[2] / prof[3]},
+                    'note': 'the pair kernel is FP64-pipe bound at this density (SURVEY 7): HBM fraction is low by '
+                            'construction; see DESIGN.md for the FP64 roofline'}
+    line = {
+        'metric': 'agent-steps/sec', 'value': value, 'unit': 'agent-steps/s', 'n_gpus': world, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic', 'config': workload_config(args, n, world),
+        'gpu_launches': launches, 'clocks': clocks, 'roofline': roofline, 'e2e': e2e,
+        'hbm_fraction_whole_step': value / world * ALGO_BYTES[args.model] / 1e9 / peak,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        n_sample = args.cpu_agents or (50000 if args.model == 'three_circle' else 200000)
+        rate, secs = cpu_port_rate(args.model, n_sample, 3, args.density, threads=1)
+        line['cpu_baseline'] = {'value': rate, 'unit': 'agent-steps/s', 'cores': 1, 'kind': 'port',
+                                'sample': '%d %s agents (density %.3g /m^2) x 3 steps after 1 warm-up step, serial C '
+                                          'port of the numba reference (bit-identical on the golden vectors), %.1f s'
+                                          % (n_sample, args.model, args.density, secs),
+                                'host_cores': os.cpu_count()}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -55,9 +55,19 @@ int dev_alloc(T **p, size_t count) {
     return CDB_OK;
 }
 
+constexpr int DT_LOG = 1024;
+constexpr int PROFILE_MAX_STEPS = 4096;
+
 inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
 }  // namespace
+
+// every kernel launch of the library goes through here (counted: cdb_launch_count)
+#define LAUNCH(sim, kernel, grid, block, smem, ...)                          \
+    do {                                                                     \
+        kernel<<<(grid), (block), (smem), (sim)->stream>>>(__VA_ARGS__);     \
+        (sim)->launches++;                                                   \
+    } while (0)
 
 struct cdb_sim {
     int device = 0;
@@ -100,10 +110,17 @@ struct cdb_sim {
     unsigned long long *d_vmax = nullptr;   // ordered-uint64 encodings: [0] max |v|, [1] max v0
     double *d_dt = nullptr;                 // [0] last dt, [1] time_tot
     double *h_dt = nullptr;                 // pinned double[2]
+    double *d_dt_log = nullptr;             // dt of the last DT_LOG fused steps
     int *d_error = nullptr;
     int *h_error = nullptr;                 // pinned
     unsigned long long *d_pair_count = nullptr;
     int64_t iterations = 0;
+
+    // instrumentation: kernel launch counter and CUDA-event timing of the step phases
+    int64_t launches = 0;
+    bool profiling = false;
+    std::vector<cudaEvent_t> ev_pool;    // 4 events per profiled step: begin, after block list, after agent-agent, end
+    size_t ev_used = 0;
 };
 
 namespace {
@@ -156,6 +173,18 @@ int check_device_error(cdb_sim *sim) {
     return fail(CDB_ERR_CUDA, "device error flag %d", e);
 }
 
+// ---- instrumentation -----------------------------------------------------------------------------------------------
+int prof_mark(cdb_sim *sim) {
+    if (!sim->profiling) return CDB_OK;
+    if (sim->ev_used == sim->ev_pool.size()) {
+        cudaEvent_t e;
+        CK(cudaEventCreate(&e));
+        sim->ev_pool.push_back(e);
+    }
+    CK(cudaEventRecord(sim->ev_pool[sim->ev_used++], sim->stream));
+    return CDB_OK;
+}
+
 // ---- block list --------------------------------------------------------------------------------------------------
 int build_block_list(cdb_sim *sim, double cell_size) {
     if (!(cell_size > 0.0) || !std::isfinite(cell_size)) return fail(CDB_ERR_INVALID_VALUE, "cell_size must be > 0");
@@ -171,8 +200,8 @@ int build_block_list(cdb_sim *sim, double cell_size) {
     }
     const int T = 256;
     if (!sim->lattice_fixed) {
-        k_bbox_init<<<1, 32, 0, st>>>(sim->d_bbox);
-        k_bbox<<<cdiv(n, T * 4) < 1184 ? cdiv(n, T * 4) : 1184, T, 0, st>>>(sim->cur, (int)n, cell_size, sim->d_bbox, sim->d_error);
+        LAUNCH(sim, k_bbox_init, 1, 32, 0, sim->d_bbox);
+        LAUNCH(sim, k_bbox, (cdiv(n, T * 4) < 1184 ? cdiv(n, T * 4) : 1184), T, 0, sim->cur, (int)n, cell_size, sim->d_bbox, sim->d_error);
         CK(cudaMemcpyAsync(sim->h_bbox, sim->d_bbox, 4 * sizeof(long long), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         CKS(check_device_error(sim));
@@ -187,16 +216,16 @@ int build_block_list(cdb_sim *sim, double cell_size) {
     CKS(ensure_cells(sim, ncell));
     CK(cudaMemsetAsync(sim->d_cell_count, 0, ncell * sizeof(int), st));
     CK(cudaMemsetAsync(sim->d_cell_fill, 0, ncell * sizeof(int), st));
-    k_cell_count<<<cdiv(n, T), T, 0, st>>>(sim->cur, (int)n, cell_size, sim->d_grid, sim->d_cell_of_slot, sim->d_cell_count, sim->d_error);
+    LAUNCH(sim, k_cell_count, cdiv(n, T), T, 0, sim->cur, (int)n, cell_size, sim->d_grid, sim->d_cell_of_slot, sim->d_cell_count, sim->d_error);
     // exclusive scan count -> start
     const int nblk = cdiv(ncell, SCAN_TILE);
-    k_scan_tiles<<<nblk, SCAN_THREADS, 0, st>>>(sim->d_cell_count, sim->d_cell_start, (int)ncell, sim->d_scan_partials);
-    k_scan_partials<<<1, 1024, 0, st>>>(sim->d_scan_partials, nblk);
-    k_scan_add<<<nblk, SCAN_THREADS, 0, st>>>(sim->d_cell_start, (int)ncell, sim->d_scan_partials, (int)n);
-    k_scatter<<<cdiv(n, T), T, 0, st>>>(sim->d_cell_of_slot, (int)n, sim->d_cell_start, sim->d_cell_fill, sim->d_order_tmp);
-    k_rank_fix<<<cdiv(n, T), T, 0, st>>>(sim->d_order_tmp, (int)n, sim->cur.id, sim->d_cell_of_slot, sim->d_cell_start,
+    LAUNCH(sim, k_scan_tiles, nblk, SCAN_THREADS, 0, sim->d_cell_count, sim->d_cell_start, (int)ncell, sim->d_scan_partials);
+    LAUNCH(sim, k_scan_partials, 1, 1024, 0, sim->d_scan_partials, nblk);
+    LAUNCH(sim, k_scan_add, nblk, SCAN_THREADS, 0, sim->d_cell_start, (int)ncell, sim->d_scan_partials, (int)n);
+    LAUNCH(sim, k_scatter, cdiv(n, T), T, 0, sim->d_cell_of_slot, (int)n, sim->d_cell_start, sim->d_cell_fill, sim->d_order_tmp);
+    LAUNCH(sim, k_rank_fix, cdiv(n, T), T, 0, sim->d_order_tmp, (int)n, sim->cur.id, sim->d_cell_of_slot, sim->d_cell_start,
                                          sim->d_cell_count, sim->d_order);
-    k_gather<<<cdiv(n, T), T, 0, st>>>(sim->cur, sim->alt, (int)n, sim->n_planes, sim->d_order, sim->d_cell_of_slot, sim->d_order_tmp);
+    LAUNCH(sim, k_gather, cdiv(n, T), T, 0, sim->cur, sim->alt, (int)n, sim->n_planes, sim->d_order, sim->d_cell_of_slot, sim->d_order_tmp);
     // d_order_tmp now holds the flat cell of every *sorted* slot
     std::swap(sim->cur, sim->alt);
     std::swap(sim->d_cell_of_slot, sim->d_order_tmp);
@@ -207,58 +236,61 @@ int build_block_list(cdb_sim *sim, double cell_size) {
 
 int launch_reduce_vmax(cdb_sim *sim) {
     cudaStream_t st = sim->stream;
-    k_vmax_init<<<1, 32, 0, st>>>(sim->d_vmax);
+    LAUNCH(sim, k_vmax_init, 1, 32, 0, sim->d_vmax);
     if (sim->n > 0) {
         int blocks = cdiv(sim->n, 256 * 4);
         if (blocks > 1184) blocks = 1184;
-        k_vmax<<<blocks, 256, 0, st>>>(sim->cur, (int)sim->n, sim->d_vmax);
+        LAUNCH(sim, k_vmax, blocks, 256, 0, sim->cur, (int)sim->n, sim->d_vmax);
     }
     CK(cudaGetLastError());
     return CDB_OK;
 }
 
 int node_reset(cdb_sim *sim) {
-    if (sim->n) k_reset<<<cdiv(sim->n, 256), 256, 0, sim->stream>>>(sim->cur, (int)sim->n, sim->model);
+    if (sim->n) LAUNCH(sim, k_reset, cdiv(sim->n, 256), 256, 0, sim->cur, (int)sim->n, sim->model);
     CK(cudaGetLastError());
     return CDB_OK;
 }
 int node_navigation(cdb_sim *sim) {
-    if (sim->n && sim->n_nav) k_navigation<<<cdiv(sim->n, 256), 256, 0, sim->stream>>>(sim->cur, (int)sim->n, sim->d_nav, sim->n_nav);
+    if (sim->n && sim->n_nav) LAUNCH(sim, k_navigation, cdiv(sim->n, 256), 256, 0, sim->cur, (int)sim->n, sim->d_nav, sim->n_nav);
     CK(cudaGetLastError());
     return CDB_OK;
 }
 int node_orientation(cdb_sim *sim) {
-    if (sim->n && sim->model == CDB_MODEL_THREE_CIRCLE) k_orientation<<<cdiv(sim->n, 256), 256, 0, sim->stream>>>(sim->cur, (int)sim->n);
+    if (sim->n && sim->model == CDB_MODEL_THREE_CIRCLE) LAUNCH(sim, k_orientation, cdiv(sim->n, 256), 256, 0, sim->cur, (int)sim->n);
     CK(cudaGetLastError());
     return CDB_OK;
 }
 int node_adjust(cdb_sim *sim) {
-    if (sim->n) k_adjust<<<cdiv(sim->n, 256), 256, 0, sim->stream>>>(sim->cur, (int)sim->n, sim->model);
+    if (sim->n) LAUNCH(sim, k_adjust, cdiv(sim->n, 256), 256, 0, sim->cur, (int)sim->n, sim->model);
+    CK(cudaGetLastError());
+    return CDB_OK;
+}
+int launch_agent_agent(cdb_sim *sim) {
+    if (sim->n == 0) return CDB_OK;
+    const int T = 128;
+    if (sim->model == CDB_MODEL_CIRCULAR)
+        LAUNCH(sim, k_agent_agent_circular_v1, cdiv(sim->n, T), T, 0, sim->cur, (int)sim->n, sim->d_grid, sim->d_cell_of_slot,
+                                                                          sim->d_cell_start, sim->d_cell_count);
+    else
+        LAUNCH(sim, k_agent_agent_three_circle_v1, cdiv(sim->n, T), T, 0, sim->cur, (int)sim->n, sim->d_grid, sim->d_cell_of_slot,
+                                                                              sim->d_cell_start, sim->d_cell_count);
     CK(cudaGetLastError());
     return CDB_OK;
 }
 int node_agent_agent(cdb_sim *sim, double cell_size) {
     CKS(build_block_list(sim, cell_size));
-    if (sim->n == 0) return CDB_OK;
-    const int T = 128;
-    if (sim->model == CDB_MODEL_CIRCULAR)
-        k_agent_agent_circular_v1<<<cdiv(sim->n, T), T, 0, sim->stream>>>(sim->cur, (int)sim->n, sim->d_grid, sim->d_cell_of_slot,
-                                                                          sim->d_cell_start, sim->d_cell_count);
-    else
-        k_agent_agent_three_circle_v1<<<cdiv(sim->n, T), T, 0, sim->stream>>>(sim->cur, (int)sim->n, sim->d_grid, sim->d_cell_of_slot,
-                                                                              sim->d_cell_start, sim->d_cell_count);
-    CK(cudaGetLastError());
-    return CDB_OK;
+    return launch_agent_agent(sim);
 }
 int node_agent_obstacle(cdb_sim *sim) {
     if (sim->n && sim->n_obstacles)
-        k_agent_obstacle<<<cdiv(sim->n, 128), 128, 0, sim->stream>>>(sim->cur, (int)sim->n, sim->model, sim->d_obstacles, (int)sim->n_obstacles);
+        LAUNCH(sim, k_agent_obstacle, cdiv(sim->n, 128), 128, 0, sim->cur, (int)sim->n, sim->model, sim->d_obstacles, (int)sim->n_obstacles);
     CK(cudaGetLastError());
     return CDB_OK;
 }
 int node_integrate(cdb_sim *sim, double dt_min, double dt_max) {
     CKS(launch_reduce_vmax(sim));
-    k_integrate<<<sim->n ? cdiv(sim->n, 256) : 1, 256, 0, sim->stream>>>(sim->cur, (int)sim->n, sim->model, dt_min, dt_max, sim->d_vmax, sim->d_dt);
+    LAUNCH(sim, k_integrate, (sim->n ? cdiv(sim->n, 256) : 1), 256, 0, sim->cur, (int)sim->n, sim->model, dt_min, dt_max, sim->d_vmax, sim->d_dt);
     CK(cudaGetLastError());
     sim->tables_valid = false;   // positions moved
     return CDB_OK;
@@ -297,6 +329,7 @@ int cdb_create(int device, int model, int64_t capacity, cdb_sim **out) {
         CKS(dev_alloc(&sim->d_bbox, 4));
         CKS(dev_alloc(&sim->d_vmax, 2));
         CKS(dev_alloc(&sim->d_dt, 2));
+        CKS(dev_alloc(&sim->d_dt_log, DT_LOG));
         CKS(dev_alloc(&sim->d_error, 1));
         CKS(dev_alloc(&sim->d_pair_count, 1));
         CKS(dev_alloc(&sim->d_nav, MAX_NAV_TARGETS));
@@ -323,7 +356,8 @@ int cdb_destroy(cdb_sim *sim) {
     cudaFree(sim->d_bbox); cudaFreeHost(sim->h_bbox);
     cudaFree(sim->d_obstacles);
     for (auto &f : sim->nav) { cudaFree((void *)f.U); cudaFree((void *)f.V); }
-    cudaFree(sim->d_nav); cudaFree(sim->d_vmax); cudaFree(sim->d_dt); cudaFreeHost(sim->h_dt);
+    cudaFree(sim->d_nav); cudaFree(sim->d_vmax); cudaFree(sim->d_dt); cudaFree(sim->d_dt_log); cudaFreeHost(sim->h_dt);
+    for (auto e : sim->ev_pool) cudaEventDestroy(e);
     cudaFree(sim->d_error); cudaFreeHost(sim->h_error); cudaFree(sim->d_pair_count);
     if (sim->own_stream && sim->stream) cudaStreamDestroy(sim->stream);
     delete sim;
@@ -365,9 +399,9 @@ int cdb_upload_agents_aos(cdb_sim *sim, const void *agents, int64_t n, int64_t i
     CK(cudaMemcpyAsync(sim->d_aos, agents, n * itemsize, cudaMemcpyHostToDevice, sim->stream));
     const int smem = AOS_REC_PER_BLOCK * (int)itemsize;
     if (sim->model == CDB_MODEL_CIRCULAR)
-        k_unpack_aos<0><<<cdiv(n, AOS_REC_PER_BLOCK), AOS_REC_PER_BLOCK, smem, sim->stream>>>(sim->d_aos, (int)n, sim->cur);
+        LAUNCH(sim, k_unpack_aos<0>, cdiv(n, AOS_REC_PER_BLOCK), AOS_REC_PER_BLOCK, smem, sim->d_aos, (int)n, sim->cur);
     else
-        k_unpack_aos<1><<<cdiv(n, AOS_REC_PER_BLOCK), AOS_REC_PER_BLOCK, smem, sim->stream>>>(sim->d_aos, (int)n, sim->cur);
+        LAUNCH(sim, k_unpack_aos<1>, cdiv(n, AOS_REC_PER_BLOCK), AOS_REC_PER_BLOCK, smem, sim->d_aos, (int)n, sim->cur);
     CK(cudaGetLastError());
     // the host buffer may be pageable and reused by the caller right away
     CK(cudaStreamSynchronize(sim->stream));
@@ -384,9 +418,9 @@ int cdb_download_agents_aos(cdb_sim *sim, void *agents, int64_t n, int64_t items
     const uint32_t mask = field_mask & CDB_F_ALL_MUTABLE;
     const uint32_t pack_mask = (field_mask & CDB_F_WHOLE_RECORD) ? (uint32_t)CDB_F_ALL_MUTABLE : mask;
     if (sim->model == CDB_MODEL_CIRCULAR)
-        k_pack_aos<0><<<cdiv(n, 128), 128, 0, sim->stream>>>(sim->cur, (int)n, sim->d_aos, pack_mask);
+        LAUNCH(sim, k_pack_aos<0>, cdiv(n, 128), 128, 0, sim->cur, (int)n, sim->d_aos, pack_mask);
     else
-        k_pack_aos<1><<<cdiv(n, 128), 128, 0, sim->stream>>>(sim->cur, (int)n, sim->d_aos, pack_mask);
+        LAUNCH(sim, k_pack_aos<1>, cdiv(n, 128), 128, 0, sim->cur, (int)n, sim->d_aos, pack_mask);
     CK(cudaGetLastError());
     if (field_mask & CDB_F_WHOLE_RECORD) {
         CK(cudaMemcpyAsync(agents, sim->d_aos, n * itemsize, cudaMemcpyDeviceToHost, sim->stream));
@@ -485,22 +519,57 @@ int cdb_step(cdb_sim *sim, uint32_t flags, double cell_size, double dt_min, doub
     SIM_ENTRY();
     if (n_steps < 0) return fail(CDB_ERR_INVALID_VALUE, "negative n_steps");
     for (int64_t k = 0; k < n_steps; ++k) {
+        const bool prof = sim->profiling && sim->ev_used + 4 <= (size_t)PROFILE_MAX_STEPS * 4;
+        const bool prof_saved = sim->profiling;
+        sim->profiling = prof;
+        CKS(prof_mark(sim));
         if (flags & CDB_STEP_NAVIGATION) CKS(node_navigation(sim));
         if (flags & CDB_STEP_ORIENTATION) CKS(node_orientation(sim));
         if (flags & CDB_STEP_ADJUSTING) CKS(node_adjust(sim));
-        if (flags & CDB_STEP_AGENT_AGENT) CKS(node_agent_agent(sim, cell_size));
+        if (flags & CDB_STEP_AGENT_AGENT) CKS(build_block_list(sim, cell_size));
+        CKS(prof_mark(sim));
+        if (flags & CDB_STEP_AGENT_AGENT) CKS(launch_agent_agent(sim));
+        CKS(prof_mark(sim));
         if (flags & CDB_STEP_AGENT_OBSTACLE) CKS(node_agent_obstacle(sim));
         if (flags & CDB_STEP_INTEGRATOR) {
             CKS(node_integrate(sim, dt_min, dt_max));
-            if (dt_out) {
-                CK(cudaMemcpyAsync(sim->h_dt, sim->d_dt, 2 * sizeof(double), cudaMemcpyDeviceToHost, sim->stream));
-                CK(cudaStreamSynchronize(sim->stream));
-                dt_out[k] = sim->h_dt[0];
-            }
+            if (dt_out) CK(cudaMemcpyAsync(sim->d_dt_log + (k % DT_LOG), sim->d_dt, sizeof(double), cudaMemcpyDeviceToDevice, sim->stream));
         }
         if (flags & CDB_STEP_RESET) CKS(node_reset(sim));
+        CKS(prof_mark(sim));
+        sim->profiling = prof_saved;
         sim->iterations++;
+        if (dt_out && (flags & CDB_STEP_INTEGRATOR) && ((k + 1) % DT_LOG == 0 || k + 1 == n_steps)) {
+            const int64_t first = k / DT_LOG * DT_LOG, cnt = k + 1 - first;
+            CK(cudaMemcpyAsync(dt_out + first, sim->d_dt_log, cnt * sizeof(double), cudaMemcpyDeviceToHost, sim->stream));
+            CK(cudaStreamSynchronize(sim->stream));
+        }
     }
+    return CDB_OK;
+}
+
+int64_t cdb_launch_count(const cdb_sim *sim) { return sim ? sim->launches : -1; }
+
+int cdb_profile_enable(cdb_sim *sim, int enable) {
+    SIM_ENTRY();
+    sim->profiling = enable != 0;
+    sim->ev_used = 0;
+    return CDB_OK;
+}
+
+int cdb_profile_read(cdb_sim *sim, double ms[3], int64_t *steps) {
+    SIM_ENTRY();
+    CK(cudaStreamSynchronize(sim->stream));
+    ms[0] = ms[1] = ms[2] = 0.0;
+    const size_t n = sim->ev_used / 4;
+    for (size_t k = 0; k < n; ++k)
+        for (int j = 0; j < 3; ++j) {
+            float t = 0.f;
+            CK(cudaEventElapsedTime(&t, sim->ev_pool[4 * k + j], sim->ev_pool[4 * k + j + 1]));
+            ms[j] += t;
+        }
+    if (steps) *steps = (int64_t)n;
+    sim->ev_used = 0;
     return CDB_OK;
 }
 
@@ -530,7 +599,7 @@ int cdb_get_cell_ids(cdb_sim *sim, int64_t *cell_of_agent, int64_t n) {
     if (n == 0) return CDB_OK;
     long long *d = nullptr;
     CKS(dev_alloc(&d, (size_t)n));
-    k_export_cell_ids<<<cdiv(n, 256), 256, 0, sim->stream>>>(sim->cur.id, sim->d_cell_of_slot, (int)n, d);
+    LAUNCH(sim, k_export_cell_ids, cdiv(n, 256), 256, 0, sim->cur.id, sim->d_cell_of_slot, (int)n, d);
     CK(cudaMemcpyAsync(cell_of_agent, d, n * sizeof(long long), cudaMemcpyDeviceToHost, sim->stream));
     CK(cudaStreamSynchronize(sim->stream));
     cudaFree(d);
@@ -545,11 +614,11 @@ int cdb_get_cell_tables(cdb_sim *sim, int64_t *points_indices, int64_t n, int64_
     long long *d = nullptr;
     const int64_t m = n > n_cells ? n : n_cells;
     CKS(dev_alloc(&d, (size_t)m));
-    k_widen<<<cdiv(n, 256), 256, 0, sim->stream>>>(sim->cur.id, (int)n, d);
+    LAUNCH(sim, k_widen, cdiv(n, 256), 256, 0, sim->cur.id, (int)n, d);
     CK(cudaMemcpyAsync(points_indices, d, n * sizeof(long long), cudaMemcpyDeviceToHost, sim->stream));
-    k_widen<<<cdiv(n_cells, 256), 256, 0, sim->stream>>>(sim->d_cell_count, (int)n_cells, d);
+    LAUNCH(sim, k_widen, cdiv(n_cells, 256), 256, 0, sim->d_cell_count, (int)n_cells, d);
     CK(cudaMemcpyAsync(cells_count, d, n_cells * sizeof(long long), cudaMemcpyDeviceToHost, sim->stream));
-    k_widen<<<cdiv(n_cells, 256), 256, 0, sim->stream>>>(sim->d_cell_start, (int)n_cells, d);
+    LAUNCH(sim, k_widen, cdiv(n_cells, 256), 256, 0, sim->d_cell_start, (int)n_cells, d);
     CK(cudaMemcpyAsync(cells_offset, d, n_cells * sizeof(long long), cudaMemcpyDeviceToHost, sim->stream));
     CK(cudaStreamSynchronize(sim->stream));
     cudaFree(d);
@@ -565,7 +634,7 @@ int cdb_get_neighbor_pairs(cdb_sim *sim, int64_t *pairs, int64_t cap, int64_t *c
     long long *d = nullptr;
     CKS(dev_alloc(&d, (size_t)(cap > 0 ? 2 * cap : 1)));
     CK(cudaMemsetAsync(sim->d_pair_count, 0, sizeof(unsigned long long), sim->stream));
-    k_export_pairs<<<cdiv(sim->n, 128), 128, 0, sim->stream>>>(sim->cur.id, (int)sim->n, sim->d_grid, sim->d_cell_of_slot, sim->d_cell_start,
+    LAUNCH(sim, k_export_pairs, cdiv(sim->n, 128), 128, 0, sim->cur.id, (int)sim->n, sim->d_grid, sim->d_cell_of_slot, sim->d_cell_start,
                                                              sim->d_cell_count, d, cap > 0 && pairs ? cap : 0, sim->d_pair_count);
     unsigned long long c = 0;
     CK(cudaMemcpyAsync(&c, sim->d_pair_count, sizeof(c), cudaMemcpyDeviceToHost, sim->stream));

@@ -131,6 +131,20 @@ class DeviceAgents:
         _lib.check(self.lib.cdb_get_time(self.handle, C.byref(t), C.byref(it)))
         return t.value, it.value
 
+    # -- instrumentation ---------------------------------------------------------------------------------------------
+    def launch_count(self):
+        return int(self.lib.cdb_launch_count(self.handle))
+
+    def profile(self, enable=True):
+        _lib.check(self.lib.cdb_profile_enable(self.handle, 1 if enable else 0))
+
+    def profile_read(self):
+        """-> (ms_blocklist_and_pre, ms_agent_agent, ms_post, steps) summed since the last read."""
+        ms = (C.c_double * 3)()
+        steps = C.c_int64()
+        _lib.check(self.lib.cdb_profile_read(self.handle, ms, C.byref(steps)))
+        return ms[0], ms[1], ms[2], steps.value
+
     # -- block list exports ------------------------------------------------------------------------------------------
     def build_block_list(self, cell_size):
         _lib.check(self.lib.cdb_build_block_list(self.handle, float(cell_size)))

@@ -116,6 +116,13 @@ int cdb_step(cdb_sim *sim, uint32_t node_flags, double cell_size, double dt_min,
              double *dt_out);
 int cdb_get_time(cdb_sim *sim, double *time_tot, int64_t *iterations);
 
+/* ---- instrumentation (no reference counterpart) -------------------------------------------------------------------- */
+int64_t cdb_launch_count(const cdb_sim *sim);            /* kernels launched by this sim so far */
+int cdb_profile_enable(cdb_sim *sim, int enable);        /* CUDA-event timing of the phases of cdb_step on the sim's stream */
+/* ms[0] = per-agent nodes before + block list build, ms[1] = agent-agent kernel, ms[2] = obstacle + integrator + reset;
+ * summed over the profiled steps since the last read (at most 4096 steps are recorded). */
+int cdb_profile_read(cdb_sim *sim, double ms[3], int64_t *steps);
+
 /* ---- block list: debug / parity exports (cell_lists.add_to_cells & iter_nearest_neighbors, call sites
  * core/interactions.py:191-205; spec core/block_list.py:28-52) ---------------------------------------------------- */
 int cdb_build_block_list(cdb_sim *sim, double cell_size);
