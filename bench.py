@@ -149,7 +149,7 @@ def run_reference(args, rank, world):
         'impl': 'reference', 'metric': 'agent-steps/sec', 'value': rate, 'unit': 'agent-steps/s', 'n_gpus': args.gpus,
         'steps': steps, 'warmup': 1, 'ms_per_step': 1e3 * secs / steps, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-        'config': workload_config(args, n_sample, args.gpus),
+        'config': workload_config(args, args.agents, args.gpus),
         'cpu_baseline': {'value': rate, 'unit': 'agent-steps/s', 'cores': cores, 'kind': 'port', 'sample': sample},
         'e2e': {'value': rate, 'unit': 'agent-steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }

@@ -19,6 +19,7 @@
 #include <vector>
 
 #include "kernels.cuh"
+#include "step_kernel.cuh"
 
 namespace {
 
@@ -73,7 +74,11 @@ struct cdb_sim {
     int device = 0;
     int model = 0;
     int64_t itemsize = 0;
-    int n_planes = 0;
+    int n_planes = 0;         // planes that mirror record fields
+    int n_alloc_planes = 0;   // + derived planes (three-circle: shoulder offsets, extent)
+    int variant = 2;          // agent-agent kernel: 1 = one-phase reference kernel, 2 = two-phase fused kernel
+    bool auto_lattice_valid = false;
+    int auto_lattice_age = 0;
     int64_t capacity = 0;   // agent slots allocated (incl. room for ghosts / migrants)
     int64_t n = 0;          // agents currently held
     cudaStream_t stream = nullptr;
@@ -90,6 +95,7 @@ struct cdb_sim {
     Grid grid{};             // host copy
     Grid *d_grid = nullptr;
     double cell_size = 0.0;
+    double cell_size_lattice = 0.0;
     bool tables_valid = false;
     int64_t cell_capacity = 0;
     int *d_cell_count = nullptr, *d_cell_start = nullptr, *d_cell_fill = nullptr;
@@ -142,8 +148,8 @@ int ensure_capacity(cdb_sim *sim, int64_t n) {
     if (n <= sim->capacity && sim->cur.p) return CDB_OK;
     int64_t cap = n < 1024 ? 1024 : n;
     free_soa(sim->cur); free_soa(sim->alt);
-    CKS(alloc_soa(sim->cur, sim->n_planes, cap));
-    CKS(alloc_soa(sim->alt, sim->n_planes, cap));
+    CKS(alloc_soa(sim->cur, sim->n_alloc_planes, cap));
+    CKS(alloc_soa(sim->alt, sim->n_alloc_planes, cap));
     CKS(dev_alloc(&sim->d_cell_of_slot, cap));
     CKS(dev_alloc(&sim->d_order_tmp, cap));
     CKS(dev_alloc(&sim->d_order, cap));
@@ -186,7 +192,7 @@ int prof_mark(cdb_sim *sim) {
 }
 
 // ---- block list --------------------------------------------------------------------------------------------------
-int build_block_list(cdb_sim *sim, double cell_size) {
+int build_block_list(cdb_sim *sim, double cell_size, bool padded_lattice = false, unsigned long long *vmax = nullptr) {
     if (!(cell_size > 0.0) || !std::isfinite(cell_size)) return fail(CDB_ERR_INVALID_VALUE, "cell_size must be > 0");
     const int64_t n = sim->n;
     sim->cell_size = cell_size;
@@ -199,7 +205,12 @@ int build_block_list(cdb_sim *sim, double cell_size) {
         return CDB_OK;
     }
     const int T = 256;
-    if (!sim->lattice_fixed) {
+    // padded_lattice (fused steps): derive the lattice from the bounding box once, pad it by one cell and keep it for the
+    // next steps -- cells stay anchored at multiples of cell_size and agents that leave the lattice are binned into its
+    // border cells (adjacency is preserved by clamping), so neighbour sets and forces do not depend on this choice.
+    const bool reuse = padded_lattice && sim->auto_lattice_valid && sim->cell_size_lattice == cell_size && sim->auto_lattice_age < 64;
+    if (reuse) sim->auto_lattice_age++;
+    if (!sim->lattice_fixed && !reuse) {
         LAUNCH(sim, k_bbox_init, 1, 32, 0, sim->d_bbox);
         LAUNCH(sim, k_bbox, (cdiv(n, T * 4) < 1184 ? cdiv(n, T * 4) : 1184), T, 0, sim->cur, (int)n, cell_size, sim->d_bbox, sim->d_error);
         CK(cudaMemcpyAsync(sim->h_bbox, sim->d_bbox, 4 * sizeof(long long), cudaMemcpyDeviceToHost, st));
@@ -209,14 +220,18 @@ int build_block_list(cdb_sim *sim, double cell_size) {
         long long nx = x1 - x0 + 1, ny = y1 - y0 + 1;
         if (nx <= 0 || ny <= 0 || (double)nx * (double)ny > 2.0e9)
             return fail(CDB_ERR_CAPACITY, "block list of %lld x %lld cells is too large", nx, ny);
+        if (padded_lattice) { x0 -= 1; y0 -= 1; nx += 2; ny += 2; }
         sim->grid = Grid{x0, y0, nx, ny, nx * ny};
+        sim->auto_lattice_valid = padded_lattice;
+        sim->auto_lattice_age = 0;
+        sim->cell_size_lattice = cell_size;
         CK(cudaMemcpyAsync(sim->d_grid, &sim->grid, sizeof(Grid), cudaMemcpyHostToDevice, st));
     }
     const int64_t ncell = sim->grid.ncell;
     CKS(ensure_cells(sim, ncell));
     CK(cudaMemsetAsync(sim->d_cell_count, 0, ncell * sizeof(int), st));
     CK(cudaMemsetAsync(sim->d_cell_fill, 0, ncell * sizeof(int), st));
-    LAUNCH(sim, k_cell_count, cdiv(n, T), T, 0, sim->cur, (int)n, cell_size, sim->d_grid, sim->d_cell_of_slot, sim->d_cell_count, sim->d_error);
+    LAUNCH(sim, k_cell_count, cdiv(n, T), T, 0, sim->cur, (int)n, cell_size, sim->d_grid, sim->d_cell_of_slot, sim->d_cell_count, sim->d_error, vmax);
     // exclusive scan count -> start
     const int nblk = cdiv(ncell, SCAN_TILE);
     LAUNCH(sim, k_scan_tiles, nblk, SCAN_THREADS, 0, sim->d_cell_count, sim->d_cell_start, (int)ncell, sim->d_scan_partials);
@@ -225,7 +240,7 @@ int build_block_list(cdb_sim *sim, double cell_size) {
     LAUNCH(sim, k_scatter, cdiv(n, T), T, 0, sim->d_cell_of_slot, (int)n, sim->d_cell_start, sim->d_cell_fill, sim->d_order_tmp);
     LAUNCH(sim, k_rank_fix, cdiv(n, T), T, 0, sim->d_order_tmp, (int)n, sim->cur.id, sim->d_cell_of_slot, sim->d_cell_start,
                                          sim->d_cell_count, sim->d_order);
-    LAUNCH(sim, k_gather, cdiv(n, T), T, 0, sim->cur, sim->alt, (int)n, sim->n_planes, sim->d_order, sim->d_cell_of_slot, sim->d_order_tmp);
+    LAUNCH(sim, k_gather, cdiv(n, T), T, 0, sim->cur, sim->alt, (int)n, sim->n_planes, sim->model, sim->d_order, sim->d_cell_of_slot, sim->d_order_tmp);
     // d_order_tmp now holds the flat cell of every *sorted* slot
     std::swap(sim->cur, sim->alt);
     std::swap(sim->d_cell_of_slot, sim->d_order_tmp);
@@ -266,8 +281,43 @@ int node_adjust(cdb_sim *sim) {
     CK(cudaGetLastError());
     return CDB_OK;
 }
+StepArgs step_args(cdb_sim *sim, unsigned flags, double dt_min, double dt_max, double *dt_log) {
+    StepArgs a{};
+    a.in = sim->cur;
+    a.out = (flags & CDB_STEP_INTEGRATOR) ? sim->alt : sim->cur;
+    a.n = (int)sim->n;
+    a.grid = sim->d_grid;
+    a.cell_sorted = sim->d_cell_of_slot; a.cell_start = sim->d_cell_start; a.cell_count = sim->d_cell_count;
+    a.nav = sim->d_nav; a.n_nav = sim->n_nav;
+    a.obs = sim->d_obstacles; a.n_obs = (int)sim->n_obstacles;
+    a.flags = flags;
+    a.dt_min = dt_min; a.dt_max = dt_max;
+    a.vmax = sim->d_vmax; a.dt_out = sim->d_dt; a.dt_log = dt_log;
+    return a;
+}
+
+// the fused kernel; requires a current block list when CDB_STEP_AGENT_AGENT is selected
+int launch_step_kernel(cdb_sim *sim, unsigned flags, double dt_min, double dt_max, double *dt_log) {
+    if (sim->n == 0) {
+        if (flags & CDB_STEP_INTEGRATOR) LAUNCH(sim, k_integrate, 1, 32, 0, sim->cur, 0, sim->model, dt_min, dt_max, sim->d_vmax, sim->d_dt);
+        CK(cudaGetLastError());
+        return CDB_OK;
+    }
+    const StepArgs a = step_args(sim, flags, dt_min, dt_max, dt_log);
+    const int smem = (STEP_THREADS / 32) * LCAP * 32 * (int)sizeof(int);
+    if (sim->model == CDB_MODEL_CIRCULAR) LAUNCH(sim, k_step<0>, cdiv(sim->n, STEP_THREADS), STEP_THREADS, smem, a);
+    else LAUNCH(sim, k_step<1>, cdiv(sim->n, STEP_THREADS), STEP_THREADS, smem, a);
+    CK(cudaGetLastError());
+    if (flags & CDB_STEP_INTEGRATOR) {
+        std::swap(sim->cur, sim->alt);
+        sim->tables_valid = false;
+    }
+    return CDB_OK;
+}
+
 int launch_agent_agent(cdb_sim *sim) {
     if (sim->n == 0) return CDB_OK;
+    if (sim->variant != 1) return launch_step_kernel(sim, CDB_STEP_AGENT_AGENT, 0.0, 0.0, nullptr);
     const int T = 128;
     if (sim->model == CDB_MODEL_CIRCULAR)
         LAUNCH(sim, k_agent_agent_circular_v1, cdiv(sim->n, T), T, 0, sim->cur, (int)sim->n, sim->d_grid, sim->d_cell_of_slot,
@@ -321,6 +371,7 @@ int cdb_create(int device, int model, int64_t capacity, cdb_sim **out) {
     sim->model = model;
     sim->itemsize = model == CDB_MODEL_CIRCULAR ? 228 : 316;
     sim->n_planes = model == CDB_MODEL_CIRCULAR ? NP_CIRC : NP_THREE;
+    sim->n_alloc_planes = model == CDB_MODEL_CIRCULAR ? NP_CIRC : NP_THREE_ALL;
     int rc = [&]() -> int {
         CK(cudaStreamCreateWithFlags(&sim->stream, cudaStreamNonBlocking));
         sim->own_stream = true;
@@ -395,6 +446,7 @@ int cdb_upload_agents_aos(cdb_sim *sim, const void *agents, int64_t n, int64_t i
     }
     sim->n = n;
     sim->tables_valid = false;
+    sim->auto_lattice_valid = false;
     if (n == 0) return CDB_OK;
     CK(cudaMemcpyAsync(sim->d_aos, agents, n * itemsize, cudaMemcpyHostToDevice, sim->stream));
     const int smem = AOS_REC_PER_BLOCK * (int)itemsize;
@@ -523,19 +575,31 @@ int cdb_step(cdb_sim *sim, uint32_t flags, double cell_size, double dt_min, doub
         const bool prof_saved = sim->profiling;
         sim->profiling = prof;
         CKS(prof_mark(sim));
-        if (flags & CDB_STEP_NAVIGATION) CKS(node_navigation(sim));
-        if (flags & CDB_STEP_ORIENTATION) CKS(node_orientation(sim));
-        if (flags & CDB_STEP_ADJUSTING) CKS(node_adjust(sim));
-        if (flags & CDB_STEP_AGENT_AGENT) CKS(build_block_list(sim, cell_size));
-        CKS(prof_mark(sim));
-        if (flags & CDB_STEP_AGENT_AGENT) CKS(launch_agent_agent(sim));
-        CKS(prof_mark(sim));
-        if (flags & CDB_STEP_AGENT_OBSTACLE) CKS(node_agent_obstacle(sim));
-        if (flags & CDB_STEP_INTEGRATOR) {
-            CKS(node_integrate(sim, dt_min, dt_max));
-            if (dt_out) CK(cudaMemcpyAsync(sim->d_dt_log + (k % DT_LOG), sim->d_dt, sizeof(double), cudaMemcpyDeviceToDevice, sim->stream));
+        double *log_slot = (dt_out && (flags & CDB_STEP_INTEGRATOR)) ? sim->d_dt_log + (k % DT_LOG) : nullptr;
+        if (sim->variant == 1) {
+            // node-by-node path with the one-phase kernels (kept as an independent cross-check of the fused kernel)
+            if (flags & CDB_STEP_NAVIGATION) CKS(node_navigation(sim));
+            if (flags & CDB_STEP_ORIENTATION) CKS(node_orientation(sim));
+            if (flags & CDB_STEP_ADJUSTING) CKS(node_adjust(sim));
+            if (flags & CDB_STEP_AGENT_AGENT) CKS(build_block_list(sim, cell_size));
+            CKS(prof_mark(sim));
+            if (flags & CDB_STEP_AGENT_AGENT) CKS(launch_agent_agent(sim));
+            CKS(prof_mark(sim));
+            if (flags & CDB_STEP_AGENT_OBSTACLE) CKS(node_agent_obstacle(sim));
+            if (flags & CDB_STEP_INTEGRATOR) {
+                CKS(node_integrate(sim, dt_min, dt_max));
+                if (log_slot) CK(cudaMemcpyAsync(log_slot, sim->d_dt, sizeof(double), cudaMemcpyDeviceToDevice, sim->stream));
+            }
+            if (flags & CDB_STEP_RESET) CKS(node_reset(sim));
+        } else {
+            const bool need_vmax = flags & CDB_STEP_INTEGRATOR;
+            if (need_vmax) LAUNCH(sim, k_vmax_init, 1, 32, 0, sim->d_vmax);
+            if (flags & CDB_STEP_AGENT_AGENT) CKS(build_block_list(sim, cell_size, true, need_vmax ? sim->d_vmax : nullptr));
+            else if (need_vmax && sim->n > 0) LAUNCH(sim, k_vmax, (cdiv(sim->n, 1024) < 1184 ? cdiv(sim->n, 1024) : 1184), 256, 0, sim->cur, (int)sim->n, sim->d_vmax);
+            CKS(prof_mark(sim));
+            CKS(launch_step_kernel(sim, flags, dt_min, dt_max, log_slot));
+            CKS(prof_mark(sim));
         }
-        if (flags & CDB_STEP_RESET) CKS(node_reset(sim));
         CKS(prof_mark(sim));
         sim->profiling = prof_saved;
         sim->iterations++;
@@ -545,6 +609,13 @@ int cdb_step(cdb_sim *sim, uint32_t flags, double cell_size, double dt_min, doub
             CK(cudaStreamSynchronize(sim->stream));
         }
     }
+    return CDB_OK;
+}
+
+int cdb_set_variant(cdb_sim *sim, int variant) {
+    SIM_ENTRY();
+    if (variant != 1 && variant != 2) return fail(CDB_ERR_INVALID_VALUE, "unknown kernel variant %d", variant);
+    sim->variant = variant;
     return CDB_OK;
 }
 

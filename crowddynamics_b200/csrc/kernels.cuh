@@ -359,15 +359,36 @@ __device__ __forceinline__ int flat_cell(double px, double py, double cell_size,
     return (int)(cx * g.ny + cy);
 }
 
-__global__ void k_cell_count(Soa s, int n, double cell_size, const Grid *grid, int *cell_of_slot, int *cell_count, int *error) {
+__device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long v) {
+    for (int o = 16; o; o >>= 1) { unsigned long long w = __shfl_xor_sync(0xffffffffu, v, o); v = w > v ? w : v; }
+    return v;
+}
+
+// cell id of every agent + per-cell counts; optionally also the two maxima adaptive_timestep needs (integrator.py:81-90)
+__global__ void k_cell_count(Soa s, int n, double cell_size, const Grid *grid, int *cell_of_slot, int *cell_count, int *error,
+                             unsigned long long *vmax) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const Grid g = *grid;
-    double px = s(PX, i), py = s(PY, i);
-    if (!isfinite(px) || !isfinite(py)) atomicExch(error, ERR_NONFINITE);
-    int c = flat_cell(px, py, cell_size, g);
-    cell_of_slot[i] = c;
-    atomicAdd(&cell_count[c], 1);
+    double v_max = 0.0;
+    unsigned long long v0 = 0ULL;
+    if (i < n) {
+        const Grid g = *grid;
+        double px = s(PX, i), py = s(PY, i);
+        if (!isfinite(px) || !isfinite(py)) atomicExch(error, ERR_NONFINITE);
+        int c = flat_cell(px, py, cell_size, g);
+        cell_of_slot[i] = c;
+        atomicAdd(&cell_count[c], 1);
+        if (vmax) {
+            double l = hypot(s(VX, i), s(VY, i));
+            if (l > v_max) v_max = l;
+            double tv = s(V0, i);
+            v0 = isnan(tv) ? 0xffffffffffffffffULL : ordered_bits(tv);
+        }
+    }
+    if (vmax) {
+        unsigned long long vm = warp_max_u64(ordered_bits(v_max));
+        v0 = warp_max_u64(v0);
+        if ((threadIdx.x & 31) == 0) { atomicMax(&vmax[0], vm); atomicMax(&vmax[1], v0); }
+    }
 }
 
 // exclusive scan of cell counts -> cell starts (three small kernels; the table is tiny next to the agent state)
@@ -453,8 +474,10 @@ __global__ void k_rank_fix(const int *__restrict__ order_tmp, int n, const int *
     order[b + rank] = src;
 }
 
-__global__ void k_gather(Soa src, Soa dst, int n, int n_planes, const int *__restrict__ order, const int *__restrict__ cell_of_slot,
-                         int *__restrict__ cell_sorted) {
+// physical reorder into cell order (all record planes), plus the derived planes of the three-circle model:
+// shoulder displacement r_ts (sin phi, -cos phi) (power_law.py:338-350) and a conservative body extent for the prefilter
+__global__ void k_gather(Soa src, Soa dst, int n, int n_planes, int model, const int *__restrict__ order,
+                         const int *__restrict__ cell_of_slot, int *__restrict__ cell_sorted) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
     const int o = order[t];
@@ -462,6 +485,15 @@ __global__ void k_gather(Soa src, Soa dst, int n, int n_planes, const int *__res
     dst.id[t] = src.id[o];
     dst.target[t] = src.target[o];
     cell_sorted[t] = cell_of_slot[o];
+    if (model == CDB_MODEL_THREE_CIRCLE) {
+        const double phi = src(PHI, o), r_ts = src(R_TS, o);
+        dst(NP_THREE + 0, t) = r_ts * sin(phi);
+        dst(NP_THREE + 1, t) = r_ts * -cos(phi);
+        const double x = src(PX, o), y = src(PY, o);
+        const double dl = hypot(src(LSX, o) - x, src(LSY, o) - y), dr = hypot(src(RSX, o) - x, src(RSY, o) - y);
+        const double ext = fmax(src(R_T, o), fmax(dl, dr) + src(R_S, o));
+        dst(NP_THREE + 2, t) = ext * (1.0 + 1e-12);
+    }
 }
 
 __global__ void k_export_cell_ids(const int *__restrict__ id, const int *__restrict__ cell_sorted, int n, long long *out) {
@@ -612,11 +644,6 @@ __global__ void k_agent_obstacle(Soa s, int n, int model, const double *__restri
 // ---- integrator: core/integrator.py:32-97,167-193,209-256 + shoulders simulation/agents.py:473-486 ---------------
 __global__ void k_vmax_init(unsigned long long *vmax) {
     if (threadIdx.x == 0) { vmax[0] = ordered_bits(0.0); vmax[1] = ordered_bits(-__longlong_as_double(0x7ff0000000000000LL)); }
-}
-
-__device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long v) {
-    for (int o = 16; o; o >>= 1) { unsigned long long w = __shfl_xor_sync(0xffffffffu, v, o); v = w > v ? w : v; }
-    return v;
 }
 
 __global__ void k_vmax(Soa s, int n, unsigned long long *vmax) {

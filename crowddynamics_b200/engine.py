@@ -132,6 +132,9 @@ class DeviceAgents:
         return t.value, it.value
 
     # -- instrumentation ---------------------------------------------------------------------------------------------
+    def set_variant(self, variant):
+        _lib.check(self.lib.cdb_set_variant(self.handle, int(variant)))
+
     def launch_count(self):
         return int(self.lib.cdb_launch_count(self.handle))
 

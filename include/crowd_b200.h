@@ -117,6 +117,8 @@ int cdb_step(cdb_sim *sim, uint32_t node_flags, double cell_size, double dt_min,
 int cdb_get_time(cdb_sim *sim, double *time_tot, int64_t *iterations);
 
 /* ---- instrumentation (no reference counterpart) -------------------------------------------------------------------- */
+/* agent-agent kernel variant: 2 (default) = two-phase fused step kernel, 1 = one-phase kernels, kept as a cross-check */
+int cdb_set_variant(cdb_sim *sim, int variant);
 int64_t cdb_launch_count(const cdb_sim *sim);            /* kernels launched by this sim so far */
 int cdb_profile_enable(cdb_sim *sim, int enable);        /* CUDA-event timing of the phases of cdb_step on the sim's stream */
 /* ms[0] = per-agent nodes before + block list build, ms[1] = agent-agent kernel, ms[2] = obstacle + integrator + reset;

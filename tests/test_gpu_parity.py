@@ -271,3 +271,33 @@ def test_invalid_dtype_raises_invalid_type():
     with pytest.raises(InvalidValue):
         dev.agent_agent(CELL)
     dev.close()
+
+
+# ---- fused two-phase kernel vs the one-phase kernels (independent implementations of the same arithmetic) ----------------
+@pytest.mark.parametrize('model', ['circular', 'three_circle'])
+@pytest.mark.parametrize('density', [0.125, 1.0, 4.0])
+def test_fused_kernel_matches_one_phase_kernel(model, density):
+    n = 20000
+    a, obs, side = S.uniform_crowd(n, model, density=density, seed=7, overlap_fraction=0.03 if density > 1 else 0.0)
+    mid = MODEL_CIRCULAR if model == 'circular' else MODEL_THREE_CIRCLE
+    out = {}
+    for variant in (1, 2):
+        dev = DeviceAgents(mid)
+        dev.set_variant(variant)
+        dev.upload(a)
+        dev.set_obstacles(obs)
+        dev.set_navigation_field(0, *S.direction_field(0.5, (0, 0, side, side), 'swirl'))
+        dev.step(1, _lib.STEP_ALL & ~(_lib.STEP_INTEGRATOR | _lib.STEP_RESET), CELL, 0.001, 0.01, want_dt=False)
+        f = a.copy(); dev.download(f)
+        dts = dev.step(3, _lib.STEP_ALL, CELL, 0.001, 0.01)
+        g = a.copy(); dev.download(g)
+        out[variant] = (f, g, dts)
+        dev.close()
+    _assert_forces(out[2][0], out[1][0], model, tol=1e-12)
+    assert (out[1][2] == out[2][2]).all()
+    assert np.abs(out[1][1]['position'] - out[2][1]['position']).max() <= 1e-9
+    # and the one-phase path against the oracle on the same crowd (single step forces)
+    ref = a.copy()
+    O.navigation(ref, [S.direction_field(0.5, (0, 0, side, side), 'swirl')]); O.orientation(ref); O.adjusting(ref)
+    O.agent_agent_block_list(ref, CELL); O.agent_obstacle(ref, obs)
+    _assert_forces(out[2][0], ref, model)
