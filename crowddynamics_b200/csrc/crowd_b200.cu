@@ -101,6 +101,7 @@ struct cdb_sim {
     int *d_cell_count = nullptr, *d_cell_start = nullptr, *d_cell_fill = nullptr;
     int *d_cell_of_slot = nullptr;   // flat cell of each slot (of `cur`, valid after build)
     int *d_order_tmp = nullptr, *d_order = nullptr;
+    double *d_nbr = nullptr;         // packed neighbour records of the cell-sorted state
     int *d_scan_partials = nullptr;
     long long *d_bbox = nullptr;     // min ix, max ix, min iy, max iy
     long long *h_bbox = nullptr;     // pinned
@@ -153,6 +154,7 @@ int ensure_capacity(cdb_sim *sim, int64_t n) {
     CKS(dev_alloc(&sim->d_cell_of_slot, cap));
     CKS(dev_alloc(&sim->d_order_tmp, cap));
     CKS(dev_alloc(&sim->d_order, cap));
+    CKS(dev_alloc(&sim->d_nbr, (size_t)cap * (sim->model == CDB_MODEL_CIRCULAR ? REC_CIRC : REC_THREE)));
     sim->capacity = cap;
     return CDB_OK;
 }
@@ -240,7 +242,7 @@ int build_block_list(cdb_sim *sim, double cell_size, bool padded_lattice = false
     LAUNCH(sim, k_scatter, cdiv(n, T), T, 0, sim->d_cell_of_slot, (int)n, sim->d_cell_start, sim->d_cell_fill, sim->d_order_tmp);
     LAUNCH(sim, k_rank_fix, cdiv(n, T), T, 0, sim->d_order_tmp, (int)n, sim->cur.id, sim->d_cell_of_slot, sim->d_cell_start,
                                          sim->d_cell_count, sim->d_order);
-    LAUNCH(sim, k_gather, cdiv(n, T), T, 0, sim->cur, sim->alt, (int)n, sim->n_planes, sim->model, sim->d_order, sim->d_cell_of_slot, sim->d_order_tmp);
+    LAUNCH(sim, k_gather, cdiv(n, T), T, 0, sim->cur, sim->alt, (int)n, sim->n_planes, sim->model, sim->d_order, sim->d_cell_of_slot, sim->d_order_tmp, sim->d_nbr);
     // d_order_tmp now holds the flat cell of every *sorted* slot
     std::swap(sim->cur, sim->alt);
     std::swap(sim->d_cell_of_slot, sim->d_order_tmp);
@@ -285,6 +287,7 @@ StepArgs step_args(cdb_sim *sim, unsigned flags, double dt_min, double dt_max, d
     StepArgs a{};
     a.in = sim->cur;
     a.out = (flags & CDB_STEP_INTEGRATOR) ? sim->alt : sim->cur;
+    a.nbr = sim->d_nbr;
     a.n = (int)sim->n;
     a.grid = sim->d_grid;
     a.cell_sorted = sim->d_cell_of_slot; a.cell_start = sim->d_cell_start; a.cell_count = sim->d_cell_count;
@@ -304,7 +307,7 @@ int launch_step_kernel(cdb_sim *sim, unsigned flags, double dt_min, double dt_ma
         return CDB_OK;
     }
     const StepArgs a = step_args(sim, flags, dt_min, dt_max, dt_log);
-    const int smem = (STEP_THREADS / 32) * LCAP * 32 * (int)sizeof(int);
+    const int smem = 0;
     if (sim->model == CDB_MODEL_CIRCULAR) LAUNCH(sim, k_step<0>, cdiv(sim->n, STEP_THREADS), STEP_THREADS, smem, a);
     else LAUNCH(sim, k_step<1>, cdiv(sim->n, STEP_THREADS), STEP_THREADS, smem, a);
     CK(cudaGetLastError());
@@ -371,7 +374,7 @@ int cdb_create(int device, int model, int64_t capacity, cdb_sim **out) {
     sim->model = model;
     sim->itemsize = model == CDB_MODEL_CIRCULAR ? 228 : 316;
     sim->n_planes = model == CDB_MODEL_CIRCULAR ? NP_CIRC : NP_THREE;
-    sim->n_alloc_planes = model == CDB_MODEL_CIRCULAR ? NP_CIRC : NP_THREE_ALL;
+    sim->n_alloc_planes = sim->n_planes;
     int rc = [&]() -> int {
         CK(cudaStreamCreateWithFlags(&sim->stream, cudaStreamNonBlocking));
         sim->own_stream = true;
@@ -403,7 +406,7 @@ int cdb_destroy(cdb_sim *sim) {
     free_soa(sim->cur); free_soa(sim->alt);
     cudaFree(sim->d_aos); cudaFreeHost(sim->h_bounce);
     cudaFree(sim->d_grid); cudaFree(sim->d_cell_count); cudaFree(sim->d_cell_start); cudaFree(sim->d_cell_fill);
-    cudaFree(sim->d_cell_of_slot); cudaFree(sim->d_order_tmp); cudaFree(sim->d_order); cudaFree(sim->d_scan_partials);
+    cudaFree(sim->d_cell_of_slot); cudaFree(sim->d_order_tmp); cudaFree(sim->d_order); cudaFree(sim->d_nbr); cudaFree(sim->d_scan_partials);
     cudaFree(sim->d_bbox); cudaFreeHost(sim->h_bbox);
     cudaFree(sim->d_obstacles);
     for (auto &f : sim->nav) { cudaFree((void *)f.U); cudaFree((void *)f.V); }

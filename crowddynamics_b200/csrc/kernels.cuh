@@ -474,10 +474,13 @@ __global__ void k_rank_fix(const int *__restrict__ order_tmp, int n, const int *
     order[b + rank] = src;
 }
 
-// physical reorder into cell order (all record planes), plus the derived planes of the three-circle model:
-// shoulder displacement r_ts (sin phi, -cos phi) (power_law.py:338-350) and a conservative body extent for the prefilter
+// physical reorder into cell order (all record planes) + the packed neighbour records the pair kernel sweeps:
+//   circular      {px, py, vx, vy, radius, -}                                                   48 B
+//   three-circle  {px, py, vx, vy, extent, r_t, r_s, - | lsx, lsy, rsx, rsy, ox, oy, -, -}     128 B (one line)
+// extent = conservative radius of the whole body around the centre (from the STORED shoulder positions), (ox, oy) =
+// r_ts (sin phi, -cos phi), the shoulder displacement of power_law.py:338-350.
 __global__ void k_gather(Soa src, Soa dst, int n, int n_planes, int model, const int *__restrict__ order,
-                         const int *__restrict__ cell_of_slot, int *__restrict__ cell_sorted) {
+                         const int *__restrict__ cell_of_slot, int *__restrict__ cell_sorted, double *__restrict__ nbr) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
     const int o = order[t];
@@ -485,14 +488,19 @@ __global__ void k_gather(Soa src, Soa dst, int n, int n_planes, int model, const
     dst.id[t] = src.id[o];
     dst.target[t] = src.target[o];
     cell_sorted[t] = cell_of_slot[o];
-    if (model == CDB_MODEL_THREE_CIRCLE) {
-        const double phi = src(PHI, o), r_ts = src(R_TS, o);
-        dst(NP_THREE + 0, t) = r_ts * sin(phi);
-        dst(NP_THREE + 1, t) = r_ts * -cos(phi);
-        const double x = src(PX, o), y = src(PY, o);
-        const double dl = hypot(src(LSX, o) - x, src(LSY, o) - y), dr = hypot(src(RSX, o) - x, src(RSY, o) - y);
-        const double ext = fmax(src(R_T, o), fmax(dl, dr) + src(R_S, o));
-        dst(NP_THREE + 2, t) = ext * (1.0 + 1e-12);
+    const double x = src(PX, o), y = src(PY, o), vx = src(VX, o), vy = src(VY, o);
+    if (model == CDB_MODEL_CIRCULAR) {
+        double2 *r = reinterpret_cast<double2 *>(nbr + (size_t)t * 6);
+        r[0] = make_double2(x, y); r[1] = make_double2(vx, vy); r[2] = make_double2(src(RADIUS, o), 0.0);
+    } else {
+        const double phi = src(PHI, o), r_ts = src(R_TS, o), r_t = src(R_T, o), r_s = src(R_S, o);
+        const double lsx = src(LSX, o), lsy = src(LSY, o), rsx = src(RSX, o), rsy = src(RSY, o);
+        const double dl = hypot(lsx - x, lsy - y), dr = hypot(rsx - x, rsy - y);
+        const double ext = fmax(r_t, fmax(dl, dr) + r_s) * (1.0 + 1e-12);
+        double2 *r = reinterpret_cast<double2 *>(nbr + (size_t)t * 16);
+        r[0] = make_double2(x, y); r[1] = make_double2(vx, vy); r[2] = make_double2(ext, r_t); r[3] = make_double2(r_s, 0.0);
+        r[4] = make_double2(lsx, lsy); r[5] = make_double2(rsx, rsy);
+        r[6] = make_double2(r_ts * sin(phi), r_ts * -cos(phi)); r[7] = make_double2(0.0, 0.0);
     }
 }
 
@@ -602,21 +610,23 @@ __device__ __forceinline__ void walls_circular(double px, double py, double r, d
     }
 }
 
-__device__ __forceinline__ void walls_three_circle(const double x[3][2], const double r[3], double vx, double vy, double mu, double kappa,
-                                                   double damping, const double *__restrict__ obs, int n_obs, double &fx, double &fy,
-                                                   double &torque) {
+__device__ __forceinline__ void walls_three_circle(double px, double py, double lsx, double lsy, double rsx, double rsy, double r_t,
+                                                   double r_s, double vx, double vy, double mu, double kappa, double damping,
+                                                   const double *__restrict__ obs, int n_obs, double &fx, double &fy, double &torque) {
     for (int w = 0; w < n_obs; ++w) {
-        double h_min = nan(""), nx = 0.0, ny = 0.0;
-        int i_min = 0;
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {   // distance.py:154-180
+        const double p0x = obs[4 * w], p0y = obs[4 * w + 1], p1x = obs[4 * w + 2], p1y = obs[4 * w + 3];
+        double h_min = nan(""), nx = 0.0, ny = 0.0, sx = 0.0, sy = 0.0, sr = 0.0;
+#pragma unroll 1
+        for (int k = 0; k < 3; ++k) {   // distance.py:154-180: torso, left, right; strict '<', first wins
+            const double xk = k == 0 ? px : (k == 1 ? lsx : rsx), yk = k == 0 ? py : (k == 1 ? lsy : rsy);
+            const double rk = k == 0 ? r_t : r_s;
             double ax, ay;
-            double h = distance_circle_line(x[k][0], x[k][1], r[k], obs[4 * w], obs[4 * w + 1], obs[4 * w + 2], obs[4 * w + 3], ax, ay);
-            if (h < h_min || isnan(h_min)) { h_min = h; nx = ax; ny = ay; i_min = k; }
+            double h = distance_circle_line(xk, yk, rk, p0x, p0y, p1x, p1y, ax, ay);
+            if (h < h_min || isnan(h_min)) { h_min = h; nx = ax; ny = ay; sx = xk; sy = yk; sr = rk; }
         }
         if (h_min < 0.0) {
-            double mx = x[i_min][0] - r[i_min] * nx - x[0][0];
-            double my = x[i_min][1] - r[i_min] * ny - x[0][1];
+            double mx = sx - sr * nx - px;
+            double my = sy - sr * ny - py;
             double cx, cy;
             force_contact(h_min, nx, ny, vx, vy, ny, -nx, mu, kappa, damping, cx, cy);
             fx += cx; fy += cy;
@@ -632,10 +642,9 @@ __global__ void k_agent_obstacle(Soa s, int n, int model, const double *__restri
     if (model == CDB_MODEL_CIRCULAR) {
         walls_circular(s(PX, i), s(PY, i), s(RADIUS, i), s(VX, i), s(VY, i), s(MU, i), s(KAPPA, i), s(DAMPING, i), obs, n_obs, fx, fy);
     } else {
-        double x[3][2] = {{s(PX, i), s(PY, i)}, {s(LSX, i), s(LSY, i)}, {s(RSX, i), s(RSY, i)}};
-        double r[3] = {s(R_T, i), s(R_S, i), s(R_S, i)};
         double tq = s(TORQUE, i);
-        walls_three_circle(x, r, s(VX, i), s(VY, i), s(MU, i), s(KAPPA, i), s(DAMPING, i), obs, n_obs, fx, fy, tq);
+        walls_three_circle(s(PX, i), s(PY, i), s(LSX, i), s(LSY, i), s(RSX, i), s(RSY, i), s(R_T, i), s(R_S, i), s(VX, i), s(VY, i),
+                           s(MU, i), s(KAPPA, i), s(DAMPING, i), obs, n_obs, fx, fy, tq);
         s(TORQUE, i) = tq;
     }
     s(FX, i) = fx; s(FY, i) = fy;

@@ -1,30 +1,42 @@
 // step_kernel.cuh -- the fused per-agent step kernel (navigation sample, orientation, adjusting, agent-agent,
-// agent-obstacle, adaptive-dt velocity Verlet, reset) over cell-sorted SoA state.
+// agent-obstacle, adaptive-dt velocity Verlet, reset) over cell-sorted state.
 //
-// Agent-agent part, one thread per cell-sorted agent ("me"), two phases per warp:
-//   phase 1 (classify)  sweep the three neighbour cell-columns; for every candidate decide with a handful of fp64
-//                       operations and NO sqrt/div/hypot whether the pair can contribute a force at all:
-//                         - conservative sight gate     d^2 <= (3 + r_tot)^2 (1 + eps)
-//                         - the reference's own time-to-collision quantities a, b, c, disc = b*b - a*c, computed with the
-//                           reference's exact operation order, so "disc > 0 and b > 0" is EXACTLY the necessary condition for
-//                           its social force to be non-zero (power_law.py:236-246), or
-//                         - conservative contact test   d^2 <= r_tot^2 (1 + eps)
-//                       survivors (about 3-5 of ~115 candidates at 1 agent/m^2) are appended to a per-lane list in shared
-//                       memory;
-//   phase 2 (evaluate)  every lane runs the exact reference pair arithmetic (gate with hypot, tau, gradient, exp, truncation,
-//                       contact, torque) on its short list.
-// A pair dropped in phase 1 contributes exactly (0, 0) in the reference as well, so results are identical to evaluating
-// every candidate; the expensive, divergent part runs on ~4 % of the candidates instead of all of them.
+// Agent-agent part: one thread per cell-sorted agent ("target"), one warp per 32 consecutive targets, two phases.
+//
+//   phase 1 (classify)  every lane sweeps the three neighbour cell-columns of its own target, reading the candidates'
+//                       packed neighbour records (48 B circular / first 64 B of 128 B three-circle; built by k_gather), and
+//                       decides with ~25 branch-free fp64 operations -- no sqrt, div or hypot -- whether the pair can
+//                       contribute a force at all:
+//                         gate     d^2 <= (3 + R)^2 (1 + eps)            conservative form of  h < SIGTH_SOC
+//                         contact  d^2 <= R^2 (1 + eps)                  conservative form of  h < 0
+//                         social   disc > 0 and b > 0   (circular: the reference's own a, b, c, disc = b*b - a*c, computed
+//                                  with its exact operation order, so this is exactly the necessary condition for a
+//                                  non-zero social force, power_law.py:236-246);
+//                                  three-circle: the same test on the bounding circles (R = sum of body extents), which
+//                                  contains every one of the 9 part pairs of power_law.py:308-329.
+//                       Survivors (3-6 of ~115 candidates at 1 agent/m^2) go to a per-lane list in shared memory.
+//   phase 2 (evaluate)  the ragged per-lane lists are flattened and dealt out evenly over the 32 lanes; each lane runs the
+//                       exact reference pair arithmetic (hypot gate, tau, gradient, exp, truncation, contact, torque) for
+//                       whichever (target, neighbour) it was dealt, and the target lanes add up their results in list
+//                       order -- deterministic, independent of how the work was dealt.
+// A pair dropped in phase 1 contributes exactly (0, 0) in the reference too, so results equal evaluating every candidate.
 #pragma once
 #include "kernels.cuh"
 
 constexpr int STEP_THREADS = 128;
-constexpr int LCAP = 32;     // survivor list entries per lane
-constexpr int CHUNK = 8;     // candidates classified between two list-capacity checks
+constexpr int STEP_WARPS = STEP_THREADS / 32;
+constexpr int LCAP = 16;     // survivor list entries per lane between two flushes
+constexpr int CHUNK = 4;     // candidates classified between two list-capacity checks
 #define PREFILTER_EPS 1e-12
+#define BOUND_EPS 1e-9
+
+// packed neighbour records (doubles per agent)
+constexpr int REC_CIRC = 6;     // px py vx vy r -
+constexpr int REC_THREE = 16;   // px py vx vy ext rt rs - | lsx lsy rsx rsy ox oy - -
 
 struct StepArgs {
     Soa in, out;             // out == in unless integrating (then the new state is written to the other buffer)
+    const double *nbr;       // packed neighbour records of `in`
     int n;
     const Grid *grid;
     const int *cell_sorted, *cell_start, *cell_count;
@@ -39,34 +51,47 @@ struct StepArgs {
     double *dt_log;          // where to log this step's dt (or nullptr)
 };
 
+struct WarpSmem {
+    int list[LCAP * 32];     // entry k of lane l at list[k * 32 + l]
+    int pre[33];             // exclusive prefix of the per-lane counts, pre[32] = total
+    double res[3][32];       // results of one dealt round
+};
+
+__device__ __forceinline__ double2 ldg2(const double *p) { return __ldg(reinterpret_cast<const double2 *>(p)); }
+
 // ---- exact three-circle pair in the reference's (i, j) orientation, register-only (no dynamic indexing) ---------------
 struct Three {               // kinematics of one three-circle agent as the pair kernels need them
-    double x[3], y[3];       // torso, left shoulder, right shoulder centres
+    double x0, y0, x1, y1, x2, y2;   // torso, left shoulder, right shoulder centres
     double rt, rs;           // torso / shoulder radius
     double vx, vy;
     double ox, oy;           // r_ts * (sin(phi), -cos(phi)): shoulder displacement (power_law.py:338-350, agents.py:483-484)
 };
 
+__device__ __forceinline__ double sel3(int k, double a, double b, double c) { return k == 0 ? a : (k == 1 ? b : c); }
+
 __device__ __forceinline__ void pair_three_exact(const Three &I, const Three &J, bool me_is_i, const ThreePar &me,
                                                  double &fx, double &fy, double &torque) {
-    const double ri[3] = {I.rt, I.rs, I.rs}, rj[3] = {J.rt, J.rs, J.rs};
+    const double jx[3] = {J.x0, J.x1, J.x2}, jy[3] = {J.y0, J.y1, J.y2}, rj[3] = {J.rt, J.rs, J.rs};
+    const double ixs[3] = {I.x0, I.x1, I.x2}, iys[3] = {I.y0, I.y1, I.y2};   // statically indexed only (pj unrolled)
     // distance_three_circles (distance.py:55-105): strict '<', first wins, order torso, left, right
     double h_min = nan(""), sx = 0.0, sy = 0.0, sd = 0.0;   // selected x, y, d (normal = x / d computed once, same value)
     double mix = 0.0, miy = 0.0, mir = 0.0;                  // x0[i_min], r0[i_min]
     double qx = 0.0, qy = 0.0, mjr = 0.0;                    // x0[j_min] (the :103 quirk), r1[j_min]
-#pragma unroll
-    for (int pi = 0; pi < 3; ++pi)
+#pragma unroll 1
+    for (int pi = 0; pi < 3; ++pi) {
+        const double xi = sel3(pi, I.x0, I.x1, I.x2), yi = sel3(pi, I.y0, I.y1, I.y2), rip = pi == 0 ? I.rt : I.rs;
 #pragma unroll
         for (int pj = 0; pj < 3; ++pj) {
-            double x = I.x[pi] - J.x[pj], y = I.y[pi] - J.y[pj];
+            double x = xi - jx[pj], y = yi - jy[pj];
             double d = hypot(x, y);
-            double h = d - (ri[pi] + rj[pj]);
+            double h = d - (rip + rj[pj]);
             if (h < h_min || isnan(h_min)) {
                 h_min = h; sx = x; sy = y; sd = d;
-                mix = I.x[pi]; miy = I.y[pi]; mir = ri[pi];
-                qx = I.x[pj]; qy = I.y[pj]; mjr = rj[pj];
+                mix = xi; miy = yi; mir = rip;
+                qx = ixs[pj]; qy = iys[pj]; mjr = rj[pj];
             }
         }
+    }
     if (!(h_min < SIGTH_SOC)) return;
     double nx = 0.0, ny = 0.0;
     if (sd != 0.0) { nx = sx / sd; ny = sy / sd; }
@@ -78,34 +103,34 @@ __device__ __forceinline__ void pair_three_exact(const Three &I, const Three &J,
         // `isnan(tau) or 0 < tau_new < tau`.  tau_new = (b - d) / a is monotone in its numerator, so the division is only
         // needed when the numerator is positive and smaller than the selected one -- same decisions, fewer divisions.
         double tau = nan(""), num_sel = 0.0, b_min = 0.0, d_min = 0.0, oix = 0.0, oiy = 0.0, ojx = 0.0, ojy = 0.0;
-#pragma unroll
-        for (int pi = 0; pi < 3; ++pi)
+#pragma unroll 1
+        for (int pi = 0; pi < 3; ++pi) {
+            const double xi = sel3(pi, I.x0, I.x1, I.x2), yi = sel3(pi, I.y0, I.y1, I.y2), rip = pi == 0 ? I.rt : I.rs;
 #pragma unroll
             for (int pj = 0; pj < 3; ++pj) {
-                double x = I.x[pi] - J.x[pj], y = I.y[pi] - J.y[pj];
-                double r_tot = ri[pi] + rj[pj];
+                double x = xi - jx[pj], y = yi - jy[pj];
+                double r_tot = rip + rj[pj];
                 double b = -(x * vx + y * vy);
                 double c = (x * x + y * y) - r_tot * r_tot;
                 double disc = b * b - a * c;
                 if (!(disc > 0.0)) continue;         // sqrt gives NaN (disc < 0 or NaN) or 0
                 double dd = sqrt(disc);
                 double num = b - dd;
-                bool take;
-                double tau_new;
+                bool take = false;
+                double tau_new = 0.0;
                 if (isnan(tau)) { tau_new = num / a; take = true; }
                 else if (num > 0.0 && num < num_sel) { tau_new = num / a; take = 0.0 < tau_new && tau_new < tau; }
-                else { tau_new = 0.0; take = false; }
                 if (take) {
                     tau = tau_new; num_sel = num; b_min = b; d_min = dd;
                     // shoulder displacement of the contacting parts: 0 for the torso, +o for left, -o for right
-                    oix = pi == 0 ? 0.0 : (pi == 1 ? I.ox : 0.0 - I.ox);
-                    oiy = pi == 0 ? 0.0 : (pi == 1 ? I.oy : 0.0 - I.oy);
+                    oix = sel3(pi, 0.0, I.ox, 0.0 - I.ox); oiy = sel3(pi, 0.0, I.oy, 0.0 - I.oy);
                     ojx = pj == 0 ? 0.0 : (pj == 1 ? J.ox : 0.0 - J.ox);
                     ojy = pj == 0 ? 0.0 : (pj == 1 ? J.oy : 0.0 - J.oy);
                 }
             }
+        }
         if (!(isnan(tau) || tau <= 0.0)) {
-            double xr = I.x[0] - J.x[0], yr = I.y[0] - J.y[0];
+            double xr = I.x0 - J.x0, yr = I.y0 - J.y0;
             double ox = oix - ojx, oy = oiy - ojy;
             double gx = (vx - (a * (xr + 2 * ox) + b_min * vx) / d_min) / a;   // power_law.py:131-149
             double gy = (vy - (a * (yr + 2 * oy) + b_min * vy) / d_min) / a;
@@ -123,186 +148,207 @@ __device__ __forceinline__ void pair_three_exact(const Three &I, const Three &J,
         if (me_is_i) { fsx += cx; fsy += cy; } else { fsx -= cx; fsy -= cy; }
     }
     double mx, my;   // moment arms, distance.py:102-103
-    if (me_is_i) { mx = mix + mir * nx - I.x[0]; my = miy + mir * ny - I.y[0]; }
-    else { mx = qx - mjr * nx - J.x[0]; my = qy - mjr * ny - J.y[0]; }
+    if (me_is_i) { mx = mix + mir * nx - I.x0; my = miy + mir * ny - I.y0; }
+    else { mx = qx - mjr * nx - J.x0; my = qy - mjr * ny - J.y0; }
     fx += fsx; fy += fsy;
     torque += mx * fsy - my * fsx;
 }
 
-__device__ __forceinline__ void load_three(const Soa &s, int ox_plane, int u, Three &k) {
-    k.x[0] = __ldg(&s(PX, u)); k.y[0] = __ldg(&s(PY, u));
-    k.x[1] = __ldg(&s(LSX, u)); k.y[1] = __ldg(&s(LSY, u));
-    k.x[2] = __ldg(&s(RSX, u)); k.y[2] = __ldg(&s(RSY, u));
-    k.rt = __ldg(&s(R_T, u)); k.rs = __ldg(&s(R_S, u));
-    k.vx = __ldg(&s(VX, u)); k.vy = __ldg(&s(VY, u));
-    k.ox = __ldg(&s(ox_plane, u)); k.oy = __ldg(&s(ox_plane + 1, u));
+__device__ __forceinline__ void sel_three(bool first, const Three &a, const Three &b, Three &o) {
+    o.x0 = first ? a.x0 : b.x0; o.y0 = first ? a.y0 : b.y0; o.x1 = first ? a.x1 : b.x1; o.y1 = first ? a.y1 : b.y1;
+    o.x2 = first ? a.x2 : b.x2; o.y2 = first ? a.y2 : b.y2; o.rt = first ? a.rt : b.rt; o.rs = first ? a.rs : b.rs;
+    o.vx = first ? a.vx : b.vx; o.vy = first ? a.vy : b.vy; o.ox = first ? a.ox : b.ox; o.oy = first ? a.oy : b.oy;
 }
 
-// derived planes of the three-circle model (filled by k_gather every step)
-enum { D_OX = NP_THREE, D_OY, D_EXT, NP_THREE_ALL };
-
-// ---- phase-1 classifiers ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ bool classify_circular(const CircMe &me, const Soa &s, int u) {
-    const double x = me.px - __ldg(&s(PX, u)), y = me.py - __ldg(&s(PY, u));
-    const double r_tot = me.r + __ldg(&s(RADIUS, u));
-    const double d2 = x * x + y * y;
-    const double lim = SIGTH_SOC + r_tot;
-    if (!(d2 <= lim * lim * (1.0 + PREFILTER_EPS))) return false;
-    const double vx = me.vx - __ldg(&s(VX, u)), vy = me.vy - __ldg(&s(VY, u));
-    const double a = vx * vx + vy * vy;
-    const double b = -(x * vx + y * vy);
-    const double rr = r_tot * r_tot;
-    const double c = d2 - rr;
-    const double disc = b * b - a * c;
-    return (disc > 0.0 && b > 0.0) || d2 <= rr * (1.0 + PREFILTER_EPS);
-}
-
-__device__ __forceinline__ bool classify_three(const Three &me, double me_ext, bool me_is_i, const Soa &s, int u) {
-    const double x = me.x[0] - __ldg(&s(PX, u)), y = me.y[0] - __ldg(&s(PY, u));
-    const double e_tot = me_ext + __ldg(&s(D_EXT, u));
-    const double d2 = x * x + y * y;
-    const double lim = SIGTH_SOC + e_tot;
-    if (!(d2 <= lim * lim * (1.0 + PREFILTER_EPS))) return false;
-    if (d2 <= e_tot * e_tot * (1.0 + PREFILTER_EPS)) return true;          // may touch: contact branch possible
-    const double vx = me.vx - __ldg(&s(VX, u)), vy = me.vy - __ldg(&s(VY, u));
-    const double a = vx * vx + vy * vy;
-    if (a == 0.0) return false;
-    const double ux[3] = {__ldg(&s(PX, u)), __ldg(&s(LSX, u)), __ldg(&s(RSX, u))};
-    const double uy[3] = {__ldg(&s(PY, u)), __ldg(&s(LSY, u)), __ldg(&s(RSY, u))};
-    const double urt = __ldg(&s(R_T, u)), urs = __ldg(&s(R_S, u));
-    const double mr[3] = {me.rt, me.rs, me.rs}, ur[3] = {urt, urs, urs};
-    // The reference's loop (power_law.py:308-329) lets the FIRST part pair with a real, non-zero discriminant fix the sign
-    // of tau for good, so the social force is non-zero only if that first pair has b - d > 0, for which b > 0 is necessary.
-    // (x_rel, v_rel) -> (-x_rel, -v_rel) leaves b, c, disc bitwise unchanged, so only the enumeration order depends on who is i.
-#pragma unroll
-    for (int k = 0; k < 9; ++k) {
-        const int hi = k / 3, lo = k % 3;
-        const double mx = me_is_i ? me.x[hi] : me.x[lo], my = me_is_i ? me.y[hi] : me.y[lo];
-        const double mrr = me_is_i ? mr[hi] : mr[lo];
-        const double oxx = me_is_i ? ux[lo] : ux[hi], oyy = me_is_i ? uy[lo] : uy[hi];
-        const double orr = me_is_i ? ur[lo] : ur[hi];
-        const double xr = mx - oxx, yr = my - oyy;
-        const double r_tot = me_is_i ? (mrr + orr) : (orr + mrr);
-        const double b = -(xr * vx + yr * vy);
-        const double c = (xr * xr + yr * yr) - r_tot * r_tot;
-        const double disc = b * b - a * c;
-        if (disc > 0.0) return b > 0.0;
-    }
-    return false;
+__device__ __forceinline__ void load_three_rec(const double *__restrict__ nbr, int u, Three &k) {
+    const double *r = nbr + (size_t)u * REC_THREE;
+    const double2 a = ldg2(r), b = ldg2(r + 2), c = ldg2(r + 4), d = ldg2(r + 6), e = ldg2(r + 8), f = ldg2(r + 10), g = ldg2(r + 12);
+    k.x0 = a.x; k.y0 = a.y; k.vx = b.x; k.vy = b.y; k.rt = c.y; k.rs = d.x;
+    k.x1 = e.x; k.y1 = e.y; k.x2 = f.x; k.y2 = f.y; k.ox = g.x; k.oy = g.y;
 }
 
 // =====================================================================================================================
 template <int MODEL>
 __global__ void __launch_bounds__(STEP_THREADS) k_step(const StepArgs A) {
-    extern __shared__ int s_list[];
+    __shared__ WarpSmem s_warp[STEP_WARPS];
     const int t = blockIdx.x * STEP_THREADS + threadIdx.x;
     const int lane = threadIdx.x & 31;
-    int *list = s_list + (threadIdx.x >> 5) * (LCAP * 32) + lane;   // entry k of this lane at list[k * 32]
+    WarpSmem &W = s_warp[threadIdx.x >> 5];
+    const int t0 = t - lane;             // first target of this warp
     const bool active = t < A.n;
     const Soa &s = A.in;
     const unsigned FULL = 0xffffffffu;
-    const int tt = active ? t : 0;     // inactive lanes read slot 0 and never write
-
-    // ---- own state -----------------------------------------------------------------------------------------------------
-    const double px = s(PX, tt), py = s(PY, tt), vx = s(VX, tt), vy = s(VY, tt);
-    const double mass = s(MASS, tt);
-    const ThreePar par = {mass, s(K_SOC, tt), s(TAU_0, tt), s(MU, tt), s(KAPPA, tt), s(DAMPING, tt)};
-    double e0x = s(E0X, tt), e0y = s(E0Y, tt);
-    double fx = s(FX, tt), fy = s(FY, tt), tq = 0.0, phi0 = 0.0;
-    CircMe cme;
-    Three tme;
-    double t_ext = 0.0;
-    if (MODEL == 0) {
-        cme = CircMe{px, py, vx, vy, s(RADIUS, tt), mass, par.k_soc, par.tau_0, par.mu, par.kappa, par.damping};
-    } else {
-        load_three(s, D_OX, tt, tme);
-        t_ext = s(D_EXT, tt);
-        tq = s(TORQUE, tt);
-        phi0 = s(PHI0, tt);
-    }
+    const int tt = active ? t : 0;       // inactive lanes read slot 0 and never write
+    constexpr int REC = MODEL == 0 ? REC_CIRC : REC_THREE;
 
     // ---- Navigation, Orientation, Adjusting (logic.py:149-165,258-261,89-94) --------------------------------------------
-    if (A.flags & CDB_STEP_NAVIGATION) navigation_sample(A.nav, A.n_nav, s.target[tt], px, py, e0x, e0y);
-    if (MODEL == 1 && (A.flags & CDB_STEP_ORIENTATION)) phi0 = atan2(e0y, e0x);
-    if (A.flags & CDB_STEP_ADJUSTING) {
-        double ax, ay;
-        adjust_force(mass, s(TAU_ADJ, tt), s(V0, tt), e0x, e0y, vx, vy, ax, ay);
-        fx += ax; fy += ay;
-        if (MODEL == 1) tq += adjust_torque(s(INERTIA, tt), s(TAU_ROT, tt), phi0, s(PHI, tt), s(OMEGA0, tt), s(OMEGA, tt));
+    double e0x = s(E0X, tt), e0y = s(E0Y, tt);
+    double fx = s(FX, tt), fy = s(FY, tt), tq = 0.0, phi0 = 0.0;
+    if (MODEL == 1) { tq = s(TORQUE, tt); phi0 = s(PHI0, tt); }
+    {
+        const double px = s(PX, tt), py = s(PY, tt);
+        if (A.flags & CDB_STEP_NAVIGATION) navigation_sample(A.nav, A.n_nav, s.target[tt], px, py, e0x, e0y);
+        if (MODEL == 1 && (A.flags & CDB_STEP_ORIENTATION)) phi0 = atan2(e0y, e0x);
+        if (A.flags & CDB_STEP_ADJUSTING) {
+            double ax, ay;
+            adjust_force(s(MASS, tt), s(TAU_ADJ, tt), s(V0, tt), e0x, e0y, s(VX, tt), s(VY, tt), ax, ay);
+            fx += ax; fy += ay;
+            if (MODEL == 1) tq += adjust_torque(s(INERTIA, tt), s(TAU_ROT, tt), phi0, s(PHI, tt), s(OMEGA0, tt), s(OMEGA, tt));
+        }
     }
 
     // ---- AgentAgentInteractions (interactions.py:191-205) -----------------------------------------------------------------
     if (A.flags & CDB_STEP_AGENT_AGENT) {
-        const Grid g = *A.grid;
-        const int ny = (int)g.ny, nxg = (int)g.nx;
+        const double *__restrict__ nbr = A.nbr;
+        // what phase 1 needs of the target: centre, velocity, radius (circular) / body extent (three-circle)
+        double mpx, mpy, mvx, mvy, mr;
+        {
+            const double *r = nbr + (size_t)tt * REC;
+            const double2 p = ldg2(r), v = ldg2(r + 2);
+            mpx = p.x; mpy = p.y; mvx = v.x; mvy = v.y; mr = __ldg(r + 4);
+        }
+        const int ny = (int)A.grid->ny, nxg = (int)A.grid->nx;
         const int c = A.cell_sorted[tt];
         const int cx = c / ny, cy = c - cx * ny;
         const int ylo = cy > 0 ? cy - 1 : 0, yhi = cy + 1 < ny ? cy + 1 : ny - 1;
         int cnt = 0;
 
         auto flush = [&]() {
-            const int m = __reduce_max_sync(FULL, cnt);
-            for (int k = 0; k < m; ++k) {
-                if (k < cnt) {
-                    const int u = list[k * 32];
+            // flatten the ragged lists: pre[l] = first flattened index of lane l
+            int incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { int w = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += w; }
+            const int total = __shfl_sync(FULL, incl, 31);
+            const int mypre = incl - cnt;
+            W.pre[lane] = mypre;
+            if (lane == 31) W.pre[32] = total;
+            __syncwarp();
+            for (int r0 = 0; r0 < total; r0 += 32) {
+                const int f = r0 + lane;
+                double rfx = 0.0, rfy = 0.0, rtq = 0.0;
+                if (f < total) {
+                    int l = 0;   // largest l with pre[l] <= f (lanes with empty lists share a prefix value: skipped by '<=')
+#pragma unroll
+                    for (int o = 16; o; o >>= 1) if (W.pre[l + o] <= f) l += o;
+                    const int u = W.list[(f - W.pre[l]) * 32 + l];
+                    const int tg = t0 + l;    // the target this entry belongs to
+                    const ThreePar par = {s(MASS, tg), s(K_SOC, tg), s(TAU_0, tg), s(MU, tg), s(KAPPA, tg), s(DAMPING, tg)};
                     if (MODEL == 0) {
-                        pair_circular(cme, __ldg(&s(PX, u)), __ldg(&s(PY, u)), __ldg(&s(VX, u)), __ldg(&s(VY, u)),
-                                      __ldg(&s(RADIUS, u)), fx, fy);
+                        const double *rm = nbr + (size_t)tg * REC, *ro = nbr + (size_t)u * REC;
+                        const double2 p = ldg2(rm), v = ldg2(rm + 2), po = ldg2(ro), vo = ldg2(ro + 2);
+                        const CircMe me = {p.x, p.y, v.x, v.y, __ldg(rm + 4), par.mass, par.k_soc, par.tau_0, par.mu, par.kappa, par.damping};
+                        pair_circular(me, po.x, po.y, vo.x, vo.y, __ldg(ro + 4), rfx, rfy);
                     } else {
-                        Three other;
-                        load_three(s, D_OX, u, other);
+                        Three me, other;
+                        load_three_rec(nbr, tg, me);
+                        load_three_rec(nbr, u, other);
                         // reference pair orientation: i is the lexicographically smaller (cell_x, cell_y, agent index),
                         // which is exactly the order of the cell-sorted slots
-                        if (t < u) pair_three_exact(tme, other, true, par, fx, fy, tq);
-                        else pair_three_exact(other, tme, false, par, fx, fy, tq);
+                        const bool me_is_i = tg < u;
+                        Three I, J;     // one inlined copy of the pair arithmetic: select the roles instead of branching
+                        sel_three(me_is_i, me, other, I);
+                        sel_three(me_is_i, other, me, J);
+                        pair_three_exact(I, J, me_is_i, par, rfx, rfy, rtq);
                     }
                 }
+                W.res[0][lane] = rfx; W.res[1][lane] = rfy;
+                if (MODEL == 1) W.res[2][lane] = rtq;
+                __syncwarp();
+                // every target adds up its own entries of this round, in list order
+                const int lo = max(mypre, r0) - r0, hi = min(mypre + cnt, r0 + 32) - r0;
+                const int span = __reduce_max_sync(FULL, hi - lo);
+                for (int k = 0; k < span; ++k)
+                    if (lo + k < hi) {
+                        fx += W.res[0][lo + k]; fy += W.res[1][lo + k];
+                        if (MODEL == 1) tq += W.res[2][lo + k];
+                    }
+                __syncwarp();
             }
             cnt = 0;
         };
 
-#pragma unroll 1
-        for (int dx = -1; dx <= 1; ++dx) {
-            const int x2 = cx + dx;
-            int b = 0, e = 0;
-            if (active && x2 >= 0 && x2 < nxg) {
-                b = A.cell_start[x2 * ny + ylo];
-                e = A.cell_start[x2 * ny + yhi] + A.cell_count[x2 * ny + yhi];
-            }
-            const int maxlen = __reduce_max_sync(FULL, e - b);
-#pragma unroll 1
-            for (int k0 = 0; k0 < maxlen; k0 += CHUNK) {
-                if (__any_sync(FULL, cnt > LCAP - CHUNK)) flush();
+        // classify until some list is nearly full or all three cell-columns are done, then evaluate; repeat.
+        // (one flush call site: the pair arithmetic is inlined exactly once)
+        int dx = -1, b = 0, e = 0, maxlen = 0, k0 = 0;
+        bool have_col = false, done = false;
+        do {
+            while (true) {
+                if (!have_col) {
+                    if (dx > 1) { done = true; break; }
+                    const int x2 = cx + dx;
+                    b = 0; e = 0;
+                    if (active && x2 >= 0 && x2 < nxg) {
+                        b = A.cell_start[x2 * ny + ylo];
+                        e = A.cell_start[x2 * ny + yhi] + A.cell_count[x2 * ny + yhi];
+                    }
+                    maxlen = __reduce_max_sync(FULL, e - b);
+                    k0 = 0;
+                    have_col = true;
+                }
+                if (k0 >= maxlen) { have_col = false; ++dx; continue; }
+                if (__any_sync(FULL, cnt > LCAP - CHUNK)) break;
+                bool keep[CHUNK];
 #pragma unroll
                 for (int kk = 0; kk < CHUNK; ++kk) {
                     const int u = b + k0 + kk;
-                    if (u < e && u != t) {
-                        const bool keep = MODEL == 0 ? classify_circular(cme, s, u) : classify_three(tme, t_ext, t < u, s, u);
-                        if (keep) { list[cnt * 32] = u; ++cnt; }
+                    const bool inr = u < e;
+                    const double *r = nbr + (size_t)(inr ? u : tt) * REC;
+                    const double2 p = ldg2(r), v = ldg2(r + 2);
+                    const double ro = __ldg(r + 4);
+                    const double x = mpx - p.x, y = mpy - p.y;
+                    const double R = mr + ro;                    // r_tot (circular) / sum of body extents (three-circle)
+                    const double d2 = x * x + y * y;
+                    const double lim = SIGTH_SOC + R;
+                    const double RR = R * R;
+                    const bool gate = d2 <= lim * lim * (1.0 + PREFILTER_EPS);
+                    const bool contact = d2 <= RR * (1.0 + PREFILTER_EPS);
+                    const double vx = mvx - v.x, vy = mvy - v.y;
+                    const double a = vx * vx + vy * vy;
+                    const double bb = -(x * vx + y * vy);
+                    bool social;
+                    if (MODEL == 0) {
+                        const double cc = d2 - RR;
+                        const double disc = bb * bb - a * cc;
+                        social = disc > 0.0 && bb > 0.0;
+                    } else {
+                        // bounding circles (inflated by BOUND_EPS so that rounding in the exact per-part discriminants
+                        // cannot matter): no real root for them => none for any part pair; all part pairs receding
+                        // (b_k <= b + R |v| <= 0) => no positive time-to-collision
+                        const double Rs = R * (1.0 + BOUND_EPS), RRs = Rs * Rs;
+                        const double disc = bb * bb - a * (d2 - RRs);
+                        social = disc >= 0.0 && (bb >= 0.0 || bb * bb <= RRs * a);
                     }
+                    keep[kk] = inr && u != t && gate && (social || contact);
                 }
+#pragma unroll
+                for (int kk = 0; kk < CHUNK; ++kk)
+                    if (keep[kk]) { W.list[cnt * 32 + lane] = b + k0 + kk; ++cnt; }
+                k0 += CHUNK;
             }
-        }
-        flush();
+            flush();
+        } while (!done);
     }
     if (!active) return;
+
+    // ---- own state for the wall and integrator parts ------------------------------------------------------------------------
+    const double px = s(PX, t), py = s(PY, t), vx = s(VX, t), vy = s(VY, t), mass = s(MASS, t);
+    const double mu = s(MU, t), kappa = s(KAPPA, t), damping = s(DAMPING, t);
 
     // ---- AgentObstacleInteractions (interactions.py:208-214) ---------------------------------------------------------------
     if ((A.flags & CDB_STEP_AGENT_OBSTACLE) && A.n_obs > 0) {
         if (MODEL == 0) {
-            walls_circular(px, py, cme.r, vx, vy, par.mu, par.kappa, par.damping, A.obs, A.n_obs, fx, fy);
+            walls_circular(px, py, s(RADIUS, t), vx, vy, mu, kappa, damping, A.obs, A.n_obs, fx, fy);
         } else {
-            const double x[3][2] = {{tme.x[0], tme.y[0]}, {tme.x[1], tme.y[1]}, {tme.x[2], tme.y[2]}};
-            const double r[3] = {tme.rt, tme.rs, tme.rs};
-            walls_three_circle(x, r, vx, vy, par.mu, par.kappa, par.damping, A.obs, A.n_obs, fx, fy, tq);
+            walls_three_circle(px, py, s(LSX, t), s(LSY, t), s(RSX, t), s(RSY, t), s(R_T, t), s(R_S, t), vx, vy, mu, kappa, damping,
+                               A.obs, A.n_obs, fx, fy, tq);
         }
     }
 
     const Soa &o = A.out;
+    const bool rst = A.flags & CDB_STEP_RESET;
     if (!(A.flags & CDB_STEP_INTEGRATOR)) {
         // node-wise use: publish what the selected nodes wrote, in place
         o(E0X, t) = e0x; o(E0Y, t) = e0y;
-        const bool rst = A.flags & CDB_STEP_RESET;
         o(FX, t) = rst ? 0.0 : fx; o(FY, t) = rst ? 0.0 : fy;
         if (MODEL == 1) { o(PHI0, t) = phi0; o(TORQUE, t) = rst ? 0.0 : tq; }
         return;
@@ -317,13 +363,12 @@ __global__ void __launch_bounds__(STEP_THREADS) k_step(const StepArgs A) {
     double nvx = vx, nvy = vy, npx = px, npy = py;
     verlet(fx, s(FPX, t), mass, dt, nvx, npx);
     verlet(fy, s(FPY, t), mass, dt, nvy, npy);
-    const bool rst = A.flags & CDB_STEP_RESET;
     o(PX, t) = npx; o(PY, t) = npy; o(VX, t) = nvx; o(VY, t) = nvy;
     o(E0X, t) = e0x; o(E0Y, t) = e0y;
     o(FX, t) = rst ? 0.0 : fx; o(FY, t) = rst ? 0.0 : fy;
     o(FPX, t) = fx; o(FPY, t) = fy;
     o(RADIUS, t) = s(RADIUS, t); o(MASS, t) = mass; o(V0, t) = s(V0, t); o(TAU_ADJ, t) = s(TAU_ADJ, t);
-    o(K_SOC, t) = par.k_soc; o(TAU_0, t) = par.tau_0; o(MU, t) = par.mu; o(KAPPA, t) = par.kappa; o(DAMPING, t) = par.damping;
+    o(K_SOC, t) = s(K_SOC, t); o(TAU_0, t) = s(TAU_0, t); o(MU, t) = mu; o(KAPPA, t) = kappa; o(DAMPING, t) = damping;
     o.id[t] = s.id[t];
     o.target[t] = s.target[t];
     if (MODEL == 1) {
@@ -333,7 +378,7 @@ __global__ void __launch_bounds__(STEP_THREADS) k_step(const StepArgs A) {
         phi = wrap_to_pi(phi);
         const double ox = sin(phi) * r_ts, oy = -cos(phi) * r_ts;   // shoulders(), agents.py:473-486
         o(LSX, t) = npx - ox; o(LSY, t) = npy - oy; o(RSX, t) = npx + ox; o(RSY, t) = npy + oy;
-        o(R_T, t) = tme.rt; o(R_S, t) = tme.rs; o(R_TS, t) = r_ts; o(INERTIA, t) = inertia; o(OMEGA0, t) = s(OMEGA0, t);
+        o(R_T, t) = s(R_T, t); o(R_S, t) = s(R_S, t); o(R_TS, t) = r_ts; o(INERTIA, t) = inertia; o(OMEGA0, t) = s(OMEGA0, t);
         o(PHI, t) = phi; o(OMEGA, t) = w; o(PHI0, t) = phi0;
         o(TORQUE, t) = rst ? 0.0 : tq; o(TORQUE_PREV, t) = tq; o(TAU_ROT, t) = s(TAU_ROT, t);
     }
