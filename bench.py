@@ -206,7 +206,7 @@ def main():
 
     if world > 1:
         from crowddynamics_b200.parallel import StripSimulation
-        sim = StripSimulation.synthetic(args.model, n, args.density, rank, world, local_rank, seed=rank)
+        sim = StripSimulation.synthetic(args.model, n, args.density, rank, world, local_rank, seed=rank, dist=dist)
         step_fn, dev = sim.step, sim.dev
         n_local = sim.n_owned
     else:

@@ -72,17 +72,16 @@ def _signatures(L):
         'cdb_get_neighbor_pairs': (i32, [vp, vp, i64, pi64]),
         'cdb_set_lattice': (i32, [vp, i64, i64, i64, i64]),
         'cdb_clear_lattice': (i32, [vp]),
-        'cdb_set_strip': (i32, [vp, i64, i64, i32, i32]),
-        'cdb_halo_record_doubles': (i64, [vp]),
-        'cdb_migrant_record_doubles': (i64, [vp]),
-        'cdb_halo_pack': (i32, [vp, i32, vp, i64]),
-        'cdb_halo_unpack': (i32, [vp, i32, vp, i64]),
-        'cdb_migrants_pack': (i32, [vp, i32, vp, i64]),
-        'cdb_migrants_unpack': (i32, [vp, i32, vp, i64]),
-        'cdb_strip_step_begin': (i32, [vp, u32, f64]),
-        'cdb_strip_vmax_ptr': (vp, [vp]),
-        'cdb_strip_step_finish': (i32, [vp, u32, f64, f64]),
-        'cdb_strip_absorb': (i32, [vp]),
+        'cdb_set_strip': (i32, [vp, i64, i64, i64, i64, i32, i32, i64, i64]),
+        'cdb_set_agent_ids': (i32, [vp, vp, i64]),
+        'cdb_halo_buffer_doubles': (i64, [vp]),
+        'cdb_migrant_buffer_doubles': (i64, [vp]),
+        'cdb_strip_begin': (i32, [vp, u32, f64, vp, vp]),
+        'cdb_strip_export_vmax': (i32, [vp, vp]),
+        'cdb_strip_import_vmax': (i32, [vp, vp]),
+        'cdb_strip_finish': (i32, [vp, u32, f64, f64, vp, vp, vp, vp]),
+        'cdb_strip_absorb': (i32, [vp, vp, vp, pi64]),
+        'cdb_export_agents': (i32, [vp, vp, vp, i64, pi64]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)

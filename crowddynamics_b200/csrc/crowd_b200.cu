@@ -20,6 +20,7 @@
 
 #include "kernels.cuh"
 #include "step_kernel.cuh"
+#include "strip_kernels.cuh"
 
 namespace {
 
@@ -123,6 +124,14 @@ struct cdb_sim {
     unsigned long long *d_pair_count = nullptr;
     int64_t iterations = 0;
 
+    // strip decomposition
+    bool strip = false;
+    int has_left = 0, has_right = 0;
+    int64_t halo_cap = 0, mig_cap = 0;
+    int64_t n_dead = 0;              // slots vacated by migrants (dropped at the next sort)
+    int *d_counters = nullptr;       // [0] migrants left, [1] migrants right, [2] appended
+    int *h_counters = nullptr;       // pinned
+
     // instrumentation: kernel launch counter and CUDA-event timing of the step phases
     int64_t launches = 0;
     bool profiling = false;
@@ -145,17 +154,25 @@ void free_soa(Soa &s) {
     s = Soa{};
 }
 
+int alloc_ghost_tail(cdb_sim *sim);
+
 int ensure_capacity(cdb_sim *sim, int64_t n) {
     if (n <= sim->capacity && sim->cur.p) return CDB_OK;
     int64_t cap = n < 1024 ? 1024 : n;
     free_soa(sim->cur); free_soa(sim->alt);
     CKS(alloc_soa(sim->cur, sim->n_alloc_planes, cap));
     CKS(alloc_soa(sim->alt, sim->n_alloc_planes, cap));
+    sim->capacity = cap;
+    CKS(dev_alloc(&sim->d_order, cap));
+    return alloc_ghost_tail(sim);
+}
+
+// buffers that also hold the ghost agents of the two neighbour strips (slots [capacity, capacity + 2 * halo_cap))
+int alloc_ghost_tail(cdb_sim *sim) {
+    const size_t cap = (size_t)(sim->capacity + 2 * sim->halo_cap);
     CKS(dev_alloc(&sim->d_cell_of_slot, cap));
     CKS(dev_alloc(&sim->d_order_tmp, cap));
-    CKS(dev_alloc(&sim->d_order, cap));
-    CKS(dev_alloc(&sim->d_nbr, (size_t)cap * (sim->model == CDB_MODEL_CIRCULAR ? REC_CIRC : REC_THREE)));
-    sim->capacity = cap;
+    CKS(dev_alloc(&sim->d_nbr, cap * (sim->model == CDB_MODEL_CIRCULAR ? REC_CIRC : REC_THREE)));
     return CDB_OK;
 }
 
@@ -196,12 +213,13 @@ int prof_mark(cdb_sim *sim) {
 // ---- block list --------------------------------------------------------------------------------------------------
 int build_block_list(cdb_sim *sim, double cell_size, bool padded_lattice = false, unsigned long long *vmax = nullptr) {
     if (!(cell_size > 0.0) || !std::isfinite(cell_size)) return fail(CDB_ERR_INVALID_VALUE, "cell_size must be > 0");
-    const int64_t n = sim->n;
+    const int64_t n = sim->n;                   // slots in use, including the ones vacated by migrants
+    const int64_t live = sim->n - sim->n_dead;
     sim->cell_size = cell_size;
     sim->tables_valid = false;
     cudaStream_t st = sim->stream;
-    if (n == 0) {
-        sim->grid = Grid{0, 0, 0, 0, 0};
+    if (n == 0 && !sim->strip) {
+        sim->grid = Grid{0, 0, 0, 0, 0, 0, 0};
         CK(cudaMemcpyAsync(sim->d_grid, &sim->grid, sizeof(Grid), cudaMemcpyHostToDevice, st));
         sim->tables_valid = true;
         return CDB_OK;
@@ -223,7 +241,7 @@ int build_block_list(cdb_sim *sim, double cell_size, bool padded_lattice = false
         if (nx <= 0 || ny <= 0 || (double)nx * (double)ny > 2.0e9)
             return fail(CDB_ERR_CAPACITY, "block list of %lld x %lld cells is too large", nx, ny);
         if (padded_lattice) { x0 -= 1; y0 -= 1; nx += 2; ny += 2; }
-        sim->grid = Grid{x0, y0, nx, ny, nx * ny};
+        sim->grid = Grid{x0, y0, nx, ny, nx * ny, 0, nx - 1};
         sim->auto_lattice_valid = padded_lattice;
         sim->auto_lattice_age = 0;
         sim->cell_size_lattice = cell_size;
@@ -233,20 +251,22 @@ int build_block_list(cdb_sim *sim, double cell_size, bool padded_lattice = false
     CKS(ensure_cells(sim, ncell));
     CK(cudaMemsetAsync(sim->d_cell_count, 0, ncell * sizeof(int), st));
     CK(cudaMemsetAsync(sim->d_cell_fill, 0, ncell * sizeof(int), st));
-    LAUNCH(sim, k_cell_count, cdiv(n, T), T, 0, sim->cur, (int)n, cell_size, sim->d_grid, sim->d_cell_of_slot, sim->d_cell_count, sim->d_error, vmax);
+    if (n > 0) LAUNCH(sim, k_cell_count, cdiv(n, T), T, 0, sim->cur, (int)n, cell_size, sim->d_grid, sim->d_cell_of_slot, sim->d_cell_count, sim->d_error, vmax);
     // exclusive scan count -> start
     const int nblk = cdiv(ncell, SCAN_TILE);
     LAUNCH(sim, k_scan_tiles, nblk, SCAN_THREADS, 0, sim->d_cell_count, sim->d_cell_start, (int)ncell, sim->d_scan_partials);
     LAUNCH(sim, k_scan_partials, 1, 1024, 0, sim->d_scan_partials, nblk);
-    LAUNCH(sim, k_scan_add, nblk, SCAN_THREADS, 0, sim->d_cell_start, (int)ncell, sim->d_scan_partials, (int)n);
-    LAUNCH(sim, k_scatter, cdiv(n, T), T, 0, sim->d_cell_of_slot, (int)n, sim->d_cell_start, sim->d_cell_fill, sim->d_order_tmp);
-    LAUNCH(sim, k_rank_fix, cdiv(n, T), T, 0, sim->d_order_tmp, (int)n, sim->cur.id, sim->d_cell_of_slot, sim->d_cell_start,
+    LAUNCH(sim, k_scan_add, nblk, SCAN_THREADS, 0, sim->d_cell_start, (int)ncell, sim->d_scan_partials, (int)live);
+    if (n > 0) LAUNCH(sim, k_scatter, cdiv(n, T), T, 0, sim->d_cell_of_slot, (int)n, sim->d_cell_start, sim->d_cell_fill, sim->d_order_tmp);
+    if (live > 0) LAUNCH(sim, k_rank_fix, cdiv(live, T), T, 0, sim->d_order_tmp, (int)live, sim->cur.id, sim->d_cell_of_slot, sim->d_cell_start,
                                          sim->d_cell_count, sim->d_order);
-    LAUNCH(sim, k_gather, cdiv(n, T), T, 0, sim->cur, sim->alt, (int)n, sim->n_planes, sim->model, sim->d_order, sim->d_cell_of_slot, sim->d_order_tmp, sim->d_nbr);
+    if (live > 0) LAUNCH(sim, k_gather, cdiv(live, T), T, 0, sim->cur, sim->alt, (int)live, sim->n_planes, sim->model, sim->d_order, sim->d_cell_of_slot, sim->d_order_tmp, sim->d_nbr);
     // d_order_tmp now holds the flat cell of every *sorted* slot
     std::swap(sim->cur, sim->alt);
     std::swap(sim->d_cell_of_slot, sim->d_order_tmp);
     CK(cudaGetLastError());
+    sim->n = live;
+    sim->n_dead = 0;
     sim->tables_valid = true;
     return CDB_OK;
 }
@@ -386,6 +406,8 @@ int cdb_create(int device, int model, int64_t capacity, cdb_sim **out) {
         CKS(dev_alloc(&sim->d_dt_log, DT_LOG));
         CKS(dev_alloc(&sim->d_error, 1));
         CKS(dev_alloc(&sim->d_pair_count, 1));
+        CKS(dev_alloc(&sim->d_counters, 4));
+        CK(cudaMallocHost((void **)&sim->h_counters, 4 * sizeof(int)));
         CKS(dev_alloc(&sim->d_nav, MAX_NAV_TARGETS));
         CK(cudaMemset(sim->d_error, 0, sizeof(int)));
         CK(cudaMemset(sim->d_dt, 0, 2 * sizeof(double)));
@@ -413,6 +435,7 @@ int cdb_destroy(cdb_sim *sim) {
     cudaFree(sim->d_nav); cudaFree(sim->d_vmax); cudaFree(sim->d_dt); cudaFree(sim->d_dt_log); cudaFreeHost(sim->h_dt);
     for (auto e : sim->ev_pool) cudaEventDestroy(e);
     cudaFree(sim->d_error); cudaFreeHost(sim->h_error); cudaFree(sim->d_pair_count);
+    cudaFree(sim->d_counters); cudaFreeHost(sim->h_counters);
     if (sim->own_stream && sim->stream) cudaStreamDestroy(sim->stream);
     delete sim;
     return CDB_OK;
@@ -448,6 +471,7 @@ int cdb_upload_agents_aos(cdb_sim *sim, const void *agents, int64_t n, int64_t i
         sim->aos_capacity = n * itemsize;
     }
     sim->n = n;
+    sim->n_dead = 0;
     sim->tables_valid = false;
     sim->auto_lattice_valid = false;
     if (n == 0) return CDB_OK;
@@ -727,7 +751,7 @@ int cdb_set_lattice(cdb_sim *sim, int64_t ix_min, int64_t iy_min, int64_t nx, in
     SIM_ENTRY();
     if (nx <= 0 || ny <= 0 || (double)nx * (double)ny > 2.0e9) return fail(CDB_ERR_INVALID_VALUE, "bad lattice shape");
     CK(cudaStreamSynchronize(sim->stream));
-    sim->grid = Grid{ix_min, iy_min, nx, ny, nx * ny};
+    sim->grid = Grid{ix_min, iy_min, nx, ny, nx * ny, 0, nx - 1};
     sim->lattice_fixed = true;
     sim->tables_valid = false;
     CK(cudaMemcpy(sim->d_grid, &sim->grid, sizeof(Grid), cudaMemcpyHostToDevice));
@@ -740,16 +764,147 @@ int cdb_clear_lattice(cdb_sim *sim) {
     return CDB_OK;
 }
 
-int cdb_set_strip(cdb_sim *sim, int64_t, int64_t, int, int) { SIM_ENTRY(); return fail(CDB_ERR_STATE, "strip decomposition not built yet"); }
-int64_t cdb_halo_record_doubles(const cdb_sim *sim) { return sim ? (sim->model == CDB_MODEL_CIRCULAR ? 6 : 14) : -1; }
-int64_t cdb_migrant_record_doubles(const cdb_sim *sim) { return sim ? sim->n_planes + 2 : -1; }
-int cdb_halo_pack(cdb_sim *sim, int, double *, int64_t) { SIM_ENTRY(); return fail(CDB_ERR_STATE, "strip decomposition not built yet"); }
-int cdb_halo_unpack(cdb_sim *sim, int, const double *, int64_t) { SIM_ENTRY(); return fail(CDB_ERR_STATE, "strip decomposition not built yet"); }
-int cdb_migrants_pack(cdb_sim *sim, int, double *, int64_t) { SIM_ENTRY(); return fail(CDB_ERR_STATE, "strip decomposition not built yet"); }
-int cdb_migrants_unpack(cdb_sim *sim, int, const double *, int64_t) { SIM_ENTRY(); return fail(CDB_ERR_STATE, "strip decomposition not built yet"); }
-int cdb_strip_step_begin(cdb_sim *sim, uint32_t, double) { SIM_ENTRY(); return fail(CDB_ERR_STATE, "strip decomposition not built yet"); }
-double *cdb_strip_vmax_ptr(cdb_sim *sim) { return sim ? (double *)sim->d_vmax : nullptr; }
-int cdb_strip_step_finish(cdb_sim *sim, uint32_t, double, double) { SIM_ENTRY(); return fail(CDB_ERR_STATE, "strip decomposition not built yet"); }
-int cdb_strip_absorb(cdb_sim *sim) { SIM_ENTRY(); return fail(CDB_ERR_STATE, "strip decomposition not built yet"); }
+int cdb_set_strip(cdb_sim *sim, int64_t ix_min, int64_t iy_min, int64_t nx_owned, int64_t ny, int has_left, int has_right,
+                  int64_t halo_cap, int64_t migrant_cap) {
+    SIM_ENTRY();
+    if (nx_owned <= 0 || ny <= 0 || halo_cap < 0 || migrant_cap < 0) return fail(CDB_ERR_INVALID_VALUE, "bad strip shape");
+    CK(cudaStreamSynchronize(sim->stream));
+    sim->strip = true;
+    sim->has_left = has_left ? 1 : 0;
+    sim->has_right = has_right ? 1 : 0;
+    sim->halo_cap = halo_cap;
+    sim->mig_cap = migrant_cap;
+    const int64_t nx = nx_owned + sim->has_left + sim->has_right;
+    sim->grid = Grid{ix_min - sim->has_left, iy_min, nx, ny, nx * ny, sim->has_left, nx - 1 - sim->has_right};
+    sim->lattice_fixed = true;
+    sim->tables_valid = false;
+    CK(cudaMemcpy(sim->d_grid, &sim->grid, sizeof(Grid), cudaMemcpyHostToDevice));
+    return alloc_ghost_tail(sim);
+}
+
+int cdb_set_agent_ids(cdb_sim *sim, const int64_t *ids, int64_t n) {
+    SIM_ENTRY();
+    if (n != sim->n) return fail(CDB_ERR_INVALID_VALUE, "id count does not match the uploaded agents");
+    if (n == 0) return CDB_OK;
+    long long *d = nullptr;
+    CKS(dev_alloc(&d, (size_t)n));
+    CK(cudaMemcpyAsync(d, ids, n * sizeof(long long), cudaMemcpyHostToDevice, sim->stream));
+    LAUNCH(sim, k_set_ids, cdiv(n, 256), 256, 0, sim->cur, d, (int)n);
+    CK(cudaStreamSynchronize(sim->stream));
+    cudaFree(d);
+    return CDB_OK;
+}
+
+int64_t cdb_halo_buffer_doubles(const cdb_sim *sim) {
+    if (!sim) return -1;
+    const int rec = sim->model == CDB_MODEL_CIRCULAR ? REC_CIRC : REC_THREE;
+    return MSG_HEADER + halo_counts_doubles(sim->grid.ny) + sim->halo_cap * rec;
+}
+int64_t cdb_migrant_buffer_doubles(const cdb_sim *sim) { return sim ? MSG_HEADER + sim->mig_cap * (sim->n_planes + 2) : -1; }
+
+int cdb_strip_begin(cdb_sim *sim, uint32_t flags, double cell_size, double *halo_left_out, double *halo_right_out) {
+    SIM_ENTRY();
+    if (!sim->strip) return fail(CDB_ERR_STATE, "cdb_set_strip has not been called");
+    CKS(prof_mark(sim));
+    LAUNCH(sim, k_vmax_init, 1, 32, 0, sim->d_vmax);
+    CKS(build_block_list(sim, cell_size, false, sim->d_vmax));
+    const int rec = sim->model == CDB_MODEL_CIRCULAR ? REC_CIRC : REC_THREE;
+    const int ny = (int)sim->grid.ny;
+    if (sim->has_left && halo_left_out)
+        LAUNCH(sim, k_halo_pack, 32, 256, 0, sim->d_nbr, rec, sim->d_cell_start, sim->d_cell_count, (int)sim->grid.cx_lo, ny, halo_left_out,
+               (long long)sim->halo_cap, sim->d_error);
+    if (sim->has_right && halo_right_out)
+        LAUNCH(sim, k_halo_pack, 32, 256, 0, sim->d_nbr, rec, sim->d_cell_start, sim->d_cell_count, (int)sim->grid.cx_hi, ny, halo_right_out,
+               (long long)sim->halo_cap, sim->d_error);
+    CK(cudaGetLastError());
+    CKS(prof_mark(sim));
+    return CDB_OK;
+}
+
+int cdb_strip_export_vmax(cdb_sim *sim, double *dev_vmax2) {
+    SIM_ENTRY();
+    LAUNCH(sim, k_vmax_export, 1, 32, 0, sim->d_vmax, dev_vmax2);
+    CK(cudaGetLastError());
+    return CDB_OK;
+}
+int cdb_strip_import_vmax(cdb_sim *sim, const double *dev_vmax2) {
+    SIM_ENTRY();
+    LAUNCH(sim, k_vmax_import, 1, 32, 0, dev_vmax2, sim->d_vmax);
+    CK(cudaGetLastError());
+    return CDB_OK;
+}
+
+int cdb_strip_finish(cdb_sim *sim, uint32_t flags, double dt_min, double dt_max, const double *halo_left_in,
+                     const double *halo_right_in, double *mig_left_out, double *mig_right_out) {
+    SIM_ENTRY();
+    if (!sim->strip || !sim->tables_valid) return fail(CDB_ERR_STATE, "cdb_strip_begin must precede cdb_strip_finish");
+    const int rec = sim->model == CDB_MODEL_CIRCULAR ? REC_CIRC : REC_THREE;
+    const int ny = (int)sim->grid.ny;
+    const int base_l = (int)sim->capacity, base_r = (int)(sim->capacity + sim->halo_cap);
+    if (sim->has_left) {
+        if (halo_left_in) LAUNCH(sim, k_halo_unpack, 1, 1024, 0, halo_left_in, rec, sim->d_nbr, sim->d_cell_of_slot, sim->d_cell_start, sim->d_cell_count,
+                                 0, ny, base_l, (long long)sim->halo_cap, sim->d_error);
+        else LAUNCH(sim, k_ghost_clear, 4, 256, 0, sim->d_cell_start, sim->d_cell_count, 0, ny, base_l);
+    }
+    if (sim->has_right) {
+        const int col = (int)sim->grid.nx - 1;
+        if (halo_right_in) LAUNCH(sim, k_halo_unpack, 1, 1024, 0, halo_right_in, rec, sim->d_nbr, sim->d_cell_of_slot, sim->d_cell_start, sim->d_cell_count,
+                                  col, ny, base_r, (long long)sim->halo_cap, sim->d_error);
+        else LAUNCH(sim, k_ghost_clear, 4, 256, 0, sim->d_cell_start, sim->d_cell_count, col, ny, base_r);
+    }
+    CKS(prof_mark(sim));
+    CKS(launch_step_kernel(sim, flags, dt_min, dt_max, nullptr));
+    CKS(prof_mark(sim));
+    sim->iterations++;
+    LAUNCH(sim, k_counters_zero, 1, 32, 0, sim->d_counters, 4);
+    if (sim->n > 0)
+        LAUNCH(sim, k_migrants_pack, cdiv(sim->n, 256), 256, 0, sim->cur, (int)sim->n, sim->n_planes, sim->cell_size, sim->grid.ix_min,
+               (int)sim->grid.cx_lo, (int)sim->grid.cx_hi, sim->has_left, sim->has_right, mig_left_out, mig_right_out, (long long)sim->mig_cap,
+               sim->d_counters, sim->d_error);
+    LAUNCH(sim, k_migrants_header, 1, 32, 0, sim->has_left ? mig_left_out : nullptr, sim->has_right ? mig_right_out : nullptr, sim->d_counters,
+           (long long)sim->mig_cap);
+    CK(cudaGetLastError());
+    CKS(prof_mark(sim));
+    return CDB_OK;
+}
+
+int cdb_strip_absorb(cdb_sim *sim, const double *mig_left_in, const double *mig_right_in, int64_t *n_out) {
+    SIM_ENTRY();
+    if (!sim->strip) return fail(CDB_ERR_STATE, "cdb_set_strip has not been called");
+    const int g = cdiv(sim->mig_cap > 0 ? sim->mig_cap : 1, 128);
+    if (sim->has_left && mig_left_in)
+        LAUNCH(sim, k_migrants_unpack, g, 128, 0, mig_left_in, sim->cur, (int)sim->n, sim->n_planes, (long long)sim->capacity, sim->d_counters, sim->d_error);
+    if (sim->has_right && mig_right_in)
+        LAUNCH(sim, k_migrants_unpack, g, 128, 0, mig_right_in, sim->cur, (int)sim->n, sim->n_planes, (long long)sim->capacity, sim->d_counters, sim->d_error);
+    CK(cudaMemcpyAsync(sim->h_counters, sim->d_counters, 4 * sizeof(int), cudaMemcpyDeviceToHost, sim->stream));
+    CKS(check_device_error(sim));    // synchronizes
+    const int64_t out = std::min<int64_t>(sim->h_counters[0], sim->mig_cap) + std::min<int64_t>(sim->h_counters[1], sim->mig_cap);
+    sim->n_dead += out;
+    sim->n += sim->h_counters[2];
+    sim->tables_valid = false;
+    if (n_out) *n_out = sim->n - sim->n_dead;
+    return CDB_OK;
+}
+
+int cdb_export_agents(cdb_sim *sim, void *agents, int64_t *ids, int64_t cap, int64_t *count) {
+    SIM_ENTRY();
+    if (!count) return fail(CDB_ERR_INVALID_VALUE, "count is NULL");
+    const int64_t live = sim->n - sim->n_dead;
+    *count = live;
+    if (live == 0) return CDB_OK;
+    if (cap < live || !agents || !ids) return fail(CDB_ERR_CAPACITY, "export buffer holds %lld agents, %lld needed", (long long)cap, (long long)live);
+    uint8_t *d_rec = nullptr;
+    long long *d_ids = nullptr;
+    CKS(dev_alloc(&d_rec, (size_t)(live * sim->itemsize + 16)));
+    CKS(dev_alloc(&d_ids, (size_t)live));
+    CK(cudaMemsetAsync(sim->d_counters + 3, 0, sizeof(int), sim->stream));
+    if (sim->model == CDB_MODEL_CIRCULAR) LAUNCH(sim, k_export_records<0>, cdiv(sim->n, 128), 128, 0, sim->cur, (int)sim->n, d_rec, d_ids, sim->d_counters + 3);
+    else LAUNCH(sim, k_export_records<1>, cdiv(sim->n, 128), 128, 0, sim->cur, (int)sim->n, d_rec, d_ids, sim->d_counters + 3);
+    CK(cudaMemcpyAsync(agents, d_rec, live * sim->itemsize, cudaMemcpyDeviceToHost, sim->stream));
+    CK(cudaMemcpyAsync(ids, d_ids, live * sizeof(long long), cudaMemcpyDeviceToHost, sim->stream));
+    CK(cudaStreamSynchronize(sim->stream));
+    cudaFree(d_rec); cudaFree(d_ids);
+    return CDB_OK;
+}
 
 }  // extern "C"

@@ -26,7 +26,10 @@ struct Soa {
     __device__ __forceinline__ double &operator()(int plane, int i) const { return p[(long long)plane * stride + i]; }
 };
 
-struct Grid { long long ix_min, iy_min, nx, ny, ncell; };
+struct Grid {
+    long long ix_min, iy_min, nx, ny, ncell;
+    long long cx_lo, cx_hi;   // column range owned agents are binned into (whole lattice unless ghost columns exist)
+};
 
 struct NavField { const double *U, *V; long long ny, nx; double minx, miny, step; int valid; };
 
@@ -301,7 +304,7 @@ template <int MODEL>
 __global__ void k_pack_aos(Soa s, int n, uint8_t *__restrict__ aos, unsigned mask) {
     constexpr int ITEM = MODEL == 0 ? 228 : 316;
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n) return;
+    if (t >= n || s.id[t] < 0) return;
     uint32_t *rec = reinterpret_cast<uint32_t *>(aos + (size_t)s.id[t] * ITEM);
     const FieldMap *fm = MODEL == 0 ? c_fields_circ : c_fields_three;
     constexpr int NF = MODEL == 0 ? N_FIELDS_CIRC : N_FIELDS_THREE;
@@ -354,7 +357,7 @@ __device__ __forceinline__ int flat_cell(double px, double py, double cell_size,
     double fx = floor(px / cell_size), fy = floor(py / cell_size);
     // clamp into the lattice (no-op for a bounding-box lattice; border binning for a fixed one)
     double rx = fx - (double)g.ix_min, ry = fy - (double)g.iy_min;
-    long long cx = rx < 0.0 ? 0 : (rx > (double)(g.nx - 1) ? g.nx - 1 : (long long)rx);
+    long long cx = rx < (double)g.cx_lo ? g.cx_lo : (rx > (double)g.cx_hi ? g.cx_hi : (long long)rx);
     long long cy = ry < 0.0 ? 0 : (ry > (double)(g.ny - 1) ? g.ny - 1 : (long long)ry);
     return (int)(cx * g.ny + cy);
 }
@@ -370,7 +373,9 @@ __global__ void k_cell_count(Soa s, int n, double cell_size, const Grid *grid, i
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     double v_max = 0.0;
     unsigned long long v0 = 0ULL;
-    if (i < n) {
+    if (i < n && s.id[i] < 0) {
+        cell_of_slot[i] = -1;          // slot vacated by a migrant: dropped by the sort
+    } else if (i < n) {
         const Grid g = *grid;
         double px = s(PX, i), py = s(PY, i);
         if (!isfinite(px) || !isfinite(py)) atomicExch(error, ERR_NONFINITE);
@@ -456,6 +461,7 @@ __global__ void k_scatter(const int *__restrict__ cell_of_slot, int n, const int
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int c = cell_of_slot[i];
+    if (c < 0) return;
     order_tmp[cell_start[c] + atomicAdd(&cell_fill[c], 1)] = i;
 }
 

@@ -242,9 +242,10 @@ __global__ void __launch_bounds__(STEP_THREADS) k_step(const StepArgs A) {
                         Three me, other;
                         load_three_rec(nbr, tg, me);
                         load_three_rec(nbr, u, other);
-                        // reference pair orientation: i is the lexicographically smaller (cell_x, cell_y, agent index),
-                        // which is exactly the order of the cell-sorted slots
-                        const bool me_is_i = tg < u;
+                        // reference pair orientation: i is the lexicographically smaller (cell_x, cell_y, agent index):
+                        // cell order, then (same cell => both owned) the order of the cell-sorted slots
+                        const int ctg = A.cell_sorted[tg], cu = A.cell_sorted[u];
+                        const bool me_is_i = ctg < cu || (ctg == cu && tg < u);   // ghosts never share a cell with owned agents
                         Three I, J;     // one inlined copy of the pair arithmetic: select the roles instead of branching
                         sel_three(me_is_i, me, other, I);
                         sel_three(me_is_i, other, me, J);

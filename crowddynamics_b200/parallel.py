@@ -1,0 +1,314 @@
+"""Spatial strip decomposition of one crowd over the GPUs of a node (no reference counterpart).
+
+One process per GPU (``torch.distributed``, NCCL over NVLink).  The cell lattice is global and anchored at multiples of
+the cell size, so every rank computes identical cell coordinates; rank g owns a contiguous range of cell *columns*.
+Per step and per neighbour one halo message (the first / last owned cell column as packed neighbour records + per-cell
+counts) and one migrant message (agents whose column left the strip, with their full state) are exchanged with
+``batch_isend_irecv``; when dt_min != dt_max the two maxima of ``adaptive_timestep`` are MAX-all-reduced.  Forces are
+computed in gather form on the owner of each agent, so no force ever travels back.
+
+The message buffers are ordinary torch tensors; the CUDA library packs / unpacks them through raw device pointers
+(``include/crowd_b200.h``: cdb_strip_begin / cdb_strip_finish / cdb_strip_absorb).
+"""
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import _lib
+from .structures import MODEL_CIRCULAR, MODEL_THREE_CIRCLE, model_of
+
+
+def partition_columns(ix_min, nx, world):
+    """Split cell columns [ix_min, ix_min + nx) into `world` contiguous strips of (almost) equal width.
+    Returns world + 1 boundaries."""
+    if nx < world:
+        raise ValueError('fewer cell columns (%d) than ranks (%d)' % (nx, world))
+    return [ix_min + (nx * g) // world for g in range(world + 1)]
+
+
+def lattice_of(positions, cell_size, pad=1):
+    """Global lattice (ix_min, iy_min, nx, ny) covering all positions, padded by `pad` cells."""
+    c = np.floor(np.asarray(positions) / cell_size).astype(np.int64)
+    lo, hi = c.min(axis=0) - pad, c.max(axis=0) + pad
+    return int(lo[0]), int(lo[1]), int(hi[0] - lo[0] + 1), int(hi[1] - lo[1] + 1)
+
+
+def owner_of_columns(cols, bounds):
+    """Rank owning each cell column (columns outside the lattice belong to the first / last rank)."""
+    return np.clip(np.searchsorted(np.asarray(bounds[1:-1]), cols, side='right'), 0, len(bounds) - 2)
+
+
+class CudaStripDevice:
+    """Adapter: DeviceAgents + the strip entry points of the C ABI, taking torch tensors as message buffers."""
+
+    def __init__(self, model, capacity, device_index, stream=None):
+        from .engine import DeviceAgents
+        self.dev = DeviceAgents(model, capacity=capacity, device=device_index, stream=stream)
+        self.lib = self.dev.lib
+        self.handle = self.dev.handle
+
+    @staticmethod
+    def _p(t):
+        return C.c_void_p(t.data_ptr()) if t is not None else None
+
+    def upload(self, agents, ids):
+        self.dev.upload(agents)
+        ids = np.ascontiguousarray(ids, dtype=np.int64)
+        _lib.check(self.lib.cdb_set_agent_ids(self.handle, C.c_void_p(ids.ctypes.data), len(ids)))
+
+    def set_strip(self, ix_min, iy_min, nx_owned, ny, has_left, has_right, halo_cap, mig_cap):
+        _lib.check(self.lib.cdb_set_strip(self.handle, ix_min, iy_min, nx_owned, ny, int(has_left), int(has_right),
+                                          halo_cap, mig_cap))
+        return int(self.lib.cdb_halo_buffer_doubles(self.handle)), int(self.lib.cdb_migrant_buffer_doubles(self.handle))
+
+    def set_obstacles(self, obstacles):
+        self.dev.set_obstacles(obstacles)
+
+    def set_navigation_field(self, target, mgrid, direction_map):
+        self.dev.set_navigation_field(target, mgrid, direction_map)
+
+    def begin(self, flags, cell_size, halo_left_out, halo_right_out):
+        _lib.check(self.lib.cdb_strip_begin(self.handle, flags, cell_size, self._p(halo_left_out), self._p(halo_right_out)))
+
+    def export_vmax(self, buf):
+        _lib.check(self.lib.cdb_strip_export_vmax(self.handle, self._p(buf)))
+
+    def import_vmax(self, buf):
+        _lib.check(self.lib.cdb_strip_import_vmax(self.handle, self._p(buf)))
+
+    def finish(self, flags, dt_min, dt_max, halo_left_in, halo_right_in, mig_left_out, mig_right_out):
+        _lib.check(self.lib.cdb_strip_finish(self.handle, flags, dt_min, dt_max, self._p(halo_left_in),
+                                             self._p(halo_right_in), self._p(mig_left_out), self._p(mig_right_out)))
+
+    def absorb(self, mig_left_in, mig_right_in):
+        n = C.c_int64()
+        _lib.check(self.lib.cdb_strip_absorb(self.handle, self._p(mig_left_in), self._p(mig_right_in), C.byref(n)))
+        return n.value
+
+    def export_agents(self, dtype):
+        cnt = C.c_int64()
+        cap = int(self.lib.cdb_num_agents(self.handle))
+        out = np.zeros(max(cap, 1), dtype=dtype)
+        ids = np.zeros(max(cap, 1), dtype=np.int64)
+        _lib.check(self.lib.cdb_export_agents(self.handle, C.c_void_p(out.ctypes.data), C.c_void_p(ids.ctypes.data), cap,
+                                              C.byref(cnt)))
+        return out[:cnt.value], ids[:cnt.value]
+
+    def time(self):
+        return self.dev.time()
+
+    # instrumentation passthrough (bench.py)
+    def profile(self, enable=True):
+        self.dev.profile(enable)
+
+    def profile_read(self):
+        return self.dev.profile_read()
+
+    def launch_count(self):
+        return self.dev.launch_count()
+
+
+class StripSimulation:
+    """One rank's strip of a crowd that is decomposed along x."""
+
+    def __init__(self, dev, rank, world, bounds, lattice, cell_size, halo_cap, mig_cap, tensor_device, n_owned,
+                 dist=None, flags=_lib.STEP_ALL, dt_min=0.01, dt_max=0.01):
+        import torch
+        self.torch = torch
+        self.dist = dist
+        self.dev = dev
+        self.rank, self.world = rank, world
+        self.bounds = list(bounds)
+        self.cell_size = float(cell_size)
+        self.flags, self.dt_min, self.dt_max = flags, dt_min, dt_max
+        self.left = rank - 1 if rank > 0 else None
+        self.right = rank + 1 if rank < world - 1 else None
+        ix_min, iy_min, nx, ny = lattice
+        halo_doubles, mig_doubles = dev.set_strip(self.bounds[rank], iy_min, self.bounds[rank + 1] - self.bounds[rank], ny,
+                                                  self.left is not None, self.right is not None, halo_cap, mig_cap)
+
+        def buf(n):
+            return torch.zeros(n, dtype=torch.float64, device=tensor_device)
+        self.halo_out = {s: buf(halo_doubles) for s in ('l', 'r')}
+        self.halo_in = {s: buf(halo_doubles) for s in ('l', 'r')}
+        self.mig_out = {s: buf(mig_doubles) for s in ('l', 'r')}
+        self.mig_in = {s: buf(mig_doubles) for s in ('l', 'r')}
+        self.vmax = buf(2)
+        self._n_owned = n_owned
+
+    def n_owned(self):
+        return self._n_owned
+
+    # -- neighbour exchange ---------------------------------------------------------------------------------------------
+    def _exchange(self, out, inn):
+        """Send out['l'] to the left neighbour and out['r'] to the right one; receive into inn['l'] / inn['r']."""
+        if self.world == 1:
+            return
+        dist = self.dist
+        ops = []
+        if self.left is not None:
+            ops.append(dist.P2POp(dist.isend, out['l'], self.left))
+            ops.append(dist.P2POp(dist.irecv, inn['l'], self.left))
+        if self.right is not None:
+            ops.append(dist.P2POp(dist.isend, out['r'], self.right))
+            ops.append(dist.P2POp(dist.irecv, inn['r'], self.right))
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+
+    # -- the phases of one step (driven by step() over torch.distributed, or by LocalGroup in one process) ---------------
+    def phase_begin(self):
+        L, R = self.left is not None, self.right is not None
+        self.dev.begin(self.flags, self.cell_size, self.halo_out['l'] if L else None, self.halo_out['r'] if R else None)
+
+    def phase_finish(self, flags=None):
+        L, R = self.left is not None, self.right is not None
+        self.dev.finish(self.flags if flags is None else flags, self.dt_min, self.dt_max,
+                        self.halo_in['l'] if L else None, self.halo_in['r'] if R else None,
+                        self.mig_out['l'] if L else None, self.mig_out['r'] if R else None)
+
+    def phase_absorb(self):
+        L, R = self.left is not None, self.right is not None
+        self._n_owned = self.dev.absorb(self.mig_in['l'] if L else None, self.mig_in['r'] if R else None)
+
+    @property
+    def adaptive(self):
+        return self.dt_min != self.dt_max and bool(self.flags & _lib.STEP_INTEGRATOR)
+
+    def step(self, n_steps=1):
+        for _ in range(n_steps):
+            self.phase_begin()
+            self._exchange(self.halo_out, self.halo_in)
+            if self.adaptive and self.world > 1:
+                self.dev.export_vmax(self.vmax)
+                self.dist.all_reduce(self.vmax, op=self.dist.ReduceOp.MAX)
+                self.dev.import_vmax(self.vmax)
+            self.phase_finish()
+            self._exchange(self.mig_out, self.mig_in)
+            self.phase_absorb()
+
+    def settle(self):
+        """Move agents that were generated outside this rank's columns to their owner (one hop), without stepping."""
+        self.dev.begin(0, self.cell_size, None, None)
+        self.phase_finish(flags=0)
+        self._exchange(self.mig_out, self.mig_in)
+        self.phase_absorb()
+
+    def export(self, dtype):
+        return self.dev.export_agents(dtype)
+
+    # -- construction helpers ---------------------------------------------------------------------------------------------
+    @classmethod
+    def from_global(cls, agents, obstacles, fields, cell_size, rank, world, device_index=0, dist=None, lattice=None,
+                    flags=_lib.STEP_ALL, dt_min=0.01, dt_max=0.01, make_device=None, tensor_device=None, slack=1.5):
+        """Every rank holds the same global `agents` array and keeps the agents of its own cell columns
+        (global id = row index).  Used by the tests: the union over ranks must reproduce the single-GPU result."""
+        model = model_of(agents)
+        lattice = lattice or lattice_of(agents['position'], cell_size)
+        ix_min, iy_min, nx, ny = lattice
+        bounds = partition_columns(ix_min, nx, world)
+        cols = np.floor(agents['position'][:, 0] / cell_size).astype(np.int64)
+        mine = owner_of_columns(cols, bounds) == rank
+        ids = np.nonzero(mine)[0].astype(np.int64)
+        local = np.ascontiguousarray(agents[mine])
+        per_col = max(1, int(np.bincount(np.clip(cols - ix_min, 0, nx - 1), minlength=nx).max()))
+        halo_cap = int(slack * per_col) + 64
+        mig_cap = halo_cap
+        capacity = int(slack * len(local)) + 2 * mig_cap + 1024
+        if make_device is None:
+            import torch
+            dev = CudaStripDevice(model, capacity, device_index, stream=torch.cuda.current_stream().cuda_stream)
+            tensor_device = torch.device('cuda', device_index)
+        else:
+            dev = make_device(model, capacity)
+        dev.upload(local, ids)
+        dev.set_obstacles(obstacles)
+        for t, (mg, uv) in enumerate(fields or ()):
+            dev.set_navigation_field(t, mg, uv)
+        return cls(dev, rank, world, bounds, lattice, cell_size, halo_cap, mig_cap, tensor_device, len(local), dist=dist,
+                   flags=flags, dt_min=dt_min, dt_max=dt_max)
+
+    @classmethod
+    def synthetic(cls, model, n_per_rank, density, rank, world, device_index, seed=0, cell_size=3.6, dist=None,
+                  dt_min=0.01, dt_max=0.01):
+        """Weak-scaling benchmark crowd: every rank generates its own n_per_rank agents in its own square of a
+        world x 1 row of rooms without inner walls (one walled rectangle); strips are aligned to cell columns, so agents a
+        rank generated beyond its last column are handed to the neighbour before the first step."""
+        import torch
+        from . import synthetic as S
+        m = int(math.ceil(math.sqrt(n_per_rank)))
+        side = m / math.sqrt(density)
+        agents, _, _ = S.uniform_crowd(n_per_rank, model, density=density, seed=seed, origin=(rank * side, 0.0))
+        obstacles = S.walls_of_box(0.0, 0.0, world * side, side)
+        ix_min, iy_min = -1, -1
+        nx = int(math.floor(world * side / cell_size)) + 3
+        ny = int(math.floor(side / cell_size)) + 3
+        # column boundaries follow the rooms: rank g owns the columns whose left edge lies in [g * side, (g + 1) * side)
+        bounds = [ix_min] + [int(math.ceil(g * side / cell_size)) for g in range(1, world)] + [ix_min + nx]
+        mid = MODEL_CIRCULAR if model == 'circular' else MODEL_THREE_CIRCLE
+        per_col = int(1.3 * density * cell_size * side) + 256
+        halo_cap, mig_cap = per_col, per_col
+        capacity = int(1.05 * n_per_rank) + 4 * mig_cap
+        dev = CudaStripDevice(mid, capacity, device_index, stream=torch.cuda.current_stream().cuda_stream)
+        ids = np.arange(n_per_rank, dtype=np.int64) + rank * n_per_rank
+        dev.upload(agents, ids)
+        dev.set_obstacles(obstacles)
+        x0 = rank * side
+        mg, uv = S.direction_field(1.0, (x0 - 8.0, 0.0, x0 + side + 8.0, side), 'exit', point=(world * side, side / 2))
+        dev.set_navigation_field(0, mg, uv)
+        sim = cls(dev, rank, world, bounds, (ix_min, iy_min, nx, ny), cell_size, halo_cap, mig_cap,
+                  torch.device('cuda', device_index), n_per_rank, dist=dist, dt_min=dt_min, dt_max=dt_max)
+        sim.settle()
+        return sim
+
+
+class LocalGroup:
+    """All strips of a decomposition inside ONE process (message exchange by tensor copies instead of send/recv).
+    Functionally identical to one process per GPU; used to validate the strip kernels on a single device."""
+
+    def __init__(self, sims):
+        self.sims = list(sims)
+
+    def _exchange(self, out_name, in_name):
+        for g, s in enumerate(self.sims):
+            if s.right is not None:
+                r = self.sims[g + 1]
+                getattr(r, in_name)['l'].copy_(getattr(s, out_name)['r'])
+                getattr(s, in_name)['r'].copy_(getattr(r, out_name)['l'])
+
+    def settle(self):
+        for s in self.sims:
+            s.dev.begin(0, s.cell_size, None, None)
+            s.phase_finish(flags=0)
+        self._exchange('mig_out', 'mig_in')
+        for s in self.sims:
+            s.phase_absorb()
+
+    def step(self, n_steps=1):
+        torch = self.sims[0].torch
+        for _ in range(n_steps):
+            for s in self.sims:
+                s.phase_begin()
+            self._exchange('halo_out', 'halo_in')
+            if self.sims[0].adaptive and len(self.sims) > 1:
+                for s in self.sims:
+                    s.dev.export_vmax(s.vmax)
+                v = torch.stack([s.vmax for s in self.sims])
+                # NaN-propagating maximum, like np.max in the reference's adaptive_timestep
+                m = torch.where(torch.isnan(v).any(0), torch.full_like(v[0], float('nan')), v.max(0).values)
+                for s in self.sims:
+                    s.vmax.copy_(m)
+                    s.dev.import_vmax(s.vmax)
+            for s in self.sims:
+                s.phase_finish()
+            self._exchange('mig_out', 'mig_in')
+            for s in self.sims:
+                s.phase_absorb()
+
+    def export(self, dtype):
+        """-> (agents, ids) of the whole crowd ordered by global id."""
+        parts = [s.export(dtype) for s in self.sims]
+        agents = np.concatenate([p[0] for p in parts])
+        ids = np.concatenate([p[1] for p in parts])
+        order = np.argsort(ids, kind='stable')
+        return agents[order], ids[order]

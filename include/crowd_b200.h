@@ -141,23 +141,34 @@ int cdb_get_neighbor_pairs(cdb_sim *sim, int64_t *pairs, int64_t cap, int64_t *c
  * cell_size, so cell coordinates are identical; agents outside are binned into the border cells). */
 int cdb_set_lattice(cdb_sim *sim, int64_t ix_min, int64_t iy_min, int64_t nx, int64_t ny);
 int cdb_clear_lattice(cdb_sim *sim);
-/* Declare that this sim owns cell columns [ix_lo, ix_hi) of the lattice; columns ix_lo-1 and ix_hi hold ghosts. */
-int cdb_set_strip(cdb_sim *sim, int64_t ix_lo, int64_t ix_hi, int has_left, int has_right);
-/* Halo / migrant buffers are plain device memory owned by the caller (e.g. torch tensors given to NCCL send/recv). */
-int64_t cdb_halo_record_doubles(const cdb_sim *sim);
-int64_t cdb_migrant_record_doubles(const cdb_sim *sim);
-/* side: 0 = left neighbour, 1 = right.  Buffers start with a 4-double header (count, ...). */
-int cdb_halo_pack(cdb_sim *sim, int side, double *dev_buf, int64_t cap_records);
-int cdb_halo_unpack(cdb_sim *sim, int side, const double *dev_buf, int64_t cap_records);
-int cdb_migrants_pack(cdb_sim *sim, int side, double *dev_buf, int64_t cap_records);
-int cdb_migrants_unpack(cdb_sim *sim, int side, const double *dev_buf, int64_t cap_records);
-/* The strip step is split around the exchanges:  begin (sort, pack halos) | exchange | finish (forces, integrate,
- * pack migrants) | exchange | absorb (append migrants).  v_max_inout / v0_max_inout are device doubles reduced by the
- * caller across ranks (MAX) between begin and finish when dt_min != dt_max. */
-int cdb_strip_step_begin(cdb_sim *sim, uint32_t node_flags, double cell_size);
-double *cdb_strip_vmax_ptr(cdb_sim *sim);   /* device double[2]: max |v|, max target_velocity of owned agents */
-int cdb_strip_step_finish(cdb_sim *sim, uint32_t node_flags, double dt_min, double dt_max);
-int cdb_strip_absorb(cdb_sim *sim);
+/* Strip decomposition along x, aligned to cell columns.  This sim owns the nx_owned cell columns starting at global
+ * column ix_min (rows iy_min .. iy_min + ny - 1 -- every rank uses the same rows); one ghost column is added on each side
+ * that has a neighbour.  halo_cap / migrant_cap: record capacity of one halo / migrant message. */
+int cdb_set_strip(cdb_sim *sim, int64_t ix_min, int64_t iy_min, int64_t nx_owned, int64_t ny, int has_left, int has_right,
+                  int64_t halo_cap, int64_t migrant_cap);
+/* Global agent indices of the uploaded agents (used for pair orientation and to identify agents after migration). */
+int cdb_set_agent_ids(cdb_sim *sim, const int64_t *ids, int64_t n);
+/* Message sizes in doubles.  Messages are plain device memory owned by the caller (e.g. torch tensors handed to NCCL
+ * send/recv); they start with a 4-double header whose first entry is the record count. */
+int64_t cdb_halo_buffer_doubles(const cdb_sim *sim);
+int64_t cdb_migrant_buffer_doubles(const cdb_sim *sim);
+/* One strip step is split around the two exchanges:
+ *   begin   block list of the owned agents; packs the first / last owned cell column (neighbour records + per-cell
+ *           counts) into halo_left_out / halo_right_out (NULL where there is no neighbour)
+ *   -- caller exchanges halos, and MAX-reduces the two doubles of export_vmax across ranks when dt_min != dt_max --
+ *   finish  installs the received ghost columns, runs the fused step kernel on the owned agents, then packs the agents
+ *           that left the strip into mig_left_out / mig_right_out
+ *   -- caller exchanges migrants --
+ *   absorb  appends the received migrants; *n_out = agents now owned (one host sync). */
+int cdb_strip_begin(cdb_sim *sim, uint32_t node_flags, double cell_size, double *halo_left_out, double *halo_right_out);
+int cdb_strip_export_vmax(cdb_sim *sim, double *dev_vmax2);
+int cdb_strip_import_vmax(cdb_sim *sim, const double *dev_vmax2);
+int cdb_strip_finish(cdb_sim *sim, uint32_t node_flags, double dt_min, double dt_max, const double *halo_left_in,
+                     const double *halo_right_in, double *mig_left_out, double *mig_right_out);
+int cdb_strip_absorb(cdb_sim *sim, const double *mig_left_in, const double *mig_right_in, int64_t *n_out);
+/* Live agents in device order: packed records rebuilt from the device state (record fields the kernels never touch are
+ * zero) and their global ids. */
+int cdb_export_agents(cdb_sim *sim, void *agents, int64_t *ids, int64_t cap, int64_t *count);
 
 #ifdef __cplusplus
 }
