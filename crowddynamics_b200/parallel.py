@@ -161,10 +161,10 @@ class StripSimulation:
         L, R = self.left is not None, self.right is not None
         self.dev.begin(self.flags, self.cell_size, self.halo_out['l'] if L else None, self.halo_out['r'] if R else None)
 
-    def phase_finish(self, flags=None):
+    def phase_finish(self, flags=None, use_halo=True):
         L, R = self.left is not None, self.right is not None
         self.dev.finish(self.flags if flags is None else flags, self.dt_min, self.dt_max,
-                        self.halo_in['l'] if L else None, self.halo_in['r'] if R else None,
+                        self.halo_in['l'] if L and use_halo else None, self.halo_in['r'] if R and use_halo else None,
                         self.mig_out['l'] if L else None, self.mig_out['r'] if R else None)
 
     def phase_absorb(self):
@@ -190,7 +190,7 @@ class StripSimulation:
     def settle(self):
         """Move agents that were generated outside this rank's columns to their owner (one hop), without stepping."""
         self.dev.begin(0, self.cell_size, None, None)
-        self.phase_finish(flags=0)
+        self.phase_finish(flags=0, use_halo=False)
         self._exchange(self.mig_out, self.mig_in)
         self.phase_absorb()
 
@@ -279,7 +279,7 @@ class LocalGroup:
     def settle(self):
         for s in self.sims:
             s.dev.begin(0, s.cell_size, None, None)
-            s.phase_finish(flags=0)
+            s.phase_finish(flags=0, use_halo=False)
         self._exchange('mig_out', 'mig_in')
         for s in self.sims:
             s.phase_absorb()
