@@ -10,7 +10,7 @@ import subprocess
 from .exceptions import ExtensionMissing, InvalidType, InvalidValue, DeviceError, CrowdDynamicsException
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'csrc', 'libcrowd_b200.so')
+LIB_PATH = os.environ.get('CROWD_B200_LIB') or os.path.join(_HERE, 'csrc', 'libcrowd_b200.so')
 HEADER_PATH = os.path.abspath(os.path.join(_HERE, '..', 'include', 'crowd_b200.h'))
 
 CDB_OK, CDB_ERR_INVALID_TYPE, CDB_ERR_INVALID_VALUE, CDB_ERR_CUDA, CDB_ERR_CAPACITY, CDB_ERR_STATE = range(6)

@@ -817,7 +817,6 @@ int cdb_strip_begin(cdb_sim *sim, uint32_t flags, double cell_size, double *halo
         LAUNCH(sim, k_halo_pack, 32, 256, 0, sim->d_nbr, rec, sim->d_cell_start, sim->d_cell_count, (int)sim->grid.cx_hi, ny, halo_right_out,
                (long long)sim->halo_cap, sim->d_error);
     CK(cudaGetLastError());
-    CKS(prof_mark(sim));
     return CDB_OK;
 }
 

@@ -168,8 +168,14 @@ __device__ __forceinline__ void load_three_rec(const double *__restrict__ nbr, i
 }
 
 // =====================================================================================================================
+#ifndef STEP_MINB_CIRC
+#define STEP_MINB_CIRC 5
+#endif
+#ifndef STEP_MINB_THREE
+#define STEP_MINB_THREE 4
+#endif
 template <int MODEL>
-__global__ void __launch_bounds__(STEP_THREADS) k_step(const StepArgs A) {
+__global__ void __launch_bounds__(STEP_THREADS, MODEL == 0 ? STEP_MINB_CIRC : STEP_MINB_THREE) k_step(const StepArgs A) {
     __shared__ WarpSmem s_warp[STEP_WARPS];
     const int t = blockIdx.x * STEP_THREADS + threadIdx.x;
     const int lane = threadIdx.x & 31;
