@@ -61,9 +61,12 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.time(), line.strip()))
 
-    def stop(self):
+    def mark(self):
+        return time.time()
+
+    def stop(self, t0=None, t1=None):
         if self.proc is None:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
         time.sleep(0.15)
@@ -74,7 +77,10 @@ class ClockSampler:
             self.proc.kill()
         sm, smax, reasons = [], [], set()
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        for r in self.rows:
+        rows = [r for (ts, r) in self.rows if (t0 is None or ts >= t0) and (t1 is None or ts <= t1 + 0.12)]
+        if not rows:
+            rows = [r for (_, r) in self.rows[-2:]]
+        for r in rows:
             c = [x.strip() for x in r.split(',')]
             if len(c) < 9:
                 continue
@@ -170,8 +176,8 @@ def workload_config(args, n_per_gpu, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=20)
-    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--steps', type=int, default=300)
+    ap.add_argument('--warmup', type=int, default=10)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--model', default='three_circle', choices=['circular', 'three_circle'])
     ap.add_argument('--agents', type=int, default=1000000, help='agents per GPU')
@@ -230,20 +236,21 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     step_fn(args.warmup)
     sync()
     dev.profile(True)
     launches0 = dev.launch_count()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync()
+    t_begin = time.time()
     ev0.record()
     step_fn(args.steps)
     ev1.record()
     sync()
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_begin, time.time()) if rank == 0 else None
     ms = ev0.elapsed_time(ev1)
     launches = dev.launch_count() - launches0
     prof = dev.profile_read()
