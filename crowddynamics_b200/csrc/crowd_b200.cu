@@ -103,7 +103,6 @@ struct cdb_sim {
     int *d_cell_of_slot = nullptr;   // flat cell of each slot (of `cur`, valid after build)
     int *d_order_tmp = nullptr, *d_order = nullptr;
     double *d_nbr = nullptr;         // packed neighbour records of the cell-sorted state
-    float4 *d_nbrf = nullptr;        // fp32 sight-gate records
     int *d_scan_partials = nullptr;
     long long *d_bbox = nullptr;     // min ix, max ix, min iy, max iy
     long long *h_bbox = nullptr;     // pinned
@@ -174,7 +173,6 @@ int alloc_ghost_tail(cdb_sim *sim) {
     CKS(dev_alloc(&sim->d_cell_of_slot, cap));
     CKS(dev_alloc(&sim->d_order_tmp, cap));
     CKS(dev_alloc(&sim->d_nbr, cap * (sim->model == CDB_MODEL_CIRCULAR ? REC_CIRC : REC_THREE)));
-    CKS(dev_alloc(&sim->d_nbrf, cap));
     return CDB_OK;
 }
 
@@ -262,7 +260,7 @@ int build_block_list(cdb_sim *sim, double cell_size, bool padded_lattice = false
     if (n > 0) LAUNCH(sim, k_scatter, cdiv(n, T), T, 0, sim->d_cell_of_slot, (int)n, sim->d_cell_start, sim->d_cell_fill, sim->d_order_tmp);
     if (live > 0) LAUNCH(sim, k_rank_fix, cdiv(live, T), T, 0, sim->d_order_tmp, (int)live, sim->cur.id, sim->d_cell_of_slot, sim->d_cell_start,
                                          sim->d_cell_count, sim->d_order);
-    if (live > 0) LAUNCH(sim, k_gather, cdiv(live, T), T, 0, sim->cur, sim->alt, (int)live, sim->n_planes, sim->model, sim->d_order, sim->d_cell_of_slot, sim->d_order_tmp, sim->d_nbr, sim->d_nbrf, sim->d_grid, cell_size);
+    if (live > 0) LAUNCH(sim, k_gather, cdiv(live, T), T, 0, sim->cur, sim->alt, (int)live, sim->n_planes, sim->model, sim->d_order, sim->d_cell_of_slot, sim->d_order_tmp, sim->d_nbr);
     // d_order_tmp now holds the flat cell of every *sorted* slot
     std::swap(sim->cur, sim->alt);
     std::swap(sim->d_cell_of_slot, sim->d_order_tmp);
@@ -310,7 +308,6 @@ StepArgs step_args(cdb_sim *sim, unsigned flags, double dt_min, double dt_max, d
     a.in = sim->cur;
     a.out = (flags & CDB_STEP_INTEGRATOR) ? sim->alt : sim->cur;
     a.nbr = sim->d_nbr;
-    a.nbrf = sim->d_nbrf;
     a.n = (int)sim->n;
     a.grid = sim->d_grid;
     a.cell_sorted = sim->d_cell_of_slot; a.cell_start = sim->d_cell_start; a.cell_count = sim->d_cell_count;
@@ -431,7 +428,7 @@ int cdb_destroy(cdb_sim *sim) {
     free_soa(sim->cur); free_soa(sim->alt);
     cudaFree(sim->d_aos); cudaFreeHost(sim->h_bounce);
     cudaFree(sim->d_grid); cudaFree(sim->d_cell_count); cudaFree(sim->d_cell_start); cudaFree(sim->d_cell_fill);
-    cudaFree(sim->d_cell_of_slot); cudaFree(sim->d_order_tmp); cudaFree(sim->d_order); cudaFree(sim->d_nbr); cudaFree(sim->d_nbrf); cudaFree(sim->d_scan_partials);
+    cudaFree(sim->d_cell_of_slot); cudaFree(sim->d_order_tmp); cudaFree(sim->d_order); cudaFree(sim->d_nbr); cudaFree(sim->d_scan_partials);
     cudaFree(sim->d_bbox); cudaFreeHost(sim->h_bbox);
     cudaFree(sim->d_obstacles);
     for (auto &f : sim->nav) { cudaFree((void *)f.U); cudaFree((void *)f.V); }
@@ -844,13 +841,13 @@ int cdb_strip_finish(cdb_sim *sim, uint32_t flags, double dt_min, double dt_max,
     const int ny = (int)sim->grid.ny;
     const int base_l = (int)sim->capacity, base_r = (int)(sim->capacity + sim->halo_cap);
     if (sim->has_left) {
-        if (halo_left_in) LAUNCH(sim, k_halo_unpack, 1, 1024, 0, halo_left_in, rec, sim->d_nbr, sim->d_nbrf, sim->d_grid, sim->cell_size, sim->d_cell_of_slot, sim->d_cell_start, sim->d_cell_count,
+        if (halo_left_in) LAUNCH(sim, k_halo_unpack, 1, 1024, 0, halo_left_in, rec, sim->d_nbr, sim->d_cell_of_slot, sim->d_cell_start, sim->d_cell_count,
                                  0, ny, base_l, (long long)sim->halo_cap, sim->d_error);
         else LAUNCH(sim, k_ghost_clear, 4, 256, 0, sim->d_cell_start, sim->d_cell_count, 0, ny, base_l);
     }
     if (sim->has_right) {
         const int col = (int)sim->grid.nx - 1;
-        if (halo_right_in) LAUNCH(sim, k_halo_unpack, 1, 1024, 0, halo_right_in, rec, sim->d_nbr, sim->d_nbrf, sim->d_grid, sim->cell_size, sim->d_cell_of_slot, sim->d_cell_start, sim->d_cell_count,
+        if (halo_right_in) LAUNCH(sim, k_halo_unpack, 1, 1024, 0, halo_right_in, rec, sim->d_nbr, sim->d_cell_of_slot, sim->d_cell_start, sim->d_cell_count,
                                   col, ny, base_r, (long long)sim->halo_cap, sim->d_error);
         else LAUNCH(sim, k_ghost_clear, 4, 256, 0, sim->d_cell_start, sim->d_cell_count, col, ny, base_r);
     }

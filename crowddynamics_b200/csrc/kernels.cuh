@@ -486,8 +486,7 @@ __global__ void k_rank_fix(const int *__restrict__ order_tmp, int n, const int *
 // extent = conservative radius of the whole body around the centre (from the STORED shoulder positions), (ox, oy) =
 // r_ts (sin phi, -cos phi), the shoulder displacement of power_law.py:338-350.
 __global__ void k_gather(Soa src, Soa dst, int n, int n_planes, int model, const int *__restrict__ order,
-                         const int *__restrict__ cell_of_slot, int *__restrict__ cell_sorted, double *__restrict__ nbr,
-                         float4 *__restrict__ nbrf, const Grid *grid, double cell_size) {
+                         const int *__restrict__ cell_of_slot, int *__restrict__ cell_sorted, double *__restrict__ nbr) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
     const int o = order[t];
@@ -496,11 +495,9 @@ __global__ void k_gather(Soa src, Soa dst, int n, int n_planes, int model, const
     dst.target[t] = src.target[o];
     cell_sorted[t] = cell_of_slot[o];
     const double x = src(PX, o), y = src(PY, o), vx = src(VX, o), vy = src(VY, o);
-    double R;    // radius (circular) / body extent (three-circle): what the sight gate adds to 3.0
     if (model == CDB_MODEL_CIRCULAR) {
-        R = src(RADIUS, o);
         double2 *r = reinterpret_cast<double2 *>(nbr + (size_t)t * 6);
-        r[0] = make_double2(x, y); r[1] = make_double2(vx, vy); r[2] = make_double2(R, 0.0);
+        r[0] = make_double2(x, y); r[1] = make_double2(vx, vy); r[2] = make_double2(src(RADIUS, o), 0.0);
     } else {
         const double phi = src(PHI, o), r_ts = src(R_TS, o), r_t = src(R_T, o), r_s = src(R_S, o);
         const double lsx = src(LSX, o), lsy = src(LSY, o), rsx = src(RSX, o), rsy = src(RSY, o);
@@ -510,13 +507,7 @@ __global__ void k_gather(Soa src, Soa dst, int n, int n_planes, int model, const
         r[0] = make_double2(x, y); r[1] = make_double2(vx, vy); r[2] = make_double2(ext, r_t); r[3] = make_double2(r_s, 0.0);
         r[4] = make_double2(lsx, lsy); r[5] = make_double2(rsx, rsy);
         r[6] = make_double2(r_ts * sin(phi), r_ts * -cos(phi)); r[7] = make_double2(0.0, 0.0);
-        R = ext;
     }
-    // fp32 gate record: coordinates relative to the lattice origin; the radius is inflated by this agent's own fp32
-    // position rounding error (and rounded up), so  d_f <= 3 + R_i + R_j (+ fp32 slack)  can never lose a pair
-    const double rx = x - (double)grid->ix_min * cell_size, ry = y - (double)grid->iy_min * cell_size;
-    const double Rd = R * (1.0 + 2e-7) + 3.0 * fmax(fabs(rx), fabs(ry)) * 1.2e-7 + 1e-7;
-    nbrf[t] = make_float4((float)rx, (float)ry, __double2float_ru(Rd), 0.0f);
 }
 
 __global__ void k_export_cell_ids(const int *__restrict__ id, const int *__restrict__ cell_sorted, int n, long long *out) {

@@ -25,9 +25,8 @@
 
 constexpr int STEP_THREADS = 128;
 constexpr int STEP_WARPS = STEP_THREADS / 32;
-constexpr int LCAP1 = 48;    // per-lane list of candidates that passed the fp32 sight gate
-constexpr int LCAP2 = 16;    // per-lane list of candidates that may contribute a force (input of phase 2)
-constexpr int CHUNK = 4;     // candidates swept between two list-capacity checks
+constexpr int LCAP = 16;     // survivor list entries per lane between two flushes
+constexpr int CHUNK = 4;     // candidates classified between two list-capacity checks
 #define PREFILTER_EPS 1e-12
 #define BOUND_EPS 1e-9
 
@@ -38,7 +37,6 @@ constexpr int REC_THREE = 16;   // px py vx vy ext rt rs - | lsx lsy rsx rsy ox 
 struct StepArgs {
     Soa in, out;             // out == in unless integrating (then the new state is written to the other buffer)
     const double *nbr;       // packed neighbour records of `in`
-    const float4 *nbrf;      // fp32 gate records {x - x0, y - y0, R inflated by its own rounding error, -}
     int n;
     const Grid *grid;
     const int *cell_sorted, *cell_start, *cell_count;
@@ -54,8 +52,7 @@ struct StepArgs {
 };
 
 struct WarpSmem {
-    int list1[LCAP1 * 32];   // entry k of lane l at list[k * 32 + l]
-    int list2[LCAP2 * 32];
+    int list[LCAP * 32];     // entry k of lane l at list[k * 32 + l]
     int pre[33];             // exclusive prefix of the per-lane counts, pre[32] = total
     double res[3][32];       // results of one dealt round
 };
@@ -209,29 +206,26 @@ __global__ void __launch_bounds__(STEP_THREADS, MODEL == 0 ? STEP_MINB_CIRC : ST
     // ---- AgentAgentInteractions (interactions.py:191-205) -----------------------------------------------------------------
     if (A.flags & CDB_STEP_AGENT_AGENT) {
         const double *__restrict__ nbr = A.nbr;
-        const float4 *__restrict__ nbrf = A.nbrf;
-        // what the classifiers need of the target: centre, velocity, radius (circular) / body extent (three-circle)
+        // what phase 1 needs of the target: centre, velocity, radius (circular) / body extent (three-circle)
         double mpx, mpy, mvx, mvy, mr;
         {
             const double *r = nbr + (size_t)tt * REC;
             const double2 p = ldg2(r), v = ldg2(r + 2);
             mpx = p.x; mpy = p.y; mvx = v.x; mvy = v.y; mr = __ldg(r + 4);
         }
-        const float4 mf = __ldg(nbrf + tt);
-        const float gateA = (3.0f + mf.z) * 1.000001f + 2e-6f;     // fp32 sight gate: d_f <= gateA + 1.000001 R_j
         const int ny = (int)A.grid->ny, nxg = (int)A.grid->nx;
         const int c = A.cell_sorted[tt];
         const int cx = c / ny, cy = c - cx * ny;
         const int ylo = cy > 0 ? cy - 1 : 0, yhi = cy + 1 < ny ? cy + 1 : ny - 1;
-        int cnt1 = 0, cnt2 = 0;
+        int cnt = 0;
 
-        // phase 2: evaluate list2, dealt evenly over the lanes
-        auto phase2 = [&]() {
-            int incl = cnt2;
+        auto flush = [&]() {
+            // flatten the ragged lists: pre[l] = first flattened index of lane l
+            int incl = cnt;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) { int w = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += w; }
             const int total = __shfl_sync(FULL, incl, 31);
-            const int mypre = incl - cnt2;
+            const int mypre = incl - cnt;
             W.pre[lane] = mypre;
             if (lane == 31) W.pre[32] = total;
             __syncwarp();
@@ -242,7 +236,7 @@ __global__ void __launch_bounds__(STEP_THREADS, MODEL == 0 ? STEP_MINB_CIRC : ST
                     int l = 0;   // largest l with pre[l] <= f (lanes with empty lists share a prefix value: skipped by '<=')
 #pragma unroll
                     for (int o = 16; o; o >>= 1) if (W.pre[l + o] <= f) l += o;
-                    const int u = W.list2[(f - W.pre[l]) * 32 + l];
+                    const int u = W.list[(f - W.pre[l]) * 32 + l];
                     const int tg = t0 + l;    // the target this entry belongs to
                     const ThreePar par = {s(MASS, tg), s(K_SOC, tg), s(TAU_0, tg), s(MU, tg), s(KAPPA, tg), s(DAMPING, tg)};
                     if (MODEL == 0) {
@@ -268,7 +262,7 @@ __global__ void __launch_bounds__(STEP_THREADS, MODEL == 0 ? STEP_MINB_CIRC : ST
                 if (MODEL == 1) W.res[2][lane] = rtq;
                 __syncwarp();
                 // every target adds up its own entries of this round, in list order
-                const int lo = max(mypre, r0) - r0, hi = min(mypre + cnt2, r0 + 32) - r0;
+                const int lo = max(mypre, r0) - r0, hi = min(mypre + cnt, r0 + 32) - r0;
                 const int span = __reduce_max_sync(FULL, hi - lo);
                 for (int k = 0; k < span; ++k)
                     if (lo + k < hi) {
@@ -277,96 +271,69 @@ __global__ void __launch_bounds__(STEP_THREADS, MODEL == 0 ? STEP_MINB_CIRC : ST
                     }
                 __syncwarp();
             }
-            cnt2 = 0;
+            cnt = 0;
         };
 
-        // A small state machine keeps ONE call site per stage (the pair arithmetic is inlined exactly once):
-        //   sweep    fp32 sight gate over the candidates of the three neighbour cell-columns        -> list1
-        //   drain    exact fp64 classification of list1 (can the pair contribute a force at all?)   -> list2
-        //   phase2   exact pair arithmetic on list2
-        int dx = -1, b = 0, e = 0, maxlen = 0, k0 = 0, k1 = 0, m1 = 0;
-        bool have_col = false, sweep_done = false, draining = false;
-        while (true) {
-            const bool l2_full = __any_sync(FULL, cnt2 >= LCAP2);
-            if (l2_full || (sweep_done && !draining && __any_sync(FULL, cnt2 > 0))) { phase2(); continue; }
-            if (draining) {
-                if (k1 < m1) {
-                    if (k1 < cnt1) {
-                        const int u = W.list1[k1 * 32 + lane];
-                        const double *r = nbr + (size_t)u * REC;
-                        const double2 p = ldg2(r), v = ldg2(r + 2);
-                        const double ro = __ldg(r + 4);
-                        const double x = mpx - p.x, y = mpy - p.y;
-                        const double R = mr + ro;                    // r_tot (circular) / sum of body extents (three-circle)
-                        const double d2 = x * x + y * y;
-                        const double lim = SIGTH_SOC + R;
-                        const double RR = R * R;
-                        const bool gate = d2 <= lim * lim * (1.0 + PREFILTER_EPS);
-                        const bool contact = d2 <= RR * (1.0 + PREFILTER_EPS);
-                        const double vx = mvx - v.x, vy = mvy - v.y;
-                        const double a = vx * vx + vy * vy;
-                        const double bb = -(x * vx + y * vy);
-                        bool social;
-                        if (MODEL == 0) {
-                            // the reference's own quantities in its own operation order: exact necessary condition
-                            const double cc = d2 - RR;
-                            const double disc = bb * bb - a * cc;
-                            social = disc > 0.0 && bb > 0.0;
-                        } else {
-                            // bounding circles (inflated by BOUND_EPS so that rounding in the exact per-part discriminants
-                            // cannot matter): no real root for them => none for any part pair; all part pairs receding
-                            // (b_k <= b + R |v| <= 0) => no positive time-to-collision
-                            const double Rs = R * (1.0 + BOUND_EPS), RRs = Rs * Rs;
-                            const double disc = bb * bb - a * (d2 - RRs);
-                            social = disc >= 0.0 && (bb >= 0.0 || bb * bb <= RRs * a);
-                        }
-                        if (gate && (social || contact)) { W.list2[cnt2 * 32 + lane] = u; ++cnt2; }
+        // classify until some list is nearly full or all three cell-columns are done, then evaluate; repeat.
+        // (one flush call site: the pair arithmetic is inlined exactly once)
+        int dx = -1, b = 0, e = 0, maxlen = 0, k0 = 0;
+        bool have_col = false, done = false;
+        do {
+            while (true) {
+                if (!have_col) {
+                    if (dx > 1) { done = true; break; }
+                    const int x2 = cx + dx;
+                    b = 0; e = 0;
+                    if (active && x2 >= 0 && x2 < nxg) {
+                        b = A.cell_start[x2 * ny + ylo];
+                        e = A.cell_start[x2 * ny + yhi] + A.cell_count[x2 * ny + yhi];
                     }
-                    ++k1;
-                    continue;
+                    maxlen = __reduce_max_sync(FULL, e - b);
+                    k0 = 0;
+                    have_col = true;
                 }
-                draining = false;
-                cnt1 = 0;
-                continue;
-            }
-            if (sweep_done) break;
-            if (!have_col) {
-                if (dx > 1) {
-                    sweep_done = true;
-                    m1 = __reduce_max_sync(FULL, cnt1); k1 = 0; draining = m1 > 0;
-                    continue;
-                }
-                const int x2 = cx + dx;
-                b = 0; e = 0;
-                if (active && x2 >= 0 && x2 < nxg) {
-                    b = A.cell_start[x2 * ny + ylo];
-                    e = A.cell_start[x2 * ny + yhi] + A.cell_count[x2 * ny + yhi];
-                }
-                maxlen = __reduce_max_sync(FULL, e - b);
-                k0 = 0;
-                have_col = true;
-            }
-            if (k0 >= maxlen) { have_col = false; ++dx; continue; }
-            if (__any_sync(FULL, cnt1 > LCAP1 - CHUNK)) {
-                m1 = __reduce_max_sync(FULL, cnt1); k1 = 0; draining = true;
-                continue;
-            }
-            bool keep[CHUNK];
+                if (k0 >= maxlen) { have_col = false; ++dx; continue; }
+                if (__any_sync(FULL, cnt > LCAP - CHUNK)) break;
+                bool keep[CHUNK];
 #pragma unroll
-            for (int kk = 0; kk < CHUNK; ++kk) {
-                const int u = b + k0 + kk;
-                const bool inr = u < e;
-                const float4 q = __ldg(nbrf + (inr ? u : tt));
-                const float fxd = mf.x - q.x, fyd = mf.y - q.y;
-                const float d2 = fmaf(fxd, fxd, fyd * fyd);
-                const float lim = fmaf(q.z, 1.000001f, gateA);
-                keep[kk] = inr && u != t && d2 <= lim * lim;
-            }
+                for (int kk = 0; kk < CHUNK; ++kk) {
+                    const int u = b + k0 + kk;
+                    const bool inr = u < e;
+                    const double *r = nbr + (size_t)(inr ? u : tt) * REC;
+                    const double2 p = ldg2(r), v = ldg2(r + 2);
+                    const double ro = __ldg(r + 4);
+                    const double x = mpx - p.x, y = mpy - p.y;
+                    const double R = mr + ro;                    // r_tot (circular) / sum of body extents (three-circle)
+                    const double d2 = x * x + y * y;
+                    const double lim = SIGTH_SOC + R;
+                    const double RR = R * R;
+                    const bool gate = d2 <= lim * lim * (1.0 + PREFILTER_EPS);
+                    const bool contact = d2 <= RR * (1.0 + PREFILTER_EPS);
+                    const double vx = mvx - v.x, vy = mvy - v.y;
+                    const double a = vx * vx + vy * vy;
+                    const double bb = -(x * vx + y * vy);
+                    bool social;
+                    if (MODEL == 0) {
+                        const double cc = d2 - RR;
+                        const double disc = bb * bb - a * cc;
+                        social = disc > 0.0 && bb > 0.0;
+                    } else {
+                        // bounding circles (inflated by BOUND_EPS so that rounding in the exact per-part discriminants
+                        // cannot matter): no real root for them => none for any part pair; all part pairs receding
+                        // (b_k <= b + R |v| <= 0) => no positive time-to-collision
+                        const double Rs = R * (1.0 + BOUND_EPS), RRs = Rs * Rs;
+                        const double disc = bb * bb - a * (d2 - RRs);
+                        social = disc >= 0.0 && (bb >= 0.0 || bb * bb <= RRs * a);
+                    }
+                    keep[kk] = inr && u != t && gate && (social || contact);
+                }
 #pragma unroll
-            for (int kk = 0; kk < CHUNK; ++kk)
-                if (keep[kk]) { W.list1[cnt1 * 32 + lane] = b + k0 + kk; ++cnt1; }
-            k0 += CHUNK;
-        }
+                for (int kk = 0; kk < CHUNK; ++kk)
+                    if (keep[kk]) { W.list[cnt * 32 + lane] = b + k0 + kk; ++cnt; }
+                k0 += CHUNK;
+            }
+            flush();
+        } while (!done);
     }
     if (!active) return;
 

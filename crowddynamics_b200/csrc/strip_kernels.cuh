@@ -26,8 +26,7 @@ __global__ void k_halo_pack(const double *__restrict__ nbr, int rec, const int *
 }
 
 // message -> ghost column `col` of the local lattice; ghost records live at slots [base, base + count) of nbr.
-__global__ void k_halo_unpack(const double *__restrict__ msg, int rec, double *__restrict__ nbr, float4 *__restrict__ nbrf,
-                              const Grid *grid, double cell_size, int *__restrict__ cell_sorted,
+__global__ void k_halo_unpack(const double *__restrict__ msg, int rec, double *__restrict__ nbr, int *__restrict__ cell_sorted,
                               int *__restrict__ cell_start, int *__restrict__ cell_count, int col, int ny, int base, long long cap,
                               int *error) {
     // single block: exclusive scan of the per-cell counts
@@ -65,13 +64,6 @@ __global__ void k_halo_unpack(const double *__restrict__ msg, int rec, double *_
     const double *src = msg + MSG_HEADER + halo_counts_doubles(ny);
     double *dst = nbr + (size_t)base * rec;
     for (long long i = threadIdx.x; i < (long long)count * rec; i += blockDim.x) dst[i] = src[i];
-    // fp32 gate records of the ghosts, relative to THIS rank's lattice origin (same construction as k_gather)
-    const double x0 = (double)grid->ix_min * cell_size, y0 = (double)grid->iy_min * cell_size;
-    for (int i = threadIdx.x; i < count; i += blockDim.x) {
-        const double rx = src[(size_t)i * rec] - x0, ry = src[(size_t)i * rec + 1] - y0, R = src[(size_t)i * rec + 4];
-        const double Rd = R * (1.0 + 2e-7) + 3.0 * fmax(fabs(rx), fabs(ry)) * 1.2e-7 + 1e-7;
-        nbrf[base + i] = make_float4((float)rx, (float)ry, __double2float_ru(Rd), 0.0f);
-    }
 }
 
 // no neighbour on this side / nothing received: empty ghost column
