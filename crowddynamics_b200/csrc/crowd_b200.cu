@@ -532,9 +532,16 @@ int cdb_set_obstacles(cdb_sim *sim, const double *segments, int64_t n_segments) 
     if (n_segments < 0 || (n_segments > 0 && !segments)) return fail(CDB_ERR_INVALID_VALUE, "bad obstacle buffer");
     CK(cudaSetDevice(sim->device));
     CK(cudaStreamSynchronize(sim->stream));
-    CKS(dev_alloc(&sim->d_obstacles, (size_t)n_segments * 4));
+    CKS(dev_alloc(&sim->d_obstacles, (size_t)n_segments * SEG));
     sim->n_obstacles = n_segments;
-    if (n_segments) CK(cudaMemcpy(sim->d_obstacles, segments, n_segments * 4 * sizeof(double), cudaMemcpyHostToDevice));
+    if (n_segments) {
+        double *raw = nullptr;
+        CKS(dev_alloc(&raw, (size_t)n_segments * 4));
+        CK(cudaMemcpy(raw, segments, n_segments * 4 * sizeof(double), cudaMemcpyHostToDevice));
+        LAUNCH(sim, k_obstacle_prep, cdiv(n_segments, 128), 128, 0, raw, (int)n_segments, sim->d_obstacles);
+        CK(cudaStreamSynchronize(sim->stream));
+        cudaFree(raw);
+    }
     return CDB_OK;
 }
 

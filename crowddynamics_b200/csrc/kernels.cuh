@@ -245,13 +245,24 @@ __device__ __forceinline__ void pair_three_circle(const ThreeKin &I, const Three
 }
 
 // ---- distance_circle_line, core/distance.py:110-146 ----------------------------------------------------------------
-__device__ __forceinline__ double distance_circle_line(double x, double y, double r, double p0x, double p0y, double p1x, double p1y,
-                                                       double &nx, double &ny) {
-    double dx = p1x - p0x, dy = p1y - p0y;
-    double l_w = hypot(dx, dy);
-    double twx = dx / l_w, twy = dy / l_w;
+// The agent-independent part (d = p1 - p0, l_w = |d|, t_w = d / l_w) is evaluated once per segment by k_obstacle_prep with
+// the same operations, so per-agent results are unchanged.  Segment record: {p0x, p0y, p1x, p1y, t_wx, t_wy, l_w, -}.
+constexpr int SEG = 8;
+
+__global__ void k_obstacle_prep(const double *__restrict__ raw, int n_obs, double *__restrict__ seg) {
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= n_obs) return;
+    const double p0x = raw[4 * w], p0y = raw[4 * w + 1], p1x = raw[4 * w + 2], p1y = raw[4 * w + 3];
+    const double dx = p1x - p0x, dy = p1y - p0y;
+    const double l_w = hypot(dx, dy);
+    double *s = seg + (size_t)w * SEG;
+    s[0] = p0x; s[1] = p0y; s[2] = p1x; s[3] = p1y; s[4] = dx / l_w; s[5] = dy / l_w; s[6] = l_w; s[7] = 0.0;
+}
+
+__device__ __forceinline__ double distance_circle_line(double x, double y, double r, const double *__restrict__ s, double &nx, double &ny) {
+    const double twx = s[4], twy = s[5], l_w = s[6];
     double nwx = -twy, nwy = twx;   // rotate90
-    double q0x = x - p0x, q0y = y - p0y, q1x = x - p1x, q1y = y - p1y;
+    double q0x = x - s[0], q0y = y - s[1], q1x = x - s[2], q1y = y - s[3];
     double l_t = -(twx * q1x + twy * q1y) - (twx * q0x + twy * q0y);
     double d_iw;
     if (l_t > l_w) {
@@ -261,10 +272,22 @@ __device__ __forceinline__ double distance_circle_line(double x, double y, doubl
     } else {
         double l_n = nwx * q0x + nwy * q0y;
         d_iw = fabs(l_n);
-        double s = isnan(l_n) ? l_n : (double)((l_n > 0.0) - (l_n < 0.0));   // np.sign
-        nx = s * nwx; ny = s * nwy;
+        double sg = isnan(l_n) ? l_n : (double)((l_n > 0.0) - (l_n < 0.0));   // np.sign
+        nx = sg * nwx; ny = sg * nwy;
     }
     return d_iw - r;
+}
+
+// Can a circle (x, y, r) have h < 0 against this segment?  Same branch selection as above; hypot(q) < r is replaced by the
+// conservative q.q <= r^2 (1 + eps), |l_n| < r is exact.  NaNs (degenerate segment) compare false, like h < 0 does.
+__device__ __forceinline__ bool wall_may_touch(double x, double y, double r, const double *__restrict__ s) {
+    const double twx = s[4], twy = s[5], l_w = s[6];
+    const double q0x = x - s[0], q0y = y - s[1], q1x = x - s[2], q1y = y - s[3];
+    const double l_t = -(twx * q1x + twy * q1y) - (twx * q0x + twy * q0y);
+    const double rr = r * r * (1.0 + 1e-12);
+    if (l_t > l_w) return q0x * q0x + q0y * q0y <= rr;
+    if (l_t < -l_w) return q1x * q1x + q1y * q1y <= rr;
+    return fabs(-twy * q0x + twx * q0y) < r;
 }
 
 // =====================================================================================================================
@@ -606,8 +629,10 @@ __global__ void k_adjust(Soa s, int n, int model) {
 __device__ __forceinline__ void walls_circular(double px, double py, double r, double vx, double vy, double mu, double kappa, double damping,
                                                const double *__restrict__ obs, int n_obs, double &fx, double &fy) {
     for (int w = 0; w < n_obs; ++w) {
+        const double *s = obs + (size_t)w * SEG;
+        if (!wall_may_touch(px, py, r, s)) continue;
         double nx, ny;
-        double h = distance_circle_line(px, py, r, obs[4 * w], obs[4 * w + 1], obs[4 * w + 2], obs[4 * w + 3], nx, ny);
+        double h = distance_circle_line(px, py, r, s, nx, ny);
         if (h < 0.0) {
             double cx, cy;
             force_contact(h, nx, ny, vx, vy, ny, -nx, mu, kappa, damping, cx, cy);
@@ -620,14 +645,16 @@ __device__ __forceinline__ void walls_three_circle(double px, double py, double 
                                                    double r_s, double vx, double vy, double mu, double kappa, double damping,
                                                    const double *__restrict__ obs, int n_obs, double &fx, double &fy, double &torque) {
     for (int w = 0; w < n_obs; ++w) {
-        const double p0x = obs[4 * w], p0y = obs[4 * w + 1], p1x = obs[4 * w + 2], p1y = obs[4 * w + 3];
+        const double *s = obs + (size_t)w * SEG;
+        // h_min < 0 needs some part with h < 0
+        if (!(wall_may_touch(px, py, r_t, s) || wall_may_touch(lsx, lsy, r_s, s) || wall_may_touch(rsx, rsy, r_s, s))) continue;
         double h_min = nan(""), nx = 0.0, ny = 0.0, sx = 0.0, sy = 0.0, sr = 0.0;
 #pragma unroll 1
         for (int k = 0; k < 3; ++k) {   // distance.py:154-180: torso, left, right; strict '<', first wins
             const double xk = k == 0 ? px : (k == 1 ? lsx : rsx), yk = k == 0 ? py : (k == 1 ? lsy : rsy);
             const double rk = k == 0 ? r_t : r_s;
             double ax, ay;
-            double h = distance_circle_line(xk, yk, rk, p0x, p0y, p1x, p1y, ax, ay);
+            double h = distance_circle_line(xk, yk, rk, s, ax, ay);
             if (h < h_min || isnan(h_min)) { h_min = h; nx = ax; ny = ay; sx = xk; sy = yk; sr = rk; }
         }
         if (h_min < 0.0) {

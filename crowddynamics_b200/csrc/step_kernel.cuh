@@ -26,7 +26,10 @@
 constexpr int STEP_THREADS = 128;
 constexpr int STEP_WARPS = STEP_THREADS / 32;
 constexpr int LCAP = 16;     // survivor list entries per lane between two flushes
-constexpr int CHUNK = 4;     // candidates classified between two list-capacity checks
+#ifndef STEP_CHUNK
+#define STEP_CHUNK 4
+#endif
+constexpr int CHUNK = STEP_CHUNK;     // candidates classified between two list-capacity checks
 #define PREFILTER_EPS 1e-12
 #define BOUND_EPS 1e-9
 
