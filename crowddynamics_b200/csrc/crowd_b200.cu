@@ -81,7 +81,9 @@ struct cdb_sim {
     bool auto_lattice_valid = false;
     int auto_lattice_age = 0;
     int64_t capacity = 0;   // agent slots allocated (incl. room for ghosts / migrants)
-    int64_t n = 0;          // agents currently held
+    int64_t n = 0;          // slots in use in `cur` (agents currently held, incl. slots vacated by migrants)
+    int64_t n_sorted = 0;   // live agents in the current block list
+    bool perm_valid = false; // block list refers to `cur` through d_order (planes not physically sorted)
     cudaStream_t stream = nullptr;
     bool own_stream = false;
 
@@ -211,7 +213,7 @@ int prof_mark(cdb_sim *sim) {
 }
 
 // ---- block list --------------------------------------------------------------------------------------------------
-int build_block_list(cdb_sim *sim, double cell_size, bool padded_lattice = false, unsigned long long *vmax = nullptr) {
+int build_block_list(cdb_sim *sim, double cell_size, bool padded_lattice = false, unsigned long long *vmax = nullptr, bool physical = true) {
     if (!(cell_size > 0.0) || !std::isfinite(cell_size)) return fail(CDB_ERR_INVALID_VALUE, "cell_size must be > 0");
     const int64_t n = sim->n;                   // slots in use, including the ones vacated by migrants
     const int64_t live = sim->n - sim->n_dead;
@@ -222,6 +224,8 @@ int build_block_list(cdb_sim *sim, double cell_size, bool padded_lattice = false
         sim->grid = Grid{0, 0, 0, 0, 0, 0, 0};
         CK(cudaMemcpyAsync(sim->d_grid, &sim->grid, sizeof(Grid), cudaMemcpyHostToDevice, st));
         sim->tables_valid = true;
+        sim->n_sorted = 0;
+        sim->perm_valid = false;
         return CDB_OK;
     }
     const int T = 256;
@@ -260,13 +264,23 @@ int build_block_list(cdb_sim *sim, double cell_size, bool padded_lattice = false
     if (n > 0) LAUNCH(sim, k_scatter, cdiv(n, T), T, 0, sim->d_cell_of_slot, (int)n, sim->d_cell_start, sim->d_cell_fill, sim->d_order_tmp);
     if (live > 0) LAUNCH(sim, k_rank_fix, cdiv(live, T), T, 0, sim->d_order_tmp, (int)live, sim->cur.id, sim->d_cell_of_slot, sim->d_cell_start,
                                          sim->d_cell_count, sim->d_order);
-    if (live > 0) LAUNCH(sim, k_gather, cdiv(live, T), T, 0, sim->cur, sim->alt, (int)live, sim->n_planes, sim->model, sim->d_order, sim->d_cell_of_slot, sim->d_order_tmp, sim->d_nbr);
-    // d_order_tmp now holds the flat cell of every *sorted* slot
-    std::swap(sim->cur, sim->alt);
-    std::swap(sim->d_cell_of_slot, sim->d_order_tmp);
+    if (physical) {
+        if (live > 0) LAUNCH(sim, k_gather, cdiv(live, T), T, 0, sim->cur, sim->alt, (int)live, sim->n_planes, sim->model,
+                             sim->d_order, sim->d_cell_of_slot, sim->d_order_tmp, sim->d_nbr);
+        // d_order_tmp now holds the flat cell of every *sorted* slot
+        std::swap(sim->cur, sim->alt);
+        std::swap(sim->d_cell_of_slot, sim->d_order_tmp);
+        sim->n = live;
+        sim->n_dead = 0;
+        sim->perm_valid = false;
+    } else {
+        if (live > 0) LAUNCH(sim, k_records, cdiv(live, T), T, 0, sim->cur, (int)live, sim->model, sim->d_order, sim->d_cell_of_slot,
+                             sim->d_order_tmp, sim->d_nbr);
+        std::swap(sim->d_cell_of_slot, sim->d_order_tmp);   // d_cell_of_slot: flat cell per sorted slot; d_order_tmp: per plane slot
+        sim->perm_valid = true;
+    }
     CK(cudaGetLastError());
-    sim->n = live;
-    sim->n_dead = 0;
+    sim->n_sorted = live;
     sim->tables_valid = true;
     return CDB_OK;
 }
@@ -308,7 +322,9 @@ StepArgs step_args(cdb_sim *sim, unsigned flags, double dt_min, double dt_max, d
     a.in = sim->cur;
     a.out = (flags & CDB_STEP_INTEGRATOR) ? sim->alt : sim->cur;
     a.nbr = sim->d_nbr;
-    a.n = (int)sim->n;
+    const bool listed = (flags & CDB_STEP_AGENT_AGENT) != 0;
+    a.n = (int)(listed ? sim->n_sorted : sim->n);
+    a.order = listed && sim->perm_valid ? sim->d_order : nullptr;
     a.grid = sim->d_grid;
     a.cell_sorted = sim->d_cell_of_slot; a.cell_start = sim->d_cell_start; a.cell_count = sim->d_cell_count;
     a.nav = sim->d_nav; a.n_nav = sim->n_nav;
@@ -321,18 +337,19 @@ StepArgs step_args(cdb_sim *sim, unsigned flags, double dt_min, double dt_max, d
 
 // the fused kernel; requires a current block list when CDB_STEP_AGENT_AGENT is selected
 int launch_step_kernel(cdb_sim *sim, unsigned flags, double dt_min, double dt_max, double *dt_log) {
-    if (sim->n == 0) {
-        if (flags & CDB_STEP_INTEGRATOR) LAUNCH(sim, k_integrate, 1, 32, 0, sim->cur, 0, sim->model, dt_min, dt_max, sim->d_vmax, sim->d_dt);
-        CK(cudaGetLastError());
-        return CDB_OK;
-    }
     const StepArgs a = step_args(sim, flags, dt_min, dt_max, dt_log);
     const int smem = 0;
-    if (sim->model == CDB_MODEL_CIRCULAR) LAUNCH(sim, k_step<0>, cdiv(sim->n, STEP_THREADS), STEP_THREADS, smem, a);
-    else LAUNCH(sim, k_step<1>, cdiv(sim->n, STEP_THREADS), STEP_THREADS, smem, a);
+    if (a.n > 0) {
+        if (sim->model == CDB_MODEL_CIRCULAR) LAUNCH(sim, k_step<0>, cdiv(a.n, STEP_THREADS), STEP_THREADS, smem, a);
+        else LAUNCH(sim, k_step<1>, cdiv(a.n, STEP_THREADS), STEP_THREADS, smem, a);
+    } else if (flags & CDB_STEP_INTEGRATOR) {
+        LAUNCH(sim, k_integrate, 1, 32, 0, sim->cur, 0, sim->model, dt_min, dt_max, sim->d_vmax, sim->d_dt);
+    }
     CK(cudaGetLastError());
     if (flags & CDB_STEP_INTEGRATOR) {
         std::swap(sim->cur, sim->alt);
+        if (a.order) { sim->n = a.n; sim->n_dead = 0; }   // the step wrote the live agents compacted, in cell order
+        sim->perm_valid = false;
         sim->tables_valid = false;
     }
     return CDB_OK;
@@ -352,7 +369,7 @@ int launch_agent_agent(cdb_sim *sim) {
     return CDB_OK;
 }
 int node_agent_agent(cdb_sim *sim, double cell_size) {
-    CKS(build_block_list(sim, cell_size));
+    CKS(build_block_list(sim, cell_size, false, nullptr, sim->variant == 1));
     return launch_agent_agent(sim);
 }
 int node_agent_obstacle(cdb_sim *sim) {
@@ -628,7 +645,7 @@ int cdb_step(cdb_sim *sim, uint32_t flags, double cell_size, double dt_min, doub
         } else {
             const bool need_vmax = flags & CDB_STEP_INTEGRATOR;
             if (need_vmax) LAUNCH(sim, k_vmax_init, 1, 32, 0, sim->d_vmax);
-            if (flags & CDB_STEP_AGENT_AGENT) CKS(build_block_list(sim, cell_size, true, need_vmax ? sim->d_vmax : nullptr));
+            if (flags & CDB_STEP_AGENT_AGENT) CKS(build_block_list(sim, cell_size, true, need_vmax ? sim->d_vmax : nullptr, false));
             else if (need_vmax && sim->n > 0) LAUNCH(sim, k_vmax, (cdiv(sim->n, 1024) < 1184 ? cdiv(sim->n, 1024) : 1184), 256, 0, sim->cur, (int)sim->n, sim->d_vmax);
             CKS(prof_mark(sim));
             CKS(launch_step_kernel(sim, flags, dt_min, dt_max, log_slot));
@@ -688,7 +705,7 @@ int cdb_get_time(cdb_sim *sim, double *time_tot, int64_t *iterations) {
 }
 
 // ---- block list exports -------------------------------------------------------------------------------------------
-int cdb_build_block_list(cdb_sim *sim, double cell_size) { SIM_ENTRY(); return build_block_list(sim, cell_size); }
+int cdb_build_block_list(cdb_sim *sim, double cell_size) { SIM_ENTRY(); return build_block_list(sim, cell_size, false, nullptr, false); }
 
 int cdb_get_grid(cdb_sim *sim, int64_t grid[4]) {
     SIM_ENTRY();
@@ -704,7 +721,7 @@ int cdb_get_cell_ids(cdb_sim *sim, int64_t *cell_of_agent, int64_t n) {
     if (n == 0) return CDB_OK;
     long long *d = nullptr;
     CKS(dev_alloc(&d, (size_t)n));
-    LAUNCH(sim, k_export_cell_ids, cdiv(n, 256), 256, 0, sim->cur.id, sim->d_cell_of_slot, (int)n, d);
+    LAUNCH(sim, k_export_cell_ids, cdiv(n, 256), 256, 0, sim->cur.id, sim->perm_valid ? sim->d_order : nullptr, sim->d_cell_of_slot, (int)n, d);
     CK(cudaMemcpyAsync(cell_of_agent, d, n * sizeof(long long), cudaMemcpyDeviceToHost, sim->stream));
     CK(cudaStreamSynchronize(sim->stream));
     cudaFree(d);
@@ -719,11 +736,11 @@ int cdb_get_cell_tables(cdb_sim *sim, int64_t *points_indices, int64_t n, int64_
     long long *d = nullptr;
     const int64_t m = n > n_cells ? n : n_cells;
     CKS(dev_alloc(&d, (size_t)m));
-    LAUNCH(sim, k_widen, cdiv(n, 256), 256, 0, sim->cur.id, (int)n, d);
+    LAUNCH(sim, k_widen, cdiv(n, 256), 256, 0, sim->cur.id, sim->perm_valid ? sim->d_order : nullptr, (int)n, d);
     CK(cudaMemcpyAsync(points_indices, d, n * sizeof(long long), cudaMemcpyDeviceToHost, sim->stream));
-    LAUNCH(sim, k_widen, cdiv(n_cells, 256), 256, 0, sim->d_cell_count, (int)n_cells, d);
+    LAUNCH(sim, k_widen, cdiv(n_cells, 256), 256, 0, sim->d_cell_count, nullptr, (int)n_cells, d);
     CK(cudaMemcpyAsync(cells_count, d, n_cells * sizeof(long long), cudaMemcpyDeviceToHost, sim->stream));
-    LAUNCH(sim, k_widen, cdiv(n_cells, 256), 256, 0, sim->d_cell_start, (int)n_cells, d);
+    LAUNCH(sim, k_widen, cdiv(n_cells, 256), 256, 0, sim->d_cell_start, nullptr, (int)n_cells, d);
     CK(cudaMemcpyAsync(cells_offset, d, n_cells * sizeof(long long), cudaMemcpyDeviceToHost, sim->stream));
     CK(cudaStreamSynchronize(sim->stream));
     cudaFree(d);
@@ -739,7 +756,7 @@ int cdb_get_neighbor_pairs(cdb_sim *sim, int64_t *pairs, int64_t cap, int64_t *c
     long long *d = nullptr;
     CKS(dev_alloc(&d, (size_t)(cap > 0 ? 2 * cap : 1)));
     CK(cudaMemsetAsync(sim->d_pair_count, 0, sizeof(unsigned long long), sim->stream));
-    LAUNCH(sim, k_export_pairs, cdiv(sim->n, 128), 128, 0, sim->cur.id, (int)sim->n, sim->d_grid, sim->d_cell_of_slot, sim->d_cell_start,
+    LAUNCH(sim, k_export_pairs, cdiv(sim->n, 128), 128, 0, sim->cur.id, sim->perm_valid ? sim->d_order : nullptr, (int)sim->n, sim->d_grid, sim->d_cell_of_slot, sim->d_cell_start,
                                                              sim->d_cell_count, d, cap > 0 && pairs ? cap : 0, sim->d_pair_count);
     unsigned long long c = 0;
     CK(cudaMemcpyAsync(&c, sim->d_pair_count, sizeof(c), cudaMemcpyDeviceToHost, sim->stream));
@@ -814,7 +831,7 @@ int cdb_strip_begin(cdb_sim *sim, uint32_t flags, double cell_size, double *halo
     if (!sim->strip) return fail(CDB_ERR_STATE, "cdb_set_strip has not been called");
     CKS(prof_mark(sim));
     LAUNCH(sim, k_vmax_init, 1, 32, 0, sim->d_vmax);
-    CKS(build_block_list(sim, cell_size, false, sim->d_vmax));
+    CKS(build_block_list(sim, cell_size, false, sim->d_vmax, false));
     const int rec = sim->model == CDB_MODEL_CIRCULAR ? REC_CIRC : REC_THREE;
     const int ny = (int)sim->grid.ny;
     if (sim->has_left && halo_left_out)

@@ -413,9 +413,19 @@ __global__ void k_cell_count(Soa s, int n, double cell_size, const Grid *grid, i
         }
     }
     if (vmax) {
+        // block-level reduction first: two single-address atomics per block instead of per warp
+        __shared__ unsigned long long s_vm[32], s_v0[32];
         unsigned long long vm = warp_max_u64(ordered_bits(v_max));
         v0 = warp_max_u64(v0);
-        if ((threadIdx.x & 31) == 0) { atomicMax(&vmax[0], vm); atomicMax(&vmax[1], v0); }
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+        if (lane == 0) { s_vm[warp] = vm; s_v0[warp] = v0; }
+        __syncthreads();
+        if (warp == 0) {
+            vm = lane < nwarp ? s_vm[lane] : 0ULL;
+            v0 = lane < nwarp ? s_v0[lane] : 0ULL;
+            vm = warp_max_u64(vm); v0 = warp_max_u64(v0);
+            if (lane == 0) { atomicMax(&vmax[0], vm); atomicMax(&vmax[1], v0); }
+        }
     }
 }
 
@@ -533,17 +543,46 @@ __global__ void k_gather(Soa src, Soa dst, int n, int n_planes, int model, const
     }
 }
 
-__global__ void k_export_cell_ids(const int *__restrict__ id, const int *__restrict__ cell_sorted, int n, long long *out) {
+// packed neighbour records in cell order WITHOUT moving the planes (the fused step kernel reads its own agent through
+// `order` and writes the new state in cell order, so the physical sort happens as a by-product of the step):
+//   circular      {px, py, vx, vy, radius, -}                                                   48 B
+//   three-circle  {px, py, vx, vy, extent, r_t, r_s, - | lsx, lsy, rsx, rsy, ox, oy, -, -}     128 B (one line)
+// extent = conservative radius of the whole body around the centre (from the STORED shoulder positions), (ox, oy) =
+// r_ts (sin phi, -cos phi), the shoulder displacement of power_law.py:338-350.
+__global__ void k_records(Soa src, int n, int model, const int *__restrict__ order,
+                         const int *__restrict__ cell_of_slot, int *__restrict__ cell_sorted, double *__restrict__ nbr) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t < n) out[id[t]] = cell_sorted[t];
+    if (t >= n) return;
+    const int o = order[t];
+    cell_sorted[t] = cell_of_slot[o];
+    const double x = src(PX, o), y = src(PY, o), vx = src(VX, o), vy = src(VY, o);
+    if (model == CDB_MODEL_CIRCULAR) {
+        double2 *r = reinterpret_cast<double2 *>(nbr + (size_t)t * 6);
+        r[0] = make_double2(x, y); r[1] = make_double2(vx, vy); r[2] = make_double2(src(RADIUS, o), 0.0);
+    } else {
+        const double phi = src(PHI, o), r_ts = src(R_TS, o), r_t = src(R_T, o), r_s = src(R_S, o);
+        const double lsx = src(LSX, o), lsy = src(LSY, o), rsx = src(RSX, o), rsy = src(RSY, o);
+        const double dl = hypot(lsx - x, lsy - y), dr = hypot(rsx - x, rsy - y);
+        const double ext = fmax(r_t, fmax(dl, dr) + r_s) * (1.0 + 1e-12);
+        double2 *r = reinterpret_cast<double2 *>(nbr + (size_t)t * 16);
+        r[0] = make_double2(x, y); r[1] = make_double2(vx, vy); r[2] = make_double2(ext, r_t); r[3] = make_double2(r_s, 0.0);
+        r[4] = make_double2(lsx, lsy); r[5] = make_double2(rsx, rsy);
+        r[6] = make_double2(r_ts * sin(phi), r_ts * -cos(phi)); r[7] = make_double2(0.0, 0.0);
+    }
 }
-__global__ void k_widen(const int *__restrict__ in, int n, long long *out) {
+
+// perm: sorted slot -> slot of the planes (nullptr when the planes are physically in cell order)
+__global__ void k_export_cell_ids(const int *__restrict__ id, const int *__restrict__ perm, const int *__restrict__ cell_sorted, int n, long long *out) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t < n) out[t] = in[t];
+    if (t < n) out[id[perm ? perm[t] : t]] = cell_sorted[t];
+}
+__global__ void k_widen(const int *__restrict__ in, const int *__restrict__ perm, int n, long long *out) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) out[t] = in[perm ? perm[t] : t];
 }
 
 // candidate pairs of the block list, forward half stencil (0,0)+, (0,+1), (+1,-1), (+1,0), (+1,+1)
-__global__ void k_export_pairs(const int *__restrict__ id, int n, const Grid *grid, const int *__restrict__ cell_sorted,
+__global__ void k_export_pairs(const int *__restrict__ id, const int *__restrict__ perm, int n, const Grid *grid, const int *__restrict__ cell_sorted,
                                const int *__restrict__ cell_start, const int *__restrict__ cell_count, long long *pairs,
                                long long cap, unsigned long long *count) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -551,7 +590,7 @@ __global__ void k_export_pairs(const int *__restrict__ id, int n, const Grid *gr
     const Grid g = *grid;
     const int c = cell_sorted[t];
     const long long cx = c / g.ny, cy = c % g.ny;
-    const long long me = id[t];
+    const long long me = id[perm ? perm[t] : t];
     const int sx[5] = {0, 0, 1, 1, 1}, sy[5] = {0, 1, -1, 0, 1};
     for (int k = 0; k < 5; ++k) {
         long long x2 = cx + sx[k], y2 = cy + sy[k];
@@ -560,7 +599,7 @@ __global__ void k_export_pairs(const int *__restrict__ id, int n, const Grid *gr
         int b = k == 0 ? t + 1 : cell_start[d], e = cell_start[d] + cell_count[d];
         for (int u = b; u < e; ++u) {
             unsigned long long slot = atomicAdd(count, 1ULL);
-            if ((long long)slot < cap) { pairs[2 * slot] = me; pairs[2 * slot + 1] = id[u]; }
+            if ((long long)slot < cap) { pairs[2 * slot] = me; pairs[2 * slot + 1] = id[perm ? perm[u] : u]; }
         }
     }
 }

@@ -43,6 +43,7 @@ struct StepArgs {
     int n;
     const Grid *grid;
     const int *cell_sorted, *cell_start, *cell_count;
+    const int *order;        // sorted slot -> slot of `in` holding that agent (nullptr: `in` is physically in cell order)
     const NavField *nav;
     int n_nav;
     const double *obs;
@@ -188,21 +189,22 @@ __global__ void __launch_bounds__(STEP_THREADS, MODEL == 0 ? STEP_MINB_CIRC : ST
     const Soa &s = A.in;
     const unsigned FULL = 0xffffffffu;
     const int tt = active ? t : 0;       // inactive lanes read slot 0 and never write
+    const int oo = A.order ? A.order[tt] : tt;   // where this agent's planes live in `in`
     constexpr int REC = MODEL == 0 ? REC_CIRC : REC_THREE;
 
     // ---- Navigation, Orientation, Adjusting (logic.py:149-165,258-261,89-94) --------------------------------------------
-    double e0x = s(E0X, tt), e0y = s(E0Y, tt);
-    double fx = s(FX, tt), fy = s(FY, tt), tq = 0.0, phi0 = 0.0;
-    if (MODEL == 1) { tq = s(TORQUE, tt); phi0 = s(PHI0, tt); }
+    double e0x = s(E0X, oo), e0y = s(E0Y, oo);
+    double fx = s(FX, oo), fy = s(FY, oo), tq = 0.0, phi0 = 0.0;
+    if (MODEL == 1) { tq = s(TORQUE, oo); phi0 = s(PHI0, oo); }
     {
-        const double px = s(PX, tt), py = s(PY, tt);
-        if (A.flags & CDB_STEP_NAVIGATION) navigation_sample(A.nav, A.n_nav, s.target[tt], px, py, e0x, e0y);
+        const double px = s(PX, oo), py = s(PY, oo);
+        if (A.flags & CDB_STEP_NAVIGATION) navigation_sample(A.nav, A.n_nav, s.target[oo], px, py, e0x, e0y);
         if (MODEL == 1 && (A.flags & CDB_STEP_ORIENTATION)) phi0 = atan2(e0y, e0x);
         if (A.flags & CDB_STEP_ADJUSTING) {
             double ax, ay;
-            adjust_force(s(MASS, tt), s(TAU_ADJ, tt), s(V0, tt), e0x, e0y, s(VX, tt), s(VY, tt), ax, ay);
+            adjust_force(s(MASS, oo), s(TAU_ADJ, oo), s(V0, oo), e0x, e0y, s(VX, oo), s(VY, oo), ax, ay);
             fx += ax; fy += ay;
-            if (MODEL == 1) tq += adjust_torque(s(INERTIA, tt), s(TAU_ROT, tt), phi0, s(PHI, tt), s(OMEGA0, tt), s(OMEGA, tt));
+            if (MODEL == 1) tq += adjust_torque(s(INERTIA, oo), s(TAU_ROT, oo), phi0, s(PHI, oo), s(OMEGA0, oo), s(OMEGA, oo));
         }
     }
 
@@ -241,7 +243,8 @@ __global__ void __launch_bounds__(STEP_THREADS, MODEL == 0 ? STEP_MINB_CIRC : ST
                     for (int o = 16; o; o >>= 1) if (W.pre[l + o] <= f) l += o;
                     const int u = W.list[(f - W.pre[l]) * 32 + l];
                     const int tg = t0 + l;    // the target this entry belongs to
-                    const ThreePar par = {s(MASS, tg), s(K_SOC, tg), s(TAU_0, tg), s(MU, tg), s(KAPPA, tg), s(DAMPING, tg)};
+                    const int og = A.order ? A.order[tg] : tg;
+                    const ThreePar par = {s(MASS, og), s(K_SOC, og), s(TAU_0, og), s(MU, og), s(KAPPA, og), s(DAMPING, og)};
                     if (MODEL == 0) {
                         const double *rm = nbr + (size_t)tg * REC, *ro = nbr + (size_t)u * REC;
                         const double2 p = ldg2(rm), v = ldg2(rm + 2), po = ldg2(ro), vo = ldg2(ro + 2);
@@ -341,15 +344,15 @@ __global__ void __launch_bounds__(STEP_THREADS, MODEL == 0 ? STEP_MINB_CIRC : ST
     if (!active) return;
 
     // ---- own state for the wall and integrator parts ------------------------------------------------------------------------
-    const double px = s(PX, t), py = s(PY, t), vx = s(VX, t), vy = s(VY, t), mass = s(MASS, t);
-    const double mu = s(MU, t), kappa = s(KAPPA, t), damping = s(DAMPING, t);
+    const double px = s(PX, oo), py = s(PY, oo), vx = s(VX, oo), vy = s(VY, oo), mass = s(MASS, oo);
+    const double mu = s(MU, oo), kappa = s(KAPPA, oo), damping = s(DAMPING, oo);
 
     // ---- AgentObstacleInteractions (interactions.py:208-214) ---------------------------------------------------------------
     if ((A.flags & CDB_STEP_AGENT_OBSTACLE) && A.n_obs > 0) {
         if (MODEL == 0) {
-            walls_circular(px, py, s(RADIUS, t), vx, vy, mu, kappa, damping, A.obs, A.n_obs, fx, fy);
+            walls_circular(px, py, s(RADIUS, oo), vx, vy, mu, kappa, damping, A.obs, A.n_obs, fx, fy);
         } else {
-            walls_three_circle(px, py, s(LSX, t), s(LSY, t), s(RSX, t), s(RSY, t), s(R_T, t), s(R_S, t), vx, vy, mu, kappa, damping,
+            walls_three_circle(px, py, s(LSX, oo), s(LSY, oo), s(RSX, oo), s(RSY, oo), s(R_T, oo), s(R_S, oo), vx, vy, mu, kappa, damping,
                                A.obs, A.n_obs, fx, fy, tq);
         }
     }
@@ -358,9 +361,9 @@ __global__ void __launch_bounds__(STEP_THREADS, MODEL == 0 ? STEP_MINB_CIRC : ST
     const bool rst = A.flags & CDB_STEP_RESET;
     if (!(A.flags & CDB_STEP_INTEGRATOR)) {
         // node-wise use: publish what the selected nodes wrote, in place
-        o(E0X, t) = e0x; o(E0Y, t) = e0y;
-        o(FX, t) = rst ? 0.0 : fx; o(FY, t) = rst ? 0.0 : fy;
-        if (MODEL == 1) { o(PHI0, t) = phi0; o(TORQUE, t) = rst ? 0.0 : tq; }
+        o(E0X, oo) = e0x; o(E0Y, oo) = e0y;
+        o(FX, oo) = rst ? 0.0 : fx; o(FY, oo) = rst ? 0.0 : fy;
+        if (MODEL == 1) { o(PHI0, oo) = phi0; o(TORQUE, oo) = rst ? 0.0 : tq; }
         return;
     }
 
@@ -371,25 +374,25 @@ __global__ void __launch_bounds__(STEP_THREADS, MODEL == 0 ? STEP_MINB_CIRC : ST
         if (A.dt_log) *A.dt_log = dt;
     }
     double nvx = vx, nvy = vy, npx = px, npy = py;
-    verlet(fx, s(FPX, t), mass, dt, nvx, npx);
-    verlet(fy, s(FPY, t), mass, dt, nvy, npy);
+    verlet(fx, s(FPX, oo), mass, dt, nvx, npx);
+    verlet(fy, s(FPY, oo), mass, dt, nvy, npy);
     o(PX, t) = npx; o(PY, t) = npy; o(VX, t) = nvx; o(VY, t) = nvy;
     o(E0X, t) = e0x; o(E0Y, t) = e0y;
     o(FX, t) = rst ? 0.0 : fx; o(FY, t) = rst ? 0.0 : fy;
     o(FPX, t) = fx; o(FPY, t) = fy;
-    o(RADIUS, t) = s(RADIUS, t); o(MASS, t) = mass; o(V0, t) = s(V0, t); o(TAU_ADJ, t) = s(TAU_ADJ, t);
-    o(K_SOC, t) = s(K_SOC, t); o(TAU_0, t) = s(TAU_0, t); o(MU, t) = mu; o(KAPPA, t) = kappa; o(DAMPING, t) = damping;
-    o.id[t] = s.id[t];
-    o.target[t] = s.target[t];
+    o(RADIUS, t) = s(RADIUS, oo); o(MASS, t) = mass; o(V0, t) = s(V0, oo); o(TAU_ADJ, t) = s(TAU_ADJ, oo);
+    o(K_SOC, t) = s(K_SOC, oo); o(TAU_0, t) = s(TAU_0, oo); o(MU, t) = mu; o(KAPPA, t) = kappa; o(DAMPING, t) = damping;
+    o.id[t] = s.id[oo];
+    o.target[t] = s.target[oo];
     if (MODEL == 1) {
-        const double inertia = s(INERTIA, t), r_ts = s(R_TS, t);
-        double w = s(OMEGA, t), phi = s(PHI, t);
-        verlet(tq, s(TORQUE_PREV, t), inertia, dt, w, phi);
+        const double inertia = s(INERTIA, oo), r_ts = s(R_TS, oo);
+        double w = s(OMEGA, oo), phi = s(PHI, oo);
+        verlet(tq, s(TORQUE_PREV, oo), inertia, dt, w, phi);
         phi = wrap_to_pi(phi);
         const double ox = sin(phi) * r_ts, oy = -cos(phi) * r_ts;   // shoulders(), agents.py:473-486
         o(LSX, t) = npx - ox; o(LSY, t) = npy - oy; o(RSX, t) = npx + ox; o(RSY, t) = npy + oy;
-        o(R_T, t) = s(R_T, t); o(R_S, t) = s(R_S, t); o(R_TS, t) = r_ts; o(INERTIA, t) = inertia; o(OMEGA0, t) = s(OMEGA0, t);
+        o(R_T, t) = s(R_T, oo); o(R_S, t) = s(R_S, oo); o(R_TS, t) = r_ts; o(INERTIA, t) = inertia; o(OMEGA0, t) = s(OMEGA0, oo);
         o(PHI, t) = phi; o(OMEGA, t) = w; o(PHI0, t) = phi0;
-        o(TORQUE, t) = rst ? 0.0 : tq; o(TORQUE_PREV, t) = tq; o(TAU_ROT, t) = s(TAU_ROT, t);
+        o(TORQUE, t) = rst ? 0.0 : tq; o(TORQUE_PREV, t) = tq; o(TAU_ROT, t) = s(TAU_ROT, oo);
     }
 }
