@@ -173,7 +173,7 @@ __device__ __forceinline__ void load_three_rec(const double *__restrict__ nbr, i
 
 // =====================================================================================================================
 #ifndef STEP_MINB_CIRC
-#define STEP_MINB_CIRC 5
+#define STEP_MINB_CIRC 8
 #endif
 #ifndef STEP_MINB_THREE
 #define STEP_MINB_THREE 4
