@@ -207,3 +207,31 @@ def hallway(seed=0, model='circular', size=50, width=40.0, height=5.0, ratio=1.0
     bounds = (0.0, 0.0, width, height)
     fields = [direction_field(step, bounds, 'x-'), direction_field(step, bounds, 'x+')]
     return agents, obstacles, fields
+
+
+def room_with_exit(n, model='circular', density=1.0, seed=0, door_width=1.2, hall_length=5.0, step=0.5):
+    """BASELINE config 4 flavour (reference examples/simulations.py:166-236, examples/fields.py:175-210): a square room
+    whose right wall has a door gap in the middle leading into an exit hall; 11 wall segments (3 room walls as one open
+    polyline + two 4-edge rectangles flanking the door, as geom_to_linear_obstacles would emit them); every agent has
+    target 0; the direction field points at the door (synthetic stand-in for the FMM field, same (U, V)[iy, ix] layout)."""
+    agents, _, side = uniform_crowd(n, model, density=density, seed=seed)
+    y_lo, y_hi = side / 2 - door_width / 2, side / 2 + door_width / 2
+    t = 0.3                                            # wall thickness of the two door posts
+    segs = [((side, 0.0), (0.0, 0.0)), ((0.0, 0.0), (0.0, side)), ((0.0, side), (side, side))]
+
+    def rect(x0, y0, x1, y1):
+        c = [(x0, y0), (x1, y0), (x1, y1), (x0, y1)]
+        return [(c[k], c[(k + 1) % 4]) for k in range(4)]
+    segs += rect(side, 0.0, side + t, y_lo) + rect(side, y_hi, side + t, side)
+    obstacles = np.zeros(len(segs), dtype=obstacle_type_linear)
+    for k, (p0, p1) in enumerate(segs):
+        obstacles[k]['p0'], obstacles[k]['p1'] = p0, p1
+    agents['target'] = 0
+    bounds = (0.0, 0.0, side + hall_length, side)
+    fields = [direction_field(step, bounds, 'exit', point=(side + 0.5 * t, side / 2))]
+    e = np.stack((side - agents['position'][:, 0], side / 2 - agents['position'][:, 1]), axis=1)
+    e /= np.hypot(*e.T)[:, None]
+    agents['target_direction'] = e
+    if model != 'circular':
+        agents['target_orientation'] = np.arctan2(e[:, 1], e[:, 0])
+    return agents, obstacles, fields, side

@@ -65,3 +65,26 @@ def test_resident_nodes_and_host_sync():
     sim.update(); O.step(ref, obstacles, fields, 3.6, 0.01, 0.01)
     sim.logic.state.sync_host()
     assert np.abs(agents['position'] - ref['position']).max() <= 1e-9
+
+
+@pytest.mark.parametrize('model', ['circular', 'three_circle'])
+def test_room_evacuation_style_config(model):
+    """BASELINE config 4 flavour at test size: room with a door, 11 wall segments, static exit field, all target 0;
+    40 fused resident updates against the oracle."""
+    agents, obstacles, fields, side = S.room_with_exit(4000, model, density=2.0, seed=6)
+    assert len(obstacles) == 11
+    ref = agents.copy()
+    sim = L.MultiAgentSimulation(agents, obstacles, fields)
+    sim.logic = L.FusedStep(sim, dt_min=0.001, dt_max=0.01, steps_per_update=10, step=0.5)
+    t = 0.0
+    for _ in range(4):
+        sim.update()
+        for _ in range(10):
+            t += O.step(ref, obstacles, fields, 3.6, 0.001, 0.01)
+    sim.logic.state.sync_host()
+    assert abs(sim.data['time_tot'] - t) <= 1e-12
+    assert np.abs(agents['position'] - ref['position']).max() <= 1e-8
+    assert np.abs(agents['velocity'] - ref['velocity']).max() <= 1e-6
+    # the crowd heads for the door
+    d0 = np.hypot(side - ref['position'][:, 0], side / 2 - ref['position'][:, 1]).mean()
+    assert np.hypot(side - agents['position'][:, 0], side / 2 - agents['position'][:, 1]).mean() <= d0 + 1e-9
