@@ -76,11 +76,9 @@ __device__ __forceinline__ double sel3(int k, double a, double b, double c) { re
 __device__ __forceinline__ void pair_three_exact(const Three &I, const Three &J, bool me_is_i, const ThreePar &me,
                                                  double &fx, double &fy, double &torque) {
     const double jx[3] = {J.x0, J.x1, J.x2}, jy[3] = {J.y0, J.y1, J.y2}, rj[3] = {J.rt, J.rs, J.rs};
-    const double ixs[3] = {I.x0, I.x1, I.x2}, iys[3] = {I.y0, I.y1, I.y2};   // statically indexed only (pj unrolled)
     // distance_three_circles (distance.py:55-105): strict '<', first wins, order torso, left, right
     double h_min = nan(""), sx = 0.0, sy = 0.0, sd = 0.0;   // selected x, y, d (normal = x / d computed once, same value)
-    double mix = 0.0, miy = 0.0, mir = 0.0;                  // x0[i_min], r0[i_min]
-    double qx = 0.0, qy = 0.0, mjr = 0.0;                    // x0[j_min] (the :103 quirk), r1[j_min]
+    int i_min = 0, j_min = 0;
 #pragma unroll 1
     for (int pi = 0; pi < 3; ++pi) {
         const double xi = sel3(pi, I.x0, I.x1, I.x2), yi = sel3(pi, I.y0, I.y1, I.y2), rip = pi == 0 ? I.rt : I.rs;
@@ -89,11 +87,7 @@ __device__ __forceinline__ void pair_three_exact(const Three &I, const Three &J,
             double x = xi - jx[pj], y = yi - jy[pj];
             double d = hypot(x, y);
             double h = d - (rip + rj[pj]);
-            if (h < h_min || isnan(h_min)) {
-                h_min = h; sx = x; sy = y; sd = d;
-                mix = xi; miy = yi; mir = rip;
-                qx = ixs[pj]; qy = iys[pj]; mjr = rj[pj];
-            }
+            if (h < h_min || isnan(h_min)) { h_min = h; sx = x; sy = y; sd = d; i_min = pi; j_min = pj; }
         }
     }
     if (!(h_min < SIGTH_SOC)) return;
@@ -106,7 +100,8 @@ __device__ __forceinline__ void pair_three_exact(const Three &I, const Three &J,
         // smallest time-to-collision over the 9 part pairs with the reference's selection rule (power_law.py:308-329):
         // `isnan(tau) or 0 < tau_new < tau`.  tau_new = (b - d) / a is monotone in its numerator, so the division is only
         // needed when the numerator is positive and smaller than the selected one -- same decisions, fewer divisions.
-        double tau = nan(""), num_sel = 0.0, b_min = 0.0, d_min = 0.0, oix = 0.0, oiy = 0.0, ojx = 0.0, ojy = 0.0;
+        double tau = nan(""), num_sel = 0.0, b_min = 0.0, d_min = 0.0;
+        int contact_i = 0, contact_j = 0;
 #pragma unroll 1
         for (int pi = 0; pi < 3; ++pi) {
             const double xi = sel3(pi, I.x0, I.x1, I.x2), yi = sel3(pi, I.y0, I.y1, I.y2), rip = pi == 0 ? I.rt : I.rs;
@@ -124,16 +119,13 @@ __device__ __forceinline__ void pair_three_exact(const Three &I, const Three &J,
                 double tau_new = 0.0;
                 if (isnan(tau)) { tau_new = num / a; take = true; }
                 else if (num > 0.0 && num < num_sel) { tau_new = num / a; take = 0.0 < tau_new && tau_new < tau; }
-                if (take) {
-                    tau = tau_new; num_sel = num; b_min = b; d_min = dd;
-                    // shoulder displacement of the contacting parts: 0 for the torso, +o for left, -o for right
-                    oix = sel3(pi, 0.0, I.ox, 0.0 - I.ox); oiy = sel3(pi, 0.0, I.oy, 0.0 - I.oy);
-                    ojx = pj == 0 ? 0.0 : (pj == 1 ? J.ox : 0.0 - J.ox);
-                    ojy = pj == 0 ? 0.0 : (pj == 1 ? J.oy : 0.0 - J.oy);
-                }
+                if (take) { tau = tau_new; num_sel = num; b_min = b; d_min = dd; contact_i = pi; contact_j = pj; }
             }
         }
         if (!(isnan(tau) || tau <= 0.0)) {
+            // shoulder displacement of the contacting parts: 0 for the torso, +o for left, -o for right
+            const double oix = sel3(contact_i, 0.0, I.ox, 0.0 - I.ox), oiy = sel3(contact_i, 0.0, I.oy, 0.0 - I.oy);
+            const double ojx = sel3(contact_j, 0.0, J.ox, 0.0 - J.ox), ojy = sel3(contact_j, 0.0, J.oy, 0.0 - J.oy);
             double xr = I.x0 - J.x0, yr = I.y0 - J.y0;
             double ox = oix - ojx, oy = oiy - ojy;
             double gx = (vx - (a * (xr + 2 * ox) + b_min * vx) / d_min) / a;   // power_law.py:131-149
@@ -152,8 +144,13 @@ __device__ __forceinline__ void pair_three_exact(const Three &I, const Three &J,
         if (me_is_i) { fsx += cx; fsy += cy; } else { fsx -= cx; fsy -= cy; }
     }
     double mx, my;   // moment arms, distance.py:102-103
-    if (me_is_i) { mx = mix + mir * nx - I.x0; my = miy + mir * ny - I.y0; }
-    else { mx = qx - mjr * nx - J.x0; my = qy - mjr * ny - J.y0; }
+    if (me_is_i) {    // x0[i_min] + r0[i_min] n - x0[0]
+        const double mir = i_min == 0 ? I.rt : I.rs;
+        mx = sel3(i_min, I.x0, I.x1, I.x2) + mir * nx - I.x0; my = sel3(i_min, I.y0, I.y1, I.y2) + mir * ny - I.y0;
+    } else {          // x0[j_min] - r1[j_min] n - x1[0]   (sic: agent i's part, distance.py:103)
+        const double mjr = j_min == 0 ? J.rt : J.rs;
+        mx = sel3(j_min, I.x0, I.x1, I.x2) - mjr * nx - J.x0; my = sel3(j_min, I.y0, I.y1, I.y2) - mjr * ny - J.y0;
+    }
     fx += fsx; fy += fsy;
     torque += mx * fsy - my * fsx;
 }
@@ -251,16 +248,13 @@ __global__ void __launch_bounds__(STEP_THREADS, MODEL == 0 ? STEP_MINB_CIRC : ST
                         const CircMe me = {p.x, p.y, v.x, v.y, __ldg(rm + 4), par.mass, par.k_soc, par.tau_0, par.mu, par.kappa, par.damping};
                         pair_circular(me, po.x, po.y, vo.x, vo.y, __ldg(ro + 4), rfx, rfy);
                     } else {
-                        Three me, other;
-                        load_three_rec(nbr, tg, me);
-                        load_three_rec(nbr, u, other);
                         // reference pair orientation: i is the lexicographically smaller (cell_x, cell_y, agent index):
                         // cell order, then (same cell => both owned) the order of the cell-sorted slots
                         const int ctg = A.cell_sorted[tg], cu = A.cell_sorted[u];
                         const bool me_is_i = ctg < cu || (ctg == cu && tg < u);   // ghosts never share a cell with owned agents
-                        Three I, J;     // one inlined copy of the pair arithmetic: select the roles instead of branching
-                        sel_three(me_is_i, me, other, I);
-                        sel_three(me_is_i, other, me, J);
+                        Three I, J;     // loaded straight into their roles: one inlined copy of the pair arithmetic, no selects
+                        load_three_rec(nbr, me_is_i ? tg : u, I);
+                        load_three_rec(nbr, me_is_i ? u : tg, J);
                         pair_three_exact(I, J, me_is_i, par, rfx, rfy, rtq);
                     }
                 }
