@@ -29,6 +29,33 @@ ALGO_BYTES = {'circular': 184 + 16, 'three_circle': 312 + 16}   # s
 CELL = 3.6
 
 
+def profile_counters(model, n_agents, density):
+    """DRAM traffic and fp64 instruction count of ONE launch of the dominant kernel from the committed ncu --set full
+    summary (profiles/ncu_full_<model>_<tag>.txt) -- only valid for the workload that was profiled (1 M agents, 1 /m^2)."""
+    if n_agents != 1000000 or abs(density - 1.0) > 1e-12:
+        return None
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, 'profiles', 'ncu_full_%s_*.txt' % model)))
+    if not files:
+        return None
+    out = {'source': os.path.relpath(files[-1], ROOT)}
+    unit_scale = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
+    with open(files[-1]) as f:
+        for line in f:
+            c = line.split()
+            if len(c) < 2:
+                continue
+            try:
+                if c[0] in ('dram__bytes_read.sum', 'dram__bytes_write.sum'):
+                    out[c[0]] = float(c[-1].replace(',', '')) * unit_scale.get(c[1], 1.0)
+                elif c[0] in ('smsp__inst_executed_pipe_fp64.sum', 'sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active',
+                              'gpu__time_duration.sum'):
+                    out[c[0]] = float(c[-1].replace(',', ''))
+            except ValueError:
+                pass
+    return out
+
+
 def measured_peaks():
     p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(p):
@@ -295,18 +322,40 @@ def main():
         k_ms = prof[1] / prof[3]                      # dominant kernel: agent-agent (+ fused epilogue)
         algo_bytes = ALGO_BYTES[args.model] * n_rank0
         achieved = algo_bytes / (k_ms * 1e-3) / 1e9
-        roofline = {'bound': 'hbm', 'kernel': 'agent_agent', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
-                    'frac': achieved / peak, 'peak_source': peak_src, 'traffic': None,
+        pc = profile_counters(args.model, n_rank0, args.density)
+        traffic = None
+        if pc and 'dram__bytes_read.sum' in pc:
+            traffic = pc['dram__bytes_read.sum'] + pc['dram__bytes_write.sum']
+        roofline = {'bound': 'hbm', 'kernel': 'k_step<%s> (fused agent-agent + walls + integrator)' % args.model,
+                    'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+                    'frac': achieved / peak, 'peak_source': peak_src, 'traffic': traffic,
+                    'traffic_source': pc['source'] if pc else None,
                     'kernel_ms': k_ms, 'algorithmic_bytes_per_launch': algo_bytes,
                     'phase_ms_per_step': {'pre_and_block_list': prof[0] / prof[3], 'agent_agent': k_ms,
                                           'post': prof[2] / prof[3]},
                     'note': 'the pair kernel is FP64-pipe bound at this density (SURVEY 7): HBM fraction is low by '
                             'construction; see DESIGN.md for the FP64 roofline'}
+    # fp64 roofline of the same kernel: DFMA peak measured live, fp64 warp-instructions per launch from the committed profile
+    fp64 = None
+    try:
+        import ctypes as C
+        tf = C.c_double()
+        _lib.check(_lib.load().cdb_measure_fp64_peak(local_rank, C.byref(tf)))
+        fp64 = {'peak_tflops_measured_dfma': tf.value}
+        if roofline and pc and 'smsp__inst_executed_pipe_fp64.sum' in pc:
+            # one fp64 warp-instruction = 32 lanes; counted as 1 flop/lane (an FMA would be 2): utilisation of the pipe
+            inst = pc['smsp__inst_executed_pipe_fp64.sum']
+            rate = inst * 32 / (roofline['kernel_ms'] * 1e-3)
+            fp64.update({'fp64_warp_instructions_per_launch': inst, 'achieved_lane_ops_per_s': rate,
+                         'pipe_frac_live': rate / (tf.value * 1e12 / 2.0),
+                         'pipe_frac_ncu': pc.get('sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active')})
+    except Exception as exc:   # pragma: no cover
+        fp64 = {'error': str(exc)}
     line = {
         'metric': 'agent-steps/sec', 'value': value, 'unit': 'agent-steps/s', 'n_gpus': world, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic', 'config': workload_config(args, n, world),
-        'gpu_launches': launches, 'clocks': clocks, 'roofline': roofline, 'e2e': e2e,
+        'gpu_launches': launches, 'clocks': clocks, 'roofline': roofline, 'roofline_fp64': fp64, 'e2e': e2e,
         'hbm_fraction_whole_step': value / world * ALGO_BYTES[args.model] / 1e9 / peak,
     }
     if world == 1 and not args.no_cpu_baseline:

@@ -42,6 +42,7 @@ def _signatures(L):
         'cdb_last_error': (C.c_char_p, []),
         'cdb_version': (i32, []),
         'cdb_device_count': (i32, [C.POINTER(i32)]),
+        'cdb_measure_fp64_peak': (i32, [i32, pf64]),
         'cdb_create': (i32, [i32, i32, i64, C.POINTER(vp)]),
         'cdb_destroy': (i32, [vp]),
         'cdb_set_stream': (i32, [vp, vp]),

@@ -400,6 +400,32 @@ int cdb_device_count(int *count) {
     return CDB_OK;
 }
 
+int cdb_measure_fp64_peak(int device, double *tflops) {
+    if (!tflops) return fail(CDB_ERR_INVALID_VALUE, "tflops is NULL");
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    double *d = nullptr;
+    CK(cudaMalloc((void **)&d, sizeof(double)));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 15;
+    double best = 0.0;
+    for (int rep = 0; rep < 4; ++rep) {
+        CK(cudaEventRecord(e0));
+        k_dfma_peak<<<blocks, threads>>>(d, iters, 1.0 + rep);
+        CK(cudaEventRecord(e1));
+        CK(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        const double flops = 2.0 * 8.0 * (double)iters * blocks * threads;
+        if (rep > 0 && flops / (ms * 1e-3) > best) best = flops / (ms * 1e-3);
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+    *tflops = best * 1e-12;
+    return CDB_OK;
+}
+
 int cdb_create(int device, int model, int64_t capacity, cdb_sim **out) {
     if (!out) return fail(CDB_ERR_INVALID_VALUE, "out is NULL");
     *out = nullptr;

@@ -850,3 +850,16 @@ k_agent_agent_three_circle_v1(Soa s, int n, const Grid *grid, const int *__restr
     }
     s(FX, t) += fx; s(FY, t) += fy; s(TORQUE, t) += tq;
 }
+
+// =====================================================================================================================
+// FP64 roofline denominator: DFMA throughput measured on the device (MEASURED_PEAKS.json has no fp64 entry)
+// =====================================================================================================================
+__global__ void k_dfma_peak(double *out, int iters, double seed) {
+    double a0 = seed + threadIdx.x, a1 = a0 + 1.0, a2 = a0 + 2.0, a3 = a0 + 3.0, a4 = a0 + 4.0, a5 = a0 + 5.0, a6 = a0 + 6.0, a7 = a0 + 7.0;
+    const double m = 0.999999, c = 1e-9;
+    for (int i = 0; i < iters; ++i) {
+        a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+        a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+    if (a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7 == 123.456) out[0] = a0;   // keep the chains alive
+}

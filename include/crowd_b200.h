@@ -72,6 +72,8 @@ enum {
 const char *cdb_last_error(void);
 int cdb_version(void);
 int cdb_device_count(int *count);
+/* DFMA throughput of the device in TFLOP/s (8 independent chains per thread): the fp64 roofline denominator. */
+int cdb_measure_fp64_peak(int device, double *tflops);
 
 /* ---- lifetime ---------------------------------------------------------------------------------------------------
  * Replaces: nothing in the reference (its state is the host array simulation.agents.array, agents.py:605-680);

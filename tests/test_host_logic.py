@@ -1,0 +1,85 @@
+"""Host-side pieces that need no GPU: the logic-tree surface mirrored from the reference (simulation/base.py:27-84,
+tests simulation/tests/test_base.py:15-22), the data contract, the synthetic workloads."""
+import numpy as np
+import pytest
+
+from crowddynamics_b200 import synthetic as S
+from crowddynamics_b200.exceptions import InvalidType, CrowdDynamicsException
+from crowddynamics_b200.logic import LogicNodeBase, post_order_iter, pre_order_iter
+from crowddynamics_b200.structures import (agent_type_circular, agent_type_three_circle, obstacle_type_linear, as_obstacles,
+                                           model_of, is_model, MODEL_CIRCULAR, MODEL_THREE_CIRCLE)
+
+
+class Node(LogicNodeBase):
+    def __init__(self, name):
+        super().__init__(name=name)
+        self.calls = 0
+
+    def update(self):
+        self.calls += 1
+
+
+def test_tree_composition_matches_reference_semantics():
+    # examples/simulations.py:123-136: `<<` is left associative and returns self
+    reset, inside, integ, fluct, adj, nav, ori, aa, ao = (Node(n) for n in (
+        'Reset', 'InsideDomain', 'Integrator', 'Fluctuation', 'Adjusting', 'Navigation', 'Orientation',
+        'AgentAgentInteractions', 'AgentObstacleInteractions'))
+    tree = reset << inside << (integ << (fluct, adj << (nav, ori), aa, ao))
+    assert tree is reset and reset.children == (inside, integ)
+    order = [n.name for n in post_order_iter(reset)]
+    assert order == ['InsideDomain', 'Fluctuation', 'Navigation', 'Orientation', 'Adjusting', 'AgentAgentInteractions',
+                     'AgentObstacleInteractions', 'Integrator', 'Reset']
+    assert [n.name for n in pre_order_iter(reset)][0] == 'Reset'
+    assert reset['Adjusting'] is adj and nav.root is reset
+    with pytest.raises(KeyError):
+        reset['Nope']
+    for n in post_order_iter(reset):
+        n.update()
+    assert all(n.calls == 1 for n in pre_order_iter(reset))
+
+
+def test_inject_before_and_after():
+    a, b, c, d = Node('a'), Node('b'), Node('c'), Node('d')
+    a << (b, c)
+    b.inject_before(d)          # d takes b's place, b becomes d's child
+    assert d.parent is a and b.parent is d
+    e = Node('e')
+    a.inject_after(e)           # e adopts a's children and hangs under a
+    assert e.parent is a and a.children == (e,) and set(e.children) == {c, d}
+
+
+def test_data_contract():
+    assert agent_type_circular.itemsize == 228 and agent_type_three_circle.itemsize == 316
+    assert agent_type_circular.fields['position'][1] == 92 and agent_type_circular.fields['radius'][1] == 28
+    assert agent_type_three_circle.fields['position'][1] == 124 and agent_type_three_circle.fields['orientation'][1] == 260
+    assert agent_type_three_circle.fields['std_rand_torque'][1] == 308
+    a = np.zeros(3, dtype=agent_type_circular)
+    assert model_of(a) == MODEL_CIRCULAR and model_of(np.zeros(1, dtype=agent_type_three_circle)) == MODEL_THREE_CIRCLE
+    assert is_model(a, 'circular') and not is_model(a, 'three_circle')
+    with pytest.raises(InvalidType):
+        model_of(np.zeros(2, dtype=obstacle_type_linear))
+    with pytest.raises(InvalidType):
+        model_of(np.zeros(2))
+    assert issubclass(InvalidType, CrowdDynamicsException)
+    obs = S.walls_of_box(0, 0, 2, 3)
+    assert as_obstacles(obs).shape == (4, 4) and as_obstacles(None).shape == (0, 4)
+    assert (as_obstacles(obs) == as_obstacles(as_obstacles(obs))).all()
+
+
+def test_synthetic_workloads_are_seeded_and_sane():
+    a1, o1, s1 = S.uniform_crowd(500, 'three_circle', density=1.0, seed=3)
+    a2, o2, s2 = S.uniform_crowd(500, 'three_circle', density=1.0, seed=3)
+    assert (a1.view(np.uint8) == a2.view(np.uint8)).all() and s1 == s2
+    # non-overlapping jittered lattice, adult body ranges (conf/body_types.cfg)
+    d = np.hypot(*(a1['position'][:, None] - a1['position'][None]).transpose(2, 0, 1)) + np.eye(500) * 10
+    assert d.min() > 2 * 0.29
+    assert (a1['radius'] >= 0.22).all() and (a1['radius'] <= 0.29).all() and (a1['mass'] >= 65.5).all()
+    off = np.stack((np.sin(a1['orientation']), -np.cos(a1['orientation'])), 1) * a1['r_ts'][:, None]
+    assert np.allclose(a1['position_ls'], a1['position'] - off)
+    ag, ob, fields = S.hallway(seed=0)
+    assert len(ag) == 50 and len(ob) == 2 and len(fields) == 2 and set(ag['target']) == {0, 1}
+    mg, (U, V) = fields[1]
+    assert U.shape == mg.shape == (51, 401) and (U == 1).all() and (V == 0).all()
+    assert mg.indicer(np.array([[0.05, 0.19], [39.99, 4.99]])).tolist() == [[0, 1], [399, 49]]
+    ar, obr, fr, side = S.room_with_exit(300, 'circular')
+    assert len(obr) == 11 and (ar['target'] == 0).all()
