@@ -211,6 +211,7 @@ def main():
     ap.add_argument('--density', type=float, default=1.0)
     ap.add_argument('--cpu-agents', type=int, default=0, help='agents in the CPU baseline sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-fp64-peak', action='store_true', help='skip the DFMA peak micro-benchmark (used under ncu)')
     ap.add_argument('--e2e-steps', type=int, default=3)
     args = ap.parse_args()
 
@@ -338,19 +339,23 @@ def main():
     # fp64 roofline of the same kernel: DFMA peak measured live, fp64 warp-instructions per launch from the committed profile
     fp64 = None
     try:
+        if args.no_fp64_peak:
+            raise RuntimeError('skipped (--no-fp64-peak)')
         import ctypes as C
         tf = C.c_double()
         _lib.check(_lib.load().cdb_measure_fp64_peak(local_rank, C.byref(tf)))
         fp64 = {'peak_tflops_measured_dfma': tf.value}
-        if roofline and pc and 'smsp__inst_executed_pipe_fp64.sum' in pc:
-            # one fp64 warp-instruction = 32 lanes; counted as 1 flop/lane (an FMA would be 2): utilisation of the pipe
-            inst = pc['smsp__inst_executed_pipe_fp64.sum']
-            rate = inst * 32 / (roofline['kernel_ms'] * 1e-3)
-            fp64.update({'fp64_warp_instructions_per_launch': inst, 'achieved_lane_ops_per_s': rate,
-                         'pipe_frac_live': rate / (tf.value * 1e12 / 2.0),
-                         'pipe_frac_ncu': pc.get('sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active')})
+        key = 'sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active'
+        if roofline and pc and key in pc and 'gpu__time_duration.sum' in pc:
+            # fp64-pipe utilisation of the profiled launch, rescaled to the live kernel duration (same instruction count)
+            with open(os.path.join(ROOT, pc['source'])) as f:
+                unit = [l.split()[1] for l in f if l.startswith('gpu__time_duration.sum')][0]
+            t_ncu_ms = pc['gpu__time_duration.sum'] * {'us': 1e-3, 'ms': 1.0, 'ns': 1e-6, 's': 1e3}.get(unit, 1.0)
+            fp64.update({'pipe_frac_ncu': pc[key] / 100.0, 'kernel_ms_ncu': t_ncu_ms,
+                         'pipe_frac_live': pc[key] / 100.0 * t_ncu_ms / roofline['kernel_ms'],
+                         'source': pc['source']})
     except Exception as exc:   # pragma: no cover
-        fp64 = {'error': str(exc)}
+        fp64 = {'note': str(exc)}
     line = {
         'metric': 'agent-steps/sec', 'value': value, 'unit': 'agent-steps/s', 'n_gpus': world, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',

@@ -1,10 +1,10 @@
 set -x
 mkdir -p gpurun_out
 for m in three_circle circular; do
-  ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_${m}_r1.csv python bench.py --model $m --steps 3 --warmup 3 --no-cpu-baseline --e2e-steps 1 > gpurun_out/launches_${m}.log 2>&1
-  ncu --set full --clock-control none --import-source on -k regex:k_step -s 3 -c 1 -o gpurun_out/prof_${m}_r1b -f python bench.py --model $m --steps 2 --warmup 3 --no-cpu-baseline --e2e-steps 1 > gpurun_out/ncu_${m}.log 2>&1
+  ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_${m}_r1.csv python bench.py --model $m --steps 3 --warmup 3 --no-cpu-baseline --no-fp64-peak --e2e-steps 1 > gpurun_out/launches_${m}.log 2>&1
+  ncu --set full --clock-control none --import-source on -k regex:k_step -s 3 -c 1 -o gpurun_out/prof_${m}_r1d -f python bench.py --model $m --steps 2 --warmup 3 --no-cpu-baseline --e2e-steps 1 > gpurun_out/ncu_${m}.log 2>&1
 done
-python bench.py --steps 20 --warmup 5 > gpurun_out/bench_three_circle.json 2> gpurun_out/bench_three_circle.err
-python bench.py --model circular --steps 20 --warmup 5 > gpurun_out/bench_circular.json 2> gpurun_out/bench_circular.err
+python bench.py > gpurun_out/bench_three_circle.json 2> gpurun_out/bench_three_circle.err
+python bench.py --model circular > gpurun_out/bench_circular.json 2> gpurun_out/bench_circular.err
 python bench.py --impl reference --steps 3 > gpurun_out/bench_reference.json 2>&1
 tail -c 600 gpurun_out/bench_three_circle.json
