@@ -222,6 +222,9 @@ __global__ void __launch_bounds__(STEP_THREADS, MODEL == 0 ? STEP_MINB_CIRC : ST
         int cnt = 0;
 
         auto flush = [&]() {
+#ifdef SWEEP_ONLY
+            fx += (double)cnt; cnt = 0; return;
+#endif
             // flatten the ragged lists: pre[l] = first flattened index of lane l
             int incl = cnt;
 #pragma unroll
