@@ -23,6 +23,7 @@ F_WHOLE_RECORD = 1 << 31
 STEP_NAVIGATION, STEP_ORIENTATION, STEP_ADJUSTING, STEP_AGENT_AGENT, STEP_AGENT_OBSTACLE, STEP_INTEGRATOR, \
     STEP_RESET = (1 << k for k in range(7))
 STEP_ALL = (1 << 7) - 1
+STEP_FLUCTUATION = 1 << 7
 
 _lib = None
 
@@ -54,6 +55,8 @@ def _signatures(L):
         'cdb_set_navigation_field': (i32, [vp, i64, vp, vp, i64, i64, f64, f64, f64]),
         'cdb_clear_navigation': (i32, [vp]),
         'cdb_reset': (i32, [vp]),
+        'cdb_set_seed': (i32, [vp, C.c_uint64]),
+        'cdb_fluctuation': (i32, [vp]),
         'cdb_navigation': (i32, [vp]),
         'cdb_orientation': (i32, [vp]),
         'cdb_adjust': (i32, [vp]),

@@ -125,6 +125,8 @@ struct cdb_sim {
     int *h_error = nullptr;                 // pinned
     unsigned long long *d_pair_count = nullptr;
     int64_t iterations = 0;
+    unsigned long long seed = 0x9E3779B97F4A7C15ULL;   // Fluctuation
+    unsigned long long fluct_calls = 0;               // per-node Fluctuation calls (keeps successive calls independent)
 
     // strip decomposition
     bool strip = false;
@@ -332,6 +334,7 @@ StepArgs step_args(cdb_sim *sim, unsigned flags, double dt_min, double dt_max, d
     a.flags = flags;
     a.dt_min = dt_min; a.dt_max = dt_max;
     a.vmax = sim->d_vmax; a.dt_out = sim->d_dt; a.dt_log = dt_log;
+    a.seed = sim->seed; a.step = (unsigned long long)sim->iterations;
     return a;
 }
 
@@ -627,6 +630,15 @@ int cdb_clear_navigation(cdb_sim *sim) {
     CK(cudaSetDevice(sim->device))
 
 int cdb_reset(cdb_sim *sim) { SIM_ENTRY(); return node_reset(sim); }
+int cdb_set_seed(cdb_sim *sim, uint64_t seed) { SIM_ENTRY(); sim->seed = seed; sim->fluct_calls = 0; return CDB_OK; }
+int cdb_fluctuation(cdb_sim *sim) {
+    SIM_ENTRY();
+    // key the stream on a private call counter in the high half, so that node-wise calls never reuse a fused step's stream
+    const unsigned long long step = (1ULL << 63) | sim->fluct_calls++;
+    if (sim->n) LAUNCH(sim, k_fluctuation, cdiv(sim->n, 256), 256, 0, sim->cur, (int)sim->n, sim->model, sim->seed, step);
+    CK(cudaGetLastError());
+    return CDB_OK;
+}
 int cdb_navigation(cdb_sim *sim) { SIM_ENTRY(); return node_navigation(sim); }
 int cdb_orientation(cdb_sim *sim) { SIM_ENTRY(); return node_orientation(sim); }
 int cdb_adjust(cdb_sim *sim) { SIM_ENTRY(); return node_adjust(sim); }
@@ -655,6 +667,8 @@ int cdb_step(cdb_sim *sim, uint32_t flags, double cell_size, double dt_min, doub
         double *log_slot = (dt_out && (flags & CDB_STEP_INTEGRATOR)) ? sim->d_dt_log + (k % DT_LOG) : nullptr;
         if (sim->variant == 1) {
             // node-by-node path with the one-phase kernels (kept as an independent cross-check of the fused kernel)
+            if ((flags & CDB_STEP_FLUCTUATION) && sim->n)
+                LAUNCH(sim, k_fluctuation, cdiv(sim->n, 256), 256, 0, sim->cur, (int)sim->n, sim->model, sim->seed, (unsigned long long)sim->iterations);
             if (flags & CDB_STEP_NAVIGATION) CKS(node_navigation(sim));
             if (flags & CDB_STEP_ORIENTATION) CKS(node_orientation(sim));
             if (flags & CDB_STEP_ADJUSTING) CKS(node_adjust(sim));

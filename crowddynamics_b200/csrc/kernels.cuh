@@ -11,10 +11,12 @@
 enum Plane {
     PX, PY, VX, VY, E0X, E0Y, FX, FY, FPX, FPY,                 // position, velocity, target_direction, force, force_prev
     RADIUS, MASS, V0, TAU_ADJ, K_SOC, TAU_0, MU, KAPPA, DAMPING,  // per-agent constants
+    STD_RAND_FORCE,                                             // scale of the fluctuation force (Fluctuation node)
     NP_CIRC,
     LSX = NP_CIRC, LSY, RSX, RSY,                               // position_ls, position_rs
     R_T, R_S, R_TS, INERTIA, OMEGA0,                            // body constants (three-circle)
     PHI, OMEGA, PHI0, TORQUE, TORQUE_PREV, TAU_ROT,             // orientation, angular_velocity, target_orientation, ...
+    STD_RAND_TORQUE,
     NP_THREE
 };
 
@@ -55,19 +57,19 @@ constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
     {E0X, B + 124, CDB_F_TARGET_DIRECTION}, {E0Y, B + 132, CDB_F_TARGET_DIRECTION}, {FX, B + 140, CDB_F_FORCE},   \
     {FY, B + 148, CDB_F_FORCE}, {FPX, B + 156, CDB_F_FORCE_PREV}, {FPY, B + 164, CDB_F_FORCE_PREV},            \
     {TAU_ADJ, B + 172, 0}, {K_SOC, B + 180, 0}, {TAU_0, B + 188, 0}, {MU, B + 196, 0}, {KAPPA, B + 204, 0},     \
-    {DAMPING, B + 212, 0}
+    {DAMPING, B + 212, 0}, {STD_RAND_FORCE, B + 220, 0}
 #define THREE_FIELDS                                                                                           \
     {LSX, 0, CDB_F_SHOULDERS}, {LSY, 8, CDB_F_SHOULDERS}, {RSX, 16, CDB_F_SHOULDERS}, {RSY, 24, CDB_F_SHOULDERS}, \
     {R_T, 32 + 36, 0}, {R_S, 32 + 44, 0}, {R_TS, 32 + 52, 0}, {INERTIA, 32 + 68, 0}, {OMEGA0, 32 + 84, 0},     \
     {PHI, 260, CDB_F_ORIENTATION}, {OMEGA, 268, CDB_F_ANGULAR_VELOCITY}, {PHI0, 276, CDB_F_TARGET_ORIENTATION}, \
-    {TORQUE, 284, CDB_F_TORQUE}, {TORQUE_PREV, 292, CDB_F_TORQUE_PREV}, {TAU_ROT, 300, 0}
+    {TORQUE, 284, CDB_F_TORQUE}, {TORQUE_PREV, 292, CDB_F_TORQUE_PREV}, {TAU_ROT, 300, 0}, {STD_RAND_TORQUE, 308, 0}
 
 __constant__ FieldMap c_fields_circ[] = {CIRC_FIELDS(0)};
 __constant__ FieldMap c_fields_three[] = {CIRC_FIELDS(32), THREE_FIELDS};
 static const FieldMap h_fields_circ[] = {CIRC_FIELDS(0)};
 static const FieldMap h_fields_three[] = {CIRC_FIELDS(32), THREE_FIELDS};
-constexpr int N_FIELDS_CIRC = 19;
-constexpr int N_FIELDS_THREE = 19 + 15;
+constexpr int N_FIELDS_CIRC = 20;
+constexpr int N_FIELDS_THREE = 20 + 16;
 static_assert(sizeof(h_fields_circ) / sizeof(FieldMap) == N_FIELDS_CIRC, "field table");
 static_assert(sizeof(h_fields_three) / sizeof(FieldMap) == N_FIELDS_THREE, "field table");
 
@@ -101,6 +103,40 @@ __device__ __forceinline__ double wrap_to_pi(double rad) {
     if (rad < 0 && rad_ == CDB_PI) return -CDB_PI;
     else if (rad_ > CDB_PI) return rad_ - (2 * CDB_PI);
     else return rad_;
+}
+
+// ---- Fluctuation (core/motion/fluctuation.py:14-62; logic.py:78-86) ------------------------------------------------------
+// The reference draws from numpy's unseeded global RNG, so only the DISTRIBUTIONS can be matched:
+//   force  = mass * xi * (cos phi, sin phi),  phi ~ U(0, 2 pi),  xi ~ scale * TruncNormal[0, 3]
+//   torque = inertia_rot * scale_t * TruncNormal[-3, 3]
+// Counter-based Philox4x32-10 keyed by (seed, step), counter = agent id: reproducible, independent of the cell order and of
+// the strip decomposition.  Truncated normals by inversion: x = Phi^-1(Phi(a) + u (Phi(b) - Phi(a))).
+__device__ __forceinline__ void philox4x32_10(unsigned c0, unsigned c1, unsigned c2, unsigned c3, unsigned k0, unsigned k1, unsigned out[4]) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const unsigned hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const unsigned hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        c0 = hi1 ^ c1 ^ k0; c1 = lo1; c2 = hi0 ^ c3 ^ k1; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+__device__ __forceinline__ double u01(unsigned a, unsigned b) {   // uniform in (0, 1), 64 random bits
+    return ((double)a * 4294967296.0 + (double)b + 0.5) * 5.421010862427522e-20;
+}
+#define PHI_CDF_3 0.9986501019683699     // Phi(3)
+__device__ __forceinline__ void fluctuation(unsigned long long seed, unsigned long long step, int id, double mass, double scale_f,
+                                            double inertia, double scale_t, bool rotational, double &fx, double &fy, double &tq) {
+    unsigned r0[4], r1[4];
+    philox4x32_10((unsigned)id, 0u, (unsigned)step, (unsigned)(step >> 32), (unsigned)seed, (unsigned)(seed >> 32), r0);
+    const double phi = 2.0 * CDB_PI * u01(r0[0], r0[1]);
+    const double xi = scale_f * normcdfinv(0.5 + u01(r0[2], r0[3]) * (PHI_CDF_3 - 0.5));
+    const double mm = mass * xi;
+    fx += mm * cos(phi); fy += mm * sin(phi);
+    if (rotational) {
+        philox4x32_10((unsigned)id, 1u, (unsigned)step, (unsigned)(step >> 32), (unsigned)seed, (unsigned)(seed >> 32), r1);
+        tq += inertia * (scale_t * normcdfinv((1.0 - PHI_CDF_3) + u01(r1[0], r1[1]) * (2.0 * PHI_CDF_3 - 1.0)));
+    }
 }
 
 // core/motion/contact.py:14-48:  -h (mu n - kappa (v.t) t) + damping (v.n) n
@@ -627,6 +663,17 @@ __device__ __forceinline__ void navigation_sample(const NavField *nav, int n_nav
         e0x = f.U[jy * f.nx + jx];
         e0y = f.V[jy * f.nx + jx];
     }
+}
+
+__global__ void k_fluctuation(Soa s, int n, int model, unsigned long long seed, unsigned long long step) {   // logic.py:78-86
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || s.id[i] < 0) return;
+    double fx = s(FX, i), fy = s(FY, i), tq = 0.0;
+    const bool rot = model == CDB_MODEL_THREE_CIRCLE;
+    if (rot) tq = s(TORQUE, i);
+    fluctuation(seed, step, s.id[i], s(MASS, i), s(STD_RAND_FORCE, i), rot ? s(INERTIA, i) : 0.0, rot ? s(STD_RAND_TORQUE, i) : 0.0, rot, fx, fy, tq);
+    s(FX, i) = fx; s(FY, i) = fy;
+    if (rot) s(TORQUE, i) = tq;
 }
 
 __global__ void k_navigation(Soa s, int n, const NavField *nav, int n_nav) {

@@ -53,6 +53,7 @@ struct StepArgs {
     const unsigned long long *vmax;
     double *dt_out;          // [0] dt, [1] time_tot
     double *dt_log;          // where to log this step's dt (or nullptr)
+    unsigned long long seed, step;   // Fluctuation: Philox key
 };
 
 struct WarpSmem {
@@ -193,6 +194,9 @@ __global__ void __launch_bounds__(STEP_THREADS, MODEL == 0 ? STEP_MINB_CIRC : ST
     double e0x = s(E0X, oo), e0y = s(E0Y, oo);
     double fx = s(FX, oo), fy = s(FY, oo), tq = 0.0, phi0 = 0.0;
     if (MODEL == 1) { tq = s(TORQUE, oo); phi0 = s(PHI0, oo); }
+    if (A.flags & CDB_STEP_FLUCTUATION)      // logic.py:78-86, first in the reference's post-order
+        fluctuation(A.seed, A.step, s.id[oo], s(MASS, oo), s(STD_RAND_FORCE, oo), MODEL == 1 ? s(INERTIA, oo) : 0.0,
+                    MODEL == 1 ? s(STD_RAND_TORQUE, oo) : 0.0, MODEL == 1, fx, fy, tq);
     {
         const double px = s(PX, oo), py = s(PY, oo);
         if (A.flags & CDB_STEP_NAVIGATION) navigation_sample(A.nav, A.n_nav, s.target[oo], px, py, e0x, e0y);
@@ -379,6 +383,7 @@ __global__ void __launch_bounds__(STEP_THREADS, MODEL == 0 ? STEP_MINB_CIRC : ST
     o(FPX, t) = fx; o(FPY, t) = fy;
     o(RADIUS, t) = s(RADIUS, oo); o(MASS, t) = mass; o(V0, t) = s(V0, oo); o(TAU_ADJ, t) = s(TAU_ADJ, oo);
     o(K_SOC, t) = s(K_SOC, oo); o(TAU_0, t) = s(TAU_0, oo); o(MU, t) = mu; o(KAPPA, t) = kappa; o(DAMPING, t) = damping;
+    o(STD_RAND_FORCE, t) = s(STD_RAND_FORCE, oo);
     o.id[t] = s.id[oo];
     o.target[t] = s.target[oo];
     if (MODEL == 1) {
@@ -391,5 +396,6 @@ __global__ void __launch_bounds__(STEP_THREADS, MODEL == 0 ? STEP_MINB_CIRC : ST
         o(R_T, t) = s(R_T, oo); o(R_S, t) = s(R_S, oo); o(R_TS, t) = r_ts; o(INERTIA, t) = inertia; o(OMEGA0, t) = s(OMEGA0, oo);
         o(PHI, t) = phi; o(OMEGA, t) = w; o(PHI0, t) = phi0;
         o(TORQUE, t) = rst ? 0.0 : tq; o(TORQUE_PREV, t) = tq; o(TAU_ROT, t) = s(TAU_ROT, oo);
+        o(STD_RAND_TORQUE, t) = s(STD_RAND_TORQUE, oo);
     }
 }

@@ -99,6 +99,12 @@ class DeviceAgents:
     def reset(self):
         _lib.check(self.lib.cdb_reset(self.handle))
 
+    def set_seed(self, seed):
+        _lib.check(self.lib.cdb_set_seed(self.handle, int(seed) & (2 ** 64 - 1)))
+
+    def fluctuation(self):
+        _lib.check(self.lib.cdb_fluctuation(self.handle))
+
     def navigation(self):
         _lib.check(self.lib.cdb_navigation(self.handle))
 

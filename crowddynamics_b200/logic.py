@@ -255,6 +255,21 @@ class Integrator(LogicNode):
         self.simulation.data['time_tot'] += dt
 
 
+class Fluctuation(LogicNode):
+    """logic.py:78-86 -- stochastic force / torque.  The reference draws from numpy's unseeded global RNG; this node uses a
+    counter-based Philox generator on the device (``seed`` param), so parity with the reference is distributional:
+    |xi| / (m * std_rand_force) ~ TruncNormal[0, 3], direction ~ U(0, 2 pi), eta / (I * std_rand_torque) ~ TruncNormal[-3, 3]."""
+    _params = dict(seed=None)
+
+    def update(self):
+        dev = self.state.begin()
+        if self.seed is not None and getattr(self.state, '_seed', None) != self.seed:
+            dev.set_seed(self.seed)
+            self.state._seed = self.seed
+        dev.fluctuation()
+        self.state.end(_lib.F_FORCE | _lib.F_TORQUE)
+
+
 class Adjusting(LogicNode):
     """logic.py:89-94"""
 
@@ -316,7 +331,7 @@ class FusedStep(LogicNode):
     agent-agent -> agent-obstacle -> integrator -> reset (post-order of examples/simulations.py:123-136), resident on
     the device.  ``steps_per_update`` > 1 advances several iterations per call."""
     _params = dict(dt_min=0.01, dt_max=0.01, cell_size=3.6, step=0.1, radius=0.5, strength=0.3, steps_per_update=1,
-                   navigation=True, sync_every_update=False)
+                   navigation=True, fluctuation=False, seed=None, sync_every_update=False)
 
     def __init__(self, simulation, *args, **kwargs):
         kwargs.setdefault('mode', 'resident')
@@ -331,6 +346,11 @@ class FusedStep(LogicNode):
             self.state.ensure_navigation(self.step, self.radius, self.strength)
         else:
             flags &= ~_lib.STEP_NAVIGATION
+        if self.fluctuation:
+            flags |= _lib.STEP_FLUCTUATION
+            if self.seed is not None and getattr(self.state, '_seed', None) != self.seed:
+                dev.set_seed(self.seed)
+                self.state._seed = self.seed
         dts = dev.step(self.steps_per_update, flags, self.cell_size, self.dt_min, self.dt_max)
         self.state.dirty_host = True
         if len(dts):
@@ -373,12 +393,13 @@ class MultiAgentSimulation:
         self.data['iterations'] += 1
 
 
-def hallway_logic(simulation, mode='strict', dt_min=0.01, dt_max=0.01, cell_size=None):
-    """The replaced part of the Hallway / RoomWithOneExit logic tree (examples/simulations.py:123-136), without the
-    host-side Fluctuation / InsideDomain nodes."""
+def hallway_logic(simulation, mode='strict', dt_min=0.01, dt_max=0.01, cell_size=None, fluctuation=False, seed=None):
+    """The replaced part of the Hallway / RoomWithOneExit logic tree (examples/simulations.py:123-136); InsideDomain stays a
+    host-side node of the reference, Fluctuation is optional (stochastic)."""
     aa = dict(cell_size=cell_size) if cell_size else {}
+    fl = (Fluctuation(simulation, seed=seed),) if fluctuation else ()
     return Reset(simulation, mode=mode) << (
-        Integrator(simulation, dt_min=dt_min, dt_max=dt_max) << (
+        Integrator(simulation, dt_min=dt_min, dt_max=dt_max) << fl + (
             Adjusting(simulation) << (Navigation(simulation), Orientation(simulation)),
             AgentAgentInteractions(simulation, **aa),
             AgentObstacleInteractions(simulation)))

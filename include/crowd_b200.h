@@ -65,7 +65,8 @@ enum {
     CDB_STEP_AGENT_OBSTACLE = 1u << 4,
     CDB_STEP_INTEGRATOR = 1u << 5,
     CDB_STEP_RESET = 1u << 6,
-    CDB_STEP_ALL = (1u << 7) - 1
+    CDB_STEP_ALL = (1u << 7) - 1,        /* the seven deterministic nodes */
+    CDB_STEP_FLUCTUATION = 1u << 7       /* + Fluctuation (stochastic: distribution parity only), runs first like in the reference tree */
 };
 
 /* ---- library ---------------------------------------------------------------------------------------------------- */
@@ -104,6 +105,10 @@ int cdb_clear_navigation(cdb_sim *sim);
 
 /* ---- per-node entry points (one per replaced LogicNode.update) ------------------------------------------------------ */
 int cdb_reset(cdb_sim *sim);                 /* Reset.update, logic.py:59-64 */
+/* Fluctuation.update, logic.py:78-86 -> core/motion/fluctuation.py:14-62.  Counter-based RNG (Philox, key = seed and the
+ * sim's iteration counter, counter = agent id); the reference uses numpy's unseeded global RNG, so parity is statistical. */
+int cdb_set_seed(cdb_sim *sim, uint64_t seed);
+int cdb_fluctuation(cdb_sim *sim);
 int cdb_navigation(cdb_sim *sim);            /* Navigation.update sampling, logic.py:149-165 + navigation.py:60-78 + quickest_path.py:41-44 */
 int cdb_orientation(cdb_sim *sim);           /* Orientation.update, logic.py:258-261 + steering/orientation.py:17-21 */
 int cdb_adjust(cdb_sim *sim);                /* Adjusting.update, logic.py:89-94 + motion/adjusting.py:101-121 */
