@@ -172,7 +172,7 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    n_sample = args.cpu_agents or (20000 if args.model == 'three_circle' else 100000)
+    n_sample = args.cpu_agents or (50000 if args.model == 'three_circle' else 200000)
     # warm-up steps are run inside cpu_port_rate (1 per replica); `steps` timed steps per replica
     steps = max(1, min(args.steps, 5))
     rate, secs = cpu_port_rate(args.model, n_sample, steps, args.density, threads=cores)
