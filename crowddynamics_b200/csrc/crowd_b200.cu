@@ -58,6 +58,7 @@ int dev_alloc(T **p, size_t count) {
 }
 
 constexpr int DT_LOG = 1024;
+constexpr int STRIP_REFRESH = 16;
 constexpr int PROFILE_MAX_STEPS = 4096;
 
 inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
@@ -134,6 +135,10 @@ struct cdb_sim {
     int64_t halo_cap = 0, mig_cap = 0;
     int64_t n_dead = 0;              // slots vacated by migrants (dropped at the next sort)
     int *d_counters = nullptr;       // [0] migrants left, [1] migrants right, [2] appended
+    DevCounts *d_counts = nullptr;   // device-side slot / live counts: in strip mode the host only keeps upper bounds in n
+    DevCounts *h_counts = nullptr;   // pinned
+    bool dev_counts = false;
+    int steps_since_refresh = 0;
     int *h_counters = nullptr;       // pinned
 
     // instrumentation: kernel launch counter and CUDA-event timing of the step phases
@@ -217,8 +222,10 @@ int prof_mark(cdb_sim *sim) {
 // ---- block list --------------------------------------------------------------------------------------------------
 int build_block_list(cdb_sim *sim, double cell_size, bool padded_lattice = false, unsigned long long *vmax = nullptr, bool physical = true) {
     if (!(cell_size > 0.0) || !std::isfinite(cell_size)) return fail(CDB_ERR_INVALID_VALUE, "cell_size must be > 0");
-    const int64_t n = sim->n;                   // slots in use, including the ones vacated by migrants
-    const int64_t live = sim->n - sim->n_dead;
+    const int64_t n = sim->n;                   // slots in use, including the ones vacated by migrants (upper bound with dev_counts)
+    const int64_t live = sim->dev_counts ? sim->n : sim->n - sim->n_dead;
+    const int *slots_dev = sim->dev_counts ? &sim->d_counts->slots : nullptr;
+    int *live_dev = sim->dev_counts ? &sim->d_counts->live : nullptr;
     sim->cell_size = cell_size;
     sim->tables_valid = false;
     cudaStream_t st = sim->stream;
@@ -257,15 +264,15 @@ int build_block_list(cdb_sim *sim, double cell_size, bool padded_lattice = false
     CKS(ensure_cells(sim, ncell));
     CK(cudaMemsetAsync(sim->d_cell_count, 0, ncell * sizeof(int), st));
     CK(cudaMemsetAsync(sim->d_cell_fill, 0, ncell * sizeof(int), st));
-    if (n > 0) LAUNCH(sim, k_cell_count, cdiv(n, T), T, 0, sim->cur, (int)n, cell_size, sim->d_grid, sim->d_cell_of_slot, sim->d_cell_count, sim->d_error, vmax);
+    if (n > 0) LAUNCH(sim, k_cell_count, cdiv(n, T), T, 0, sim->cur, (int)n, cell_size, sim->d_grid, sim->d_cell_of_slot, sim->d_cell_count, sim->d_error, vmax, slots_dev);
     // exclusive scan count -> start
     const int nblk = cdiv(ncell, SCAN_TILE);
     LAUNCH(sim, k_scan_tiles, nblk, SCAN_THREADS, 0, sim->d_cell_count, sim->d_cell_start, (int)ncell, sim->d_scan_partials);
     LAUNCH(sim, k_scan_partials, 1, 1024, 0, sim->d_scan_partials, nblk);
-    LAUNCH(sim, k_scan_add, nblk, SCAN_THREADS, 0, sim->d_cell_start, (int)ncell, sim->d_scan_partials, (int)live);
-    if (n > 0) LAUNCH(sim, k_scatter, cdiv(n, T), T, 0, sim->d_cell_of_slot, (int)n, sim->d_cell_start, sim->d_cell_fill, sim->d_order_tmp);
+    LAUNCH(sim, k_scan_add, nblk, SCAN_THREADS, 0, sim->d_cell_start, (int)ncell, sim->d_scan_partials, sim->d_cell_count, live_dev);
+    if (n > 0) LAUNCH(sim, k_scatter, cdiv(n, T), T, 0, sim->d_cell_of_slot, (int)n, sim->d_cell_start, sim->d_cell_fill, sim->d_order_tmp, slots_dev);
     if (live > 0) LAUNCH(sim, k_rank_fix, cdiv(live, T), T, 0, sim->d_order_tmp, (int)live, sim->cur.id, sim->d_cell_of_slot, sim->d_cell_start,
-                                         sim->d_cell_count, sim->d_order);
+                                         sim->d_cell_count, sim->d_order, live_dev);
     if (physical) {
         if (live > 0) LAUNCH(sim, k_gather, cdiv(live, T), T, 0, sim->cur, sim->alt, (int)live, sim->n_planes, sim->model,
                              sim->d_order, sim->d_cell_of_slot, sim->d_order_tmp, sim->d_nbr);
@@ -276,7 +283,7 @@ int build_block_list(cdb_sim *sim, double cell_size, bool padded_lattice = false
         sim->n_dead = 0;
         sim->perm_valid = false;
     } else {
-        if (live > 0) LAUNCH(sim, k_records, cdiv(live, T), T, 0, sim->cur, (int)live, sim->model, sim->d_order, sim->d_cell_of_slot,
+        if (live > 0) LAUNCH(sim, k_records, cdiv(live, T), T, 0, sim->cur, (int)live, live_dev, sim->model, sim->d_order, sim->d_cell_of_slot,
                              sim->d_order_tmp, sim->d_nbr);
         std::swap(sim->d_cell_of_slot, sim->d_order_tmp);   // d_cell_of_slot: flat cell per sorted slot; d_order_tmp: per plane slot
         sim->perm_valid = true;
@@ -327,6 +334,7 @@ StepArgs step_args(cdb_sim *sim, unsigned flags, double dt_min, double dt_max, d
     const bool listed = (flags & CDB_STEP_AGENT_AGENT) != 0;
     a.n = (int)(listed ? sim->n_sorted : sim->n);
     a.order = listed && sim->perm_valid ? sim->d_order : nullptr;
+    a.n_dev = listed && sim->dev_counts ? &sim->d_counts->live : (sim->dev_counts ? &sim->d_counts->slots : nullptr);
     a.grid = sim->d_grid;
     a.cell_sorted = sim->d_cell_of_slot; a.cell_start = sim->d_cell_start; a.cell_count = sim->d_cell_count;
     a.nav = sim->d_nav; a.n_nav = sim->n_nav;
@@ -351,7 +359,10 @@ int launch_step_kernel(cdb_sim *sim, unsigned flags, double dt_min, double dt_ma
     CK(cudaGetLastError());
     if (flags & CDB_STEP_INTEGRATOR) {
         std::swap(sim->cur, sim->alt);
-        if (a.order) { sim->n = a.n; sim->n_dead = 0; }   // the step wrote the live agents compacted, in cell order
+        if (a.order) {   // the step wrote the live agents compacted, in cell order
+            sim->n = a.n; sim->n_dead = 0;
+            if (sim->dev_counts) LAUNCH(sim, k_counts_after_step, 1, 32, 0, sim->d_counts);
+        }
         sim->perm_valid = false;
         sim->tables_valid = false;
     }
@@ -453,9 +464,13 @@ int cdb_create(int device, int model, int64_t capacity, cdb_sim **out) {
         CKS(dev_alloc(&sim->d_error, 1));
         CKS(dev_alloc(&sim->d_pair_count, 1));
         CKS(dev_alloc(&sim->d_counters, 4));
+        CKS(dev_alloc(&sim->d_counts, 1));
+        CK(cudaMallocHost((void **)&sim->h_counts, sizeof(DevCounts)));
         CK(cudaMallocHost((void **)&sim->h_counters, 4 * sizeof(int)));
         CKS(dev_alloc(&sim->d_nav, MAX_NAV_TARGETS));
         CK(cudaMemset(sim->d_error, 0, sizeof(int)));
+        CK(cudaMemset(sim->d_counters, 0, 4 * sizeof(int)));
+        CK(cudaMemset(sim->d_counts, 0, sizeof(DevCounts)));
         CK(cudaMemset(sim->d_dt, 0, 2 * sizeof(double)));
         CK(cudaMallocHost((void **)&sim->h_bbox, 4 * sizeof(long long)));
         CK(cudaMallocHost((void **)&sim->h_dt, 2 * sizeof(double)));
@@ -481,7 +496,7 @@ int cdb_destroy(cdb_sim *sim) {
     cudaFree(sim->d_nav); cudaFree(sim->d_vmax); cudaFree(sim->d_dt); cudaFree(sim->d_dt_log); cudaFreeHost(sim->h_dt);
     for (auto e : sim->ev_pool) cudaEventDestroy(e);
     cudaFree(sim->d_error); cudaFreeHost(sim->h_error); cudaFree(sim->d_pair_count);
-    cudaFree(sim->d_counters); cudaFreeHost(sim->h_counters);
+    cudaFree(sim->d_counters); cudaFreeHost(sim->h_counters); cudaFree(sim->d_counts); cudaFreeHost(sim->h_counts);
     if (sim->own_stream && sim->stream) cudaStreamDestroy(sim->stream);
     delete sim;
     return CDB_OK;
@@ -528,6 +543,7 @@ int cdb_upload_agents_aos(cdb_sim *sim, const void *agents, int64_t n, int64_t i
     else
         LAUNCH(sim, k_unpack_aos<1>, cdiv(n, AOS_REC_PER_BLOCK), AOS_REC_PER_BLOCK, smem, sim->d_aos, (int)n, sim->cur);
     CK(cudaGetLastError());
+    if (sim->dev_counts) LAUNCH(sim, k_counts_set, 1, 32, 0, sim->d_counts, (int)n);
     // the host buffer may be pageable and reused by the caller right away
     CK(cudaStreamSynchronize(sim->stream));
     return CDB_OK;
@@ -843,6 +859,10 @@ int cdb_set_strip(cdb_sim *sim, int64_t ix_min, int64_t iy_min, int64_t nx_owned
     sim->lattice_fixed = true;
     sim->tables_valid = false;
     CK(cudaMemcpy(sim->d_grid, &sim->grid, sizeof(Grid), cudaMemcpyHostToDevice));
+    sim->dev_counts = true;
+    sim->steps_since_refresh = 0;
+    LAUNCH(sim, k_counts_set, 1, 32, 0, sim->d_counts, (int)sim->n);
+    CK(cudaStreamSynchronize(sim->stream));
     return alloc_ghost_tail(sim);
 }
 
@@ -921,7 +941,7 @@ int cdb_strip_finish(cdb_sim *sim, uint32_t flags, double dt_min, double dt_max,
     sim->iterations++;
     LAUNCH(sim, k_counters_zero, 1, 32, 0, sim->d_counters, 4);
     if (sim->n > 0)
-        LAUNCH(sim, k_migrants_pack, cdiv(sim->n, 256), 256, 0, sim->cur, (int)sim->n, sim->n_planes, sim->cell_size, sim->grid.ix_min,
+        LAUNCH(sim, k_migrants_pack, cdiv(sim->n, 256), 256, 0, sim->cur, (int)sim->n, sim->dev_counts ? &sim->d_counts->slots : nullptr, sim->n_planes, sim->cell_size, sim->grid.ix_min,
                (int)sim->grid.cx_lo, (int)sim->grid.cx_hi, sim->has_left, sim->has_right, mig_left_out, mig_right_out, (long long)sim->mig_cap,
                sim->d_counters, sim->d_error);
     LAUNCH(sim, k_migrants_header, 1, 32, 0, sim->has_left ? mig_left_out : nullptr, sim->has_right ? mig_right_out : nullptr, sim->d_counters,
@@ -931,27 +951,53 @@ int cdb_strip_finish(cdb_sim *sim, uint32_t flags, double dt_min, double dt_max,
     return CDB_OK;
 }
 
+// exact counts back on the host (one sync): slots in use, slots vacated by the last step's migrants; also surfaces device errors
+static int strip_refresh(cdb_sim *sim) {
+    CK(cudaMemcpyAsync(sim->h_counters, sim->d_counters, 4 * sizeof(int), cudaMemcpyDeviceToHost, sim->stream));
+    CK(cudaMemcpyAsync(sim->h_counts, sim->d_counts, sizeof(DevCounts), cudaMemcpyDeviceToHost, sim->stream));
+    CKS(check_device_error(sim));    // synchronizes
+    sim->n = sim->h_counts->slots;
+    sim->n_dead = std::min<int64_t>(sim->h_counters[0], sim->mig_cap) + std::min<int64_t>(sim->h_counters[1], sim->mig_cap);
+    sim->steps_since_refresh = 0;
+    return CDB_OK;
+}
+
 int cdb_strip_absorb(cdb_sim *sim, const double *mig_left_in, const double *mig_right_in, int64_t *n_out) {
     SIM_ENTRY();
     if (!sim->strip) return fail(CDB_ERR_STATE, "cdb_set_strip has not been called");
     const int g = cdiv(sim->mig_cap > 0 ? sim->mig_cap : 1, 128);
+    const int *slots_dev = &sim->d_counts->slots;
     if (sim->has_left && mig_left_in)
-        LAUNCH(sim, k_migrants_unpack, g, 128, 0, mig_left_in, sim->cur, (int)sim->n, sim->n_planes, (long long)sim->capacity, sim->d_counters, sim->d_error);
+        LAUNCH(sim, k_migrants_unpack, g, 128, 0, mig_left_in, sim->cur, (int)sim->n, slots_dev, sim->n_planes, (long long)sim->capacity, sim->d_counters, sim->d_error);
     if (sim->has_right && mig_right_in)
-        LAUNCH(sim, k_migrants_unpack, g, 128, 0, mig_right_in, sim->cur, (int)sim->n, sim->n_planes, (long long)sim->capacity, sim->d_counters, sim->d_error);
-    CK(cudaMemcpyAsync(sim->h_counters, sim->d_counters, 4 * sizeof(int), cudaMemcpyDeviceToHost, sim->stream));
-    CKS(check_device_error(sim));    // synchronizes
-    const int64_t out = std::min<int64_t>(sim->h_counters[0], sim->mig_cap) + std::min<int64_t>(sim->h_counters[1], sim->mig_cap);
-    sim->n_dead += out;
-    sim->n += sim->h_counters[2];
+        LAUNCH(sim, k_migrants_unpack, g, 128, 0, mig_right_in, sim->cur, (int)sim->n, slots_dev, sim->n_planes, (long long)sim->capacity, sim->d_counters, sim->d_error);
+    LAUNCH(sim, k_counts_after_absorb, 1, 32, 0, sim->d_counts, sim->d_counters);
+    CK(cudaGetLastError());
     sim->tables_valid = false;
-    if (n_out) *n_out = sim->n - sim->n_dead;
+    // The exact counts stay on the device; the host keeps an upper bound for its launch sizes and only synchronises every
+    // STRIP_REFRESH steps (or when the bound would not fit the allocation, or when the caller asks for the exact count).
+    const int64_t bound = sim->n + 2 * sim->mig_cap;
+    if (++sim->steps_since_refresh >= STRIP_REFRESH || bound > sim->capacity || n_out) {
+        CKS(strip_refresh(sim));
+        if (n_out) *n_out = sim->n - sim->n_dead;
+    } else {
+        sim->n = bound;
+    }
+    return CDB_OK;
+}
+
+int cdb_strip_count(cdb_sim *sim, int64_t *n_out) {
+    SIM_ENTRY();
+    if (!sim->strip || !n_out) return fail(CDB_ERR_STATE, "cdb_set_strip has not been called");
+    CKS(strip_refresh(sim));
+    *n_out = sim->n - sim->n_dead;
     return CDB_OK;
 }
 
 int cdb_export_agents(cdb_sim *sim, void *agents, int64_t *ids, int64_t cap, int64_t *count) {
     SIM_ENTRY();
     if (!count) return fail(CDB_ERR_INVALID_VALUE, "count is NULL");
+    if (sim->dev_counts) CKS(strip_refresh(sim));
     const int64_t live = sim->n - sim->n_dead;
     *count = live;
     if (live == 0) return CDB_OK;

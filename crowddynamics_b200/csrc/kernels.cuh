@@ -81,6 +81,11 @@ static inline const FieldMap *host_field_map(int model, int *count) {
 // =====================================================================================================================
 // small helpers
 // =====================================================================================================================
+// element count of a launch: the host-side bound, tightened by a device-side count when the host does not know the exact
+// number (strip decomposition without a per-step host sync: DevCounts)
+struct DevCounts { int slots; int live; };
+__device__ __forceinline__ int eff_n(int n_host, const int *n_dev) { return n_dev ? min(n_host, *n_dev) : n_host; }
+
 __device__ __forceinline__ unsigned long long ordered_bits(double x) {
     unsigned long long b = (unsigned long long)__double_as_longlong(x);
     return (b & 0x8000000000000000ULL) ? ~b : (b | 0x8000000000000000ULL);
@@ -427,8 +432,9 @@ __device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long v)
 }
 
 // cell id of every agent + per-cell counts; optionally also the two maxima adaptive_timestep needs (integrator.py:81-90)
-__global__ void k_cell_count(Soa s, int n, double cell_size, const Grid *grid, int *cell_of_slot, int *cell_count, int *error,
-                             unsigned long long *vmax) {
+__global__ void k_cell_count(Soa s, int n_host, double cell_size, const Grid *grid, int *cell_of_slot, int *cell_count, int *error,
+                             unsigned long long *vmax, const int *n_dev) {
+    const int n = eff_n(n_host, n_dev);
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     double v_max = 0.0;
     unsigned long long v0 = 0ULL;
@@ -518,17 +524,23 @@ __global__ void k_scan_partials(int *partials, int m) {
     }
 }
 
-__global__ void k_scan_add(int *out, int n, const int *__restrict__ partials, int total) {
+// adds the tile offsets; the grand total (= live agents) goes to out[n] and, when asked for, to *live_out (device-side count)
+__global__ void k_scan_add(int *out, int n, const int *__restrict__ partials, const int *__restrict__ counts, int *live_out) {
     const int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
     const int add = partials[blockIdx.x];
 #pragma unroll
-    for (int k = 0; k < SCAN_ITEMS; ++k) if (base + k < n) out[base + k] += add;
-    if (blockIdx.x == 0 && threadIdx.x == 0) out[n] = total;
+    for (int k = 0; k < SCAN_ITEMS; ++k)
+        if (base + k < n) {
+            const int v = out[base + k] + add;
+            out[base + k] = v;
+            if (base + k == n - 1) { out[n] = v + counts[n - 1]; if (live_out) *live_out = v + counts[n - 1]; }
+        }
 }
 
-__global__ void k_scatter(const int *__restrict__ cell_of_slot, int n, const int *__restrict__ cell_start, int *cell_fill, int *order_tmp) {
+__global__ void k_scatter(const int *__restrict__ cell_of_slot, int n_host, const int *__restrict__ cell_start, int *cell_fill, int *order_tmp,
+                          const int *n_dev) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    if (i >= eff_n(n_host, n_dev)) return;
     const int c = cell_of_slot[i];
     if (c < 0) return;
     order_tmp[cell_start[c] + atomicAdd(&cell_fill[c], 1)] = i;
@@ -536,10 +548,10 @@ __global__ void k_scatter(const int *__restrict__ cell_of_slot, int n, const int
 
 // make the order inside every cell deterministic: ascending original agent index (== stable counting sort of the
 // reference block list, whatever order the atomics of k_scatter resolved in)
-__global__ void k_rank_fix(const int *__restrict__ order_tmp, int n, const int *__restrict__ id, const int *__restrict__ cell_of_slot,
-                           const int *__restrict__ cell_start, const int *__restrict__ cell_count, int *__restrict__ order) {
+__global__ void k_rank_fix(const int *__restrict__ order_tmp, int n_host, const int *__restrict__ id, const int *__restrict__ cell_of_slot,
+                           const int *__restrict__ cell_start, const int *__restrict__ cell_count, int *__restrict__ order, const int *n_dev) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n) return;
+    if (t >= eff_n(n_host, n_dev)) return;
     const int src = order_tmp[t];
     const int c = cell_of_slot[src];
     const int b = cell_start[c], e = b + cell_count[c];
@@ -585,10 +597,10 @@ __global__ void k_gather(Soa src, Soa dst, int n, int n_planes, int model, const
 //   three-circle  {px, py, vx, vy, extent, r_t, r_s, - | lsx, lsy, rsx, rsy, ox, oy, -, -}     128 B (one line)
 // extent = conservative radius of the whole body around the centre (from the STORED shoulder positions), (ox, oy) =
 // r_ts (sin phi, -cos phi), the shoulder displacement of power_law.py:338-350.
-__global__ void k_records(Soa src, int n, int model, const int *__restrict__ order,
+__global__ void k_records(Soa src, int n_host, const int *n_dev, int model, const int *__restrict__ order,
                          const int *__restrict__ cell_of_slot, int *__restrict__ cell_sorted, double *__restrict__ nbr) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n) return;
+    if (t >= eff_n(n_host, n_dev)) return;
     const int o = order[t];
     cell_sorted[t] = cell_of_slot[o];
     const double x = src(PX, o), y = src(PY, o), vx = src(VX, o), vy = src(VY, o);

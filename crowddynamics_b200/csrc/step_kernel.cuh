@@ -40,7 +40,8 @@ constexpr int REC_THREE = 16;   // px py vx vy ext rt rs - | lsx lsy rsx rsy ox 
 struct StepArgs {
     Soa in, out;             // out == in unless integrating (then the new state is written to the other buffer)
     const double *nbr;       // packed neighbour records of `in`
-    int n;
+    int n;                   // targets (host-side bound)
+    const int *n_dev;        // device-side exact count (nullptr: n is exact)
     const Grid *grid;
     const int *cell_sorted, *cell_start, *cell_count;
     const int *order;        // sorted slot -> slot of `in` holding that agent (nullptr: `in` is physically in cell order)
@@ -183,7 +184,7 @@ __global__ void __launch_bounds__(STEP_THREADS, MODEL == 0 ? STEP_MINB_CIRC : ST
     const int lane = threadIdx.x & 31;
     WarpSmem &W = s_warp[threadIdx.x >> 5];
     const int t0 = t - lane;             // first target of this warp
-    const bool active = t < A.n;
+    const bool active = t < eff_n(A.n, A.n_dev);
     const Soa &s = A.in;
     const unsigned FULL = 0xffffffffu;
     const int tt = active ? t : 0;       // inactive lanes read slot 0 and never write

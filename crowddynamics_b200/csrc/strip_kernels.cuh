@@ -75,13 +75,19 @@ __global__ void k_ghost_clear(int *cell_start, int *cell_count, int col, int ny,
 
 __global__ void k_counters_zero(int *c, int n) { if (threadIdx.x < n) c[threadIdx.x] = 0; }
 
+// device-side bookkeeping of the strip step (no host round trip): after the integrating step the live agents are compact
+// in [0, live); after absorbing migrants the slot count grows by the number appended
+__global__ void k_counts_after_step(DevCounts *c) { if (threadIdx.x == 0) c->slots = c->live; }
+__global__ void k_counts_after_absorb(DevCounts *c, const int *counters) { if (threadIdx.x == 0) c->slots += counters[2]; }
+__global__ void k_counts_set(DevCounts *c, int slots) { if (threadIdx.x == 0) { c->slots = slots; c->live = slots; } }
+
 // agents whose cell column left the owned range [col_lo, col_hi] move to the neighbour: append the whole agent to the
 // message of that side and vacate the slot (id = -1).  counters: [0] left, [1] right.
-__global__ void k_migrants_pack(Soa s, int n, int n_planes, double cell_size, long long ix_min_local, int col_lo, int col_hi,
-                                int has_left, int has_right, double *__restrict__ msg_left, double *__restrict__ msg_right,
+__global__ void k_migrants_pack(Soa s, int n_host, const int *n_dev, int n_planes, double cell_size, long long ix_min_local, int col_lo,
+                                int col_hi, int has_left, int has_right, double *__restrict__ msg_left, double *__restrict__ msg_right,
                                 long long cap, int *counters, int *error) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n || s.id[i] < 0) return;
+    if (i >= eff_n(n_host, n_dev) || s.id[i] < 0) return;
     const double col = floor(s(PX, i) / cell_size) - (double)ix_min_local;
     int side = -1;
     if (has_left && col < (double)col_lo) side = 0;
@@ -104,11 +110,12 @@ __global__ void k_migrants_header(double *msg_left, double *msg_right, const int
 }
 
 // append received migrants after the current slots; counters[2] = number appended so far
-__global__ void k_migrants_unpack(const double *__restrict__ msg, Soa s, int n_slots, int n_planes, long long capacity, int *counters,
-                                  int *error) {
+__global__ void k_migrants_unpack(const double *__restrict__ msg, Soa s, int n_slots_host, const int *n_slots_dev, int n_planes,
+                                  long long capacity, int *counters, int *error) {
     const int m = (int)msg[0];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= m) return;
+    const int n_slots = n_slots_dev ? *n_slots_dev : n_slots_host;
     const int slot = n_slots + atomicAdd(&counters[2], 1);
     if (slot >= capacity) { atomicExch(error, ERR_CELL_RANGE + 4); return; }
     const double *src = msg + MSG_HEADER + (size_t)i * (n_planes + 2);

@@ -82,8 +82,13 @@ class CudaStripDevice:
                                              self._p(halo_right_in), self._p(mig_left_out), self._p(mig_right_out)))
 
     def absorb(self, mig_left_in, mig_right_in):
+        """Appends the received migrants; returns None: the exact count stays on the device (see count())."""
+        _lib.check(self.lib.cdb_strip_absorb(self.handle, self._p(mig_left_in), self._p(mig_right_in), None))
+        return None
+
+    def count(self):
         n = C.c_int64()
-        _lib.check(self.lib.cdb_strip_absorb(self.handle, self._p(mig_left_in), self._p(mig_right_in), C.byref(n)))
+        _lib.check(self.lib.cdb_strip_count(self.handle, C.byref(n)))
         return n.value
 
     def export_agents(self, dtype):
@@ -138,6 +143,9 @@ class StripSimulation:
         self._n_owned = n_owned
 
     def n_owned(self):
+        """Agents currently owned by this rank (asks the device when the last step did not report it)."""
+        if self._n_owned is None:
+            self._n_owned = self.dev.count()
         return self._n_owned
 
     # -- neighbour exchange ---------------------------------------------------------------------------------------------

@@ -166,13 +166,15 @@ int64_t cdb_migrant_buffer_doubles(const cdb_sim *sim);
  *   finish  installs the received ghost columns, runs the fused step kernel on the owned agents, then packs the agents
  *           that left the strip into mig_left_out / mig_right_out
  *   -- caller exchanges migrants --
- *   absorb  appends the received migrants; *n_out = agents now owned (one host sync). */
+ *   absorb  appends the received migrants.  The exact agent counts stay on the device: the host keeps upper bounds for its
+ *           launch sizes and synchronises only every 16th step -- or when n_out is non-NULL (*n_out = agents now owned). */
 int cdb_strip_begin(cdb_sim *sim, uint32_t node_flags, double cell_size, double *halo_left_out, double *halo_right_out);
 int cdb_strip_export_vmax(cdb_sim *sim, double *dev_vmax2);
 int cdb_strip_import_vmax(cdb_sim *sim, const double *dev_vmax2);
 int cdb_strip_finish(cdb_sim *sim, uint32_t node_flags, double dt_min, double dt_max, const double *halo_left_in,
                      const double *halo_right_in, double *mig_left_out, double *mig_right_out);
 int cdb_strip_absorb(cdb_sim *sim, const double *mig_left_in, const double *mig_right_in, int64_t *n_out);
+int cdb_strip_count(cdb_sim *sim, int64_t *n_out);   /* agents currently owned (one host sync) */
 /* Live agents in device order: packed records rebuilt from the device state (record fields the kernels never touch are
  * zero) and their global ids. */
 int cdb_export_agents(cdb_sim *sim, void *agents, int64_t *ids, int64_t cap, int64_t *count);
