@@ -83,7 +83,6 @@ def _signatures(L):
         'cdb_strip_begin': (i32, [vp, u32, f64, vp, vp]),
         'cdb_strip_export_vmax': (i32, [vp, vp]),
         'cdb_strip_import_vmax': (i32, [vp, vp]),
-        'cdb_strip_interior': (i32, [vp, u32, f64, f64]),
         'cdb_strip_finish': (i32, [vp, u32, f64, f64, vp, vp, vp, vp]),
         'cdb_strip_absorb': (i32, [vp, vp, vp, pi64]),
         'cdb_strip_count': (i32, [vp, pi64]),

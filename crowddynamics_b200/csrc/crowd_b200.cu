@@ -138,7 +138,6 @@ struct cdb_sim {
     DevCounts *d_counts = nullptr;   // device-side slot / live counts: in strip mode the host only keeps upper bounds in n
     DevCounts *h_counts = nullptr;   // pinned
     bool dev_counts = false;
-    bool interior_done = false;      // pass 1 of this step already ran (cdb_strip_interior)
     int steps_since_refresh = 0;
     int *h_counters = nullptr;       // pinned
 
@@ -327,11 +326,8 @@ int node_adjust(cdb_sim *sim) {
     CK(cudaGetLastError());
     return CDB_OK;
 }
-StepArgs step_args(cdb_sim *sim, unsigned flags, double dt_min, double dt_max, double *dt_log, int pass) {
+StepArgs step_args(cdb_sim *sim, unsigned flags, double dt_min, double dt_max, double *dt_log) {
     StepArgs a{};
-    a.pass = pass;
-    a.border_lo = sim->strip && sim->has_left ? (int)sim->grid.cx_lo : -1;
-    a.border_hi = sim->strip && sim->has_right ? (int)sim->grid.cx_hi : -1;
     a.in = sim->cur;
     a.out = (flags & CDB_STEP_INTEGRATOR) ? sim->alt : sim->cur;
     a.nbr = sim->d_nbr;
@@ -351,17 +347,17 @@ StepArgs step_args(cdb_sim *sim, unsigned flags, double dt_min, double dt_max, d
 }
 
 // the fused kernel; requires a current block list when CDB_STEP_AGENT_AGENT is selected
-int launch_step_kernel(cdb_sim *sim, unsigned flags, double dt_min, double dt_max, double *dt_log, int pass = 0) {
-    const StepArgs a = step_args(sim, flags, dt_min, dt_max, dt_log, pass);
+int launch_step_kernel(cdb_sim *sim, unsigned flags, double dt_min, double dt_max, double *dt_log) {
+    const StepArgs a = step_args(sim, flags, dt_min, dt_max, dt_log);
     const int smem = 0;
     if (a.n > 0) {
         if (sim->model == CDB_MODEL_CIRCULAR) LAUNCH(sim, k_step<0>, cdiv(a.n, STEP_THREADS), STEP_THREADS, smem, a);
         else LAUNCH(sim, k_step<1>, cdiv(a.n, STEP_THREADS), STEP_THREADS, smem, a);
-    } else if ((flags & CDB_STEP_INTEGRATOR) && pass != 2) {
+    } else if (flags & CDB_STEP_INTEGRATOR) {
         LAUNCH(sim, k_integrate, 1, 32, 0, sim->cur, 0, sim->model, dt_min, dt_max, sim->d_vmax, sim->d_dt);
     }
     CK(cudaGetLastError());
-    if ((flags & CDB_STEP_INTEGRATOR) && pass != 1) {
+    if (flags & CDB_STEP_INTEGRATOR) {
         std::swap(sim->cur, sim->alt);
         if (a.order) {   // the step wrote the live agents compacted, in cell order
             sim->n = a.n; sim->n_dead = 0;
@@ -921,16 +917,6 @@ int cdb_strip_import_vmax(cdb_sim *sim, const double *dev_vmax2) {
     return CDB_OK;
 }
 
-int cdb_strip_interior(cdb_sim *sim, uint32_t flags, double dt_min, double dt_max) {
-    SIM_ENTRY();
-    if (!sim->strip || !sim->tables_valid) return fail(CDB_ERR_STATE, "cdb_strip_begin must precede cdb_strip_interior");
-    if (!(flags & CDB_STEP_AGENT_AGENT)) return CDB_OK;      // nothing to overlap
-    CKS(prof_mark(sim));
-    CKS(launch_step_kernel(sim, flags, dt_min, dt_max, nullptr, 1));
-    sim->interior_done = true;
-    return CDB_OK;
-}
-
 int cdb_strip_finish(cdb_sim *sim, uint32_t flags, double dt_min, double dt_max, const double *halo_left_in,
                      const double *halo_right_in, double *mig_left_out, double *mig_right_out) {
     SIM_ENTRY();
@@ -949,9 +935,8 @@ int cdb_strip_finish(cdb_sim *sim, uint32_t flags, double dt_min, double dt_max,
                                   col, ny, base_r, (long long)sim->halo_cap, sim->d_error);
         else LAUNCH(sim, k_ghost_clear, 4, 256, 0, sim->d_cell_start, sim->d_cell_count, col, ny, base_r);
     }
-    if (!sim->interior_done) CKS(prof_mark(sim));
-    CKS(launch_step_kernel(sim, flags, dt_min, dt_max, nullptr, sim->interior_done ? 2 : 0));
-    sim->interior_done = false;
+    CKS(prof_mark(sim));
+    CKS(launch_step_kernel(sim, flags, dt_min, dt_max, nullptr));
     CKS(prof_mark(sim));
     sim->iterations++;
     LAUNCH(sim, k_counters_zero, 1, 32, 0, sim->d_counters, 4);

@@ -55,9 +55,6 @@ struct StepArgs {
     double *dt_out;          // [0] dt, [1] time_tot
     double *dt_log;          // where to log this step's dt (or nullptr)
     unsigned long long seed, step;   // Fluctuation: Philox key
-    // strip decomposition: pass 1 handles the warps that need no ghost agents (it overlaps the halo exchange), pass 2 the
-    // warps with a target in a cell column that borders a neighbour strip; pass 0 = everything
-    int pass, border_lo, border_hi;  // border columns (-1: no neighbour on that side)
 };
 
 struct WarpSmem {
@@ -194,16 +191,6 @@ __global__ void __launch_bounds__(STEP_THREADS, MODEL == 0 ? STEP_MINB_CIRC : ST
     const int oo = A.order ? A.order[tt] : tt;   // where this agent's planes live in `in`
     constexpr int REC = MODEL == 0 ? REC_CIRC : REC_THREE;
 
-    if (t == 0 && (A.flags & CDB_STEP_INTEGRATOR) && A.pass != 2) {
-        const double dt0 = adaptive_timestep(A.vmax, A.dt_min, A.dt_max);
-        A.dt_out[0] = dt0; A.dt_out[1] += dt0;
-        if (A.dt_log) *A.dt_log = dt0;
-    }
-    if (A.pass != 0) {
-        const int cxm = A.cell_sorted[tt] / (int)A.grid->ny;
-        const bool border = __any_sync(FULL, active && (cxm == A.border_lo || cxm == A.border_hi));
-        if (border == (A.pass == 1)) return;     // whole warp: not this pass's business
-    }
     // ---- Navigation, Orientation, Adjusting (logic.py:149-165,258-261,89-94) --------------------------------------------
     double e0x = s(E0X, oo), e0y = s(E0Y, oo);
     double fx = s(FX, oo), fy = s(FY, oo), tq = 0.0, phi0 = 0.0;
@@ -384,6 +371,10 @@ __global__ void __launch_bounds__(STEP_THREADS, MODEL == 0 ? STEP_MINB_CIRC : ST
 
     // ---- Integrator (integrator.py:209-256) + Reset (logic.py:59-64); new state goes to the other buffer --------------------
     const double dt = adaptive_timestep(A.vmax, A.dt_min, A.dt_max);
+    if (t == 0) {
+        A.dt_out[0] = dt; A.dt_out[1] += dt;
+        if (A.dt_log) *A.dt_log = dt;
+    }
     double nvx = vx, nvy = vy, npx = px, npy = py;
     verlet(fx, s(FPX, oo), mass, dt, nvx, npx);
     verlet(fy, s(FPY, oo), mass, dt, nvy, npy);

@@ -77,9 +77,6 @@ class CudaStripDevice:
     def import_vmax(self, buf):
         _lib.check(self.lib.cdb_strip_import_vmax(self.handle, self._p(buf)))
 
-    def interior(self, flags, dt_min, dt_max):
-        _lib.check(self.lib.cdb_strip_interior(self.handle, flags, dt_min, dt_max))
-
     def finish(self, flags, dt_min, dt_max, halo_left_in, halo_right_in, mig_left_out, mig_right_out):
         _lib.check(self.lib.cdb_strip_finish(self.handle, flags, dt_min, dt_max, self._p(halo_left_in),
                                              self._p(halo_right_in), self._p(mig_left_out), self._p(mig_right_out)))
@@ -152,10 +149,10 @@ class StripSimulation:
         return self._n_owned
 
     # -- neighbour exchange ---------------------------------------------------------------------------------------------
-    def _exchange_start(self, out, inn):
-        """Post the sends / receives with both neighbours; returns the requests (compute can be queued before waiting)."""
+    def _exchange(self, out, inn):
+        """Send out['l'] to the left neighbour and out['r'] to the right one; receive into inn['l'] / inn['r']."""
         if self.world == 1:
-            return []
+            return
         dist = self.dist
         ops = []
         if self.left is not None:
@@ -164,26 +161,13 @@ class StripSimulation:
         if self.right is not None:
             ops.append(dist.P2POp(dist.isend, out['r'], self.right))
             ops.append(dist.P2POp(dist.irecv, inn['r'], self.right))
-        return dist.batch_isend_irecv(ops)
-
-    @staticmethod
-    def _exchange_wait(reqs):
-        for req in reqs:
+        for req in dist.batch_isend_irecv(ops):
             req.wait()
-
-    def _exchange(self, out, inn):
-        """Send out['l'] to the left neighbour and out['r'] to the right one; receive into inn['l'] / inn['r']."""
-        self._exchange_wait(self._exchange_start(out, inn))
 
     # -- the phases of one step (driven by step() over torch.distributed, or by LocalGroup in one process) ---------------
     def phase_begin(self):
         L, R = self.left is not None, self.right is not None
         self.dev.begin(self.flags, self.cell_size, self.halo_out['l'] if L else None, self.halo_out['r'] if R else None)
-
-    def phase_interior(self):
-        """The part of the step that needs no ghosts; queued behind the block list while the halos are in flight."""
-        if hasattr(self.dev, 'interior'):
-            self.dev.interior(self.flags, self.dt_min, self.dt_max)
 
     def phase_finish(self, flags=None, use_halo=True):
         L, R = self.left is not None, self.right is not None
@@ -202,13 +186,11 @@ class StripSimulation:
     def step(self, n_steps=1):
         for _ in range(n_steps):
             self.phase_begin()
-            if self.adaptive and self.world > 1:      # dt must be global before anything integrates
+            self._exchange(self.halo_out, self.halo_in)
+            if self.adaptive and self.world > 1:
                 self.dev.export_vmax(self.vmax)
                 self.dist.all_reduce(self.vmax, op=self.dist.ReduceOp.MAX)
                 self.dev.import_vmax(self.vmax)
-            reqs = self._exchange_start(self.halo_out, self.halo_in)
-            self.phase_interior()                     # overlaps the halo exchange
-            self._exchange_wait(reqs)
             self.phase_finish()
             self._exchange(self.mig_out, self.mig_in)
             self.phase_absorb()
@@ -315,6 +297,7 @@ class LocalGroup:
         for _ in range(n_steps):
             for s in self.sims:
                 s.phase_begin()
+            self._exchange('halo_out', 'halo_in')
             if self.sims[0].adaptive and len(self.sims) > 1:
                 for s in self.sims:
                     s.dev.export_vmax(s.vmax)
@@ -324,9 +307,6 @@ class LocalGroup:
                 for s in self.sims:
                     s.vmax.copy_(m)
                     s.dev.import_vmax(s.vmax)
-            for s in self.sims:
-                s.phase_interior()
-            self._exchange('halo_out', 'halo_in')
             for s in self.sims:
                 s.phase_finish()
             self._exchange('mig_out', 'mig_in')

@@ -163,8 +163,6 @@ int64_t cdb_migrant_buffer_doubles(const cdb_sim *sim);
  *   begin   block list of the owned agents; packs the first / last owned cell column (neighbour records + per-cell
  *           counts) into halo_left_out / halo_right_out (NULL where there is no neighbour)
  *   -- caller exchanges halos, and MAX-reduces the two doubles of export_vmax across ranks when dt_min != dt_max --
- *   interior (optional, between begin and finish) runs the fused step kernel for all warps that need no ghost agents, so
- *           that it overlaps the halo exchange; finish then only handles the warps next to a strip border
  *   finish  installs the received ghost columns, runs the fused step kernel on the owned agents, then packs the agents
  *           that left the strip into mig_left_out / mig_right_out
  *   -- caller exchanges migrants --
@@ -173,7 +171,6 @@ int64_t cdb_migrant_buffer_doubles(const cdb_sim *sim);
 int cdb_strip_begin(cdb_sim *sim, uint32_t node_flags, double cell_size, double *halo_left_out, double *halo_right_out);
 int cdb_strip_export_vmax(cdb_sim *sim, double *dev_vmax2);
 int cdb_strip_import_vmax(cdb_sim *sim, const double *dev_vmax2);
-int cdb_strip_interior(cdb_sim *sim, uint32_t node_flags, double dt_min, double dt_max);
 int cdb_strip_finish(cdb_sim *sim, uint32_t node_flags, double dt_min, double dt_max, const double *halo_left_in,
                      const double *halo_right_in, double *mig_left_out, double *mig_right_out);
 int cdb_strip_absorb(cdb_sim *sim, const double *mig_left_in, const double *mig_right_in, int64_t *n_out);
