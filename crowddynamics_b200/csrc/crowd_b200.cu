@@ -295,7 +295,6 @@ int build_block_list(cdb_sim *sim, double cell_size, bool padded_lattice = false
 }
 
 int launch_reduce_vmax(cdb_sim *sim) {
-    cudaStream_t st = sim->stream;
     LAUNCH(sim, k_vmax_init, 1, 32, 0, sim->d_vmax);
     if (sim->n > 0) {
         int blocks = cdiv(sim->n, 256 * 4);
@@ -889,6 +888,7 @@ int64_t cdb_migrant_buffer_doubles(const cdb_sim *sim) { return sim ? MSG_HEADER
 int cdb_strip_begin(cdb_sim *sim, uint32_t flags, double cell_size, double *halo_left_out, double *halo_right_out) {
     SIM_ENTRY();
     if (!sim->strip) return fail(CDB_ERR_STATE, "cdb_set_strip has not been called");
+    if (sim->variant == 1) return fail(CDB_ERR_STATE, "the strip decomposition needs the fused step kernel (variant 2)");
     CKS(prof_mark(sim));
     LAUNCH(sim, k_vmax_init, 1, 32, 0, sim->d_vmax);
     CKS(build_block_list(sim, cell_size, false, sim->d_vmax, false));
