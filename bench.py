@@ -190,9 +190,10 @@ def run_reference(args, rank, world):
 
 
 def workload_config(args, n_per_gpu, world):
-    return {'workload': 'synthetic %d %s agents per GPU, uniform %.3g agents/m^2 in a walled square room, 4 wall '
-                        'segments, static exit direction field (step 1 m), cell 3.6 m, dt_min=dt_max=0.01'
-                        % (n_per_gpu, args.model, args.density),
+    geom = ('a room with a door (11 wall segments)' if getattr(args, 'workload', 'room') == 'room_exit'
+            else 'a walled square room, 4 wall segments')
+    return {'workload': 'synthetic %d %s agents per GPU, uniform %.3g agents/m^2 in %s, static exit direction field '
+                        '(step 1 m), cell 3.6 m, dt_min=dt_max=0.01' % (n_per_gpu, args.model, args.density, geom),
             'agents_per_gpu': n_per_gpu, 'agent_model': args.model, 'density': args.density,
             'parallelism': 'strips%d' % world if world > 1 else 'single',
             'l2_policy': 'inputs larger than L2 (%d MB of SoA state streamed per step)'
@@ -209,6 +210,8 @@ def main():
     ap.add_argument('--model', default='three_circle', choices=['circular', 'three_circle'])
     ap.add_argument('--agents', type=int, default=1000000, help='agents per GPU')
     ap.add_argument('--density', type=float, default=1.0)
+    ap.add_argument('--workload', default='room', choices=['room', 'room_exit'],
+                    help="room: walled square (configs 2/3/5); room_exit: room with a door, 11 wall segments, exit field (config 4)")
     ap.add_argument('--cpu-agents', type=int, default=0, help='agents in the CPU baseline sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-fp64-peak', action='store_true', help='skip the DFMA peak micro-benchmark (used under ncu)')
@@ -244,11 +247,17 @@ def main():
         step_fn, dev = sim.step, sim.dev
         n_local = sim.n_owned
     else:
-        agents, obstacles, side = make_crowd(args.model, n, args.density, seed=0)
+        if args.workload == 'room_exit':
+            from crowddynamics_b200 import synthetic as S
+            agents, obstacles, fields, side = S.room_with_exit(n, args.model, density=args.density, seed=0, step=1.0)
+            field = fields[0]
+        else:
+            agents, obstacles, side = make_crowd(args.model, n, args.density, seed=0)
+            field = make_field(side)
         dev = DeviceAgents(mid, capacity=n, device=local_rank)
         dev.set_stream(torch.cuda.current_stream().cuda_stream)
         dev.set_obstacles(obstacles)
-        dev.set_navigation_field(0, *make_field(side))
+        dev.set_navigation_field(0, *field)
         # pinned host image of simulation.agents.array (packed records), the e2e leg copies it every step
         host = torch.empty(n * itemsize, dtype=torch.uint8).pin_memory()
         host.numpy()[:] = agents.view(np.uint8).reshape(-1)
