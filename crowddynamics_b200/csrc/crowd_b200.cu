@@ -275,7 +275,7 @@ int build_block_list(cdb_sim *sim, double cell_size, bool padded_lattice = false
                                          sim->d_cell_count, sim->d_order, live_dev);
     if (physical) {
         if (live > 0) LAUNCH(sim, k_gather, cdiv(live, T), T, 0, sim->cur, sim->alt, (int)live, sim->n_planes, sim->model,
-                             sim->d_order, sim->d_cell_of_slot, sim->d_order_tmp, sim->d_nbr);
+                             sim->d_order, sim->d_cell_of_slot, sim->d_order_tmp, sim->d_nbr, cell_size);
         // d_order_tmp now holds the flat cell of every *sorted* slot
         std::swap(sim->cur, sim->alt);
         std::swap(sim->d_cell_of_slot, sim->d_order_tmp);
@@ -284,7 +284,7 @@ int build_block_list(cdb_sim *sim, double cell_size, bool padded_lattice = false
         sim->perm_valid = false;
     } else {
         if (live > 0) LAUNCH(sim, k_records, cdiv(live, T), T, 0, sim->cur, (int)live, live_dev, sim->model, sim->d_order, sim->d_cell_of_slot,
-                             sim->d_order_tmp, sim->d_nbr);
+                             sim->d_order_tmp, sim->d_nbr, cell_size);
         std::swap(sim->d_cell_of_slot, sim->d_order_tmp);   // d_cell_of_slot: flat cell per sorted slot; d_order_tmp: per plane slot
         sim->perm_valid = true;
     }
@@ -330,6 +330,7 @@ StepArgs step_args(cdb_sim *sim, unsigned flags, double dt_min, double dt_max, d
     a.in = sim->cur;
     a.out = (flags & CDB_STEP_INTEGRATOR) ? sim->alt : sim->cur;
     a.nbr = sim->d_nbr;
+    a.cell_size = sim->cell_size;
     const bool listed = (flags & CDB_STEP_AGENT_AGENT) != 0;
     a.n = (int)(listed ? sim->n_sorted : sim->n);
     a.order = listed && sim->perm_valid ? sim->d_order : nullptr;

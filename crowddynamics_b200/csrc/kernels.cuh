@@ -563,11 +563,11 @@ __global__ void k_rank_fix(const int *__restrict__ order_tmp, int n_host, const 
 
 // physical reorder into cell order (all record planes) + the packed neighbour records the pair kernel sweeps:
 //   circular      {px, py, vx, vy, radius, -}                                                   48 B
-//   three-circle  {px, py, vx, vy, extent, r_t, r_s, - | lsx, lsy, rsx, rsy, ox, oy, -, -}     128 B (one line)
+//   three-circle  {px, py, vx, vy, extent, r_t, r_s, - | lsx, lsy, rsx, rsy, ox, oy, cell_x, cell_y}     128 B (one line)
 // extent = conservative radius of the whole body around the centre (from the STORED shoulder positions), (ox, oy) =
 // r_ts (sin phi, -cos phi), the shoulder displacement of power_law.py:338-350.
 __global__ void k_gather(Soa src, Soa dst, int n, int n_planes, int model, const int *__restrict__ order,
-                         const int *__restrict__ cell_of_slot, int *__restrict__ cell_sorted, double *__restrict__ nbr) {
+                         const int *__restrict__ cell_of_slot, int *__restrict__ cell_sorted, double *__restrict__ nbr, double cell_size) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
     const int o = order[t];
@@ -587,18 +587,19 @@ __global__ void k_gather(Soa src, Soa dst, int n, int n_planes, int model, const
         double2 *r = reinterpret_cast<double2 *>(nbr + (size_t)t * 16);
         r[0] = make_double2(x, y); r[1] = make_double2(vx, vy); r[2] = make_double2(ext, r_t); r[3] = make_double2(r_s, 0.0);
         r[4] = make_double2(lsx, lsy); r[5] = make_double2(rsx, rsy);
-        r[6] = make_double2(r_ts * sin(phi), r_ts * -cos(phi)); r[7] = make_double2(0.0, 0.0);
+        r[6] = make_double2(r_ts * sin(phi), r_ts * -cos(phi));
+        r[7] = make_double2(floor(x / cell_size), floor(y / cell_size));   // true cell coordinates: pair orientation
     }
 }
 
 // packed neighbour records in cell order WITHOUT moving the planes (the fused step kernel reads its own agent through
 // `order` and writes the new state in cell order, so the physical sort happens as a by-product of the step):
 //   circular      {px, py, vx, vy, radius, -}                                                   48 B
-//   three-circle  {px, py, vx, vy, extent, r_t, r_s, - | lsx, lsy, rsx, rsy, ox, oy, -, -}     128 B (one line)
+//   three-circle  {px, py, vx, vy, extent, r_t, r_s, - | lsx, lsy, rsx, rsy, ox, oy, cell_x, cell_y}     128 B (one line)
 // extent = conservative radius of the whole body around the centre (from the STORED shoulder positions), (ox, oy) =
 // r_ts (sin phi, -cos phi), the shoulder displacement of power_law.py:338-350.
 __global__ void k_records(Soa src, int n_host, const int *n_dev, int model, const int *__restrict__ order,
-                         const int *__restrict__ cell_of_slot, int *__restrict__ cell_sorted, double *__restrict__ nbr) {
+                         const int *__restrict__ cell_of_slot, int *__restrict__ cell_sorted, double *__restrict__ nbr, double cell_size) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= eff_n(n_host, n_dev)) return;
     const int o = order[t];
@@ -615,7 +616,8 @@ __global__ void k_records(Soa src, int n_host, const int *n_dev, int model, cons
         double2 *r = reinterpret_cast<double2 *>(nbr + (size_t)t * 16);
         r[0] = make_double2(x, y); r[1] = make_double2(vx, vy); r[2] = make_double2(ext, r_t); r[3] = make_double2(r_s, 0.0);
         r[4] = make_double2(lsx, lsy); r[5] = make_double2(rsx, rsy);
-        r[6] = make_double2(r_ts * sin(phi), r_ts * -cos(phi)); r[7] = make_double2(0.0, 0.0);
+        r[6] = make_double2(r_ts * sin(phi), r_ts * -cos(phi));
+        r[7] = make_double2(floor(x / cell_size), floor(y / cell_size));   // true cell coordinates: pair orientation
     }
 }
 

@@ -35,11 +35,12 @@ constexpr int CHUNK = STEP_CHUNK;     // candidates classified between two list-
 
 // packed neighbour records (doubles per agent)
 constexpr int REC_CIRC = 6;     // px py vx vy r -
-constexpr int REC_THREE = 16;   // px py vx vy ext rt rs - | lsx lsy rsx rsy ox oy - -
+constexpr int REC_THREE = 16;   // px py vx vy ext rt rs - | lsx lsy rsx rsy ox oy cell_x cell_y
 
 struct StepArgs {
     Soa in, out;             // out == in unless integrating (then the new state is written to the other buffer)
     const double *nbr;       // packed neighbour records of `in`
+    double cell_size;
     int n;                   // targets (host-side bound)
     const int *n_dev;        // device-side exact count (nullptr: n is exact)
     const Grid *grid;
@@ -256,10 +257,13 @@ __global__ void __launch_bounds__(STEP_THREADS, MODEL == 0 ? STEP_MINB_CIRC : ST
                         const CircMe me = {p.x, p.y, v.x, v.y, __ldg(rm + 4), par.mass, par.k_soc, par.tau_0, par.mu, par.kappa, par.damping};
                         pair_circular(me, po.x, po.y, vo.x, vo.y, __ldg(ro + 4), rfx, rfy);
                     } else {
-                        // reference pair orientation: i is the lexicographically smaller (cell_x, cell_y, agent index):
-                        // cell order, then (same cell => both owned) the order of the cell-sorted slots
-                        const int ctg = A.cell_sorted[tg], cu = A.cell_sorted[u];
-                        const bool me_is_i = ctg < cu || (ctg == cu && tg < u);   // ghosts never share a cell with owned agents
+                        // reference pair orientation: i is the lexicographically smaller (cell_x, cell_y, agent index).
+                        // The TRUE cell coordinates floor(p / c) (last two slots of the neighbour record) are compared, not
+                        // the flat ids of the search lattice, so the convention does not depend on how the lattice was chosen
+                        // (padded, fixed, clamped, per-strip).  Agents of the same true cell share a flat cell, inside which
+                        // the slots are ordered by agent index.
+                        const double2 ca = ldg2(nbr + (size_t)tg * REC + 14), cb = ldg2(nbr + (size_t)u * REC + 14);
+                        const bool me_is_i = ca.x != cb.x ? ca.x < cb.x : (ca.y != cb.y ? ca.y < cb.y : tg < u);
                         Three I, J;     // loaded straight into their roles: one inlined copy of the pair arithmetic, no selects
                         load_three_rec(nbr, me_is_i ? tg : u, I);
                         load_three_rec(nbr, me_is_i ? u : tg, J);
