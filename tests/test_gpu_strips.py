@@ -91,6 +91,25 @@ def test_settle_moves_misplaced_agents():
     assert np.abs(got['position'] - ref['position']).max() <= 1e-12
 
 
-@pytest.mark.skipif(True, reason='needs >= 2 GPUs; run manually: torchrun --nproc-per-node 2 tests/run_strips_nccl.py')
-def test_placeholder_multi_gpu():
-    pass
+def _gpu_count():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+@pytest.mark.skipif(_gpu_count() < 2, reason='needs >= 2 GPUs (one process per GPU over NCCL)')
+def test_nccl_strips_one_process_per_gpu():
+    """torchrun with one rank per visible GPU (at most 4): halo + migrant exchange over NCCL, gathered result must equal
+    the single-GPU trajectory bit for bit (tests/run_strips_nccl.py)."""
+    n = min(_gpu_count(), 4)
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    port = s.getsockname()[1]
+    s.close()
+    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', str(n), '--master-addr', '127.0.0.1',
+           '--master-port', str(port), os.path.join(ROOT, 'tests', 'run_strips_nccl.py')]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert out.stdout.count(' OK') == 4 and 'FAIL' not in out.stdout
