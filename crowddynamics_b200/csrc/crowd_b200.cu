@@ -106,6 +106,7 @@ struct cdb_sim {
     int *d_cell_of_slot = nullptr;   // flat cell of each slot (of `cur`, valid after build)
     int *d_order_tmp = nullptr, *d_order = nullptr;
     double *d_nbr = nullptr;         // packed neighbour records of the cell-sorted state
+    double *d_nbr_sweep = nullptr;   // three-circle: compact 48 B records for the phase-1 sweep (circular: alias of d_nbr)
     int *d_scan_partials = nullptr;
     long long *d_bbox = nullptr;     // min ix, max ix, min iy, max iy
     long long *h_bbox = nullptr;     // pinned
@@ -182,6 +183,8 @@ int alloc_ghost_tail(cdb_sim *sim) {
     CKS(dev_alloc(&sim->d_cell_of_slot, cap));
     CKS(dev_alloc(&sim->d_order_tmp, cap));
     CKS(dev_alloc(&sim->d_nbr, cap * (sim->model == CDB_MODEL_CIRCULAR ? REC_CIRC : REC_THREE)));
+    if (sim->model == CDB_MODEL_CIRCULAR) sim->d_nbr_sweep = sim->d_nbr;
+    else CKS(dev_alloc(&sim->d_nbr_sweep, cap * REC_CIRC));
     return CDB_OK;
 }
 
@@ -275,7 +278,7 @@ int build_block_list(cdb_sim *sim, double cell_size, bool padded_lattice = false
                                          sim->d_cell_count, sim->d_order, live_dev);
     if (physical) {
         if (live > 0) LAUNCH(sim, k_gather, cdiv(live, T), T, 0, sim->cur, sim->alt, (int)live, sim->n_planes, sim->model,
-                             sim->d_order, sim->d_cell_of_slot, sim->d_order_tmp, sim->d_nbr, cell_size);
+                             sim->d_order, sim->d_cell_of_slot, sim->d_order_tmp, sim->d_nbr, sim->d_nbr_sweep, cell_size);
         // d_order_tmp now holds the flat cell of every *sorted* slot
         std::swap(sim->cur, sim->alt);
         std::swap(sim->d_cell_of_slot, sim->d_order_tmp);
@@ -284,7 +287,7 @@ int build_block_list(cdb_sim *sim, double cell_size, bool padded_lattice = false
         sim->perm_valid = false;
     } else {
         if (live > 0) LAUNCH(sim, k_records, cdiv(live, T), T, 0, sim->cur, (int)live, live_dev, sim->model, sim->d_order, sim->d_cell_of_slot,
-                             sim->d_order_tmp, sim->d_nbr, cell_size);
+                             sim->d_order_tmp, sim->d_nbr, sim->d_nbr_sweep, cell_size);
         std::swap(sim->d_cell_of_slot, sim->d_order_tmp);   // d_cell_of_slot: flat cell per sorted slot; d_order_tmp: per plane slot
         sim->perm_valid = true;
     }
@@ -330,6 +333,7 @@ StepArgs step_args(cdb_sim *sim, unsigned flags, double dt_min, double dt_max, d
     a.in = sim->cur;
     a.out = (flags & CDB_STEP_INTEGRATOR) ? sim->alt : sim->cur;
     a.nbr = sim->d_nbr;
+    a.nbr_sweep = sim->d_nbr_sweep;
     a.cell_size = sim->cell_size;
     const bool listed = (flags & CDB_STEP_AGENT_AGENT) != 0;
     a.n = (int)(listed ? sim->n_sorted : sim->n);
@@ -489,7 +493,7 @@ int cdb_destroy(cdb_sim *sim) {
     free_soa(sim->cur); free_soa(sim->alt);
     cudaFree(sim->d_aos); cudaFreeHost(sim->h_bounce);
     cudaFree(sim->d_grid); cudaFree(sim->d_cell_count); cudaFree(sim->d_cell_start); cudaFree(sim->d_cell_fill);
-    cudaFree(sim->d_cell_of_slot); cudaFree(sim->d_order_tmp); cudaFree(sim->d_order); cudaFree(sim->d_nbr); cudaFree(sim->d_scan_partials);
+    cudaFree(sim->d_cell_of_slot); cudaFree(sim->d_order_tmp); cudaFree(sim->d_order); if (sim->d_nbr_sweep != sim->d_nbr) cudaFree(sim->d_nbr_sweep); cudaFree(sim->d_nbr); cudaFree(sim->d_scan_partials);
     cudaFree(sim->d_bbox); cudaFreeHost(sim->h_bbox);
     cudaFree(sim->d_obstacles);
     for (auto &f : sim->nav) { cudaFree((void *)f.U); cudaFree((void *)f.V); }
@@ -926,13 +930,13 @@ int cdb_strip_finish(cdb_sim *sim, uint32_t flags, double dt_min, double dt_max,
     const int ny = (int)sim->grid.ny;
     const int base_l = (int)sim->capacity, base_r = (int)(sim->capacity + sim->halo_cap);
     if (sim->has_left) {
-        if (halo_left_in) LAUNCH(sim, k_halo_unpack, 1, 1024, 0, halo_left_in, rec, sim->d_nbr, sim->d_cell_of_slot, sim->d_cell_start, sim->d_cell_count,
+        if (halo_left_in) LAUNCH(sim, k_halo_unpack, 1, 1024, 0, halo_left_in, rec, sim->d_nbr, sim->d_nbr_sweep, sim->d_cell_of_slot, sim->d_cell_start, sim->d_cell_count,
                                  0, ny, base_l, (long long)sim->halo_cap, sim->d_error);
         else LAUNCH(sim, k_ghost_clear, 4, 256, 0, sim->d_cell_start, sim->d_cell_count, 0, ny, base_l);
     }
     if (sim->has_right) {
         const int col = (int)sim->grid.nx - 1;
-        if (halo_right_in) LAUNCH(sim, k_halo_unpack, 1, 1024, 0, halo_right_in, rec, sim->d_nbr, sim->d_cell_of_slot, sim->d_cell_start, sim->d_cell_count,
+        if (halo_right_in) LAUNCH(sim, k_halo_unpack, 1, 1024, 0, halo_right_in, rec, sim->d_nbr, sim->d_nbr_sweep, sim->d_cell_of_slot, sim->d_cell_start, sim->d_cell_count,
                                   col, ny, base_r, (long long)sim->halo_cap, sim->d_error);
         else LAUNCH(sim, k_ghost_clear, 4, 256, 0, sim->d_cell_start, sim->d_cell_count, col, ny, base_r);
     }

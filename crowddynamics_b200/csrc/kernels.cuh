@@ -567,7 +567,7 @@ __global__ void k_rank_fix(const int *__restrict__ order_tmp, int n_host, const 
 // extent = conservative radius of the whole body around the centre (from the STORED shoulder positions), (ox, oy) =
 // r_ts (sin phi, -cos phi), the shoulder displacement of power_law.py:338-350.
 __global__ void k_gather(Soa src, Soa dst, int n, int n_planes, int model, const int *__restrict__ order,
-                         const int *__restrict__ cell_of_slot, int *__restrict__ cell_sorted, double *__restrict__ nbr, double cell_size) {
+                         const int *__restrict__ cell_of_slot, int *__restrict__ cell_sorted, double *__restrict__ nbr, double *__restrict__ nbr_sweep, double cell_size) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
     const int o = order[t];
@@ -589,6 +589,8 @@ __global__ void k_gather(Soa src, Soa dst, int n, int n_planes, int model, const
         r[4] = make_double2(lsx, lsy); r[5] = make_double2(rsx, rsy);
         r[6] = make_double2(r_ts * sin(phi), r_ts * -cos(phi));
         r[7] = make_double2(floor(x / cell_size), floor(y / cell_size));   // true cell coordinates: pair orientation
+        double2 *q = reinterpret_cast<double2 *>(nbr_sweep + (size_t)t * 6);   // compact record for the phase-1 sweep
+        q[0] = make_double2(x, y); q[1] = make_double2(vx, vy); q[2] = make_double2(ext, 0.0);
     }
 }
 
@@ -599,7 +601,7 @@ __global__ void k_gather(Soa src, Soa dst, int n, int n_planes, int model, const
 // extent = conservative radius of the whole body around the centre (from the STORED shoulder positions), (ox, oy) =
 // r_ts (sin phi, -cos phi), the shoulder displacement of power_law.py:338-350.
 __global__ void k_records(Soa src, int n_host, const int *n_dev, int model, const int *__restrict__ order,
-                         const int *__restrict__ cell_of_slot, int *__restrict__ cell_sorted, double *__restrict__ nbr, double cell_size) {
+                         const int *__restrict__ cell_of_slot, int *__restrict__ cell_sorted, double *__restrict__ nbr, double *__restrict__ nbr_sweep, double cell_size) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= eff_n(n_host, n_dev)) return;
     const int o = order[t];
@@ -618,6 +620,8 @@ __global__ void k_records(Soa src, int n_host, const int *n_dev, int model, cons
         r[4] = make_double2(lsx, lsy); r[5] = make_double2(rsx, rsy);
         r[6] = make_double2(r_ts * sin(phi), r_ts * -cos(phi));
         r[7] = make_double2(floor(x / cell_size), floor(y / cell_size));   // true cell coordinates: pair orientation
+        double2 *q = reinterpret_cast<double2 *>(nbr_sweep + (size_t)t * 6);   // compact record for the phase-1 sweep
+        q[0] = make_double2(x, y); q[1] = make_double2(vx, vy); q[2] = make_double2(ext, 0.0);
     }
 }
 

@@ -40,6 +40,7 @@ constexpr int REC_THREE = 16;   // px py vx vy ext rt rs - | lsx lsy rsx rsy ox 
 struct StepArgs {
     Soa in, out;             // out == in unless integrating (then the new state is written to the other buffer)
     const double *nbr;       // packed neighbour records of `in`
+    const double *nbr_sweep; // compact 48 B sweep records {px, py, vx, vy, R, -} (circular: == nbr)
     double cell_size;
     int n;                   // targets (host-side bound)
     const int *n_dev;        // device-side exact count (nullptr: n is exact)
@@ -217,7 +218,7 @@ __global__ void __launch_bounds__(STEP_THREADS, MODEL == 0 ? STEP_MINB_CIRC : ST
         // what phase 1 needs of the target: centre, velocity, radius (circular) / body extent (three-circle)
         double mpx, mpy, mvx, mvy, mr;
         {
-            const double *r = nbr + (size_t)tt * REC;
+            const double *r = A.nbr_sweep + (size_t)tt * REC_CIRC;
             const double2 p = ldg2(r), v = ldg2(r + 2);
             mpx = p.x; mpy = p.y; mvx = v.x; mvy = v.y; mr = __ldg(r + 4);
         }
@@ -311,7 +312,7 @@ __global__ void __launch_bounds__(STEP_THREADS, MODEL == 0 ? STEP_MINB_CIRC : ST
                 for (int kk = 0; kk < CHUNK; ++kk) {
                     const int u = b + k0 + kk;
                     const bool inr = u < e;
-                    const double *r = nbr + (size_t)(inr ? u : tt) * REC;
+                    const double *r = A.nbr_sweep + (size_t)(inr ? u : tt) * REC_CIRC;
                     const double2 p = ldg2(r), v = ldg2(r + 2);
                     const double ro = __ldg(r + 4);
                     const double x = mpx - p.x, y = mpy - p.y;

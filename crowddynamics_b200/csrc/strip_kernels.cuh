@@ -26,7 +26,8 @@ __global__ void k_halo_pack(const double *__restrict__ nbr, int rec, const int *
 }
 
 // message -> ghost column `col` of the local lattice; ghost records live at slots [base, base + count) of nbr.
-__global__ void k_halo_unpack(const double *__restrict__ msg, int rec, double *__restrict__ nbr, int *__restrict__ cell_sorted,
+__global__ void k_halo_unpack(const double *__restrict__ msg, int rec, double *__restrict__ nbr, double *__restrict__ nbr_sweep,
+                              int *__restrict__ cell_sorted,
                               int *__restrict__ cell_start, int *__restrict__ cell_count, int col, int ny, int base, long long cap,
                               int *error) {
     // single block: exclusive scan of the per-cell counts
@@ -64,6 +65,11 @@ __global__ void k_halo_unpack(const double *__restrict__ msg, int rec, double *_
     const double *src = msg + MSG_HEADER + halo_counts_doubles(ny);
     double *dst = nbr + (size_t)base * rec;
     for (long long i = threadIdx.x; i < (long long)count * rec; i += blockDim.x) dst[i] = src[i];
+    if (nbr_sweep != nbr)     // three-circle: compact sweep records of the ghosts {px, py, vx, vy, extent, -}
+        for (long long i = threadIdx.x; i < (long long)count * 6; i += blockDim.x) {
+            const long long a = i / 6, f = i % 6;
+            nbr_sweep[(size_t)base * 6 + i] = f < 5 ? src[a * rec + f] : 0.0;
+        }
 }
 
 // no neighbour on this side / nothing received: empty ghost column
