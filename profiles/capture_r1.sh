@@ -2,7 +2,7 @@
 # then the bench lines.  Numbers printed by runs under ncu are never used as bench values.
 set -x
 mkdir -p gpurun_out
-TAG=${TAG:-r1e}
+TAG=${TAG:-r1f}
 for m in three_circle circular; do
   ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_${m}_r1.csv python bench.py --model $m --steps 3 --warmup 3 --no-cpu-baseline --no-fp64-peak --e2e-steps 1 > gpurun_out/launches_${m}.log 2>&1
   ncu --set full --clock-control none --import-source on -k regex:k_step -s 3 -c 1 -o gpurun_out/prof_${m}_${TAG} -f python bench.py --model $m --steps 2 --warmup 3 --no-cpu-baseline --no-fp64-peak --e2e-steps 1 > gpurun_out/ncu_${m}.log 2>&1
