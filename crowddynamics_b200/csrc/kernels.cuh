@@ -348,12 +348,15 @@ __global__ void k_unpack_aos(const uint8_t *__restrict__ aos, int n, Soa s) {
     if (t >= nrec) return;
     const int i = rec0 + t;
     const uint32_t *rec = sm + t * WORDS;    // odd word stride: conflict-free
-    const FieldMap *fm = MODEL == 0 ? c_fields_circ : c_fields_three;
+    // field table as compile-time constants: the loop unrolls into straight LDS / STG pairs
+    constexpr FieldMap fmc[] = {CIRC_FIELDS(0)};
+    constexpr FieldMap fmt[] = {CIRC_FIELDS(32), THREE_FIELDS};
     constexpr int NF = MODEL == 0 ? N_FIELDS_CIRC : N_FIELDS_THREE;
-#pragma unroll 1
+#pragma unroll
     for (int f = 0; f < NF; ++f) {
-        int w = fm[f].offset >> 2;
-        s(fm[f].plane, i) = __hiloint2double((int)rec[w + 1], (int)rec[w]);
+        const int w = (MODEL == 0 ? fmc[f < N_FIELDS_CIRC ? f : 0].offset : fmt[f].offset) >> 2;
+        const int plane = MODEL == 0 ? fmc[f < N_FIELDS_CIRC ? f : 0].plane : fmt[f].plane;
+        s(plane, i) = __hiloint2double((int)rec[w + 1], (int)rec[w]);
     }
     // States.target: int64 at byte offset B + 2 (2-byte aligned)
     const uint8_t *rb = reinterpret_cast<const uint8_t *>(rec) + (MODEL == 0 ? 2 : 34);
@@ -370,13 +373,17 @@ __global__ void k_pack_aos(Soa s, int n, uint8_t *__restrict__ aos, unsigned mas
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n || s.id[t] < 0) return;
     uint32_t *rec = reinterpret_cast<uint32_t *>(aos + (size_t)s.id[t] * ITEM);
-    const FieldMap *fm = MODEL == 0 ? c_fields_circ : c_fields_three;
+    constexpr FieldMap fmc[] = {CIRC_FIELDS(0)};
+    constexpr FieldMap fmt[] = {CIRC_FIELDS(32), THREE_FIELDS};
     constexpr int NF = MODEL == 0 ? N_FIELDS_CIRC : N_FIELDS_THREE;
-#pragma unroll 1
+#pragma unroll
     for (int f = 0; f < NF; ++f) {
-        if (!(fm[f].bit & mask)) continue;
-        double v = s(fm[f].plane, t);
-        int w = fm[f].offset >> 2;
+        const unsigned bit = MODEL == 0 ? fmc[f < N_FIELDS_CIRC ? f : 0].bit : fmt[f].bit;
+        if (bit == 0u) continue;                       // constants are never written back (known at compile time)
+        if (!(bit & mask)) continue;
+        const int w = (MODEL == 0 ? fmc[f < N_FIELDS_CIRC ? f : 0].offset : fmt[f].offset) >> 2;
+        const int plane = MODEL == 0 ? fmc[f < N_FIELDS_CIRC ? f : 0].plane : fmt[f].plane;
+        const double v = s(plane, t);
         rec[w] = (uint32_t)__double2loint(v);
         rec[w + 1] = (uint32_t)__double2hiint(v);
     }
