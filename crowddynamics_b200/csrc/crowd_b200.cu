@@ -11,11 +11,13 @@
 
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "kernels.cuh"
@@ -77,7 +79,7 @@ struct cdb_sim {
     int model = 0;
     int64_t itemsize = 0;
     int n_planes = 0;         // planes that mirror record fields
-    int n_alloc_planes = 0;   // + derived planes (three-circle: shoulder offsets, extent)
+    int n_alloc_planes = 0;   // planes allocated (== n_planes)
     int variant = 2;          // agent-agent kernel: 1 = one-phase reference kernel, 2 = two-phase fused kernel
     bool auto_lattice_valid = false;
     int auto_lattice_age = 0;
@@ -580,16 +582,24 @@ int cdb_download_agents_aos(cdb_sim *sim, void *agents, int64_t n, int64_t items
     }
     CK(cudaMemcpyAsync(sim->h_bounce, sim->d_aos, n * itemsize, cudaMemcpyDeviceToHost, sim->stream));
     CK(cudaStreamSynchronize(sim->stream));
-    // merge the selected fields into the caller's records (plumbing: byte copies only)
+    // merge the selected fields into the caller's records (plumbing: byte copies only); adjacent selected fields are
+    // copied as one run per record (position .. force_prev are contiguous in the record)
     int nf = 0;
     const FieldMap *fm = host_field_map(sim->model, &nf);
-    for (int f = 0; f < nf; ++f) {
-        if (!(fm[f].bit & mask)) continue;
-        const int off = fm[f].offset;
-        uint8_t *dst = (uint8_t *)agents + off;
-        const uint8_t *src = sim->h_bounce + off;
-        for (int64_t i = 0; i < n; ++i) memcpy(dst + i * itemsize, src + i * itemsize, 8);
+    std::vector<std::pair<int, int>> runs;   // (offset, bytes), sorted by offset
+    {
+        std::vector<int> offs;
+        for (int f = 0; f < nf; ++f) if (fm[f].bit & mask) offs.push_back(fm[f].offset);
+        std::sort(offs.begin(), offs.end());
+        for (int o : offs) {
+            if (!runs.empty() && runs.back().first + runs.back().second == o) runs.back().second += 8;
+            else runs.emplace_back(o, 8);
+        }
     }
+    uint8_t *dst = (uint8_t *)agents;
+    const uint8_t *src = sim->h_bounce;
+    for (int64_t i = 0; i < n; ++i, dst += itemsize, src += itemsize)
+        for (const auto &r : runs) memcpy(dst + r.first, src + r.first, (size_t)r.second);
     return check_device_error(sim);
 }
 
