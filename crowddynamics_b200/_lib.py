@@ -65,6 +65,7 @@ def _signatures(L):
         'cdb_integrate': (i32, [vp, f64, f64, pf64]),
         'cdb_step': (i32, [vp, u32, f64, f64, f64, i64, vp]),
         'cdb_get_time': (i32, [vp, pf64, pi64]),
+        'cdb_set_graphs': (i32, [vp, i32]),
         'cdb_set_variant': (i32, [vp, i32]),
         'cdb_launch_count': (i64, [vp]),
         'cdb_profile_enable': (i32, [vp, i32]),

@@ -59,7 +59,7 @@ int dev_alloc(T **p, size_t count) {
     return CDB_OK;
 }
 
-constexpr int DT_LOG = 1024;
+constexpr int DT_LOG = DT_LOG_SLOTS;
 constexpr int STRIP_REFRESH = 16;
 constexpr int PROFILE_MAX_STEPS = 4096;
 
@@ -129,6 +129,13 @@ struct cdb_sim {
     int *h_error = nullptr;                 // pinned
     unsigned long long *d_pair_count = nullptr;
     int64_t iterations = 0;
+    unsigned long long *d_stepctr = nullptr;   // device mirror of `iterations` (read by the kernels, advanced after every step)
+    // CUDA graph of two consecutive fused steps (the ping-pong buffers are back in place after two)
+    bool use_graphs = true;
+    cudaGraphExec_t graph_exec = nullptr;
+    int64_t graph_launches = 0;      // kernel launches inside one replay
+    uint64_t state_version = 0;      // bumped by everything that invalidates a captured graph
+    struct GraphKey { uint32_t flags; double cell_size, dt_min, dt_max; bool log; int64_t n; long long ncell, nx, ny; uint64_t version; const void *cur; } graph_key{};
     unsigned long long seed = 0x9E3779B97F4A7C15ULL;   // Fluctuation
     unsigned long long fluct_calls = 0;               // per-node Fluctuation calls (keeps successive calls independent)
 
@@ -348,7 +355,7 @@ StepArgs step_args(cdb_sim *sim, unsigned flags, double dt_min, double dt_max, d
     a.flags = flags;
     a.dt_min = dt_min; a.dt_max = dt_max;
     a.vmax = sim->d_vmax; a.dt_out = sim->d_dt; a.dt_log = dt_log;
-    a.seed = sim->seed; a.step = (unsigned long long)sim->iterations;
+    a.seed = sim->seed; a.step_ptr = sim->d_stepctr;
     return a;
 }
 
@@ -467,6 +474,8 @@ int cdb_create(int device, int model, int64_t capacity, cdb_sim **out) {
         CKS(dev_alloc(&sim->d_vmax, 2));
         CKS(dev_alloc(&sim->d_dt, 2));
         CKS(dev_alloc(&sim->d_dt_log, DT_LOG));
+        CKS(dev_alloc(&sim->d_stepctr, 1));
+        CK(cudaMemset(sim->d_stepctr, 0, sizeof(unsigned long long)));
         CKS(dev_alloc(&sim->d_error, 1));
         CKS(dev_alloc(&sim->d_pair_count, 1));
         CKS(dev_alloc(&sim->d_counters, 4));
@@ -501,6 +510,8 @@ int cdb_destroy(cdb_sim *sim) {
     for (auto &f : sim->nav) { cudaFree((void *)f.U); cudaFree((void *)f.V); }
     cudaFree(sim->d_nav); cudaFree(sim->d_vmax); cudaFree(sim->d_dt); cudaFree(sim->d_dt_log); cudaFreeHost(sim->h_dt);
     for (auto e : sim->ev_pool) cudaEventDestroy(e);
+    if (sim->graph_exec) cudaGraphExecDestroy(sim->graph_exec);
+    cudaFree(sim->d_stepctr);
     cudaFree(sim->d_error); cudaFreeHost(sim->h_error); cudaFree(sim->d_pair_count);
     cudaFree(sim->d_counters); cudaFreeHost(sim->h_counters); cudaFree(sim->d_counts); cudaFreeHost(sim->h_counts);
     if (sim->own_stream && sim->stream) cudaStreamDestroy(sim->stream);
@@ -510,6 +521,7 @@ int cdb_destroy(cdb_sim *sim) {
 
 int cdb_set_stream(cdb_sim *sim, void *cuda_stream) {
     if (!sim) return fail(CDB_ERR_INVALID_VALUE, "sim is NULL");
+    sim->state_version++;
     CK(cudaSetDevice(sim->device));
     CK(cudaStreamSynchronize(sim->stream));
     if (sim->own_stream) { cudaStreamDestroy(sim->stream); sim->own_stream = false; }
@@ -528,6 +540,7 @@ int64_t cdb_num_agents(const cdb_sim *sim) { return sim ? sim->n : -1; }
 
 int cdb_upload_agents_aos(cdb_sim *sim, const void *agents, int64_t n, int64_t itemsize) {
     if (!sim) return fail(CDB_ERR_INVALID_VALUE, "sim is NULL");
+    sim->state_version++;
     if (itemsize != sim->itemsize) return fail(CDB_ERR_INVALID_TYPE, "agent itemsize %lld does not match the model (%lld)", (long long)itemsize, (long long)sim->itemsize);
     if (n < 0 || (n > 0 && !agents)) return fail(CDB_ERR_INVALID_VALUE, "bad agents buffer");
     if (n > 2000000000LL) return fail(CDB_ERR_CAPACITY, "too many agents");
@@ -605,6 +618,7 @@ int cdb_download_agents_aos(cdb_sim *sim, void *agents, int64_t n, int64_t items
 
 int cdb_set_obstacles(cdb_sim *sim, const double *segments, int64_t n_segments) {
     if (!sim) return fail(CDB_ERR_INVALID_VALUE, "sim is NULL");
+    sim->state_version++;
     if (n_segments < 0 || (n_segments > 0 && !segments)) return fail(CDB_ERR_INVALID_VALUE, "bad obstacle buffer");
     CK(cudaSetDevice(sim->device));
     CK(cudaStreamSynchronize(sim->stream));
@@ -624,6 +638,7 @@ int cdb_set_obstacles(cdb_sim *sim, const double *segments, int64_t n_segments) 
 int cdb_set_navigation_field(cdb_sim *sim, int64_t target, const double *U, const double *V, int64_t ny, int64_t nx,
                              double minx, double miny, double step) {
     if (!sim) return fail(CDB_ERR_INVALID_VALUE, "sim is NULL");
+    sim->state_version++;
     if (target < 0 || target >= MAX_NAV_TARGETS) return fail(CDB_ERR_INVALID_VALUE, "target index %lld out of range [0, %d)", (long long)target, MAX_NAV_TARGETS);
     if (ny < 0 || nx < 0 || ((ny * nx) > 0 && (!U || !V))) return fail(CDB_ERR_INVALID_VALUE, "bad navigation field");
     CK(cudaSetDevice(sim->device));
@@ -647,6 +662,7 @@ int cdb_set_navigation_field(cdb_sim *sim, int64_t target, const double *U, cons
 
 int cdb_clear_navigation(cdb_sim *sim) {
     if (!sim) return fail(CDB_ERR_INVALID_VALUE, "sim is NULL");
+    sim->state_version++;
     CK(cudaSetDevice(sim->device));
     CK(cudaStreamSynchronize(sim->stream));
     for (auto &f : sim->nav) { cudaFree((void *)f.U); cudaFree((void *)f.V); }
@@ -660,7 +676,7 @@ int cdb_clear_navigation(cdb_sim *sim) {
     CK(cudaSetDevice(sim->device))
 
 int cdb_reset(cdb_sim *sim) { SIM_ENTRY(); return node_reset(sim); }
-int cdb_set_seed(cdb_sim *sim, uint64_t seed) { SIM_ENTRY(); sim->seed = seed; sim->fluct_calls = 0; return CDB_OK; }
+int cdb_set_seed(cdb_sim *sim, uint64_t seed) { SIM_ENTRY(); sim->seed = seed; sim->fluct_calls = 0; sim->state_version++; return CDB_OK; }
 int cdb_fluctuation(cdb_sim *sim) {
     SIM_ENTRY();
     // key the stream on a private call counter in the high half, so that node-wise calls never reuse a fused step's stream
@@ -686,50 +702,119 @@ int cdb_integrate(cdb_sim *sim, double dt_min, double dt_max, double *dt_out) {
     return CDB_OK;
 }
 
+// launches of ONE step of the selected nodes (no host synchronisation unless the search lattice has to be re-derived)
+static int issue_step(cdb_sim *sim, uint32_t flags, double cell_size, double dt_min, double dt_max, bool log_dt) {
+    double *log = log_dt && (flags & CDB_STEP_INTEGRATOR) ? sim->d_dt_log : nullptr;
+    CKS(prof_mark(sim));
+    if (sim->variant == 1) {
+        // node-by-node path with the one-phase kernels (kept as an independent cross-check of the fused kernel)
+        if ((flags & CDB_STEP_FLUCTUATION) && sim->n)
+            LAUNCH(sim, k_fluctuation, cdiv(sim->n, 256), 256, 0, sim->cur, (int)sim->n, sim->model, sim->seed, (unsigned long long)sim->iterations);
+        if (flags & CDB_STEP_NAVIGATION) CKS(node_navigation(sim));
+        if (flags & CDB_STEP_ORIENTATION) CKS(node_orientation(sim));
+        if (flags & CDB_STEP_ADJUSTING) CKS(node_adjust(sim));
+        if (flags & CDB_STEP_AGENT_AGENT) CKS(build_block_list(sim, cell_size));
+        CKS(prof_mark(sim));
+        if (flags & CDB_STEP_AGENT_AGENT) CKS(launch_agent_agent(sim));
+        CKS(prof_mark(sim));
+        if (flags & CDB_STEP_AGENT_OBSTACLE) CKS(node_agent_obstacle(sim));
+        if (flags & CDB_STEP_INTEGRATOR) {
+            CKS(node_integrate(sim, dt_min, dt_max));
+            if (log) CK(cudaMemcpyAsync(log + (sim->iterations % DT_LOG), sim->d_dt, sizeof(double), cudaMemcpyDeviceToDevice, sim->stream));
+        }
+        if (flags & CDB_STEP_RESET) CKS(node_reset(sim));
+    } else {
+        const bool need_vmax = flags & CDB_STEP_INTEGRATOR;
+        if (need_vmax) LAUNCH(sim, k_vmax_init, 1, 32, 0, sim->d_vmax);
+        if (flags & CDB_STEP_AGENT_AGENT) CKS(build_block_list(sim, cell_size, true, need_vmax ? sim->d_vmax : nullptr, false));
+        else if (need_vmax && sim->n > 0) LAUNCH(sim, k_vmax, (cdiv(sim->n, 1024) < 1184 ? cdiv(sim->n, 1024) : 1184), 256, 0, sim->cur, (int)sim->n, sim->d_vmax);
+        CKS(prof_mark(sim));
+        CKS(launch_step_kernel(sim, flags, dt_min, dt_max, log));
+        CKS(prof_mark(sim));
+    }
+    LAUNCH(sim, k_step_advance, 1, 32, 0, sim->d_stepctr);
+    CKS(prof_mark(sim));
+    sim->iterations++;
+    return CDB_OK;
+}
+
+// Two consecutive fused steps as one CUDA graph: after two steps the ping-pong buffers and the swapped index arrays are
+// back in their roles, so the same executable graph replays for every following pair as long as nothing it captured by
+// value changes (agent count, lattice shape, flags, parameters, buffers -- sim->graph_key).
+static bool graph_usable(cdb_sim *sim, uint32_t flags, double cell_size) {
+    if (!sim->use_graphs || sim->variant == 1 || sim->profiling || sim->strip || sim->n <= 0) return false;
+    if (!(flags & CDB_STEP_AGENT_AGENT) || !(flags & CDB_STEP_INTEGRATOR)) return false;
+    if (sim->lattice_fixed) return sim->cell_capacity >= sim->grid.ncell;
+    return sim->auto_lattice_valid && sim->cell_size_lattice == cell_size && sim->auto_lattice_age + 2 <= 64 &&
+           sim->cell_capacity >= sim->grid.ncell;
+}
+
+static int run_graph_pair(cdb_sim *sim, uint32_t flags, double cell_size, double dt_min, double dt_max, bool log_dt) {
+    const cdb_sim::GraphKey key{flags, cell_size, dt_min, dt_max, log_dt, sim->n, sim->grid.ncell, sim->grid.nx, sim->grid.ny,
+                                sim->state_version, sim->cur.p};
+    const cdb_sim::GraphKey &k0 = sim->graph_key;
+    const bool same = sim->graph_exec && k0.flags == key.flags && k0.cell_size == key.cell_size && k0.dt_min == key.dt_min &&
+                      k0.dt_max == key.dt_max && k0.log == key.log && k0.n == key.n && k0.ncell == key.ncell && k0.nx == key.nx &&
+                      k0.ny == key.ny && k0.version == key.version && k0.cur == key.cur;
+    if (same) {
+        CK(cudaGraphLaunch(sim->graph_exec, sim->stream));
+        sim->launches += sim->graph_launches;
+        sim->iterations += 2;
+        if (!sim->lattice_fixed) sim->auto_lattice_age += 2;
+        return CDB_OK;
+    }
+    if (sim->graph_exec) { cudaGraphExecDestroy(sim->graph_exec); sim->graph_exec = nullptr; }
+    const int64_t launches0 = sim->launches;
+    cudaGraph_t graph = nullptr;
+    CK(cudaStreamBeginCapture(sim->stream, cudaStreamCaptureModeThreadLocal));
+    int rc = issue_step(sim, flags, cell_size, dt_min, dt_max, log_dt);
+    if (rc == CDB_OK) rc = issue_step(sim, flags, cell_size, dt_min, dt_max, log_dt);
+    cudaError_t e = cudaStreamEndCapture(sim->stream, &graph);
+    if (rc != CDB_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (e != cudaSuccess) return fail(CDB_ERR_CUDA, "stream capture failed: %s", cudaGetErrorString(e));
+    sim->graph_launches = sim->launches - launches0;
+    e = cudaGraphInstantiate(&sim->graph_exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) { sim->graph_exec = nullptr; return fail(CDB_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e)); }
+    sim->graph_key = key;
+    // the capture issued the two steps on the host side (counters, buffer roles); run them
+    CK(cudaGraphLaunch(sim->graph_exec, sim->stream));
+    return CDB_OK;
+}
+
 int cdb_step(cdb_sim *sim, uint32_t flags, double cell_size, double dt_min, double dt_max, int64_t n_steps, double *dt_out) {
     SIM_ENTRY();
     if (n_steps < 0) return fail(CDB_ERR_INVALID_VALUE, "negative n_steps");
-    for (int64_t k = 0; k < n_steps; ++k) {
-        const bool prof = sim->profiling && sim->ev_used + 4 <= (size_t)PROFILE_MAX_STEPS * 4;
-        const bool prof_saved = sim->profiling;
-        sim->profiling = prof;
-        CKS(prof_mark(sim));
-        double *log_slot = (dt_out && (flags & CDB_STEP_INTEGRATOR)) ? sim->d_dt_log + (k % DT_LOG) : nullptr;
-        if (sim->variant == 1) {
-            // node-by-node path with the one-phase kernels (kept as an independent cross-check of the fused kernel)
-            if ((flags & CDB_STEP_FLUCTUATION) && sim->n)
-                LAUNCH(sim, k_fluctuation, cdiv(sim->n, 256), 256, 0, sim->cur, (int)sim->n, sim->model, sim->seed, (unsigned long long)sim->iterations);
-            if (flags & CDB_STEP_NAVIGATION) CKS(node_navigation(sim));
-            if (flags & CDB_STEP_ORIENTATION) CKS(node_orientation(sim));
-            if (flags & CDB_STEP_ADJUSTING) CKS(node_adjust(sim));
-            if (flags & CDB_STEP_AGENT_AGENT) CKS(build_block_list(sim, cell_size));
-            CKS(prof_mark(sim));
-            if (flags & CDB_STEP_AGENT_AGENT) CKS(launch_agent_agent(sim));
-            CKS(prof_mark(sim));
-            if (flags & CDB_STEP_AGENT_OBSTACLE) CKS(node_agent_obstacle(sim));
-            if (flags & CDB_STEP_INTEGRATOR) {
-                CKS(node_integrate(sim, dt_min, dt_max));
-                if (log_slot) CK(cudaMemcpyAsync(log_slot, sim->d_dt, sizeof(double), cudaMemcpyDeviceToDevice, sim->stream));
-            }
-            if (flags & CDB_STEP_RESET) CKS(node_reset(sim));
+    const bool log_dt = dt_out && (flags & CDB_STEP_INTEGRATOR);
+    int64_t k = 0, copied = 0;      // steps done / dt values already returned
+    const bool prof_saved = sim->profiling;
+    while (k < n_steps) {
+        sim->profiling = prof_saved && sim->ev_used + 4 <= (size_t)PROFILE_MAX_STEPS * 4;
+        // a pair must not straddle the end of the dt ring (its first half would be overwritten before it is read back)
+        const bool ring_ok = !log_dt || (sim->iterations % DT_LOG) != DT_LOG - 1;
+        if (n_steps - k >= 2 && ring_ok && graph_usable(sim, flags, cell_size)) {
+            CKS(run_graph_pair(sim, flags, cell_size, dt_min, dt_max, log_dt));
+            k += 2;
         } else {
-            const bool need_vmax = flags & CDB_STEP_INTEGRATOR;
-            if (need_vmax) LAUNCH(sim, k_vmax_init, 1, 32, 0, sim->d_vmax);
-            if (flags & CDB_STEP_AGENT_AGENT) CKS(build_block_list(sim, cell_size, true, need_vmax ? sim->d_vmax : nullptr, false));
-            else if (need_vmax && sim->n > 0) LAUNCH(sim, k_vmax, (cdiv(sim->n, 1024) < 1184 ? cdiv(sim->n, 1024) : 1184), 256, 0, sim->cur, (int)sim->n, sim->d_vmax);
-            CKS(prof_mark(sim));
-            CKS(launch_step_kernel(sim, flags, dt_min, dt_max, log_slot));
-            CKS(prof_mark(sim));
+            CKS(issue_step(sim, flags, cell_size, dt_min, dt_max, log_dt));
+            k += 1;
         }
-        CKS(prof_mark(sim));
         sim->profiling = prof_saved;
-        sim->iterations++;
-        if (dt_out && (flags & CDB_STEP_INTEGRATOR) && ((k + 1) % DT_LOG == 0 || k + 1 == n_steps)) {
-            const int64_t first = k / DT_LOG * DT_LOG, cnt = k + 1 - first;
-            CK(cudaMemcpyAsync(dt_out + first, sim->d_dt_log, cnt * sizeof(double), cudaMemcpyDeviceToHost, sim->stream));
+        if (log_dt && (sim->iterations % DT_LOG == 0 || k == n_steps)) {
+            // slots of the steps not yet returned: they end at slot (iterations - 1) % DT_LOG and do not wrap
+            const int64_t cnt = k - copied;
+            const int64_t first_slot = (sim->iterations - cnt) % DT_LOG;
+            CK(cudaMemcpyAsync(dt_out + copied, sim->d_dt_log + first_slot, cnt * sizeof(double), cudaMemcpyDeviceToHost, sim->stream));
             CK(cudaStreamSynchronize(sim->stream));
+            copied = k;
         }
     }
+    return CDB_OK;
+}
+
+int cdb_set_graphs(cdb_sim *sim, int enable) {
+    SIM_ENTRY();
+    sim->use_graphs = enable != 0;
     return CDB_OK;
 }
 
@@ -737,6 +822,7 @@ int cdb_set_variant(cdb_sim *sim, int variant) {
     SIM_ENTRY();
     if (variant != 1 && variant != 2) return fail(CDB_ERR_INVALID_VALUE, "unknown kernel variant %d", variant);
     sim->variant = variant;
+    sim->state_version++;
     return CDB_OK;
 }
 
@@ -848,13 +934,16 @@ int cdb_set_lattice(cdb_sim *sim, int64_t ix_min, int64_t iy_min, int64_t nx, in
     sim->grid = Grid{ix_min, iy_min, nx, ny, nx * ny, 0, nx - 1};
     sim->lattice_fixed = true;
     sim->tables_valid = false;
+    sim->state_version++;
     CK(cudaMemcpy(sim->d_grid, &sim->grid, sizeof(Grid), cudaMemcpyHostToDevice));
+    CKS(ensure_cells(sim, sim->grid.ncell));
     return CDB_OK;
 }
 int cdb_clear_lattice(cdb_sim *sim) {
     SIM_ENTRY();
     sim->lattice_fixed = false;
     sim->tables_valid = false;
+    sim->state_version++;
     return CDB_OK;
 }
 
@@ -954,6 +1043,7 @@ int cdb_strip_finish(cdb_sim *sim, uint32_t flags, double dt_min, double dt_max,
     CKS(launch_step_kernel(sim, flags, dt_min, dt_max, nullptr));
     CKS(prof_mark(sim));
     sim->iterations++;
+    LAUNCH(sim, k_step_advance, 1, 32, 0, sim->d_stepctr);
     LAUNCH(sim, k_counters_zero, 1, 32, 0, sim->d_counters, 4);
     if (sim->n > 0)
         LAUNCH(sim, k_migrants_pack, cdiv(sim->n, 256), 256, 0, sim->cur, (int)sim->n, sim->dev_counts ? &sim->d_counts->slots : nullptr, sim->n_planes, sim->cell_size, sim->grid.ix_min,

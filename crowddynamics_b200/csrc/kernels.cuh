@@ -668,6 +668,9 @@ __global__ void k_export_pairs(const int *__restrict__ id, const int *__restrict
 // =====================================================================================================================
 // per-agent nodes
 // =====================================================================================================================
+// the device-side step index (Philox key of the Fluctuation node, slot of the dt log); one thread, after every step
+__global__ void k_step_advance(unsigned long long *step) { if (threadIdx.x == 0) ++*step; }
+
 __global__ void k_reset(Soa s, int n, int model) {   // logic.py:59-64
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;

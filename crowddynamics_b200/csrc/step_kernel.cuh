@@ -24,6 +24,7 @@
 #include "kernels.cuh"
 
 constexpr int STEP_THREADS = 128;
+constexpr int DT_LOG_SLOTS = 1024;
 constexpr int STEP_WARPS = STEP_THREADS / 32;
 constexpr int LCAP = 16;     // survivor list entries per lane between two flushes
 #ifndef STEP_CHUNK
@@ -55,8 +56,9 @@ struct StepArgs {
     double dt_min, dt_max;
     const unsigned long long *vmax;
     double *dt_out;          // [0] dt, [1] time_tot
-    double *dt_log;          // where to log this step's dt (or nullptr)
-    unsigned long long seed, step;   // Fluctuation: Philox key
+    double *dt_log;          // ring of DT_LOG_SLOTS entries: this step's dt goes to slot step % DT_LOG_SLOTS (or nullptr)
+    unsigned long long seed; // Fluctuation: Philox key (with the step index)
+    const unsigned long long *step_ptr;   // device-side step index (advanced by k_step_advance after every step)
 };
 
 struct WarpSmem {
@@ -198,7 +200,7 @@ __global__ void __launch_bounds__(STEP_THREADS, MODEL == 0 ? STEP_MINB_CIRC : ST
     double fx = s(FX, oo), fy = s(FY, oo), tq = 0.0, phi0 = 0.0;
     if (MODEL == 1) { tq = s(TORQUE, oo); phi0 = s(PHI0, oo); }
     if (A.flags & CDB_STEP_FLUCTUATION)      // logic.py:78-86, first in the reference's post-order
-        fluctuation(A.seed, A.step, s.id[oo], s(MASS, oo), s(STD_RAND_FORCE, oo), MODEL == 1 ? s(INERTIA, oo) : 0.0,
+        fluctuation(A.seed, *A.step_ptr, s.id[oo], s(MASS, oo), s(STD_RAND_FORCE, oo), MODEL == 1 ? s(INERTIA, oo) : 0.0,
                     MODEL == 1 ? s(STD_RAND_TORQUE, oo) : 0.0, MODEL == 1, fx, fy, tq);
     {
         const double px = s(PX, oo), py = s(PY, oo);
@@ -378,7 +380,7 @@ __global__ void __launch_bounds__(STEP_THREADS, MODEL == 0 ? STEP_MINB_CIRC : ST
     const double dt = adaptive_timestep(A.vmax, A.dt_min, A.dt_max);
     if (t == 0) {
         A.dt_out[0] = dt; A.dt_out[1] += dt;
-        if (A.dt_log) *A.dt_log = dt;
+        if (A.dt_log) A.dt_log[*A.step_ptr % DT_LOG_SLOTS] = dt;
     }
     double nvx = vx, nvy = vy, npx = px, npy = py;
     verlet(fx, s(FPX, oo), mass, dt, nvx, npx);

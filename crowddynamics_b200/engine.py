@@ -132,6 +132,9 @@ class DeviceAgents:
                                      int(n_steps), _ptr(dts) if want_dt and n_steps else None))
         return dts
 
+    def set_graphs(self, enable):
+        _lib.check(self.lib.cdb_set_graphs(self.handle, 1 if enable else 0))
+
     def time(self):
         t, it = C.c_double(), C.c_int64()
         _lib.check(self.lib.cdb_get_time(self.handle, C.byref(t), C.byref(it)))

@@ -122,6 +122,9 @@ int cdb_integrate(cdb_sim *sim, double dt_min, double dt_max, double *dt_out);  
 int cdb_step(cdb_sim *sim, uint32_t node_flags, double cell_size, double dt_min, double dt_max, int64_t n_steps,
              double *dt_out);
 int cdb_get_time(cdb_sim *sim, double *time_tot, int64_t *iterations);
+/* cdb_step replays pairs of steps as one CUDA graph when nothing it captured changes (default on; not while profiling and
+ * not in strip mode).  Results are identical either way; this only removes launch latency for small crowds. */
+int cdb_set_graphs(cdb_sim *sim, int enable);
 
 /* ---- instrumentation (no reference counterpart) -------------------------------------------------------------------- */
 /* agent-agent kernel variant: 2 (default) = two-phase fused step kernel, 1 = one-phase kernels, kept as a cross-check */

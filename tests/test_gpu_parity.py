@@ -301,3 +301,29 @@ def test_fused_kernel_matches_one_phase_kernel(model, density):
     O.navigation(ref, [S.direction_field(0.5, (0, 0, side, side), 'swirl')]); O.orientation(ref); O.adjusting(ref)
     O.agent_agent_block_list(ref, CELL); O.agent_obstacle(ref, obs)
     _assert_forces(out[2][0], ref, model)
+
+
+# ---- CUDA-graph replay of step pairs is only a launch optimisation ------------------------------------------------------------
+@pytest.mark.parametrize('model', ['circular', 'three_circle'])
+def test_graph_replay_is_bit_identical_to_plain_launches(model):
+    agents, obstacles, side = S.uniform_crowd(5000, model, density=1.0, seed=8, overlap_fraction=0.02)
+    agents['std_rand_force'] = 0.2
+    fields = [S.direction_field(0.5, (0, 0, side, side), 'swirl')]
+    out = {}
+    for graphs in (True, False):
+        dev = DeviceAgents(MODEL_CIRCULAR if model == 'circular' else MODEL_THREE_CIRCLE)
+        dev.set_graphs(graphs)
+        dev.upload(agents)
+        dev.set_obstacles(obstacles)
+        dev.set_navigation_field(0, *fields[0])
+        dts = [dev.step(n, _lib.STEP_ALL | _lib.STEP_FLUCTUATION, CELL, 0.001, 0.01) for n in (1, 7, 2, 131, 1030)]   # odd / even, > lattice window, > dt ring
+        launches = dev.launch_count()
+        a = agents.copy()
+        dev.download(a)
+        t, it = dev.time()
+        dev.close()
+        out[graphs] = (np.concatenate(dts), a, t, it, launches)
+    assert out[True][3] == out[False][3] == 1171
+    assert (out[True][0] == out[False][0]).all() and out[True][2] == out[False][2]
+    assert rel_err_fields(out[True][1], out[False][1])[0] == 0
+    assert out[True][4] == out[False][4]                # same kernels launched, just batched
