@@ -743,6 +743,8 @@ static int issue_step(cdb_sim *sim, uint32_t flags, double cell_size, double dt_
 // value changes (agent count, lattice shape, flags, parameters, buffers -- sim->graph_key).
 static bool graph_usable(cdb_sim *sim, uint32_t flags, double cell_size) {
     if (!sim->use_graphs || sim->variant == 1 || sim->profiling || sim->strip || sim->n <= 0) return false;
+    // the legacy / per-thread default streams cannot be captured (e.g. torch's default current stream)
+    if (sim->stream == nullptr || sim->stream == cudaStreamLegacy || sim->stream == cudaStreamPerThread) return false;
     if (!(flags & CDB_STEP_AGENT_AGENT) || !(flags & CDB_STEP_INTEGRATOR)) return false;
     if (sim->lattice_fixed) return sim->cell_capacity >= sim->grid.ncell;
     return sim->auto_lattice_valid && sim->cell_size_lattice == cell_size && sim->auto_lattice_age + 2 <= 64 &&
@@ -766,7 +768,13 @@ static int run_graph_pair(cdb_sim *sim, uint32_t flags, double cell_size, double
     if (sim->graph_exec) { cudaGraphExecDestroy(sim->graph_exec); sim->graph_exec = nullptr; }
     const int64_t launches0 = sim->launches;
     cudaGraph_t graph = nullptr;
-    CK(cudaStreamBeginCapture(sim->stream, cudaStreamCaptureModeThreadLocal));
+    if (cudaStreamBeginCapture(sim->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+        // this stream cannot be captured: keep working with plain launches
+        cudaGetLastError();
+        sim->use_graphs = false;
+        CKS(issue_step(sim, flags, cell_size, dt_min, dt_max, log_dt));
+        return issue_step(sim, flags, cell_size, dt_min, dt_max, log_dt);
+    }
     int rc = issue_step(sim, flags, cell_size, dt_min, dt_max, log_dt);
     if (rc == CDB_OK) rc = issue_step(sim, flags, cell_size, dt_min, dt_max, log_dt);
     cudaError_t e = cudaStreamEndCapture(sim->stream, &graph);

@@ -327,3 +327,20 @@ def test_graph_replay_is_bit_identical_to_plain_launches(model):
     assert (out[True][0] == out[False][0]).all() and out[True][2] == out[False][2]
     assert rel_err_fields(out[True][1], out[False][1])[0] == 0
     assert out[True][4] == out[False][4]                # same kernels launched, just batched
+
+
+def test_legacy_default_stream_is_not_captured():
+    """bench.py runs the sim on torch's current stream, which is the legacy default stream: it cannot be captured into a CUDA
+    graph, so cdb_step must fall back to plain launches there (and give the same result)."""
+    import torch
+    agents, obstacles, side = S.uniform_crowd(3000, 'circular', density=1.0, seed=9)
+    out = []
+    for use_default in (True, False):
+        dev = DeviceAgents(MODEL_CIRCULAR)
+        if use_default:
+            dev.set_stream(torch.cuda.current_stream().cuda_stream)
+        dev.upload(agents); dev.set_obstacles(obstacles)
+        dts = dev.step(9, _lib.STEP_ALL & ~_lib.STEP_NAVIGATION, CELL, 0.001, 0.01)
+        a = agents.copy(); dev.download(a); dev.close()
+        out.append((dts, a))
+    assert (out[0][0] == out[1][0]).all() and rel_err_fields(out[0][1], out[1][1])[0] == 0
