@@ -13,6 +13,11 @@ GOLDEN = os.path.join(ROOT, 'tests', 'golden')
 
 def pytest_configure(config):
     config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box with -m gpu)')
+    # a fresh checkout has no built artefacts (*.so is git-ignored): build them once (nvcc cross-compiles without a GPU)
+    from crowddynamics_b200 import _lib
+    if not os.path.exists(_lib.LIB_PATH):
+        import __graft_entry__
+        __graft_entry__.build()
 
 
 def _have_gpu():
