@@ -142,3 +142,28 @@ def test_thousand_steps_stay_finite_and_inside_the_room():
     assert np.isfinite(out['position']).all() and np.isfinite(out['velocity']).all()
     assert (out['position'] > -0.5).all() and (out['position'] < side + 0.5).all()      # walls hold the crowd
     assert (out['force'] == 0).all()
+
+
+def test_million_three_circle_agents_500_steps_with_fluctuation():
+    """Config 3 flavour as a soak: 1 M three-circle agents, adaptive dt, stochastic node on, 500 fused steps (graph replay
+    on the sim's own stream): state stays finite and inside the walls, time bookkeeping adds up, agents keep their identity."""
+    agents, obstacles, side = S.uniform_crowd(N, 'three_circle', density=1.0, seed=9)
+    agents['std_rand_force'] = 0.1
+    agents['std_rand_torque'] = 0.1
+    dev = DeviceAgents(MODEL_THREE_CIRCLE)
+    dev.upload(agents)
+    dev.set_obstacles(obstacles)
+    dev.set_navigation_field(0, *S.direction_field(2.0, (0, 0, side, side), 'exit', point=(side, side / 2)))
+    dts = dev.step(500, _lib.STEP_ALL | _lib.STEP_FLUCTUATION, CELL, 0.001, 0.01)
+    out = agents.copy()
+    dev.download(out)
+    t, it = dev.time()
+    dev.close()
+    assert it == 500 and abs(t - dts.sum()) < 1e-9 and ((dts >= 0.001) & (dts <= 0.01)).all()
+    for f in ('position', 'velocity', 'orientation', 'angular_velocity', 'position_ls', 'position_rs'):
+        assert np.isfinite(out[f]).all(), f
+    assert (out['position'] > -0.5).all() and (out['position'] < side + 0.5).all()
+    assert (np.abs(out['orientation']) <= np.pi).all()
+    assert (out['mass'] == agents['mass']).all() and (out['radius'] == agents['radius']).all()     # records kept their rows
+    moved = np.hypot(*(out['position'] - agents['position']).T)
+    assert 0.5 < moved.mean() < 6.0                     # ~ 4 s of walking at ~ 1 m/s against a crowd
