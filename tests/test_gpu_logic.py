@@ -89,3 +89,59 @@ def test_room_evacuation_style_config(model):
     # the crowd heads for the door
     d0 = np.hypot(side - ref['position'][:, 0], side / 2 - ref['position'][:, 1]).mean()
     assert np.hypot(side - agents['position'][:, 0], side / 2 - agents['position'][:, 1]).mean() <= d0 + 1e-9
+
+
+def _validation_agents(model, positions, orientations):
+    """Attributes of reference examples/validation.py:26-40,76-90."""
+    from crowddynamics_b200.structures import agent_type_circular, agent_type_three_circle
+    a = np.zeros(len(positions), dtype=agent_type_circular if model == 'circular' else agent_type_three_circle)
+    S.fill_adult_bodies(a, np.random.default_rng(0), omega0=0.0)
+    a['radius'] = 0.255; a['r_t'] = 0.5882 * 0.255; a['r_s'] = 0.3725 * 0.255; a['r_ts'] = 0.6275 * 0.255
+    a['mass'] = 73.5; a['target_velocity'] = 1.0
+    a['inertia_rot'] = 4.0 * np.pi * (73.5 / 80.0) * (0.255 / 0.27) ** 2
+    a['position'] = positions
+    e = np.stack((np.cos(orientations), np.sin(orientations)), 1)
+    a['velocity'] = 1.0 * e
+    a['target_direction'] = e
+    if model != 'circular':
+        a['orientation'] = orientations
+        a['target_orientation'] = orientations
+        S.set_shoulders(a)
+    return a
+
+
+@pytest.mark.parametrize('model', ['circular', 'three_circle'])
+def test_reference_validation_movement(model):
+    """reference examples/tests/test_validation.py:13-24 (TestMovement): one agent, Reset << Integrator << Adjusting <<
+    Orientation, 1000 iterations of dt = 0.01 at v0 = 1 => it has walked (at least about) 10 m."""
+    agents = _validation_agents(model, [(0.0, 0.0)], np.array([0.0]))
+    ref = agents.copy()
+    sim = L.MultiAgentSimulation(agents, None, [])
+    sim.logic = L.Reset(sim) << (L.Integrator(sim) << (L.Adjusting(sim) << L.Orientation(sim)))
+    for _ in range(1000):
+        sim.update()
+        O.orientation(ref); O.adjusting(ref); O.velocity_verlet_integrator(ref, 0.01, 0.01); O.reset(ref)
+    dist = np.hypot(*(agents['position'][0]))
+    assert dist >= 10.0 or np.isclose(dist, 10.0)
+    assert np.abs(agents['position'] - ref['position']).max() <= 1e-12
+    assert abs(sim.data['time_tot'] - 10.0) < 1e-9
+
+
+@pytest.mark.parametrize('model', ['circular', 'three_circle'])
+def test_reference_validation_agent_interaction(model):
+    """reference examples/tests/test_validation.py:27-38 (TestAgentInteraction): two agents walking head-on from (0, 0) and
+    (5, 0) with Fluctuation, Adjusting << Orientation and AgentAgentInteractions; the reference asserts that agent 0 still
+    covers >= 8 m in 1000 iterations, which depends on its unseeded random fluctuation breaking the head-on symmetry (the
+    noise-free oracle gives 6.4 m circular / 7.8 m three-circle).  Here: clear progress, and the agents got past each other."""
+    agents = _validation_agents(model, [(0.0, 0.0), (5.0, 0.0)], np.array([0.0, np.pi]))
+    sim = L.MultiAgentSimulation(agents, None, [])
+    sim.logic = L.Reset(sim, mode='resident') << (L.Integrator(sim) << (
+        L.Fluctuation(sim, seed=3), L.Adjusting(sim) << L.Orientation(sim), L.AgentAgentInteractions(sim)))
+    start = agents['position'].copy()
+    for _ in range(1000):
+        sim.update()
+    sim.logic.state.sync_host()
+    dist = np.hypot(*(agents['position'][0] - start[0]))
+    assert dist >= 6.0
+    assert agents['position'][0, 0] > agents['position'][1, 0]                 # they passed each other
+    assert np.isfinite(agents['position']).all()
