@@ -235,3 +235,37 @@ def room_with_exit(n, model='circular', density=1.0, seed=0, door_width=1.2, hal
     if model != 'circular':
         agents['target_orientation'] = np.arctan2(e[:, 1], e[:, 0])
     return agents, obstacles, fields, side
+
+
+def leader_follower_crowd(n, model='circular', density=0.5, seed=0, n_leaders=None, n_doors=2, inner_walls=6):
+    """Stand-in for the crowds of the reference's examples/collective_motion.py: a walled square room with two door gaps
+    (left / right wall) and a few free-standing inner walls that block lines of sight; a small group of leaders
+    (``is_leader``, target = one of the exits) among herding followers (``is_follower``, no target, a random familiar
+    exit, a quarter of them already following some leader).  Returns (agents, obstacles, center_door, side)."""
+    agents, _, side = uniform_crowd(n, model, density=density, seed=seed)
+    rng = np.random.default_rng(seed + 1000)
+    n_leaders = max(1, n // 100) if n_leaders is None else n_leaders
+    leaders = rng.choice(n, size=min(n_leaders, n), replace=False)
+    agents['is_follower'] = True
+    agents['is_leader'][leaders] = True
+    agents['is_follower'][leaders] = False
+    agents['target'] = -1
+    agents['target'][leaders] = rng.integers(0, n_doors, size=len(leaders))
+    agents['familiar_exit'] = rng.integers(0, n_doors, size=n)
+    agents['index_leader'] = -1
+    followers = np.flatnonzero(agents['is_follower'])
+    if len(followers):
+        some = rng.choice(followers, size=len(followers) // 4, replace=False)
+        agents['index_leader'][some] = rng.choice(leaders, size=len(some))
+    door = 1.5
+    y_lo, y_hi = side / 2 - door / 2, side / 2 + door / 2
+    segs = [((0.0, 0.0), (side, 0.0)), ((0.0, side), (side, side)),
+            ((0.0, 0.0), (0.0, y_lo)), ((0.0, y_hi), (0.0, side)), ((side, 0.0), (side, y_lo)), ((side, y_hi), (side, side))]
+    for _ in range(inner_walls):
+        p0 = rng.uniform(0.1 * side, 0.9 * side, 2)
+        segs.append((tuple(p0), tuple(p0 + rng.uniform(-0.2 * side, 0.2 * side, 2))))
+    obstacles = np.zeros(len(segs), dtype=obstacle_type_linear)
+    for k, (p0, p1) in enumerate(segs):
+        obstacles[k]['p0'], obstacles[k]['p1'] = p0, p1
+    center_door = np.array([(0.0, side / 2), (side, side / 2)] + [tuple(rng.uniform(0, side, 2)) for _ in range(n_doors - 2)])
+    return agents, obstacles, center_door[:n_doors], side

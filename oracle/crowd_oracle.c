@@ -574,3 +574,249 @@ int oracle_step(void *agents, int64_t n, int64_t itemsize, const void *obstacles
     if ((rc = oracle_velocity_verlet_integrator(agents, n, itemsize, dt_min, dt_max, dt_out))) return rc;
     return oracle_reset(agents, n, itemsize);
 }
+
+/* =====================================================================================================================
+ * exit detection, herding, leader-follower (core/evacuation.py:137-174,
+ * core/sensory_region.py:9-16, core/geom2D.py:38-59, core/steering/collective_motion.py:16-289).
+ * ===================================================================================================================== */
+#define NO_TARGET (-1)          /* simulation/agents.py:28 */
+#define NO_LEADER (-1)          /* simulation/agents.py:29 */
+#define MISSING_NEIGHBOR (-1)   /* collective_motion.py:13 */
+
+int oracle_line_intersect(const double *x0, const double *x1, const double *y0, const double *y1) {   /* geom2D.py:38-59 */
+    const double u[2] = {x1[0] - x0[0], x1[1] - x0[1]}, v[2] = {y1[0] - y0[0], y1[1] - y0[1]};
+    const double b[2] = {y0[0] - x0[0], y0[1] - x0[1]};
+    const double d = u[0] * v[1] - u[1] * v[0];
+    if (d == 0) return 0;
+    const double t0 = b[0] * v[1] - b[1] * v[0], t1 = b[0] * u[1] - b[1] * u[0];
+    const double q0 = t0 / d, q1 = t1 / d;
+    return 0 <= q0 && q0 <= 1 && 0 <= q1 && q1 <= 1;
+}
+
+int oracle_is_obstacle_between_points(const double *p0, const double *p1, const void *obstacles, int64_t n_obs) {   /* sensory_region.py:9-16 */
+    const obstacle_linear_t *obs = obstacles;
+    for (int64_t w = 0; w < n_obs; ++w)
+        if (oracle_line_intersect(p0, p1, obs[w].p0, obs[w].p1)) return 1;
+    return 0;
+}
+
+/* evacuation.py:137-174: closest door centre in detection range with a free line of sight; -1 / 0 if none */
+int oracle_exit_detection(const double *center_door, int64_t n_doors, const void *agents, int64_t n, int64_t itemsize,
+                          const void *obstacles, int64_t n_obs, double detection_range, int64_t *detected_exit, uint8_t *has_detected) {
+    if (itemsize != 228 && itemsize != 316) return ORACLE_INVALID_TYPE;
+    for (int64_t i = 0; i < n; ++i) {
+        const double *p = circ((void *)agents, itemsize, i)->position;
+        double distance = detection_range;
+        detected_exit[i] = -1; has_detected[i] = 0;
+        for (int64_t c = 0; c < n_doors; ++c) {
+            if (oracle_is_obstacle_between_points(p, center_door + 2 * c, obstacles, n_obs)) continue;
+            const double r[2] = {center_door[2 * c] - p[0], center_door[2 * c + 1] - p[1]};
+            const double d = length2(r);
+            if (d < distance) { distance = d; detected_exit[i] = c; has_detected[i] = 1; }
+        }
+    }
+    return ORACLE_OK;
+}
+
+static inline void normalize2(const double *v, double *out) {   /* vector2D.py:152-163 */
+    const double l = length2(v);
+    if (l != 0) { out[0] = v[0] / l; out[1] = v[1] / l; } else { out[0] = v[0]; out[1] = v[1]; }
+}
+
+/* collective_motion.py:25-58; returns bit 0: agent 1 is heading away ..., bit 1: the second flag */
+int oracle_herding_relationship(const double *x1, const double *x2, const double *v1, const double *v2, double phi) {
+    if (length2(v1) == 0 || length2(v2) == 0) return 0;
+    const double rel[2] = {x2[0] - x1[0], x2[1] - x1[1]};
+    double e_rel[2], n1[2], n2[2];
+    normalize2(rel, e_rel); normalize2(v1, n1); normalize2(v2, n2);
+    const double c_i = dot2(e_rel, n1), c_j = -dot2(e_rel, n2);
+    const double cos_phi = cos(phi);
+    const int in_i = cos_phi < c_i && c_i < 1.0, in_j = cos_phi < c_j && c_j < 1.0;
+    if (in_i) return in_j ? 0 : 1;
+    return in_j ? 2 : 3;
+}
+
+typedef struct {
+    const void *agents; int64_t itemsize; const void *obstacles; int64_t n_obs;
+    int64_t k; int64_t *neighbors; double *distances, *distances_max;
+} knn_ctx_t;
+
+static void knn_set_neighbor(knn_ctx_t *c, int64_t i, int64_t j, double l) {   /* collective_motion.py:61-66 */
+    double *d = c->distances + i * c->k;
+    int64_t argmax = 0;
+    for (int64_t s = 1; s < c->k; ++s) if (d[s] > d[argmax]) argmax = s;      /* np.argmax: first maximum */
+    c->neighbors[i * c->k + argmax] = j;
+    d[argmax] = l;
+    double m = d[0];
+    for (int64_t s = 1; s < c->k; ++s) if (d[s] > m) m = d[s];
+    c->distances_max[i] = m;
+}
+
+static void knn_visit(int64_t i, int64_t j, void *ctx) {   /* collective_motion.py:94-108 */
+    knn_ctx_t *c = ctx;
+    const double *pi = circ((void *)c->agents, c->itemsize, i)->position, *pj = circ((void *)c->agents, c->itemsize, j)->position;
+    if (oracle_is_obstacle_between_points(pi, pj, c->obstacles, c->n_obs)) return;
+    const double r[2] = {pi[0] - pj[0], pi[1] - pj[1]};
+    const double l = length2(r);
+    if (l < c->distances_max[i]) knn_set_neighbor(c, i, j, l);
+    if (l < c->distances_max[j]) knn_set_neighbor(c, j, i, l);
+}
+
+/* collective_motion.py:69-110 with the block list of :262-267 (cell_size = sight); neighbors[n][k], -1 = missing */
+int oracle_find_nearest_neighbors(const void *agents, int64_t n, int64_t itemsize, double sight, int64_t k,
+                                  const void *obstacles, int64_t n_obs, int64_t *neighbors) {
+    if (itemsize != 228 && itemsize != 316) return ORACLE_INVALID_TYPE;
+    if (k < 1) return ORACLE_OK;
+    knn_ctx_t c = {agents, itemsize, obstacles, n_obs, k, neighbors, malloc(sizeof(double) * (n * k + 1)), malloc(sizeof(double) * (n + 1))};
+    for (int64_t q = 0; q < n * k; ++q) { neighbors[q] = MISSING_NEIGHBOR; c.distances[q] = sight; }
+    for (int64_t i = 0; i < n; ++i) c.distances_max[i] = sight;
+    oracle_cells_t cl;
+    int rc = oracle_add_to_cells(agents, n, itemsize, sight, &cl);
+    if (!rc) { for_each_pair(&cl, knn_visit, &c); oracle_free_cells(&cl); }
+    free(c.distances); free(c.distances_max);
+    return rc;
+}
+
+static inline void weighted_average2(const double *e0, const double *e1, double w, double *out) {   /* vector2D.py:203-226 */
+    out[0] = w * e0[0] + (1 - w) * e1[0]; out[1] = w * e0[1] + (1 - w) * e1[1];
+}
+
+/* collective_motion.py:113-154; new_direction[n][2], has_new_direction[n] */
+int oracle_herding_interaction(const void *agents, int64_t n, int64_t itemsize, const uint8_t *is_herding, const int64_t *neighbors,
+                               int64_t k, double weight_position, double phi, double *new_direction, uint8_t *has_new_direction) {
+    if (itemsize != 228 && itemsize != 316) return ORACLE_INVALID_TYPE;
+    for (int64_t i = 0; i < n; ++i) {
+        new_direction[2 * i] = new_direction[2 * i + 1] = 0; has_new_direction[i] = 0;
+        if (!is_herding[i]) continue;
+        const agent_circular_t *a = circ((void *)agents, itemsize, i);
+        double mean_position[2] = {0, 0}, mean_velocity[2] = {0, 0};
+        int64_t num = 0;
+        for (int64_t s = 0; s < k; ++s) {
+            const int64_t j = neighbors[i * k + s];
+            if (j == MISSING_NEIGHBOR) continue;
+            const agent_circular_t *b = circ((void *)agents, itemsize, j);
+            if (oracle_herding_relationship(a->position, b->position, a->velocity, b->velocity, phi) & 1) {
+                mean_position[0] += b->position[0]; mean_position[1] += b->position[1];
+                mean_velocity[0] += b->velocity[0]; mean_velocity[1] += b->velocity[1];
+                num++;
+            }
+        }
+        if (num > 0) {
+            const double rel[2] = {mean_position[0] / num - a->position[0], mean_position[1] / num - a->position[1]};
+            double e0[2], e1[2], w[2];
+            normalize2(rel, e0); normalize2(mean_velocity, e1);
+            weighted_average2(e0, e1, weight_position, w);
+            normalize2(w, new_direction + 2 * i);
+            has_new_direction[i] = 1;
+        }
+    }
+    return ORACLE_OK;
+}
+
+typedef struct { double d; int64_t k; } dist_idx_t;
+static int cmp_dist_idx(const void *a, const void *b) {
+    const dist_idx_t *x = a, *y = b;
+    if (x->d < y->d) return -1;
+    if (x->d > y->d) return 1;
+    return (x->k > y->k) - (x->k < y->k);   /* numba's argsort is not stable; ties (equal distances) are resolved by index here */
+}
+
+/* collective_motion.py:157-226; mutates target / index_leader of the followers in place, sequentially like the reference */
+int oracle_leader_follower_interaction_brute(void *agents, int64_t n, int64_t itemsize, double weight_position, double phi,
+                                             const void *obstacles, int64_t n_obs, double sight, double *new_direction, uint8_t *has_strategy) {
+    if (itemsize != 228 && itemsize != 316) return ORACLE_INVALID_TYPE;
+    int64_t n_lead = 0;
+    int64_t *leaders = malloc(sizeof(int64_t) * (n + 1));
+    for (int64_t i = 0; i < n; ++i) if (circ(agents, itemsize, i)->is_leader) leaders[n_lead++] = i;
+    dist_idx_t *dist = malloc(sizeof(dist_idx_t) * (n_lead + 1));
+    for (int64_t i = 0; i < n; ++i) { new_direction[2 * i] = new_direction[2 * i + 1] = 0; has_strategy[i] = 0; }
+    for (int64_t i = 0; i < n; ++i) {
+        agent_circular_t *a = circ(agents, itemsize, i);
+        if (!a->is_follower) continue;
+        int behind_obstacle = 0, heading_away = 0;
+        for (int64_t k = 0; k < n_lead; ++k) {
+            const agent_circular_t *b = circ(agents, itemsize, leaders[k]);
+            const double r[2] = {a->position[0] - b->position[0], a->position[1] - b->position[1]};
+            dist[k].d = length2(r); dist[k].k = k;
+        }
+        qsort(dist, n_lead, sizeof(dist_idx_t), cmp_dist_idx);
+        for (int64_t q = 0; q < n_lead; ++q) {
+            if (dist[q].d > sight) continue;
+            const int64_t j = leaders[dist[q].k];
+            const agent_circular_t *b = circ(agents, itemsize, j);
+            if (oracle_is_obstacle_between_points(a->position, b->position, obstacles, n_obs)) {
+                const int64_t leader = a->index_leader;
+                if (leader != NO_LEADER && leader == j) {
+                    behind_obstacle++;
+                    a->target = circ(agents, itemsize, leader)->target;
+                    has_strategy[i] = 1;
+                    break;
+                }
+                continue;
+            }
+            if (oracle_herding_relationship(a->position, b->position, a->velocity, b->velocity, phi) & 1) {
+                heading_away++;
+                a->index_leader = j;
+                a->target = NO_TARGET;
+                const double rel[2] = {b->position[0] - a->position[0], b->position[1] - a->position[1]};
+                double e0[2], e1[2], w[2];
+                normalize2(rel, e0); normalize2(b->velocity, e1);
+                weighted_average2(e0, e1, weight_position, w);
+                normalize2(w, new_direction + 2 * i);
+                has_strategy[i] = 1;
+                break;
+            }
+        }
+        if (behind_obstacle == 0 && heading_away == 0) {
+            const int64_t leader = a->index_leader;
+            if (leader != NO_LEADER) { a->target = circ(agents, itemsize, leader)->target; has_strategy[i] = 1; }
+        }
+    }
+    free(dist); free(leaders);
+    return ORACLE_OK;
+}
+
+/* collective_motion.py:229-243; direction[n][2] */
+int oracle_leader_follower_interaction(void *agents, int64_t n, int64_t itemsize, const void *obstacles, int64_t n_obs,
+                                       double sight, double phi, double weight_position_leader, double *direction) {
+    uint8_t *has_strategy = malloc(n + 1);
+    int rc = oracle_leader_follower_interaction_brute(agents, n, itemsize, weight_position_leader, phi, obstacles, n_obs, sight,
+                                                      direction, has_strategy);
+    if (!rc)
+        for (int64_t i = 0; i < n; ++i) {
+            agent_circular_t *a = circ(agents, itemsize, i);
+            if (!has_strategy[i] && a->is_follower) a->target = a->familiar_exit;
+        }
+    free(has_strategy);
+    return rc;
+}
+
+/* collective_motion.py:246-289; direction[n][2] */
+int oracle_leader_follower_with_herding_interaction(void *agents, int64_t n, int64_t itemsize, const void *obstacles, int64_t n_obs,
+                                                    double sight, int64_t size_nearest_other, double phi, double weight_position_herding,
+                                                    double weight_position_leader, double weight_direction_leader, double *direction) {
+    if (itemsize != 228 && itemsize != 316) return ORACLE_INVALID_TYPE;
+    const double sight_leader = 20.0;
+    int64_t *neighbors = malloc(sizeof(int64_t) * (n * size_nearest_other + 1));
+    uint8_t *is_follower = malloc(n + 1), *has_direction = malloc(n + 1), *has_strategy = malloc(n + 1);
+    double *dir_herding = malloc(sizeof(double) * (2 * n + 2)), *dir_leader = malloc(sizeof(double) * (2 * n + 2));
+    int rc = oracle_find_nearest_neighbors(agents, n, itemsize, sight, size_nearest_other, obstacles, n_obs, neighbors);
+    for (int64_t i = 0; i < n; ++i) is_follower[i] = circ(agents, itemsize, i)->is_follower;
+    if (!rc) rc = oracle_herding_interaction(agents, n, itemsize, is_follower, neighbors, size_nearest_other, weight_position_herding,
+                                             phi, dir_herding, has_direction);
+    if (!rc) {
+        for (int64_t i = 0; i < n; ++i) if (has_direction[i]) circ(agents, itemsize, i)->target = NO_TARGET;
+        rc = oracle_leader_follower_interaction_brute(agents, n, itemsize, weight_position_leader, phi, obstacles, n_obs, sight_leader,
+                                                      dir_leader, has_strategy);
+    }
+    if (!rc)
+        for (int64_t i = 0; i < n; ++i) {
+            agent_circular_t *a = circ(agents, itemsize, i);
+            if (!(has_direction[i] || has_strategy[i]) && is_follower[i]) a->target = a->familiar_exit;
+            double w[2];
+            weighted_average2(dir_leader + 2 * i, dir_herding + 2 * i, weight_direction_leader, w);
+            normalize2(w, direction + 2 * i);
+        }
+    free(neighbors); free(is_follower); free(has_direction); free(has_strategy); free(dir_herding); free(dir_leader);
+    return rc;
+}

@@ -56,6 +56,16 @@ def lib():
         L.oracle_reset.argtypes = [vp, i64, i64]
         L.oracle_step.argtypes = [vp, i64, i64, vp, i64, i64, vp, vp, i64, i64, f64, f64, f64, f64, f64, f64,
                                   C.POINTER(f64)]
+        u8p = vp
+        L.oracle_line_intersect.argtypes = [vp, vp, vp, vp]
+        L.oracle_is_obstacle_between_points.argtypes = [vp, vp, vp, i64]
+        L.oracle_exit_detection.argtypes = [vp, i64, vp, i64, i64, vp, i64, f64, vp, u8p]
+        L.oracle_herding_relationship.argtypes = [vp, vp, vp, vp, f64]
+        L.oracle_find_nearest_neighbors.argtypes = [vp, i64, i64, f64, i64, vp, i64, vp]
+        L.oracle_herding_interaction.argtypes = [vp, i64, i64, u8p, vp, i64, f64, f64, vp, u8p]
+        L.oracle_leader_follower_interaction_brute.argtypes = [vp, i64, i64, f64, f64, vp, i64, f64, vp, u8p]
+        L.oracle_leader_follower_interaction.argtypes = [vp, i64, i64, vp, i64, f64, f64, f64, vp]
+        L.oracle_leader_follower_with_herding_interaction.argtypes = [vp, i64, i64, vp, i64, f64, i64, f64, f64, f64, f64, vp]
         _LIB = L
     return _LIB
 
@@ -179,3 +189,92 @@ def step(agents, obstacles, fields, cell_size, dt_min, dt_max):
     dt = velocity_verlet_integrator(agents, dt_min, dt_max)
     reset(agents)
     return dt
+
+
+# ---- exit detection, herding, leader-follower -----------------------------------------------------
+def _obs(obstacles):
+    obs = np.ascontiguousarray(obstacles)
+    return obs, obs.ctypes.data, len(obs)
+
+
+def _v2(x):
+    return np.ascontiguousarray(x, dtype=np.float64)
+
+
+def line_intersect(x0, x1, y0, y1):
+    x0, x1, y0, y1 = _v2(x0), _v2(x1), _v2(y0), _v2(y1)
+    return bool(lib().oracle_line_intersect(x0.ctypes.data, x1.ctypes.data, y0.ctypes.data, y1.ctypes.data))
+
+
+def is_obstacle_between_points(p0, p1, obstacles):
+    p0, p1 = _v2(p0), _v2(p1)
+    obs, po, no = _obs(obstacles)
+    return bool(lib().oracle_is_obstacle_between_points(p0.ctypes.data, p1.ctypes.data, po, no))
+
+
+def exit_detection(center_door, agents, obstacles, detection_range):
+    """core/evacuation.py:137-174 on agents['position'] -> (detected_exit int64[n], has_detected bool[n])."""
+    p, n, sz = _a(agents)
+    doors = _v2(center_door).reshape(-1, 2)
+    obs, po, no = _obs(obstacles)
+    detected = np.empty(n, dtype=np.int64)
+    has = np.zeros(n, dtype=np.uint8)
+    _check(lib().oracle_exit_detection(doors.ctypes.data, len(doors), p, n, sz, po, no, float(detection_range),
+                                       detected.ctypes.data, has.ctypes.data))
+    return detected, has.astype(bool)
+
+
+def herding_relationship(x1, x2, v1, v2, phi=np.pi / 2):
+    x1, x2, v1, v2 = _v2(x1), _v2(x2), _v2(v1), _v2(v2)
+    r = lib().oracle_herding_relationship(x1.ctypes.data, x2.ctypes.data, v1.ctypes.data, v2.ctypes.data, float(phi))
+    return bool(r & 1), bool(r & 2)
+
+
+def find_nearest_neighbors(agents, sight, size_nearest_other, obstacles):
+    p, n, sz = _a(agents)
+    obs, po, no = _obs(obstacles)
+    neighbors = np.full((n, size_nearest_other), -1, dtype=np.int64)
+    _check(lib().oracle_find_nearest_neighbors(p, n, sz, float(sight), int(size_nearest_other), po, no, neighbors.ctypes.data))
+    return neighbors
+
+
+def herding_interaction(agents, is_herding, neighbors, weight_position, phi):
+    p, n, sz = _a(agents)
+    ish = np.ascontiguousarray(is_herding, dtype=np.uint8)
+    nb = np.ascontiguousarray(neighbors, dtype=np.int64)
+    out = np.zeros((n, 2))
+    has = np.zeros(n, dtype=np.uint8)
+    _check(lib().oracle_herding_interaction(p, n, sz, ish.ctypes.data, nb.ctypes.data, nb.shape[1] if nb.ndim == 2 else 0,
+                                            float(weight_position), float(phi), out.ctypes.data, has.ctypes.data))
+    return out, has.astype(bool)
+
+
+def leader_follower_interaction_brute(agents, weight_position, phi, obstacles, sight):
+    p, n, sz = _a(agents)
+    obs, po, no = _obs(obstacles)
+    out = np.zeros((n, 2))
+    has = np.zeros(n, dtype=np.uint8)
+    _check(lib().oracle_leader_follower_interaction_brute(p, n, sz, float(weight_position), float(phi), po, no, float(sight),
+                                                          out.ctypes.data, has.ctypes.data))
+    return out, has.astype(bool)
+
+
+def leader_follower_interaction(agents, obstacles, sight, phi=0.45 * np.pi, weight_position_leader=0.40):
+    p, n, sz = _a(agents)
+    obs, po, no = _obs(obstacles)
+    out = np.zeros((n, 2))
+    _check(lib().oracle_leader_follower_interaction(p, n, sz, po, no, float(sight), float(phi), float(weight_position_leader),
+                                                    out.ctypes.data))
+    return out
+
+
+def leader_follower_with_herding_interaction(agents, obstacles, sight, size_nearest_other, phi=0.45 * np.pi,
+                                             weight_position_herding=0.15, weight_position_leader=0.40,
+                                             weight_direction_leader=0.65):
+    p, n, sz = _a(agents)
+    obs, po, no = _obs(obstacles)
+    out = np.zeros((n, 2))
+    _check(lib().oracle_leader_follower_with_herding_interaction(
+        p, n, sz, po, no, float(sight), int(size_nearest_other), float(phi), float(weight_position_herding),
+        float(weight_position_leader), float(weight_direction_leader), out.ctypes.data))
+    return out

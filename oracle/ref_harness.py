@@ -19,6 +19,8 @@ Shims:
      agents.py:447-457 + traits.py:158-219, itemsize asserted 228/316), ``is_model`` and ``shoulders``
   5. ``cell_lists`` -- third-party, unpinned, not installed: restated below per the in-tree spec
      crowddynamics/core/block_list.py:28-52 ("parity unpinned" at that boundary).
+  6. ``numba.typing.typeof`` (moved to numba.core.typing in numba >= 0.49; imported by sensory_region.py,
+     collective_motion.py and evacuation.py for ``typeof(obstacle_type_linear)``)
 """
 import ast
 import importlib
@@ -193,6 +195,16 @@ def load():
             return deco
         numba.generated_jit = generated_jit
 
+    # (6) numba.typing.typeof
+    if 'numba.typing' not in sys.modules:
+        typing_pkg = types.ModuleType('numba.typing')
+        typing_pkg.__path__ = []
+        typeof_mod = types.ModuleType('numba.typing.typeof')
+        typeof_mod.typeof = numba.typeof
+        typing_pkg.typeof = typeof_mod
+        sys.modules['numba.typing'] = typing_pkg
+        sys.modules['numba.typing.typeof'] = typeof_mod
+
     # (1) stub packages
     for name, sub in (('crowddynamics', ''), ('crowddynamics.core', 'core'),
                       ('crowddynamics.core.motion', 'core/motion'),
@@ -249,6 +261,10 @@ def load():
     R.integrator = importlib.import_module('crowddynamics.core.integrator')
     R.interactions = importlib.import_module('crowddynamics.core.interactions')
     R.orientation = importlib.import_module('crowddynamics.core.steering.orientation')
+    R.geom2D = importlib.import_module('crowddynamics.core.geom2D')
+    R.sensory_region = importlib.import_module('crowddynamics.core.sensory_region')
+    R.collective_motion = importlib.import_module('crowddynamics.core.steering.collective_motion')
+    R.evacuation = importlib.import_module('crowddynamics.core.evacuation')
     R.agents = agents_mod
     R.cell_lists = sys.modules['cell_lists']
     R.exceptions = exc

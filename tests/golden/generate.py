@@ -145,8 +145,45 @@ def gen_hallway(R, steps=200):
                 obstacles=obstacles.view(np.float64).reshape(-1, 4))
 
 
+def gen_collective_fixture(R, model, n=500, seed=11):
+    """exit detection, k-nearest neighbours, herding, leader-follower (collective_motion.py,
+    evacuation.py:137-174) on a leader/follower crowd in a room with inner walls."""
+    cm, cl = R.collective_motion, R.cell_lists
+    agents, obstacles, doors, side = S.leader_follower_crowd(n, model, density=0.5, seed=seed)
+    sight, k, phi = 10.0, 5, 0.45 * np.pi
+    pos = np.ascontiguousarray(agents['position'])
+    vel = np.ascontiguousarray(agents['velocity'])
+    out = dict(initial=raw(agents), obstacles=obstacles.view(np.float64).reshape(-1, 4), center_door=doors,
+               sight=sight, size_nearest_other=k, phi=phi, detection_range=20.0)
+    pts, cnt, off, shape = cl.add_to_cells(pos, sight)
+    nbr = cm.find_nearest_neighbors(pos, sight, k, np.arange(len(cnt)), cl.neighboring_cells(shape), pts, cnt, off, obstacles)
+    out['neighbors'] = nbr
+    d, h = cm.herding_interaction(agents['is_follower'].copy(), pos, vel, nbr, 0.15, phi)
+    out['herding_direction'], out['herding_has_direction'] = d, h
+    a = agents.copy()
+    out['lfh_direction'] = cm.leader_follower_with_herding_interaction(a, obstacles, sight, k)
+    out['lfh_after'] = raw(a)
+    a = agents.copy()
+    out['lf_direction'] = cm.leader_follower_interaction(a, obstacles, 20.0)
+    out['lf_after'] = raw(a)
+    tg, has = R.evacuation.exit_detection(np.ascontiguousarray(doors), pos, obstacles, 20.0)
+    out['detected_exit'], out['has_detected'] = tg, has
+    # herding_relationship known answers (collective_motion.py:25-58), phi = pi / 2 and 0.45 pi
+    rng = np.random.default_rng(seed)
+    q = rng.normal(size=(200, 8))
+    q[:10, 4:6] = 0.0                                 # zero velocity: (False, False)
+    rel = np.array([[cm.herding_relationship(r[0:2].copy(), r[2:4].copy(), r[4:6].copy(), r[6:8].copy(), p)
+                     for p in (np.pi / 2, phi)] for r in q])
+    out['relationship_inputs'], out['relationship'] = q, rel
+    return out
+
+
 def main():
     R = H.load()
+    if '--only-collective' in sys.argv:
+        for model in ('circular', 'three_circle'):
+            np.savez_compressed(os.path.join(HERE, 'collective_%s.npz' % model), **gen_collective_fixture(R, model))
+        return
     for model in ('circular', 'three_circle'):
         fx = gen_step_fixture(R, model, n=300, seed=3, density=1.0, overlap=0.03)
         np.savez_compressed(os.path.join(HERE, 'step_%s.npz' % model), **fx)
@@ -155,6 +192,8 @@ def main():
     np.savez_compressed(os.path.join(HERE, 'pairs.npz'), **gen_pair_fixture(R))
     np.savez_compressed(os.path.join(HERE, 'known_answers.npz'), **gen_known_answers(R))
     np.savez_compressed(os.path.join(HERE, 'hallway.npz'), **gen_hallway(R))
+    for model in ('circular', 'three_circle'):
+        np.savez_compressed(os.path.join(HERE, 'collective_%s.npz' % model), **gen_collective_fixture(R, model))
     for f in sorted(os.listdir(HERE)):
         if f.endswith('.npz'):
             print('%-28s %8d bytes' % (f, os.path.getsize(os.path.join(HERE, f))))
