@@ -24,6 +24,7 @@ STEP_NAVIGATION, STEP_ORIENTATION, STEP_ADJUSTING, STEP_AGENT_AGENT, STEP_AGENT_
     STEP_RESET = (1 << k for k in range(7))
 STEP_ALL = (1 << 7) - 1
 STEP_FLUCTUATION = 1 << 7
+KNN_MAX = 32
 
 _lib = None
 
@@ -88,6 +89,14 @@ def _signatures(L):
         'cdb_strip_absorb': (i32, [vp, vp, vp, pi64]),
         'cdb_strip_count': (i32, [vp, pi64]),
         'cdb_export_agents': (i32, [vp, vp, vp, i64, pi64]),
+        'cdb_set_states': (i32, [vp, vp, vp, vp, vp, vp, i64]),
+        'cdb_get_states': (i32, [vp, vp, vp, vp, i64]),
+        'cdb_exit_detection': (i32, [vp, vp, i64, f64, i32]),
+        'cdb_get_exit_detection': (i32, [vp, vp, vp, i64]),
+        'cdb_nearest_neighbors': (i32, [vp, f64, i64, vp]),
+        'cdb_leader_follower': (i32, [vp, f64, f64, f64]),
+        'cdb_leader_follower_with_herding': (i32, [vp, f64, i64, f64, f64, f64, f64]),
+        'cdb_get_direction': (i32, [vp, vp, i64]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)

@@ -23,6 +23,7 @@
 #include "kernels.cuh"
 #include "step_kernel.cuh"
 #include "strip_kernels.cuh"
+#include "collective_kernels.cuh"
 
 namespace {
 
@@ -150,6 +151,18 @@ struct cdb_sim {
     bool dev_counts = false;
     int steps_since_refresh = 0;
     int *h_counters = nullptr;       // pinned
+
+    // collective motion (section 8(f) rank 4): States fields by original agent index, scratch of the steering kernels
+    int64_t states_n = 0;            // agents the arrays below describe (0: cdb_set_states not called yet)
+    int64_t states_cap = 0;
+    uint8_t *d_is_leader = nullptr, *d_is_follower = nullptr, *d_has_a = nullptr, *d_has_detected = nullptr;
+    long long *d_index_leader = nullptr, *d_familiar_exit = nullptr, *d_target_by_id = nullptr, *d_detected = nullptr, *d_knn = nullptr;
+    int64_t knn_cap = 0;
+    int *d_slot_of_id = nullptr, *d_leader_ids = nullptr;
+    int64_t n_leaders = 0;
+    double *d_dir_a = nullptr, *d_direction = nullptr, *d_doors = nullptr;
+    int64_t doors_cap = 0;
+    bool direction_valid = false, detection_valid = false;
 
     // instrumentation: kernel launch counter and CUDA-event timing of the step phases
     int64_t launches = 0;
@@ -508,6 +521,10 @@ int cdb_destroy(cdb_sim *sim) {
     cudaFree(sim->d_bbox); cudaFreeHost(sim->h_bbox);
     cudaFree(sim->d_obstacles);
     for (auto &f : sim->nav) { cudaFree((void *)f.U); cudaFree((void *)f.V); }
+    cudaFree(sim->d_is_leader); cudaFree(sim->d_is_follower); cudaFree(sim->d_has_a); cudaFree(sim->d_has_detected);
+    cudaFree(sim->d_index_leader); cudaFree(sim->d_familiar_exit); cudaFree(sim->d_target_by_id); cudaFree(sim->d_detected);
+    cudaFree(sim->d_knn); cudaFree(sim->d_slot_of_id); cudaFree(sim->d_leader_ids); cudaFree(sim->d_dir_a); cudaFree(sim->d_direction);
+    cudaFree(sim->d_doors);
     cudaFree(sim->d_nav); cudaFree(sim->d_vmax); cudaFree(sim->d_dt); cudaFree(sim->d_dt_log); cudaFreeHost(sim->h_dt);
     for (auto e : sim->ev_pool) cudaEventDestroy(e);
     if (sim->graph_exec) cudaGraphExecDestroy(sim->graph_exec);
@@ -1130,3 +1147,166 @@ int cdb_export_agents(cdb_sim *sim, void *agents, int64_t *ids, int64_t cap, int
 }
 
 }  // extern "C"
+
+
+// =====================================================================================================================
+// collective motion
+// =====================================================================================================================
+namespace {
+int ensure_states(cdb_sim *sim, int64_t n) {
+    if (n <= sim->states_cap) return CDB_OK;
+    const size_t cap = (size_t)(n < 1024 ? 1024 : n);
+    CKS(dev_alloc(&sim->d_is_leader, cap)); CKS(dev_alloc(&sim->d_is_follower, cap));
+    CKS(dev_alloc(&sim->d_has_a, cap)); CKS(dev_alloc(&sim->d_has_detected, cap));
+    CKS(dev_alloc(&sim->d_index_leader, cap)); CKS(dev_alloc(&sim->d_familiar_exit, cap));
+    CKS(dev_alloc(&sim->d_target_by_id, cap)); CKS(dev_alloc(&sim->d_detected, cap));
+    CKS(dev_alloc(&sim->d_slot_of_id, cap)); CKS(dev_alloc(&sim->d_leader_ids, cap));
+    CKS(dev_alloc(&sim->d_dir_a, 2 * cap)); CKS(dev_alloc(&sim->d_direction, 2 * cap));
+    CK(cudaMemset(sim->d_is_leader, 0, cap)); CK(cudaMemset(sim->d_is_follower, 0, cap));
+    CK(cudaMemset(sim->d_index_leader, 0xff, cap * sizeof(long long))); CK(cudaMemset(sim->d_familiar_exit, 0xff, cap * sizeof(long long)));
+    sim->states_cap = (int64_t)cap;
+    sim->states_n = 0; sim->n_leaders = 0;
+    return CDB_OK;
+}
+
+int collective_entry(cdb_sim *sim, bool need_states) {
+    if (sim->strip) return fail(CDB_ERR_STATE, "the collective-motion nodes are not available in strip mode");
+    if (need_states && sim->states_n != sim->n) return fail(CDB_ERR_STATE, "cdb_set_states must describe the %lld agents on the device first", (long long)sim->n);
+    CKS(ensure_states(sim, sim->n));
+    return CDB_OK;
+}
+
+int launch_leader_follower(cdb_sim *sim, double sight, double phi, double w_leader, bool with_herding, double w_direction) {
+    const int n = (int)sim->n;
+    LAUNCH(sim, k_slot_map, cdiv(n, 256), 256, 0, sim->cur, n, sim->d_slot_of_id, sim->d_target_by_id);
+    LAUNCH(sim, k_leader_follower, cdiv(n, 128), 128, 0, sim->cur, n, sim->d_obstacles, (int)sim->n_obstacles, sim->d_leader_ids, (int)sim->n_leaders,
+           sim->d_slot_of_id, sim->d_target_by_id, n, sim->d_is_follower, sim->d_index_leader, sim->d_familiar_exit, sight, std::cos(phi), w_leader,
+           with_herding ? sim->d_dir_a : nullptr, with_herding ? sim->d_has_a : nullptr, w_direction, sim->d_direction);
+    CK(cudaGetLastError());
+    sim->direction_valid = true;
+    sim->state_version++;
+    return CDB_OK;
+}
+
+int launch_herding(cdb_sim *sim, double sight, int64_t k, bool all_agents, double w_position, double phi, bool with_direction) {
+    CKS(build_block_list(sim, sight, false, nullptr, false));
+    sim->auto_lattice_valid = false;     // the step kernel's padded lattice was replaced by this one
+    const int64_t live = sim->n_sorted;
+    if ((int64_t)live * k > sim->knn_cap) { CKS(dev_alloc(&sim->d_knn, (size_t)(live * k))); sim->knn_cap = live * k; }
+    const int rec = sim->model == CDB_MODEL_CIRCULAR ? REC_CIRC : REC_THREE;
+    if (live > 0)
+        LAUNCH(sim, k_herding, cdiv(live, 128), 128, 0, sim->cur, (int)live, (const int *)nullptr, sim->d_nbr, rec, sim->d_grid, sim->d_cell_of_slot, sim->d_cell_start,
+               sim->d_cell_count, sim->d_order, sim->d_obstacles, (int)sim->n_obstacles, sight, (int)k, sim->d_is_follower, all_agents ? 1 : 0, w_position,
+               std::cos(phi), sim->d_knn, with_direction ? sim->d_dir_a : nullptr, with_direction ? sim->d_has_a : nullptr);
+    CK(cudaGetLastError());
+    sim->state_version++;
+    return CDB_OK;
+}
+}  // namespace
+
+int cdb_set_states(cdb_sim *sim, const int64_t *target, const uint8_t *is_leader, const uint8_t *is_follower,
+                   const int64_t *index_leader, const int64_t *familiar_exit, int64_t n) {
+    SIM_ENTRY();
+    if (sim->strip) return fail(CDB_ERR_STATE, "the collective-motion nodes are not available in strip mode");
+    if (n != sim->n) return fail(CDB_ERR_INVALID_VALUE, "cdb_set_states: n = %lld but the device holds %lld agents", (long long)n, (long long)sim->n);
+    CKS(ensure_states(sim, n));
+    cudaStream_t st = sim->stream;
+    CK(cudaStreamSynchronize(st));
+    if (n > 0) {
+        if (is_follower) CK(cudaMemcpy(sim->d_is_follower, is_follower, n, cudaMemcpyHostToDevice));
+        if (index_leader) CK(cudaMemcpy(sim->d_index_leader, index_leader, n * sizeof(int64_t), cudaMemcpyHostToDevice));
+        if (familiar_exit) CK(cudaMemcpy(sim->d_familiar_exit, familiar_exit, n * sizeof(int64_t), cudaMemcpyHostToDevice));
+        if (is_leader) {
+            CK(cudaMemcpy(sim->d_is_leader, is_leader, n, cudaMemcpyHostToDevice));
+            std::vector<int> ids;
+            for (int64_t i = 0; i < n; ++i) if (is_leader[i]) ids.push_back((int)i);
+            sim->n_leaders = (int64_t)ids.size();
+            if (!ids.empty()) CK(cudaMemcpy(sim->d_leader_ids, ids.data(), ids.size() * sizeof(int), cudaMemcpyHostToDevice));
+        }
+        if (target) {
+            CK(cudaMemcpy(sim->d_target_by_id, target, n * sizeof(int64_t), cudaMemcpyHostToDevice));
+            LAUNCH(sim, k_target_scatter, cdiv(n, 256), 256, 0, sim->cur, (int)n, sim->d_target_by_id);
+            CK(cudaStreamSynchronize(st));
+        }
+    }
+    sim->states_n = n;
+    sim->state_version++;
+    return CDB_OK;
+}
+
+int cdb_get_states(cdb_sim *sim, int64_t *target, uint8_t *is_follower, int64_t *index_leader, int64_t n) {
+    SIM_ENTRY();
+    CKS(collective_entry(sim, true));
+    if (n != sim->n) return fail(CDB_ERR_INVALID_VALUE, "cdb_get_states: n = %lld but the device holds %lld agents", (long long)n, (long long)sim->n);
+    if (n == 0) return CDB_OK;
+    if (target) LAUNCH(sim, k_slot_map, cdiv(n, 256), 256, 0, sim->cur, (int)n, sim->d_slot_of_id, sim->d_target_by_id);
+    CK(cudaStreamSynchronize(sim->stream));
+    if (target) CK(cudaMemcpy(target, sim->d_target_by_id, n * sizeof(int64_t), cudaMemcpyDeviceToHost));
+    if (is_follower) CK(cudaMemcpy(is_follower, sim->d_is_follower, n, cudaMemcpyDeviceToHost));
+    if (index_leader) CK(cudaMemcpy(index_leader, sim->d_index_leader, n * sizeof(int64_t), cudaMemcpyDeviceToHost));
+    return CDB_OK;
+}
+
+int cdb_exit_detection(cdb_sim *sim, const double *center_door, int64_t n_doors, double detection_range, int apply) {
+    SIM_ENTRY();
+    CKS(collective_entry(sim, apply != 0));
+    if (n_doors < 0 || (n_doors > 0 && !center_door)) return fail(CDB_ERR_INVALID_VALUE, "bad door buffer");
+    if (n_doors > sim->doors_cap) { CKS(dev_alloc(&sim->d_doors, (size_t)(2 * n_doors))); sim->doors_cap = n_doors; }
+    if (n_doors) CK(cudaMemcpyAsync(sim->d_doors, center_door, 2 * n_doors * sizeof(double), cudaMemcpyHostToDevice, sim->stream));
+    if (sim->n)
+        LAUNCH(sim, k_exit_detection, cdiv(sim->n, 128), 128, 0, sim->cur, (int)sim->n, sim->d_doors, (int)n_doors, sim->d_obstacles, (int)sim->n_obstacles,
+               detection_range, sim->d_detected, sim->d_has_detected, sim->d_is_follower, apply ? 1 : 0);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(sim->stream));   // center_door is the caller's (pageable) memory
+    sim->detection_valid = true;
+    if (apply) sim->state_version++;
+    return CDB_OK;
+}
+
+int cdb_get_exit_detection(cdb_sim *sim, int64_t *detected_exit, uint8_t *has_detected, int64_t n) {
+    SIM_ENTRY();
+    if (!sim->detection_valid || n != sim->n) return fail(CDB_ERR_STATE, "cdb_exit_detection must run first (on the same %lld agents)", (long long)sim->n);
+    CK(cudaStreamSynchronize(sim->stream));
+    if (n && detected_exit) CK(cudaMemcpy(detected_exit, sim->d_detected, n * sizeof(int64_t), cudaMemcpyDeviceToHost));
+    if (n && has_detected) CK(cudaMemcpy(has_detected, sim->d_has_detected, n, cudaMemcpyDeviceToHost));
+    return CDB_OK;
+}
+
+int cdb_nearest_neighbors(cdb_sim *sim, double sight, int64_t k, int64_t *neighbors) {
+    SIM_ENTRY();
+    CKS(collective_entry(sim, false));
+    if (k < 1 || k > CDB_KNN_MAX) return fail(CDB_ERR_INVALID_VALUE, "size_nearest_other = %lld outside [1, %d]", (long long)k, CDB_KNN_MAX);
+    if (!neighbors && sim->n) return fail(CDB_ERR_INVALID_VALUE, "neighbors is NULL");
+    if (sim->n == 0) return CDB_OK;
+    CKS(launch_herding(sim, sight, k, true, 0.0, 0.0, false));
+    CK(cudaStreamSynchronize(sim->stream));
+    CKS(check_device_error(sim));
+    CK(cudaMemcpy(neighbors, sim->d_knn, (size_t)sim->n * k * sizeof(int64_t), cudaMemcpyDeviceToHost));
+    return CDB_OK;
+}
+
+int cdb_leader_follower(cdb_sim *sim, double sight, double phi, double weight_position_leader) {
+    SIM_ENTRY();
+    CKS(collective_entry(sim, true));
+    if (sim->n == 0) return CDB_OK;
+    return launch_leader_follower(sim, sight, phi, weight_position_leader, false, 0.0);
+}
+
+int cdb_leader_follower_with_herding(cdb_sim *sim, double sight, int64_t size_nearest_other, double phi, double weight_position_herding,
+                                     double weight_position_leader, double weight_direction_leader) {
+    SIM_ENTRY();
+    CKS(collective_entry(sim, true));
+    if (size_nearest_other < 1 || size_nearest_other > CDB_KNN_MAX)
+        return fail(CDB_ERR_INVALID_VALUE, "size_nearest_other = %lld outside [1, %d]", (long long)size_nearest_other, CDB_KNN_MAX);
+    if (sim->n == 0) return CDB_OK;
+    CKS(launch_herding(sim, sight, size_nearest_other, false, weight_position_herding, phi, true));
+    return launch_leader_follower(sim, 20.0 /* sight_leader, collective_motion.py:255 */, phi, weight_position_leader, true, weight_direction_leader);
+}
+
+int cdb_get_direction(cdb_sim *sim, double *direction, int64_t n) {
+    SIM_ENTRY();
+    if (!sim->direction_valid || n != sim->n) return fail(CDB_ERR_STATE, "no direction computed for these %lld agents", (long long)sim->n);
+    CK(cudaStreamSynchronize(sim->stream));
+    if (n && direction) CK(cudaMemcpy(direction, sim->d_direction, 2 * n * sizeof(double), cudaMemcpyDeviceToHost));
+    return CDB_OK;
+}

@@ -189,6 +189,59 @@ class DeviceAgents:
             _lib.check(self.lib.cdb_get_neighbor_pairs(self.handle, _ptr(out), cnt.value, C.byref(cnt)))
         return out
 
+    # -- collective motion ---------------------------------------------------------------------------
+    def set_states(self, agents, target=True):
+        """Send the States fields the collective-motion nodes read (agents.py:33-60) next to the uploaded records."""
+        n = len(agents)
+        f = {k: np.ascontiguousarray(agents[k]) for k in ('is_leader', 'is_follower', 'index_leader', 'familiar_exit')}
+        tg = np.ascontiguousarray(agents['target']) if target else None
+        _lib.check(self.lib.cdb_set_states(self.handle, _ptr(tg) if target and n else None,
+                                           _ptr(f['is_leader'].view(np.uint8)) if n else None,
+                                           _ptr(f['is_follower'].view(np.uint8)) if n else None,
+                                           _ptr(f['index_leader']) if n else None, _ptr(f['familiar_exit']) if n else None, n))
+
+    def get_states(self, agents):
+        """Write back target / is_follower / index_leader (the States fields these nodes mutate)."""
+        n = len(agents)
+        if n == 0:
+            return
+        tg, fo, il = np.empty(n, np.int64), np.empty(n, np.uint8), np.empty(n, np.int64)
+        _lib.check(self.lib.cdb_get_states(self.handle, _ptr(tg), _ptr(fo), _ptr(il), n))
+        agents['target'] = tg
+        agents['is_follower'] = fo.astype(bool)
+        agents['index_leader'] = il
+
+    def exit_detection(self, center_door, detection_range, apply=False):
+        doors = np.ascontiguousarray(center_door, dtype=np.float64).reshape(-1, 2)
+        _lib.check(self.lib.cdb_exit_detection(self.handle, _ptr(doors) if len(doors) else None, len(doors),
+                                               float(detection_range), 1 if apply else 0))
+
+    def exit_detection_result(self):
+        det, has = np.empty(self.n, np.int64), np.empty(self.n, np.uint8)
+        _lib.check(self.lib.cdb_get_exit_detection(self.handle, _ptr(det) if self.n else None,
+                                                   _ptr(has) if self.n else None, self.n))
+        return det, has.astype(bool)
+
+    def nearest_neighbors(self, sight, size_nearest_other):
+        out = np.full((self.n, int(size_nearest_other)), -1, dtype=np.int64)
+        _lib.check(self.lib.cdb_nearest_neighbors(self.handle, float(sight), int(size_nearest_other),
+                                                  _ptr(out) if out.size else None))
+        return out
+
+    def leader_follower(self, sight, phi=0.45 * np.pi, weight_position_leader=0.40):
+        _lib.check(self.lib.cdb_leader_follower(self.handle, float(sight), float(phi), float(weight_position_leader)))
+
+    def leader_follower_with_herding(self, sight, size_nearest_other, phi=0.45 * np.pi, weight_position_herding=0.15,
+                                     weight_position_leader=0.40, weight_direction_leader=0.65):
+        _lib.check(self.lib.cdb_leader_follower_with_herding(
+            self.handle, float(sight), int(size_nearest_other), float(phi), float(weight_position_herding),
+            float(weight_position_leader), float(weight_direction_leader)))
+
+    def direction(self):
+        out = np.zeros((self.n, 2), dtype=np.float64)
+        _lib.check(self.lib.cdb_get_direction(self.handle, _ptr(out) if self.n else None, self.n))
+        return out
+
     def set_lattice(self, ix_min, iy_min, nx, ny):
         _lib.check(self.lib.cdb_set_lattice(self.handle, int(ix_min), int(iy_min), int(nx), int(ny)))
 

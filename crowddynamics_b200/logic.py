@@ -129,6 +129,8 @@ class DeviceState:
         self._obstacles_key = None
         self._nav_key = None
         self.dirty_host = False     # device is ahead of the host array (resident mode)
+        self.dirty_states = False   # ... and of its States fields target / is_follower / index_leader
+        self._states_id = None
 
     @classmethod
     def of(cls, simulation, mode=None, device=0):
@@ -165,23 +167,40 @@ class DeviceState:
             self.dirty_host = False
         return self.dev
 
-    def end(self, mask):
-        """Publish what a node wrote."""
+    def begin_states(self):
+        """``begin()`` for the collective-motion nodes, which also read the States fields (agents.py:33-60)."""
+        dev = self.begin()
+        agents = self.agents
+        if self.mode == 'strict' or self._states_id != self._host_id:
+            dev.set_states(agents, target=False)      # target travels with the records
+            self._states_id = self._host_id
+        return dev
+
+    def end(self, mask, states=False):
+        """Publish what a node wrote (``states``: also target / is_follower / index_leader)."""
         if self.mode == 'strict':
-            self.dev.download(self.agents, mask)
+            if mask:
+                self.dev.download(self.agents, mask)
+            if states:
+                self.dev.get_states(self.agents)
         else:
-            self.dirty_host = True
+            self.dirty_host = self.dirty_host or bool(mask)
+            self.dirty_states = self.dirty_states or states
 
     def sync_host(self, mask=_lib.F_ALL_MUTABLE):
         """Resident mode: refresh the host array from the device (before host-side nodes / IO read it)."""
         if self.dev is not None and self.dirty_host:
             self.dev.download(self.agents, mask)
             self.dirty_host = False
+        if self.dev is not None and self.dirty_states:
+            self.dev.get_states(self.agents)
+            self.dirty_states = False
 
     def invalidate(self):
         """Resident mode: the host array was modified by a host-side node; re-upload at the next node."""
         self.sync_host()
         self._host_id = None
+        self._states_id = None
 
     # -- geometry / fields -------------------------------------------------------------------------------------------
     def ensure_obstacles(self):
@@ -324,6 +343,45 @@ class Orientation(LogicNode):
             dev = self.state.begin()
             dev.orientation()
             self.state.end(_lib.F_TARGET_ORIENTATION)
+
+
+class ExitDetection(LogicNode):
+    """logic.py:237-256 -- herding agents detect an exit within ``detection_range`` that is in their line of sight.
+    ``center_door``: (n_doors, 2) door centres; default: the mean of every ``field.targets`` geometry, as in the reference."""
+    _params = dict(detection_range=20.0, center_door=None)
+
+    def _doors(self):
+        if self.center_door is not None:
+            return np.asarray(self.center_door, dtype=np.float64).reshape(-1, 2)
+        return np.stack([np.mean(np.asarray(target), axis=0) for target in self.simulation.field.targets])
+
+    def update(self):
+        dev = self.state.begin_states()
+        self.state.ensure_obstacles()
+        dev.exit_detection(self._doors(), self.detection_range, apply=True)
+        self.state.end(0, states=True)
+
+
+class LeaderFollower(LogicNode):
+    """logic.py:168-182"""
+    _params = dict(sight=20.0)
+
+    def update(self):
+        dev = self.state.begin_states()
+        self.state.ensure_obstacles()
+        dev.leader_follower(self.sight)
+        self.state.end(_lib.F_TARGET_DIRECTION, states=True)
+
+
+class LeaderFollowerWithHerding(LogicNode):
+    """logic.py:185-221"""
+    _params = dict(sight_follower=10.0, size_nearest_other=5)
+
+    def update(self):
+        dev = self.state.begin_states()
+        self.state.ensure_obstacles()
+        dev.leader_follower_with_herding(self.sight_follower, self.size_nearest_other)
+        self.state.end(_lib.F_TARGET_DIRECTION, states=True)
 
 
 class FusedStep(LogicNode):

@@ -182,6 +182,36 @@ int cdb_strip_count(cdb_sim *sim, int64_t *n_out);   /* agents currently owned (
  * zero) and their global ids. */
 int cdb_export_agents(cdb_sim *sim, void *agents, int64_t *ids, int64_t cap, int64_t *count);
 
+/* ---- collective motion: exit detection, herding, leader-follower ---------------------------
+ * These nodes read / write the States fields of the agent records (simulation/agents.py:33-60).  `target` lives on the
+ * device per agent (uploaded with the records); the others are set here as plain arrays indexed like the host array.
+ * Not available in strip mode (CDB_ERR_STATE).  Any pointer of cdb_set_states / cdb_get_states may be NULL (= skip). */
+#define CDB_KNN_MAX 32
+/* replaces: reading agents['target' | 'is_leader' | 'is_follower' | 'index_leader' | 'familiar_exit'] */
+int cdb_set_states(cdb_sim *sim, const int64_t *target, const uint8_t *is_leader, const uint8_t *is_follower,
+                   const int64_t *index_leader, const int64_t *familiar_exit, int64_t n);
+/* replaces: the in-place writes to agents['target' | 'is_follower' | 'index_leader'] */
+int cdb_get_states(cdb_sim *sim, int64_t *target, uint8_t *is_follower, int64_t *index_leader, int64_t n);
+/* ExitDetection.update (simulation/logic.py:237-256) -> exit_detection (core/evacuation.py:137-174): closest door centre in
+ * range with a free line of sight (is_obstacle_between_points, core/sensory_region.py:9-16; line_intersect,
+ * core/geom2D.py:38-59).  apply != 0 also does logic.py:253-255 (followers that detected an exit get it as target and stop
+ * being followers).  cdb_get_exit_detection returns the two arrays exit_detection returns. */
+int cdb_exit_detection(cdb_sim *sim, const double *center_door, int64_t n_doors, double detection_range, int apply);
+int cdb_get_exit_detection(cdb_sim *sim, int64_t *detected_exit, uint8_t *has_detected, int64_t n);
+/* find_nearest_neighbors (core/steering/collective_motion.py:69-110) over the block list with cell_size = sight
+ * (:262-267): neighbors[n][k], -1 = missing, rows in the reference's own slot order.  1 <= k <= CDB_KNN_MAX. */
+int cdb_nearest_neighbors(cdb_sim *sim, double sight, int64_t k, int64_t *neighbors);
+/* LeaderFollower.update (logic.py:168-182) -> leader_follower_interaction (collective_motion.py:229-243): updates target /
+ * index_leader of the followers and sets target_direction[is_follower] = direction[is_follower]. */
+int cdb_leader_follower(cdb_sim *sim, double sight, double phi, double weight_position_leader);
+/* LeaderFollowerWithHerding.update (logic.py:185-221) -> leader_follower_with_herding_interaction
+ * (collective_motion.py:246-289; leaders are seen up to 20 m, :255). */
+int cdb_leader_follower_with_herding(cdb_sim *sim, double sight, int64_t size_nearest_other, double phi,
+                                     double weight_position_herding, double weight_position_leader,
+                                     double weight_direction_leader);
+/* the direction array (n x 2, all agents) the last of the two calls above computed = the reference functions' return value */
+int cdb_get_direction(cdb_sim *sim, double *direction, int64_t n);
+
 #ifdef __cplusplus
 }
 #endif

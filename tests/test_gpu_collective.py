@@ -1,0 +1,236 @@
+"""SURVEY 8(f) rank 4 on the GPU: exit detection, k-nearest-neighbour herding and leader-follower steering through the C ABI,
+against the reference's golden vectors and against the C oracle (which is pinned bit-exact to the reference's numba code).
+
+Bar: every integer / boolean output (neighbour tables, detected exits, targets, leaders, follower flags) bit-exact;
+directions within 1e-12 (they pass through hypot, whose last bit may differ between libm and CUDA)."""
+import numpy as np
+import pytest
+
+from conftest import load_golden, from_raw
+from crowddynamics_b200 import synthetic as S, logic as L, _lib
+from crowddynamics_b200.core import evacuation as EV
+from crowddynamics_b200.core.steering import collective_motion as CM
+from crowddynamics_b200.engine import DeviceAgents
+from crowddynamics_b200.exceptions import InvalidValue, CrowdDynamicsException
+from crowddynamics_b200.structures import agent_type_circular, agent_type_three_circle, obstacle_type_linear, model_of
+from oracle import crowd_oracle as O
+
+pytestmark = pytest.mark.gpu
+DT = {'circular': agent_type_circular, 'three_circle': agent_type_three_circle}
+TOL = 1e-12
+
+
+def _golden(model):
+    g = load_golden('collective_%s.npz' % model)
+    agents = from_raw(g['initial'], DT[model])
+    obstacles = np.ascontiguousarray(g['obstacles']).view(obstacle_type_linear).reshape(-1)
+    return g, agents, obstacles
+
+
+def _same_states(a, b):
+    return all((a[f] == b[f]).all() for f in ('target', 'is_follower', 'index_leader', 'is_leader', 'familiar_exit'))
+
+
+@pytest.mark.parametrize('model', ['circular', 'three_circle'])
+def test_golden_functions(model):
+    g, agents, obstacles = _golden(model)
+    sight, k = float(g['sight']), int(g['size_nearest_other'])
+    nbr = CM.find_nearest_neighbors(agents.copy(), sight, k, obstacles)
+    assert (nbr == g['neighbors']).all()                       # same rows in the same slot order as the reference
+    a = agents.copy()
+    d = CM.leader_follower_with_herding_interaction(a, obstacles, sight, k)
+    ref = from_raw(g['lfh_after'], DT[model])
+    assert _same_states(a, ref)
+    assert np.abs(d - g['lfh_direction']).max() <= TOL
+    a = agents.copy()
+    d = CM.leader_follower_interaction(a, obstacles, 20.0)
+    ref = from_raw(g['lf_after'], DT[model])
+    assert _same_states(a, ref)
+    assert np.abs(d - g['lf_direction']).max() <= TOL
+    det, has = EV.exit_detection(g['center_door'], agents, obstacles, float(g['detection_range']))
+    assert (det == g['detected_exit']).all() and (has == g['has_detected']).all()
+    det, has = EV.exit_detection(g['center_door'], agents['position'].copy(), obstacles, float(g['detection_range']))
+    assert (det == g['detected_exit']).all() and (has == g['has_detected']).all()
+
+
+@pytest.mark.parametrize('model,n,density,seed,k,sight', [
+    ('circular', 20000, 0.5, 1, 5, 10.0), ('three_circle', 12000, 1.0, 2, 8, 6.0), ('circular', 3000, 0.05, 3, 1, 25.0),
+    ('circular', 5000, 2.0, 4, 32, 4.0)])
+def test_functions_against_oracle(model, n, density, seed, k, sight):
+    agents, obstacles, doors, side = S.leader_follower_crowd(n, model, density=density, seed=seed, n_doors=3)
+    nbr = CM.find_nearest_neighbors(agents.copy(), sight, k, obstacles)
+    assert (nbr == O.find_nearest_neighbors(agents, sight, k, obstacles)).all()
+    for fn, args in (('leader_follower_with_herding_interaction', (sight, k)), ('leader_follower_interaction', (20.0,))):
+        a, b = agents.copy(), agents.copy()
+        d_gpu = getattr(CM, fn)(a, obstacles, *args)
+        d_cpu = getattr(O, fn)(b, obstacles, *args)
+        assert _same_states(a, b), fn
+        assert np.abs(d_gpu - d_cpu).max() <= TOL, fn
+        assert (a['target'] != agents['target']).any()
+    det, has = EV.exit_detection(doors, agents, obstacles, 0.3 * side)
+    det2, has2 = O.exit_detection(doors, agents, obstacles, 0.3 * side)
+    assert (det == det2).all() and (has == has2).all() and 0 < has.sum() < n
+
+
+def _oracle_update(ref, obstacles, fields, doors, detection_range, dt):
+    """post-order of examples/collective_motion.py:229-240: LeaderFollowerWithHerding, ExitDetection, Navigation, Orientation,
+    Adjusting, AgentAgentInteractions, AgentObstacleInteractions, Integrator, Reset"""
+    d = O.leader_follower_with_herding_interaction(ref, obstacles, 10.0, 5)
+    f = ref['is_follower'].copy()
+    ref['target_direction'][f] = d[f]
+    det, has = O.exit_detection(doors, ref, obstacles, detection_range)
+    mask = ref['is_follower'] & has
+    ref['target'][mask] = det[mask]
+    ref['is_follower'][mask] = False
+    O.navigation(ref, fields)
+    O.orientation(ref)
+    O.adjusting(ref)
+    O.agent_agent_block_list(ref, 3.6)
+    O.agent_obstacle(ref, obstacles)
+    O.velocity_verlet_integrator(ref, dt, dt)
+    O.reset(ref)
+
+
+@pytest.mark.parametrize('model', ['circular', 'three_circle'])
+@pytest.mark.parametrize('mode', ['strict', 'resident'])
+def test_nodes_in_the_reference_tree(model, mode):
+    agents, obstacles, doors, side = S.leader_follower_crowd(1500, model, density=0.5, seed=5)
+    bounds = (-1.0, -1.0, side + 1.0, side + 1.0)
+    fields = [S.direction_field(0.5, bounds, 'exit', point=tuple(doors[0])), S.direction_field(0.5, bounds, 'exit', point=tuple(doors[1]))]
+    ref = agents.copy()
+    sim = L.MultiAgentSimulation(agents, obstacles, fields)
+    sim.logic = L.Reset(sim, mode=mode) << (L.Integrator(sim) << (
+        L.Adjusting(sim) << (
+            L.Navigation(sim, step=0.5) << (L.ExitDetection(sim, detection_range=8.0, center_door=doors) << L.LeaderFollowerWithHerding(sim)),
+            L.Orientation(sim)),
+        L.AgentAgentInteractions(sim), L.AgentObstacleInteractions(sim)))
+    assert [n.name for n in L.post_order_iter(sim.logic.root)][:3] == ['LeaderFollowerWithHerding', 'ExitDetection', 'Navigation']
+    for it in range(6):
+        sim.update()
+        _oracle_update(ref, obstacles, fields, doors, 8.0, 0.01)
+        if mode == 'strict':
+            assert _same_states(agents, ref), it
+    sim.logic.state.sync_host()
+    assert _same_states(agents, ref)
+    assert (~ref['is_follower']).sum() > (~S.leader_follower_crowd(1500, model, density=0.5, seed=5)[0]['is_follower']).sum()   # exits were detected
+    assert np.abs(agents['position'] - ref['position']).max() <= 1e-9
+    assert np.abs(agents['target_direction'] - ref['target_direction']).max() <= 1e-9
+
+
+def test_after_resort_and_state_roundtrip():
+    """The States arrays are indexed by the original agent index: fused steps re-sort the planes, results must not care."""
+    agents, obstacles, doors, side = S.leader_follower_crowd(4000, 'three_circle', density=1.0, seed=8)
+    ref = agents.copy()
+    dev = DeviceAgents(model_of(agents), capacity=len(agents))
+    dev.upload(agents)
+    dev.set_obstacles(obstacles)
+    dev.set_states(agents)
+    dev.step(3, _lib.STEP_ALL & ~_lib.STEP_NAVIGATION, 3.6, 0.01, 0.01)
+    for _ in range(3):
+        O.step(ref, obstacles, [], 3.6, 0.01, 0.01)
+    dev.leader_follower_with_herding(10.0, 5)
+    d = dev.direction()
+    d_ref = O.leader_follower_with_herding_interaction(ref, obstacles, 10.0, 5)
+    out = agents.copy()
+    dev.download(out)
+    dev.get_states(out)
+    assert _same_states(out, ref)
+    assert np.abs(d - d_ref).max() <= 1e-9
+    f = ref['is_follower']
+    assert np.abs(out['target_direction'][f] - d_ref[f]).max() <= 1e-9
+    assert np.abs(out['target_direction'][~f] - ref['target_direction'][~f]).max() <= 1e-9      # leaders keep theirs
+    # a second upload of edited states is honoured
+    out['is_follower'] = False
+    dev.set_states(out)
+    dev.leader_follower(20.0)
+    assert (dev.direction() == 0).all()
+
+
+def test_edge_cases():
+    agents, obstacles, doors, side = S.leader_follower_crowd(600, 'circular', density=0.5, seed=9)
+    # no leaders: remembered leader's target or the familiar exit (collective_motion.py:221-226, 239-241)
+    a = agents.copy(); a['is_leader'] = False
+    b = a.copy()
+    d = CM.leader_follower_interaction(a, obstacles, 20.0)
+    O.leader_follower_interaction(b, obstacles, 20.0)
+    assert (d == 0).all() and _same_states(a, b)
+    # no followers: nothing changes
+    a = agents.copy(); a['is_follower'] = False
+    d = CM.leader_follower_with_herding_interaction(a, obstacles, 10.0, 5)
+    assert (d == 0).all() and _same_states(a, _no_followers(agents))
+    # no obstacles, no doors
+    none = np.zeros(0, dtype=obstacle_type_linear)
+    a, b = agents.copy(), agents.copy()
+    d = CM.leader_follower_with_herding_interaction(a, none, 10.0, 5)
+    d2 = O.leader_follower_with_herding_interaction(b, none, 10.0, 5)
+    assert _same_states(a, b) and np.abs(d - d2).max() <= TOL
+    det, has = EV.exit_detection(np.zeros((0, 2)), agents, obstacles, 20.0)
+    assert (det == -1).all() and not has.any()
+    # agents at rest: herding_relationship is (False, False) -> nobody to follow
+    a = agents.copy(); a['velocity'] = 0.0
+    b = a.copy()
+    d = CM.leader_follower_with_herding_interaction(a, obstacles, 10.0, 5)
+    O.leader_follower_with_herding_interaction(b, obstacles, 10.0, 5)
+    assert (d == 0).all() and _same_states(a, b)
+    # coincident agents (distance 0) and a single agent
+    a = agents[:40].copy(); a['position'][1::2] = a['position'][0::2]
+    b = a.copy()
+    assert (CM.find_nearest_neighbors(a.copy(), 10.0, 5, obstacles) == O.find_nearest_neighbors(b, 10.0, 5, obstacles)).all()
+    one = agents[:1].copy()
+    assert (CM.find_nearest_neighbors(one, 10.0, 3, obstacles) == -1).all()
+    # parameter / state errors
+    with pytest.raises(InvalidValue):
+        CM.find_nearest_neighbors(agents.copy(), 10.0, 33, obstacles)
+    with pytest.raises(InvalidValue):
+        CM.leader_follower_with_herding_interaction(agents.copy(), obstacles, 10.0, 0)
+    dev = DeviceAgents(model_of(agents), capacity=len(agents))
+    dev.upload(agents)
+    with pytest.raises(CrowdDynamicsException):
+        dev.leader_follower(20.0)                      # cdb_set_states has not been called
+    with pytest.raises(CrowdDynamicsException):
+        dev.direction()
+
+
+def _no_followers(agents):
+    b = agents.copy()
+    b['is_follower'] = False
+    return b
+
+
+def test_full_size_properties():
+    """1 M agents (the bench size): size-independent properties of the steering nodes."""
+    n = 1_000_000
+    agents, obstacles, doors, side = S.leader_follower_crowd(n, 'circular', density=1.0, seed=12, n_leaders=2000)
+    dev = DeviceAgents(model_of(agents), capacity=n)
+    dev.upload(agents)
+    dev.set_obstacles(obstacles)
+    dev.set_states(agents)
+    nbr = dev.nearest_neighbors(10.0, 5)
+    pos = agents['position']
+    rows = np.arange(n)[:, None]
+    valid = nbr >= 0
+    dist = np.where(valid, np.hypot(*(pos[np.where(valid, nbr, 0)] - pos[rows.repeat(5, 1)]).transpose(2, 0, 1)), 0.0)
+    assert (dist < 10.0).all() and (nbr != rows).all()
+    # symmetric-ish: whoever is my nearest neighbour has me within its own sight
+    sample = np.random.default_rng(0).choice(n, 200, replace=False)
+    for i in sample:                                   # exact k-nearest check against brute force on a window
+        d = np.hypot(*(pos - pos[i]).T)
+        cand = np.flatnonzero((d < 10.0) & (np.arange(n) != i))
+        cand = [j for j in cand[np.argsort(d[cand])] if not O.is_obstacle_between_points(pos[i], pos[j], obstacles)][:5]
+        assert set(cand) == set(nbr[i][nbr[i] >= 0].tolist())
+    dev.leader_follower_with_herding(10.0, 5)
+    d = dev.direction()
+    out = agents.copy()
+    dev.download(out, _lib.F_TARGET_DIRECTION)
+    dev.get_states(out)
+    norm = np.hypot(*d.T)
+    assert (np.isclose(norm, 1.0, atol=1e-12) | (norm == 0)).all()
+    f = agents['is_follower']
+    assert (d[~f] == 0).all()
+    assert (out['target_direction'][f] == d[f]).all()
+    assert (out['target'][~f] == agents['target'][~f]).all() and (out['index_leader'][~f] == agents['index_leader'][~f]).all()
+    assert set(np.unique(out['target'][f])) <= {-1, 0, 1}
+    lost = f & (out['target'] != -1) & (out['index_leader'] == -1)
+    assert (out['target'][lost] == agents['familiar_exit'][lost]).all()
+    lead = out['index_leader'][f & (out['index_leader'] != -1)]
+    assert agents['is_leader'][lead].all()
