@@ -13,12 +13,27 @@ constexpr long long NO_TARGET = -1;          // simulation/agents.py:28
 constexpr long long NO_LEADER = -1;          // simulation/agents.py:29
 constexpr int KNN_MAX = 32;                  // capacity of the per-agent neighbour table (size_nearest_other <= KNN_MAX)
 
-// geom2D.py:38-59 -- segments (x0, x1) and (y0, y1)
+// geom2D.py:38-59 -- segments (x0, x1) and (y0, y1): 0 <= t0 / d <= 1 and 0 <= t1 / d <= 1.
+// The quotients are only formed when a ratio is within 1e-14 of 0 or 1 (or tiny enough to underflow): away from those
+// boundaries sign and magnitude comparisons decide exactly what the reference's divisions decide.
+__device__ __forceinline__ int unit_interval_class(double t, double d) {   // 1: clearly inside (0, 1), 0: clearly outside, -1: look closer
+    const double at = fabs(t), ad = fabs(d);
+    if (!(at > 1e-150) || !(ad > 1e-150) || !(ad < 1e150) || !(at < 1e150)) return -1;   // the quotient can neither underflow nor overflow
+    if ((t < 0.0) != (d < 0.0)) return 0;
+    if (at < ad * (1.0 - 1e-14)) return 1;
+    if (at > ad * (1.0 + 1e-14)) return 0;
+    return -1;
+}
 __device__ __forceinline__ bool line_intersect(double x0x, double x0y, double x1x, double x1y, double y0x, double y0y, double y1x, double y1y) {
     const double ux = x1x - x0x, uy = x1y - x0y, vx = y1x - y0x, vy = y1y - y0y, bx = y0x - x0x, by = y0y - x0y;
     const double d = ux * vy - uy * vx;
     if (d == 0.0) return false;
     const double t0 = bx * vy - by * vx, t1 = bx * uy - by * ux;
+    const int c0 = unit_interval_class(t0, d);
+    if (c0 == 0) return false;
+    const int c1 = unit_interval_class(t1, d);
+    if (c1 == 0) return false;
+    if (c0 == 1 && c1 == 1) return true;
     const double q0 = t0 / d, q1 = t1 / d;
     return 0.0 <= q0 && q0 <= 1.0 && 0.0 <= q1 && q1 <= 1.0;
 }
@@ -85,15 +100,35 @@ __global__ void k_exit_detection(Soa s, int n, const double *__restrict__ doors,
 }
 
 // ---- find_nearest_neighbors + herding_interaction (collective_motion.py:69-154) -----------------------------------------------
-// One thread per agent in cell order over the block list built with cell_size = sight.  The candidates of the 3x3 cells
-// are visited in ascending sorted-slot order, which is the order in which the reference's pair iteration presents them to
-// this agent, and the table is maintained with the reference's replace-the-first-maximum rule, so the rows (and therefore
-// the summation order of herding_interaction) come out identical.  `rec` doubles per neighbour record, {px, py, vx, vy} first.
-__global__ void k_herding(Soa s, int n_host, const int *n_dev, const double *__restrict__ nbr, int rec, const Grid *grid,
-                          const int *__restrict__ cell_sorted, const int *__restrict__ cell_start, const int *__restrict__ cell_count,
-                          const int *__restrict__ order, const double *__restrict__ obs, int n_obs, double sight, int k,
-                          const uint8_t *__restrict__ is_follower, int all_agents, double weight_position, double cos_phi,
-                          long long *__restrict__ knn_by_id, double *__restrict__ dir_by_id, uint8_t *__restrict__ has_by_id) {
+// One thread per agent in cell order over the block list built with cell_size = sight; the table is maintained with the
+// reference's replace-the-first-maximum rule (set_neighbor, :61-66).  `rec` doubles per neighbour record, {px, py, vx, vy} first.
+//   ORDERED = true  (cdb_nearest_neighbors): the candidates of the 3x3 cells are visited in ascending sorted-slot order, which
+//                    is the order in which the reference's pair iteration presents them to this agent, so the rows come out
+//                    in the reference's own slot order.
+//   ORDERED = false (the herding step): the block list is built with FINE cells (about the radius expected to hold 3k agents,
+//                    chosen by the host from the crowd density; cell_size <= sight).  The search first looks inside a radius
+//                    `cap` estimated from the local occupancy -- own cell first, then the surrounding cells, each skipped when
+//                    its nearest point is not closer than the current k-th best -- and only if fewer than k visible
+//                    neighbours turn up inside `cap` repeats out to `sight`.  Lines of sight are only tested when some wall
+//                    comes within the search radius of the agent.  The result is the same SET of neighbours (the k nearest
+//                    visible ones within sight); only the summation order of herding_interaction differs (<= 1e-15).
+//                    `exact_cells` = 0 (clamped / fixed lattice, cell_size == sight: cell rectangles are not reliable)
+//                    disables the pruning.
+__device__ __forceinline__ bool segment_within(double px, double py, const double *__restrict__ seg, double r) {
+    const double ax = seg[0], ay = seg[1], dx = seg[2] - ax, dy = seg[3] - ay;
+    const double len2 = dx * dx + dy * dy;
+    double tt = len2 > 0.0 ? ((px - ax) * dx + (py - ay) * dy) / len2 : 0.0;
+    tt = fmin(fmax(tt, 0.0), 1.0);
+    const double qx = ax + tt * dx - px, qy = ay + tt * dy - py;
+    return !(qx * qx + qy * qy > r * r * (1.0 + 1e-9));     // NaNs count as "within"
+}
+
+template <bool ORDERED>
+__global__ void k_herding(Soa s, int n_host, const int *n_dev, const double *__restrict__ nbr, int rec, const Grid *grid, double cell_size,
+                          int exact_cells, const int *__restrict__ cell_sorted, const int *__restrict__ cell_start,
+                          const int *__restrict__ cell_count, const int *__restrict__ order, const double *__restrict__ obs, int n_obs,
+                          double sight, int k, const uint8_t *__restrict__ is_follower, int all_agents, double weight_position,
+                          double cos_phi, long long *__restrict__ knn_by_id, double *__restrict__ dir_by_id, uint8_t *__restrict__ has_by_id) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= eff_n(n_host, n_dev)) return;
     const int slot = order[t], id = s.id[slot];
@@ -104,34 +139,112 @@ __global__ void k_herding(Soa s, int n_host, const int *n_dev, const double *__r
     }
     double dist[KNN_MAX];
     int nb[KNN_MAX];
-    for (int q = 0; q < k; ++q) { dist[q] = sight; nb[q] = -1; }
-    double dmax = sight, dmax2 = sight * sight * (1.0 + 1e-9);
+    double dmax, dmax2;
+    auto init_table = [&](double cap) {
+        for (int q = 0; q < k; ++q) { dist[q] = cap; nb[q] = -1; }
+        dmax = cap; dmax2 = cap * cap * (1.0 + 1e-9);
+    };
+    init_table(sight);
     const double2 mp = __ldg(reinterpret_cast<const double2 *>(nbr + (size_t)t * rec));
     const int ny = (int)grid->ny, nxg = (int)grid->nx;
     const int c = cell_sorted[t];
     const int cx = c / ny, cy = c - cx * ny;
-    const int ylo = cy > 0 ? cy - 1 : 0, yhi = cy + 1 < ny ? cy + 1 : ny - 1;
-    for (int dx = -1; dx <= 1; ++dx) {
-        const int x2 = cx + dx;
-        if (x2 < 0 || x2 >= nxg) continue;
-        const int b = cell_start[x2 * ny + ylo], e = cell_start[x2 * ny + yhi] + cell_count[x2 * ny + yhi];
-        for (int u = b; u < e; ++u) {
-            if (u == t) continue;
-            const double2 op = __ldg(reinterpret_cast<const double2 *>(nbr + (size_t)u * rec));
-            const double rx = mp.x - op.x, ry = mp.y - op.y;
-            if (rx * rx + ry * ry > dmax2) continue;       // conservative prefilter, the exact test follows
-            const double l = hypot(rx, ry);
-            if (!(l < dmax)) continue;
-            // line of sight in the reference's pair orientation (i = the agent that comes first in cell order)
-            const bool me_first = t < u;
-            if (is_obstacle_between_points(me_first ? mp.x : op.x, me_first ? mp.y : op.y, me_first ? op.x : mp.x, me_first ? op.y : mp.y, obs, n_obs))
-                continue;
-            int arg = 0;                                   // set_neighbor (:61-66): np.argmax = first maximum
-            for (int q = 1; q < k; ++q) if (dist[q] > dist[arg]) arg = q;
-            nb[arg] = u; dist[arg] = l;
-            dmax = dist[0];
-            for (int q = 1; q < k; ++q) dmax = fmax(dmax, dist[q]);
-            dmax2 = dmax * dmax * (1.0 + 1e-9);
+    const double mcx = floor(mp.x / sight), mcy = floor(mp.y / sight);
+    bool walls = n_obs > 0;
+
+    auto sweep = [&](int b, int e) {
+        for (int u0 = b; u0 < e; u0 += 4) {
+            double2 cp[4];
+            bool near[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {                  // four independent loads + squared distances in flight
+                const int u = u0 + j < e ? u0 + j : e - 1;
+                cp[j] = __ldg(reinterpret_cast<const double2 *>(nbr + (size_t)u * rec));
+                const double rx = mp.x - cp[j].x, ry = mp.y - cp[j].y;
+                near[j] = u0 + j < e && u != t && !(rx * rx + ry * ry > dmax2);   // conservative against the current radius
+            }
+            if (!(near[0] || near[1] || near[2] || near[3])) continue;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {                  // in slot order, with the exact tests
+                if (!near[j]) continue;
+                const int u = u0 + j;
+                const double2 op = cp[j];
+                const double l = hypot(mp.x - op.x, mp.y - op.y);
+                if (!(l < dmax)) continue;
+                if (walls) {
+                    // line of sight in the reference's pair orientation: i = the agent that comes first in the order
+                    // (cell_x, cell_y, agent index) of the block list with cell_size = sight
+                    bool me_first = t < u;
+                    if (!ORDERED) {
+                        const double ocx = floor(op.x / sight), ocy = floor(op.y / sight);
+                        me_first = mcx != ocx ? mcx < ocx : (mcy != ocy ? mcy < ocy : id < s.id[order[u]]);
+                    }
+                    if (is_obstacle_between_points(me_first ? mp.x : op.x, me_first ? mp.y : op.y, me_first ? op.x : mp.x, me_first ? op.y : mp.y, obs, n_obs))
+                        continue;
+                }
+                int arg = 0;                               // set_neighbor (:61-66): np.argmax = first maximum
+                for (int q = 1; q < k; ++q) if (dist[q] > dist[arg]) arg = q;
+                nb[arg] = u; dist[arg] = l;
+                dmax = dist[0];
+                for (int q = 1; q < k; ++q) dmax = fmax(dmax, dist[q]);
+                dmax2 = dmax * dmax * (1.0 + 1e-9);
+            }
+        }
+    };
+
+    if (ORDERED) {
+        const int ylo = cy > 0 ? cy - 1 : 0, yhi = cy + 1 < ny ? cy + 1 : ny - 1;
+        for (int dx = -1; dx <= 1; ++dx) {
+            const int x2 = cx + dx;
+            if (x2 < 0 || x2 >= nxg) continue;
+            sweep(cell_start[x2 * ny + ylo], cell_start[x2 * ny + yhi] + cell_count[x2 * ny + yhi]);
+        }
+    } else {
+        // distances from this agent to the four edges of its cell (>= 0 up to rounding, hence the slack below)
+        const double cs = cell_size;
+        const double x0 = (double)(grid->ix_min + cx) * cs, y0 = (double)(grid->iy_min + cy) * cs;
+        const double gxm = mp.x - x0, gxp = x0 + cs - mp.x, gym = mp.y - y0, gyp = y0 + cs - mp.y;
+        const double slack = 1e-9 * (1.0 + fabs(mp.x) + fabs(mp.y));
+        double cap = sight;
+        if (exact_cells) {      // radius expected to hold ~3k agents, from the occupancy of the 3x3 cells around this one
+            int cnt9 = 0;
+            for (int dx = -1; dx <= 1; ++dx)
+                for (int dy = -1; dy <= 1; ++dy) {
+                    const int x2 = cx + dx, y2 = cy + dy;
+                    if (x2 >= 0 && x2 < nxg && y2 >= 0 && y2 < ny) cnt9 += cell_count[x2 * ny + y2];
+                }
+            const double r0 = sqrt(3.0 * (double)k * 9.0 * cs * cs / (3.141592653589793 * (double)max(cnt9, 1)));
+            if (r0 < sight) cap = r0;
+        }
+#pragma unroll 1
+        for (int attempt = 0; attempt < 2; ++attempt) {
+            init_table(cap);
+            walls = false;      // can any wall cut a line of sight shorter than cap?
+            for (int w = 0; w < n_obs && !walls; ++w) walls = segment_within(mp.x, mp.y, obs + (size_t)w * SEG, cap + slack);
+            const int hw = (int)ceil(cap / cs);    // every point closer than cap lies within hw cells of the own one
+            sweep(cell_start[c], cell_start[c] + cell_count[c]);
+#pragma unroll 1
+            for (int dx = -hw; dx <= hw; ++dx) {
+                const int x2 = cx + dx;
+                if (x2 < 0 || x2 >= nxg) continue;
+                const double gx = dx < 0 ? gxm + (double)(-dx - 1) * cs : dx > 0 ? gxp + (double)(dx - 1) * cs : 0.0;
+                const double gx0 = fmax(gx, 0.0);
+#pragma unroll 1
+                for (int dy = -hw; dy <= hw; ++dy) {
+                    const int y2 = cy + dy;
+                    if ((dx == 0 && dy == 0) || y2 < 0 || y2 >= ny) continue;
+                    if (exact_cells) {
+                        const double gy = dy < 0 ? gym + (double)(-dy - 1) * cs : dy > 0 ? gyp + (double)(dy - 1) * cs : 0.0;
+                        const double gy0 = fmax(gy, 0.0);
+                        if (sqrt(gx0 * gx0 + gy0 * gy0) - slack >= dmax) continue;   // nothing in that cell is closer than the k-th best
+                    }
+                    sweep(cell_start[x2 * ny + y2], cell_start[x2 * ny + y2] + cell_count[x2 * ny + y2]);
+                }
+            }
+            bool full = true;
+            for (int q = 0; q < k; ++q) full = full && nb[q] >= 0;
+            if (full || !(cap < sight)) break;
+            cap = sight;
         }
     }
     if (knn_by_id)
@@ -163,13 +276,34 @@ __global__ void k_herding(Soa s, int n_host, const int *n_dev, const double *__r
     dir_by_id[2 * id] = ox; dir_by_id[2 * id + 1] = oy; has_by_id[id] = has;
 }
 
+// ---- leader hash grid: leaders binned by floor(p / sight) into a power-of-two table of linked lists (collisions only add
+// candidates, which the distance test rejects), so a follower looks at the 9 buckets around its own cell instead of at all
+// leaders.  lrec[q] = {px, py, vx, vy} of leader q (q = position in the id-sorted leader list).
+__device__ __forceinline__ unsigned leader_bucket(long long ix, long long iy, int bits) {
+    const unsigned long long h = (unsigned long long)ix * 0x9E3779B97F4A7C15ULL ^ (unsigned long long)iy * 0xC2B2AE3D27D4EB4FULL;
+    return (unsigned)((h * 0xD6E8FEB86659FD93ULL) >> (64 - bits));
+}
+__global__ void k_leader_records(Soa s, const int *__restrict__ leader_ids, int n_leaders, const int *__restrict__ slot_of_id,
+                                 double *__restrict__ lrec, double sight, int *__restrict__ lhead, int *__restrict__ lnext, int bits) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n_leaders) return;
+    const int ls = slot_of_id[leader_ids[q]];
+    const double px = s(PX, ls), py = s(PY, ls);
+    lrec[4 * q] = px; lrec[4 * q + 1] = py; lrec[4 * q + 2] = s(VX, ls); lrec[4 * q + 3] = s(VY, ls);
+    if (!lhead) return;
+    const double cx = floor(px / sight), cy = floor(py / sight);
+    if (!(fabs(cx) < 4.0e18) || !(fabs(cy) < 4.0e18)) { lnext[q] = -1; return; }   // non-finite: nobody can see this leader
+    lnext[q] = atomicExch(&lhead[leader_bucket((long long)cx, (long long)cy, bits)], q);
+}
+
 // ---- leader_follower_interaction_brute + the tails of leader_follower_interaction / ..._with_herding_interaction ----------------
 // (collective_motion.py:157-289).  One thread per slot.  Leaders are visited in ascending (distance, position in the id-sorted
-// leader list); only leaders within `sight` matter (the reference `continue`s the others), so every scan prefilters on the
-// squared distance.  Reads of other agents' target go to a snapshot taken before the launch (the reference mutates in place,
+// leader list); only leaders within `sight` matter (the reference `continue`s the others), so every scan looks at the hash-grid
+// buckets around the follower (or at all leaders when there is no grid) and prefilters on the squared distance.  Reads of other agents' target go to a snapshot taken before the launch (the reference mutates in place,
 // which is the same thing as long as no agent is leader and follower at once).
 __global__ void k_leader_follower(Soa s, int n, const double *__restrict__ obs, int n_obs, const int *__restrict__ leader_ids, int n_leaders,
-                                  const int *__restrict__ slot_of_id, const long long *__restrict__ target_by_id, int n_ids,
+                                  const double *__restrict__ lrec, const int *__restrict__ lhead, const int *__restrict__ lnext, int bits,
+                                  const long long *__restrict__ target_by_id, int n_ids,
                                   const uint8_t *__restrict__ is_follower, long long *__restrict__ index_leader,
                                   const long long *__restrict__ familiar_exit, double sight, double cos_phi, double weight_position,
                                   const double *__restrict__ dir_herding, const uint8_t *__restrict__ has_direction, double weight_direction,
@@ -186,22 +320,37 @@ __global__ void k_leader_follower(Soa s, int n, const double *__restrict__ obs, 
         int behind_obstacle = 0, heading_away = 0;
         double prev_d = -1.0;
         int prev_k = -1;
+        long long cix = 0, ciy = 0;
+        bool use_grid = lhead != nullptr;
+        if (use_grid) {
+            const double cx = floor(px / sight), cy = floor(py / sight);
+            if (fabs(cx) < 4.0e18 && fabs(cy) < 4.0e18) { cix = (long long)cx; ciy = (long long)cy; } else use_grid = false;
+        }
         while (true) {
             double best_d = 0.0;
             int best_k = -1;
-            for (int q = 0; q < n_leaders; ++q) {
-                const int ls = slot_of_id[__ldg(leader_ids + q)];
-                const double dx = px - s(PX, ls), dy = py - s(PY, ls);
-                if (!(dx * dx + dy * dy <= pre)) continue;
+            auto consider = [&](int q) {
+                const double2 lp = __ldg(reinterpret_cast<const double2 *>(lrec + 4 * (size_t)q));
+                const double dx = px - lp.x, dy = py - lp.y;
+                if (!(dx * dx + dy * dy <= pre)) return;
                 const double d = hypot(dx, dy);
-                if (d > sight) continue;
-                if (!(d > prev_d || (d == prev_d && q > prev_k))) continue;        // already visited
-                if (best_k < 0 || d < best_d) { best_d = d; best_k = q; }          // ties: smaller q first
+                if (d > sight) return;
+                if (!(d > prev_d || (d == prev_d && q > prev_k))) return;          // already visited
+                if (best_k < 0 || d < best_d || (d == best_d && q < best_k)) { best_d = d; best_k = q; }   // ties: smaller q first
+            };
+            if (use_grid) {
+                for (int gy = -1; gy <= 1; ++gy)
+                    for (int gx = -1; gx <= 1; ++gx)
+                        for (int q = __ldg(lhead + leader_bucket(cix + gx, ciy + gy, bits)); q >= 0; q = __ldg(lnext + q)) consider(q);
+            } else {
+                for (int q = 0; q < n_leaders; ++q) consider(q);
             }
             if (best_k < 0) break;
             prev_d = best_d; prev_k = best_k;
-            const int j = __ldg(leader_ids + best_k), ls = slot_of_id[j];
-            const double qx = s(PX, ls), qy = s(PY, ls);
+            const int j = __ldg(leader_ids + best_k);
+            const double2 lp = __ldg(reinterpret_cast<const double2 *>(lrec + 4 * (size_t)best_k));
+            const double2 lv = __ldg(reinterpret_cast<const double2 *>(lrec + 4 * (size_t)best_k + 2));
+            const double qx = lp.x, qy = lp.y;
             if (is_obstacle_between_points(px, py, qx, qy, obs, n_obs)) {
                 const long long leader = index_leader[id];
                 if (leader != NO_LEADER && leader == j) {                          // keep following the leader we remember
@@ -212,7 +361,7 @@ __global__ void k_leader_follower(Soa s, int n, const double *__restrict__ obs, 
                 }
                 continue;
             }
-            const double ux = s(VX, ls), uy = s(VY, ls);
+            const double ux = lv.x, uy = lv.y;
             if (is_heading_away(px, py, qx, qy, vx, vy, ux, uy, cos_phi)) {
                 ++heading_away;
                 index_leader[id] = j;

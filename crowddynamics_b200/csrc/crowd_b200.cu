@@ -160,6 +160,9 @@ struct cdb_sim {
     int64_t knn_cap = 0;
     int *d_slot_of_id = nullptr, *d_leader_ids = nullptr;
     int64_t n_leaders = 0;
+    double *d_lrec = nullptr;        // {px, py, vx, vy} per leader
+    int *d_lhead = nullptr, *d_lnext = nullptr;   // leader hash grid (linked lists)
+    int64_t lhead_cap = 0;
     double *d_dir_a = nullptr, *d_direction = nullptr, *d_doors = nullptr;
     int64_t doors_cap = 0;
     bool direction_valid = false, detection_valid = false;
@@ -524,7 +527,7 @@ int cdb_destroy(cdb_sim *sim) {
     cudaFree(sim->d_is_leader); cudaFree(sim->d_is_follower); cudaFree(sim->d_has_a); cudaFree(sim->d_has_detected);
     cudaFree(sim->d_index_leader); cudaFree(sim->d_familiar_exit); cudaFree(sim->d_target_by_id); cudaFree(sim->d_detected);
     cudaFree(sim->d_knn); cudaFree(sim->d_slot_of_id); cudaFree(sim->d_leader_ids); cudaFree(sim->d_dir_a); cudaFree(sim->d_direction);
-    cudaFree(sim->d_doors);
+    cudaFree(sim->d_doors); cudaFree(sim->d_lrec); cudaFree(sim->d_lhead); cudaFree(sim->d_lnext);
     cudaFree(sim->d_nav); cudaFree(sim->d_vmax); cudaFree(sim->d_dt); cudaFree(sim->d_dt_log); cudaFreeHost(sim->h_dt);
     for (auto e : sim->ev_pool) cudaEventDestroy(e);
     if (sim->graph_exec) cudaGraphExecDestroy(sim->graph_exec);
@@ -1162,6 +1165,7 @@ int ensure_states(cdb_sim *sim, int64_t n) {
     CKS(dev_alloc(&sim->d_target_by_id, cap)); CKS(dev_alloc(&sim->d_detected, cap));
     CKS(dev_alloc(&sim->d_slot_of_id, cap)); CKS(dev_alloc(&sim->d_leader_ids, cap));
     CKS(dev_alloc(&sim->d_dir_a, 2 * cap)); CKS(dev_alloc(&sim->d_direction, 2 * cap));
+    CKS(dev_alloc(&sim->d_lrec, 4 * cap)); CKS(dev_alloc(&sim->d_lnext, cap));
     CK(cudaMemset(sim->d_is_leader, 0, cap)); CK(cudaMemset(sim->d_is_follower, 0, cap));
     CK(cudaMemset(sim->d_index_leader, 0xff, cap * sizeof(long long))); CK(cudaMemset(sim->d_familiar_exit, 0xff, cap * sizeof(long long)));
     sim->states_cap = (int64_t)cap;
@@ -1178,10 +1182,24 @@ int collective_entry(cdb_sim *sim, bool need_states) {
 
 int launch_leader_follower(cdb_sim *sim, double sight, double phi, double w_leader, bool with_herding, double w_direction) {
     const int n = (int)sim->n;
+    const int L = (int)sim->n_leaders;
     LAUNCH(sim, k_slot_map, cdiv(n, 256), 256, 0, sim->cur, n, sim->d_slot_of_id, sim->d_target_by_id);
-    LAUNCH(sim, k_leader_follower, cdiv(n, 128), 128, 0, sim->cur, n, sim->d_obstacles, (int)sim->n_obstacles, sim->d_leader_ids, (int)sim->n_leaders,
-           sim->d_slot_of_id, sim->d_target_by_id, n, sim->d_is_follower, sim->d_index_leader, sim->d_familiar_exit, sight, std::cos(phi), w_leader,
-           with_herding ? sim->d_dir_a : nullptr, with_herding ? sim->d_has_a : nullptr, w_direction, sim->d_direction);
+    // hash grid over the leaders when there are enough of them to make the all-leaders scan expensive
+    int bits = 0;
+    const bool grid = L > 32 && sight > 0.0 && std::isfinite(sight);
+    if (grid) {
+        bits = 10;
+        while ((1LL << bits) < 4LL * L && bits < 26) ++bits;
+        if ((1LL << bits) > sim->lhead_cap) { CKS(dev_alloc(&sim->d_lhead, (size_t)1 << bits)); sim->lhead_cap = 1LL << bits; }
+        CK(cudaMemsetAsync(sim->d_lhead, 0xff, sizeof(int) << bits, sim->stream));
+    }
+    if (L > 0)
+        LAUNCH(sim, k_leader_records, cdiv(L, 128), 128, 0, sim->cur, sim->d_leader_ids, L, sim->d_slot_of_id, sim->d_lrec, sight,
+               grid ? sim->d_lhead : nullptr, sim->d_lnext, bits);
+    LAUNCH(sim, k_leader_follower, cdiv(n, 128), 128, 0, sim->cur, n, sim->d_obstacles, (int)sim->n_obstacles, sim->d_leader_ids, L,
+           sim->d_lrec, grid ? sim->d_lhead : nullptr, sim->d_lnext, bits, sim->d_target_by_id, n, sim->d_is_follower, sim->d_index_leader,
+           sim->d_familiar_exit, sight, std::cos(phi), w_leader, with_herding ? sim->d_dir_a : nullptr, with_herding ? sim->d_has_a : nullptr,
+           w_direction, sim->d_direction);
     CK(cudaGetLastError());
     sim->direction_valid = true;
     sim->state_version++;
@@ -1189,15 +1207,38 @@ int launch_leader_follower(cdb_sim *sim, double sight, double phi, double w_lead
 }
 
 int launch_herding(cdb_sim *sim, double sight, int64_t k, bool all_agents, double w_position, double phi, bool with_direction) {
-    CKS(build_block_list(sim, sight, false, nullptr, false));
+    if (!(sight > 0.0) || !std::isfinite(sight)) return fail(CDB_ERR_INVALID_VALUE, "sight must be > 0");
+    double cell = sight;      // the reference's block list (collective_motion.py:262-267)
+    if (!all_agents && !sim->lattice_fixed && sim->n > 0) {
+        // the herding step searches fine cells: about the radius expected to hold 3k agents at the crowd's mean density
+        LAUNCH(sim, k_bbox_init, 1, 32, 0, sim->d_bbox);
+        LAUNCH(sim, k_bbox, (cdiv(sim->n, 1024) < 1184 ? cdiv(sim->n, 1024) : 1184), 256, 0, sim->cur, (int)sim->n, sight, sim->d_bbox, sim->d_error);
+        CK(cudaMemcpyAsync(sim->h_bbox, sim->d_bbox, 4 * sizeof(long long), cudaMemcpyDeviceToHost, sim->stream));
+        CK(cudaStreamSynchronize(sim->stream));
+        CKS(check_device_error(sim));
+        const double area = (double)(sim->h_bbox[1] - sim->h_bbox[0] + 1) * (double)(sim->h_bbox[3] - sim->h_bbox[2] + 1) * sight * sight;
+        const double r0 = std::sqrt(3.0 * (double)k * area / (3.141592653589793 * (double)sim->n));
+        if (std::isfinite(r0)) cell = std::min(sight, std::max(r0, sight / 16.0));
+    }
+    CKS(build_block_list(sim, cell, false, nullptr, false));
     sim->auto_lattice_valid = false;     // the step kernel's padded lattice was replaced by this one
     const int64_t live = sim->n_sorted;
     if ((int64_t)live * k > sim->knn_cap) { CKS(dev_alloc(&sim->d_knn, (size_t)(live * k))); sim->knn_cap = live * k; }
     const int rec = sim->model == CDB_MODEL_CIRCULAR ? REC_CIRC : REC_THREE;
-    if (live > 0)
-        LAUNCH(sim, k_herding, cdiv(live, 128), 128, 0, sim->cur, (int)live, (const int *)nullptr, sim->d_nbr, rec, sim->d_grid, sim->d_cell_of_slot, sim->d_cell_start,
-               sim->d_cell_count, sim->d_order, sim->d_obstacles, (int)sim->n_obstacles, sight, (int)k, sim->d_is_follower, all_agents ? 1 : 0, w_position,
-               std::cos(phi), sim->d_knn, with_direction ? sim->d_dir_a : nullptr, with_direction ? sim->d_has_a : nullptr);
+    if (live > 0) {
+        // all_agents (cdb_nearest_neighbors): rows in the reference's slot order; the herding step: the pruned search
+        const int exact_cells = sim->lattice_fixed ? 0 : 1;
+        if (all_agents)
+            LAUNCH(sim, k_herding<true>, cdiv(live, 128), 128, 0, sim->cur, (int)live, (const int *)nullptr, sim->d_nbr, rec, sim->d_grid, sight, exact_cells,
+                   sim->d_cell_of_slot, sim->d_cell_start, sim->d_cell_count, sim->d_order, sim->d_obstacles, (int)sim->n_obstacles, sight, (int)k,
+                   sim->d_is_follower, 1, w_position, std::cos(phi), sim->d_knn, with_direction ? sim->d_dir_a : nullptr,
+                   with_direction ? sim->d_has_a : nullptr);
+        else
+            LAUNCH(sim, k_herding<false>, cdiv(live, 128), 128, 0, sim->cur, (int)live, (const int *)nullptr, sim->d_nbr, rec, sim->d_grid, cell, exact_cells,
+                   sim->d_cell_of_slot, sim->d_cell_start, sim->d_cell_count, sim->d_order, sim->d_obstacles, (int)sim->n_obstacles, sight, (int)k,
+                   sim->d_is_follower, 0, w_position, std::cos(phi), sim->d_knn, with_direction ? sim->d_dir_a : nullptr,
+                   with_direction ? sim->d_has_a : nullptr);
+    }
     CK(cudaGetLastError());
     sim->state_version++;
     return CDB_OK;

@@ -15,12 +15,17 @@ from crowddynamics_b200.engine import DeviceAgents  # noqa: E402
 from crowddynamics_b200.structures import model_of  # noqa: E402
 
 
-def timed(fn, sync, reps=5, warm=2):
+def timed(fn, sync, reps=5, warm=2, prep=None):
     for _ in range(warm):
+        if prep:
+            prep()
         fn()
     sync()
     ts = []
     for _ in range(reps):
+        if prep:
+            prep()
+            sync()
         t = time.perf_counter()
         fn()
         sync()
@@ -49,9 +54,10 @@ def main():
     reset_states()
     out['gpu_ms']['exit_detection'] = timed(lambda: dev.exit_detection(doors, 20.0, apply=False), dev.synchronize)
     out['gpu_ms']['leader_follower_with_herding(sight=10,k=5)'] = timed(
-        lambda: (reset_states(), dev.leader_follower_with_herding(10.0, 5)), dev.synchronize)
-    out['gpu_ms']['leader_follower(sight=20)'] = timed(lambda: (reset_states(), dev.leader_follower(20.0)), dev.synchronize)
-    out['gpu_ms']['set_states (H2D, included in the two lines above)'] = timed(reset_states, dev.synchronize)
+        lambda: dev.leader_follower_with_herding(10.0, 5), dev.synchronize, prep=reset_states)
+    out['gpu_ms']['leader_follower(sight=20)'] = timed(lambda: dev.leader_follower(20.0), dev.synchronize, prep=reset_states)
+    out['gpu_ms']['nearest_neighbors(sight=10,k=5) incl. D2H of the table'] = timed(lambda: dev.nearest_neighbors(10.0, 5), dev.synchronize)
+    out['gpu_ms']['set_states (pageable H2D of the five States arrays, not in the lines above)'] = timed(reset_states, dev.synchronize)
     out['gpu_agents_per_s'] = {k: n / (v * 1e-3) for k, v in out['gpu_ms'].items()}
 
     from oracle import crowd_oracle as O

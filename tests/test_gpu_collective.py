@@ -55,8 +55,11 @@ def test_golden_functions(model):
 
 @pytest.mark.parametrize('model,n,density,seed,k,sight', [
     ('circular', 20000, 0.5, 1, 5, 10.0), ('three_circle', 12000, 1.0, 2, 8, 6.0), ('circular', 3000, 0.05, 3, 1, 25.0),
-    ('circular', 5000, 2.0, 4, 32, 4.0)])
+    ('circular', 5000, 2.0, 4, 32, 4.0), ('circular', 60000, 1.0, 6, 5, 10.0), ('three_circle', 30000, 2.5, 7, 3, 10.0)])
 def test_functions_against_oracle(model, n, density, seed, k, sight):
+    # (densities stay below 2.78 /m^2, where the synthetic lattice still gets a random jitter: on an exact lattice the k-th
+    # neighbour distance is tied many times over and WHICH of the tied agents is kept depends on the visiting order, which
+    # the herding step does not share with the reference -- cdb_nearest_neighbors does)
     agents, obstacles, doors, side = S.leader_follower_crowd(n, model, density=density, seed=seed, n_doors=3)
     nbr = CM.find_nearest_neighbors(agents.copy(), sight, k, obstacles)
     assert (nbr == O.find_nearest_neighbors(agents, sight, k, obstacles)).all()
