@@ -25,6 +25,7 @@ STEP_NAVIGATION, STEP_ORIENTATION, STEP_ADJUSTING, STEP_AGENT_AGENT, STEP_AGENT_
 STEP_ALL = (1 << 7) - 1
 STEP_FLUCTUATION = 1 << 7
 KNN_MAX = 32
+POLY_DOMAIN, POLY_TARGETS = 0, 1
 
 _lib = None
 
@@ -97,6 +98,12 @@ def _signatures(L):
         'cdb_leader_follower': (i32, [vp, f64, f64, f64]),
         'cdb_leader_follower_with_herding': (i32, [vp, f64, i64, f64, f64, f64, f64]),
         'cdb_get_direction': (i32, [vp, vp, i64]),
+        'cdb_set_polygons': (i32, [vp, i32, vp, vp, i64]),
+        'cdb_set_active': (i32, [vp, vp, i64]),
+        'cdb_get_active': (i32, [vp, vp, i64]),
+        'cdb_inside_domain': (i32, [vp, pi64]),
+        'cdb_target_reached': (i32, [vp, vp, i64]),
+        'cdb_get_target_reached': (i32, [vp, vp, i64, i64]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)

@@ -390,3 +390,56 @@ __global__ void k_leader_follower(Soa s, int n, const double *__restrict__ obs, 
     direction_by_id[2 * id] = ox; direction_by_id[2 * id + 1] = oy;
     if (follower) { s(E0X, t) = ox; s(E0Y, t) = oy; }                              // logic.py:181-182, 220-221
 }
+
+// =====================================================================================================================
+// InsideDomain / TargetReached (reference simulation/logic.py:343-387), i.e.
+// matplotlib.path.Path.contains_points with radius 0 -- crossing-number rule, see oracle_point_in_polygon.  Polygons are
+// stored back to back as (x, y) pairs with an offsets table (n_polygons + 1 entries, in vertices), implicitly closed.
+// =====================================================================================================================
+__device__ __forceinline__ bool point_in_polygon(const double *__restrict__ v, int nv, double tx, double ty) {
+    if (nv < 3) return false;
+    bool inside = false;
+    double vx0 = __ldg(v + 2 * (nv - 1)), vy0 = __ldg(v + 2 * (nv - 1) + 1);
+    bool yflag0 = vy0 >= ty;
+    for (int k = 0; k < nv; ++k) {
+        const double vx1 = __ldg(v + 2 * k), vy1 = __ldg(v + 2 * k + 1);
+        const bool yflag1 = vy1 >= ty;
+        if (yflag0 != yflag1)
+            if (((vy1 - ty) * (vx0 - vx1) >= (vx1 - tx) * (vy0 - vy1)) == yflag1) inside = !inside;
+        yflag0 = yflag1; vx0 = vx1; vy0 = vy1;
+    }
+    return inside;
+}
+
+// InsideDomain.update: active[id] = contains(position); counter[0] += number of flags that changed
+__global__ void k_inside_domain(Soa s, int n, const double *__restrict__ verts, int nv, uint8_t *__restrict__ active_by_id,
+                                unsigned long long *counter) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    bool changed = false;
+    if (t < n && s.id[t] >= 0) {
+        const int id = s.id[t];
+        const bool now = point_in_polygon(verts, nv, s(PX, t), s(PY, t));
+        changed = (active_by_id[id] != 0) != now;
+        active_by_id[id] = now;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, changed);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(counter, (unsigned long long)__popc(m));
+}
+
+// TargetReached.update: reached[p][id] |= contains_p(position); counts[p] = number of agents that ever reached polygon p
+__global__ void k_target_reached(Soa s, int n, const double *__restrict__ verts, const int *__restrict__ offsets, int n_polygons,
+                                 uint8_t *__restrict__ reached, long long stride, unsigned long long *counts) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = t < n && s.id[t] >= 0;
+    const int id = live ? s.id[t] : 0;
+    const double px = live ? s(PX, t) : 0.0, py = live ? s(PY, t) : 0.0;
+    for (int p = 0; p < n_polygons; ++p) {
+        bool fresh = false;
+        if (live && !reached[(size_t)p * stride + id]) {
+            const int b = offsets[p], e = offsets[p + 1];
+            if (point_in_polygon(verts + 2 * (size_t)b, e - b, px, py)) { reached[(size_t)p * stride + id] = 1; fresh = true; }
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, fresh);
+        if ((threadIdx.x & 31) == 0 && m) atomicAdd(&counts[p], (unsigned long long)__popc(m));
+    }
+}

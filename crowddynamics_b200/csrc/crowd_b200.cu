@@ -166,6 +166,14 @@ struct cdb_sim {
     double *d_dir_a = nullptr, *d_direction = nullptr, *d_doors = nullptr;
     int64_t doors_cap = 0;
     bool direction_valid = false, detection_valid = false;
+    // host-visible state nodes (rank 3): polygons [0] domain, [1] targets; flags by original agent index
+    double *d_poly_xy[2] = {nullptr, nullptr};
+    int *d_poly_off[2] = {nullptr, nullptr};
+    int64_t n_polygons[2] = {0, 0};
+    int64_t poly_nv[2] = {0, 0};     // vertices in total
+    uint8_t *d_active = nullptr, *d_reached = nullptr;
+    int64_t active_n = 0, reached_cap = 0, reached_n = 0;
+    unsigned long long *d_poly_counts = nullptr;     // [0] InsideDomain changes of the last call, [1 + p] reached counts
 
     // instrumentation: kernel launch counter and CUDA-event timing of the step phases
     int64_t launches = 0;
@@ -527,6 +535,8 @@ int cdb_destroy(cdb_sim *sim) {
     cudaFree(sim->d_is_leader); cudaFree(sim->d_is_follower); cudaFree(sim->d_has_a); cudaFree(sim->d_has_detected);
     cudaFree(sim->d_index_leader); cudaFree(sim->d_familiar_exit); cudaFree(sim->d_target_by_id); cudaFree(sim->d_detected);
     cudaFree(sim->d_knn); cudaFree(sim->d_slot_of_id); cudaFree(sim->d_leader_ids); cudaFree(sim->d_dir_a); cudaFree(sim->d_direction);
+    cudaFree(sim->d_poly_xy[0]); cudaFree(sim->d_poly_xy[1]); cudaFree(sim->d_poly_off[0]); cudaFree(sim->d_poly_off[1]);
+    cudaFree(sim->d_active); cudaFree(sim->d_reached); cudaFree(sim->d_poly_counts);
     cudaFree(sim->d_doors); cudaFree(sim->d_lrec); cudaFree(sim->d_lhead); cudaFree(sim->d_lnext);
     cudaFree(sim->d_nav); cudaFree(sim->d_vmax); cudaFree(sim->d_dt); cudaFree(sim->d_dt_log); cudaFreeHost(sim->h_dt);
     for (auto e : sim->ev_pool) cudaEventDestroy(e);
@@ -1349,5 +1359,115 @@ int cdb_get_direction(cdb_sim *sim, double *direction, int64_t n) {
     if (!sim->direction_valid || n != sim->n) return fail(CDB_ERR_STATE, "no direction computed for these %lld agents", (long long)sim->n);
     CK(cudaStreamSynchronize(sim->stream));
     if (n && direction) CK(cudaMemcpy(direction, sim->d_direction, 2 * n * sizeof(double), cudaMemcpyDeviceToHost));
+    return CDB_OK;
+}
+
+
+// =====================================================================================================================
+// host-visible state nodes
+// =====================================================================================================================
+constexpr int MAX_POLYGONS = 1024;
+int cdb_set_polygons(cdb_sim *sim, int which, const double *xy, const int64_t *offsets, int64_t n_polygons) {
+    SIM_ENTRY();
+    if (which != CDB_POLY_DOMAIN && which != CDB_POLY_TARGETS) return fail(CDB_ERR_INVALID_VALUE, "which must be CDB_POLY_DOMAIN or CDB_POLY_TARGETS");
+    if (n_polygons < 0 || (n_polygons > 0 && (!xy || !offsets))) return fail(CDB_ERR_INVALID_VALUE, "bad polygon buffers");
+    if (which == CDB_POLY_DOMAIN && n_polygons > 1) return fail(CDB_ERR_INVALID_VALUE, "the domain is one polygon");
+    if (n_polygons > MAX_POLYGONS) return fail(CDB_ERR_CAPACITY, "at most %d target polygons", MAX_POLYGONS);
+    std::vector<int> off((size_t)n_polygons + 1, 0);
+    for (int64_t p = 0; p <= n_polygons && n_polygons > 0; ++p) {
+        if (offsets[p] < 0 || offsets[p] > 0x7fffffff || (p > 0 && offsets[p] < offsets[p - 1]) || (p == 0 && offsets[0] != 0))
+            return fail(CDB_ERR_INVALID_VALUE, "polygon offsets must start at 0 and be non-decreasing");
+        off[(size_t)p] = (int)offsets[p];
+    }
+    const int64_t nv = n_polygons > 0 ? offsets[n_polygons] : 0;
+    CK(cudaStreamSynchronize(sim->stream));
+    CKS(dev_alloc(&sim->d_poly_xy[which], (size_t)(2 * nv)));
+    CKS(dev_alloc(&sim->d_poly_off[which], (size_t)n_polygons + 1));
+    if (nv) CK(cudaMemcpy(sim->d_poly_xy[which], xy, 2 * nv * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(sim->d_poly_off[which], off.data(), off.size() * sizeof(int), cudaMemcpyHostToDevice));
+    sim->n_polygons[which] = n_polygons;
+    sim->poly_nv[which] = nv;
+    if (!sim->d_poly_counts) {
+        CKS(dev_alloc(&sim->d_poly_counts, (size_t)(1 + MAX_POLYGONS)));
+        CK(cudaMemset(sim->d_poly_counts, 0, (1 + MAX_POLYGONS) * sizeof(unsigned long long)));
+    }
+    if (which == CDB_POLY_TARGETS) {       // new targets: nobody has reached them yet
+        sim->reached_n = 0;
+        CK(cudaMemset(sim->d_poly_counts + 1, 0, MAX_POLYGONS * sizeof(unsigned long long)));
+    }
+    return CDB_OK;
+}
+
+int cdb_set_active(cdb_sim *sim, const uint8_t *active, int64_t n) {
+    SIM_ENTRY();
+    if (sim->strip) return fail(CDB_ERR_STATE, "InsideDomain is not available in strip mode");
+    if (n != sim->n || (n > 0 && !active)) return fail(CDB_ERR_INVALID_VALUE, "cdb_set_active: n = %lld but the device holds %lld agents", (long long)n, (long long)sim->n);
+    CK(cudaStreamSynchronize(sim->stream));
+    if (n > sim->active_n || !sim->d_active) CKS(dev_alloc(&sim->d_active, (size_t)std::max<int64_t>(n, 1024)));
+    if (n) CK(cudaMemcpy(sim->d_active, active, n, cudaMemcpyHostToDevice));
+    sim->active_n = n;
+    return CDB_OK;
+}
+
+int cdb_get_active(cdb_sim *sim, uint8_t *active, int64_t n) {
+    SIM_ENTRY();
+    if (!sim->d_active || n != sim->active_n || n != sim->n) return fail(CDB_ERR_STATE, "cdb_set_active must describe the %lld agents on the device first", (long long)sim->n);
+    CK(cudaStreamSynchronize(sim->stream));
+    if (n && active) CK(cudaMemcpy(active, sim->d_active, n, cudaMemcpyDeviceToHost));
+    return CDB_OK;
+}
+
+int cdb_inside_domain(cdb_sim *sim, int64_t *n_changed) {
+    SIM_ENTRY();
+    if (sim->strip) return fail(CDB_ERR_STATE, "InsideDomain is not available in strip mode");
+    if (sim->n_polygons[CDB_POLY_DOMAIN] != 1) return fail(CDB_ERR_STATE, "cdb_set_polygons(CDB_POLY_DOMAIN) must be called first");
+    if (!sim->d_active || sim->active_n != sim->n) return fail(CDB_ERR_STATE, "cdb_set_active must describe the %lld agents on the device first", (long long)sim->n);
+    CK(cudaMemsetAsync(sim->d_poly_counts, 0, sizeof(unsigned long long), sim->stream));
+    if (sim->n)
+        LAUNCH(sim, k_inside_domain, cdiv(sim->n, 128), 128, 0, sim->cur, (int)sim->n, sim->d_poly_xy[CDB_POLY_DOMAIN], (int)sim->poly_nv[CDB_POLY_DOMAIN],
+               sim->d_active, sim->d_poly_counts);
+    CK(cudaGetLastError());
+    if (n_changed) {
+        unsigned long long c = 0;
+        CK(cudaMemcpyAsync(&c, sim->d_poly_counts, sizeof(c), cudaMemcpyDeviceToHost, sim->stream));
+        CK(cudaStreamSynchronize(sim->stream));
+        *n_changed = (int64_t)c;
+    }
+    return CDB_OK;
+}
+
+int cdb_target_reached(cdb_sim *sim, int64_t *counts, int64_t n_polygons) {
+    SIM_ENTRY();
+    if (sim->strip) return fail(CDB_ERR_STATE, "TargetReached is not available in strip mode");
+    const int64_t np = sim->n_polygons[CDB_POLY_TARGETS];
+    if (n_polygons != np) return fail(CDB_ERR_INVALID_VALUE, "n_polygons = %lld but %lld target polygons are set", (long long)n_polygons, (long long)np);
+    if (np > 0 && sim->n > 0) {
+        if (sim->reached_n != sim->n || np * sim->n > sim->reached_cap) {     // first call for this crowd: nobody has arrived yet
+            if (np * sim->n > sim->reached_cap) { CKS(dev_alloc(&sim->d_reached, (size_t)(np * sim->n))); sim->reached_cap = np * sim->n; }
+            CK(cudaMemsetAsync(sim->d_reached, 0, (size_t)(np * sim->n), sim->stream));
+            CK(cudaMemsetAsync(sim->d_poly_counts + 1, 0, np * sizeof(unsigned long long), sim->stream));
+            sim->reached_n = sim->n;
+        }
+        LAUNCH(sim, k_target_reached, cdiv(sim->n, 128), 128, 0, sim->cur, (int)sim->n, sim->d_poly_xy[CDB_POLY_TARGETS], sim->d_poly_off[CDB_POLY_TARGETS], (int)np,
+               sim->d_reached, (long long)sim->n, sim->d_poly_counts + 1);
+        CK(cudaGetLastError());
+    }
+    if (counts && np > 0) {
+        std::vector<unsigned long long> c((size_t)np, 0ULL);
+        if (sim->n > 0) {
+            CK(cudaMemcpyAsync(c.data(), sim->d_poly_counts + 1, np * sizeof(unsigned long long), cudaMemcpyDeviceToHost, sim->stream));
+            CK(cudaStreamSynchronize(sim->stream));
+        }
+        for (int64_t p = 0; p < np; ++p) counts[p] = (int64_t)c[(size_t)p];
+    }
+    return CDB_OK;
+}
+
+int cdb_get_target_reached(cdb_sim *sim, uint8_t *reached_by, int64_t n_polygons, int64_t n) {
+    SIM_ENTRY();
+    if (n_polygons != sim->n_polygons[CDB_POLY_TARGETS] || n != sim->n || sim->reached_n != sim->n)
+        return fail(CDB_ERR_STATE, "cdb_target_reached must run first (on the same agents and polygons)");
+    CK(cudaStreamSynchronize(sim->stream));
+    if (n_polygons * n > 0 && reached_by) CK(cudaMemcpy(reached_by, sim->d_reached, (size_t)(n_polygons * n), cudaMemcpyDeviceToHost));
     return CDB_OK;
 }

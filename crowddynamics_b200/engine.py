@@ -242,6 +242,45 @@ class DeviceAgents:
         _lib.check(self.lib.cdb_get_direction(self.handle, _ptr(out) if self.n else None, self.n))
         return out
 
+    # -- host-visible state nodes ------------------------------------------------------------------------
+    def set_polygons(self, which, polygons):
+        """polygons: list of (nv, 2) vertex arrays (a repeated closing vertex, as in shapely's exterior, is dropped)."""
+        polys = []
+        for v in polygons:
+            v = np.ascontiguousarray(v, dtype=np.float64).reshape(-1, 2)
+            if len(v) > 1 and (v[0] == v[-1]).all():
+                v = v[:-1]
+            polys.append(v)
+        offsets = np.zeros(len(polys) + 1, dtype=np.int64)
+        offsets[1:] = np.cumsum([len(v) for v in polys])
+        xy = np.ascontiguousarray(np.concatenate(polys)) if polys else np.zeros((0, 2))
+        _lib.check(self.lib.cdb_set_polygons(self.handle, int(which), _ptr(xy) if len(xy) else None,
+                                             _ptr(offsets) if polys else None, len(polys)))
+
+    def set_active(self, active):
+        a = np.ascontiguousarray(active).view(np.uint8)
+        _lib.check(self.lib.cdb_set_active(self.handle, _ptr(a) if len(a) else None, len(a)))
+
+    def get_active(self):
+        out = np.zeros(self.n, dtype=np.uint8)
+        _lib.check(self.lib.cdb_get_active(self.handle, _ptr(out) if self.n else None, self.n))
+        return out.astype(bool)
+
+    def inside_domain(self, want_count=True):
+        c = C.c_int64(0)
+        _lib.check(self.lib.cdb_inside_domain(self.handle, C.byref(c) if want_count else None))
+        return c.value if want_count else None
+
+    def target_reached(self, n_polygons, want_counts=True):
+        counts = np.zeros(int(n_polygons), dtype=np.int64)
+        _lib.check(self.lib.cdb_target_reached(self.handle, _ptr(counts) if want_counts and n_polygons else None, int(n_polygons)))
+        return counts if want_counts else None
+
+    def target_reached_by(self, n_polygons):
+        out = np.zeros((int(n_polygons), self.n), dtype=np.uint8)
+        _lib.check(self.lib.cdb_get_target_reached(self.handle, _ptr(out) if out.size else None, int(n_polygons), self.n))
+        return out.astype(bool)
+
     def set_lattice(self, ix_min, iy_min, nx, ny):
         _lib.check(self.lib.cdb_set_lattice(self.handle, int(ix_min), int(iy_min), int(nx), int(ny)))
 

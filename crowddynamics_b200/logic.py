@@ -130,6 +130,8 @@ class DeviceState:
         self._nav_key = None
         self.dirty_host = False     # device is ahead of the host array (resident mode)
         self.dirty_states = False   # ... and of its States fields target / is_follower / index_leader
+        self.dirty_active = False   # ... and of States.active
+        self._active_id = None
         self._states_id = None
 
     @classmethod
@@ -195,12 +197,16 @@ class DeviceState:
         if self.dev is not None and self.dirty_states:
             self.dev.get_states(self.agents)
             self.dirty_states = False
+        if self.dev is not None and self.dirty_active:
+            self.agents['active'] = self.dev.get_active()
+            self.dirty_active = False
 
     def invalidate(self):
         """Resident mode: the host array was modified by a host-side node; re-upload at the next node."""
         self.sync_host()
         self._host_id = None
         self._states_id = None
+        self._active_id = None
 
     # -- geometry / fields -------------------------------------------------------------------------------------------
     def ensure_obstacles(self):
@@ -384,6 +390,74 @@ class LeaderFollowerWithHerding(LogicNode):
         self.state.end(_lib.F_TARGET_DIRECTION, states=True)
 
 
+def _exterior(geom):
+    """Vertices of a polygon given as an (nv, 2) array or as a shapely Polygon (``np.asarray(geom.exterior)``, logic.py:349)."""
+    ext = getattr(geom, 'exterior', geom)
+    coords = getattr(ext, 'coords', ext)
+    return np.asarray(coords, dtype=np.float64).reshape(-1, 2)
+
+
+class InsideDomain(LogicNode):
+    """logic.py:343-357 -- sets agents not inside the domain inactive.  ``domain``: (nv, 2) vertices or a shapely Polygon;
+    default ``simulation.field.domain``."""
+    _params = dict(domain=None)
+
+    def __init__(self, simulation, *args, **kwargs):
+        super().__init__(simulation, *args, **kwargs)
+        self.simulation.data['inactive'] = 0
+        self._vertices = _exterior(self.domain if self.domain is not None else self.simulation.field.domain)
+        self._sent_to = None
+
+    def update(self):
+        dev = self.state.begin()
+        if self._sent_to is not dev:
+            dev.set_polygons(_lib.POLY_DOMAIN, [self._vertices])
+            self._sent_to = dev
+        agents = self.state.agents
+        if self.state.mode == 'strict' or self.state._active_id != self.state._host_id:
+            dev.set_active(agents['active'])
+            self.state._active_id = self.state._host_id
+        self.simulation.data['inactive'] += dev.inside_domain()
+        if self.state.mode == 'strict':
+            agents['active'] = dev.get_active()
+        else:
+            self.state.dirty_active = True
+
+
+class TargetReached(LogicNode):
+    """logic.py:360-387 -- counts, per polygon target, the agents that have been inside it at any update so far
+    (``simulation.data['target_<i>']``).  ``polygons``: list of (nv, 2) vertex arrays / shapely Polygons, or None for an index
+    to be skipped; default ``simulation.field.targets`` (non-polygon targets are skipped, as in the reference)."""
+    prefix = 'target_{index}'
+    _params = dict(polygons=None)
+
+    def __init__(self, simulation, *args, **kwargs):
+        super().__init__(simulation, *args, **kwargs)
+        targets = self.polygons if self.polygons is not None else self.simulation.field.targets
+        self.names, self._polys = [], []
+        for i, target in enumerate(targets):
+            if target is None or not (hasattr(target, 'exterior') or isinstance(target, (np.ndarray, list, tuple))):
+                continue
+            name = self.prefix.format(index=i)
+            self.names.append(name)
+            self._polys.append(_exterior(target))
+            self.simulation.data[name] = 0
+        self._sent_to = None
+
+    @property
+    def reached_by(self):
+        """list over the measured targets of bool arrays (the reference's ``reached_by``)."""
+        return list(self.state.dev.target_reached_by(len(self._polys))) if self._sent_to is not None else []
+
+    def update(self):
+        dev = self.state.begin()
+        if self._sent_to is not dev:
+            dev.set_polygons(_lib.POLY_TARGETS, self._polys)
+            self._sent_to = dev
+        for name, count in zip(self.names, dev.target_reached(len(self._polys))):
+            self.simulation.data[name] = int(count)
+
+
 class FusedStep(LogicNode):
     """The whole replaced sub-tree in one C-ABI call per ``update()``: navigation -> orientation -> adjusting ->
     agent-agent -> agent-obstacle -> integrator -> reset (post-order of examples/simulations.py:123-136), resident on
@@ -430,18 +504,19 @@ class MultiAgentSimulation:
     class ArrayField:
         """Field given directly as arrays: obstacle segments + per-target (mgrid, (U, V))."""
 
-        def __init__(self, obstacles=None, fields=()):
+        def __init__(self, obstacles=None, fields=(), domain=None):
             self.obstacles = obstacles
             self.targets = list(range(len(fields)))
             self._fields = list(fields)
+            self.domain = domain          # (nv, 2) vertices of the domain polygon (InsideDomain)
 
         def navigation_to_target(self, target, step, radius, strength):
             mgrid, direction_map = self._fields[target]
             return mgrid, None, direction_map
 
-    def __init__(self, agents, obstacles=None, fields=(), logic=None):
+    def __init__(self, agents, obstacles=None, fields=(), logic=None, domain=None):
         self.agents = self._Agents(agents)
-        self.field = self.ArrayField(obstacles, fields)
+        self.field = self.ArrayField(obstacles, fields, domain)
         self.logic = logic
         self.data = {'iterations': 0, 'time_tot': 0.0, 'dt': 0.0}
 

@@ -212,6 +212,23 @@ int cdb_leader_follower_with_herding(cdb_sim *sim, double sight, int64_t size_ne
 /* the direction array (n x 2, all agents) the last of the two calls above computed = the reference functions' return value */
 int cdb_get_direction(cdb_sim *sim, double *direction, int64_t n);
 
+/* ---- host-visible state nodes -----------------------------------------------------------------
+ * InsideDomain / TargetReached (simulation/logic.py:343-387) = matplotlib Path(vertices).contains_points(position).
+ * Polygons: (x, y) vertex pairs back to back, offsets[n_polygons + 1] in vertices, implicitly closed (do not repeat the first
+ * vertex).  which = CDB_POLY_DOMAIN takes exactly one polygon (field.domain.exterior), CDB_POLY_TARGETS one per measured
+ * target; setting the target polygons clears their reached_by state.  Not available in strip mode. */
+#define CDB_POLY_DOMAIN 0
+#define CDB_POLY_TARGETS 1
+int cdb_set_polygons(cdb_sim *sim, int which, const double *xy, const int64_t *offsets, int64_t n_polygons);
+/* replaces: agents['active'] (simulation/agents.py:33-35) */
+int cdb_set_active(cdb_sim *sim, const uint8_t *active, int64_t n);
+int cdb_get_active(cdb_sim *sim, uint8_t *active, int64_t n);
+/* InsideDomain.update (logic.py:351-357): active = inside(domain); *n_changed (may be NULL: no host sync) = np.sum(change) */
+int cdb_inside_domain(cdb_sim *sim, int64_t *n_changed);
+/* TargetReached.update (logic.py:383-387): reached_by |= inside(target p); counts[p] (may be NULL) = np.sum(reached_by) */
+int cdb_target_reached(cdb_sim *sim, int64_t *counts, int64_t n_polygons);
+int cdb_get_target_reached(cdb_sim *sim, uint8_t *reached_by, int64_t n_polygons, int64_t n);   /* [n_polygons][n] */
+
 #ifdef __cplusplus
 }
 #endif

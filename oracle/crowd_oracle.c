@@ -820,3 +820,51 @@ int oracle_leader_follower_with_herding_interaction(void *agents, int64_t n, int
     free(neighbors); free(is_follower); free(has_direction); free(has_strategy); free(dir_herding); free(dir_leader);
     return rc;
 }
+
+/* =====================================================================================================================
+ * InsideDomain / TargetReached (simulation/logic.py:343-387).  Both rest on
+ * matplotlib.path.Path(vertices).contains_points(points) with radius 0.  matplotlib is a third-party dependency that is
+ * absent here ("parity unpinned"): this restates the crossing-number rule of its point_in_path routine (src/_path.h, after
+ * W. Randolph Franklin / Graphics Gems IV "CrossingsMultiplyTest"): an edge (v0, v1) is crossed when the flags
+ * (v0.y >= y) and (v1.y >= y) differ and the intersection with the horizontal ray lies on the +x side; the polygon is
+ * closed implicitly; the parity of the crossings decides.  Points exactly on an edge are the unpinned part.
+ * ===================================================================================================================== */
+int oracle_point_in_polygon(const double *vertices, int64_t n_vertices, double tx, double ty) {
+    if (n_vertices < 3) return 0;
+    int inside = 0;
+    double vx0 = vertices[2 * (n_vertices - 1)], vy0 = vertices[2 * (n_vertices - 1) + 1];   /* implicit closing edge first */
+    int yflag0 = vy0 >= ty;
+    for (int64_t k = 0; k < n_vertices; ++k) {
+        const double vx1 = vertices[2 * k], vy1 = vertices[2 * k + 1];
+        const int yflag1 = vy1 >= ty;
+        if (yflag0 != yflag1)
+            if (((vy1 - ty) * (vx0 - vx1) >= (vx1 - tx) * (vy0 - vy1)) == yflag1) inside ^= 1;
+        yflag0 = yflag1; vx0 = vx1; vy0 = vy1;
+    }
+    return inside;
+}
+
+/* InsideDomain.update (logic.py:351-357): active = contains(position); returns the number of agents whose flag changed */
+int64_t oracle_inside_domain(void *agents, int64_t n, int64_t itemsize, const double *vertices, int64_t n_vertices) {
+    if (itemsize != 228 && itemsize != 316) return -1;
+    int64_t changed = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        agent_circular_t *a = circ(agents, itemsize, i);
+        const uint8_t now = (uint8_t)oracle_point_in_polygon(vertices, n_vertices, a->position[0], a->position[1]);
+        changed += (a->active != 0) != (now != 0);
+        a->active = now;
+    }
+    return changed;
+}
+
+/* TargetReached.update (logic.py:383-387) for one target polygon: reached_by |= contains(position); returns sum(reached_by) */
+int64_t oracle_target_reached(const void *agents, int64_t n, int64_t itemsize, const double *vertices, int64_t n_vertices, uint8_t *reached_by) {
+    if (itemsize != 228 && itemsize != 316) return -1;
+    int64_t count = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        const agent_circular_t *a = circ((void *)agents, itemsize, i);
+        if (oracle_point_in_polygon(vertices, n_vertices, a->position[0], a->position[1])) reached_by[i] = 1;
+        count += reached_by[i] != 0;
+    }
+    return count;
+}

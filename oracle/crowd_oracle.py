@@ -66,6 +66,11 @@ def lib():
         L.oracle_leader_follower_interaction_brute.argtypes = [vp, i64, i64, f64, f64, vp, i64, f64, vp, u8p]
         L.oracle_leader_follower_interaction.argtypes = [vp, i64, i64, vp, i64, f64, f64, f64, vp]
         L.oracle_leader_follower_with_herding_interaction.argtypes = [vp, i64, i64, vp, i64, f64, i64, f64, f64, f64, f64, vp]
+        L.oracle_point_in_polygon.argtypes = [vp, i64, f64, f64]
+        L.oracle_inside_domain.restype = i64
+        L.oracle_inside_domain.argtypes = [vp, i64, i64, vp, i64]
+        L.oracle_target_reached.restype = i64
+        L.oracle_target_reached.argtypes = [vp, i64, i64, vp, i64, vp]
         _LIB = L
     return _LIB
 
@@ -278,3 +283,36 @@ def leader_follower_with_herding_interaction(agents, obstacles, sight, size_near
         p, n, sz, po, no, float(sight), int(size_nearest_other), float(phi), float(weight_position_herding),
         float(weight_position_leader), float(weight_direction_leader), out.ctypes.data))
     return out
+
+
+# ---- InsideDomain / TargetReached ----------------------------------------------------------------------
+def _poly(vertices):
+    v = np.ascontiguousarray(vertices, dtype=np.float64).reshape(-1, 2)
+    if len(v) > 1 and (v[0] == v[-1]).all():      # a closed ring (shapely exterior): the closing vertex adds nothing
+        v = np.ascontiguousarray(v[:-1])
+    return v
+
+
+def point_in_polygon(vertices, x, y):
+    v = _poly(vertices)
+    return bool(lib().oracle_point_in_polygon(v.ctypes.data, len(v), float(x), float(y)))
+
+
+def inside_domain(agents, vertices):
+    """InsideDomain.update (logic.py:351-357) -> number of agents whose ``active`` flag changed."""
+    p, n, sz = _a(agents)
+    v = _poly(vertices)
+    r = lib().oracle_inside_domain(p, n, sz, v.ctypes.data, len(v))
+    _check(r < 0)
+    return int(r)
+
+
+def target_reached(agents, vertices, reached_by):
+    """TargetReached.update (logic.py:383-387) for one polygon; ``reached_by``: bool/uint8 array updated in place."""
+    p, n, sz = _a(agents)
+    v = _poly(vertices)
+    rb = reached_by.view(np.uint8)
+    assert rb.flags.c_contiguous and len(rb) == n
+    r = lib().oracle_target_reached(p, n, sz, v.ctypes.data, len(v), rb.ctypes.data)
+    _check(r < 0)
+    return int(r)
