@@ -25,7 +25,7 @@ def test_kernels_against_oracle(model):
     ref = agents.copy()
     domain = _star(side / 2, side / 2, 0.55 * side, 0.3 * side)
     goals = [_star(side * 0.3, side * 0.3, 0.2 * side, 0.1 * side, 5), np.array([(0, 0), (side / 3, 0), (0, side / 3)]),
-             np.array([(side, side), (side + 5, side), (side + 5, side + 5)])]          # the last one holds nobody
+             np.array([(side, side), (side + 5, side), (side + 5, side + 5)])]          # outside the room: only reached after the jump
     dev = DeviceAgents(model_of(agents), capacity=len(agents))
     dev.upload(agents)
     dev.set_polygons(_lib.POLY_DOMAIN, [np.vstack((domain, domain[:1]))])             # closed ring, like shapely's exterior
@@ -52,7 +52,7 @@ def test_kernels_against_oracle(model):
                 ref['position_ls'], ref['position_rs'] = out['position_ls'], out['position_rs']
             act = dev.get_active()
             dev.upload(out); dev.set_active(act)
-    assert counts[2] == 0 and counts[0] > 0 and changed >= 0
+    assert counts[0] > 0 and counts[1] > 0
 
 
 def test_nodes_strict_and_resident():
