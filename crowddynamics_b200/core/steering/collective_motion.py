@@ -2,7 +2,6 @@
 uploaded, the kernels run, the States fields they mutate are written back)."""
 import numpy as np
 
-from ..._lib import F_TARGET_DIRECTION  # noqa: F401  (kept for symmetry with the node classes)
 from ...engine import device_agents_for
 
 MISSING_NEIGHBOR = -1

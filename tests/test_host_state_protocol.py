@@ -1,0 +1,130 @@
+"""Host logic of the drop-in nodes without a GPU: which transfers ``DeviceState`` issues in strict and resident mode
+(strict = upload -> kernel -> download of what the node writes; resident = upload once, refresh on demand).
+``DeviceAgents`` is replaced by a recorder, so no library call is made -- this checks the protocol, not the kernels."""
+import numpy as np
+import pytest
+
+from crowddynamics_b200 import synthetic as S, logic as L, _lib
+
+
+class Recorder:
+    """Stands in for engine.DeviceAgents: records the calls, returns plausible values."""
+    instances = []
+
+    def __init__(self, model, capacity=0, device=0, stream=None):
+        self.model, self.n, self.calls = model, 0, []
+        Recorder.instances.append(self)
+
+    def _rec(self, name, *a):
+        self.calls.append((name,) + a)
+
+    def upload(self, agents):
+        self.n = len(agents)
+        self._rec('upload')
+
+    def download(self, agents, mask=_lib.F_ALL_MUTABLE):
+        self._rec('download', mask)
+
+    def set_states(self, agents, target=True):
+        self._rec('set_states', target)
+
+    def get_states(self, agents):
+        self._rec('get_states')
+
+    def set_active(self, active):
+        self._rec('set_active')
+
+    def get_active(self):
+        self._rec('get_active')
+        return np.ones(self.n, dtype=bool)
+
+    def inside_domain(self, want_count=True):
+        self._rec('inside_domain')
+        return 3
+
+    def target_reached(self, n_polygons, want_counts=True):
+        self._rec('target_reached', n_polygons)
+        return np.arange(n_polygons) + 7
+
+    def integrate(self, dt_min, dt_max):
+        self._rec('integrate')
+        return dt_max
+
+    def __getattr__(self, name):            # every other node entry point: just record it
+        if name.startswith('_'):
+            raise AttributeError(name)
+        return lambda *a, **k: self._rec(name)
+
+    def names(self):
+        return [c[0] for c in self.calls]
+
+
+@pytest.fixture
+def recorder(monkeypatch):
+    Recorder.instances.clear()
+    monkeypatch.setattr(L, 'DeviceAgents', Recorder)
+    return Recorder
+
+
+def _sim(mode):
+    agents, obstacles, doors, side = S.leader_follower_crowd(50, 'circular', seed=1)
+    domain = np.array([(0, 0), (side, 0), (side, side), (0, side)])
+    sim = L.MultiAgentSimulation(agents, obstacles, (), domain=domain)
+    sim.logic = L.Reset(sim, mode=mode) << (
+        L.InsideDomain(sim), L.TargetReached(sim, polygons=[domain, None, domain * 0.5]),
+        L.Integrator(sim) << (L.Adjusting(sim) << (L.ExitDetection(sim, center_door=doors) << L.LeaderFollowerWithHerding(sim)),
+                              L.AgentAgentInteractions(sim)))
+    return sim
+
+
+def test_strict_mode_moves_exactly_what_each_node_touches(recorder):
+    sim = _sim('strict')
+    assert sim.data['inactive'] == 0 and sim.data['target_0'] == 0 and sim.data['target_2'] == 0 and 'target_1' not in sim.data
+    sim.update()
+    dev, = recorder.instances
+    names = dev.names()
+    order = [n.name for n in L.post_order_iter(sim.logic.root)]
+    assert order == ['InsideDomain', 'TargetReached', 'LeaderFollowerWithHerding', 'ExitDetection', 'Adjusting',
+                     'AgentAgentInteractions', 'Integrator', 'Reset']
+    assert names.count('upload') == len(order)                         # every node starts from the host array
+    # InsideDomain: polygon once, active in, count, active out
+    i = names.index('inside_domain')
+    assert names[i - 1] == 'set_active' and names[i + 1] == 'get_active' and 'set_polygons' in names[:i]
+    assert sim.data['inactive'] == 3
+    assert sim.data['target_0'] == 7 and sim.data['target_2'] == 8      # two measured polygons, named by their index
+    # the steering nodes send the States fields and fetch back the ones they mutate
+    j = names.index('leader_follower_with_herding')
+    assert names[j - 2:j] == ['set_states', 'set_obstacles'] and ('download', _lib.F_TARGET_DIRECTION) in dev.calls[j:j + 2]
+    assert names[j + 1:j + 3] == ['download', 'get_states']
+    k = names.index('exit_detection')
+    assert names[k + 1] == 'get_states'                                 # nothing but States fields to publish
+    assert ('set_states', False) in dev.calls                            # target travels with the records
+    sim.update()
+    assert dev.names().count('set_polygons') == 2                       # domain + targets, sent once each
+    assert sim.data['inactive'] == 6 and sim.data['iterations'] == 2
+
+
+def test_resident_mode_uploads_once_and_syncs_on_demand(recorder):
+    sim = _sim('resident')
+    for _ in range(3):
+        sim.update()
+    dev, = recorder.instances
+    names = dev.names()
+    assert names.count('upload') == 1 and names.count('set_states') == 1 and names.count('set_active') == 1
+    assert 'download' not in names and 'get_states' not in names and 'get_active' not in names
+    assert names.count('inside_domain') == 3 and sim.data['inactive'] == 9
+    st = sim.logic.state
+    assert st.dirty_host and st.dirty_states and st.dirty_active
+    st.sync_host()
+    assert dev.names()[-3:] == ['download', 'get_states', 'get_active']
+    assert not (st.dirty_host or st.dirty_states or st.dirty_active)
+    st.sync_host()
+    assert dev.names()[-3:] == ['download', 'get_states', 'get_active']  # nothing new to fetch
+    # a host-side node edited the array: everything is sent again at the next node
+    st.invalidate()
+    sim.update()
+    names = dev.names()
+    assert names.count('upload') == 2 and names.count('set_states') == 2 and names.count('set_active') == 2
+    # switching a tree to strict publishes what is pending first
+    L.DeviceState.of(sim, 'strict')
+    assert st.mode == 'strict' and not st.dirty_host
