@@ -39,7 +39,7 @@ __device__ __forceinline__ bool line_intersect(double x0x, double x0y, double x1
 }
 
 // sensory_region.py:9-16 -- obstacle records: {p0x, p0y, p1x, p1y, ...} (SEG doubles each)
-__device__ __forceinline__ bool is_obstacle_between_points(double p0x, double p0y, double p1x, double p1y, const double *__restrict__ obs, int n_obs) {
+__device__ __noinline__ bool is_obstacle_between_points(double p0x, double p0y, double p1x, double p1y, const double *__restrict__ obs, int n_obs) {
     for (int w = 0; w < n_obs; ++w) {
         const double2 a = __ldg(reinterpret_cast<const double2 *>(obs + (size_t)w * SEG));
         const double2 b = __ldg(reinterpret_cast<const double2 *>(obs + (size_t)w * SEG + 2));
@@ -164,11 +164,11 @@ __global__ void k_herding(Soa s, int n_host, const int *n_dev, const double *__r
                 near[j] = u0 + j < e && u != t && !(rx * rx + ry * ry > dmax2);   // conservative against the current radius
             }
             if (!(near[0] || near[1] || near[2] || near[3])) continue;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {                  // in slot order, with the exact tests
-                if (!near[j]) continue;
+#pragma unroll 1
+            for (int j = 0; j < 4; ++j) {                  // in slot order, with the exact tests (one copy of the code: the
+                if (!(j == 0 ? near[0] : j == 1 ? near[1] : j == 2 ? near[2] : near[3])) continue;   // kernel is fetch-bound otherwise)
                 const int u = u0 + j;
-                const double2 op = cp[j];
+                const double2 op = j == 0 ? cp[0] : j == 1 ? cp[1] : j == 2 ? cp[2] : cp[3];
                 const double l = hypot(mp.x - op.x, mp.y - op.y);
                 if (!(l < dmax)) continue;
                 if (walls) {
@@ -222,24 +222,20 @@ __global__ void k_herding(Soa s, int n_host, const int *n_dev, const double *__r
             walls = false;      // can any wall cut a line of sight shorter than cap?
             for (int w = 0; w < n_obs && !walls; ++w) walls = segment_within(mp.x, mp.y, obs + (size_t)w * SEG, cap + slack);
             const int hw = (int)ceil(cap / cs);    // every point closer than cap lies within hw cells of the own one
-            sweep(cell_start[c], cell_start[c] + cell_count[c]);
+            const int span = 2 * hw + 1;
 #pragma unroll 1
-            for (int dx = -hw; dx <= hw; ++dx) {
-                const int x2 = cx + dx;
-                if (x2 < 0 || x2 >= nxg) continue;
-                const double gx = dx < 0 ? gxm + (double)(-dx - 1) * cs : dx > 0 ? gxp + (double)(dx - 1) * cs : 0.0;
-                const double gx0 = fmax(gx, 0.0);
-#pragma unroll 1
-                for (int dy = -hw; dy <= hw; ++dy) {
-                    const int y2 = cy + dy;
-                    if ((dx == 0 && dy == 0) || y2 < 0 || y2 >= ny) continue;
-                    if (exact_cells) {
-                        const double gy = dy < 0 ? gym + (double)(-dy - 1) * cs : dy > 0 ? gyp + (double)(dy - 1) * cs : 0.0;
-                        const double gy0 = fmax(gy, 0.0);
-                        if (sqrt(gx0 * gx0 + gy0 * gy0) - slack >= dmax) continue;   // nothing in that cell is closer than the k-th best
-                    }
-                    sweep(cell_start[x2 * ny + y2], cell_start[x2 * ny + y2] + cell_count[x2 * ny + y2]);
+            for (int q = -1; q < span * span; ++q) {       // q = -1: the own cell first (it tightens the radius most)
+                const int dx = q < 0 ? 0 : q / span - hw, dy = q < 0 ? 0 : q % span - hw;
+                if (q >= 0 && dx == 0 && dy == 0) continue;
+                const int x2 = cx + dx, y2 = cy + dy;
+                if (x2 < 0 || x2 >= nxg || y2 < 0 || y2 >= ny) continue;
+                if (exact_cells && q >= 0) {
+                    const double gx = dx < 0 ? gxm + (double)(-dx - 1) * cs : dx > 0 ? gxp + (double)(dx - 1) * cs : 0.0;
+                    const double gy = dy < 0 ? gym + (double)(-dy - 1) * cs : dy > 0 ? gyp + (double)(dy - 1) * cs : 0.0;
+                    const double gx0 = fmax(gx, 0.0), gy0 = fmax(gy, 0.0);
+                    if (sqrt(gx0 * gx0 + gy0 * gy0) - slack >= dmax) continue;   // nothing in that cell is closer than the k-th best
                 }
+                sweep(cell_start[x2 * ny + y2], cell_start[x2 * ny + y2] + cell_count[x2 * ny + y2]);
             }
             bool full = true;
             for (int q = 0; q < k; ++q) full = full && nb[q] >= 0;
