@@ -20,6 +20,7 @@ import numpy as np
 
 from . import _lib
 from .engine import DeviceAgents
+from .exceptions import InvalidValue
 from .structures import is_model, model_of, as_obstacles, MODEL_THREE_CIRCLE
 
 try:  # pragma: no cover - reference package not installable here
@@ -359,7 +360,11 @@ class ExitDetection(LogicNode):
     def _doors(self):
         if self.center_door is not None:
             return np.asarray(self.center_door, dtype=np.float64).reshape(-1, 2)
-        return np.stack([np.mean(np.asarray(target), axis=0) for target in self.simulation.field.targets])
+        doors = np.asarray([np.mean(np.asarray(target, dtype=np.float64), axis=0) for target in self.simulation.field.targets])
+        if doors.ndim != 2 or doors.shape[1] != 2:
+            raise InvalidValue('ExitDetection needs door centres: field.targets must be geometries (coordinate arrays), '
+                               'or pass center_door=(n_doors, 2)')
+        return doors
 
     def update(self):
         dev = self.state.begin_states()
@@ -392,9 +397,14 @@ class LeaderFollowerWithHerding(LogicNode):
 
 def _exterior(geom):
     """Vertices of a polygon given as an (nv, 2) array or as a shapely Polygon (``np.asarray(geom.exterior)``, logic.py:349)."""
+    if geom is None:
+        raise InvalidValue('a polygon is required (field.domain is None?)')
     ext = getattr(geom, 'exterior', geom)
     coords = getattr(ext, 'coords', ext)
-    return np.asarray(coords, dtype=np.float64).reshape(-1, 2)
+    v = np.asarray(coords, dtype=np.float64)
+    if v.ndim != 2 or v.shape[1] != 2 or len(v) < 3:
+        raise InvalidValue('a polygon is (nv >= 3, 2) vertices, got shape %s' % (v.shape,))
+    return v
 
 
 class InsideDomain(LogicNode):
@@ -438,9 +448,13 @@ class TargetReached(LogicNode):
         for i, target in enumerate(targets):
             if target is None or not (hasattr(target, 'exterior') or isinstance(target, (np.ndarray, list, tuple))):
                 continue
+            try:
+                vertices = _exterior(target)
+            except (InvalidValue, ValueError, TypeError):
+                continue                       # a line / point target: "we can only measure polygon targets" (logic.py:373)
             name = self.prefix.format(index=i)
             self.names.append(name)
-            self._polys.append(_exterior(target))
+            self._polys.append(vertices)
             self.simulation.data[name] = 0
         self._sent_to = None
 

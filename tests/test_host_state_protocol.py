@@ -128,3 +128,22 @@ def test_resident_mode_uploads_once_and_syncs_on_demand(recorder):
     # switching a tree to strict publishes what is pending first
     L.DeviceState.of(sim, 'strict')
     assert st.mode == 'strict' and not st.dirty_host
+
+
+def test_geometry_arguments_are_validated(recorder):
+    from crowddynamics_b200.exceptions import InvalidValue
+    agents, obstacles, doors, side = S.leader_follower_crowd(20, 'circular', seed=2)
+    sim = L.MultiAgentSimulation(agents, obstacles, ())                  # no domain, integer targets
+    with pytest.raises(InvalidValue):
+        L.InsideDomain(sim)
+    with pytest.raises(InvalidValue):
+        L.InsideDomain(sim, domain=[(0, 0), (1, 1)])                     # not a polygon
+    node = L.ExitDetection(sim)
+    with pytest.raises(InvalidValue):
+        node._doors()                                                    # field.targets are indices here, not geometries
+    assert L.ExitDetection(sim, center_door=doors)._doors().shape == (2, 2)
+    sim.field.targets = [np.array([(0.0, 1.0), (0.0, 3.0)]), np.array([(side, 1.0), (side, 2.0), (side, 3.0)])]
+    assert np.allclose(L.ExitDetection(sim)._doors(), [(0.0, 2.0), (side, 2.0)])      # mean of the coordinates, logic.py:247-248
+    tr = L.TargetReached(sim, polygons=[np.array([(0, 0), (1, 0), (1, 1), (0, 0)])])
+    assert tr.names == ['target_0'] and sim.data['target_0'] == 0
+    assert L.TargetReached(sim).names == []                              # the two door lines are not polygons: skipped
