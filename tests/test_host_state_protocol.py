@@ -142,8 +142,8 @@ def test_geometry_arguments_are_validated(recorder):
     with pytest.raises(InvalidValue):
         node._doors()                                                    # field.targets are indices here, not geometries
     assert L.ExitDetection(sim, center_door=doors)._doors().shape == (2, 2)
-    sim.field.targets = [np.array([(0.0, 1.0), (0.0, 3.0)]), np.array([(side, 1.0), (side, 2.0), (side, 3.0)])]
+    sim.field.targets = [np.array([(0.0, 1.0), (0.0, 3.0)]), np.array([(side, 1.0), (side, 3.0)])]
     assert np.allclose(L.ExitDetection(sim)._doors(), [(0.0, 2.0), (side, 2.0)])      # mean of the coordinates, logic.py:247-248
     tr = L.TargetReached(sim, polygons=[np.array([(0, 0), (1, 0), (1, 1), (0, 0)])])
     assert tr.names == ['target_0'] and sim.data['target_0'] == 0
-    assert L.TargetReached(sim).names == []                              # the two door lines are not polygons: skipped
+    assert L.TargetReached(sim).names == []                              # the two door lines (2 vertices) are not polygons: skipped
