@@ -290,7 +290,8 @@ def main():
     clocks = sampler.stop(t_begin, time.time()) if rank == 0 else None
     ms = ev0.elapsed_time(ev1)
     launches = dev.launch_count() - launches0
-    prof = dev.profile_read()
+    ph = dev.profile_read_phases()       # pre + block list, pair sweep, pair evaluation, step kernel, post, steps
+    prof = (ph[0], ph[1] + ph[2] + ph[3], ph[4], ph[5])
     dev.profile(False)
     agents_total = n_local() if callable(n_local) else n_local
     if world > 1:
@@ -342,7 +343,8 @@ def main():
                     'traffic_source': pc['source'] if pc else None,
                     'kernel_ms': k_ms, 'algorithmic_bytes_per_launch': algo_bytes,
                     'phase_ms_per_step': {'pre_and_block_list': prof[0] / prof[3], 'agent_agent': k_ms,
-                                          'post': prof[2] / prof[3]},
+                                          'pair_sweep': ph[1] / ph[5], 'pair_eval': ph[2] / ph[5],
+                                          'step_kernel': ph[3] / ph[5], 'post': prof[2] / prof[3]},
                     'note': 'the pair kernel is FP64-pipe bound at this density (SURVEY 7): HBM fraction is low by '
                             'construction; see DESIGN.md for the FP64 roofline'}
     # fp64 roofline of the same kernel: DFMA peak measured live, fp64 warp-instructions per launch from the committed profile

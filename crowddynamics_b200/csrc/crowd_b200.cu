@@ -63,6 +63,7 @@ int dev_alloc(T **p, size_t count) {
 constexpr int DT_LOG = DT_LOG_SLOTS;
 constexpr int STRIP_REFRESH = 16;
 constexpr int PROFILE_MAX_STEPS = 4096;
+constexpr int PROF_EVENTS = 6;   // per step: begin, block list, sweep + alloc, pair evaluation, step kernel, end
 
 inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
@@ -77,11 +78,13 @@ inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
 struct cdb_sim {
     int device = 0;
+    int sm_count = 148;
     int model = 0;
     int64_t itemsize = 0;
     int n_planes = 0;         // planes that mirror record fields
     int n_alloc_planes = 0;   // planes allocated (== n_planes)
-    int variant = 2;          // agent-agent kernel: 1 = one-phase reference kernel, 2 = two-phase fused kernel
+    int variant = 3;          // agent-agent: 1 = one-phase reference kernels, 2 = two-phase inside the fused kernel (every pair
+                              // evaluated from both sides), 3 = half-stencil sweep + pair list + one evaluation per pair
     bool auto_lattice_valid = false;
     int auto_lattice_age = 0;
     int64_t capacity = 0;   // agent slots allocated (incl. room for ghosts / migrants)
@@ -111,6 +114,13 @@ struct cdb_sim {
     double *d_nbr = nullptr;         // packed neighbour records of the cell-sorted state
     double *d_nbr_sweep = nullptr;   // three-circle: compact 48 B records for the phase-1 sweep (circular: alias of d_nbr)
     int *d_scan_partials = nullptr;
+    // once-per-pair evaluation (variant 3, pair_kernels.cuh)
+    PairBuf pb{};                    // device pointers + capacity
+    double2 *d_par = nullptr;        // {-mass * k_soc, tau_0} in cell order (+ ghost tail)
+    unsigned long long *h_pctr = nullptr;   // pinned: [0] pairs found by the last step, [1] entries allocated, [2] device step counter
+    bool pairs_pending = false;      // steps were issued whose pair count has not been checked yet
+    int64_t pair_cap_request = 0;    // cdb_set_pair_capacity (0: automatic)
+    int64_t pair_overflows = 0;      // steps that had to be repeated after growing the list
     long long *d_bbox = nullptr;     // min ix, max ix, min iy, max iy
     long long *h_bbox = nullptr;     // pinned
 
@@ -178,7 +188,7 @@ struct cdb_sim {
     // instrumentation: kernel launch counter and CUDA-event timing of the step phases
     int64_t launches = 0;
     bool profiling = false;
-    std::vector<cudaEvent_t> ev_pool;    // 4 events per profiled step: begin, after block list, after agent-agent, end
+    std::vector<cudaEvent_t> ev_pool;    // PROF_EVENTS events per profiled step
     size_t ev_used = 0;
 };
 
@@ -198,6 +208,7 @@ void free_soa(Soa &s) {
 }
 
 int alloc_ghost_tail(cdb_sim *sim);
+int ensure_pairs(cdb_sim *sim, int64_t cap);
 
 int ensure_capacity(cdb_sim *sim, int64_t n) {
     if (n <= sim->capacity && sim->cur.p) return CDB_OK;
@@ -218,6 +229,21 @@ int alloc_ghost_tail(cdb_sim *sim) {
     CKS(dev_alloc(&sim->d_nbr, cap * (sim->model == CDB_MODEL_CIRCULAR ? REC_CIRC : REC_THREE)));
     if (sim->model == CDB_MODEL_CIRCULAR) sim->d_nbr_sweep = sim->d_nbr;
     else CKS(dev_alloc(&sim->d_nbr_sweep, cap * REC_CIRC));
+    CKS(dev_alloc(&sim->d_par, cap));
+    CKS(dev_alloc(&sim->pb.cnt, cap));
+    CKS(dev_alloc(&sim->pb.off, cap));
+    CKS(dev_alloc(&sim->pb.fill, cap));
+    return CDB_OK;
+}
+
+// pair list + contribution array for `cap` pairs (contents are per-step scratch: nothing to preserve)
+int ensure_pairs(cdb_sim *sim, int64_t cap) {
+    if (cap <= sim->pb.cap && sim->pb.pairs) return CDB_OK;
+    CK(cudaStreamSynchronize(sim->stream));
+    CKS(dev_alloc(&sim->pb.pairs, (size_t)cap));
+    CKS(dev_alloc(&sim->pb.cres, (size_t)cap * 8));
+    sim->pb.cap = cap;
+    sim->state_version++;
     return CDB_OK;
 }
 
@@ -320,7 +346,7 @@ int build_block_list(cdb_sim *sim, double cell_size, bool padded_lattice = false
         sim->perm_valid = false;
     } else {
         if (live > 0) LAUNCH(sim, k_records, cdiv(live, T), T, 0, sim->cur, (int)live, live_dev, sim->model, sim->d_order, sim->d_cell_of_slot,
-                             sim->d_order_tmp, sim->d_nbr, sim->d_nbr_sweep, cell_size);
+                             sim->d_order_tmp, sim->d_nbr, sim->d_nbr_sweep, cell_size, sim->d_par);
         std::swap(sim->d_cell_of_slot, sim->d_order_tmp);   // d_cell_of_slot: flat cell per sorted slot; d_order_tmp: per plane slot
         sim->perm_valid = true;
     }
@@ -383,13 +409,81 @@ StepArgs step_args(cdb_sim *sim, unsigned flags, double dt_min, double dt_max, d
     return a;
 }
 
+inline bool use_pairs(const cdb_sim *sim) { return sim->variant == 3 && !sim->strip; }
+
+// allocations of variant 3, made OUTSIDE stream capture (before steps are issued): 8 pairs per agent to start with, grown
+// by settle_pairs() when a step gets close to or beyond the capacity
+int prepare_pairs(cdb_sim *sim) {
+    if (!use_pairs(sim)) return CDB_OK;
+    if (!sim->pb.ctr) {
+        CKS(dev_alloc(&sim->pb.ctr, 2));
+        CK(cudaMallocHost((void **)&sim->h_pctr, 3 * sizeof(unsigned long long)));
+        sim->h_pctr[0] = sim->h_pctr[1] = sim->h_pctr[2] = 0;
+    }
+    if (sim->pair_cap_request > 0) return ensure_pairs(sim, sim->pair_cap_request);
+    const int64_t want = std::max<int64_t>(8 * sim->n, 1 << 16);
+    if (!sim->pb.pairs || sim->pb.cap < want / 2) CKS(ensure_pairs(sim, want));
+    return CDB_OK;
+}
+
+// variant 3: classify every unordered pair of adjacent cells once, evaluate the survivors once (pair_kernels.cuh)
+int launch_pairs(cdb_sim *sim) {
+    const int64_t n = sim->n_sorted;
+    if (n <= 0) return CDB_OK;
+    if (!sim->pb.pairs || !sim->pb.ctr) return fail(CDB_ERR_STATE, "pair buffers not prepared");
+    cudaStream_t st = sim->stream;
+    CK(cudaMemsetAsync(sim->pb.ctr, 0, 2 * sizeof(unsigned long long), st));
+    CK(cudaMemsetAsync(sim->pb.cnt, 0, (size_t)n * sizeof(int), st));
+    SweepArgs a{};
+    a.nbr_sweep = sim->d_nbr_sweep;
+    a.n = (int)n;
+    a.n_dev = sim->dev_counts ? &sim->d_counts->live : nullptr;
+    a.grid = sim->d_grid;
+    a.cell_sorted = sim->d_cell_of_slot; a.cell_start = sim->d_cell_start; a.cell_count = sim->d_cell_count;
+    a.ghost_base = -1; a.n_ghost = 0;
+    a.reach = 1;
+    a.pb = sim->pb;
+    const int blocks = cdiv(n + a.n_ghost, SW_THREADS);
+    if (sim->model == CDB_MODEL_CIRCULAR) LAUNCH(sim, k_sweep<0>, blocks, SW_THREADS, 0, a);
+    else LAUNCH(sim, k_sweep<1>, blocks, SW_THREADS, 0, a);
+    LAUNCH(sim, k_pair_alloc, cdiv(n, 256), 256, 0, sim->pb, (int)n);
+    CKS(prof_mark(sim));
+    EvalArgs e{};
+    e.nbr = sim->d_nbr; e.par = sim->d_par; e.in = sim->cur;
+    e.order = sim->perm_valid ? sim->d_order : nullptr;
+    e.ghost_base = 0x7fffffff; e.ghost_left_end = 0x7fffffff;
+    e.pb = sim->pb;
+    // persistent grid-stride launch: the number of pairs is only known on the device
+    const int eval_blocks = (int)std::min<int64_t>(cdiv(std::max<int64_t>(4 * n, 128), 128), (int64_t)sim->sm_count * (sim->model == CDB_MODEL_CIRCULAR ? 16 : 8));
+    if (sim->model == CDB_MODEL_CIRCULAR) LAUNCH(sim, k_pair_eval<0>, eval_blocks, 128, 0, e);
+    else LAUNCH(sim, k_pair_eval<1>, eval_blocks, 128, 0, e);
+    CKS(prof_mark(sim));
+    CK(cudaGetLastError());
+    sim->pairs_pending = true;
+    return CDB_OK;
+}
+
 // the fused kernel; requires a current block list when CDB_STEP_AGENT_AGENT is selected
 int launch_step_kernel(cdb_sim *sim, unsigned flags, double dt_min, double dt_max, double *dt_log) {
-    const StepArgs a = step_args(sim, flags, dt_min, dt_max, dt_log);
+    const bool pairs = use_pairs(sim);
+    if (pairs && (flags & CDB_STEP_AGENT_AGENT)) CKS(launch_pairs(sim));
+    else { CKS(prof_mark(sim)); CKS(prof_mark(sim)); }
+    StepArgs a = step_args(sim, flags, dt_min, dt_max, dt_log);
+    a.pb = sim->pb;
+    a.n_planes = sim->n_planes;
     const int smem = 0;
     if (a.n > 0) {
-        if (sim->model == CDB_MODEL_CIRCULAR) LAUNCH(sim, k_step<0>, cdiv(a.n, STEP_THREADS), STEP_THREADS, smem, a);
-        else LAUNCH(sim, k_step<1>, cdiv(a.n, STEP_THREADS), STEP_THREADS, smem, a);
+        if (pairs) {
+            auto k0 = k_step<0, 1>;
+            auto k1 = k_step<1, 1>;
+            if (sim->model == CDB_MODEL_CIRCULAR) LAUNCH(sim, k0, cdiv(a.n, 256), 256, smem, a);
+            else LAUNCH(sim, k1, cdiv(a.n, 256), 256, smem, a);
+        } else {
+            auto k0 = k_step<0, 0>;
+            auto k1 = k_step<1, 0>;
+            if (sim->model == CDB_MODEL_CIRCULAR) LAUNCH(sim, k0, cdiv(a.n, STEP_THREADS), STEP_THREADS, smem, a);
+            else LAUNCH(sim, k1, cdiv(a.n, STEP_THREADS), STEP_THREADS, smem, a);
+        }
     } else if (flags & CDB_STEP_INTEGRATOR) {
         LAUNCH(sim, k_integrate, 1, 32, 0, sim->cur, 0, sim->model, dt_min, dt_max, sim->d_vmax, sim->d_dt);
     }
@@ -402,6 +496,30 @@ int launch_step_kernel(cdb_sim *sim, unsigned flags, double dt_min, double dt_ma
         }
         sim->perm_valid = false;
         sim->tables_valid = false;
+    }
+    return CDB_OK;
+}
+
+// Host side of the "a step whose pairs did not fit is not applied" protocol: one synchronisation; *overflow says whether
+// the most recent step found more pairs than the list holds (then the list has been grown), *dev_steps is the number of
+// integrating steps the device has really applied.
+int settle_pairs(cdb_sim *sim, bool *overflow, int64_t *dev_steps) {
+    *overflow = false;
+    if (dev_steps) *dev_steps = sim->iterations;
+    if (!sim->pairs_pending || !sim->pb.ctr) return CDB_OK;
+    CK(cudaMemcpyAsync(sim->h_pctr, sim->pb.ctr, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, sim->stream));
+    CK(cudaMemcpyAsync(sim->h_pctr + 2, sim->d_stepctr, sizeof(unsigned long long), cudaMemcpyDeviceToHost, sim->stream));
+    CK(cudaStreamSynchronize(sim->stream));
+    sim->pairs_pending = false;
+    const int64_t found = (int64_t)sim->h_pctr[0];
+    if (dev_steps) *dev_steps = (int64_t)sim->h_pctr[2];
+    if (found > sim->pb.cap) {
+        *overflow = true;
+        sim->pair_overflows++;
+        sim->pair_cap_request = 0;
+        CKS(ensure_pairs(sim, std::max<int64_t>(2 * sim->pb.cap, found + found / 2)));
+    } else if (found > sim->pb.cap / 2 && sim->pair_cap_request == 0) {
+        CKS(ensure_pairs(sim, 2 * sim->pb.cap));     // the crowd is getting denser: grow before it overflows
     }
     return CDB_OK;
 }
@@ -420,8 +538,16 @@ int launch_agent_agent(cdb_sim *sim) {
     return CDB_OK;
 }
 int node_agent_agent(cdb_sim *sim, double cell_size) {
+    CKS(prepare_pairs(sim));
     CKS(build_block_list(sim, cell_size, false, nullptr, sim->variant == 1));
-    return launch_agent_agent(sim);
+    for (int attempt = 0; attempt < 8; ++attempt) {
+        CKS(launch_agent_agent(sim));
+        if (!use_pairs(sim)) return CDB_OK;
+        bool overflow = false;
+        CKS(settle_pairs(sim, &overflow, nullptr));
+        if (!overflow) return CDB_OK;      // otherwise nothing was applied: the list has been grown, run the node again
+    }
+    return fail(CDB_ERR_CAPACITY, "pair list keeps overflowing");
 }
 int node_agent_obstacle(cdb_sim *sim) {
     if (sim->n && sim->n_obstacles)
@@ -485,6 +611,7 @@ int cdb_create(int device, int model, int64_t capacity, cdb_sim **out) {
     CK(cudaSetDevice(device));
     cdb_sim *sim = new cdb_sim();
     sim->device = device;
+    cudaDeviceGetAttribute(&sim->sm_count, cudaDevAttrMultiProcessorCount, device);
     sim->model = model;
     sim->itemsize = model == CDB_MODEL_CIRCULAR ? 228 : 316;
     sim->n_planes = model == CDB_MODEL_CIRCULAR ? NP_CIRC : NP_THREE;
@@ -746,7 +873,7 @@ static int issue_step(cdb_sim *sim, uint32_t flags, double cell_size, double dt_
         if (flags & CDB_STEP_AGENT_AGENT) CKS(build_block_list(sim, cell_size));
         CKS(prof_mark(sim));
         if (flags & CDB_STEP_AGENT_AGENT) CKS(launch_agent_agent(sim));
-        CKS(prof_mark(sim));
+        CKS(prof_mark(sim)); CKS(prof_mark(sim)); CKS(prof_mark(sim));
         if (flags & CDB_STEP_AGENT_OBSTACLE) CKS(node_agent_obstacle(sim));
         if (flags & CDB_STEP_INTEGRATOR) {
             CKS(node_integrate(sim, dt_min, dt_max));
@@ -762,7 +889,8 @@ static int issue_step(cdb_sim *sim, uint32_t flags, double cell_size, double dt_
         CKS(launch_step_kernel(sim, flags, dt_min, dt_max, log));
         CKS(prof_mark(sim));
     }
-    LAUNCH(sim, k_step_advance, 1, 32, 0, sim->d_stepctr);
+    const bool checked = use_pairs(sim) && sim->variant != 1 && (flags & CDB_STEP_AGENT_AGENT) && sim->n_sorted > 0;
+    LAUNCH(sim, k_step_advance, 1, 32, 0, sim->d_stepctr, checked ? sim->pb.ctr : nullptr, (long long)sim->pb.cap);
     CKS(prof_mark(sim));
     sim->iterations++;
     return CDB_OK;
@@ -826,8 +954,10 @@ int cdb_step(cdb_sim *sim, uint32_t flags, double cell_size, double dt_min, doub
     const bool log_dt = dt_out && (flags & CDB_STEP_INTEGRATOR);
     int64_t k = 0, copied = 0;      // steps done / dt values already returned
     const bool prof_saved = sim->profiling;
+    int regrown = 0;
+    if (flags & CDB_STEP_AGENT_AGENT) CKS(prepare_pairs(sim));
     while (k < n_steps) {
-        sim->profiling = prof_saved && sim->ev_used + 4 <= (size_t)PROFILE_MAX_STEPS * 4;
+        sim->profiling = prof_saved && sim->ev_used + 2 * PROF_EVENTS <= (size_t)PROFILE_MAX_STEPS * PROF_EVENTS;
         // a pair must not straddle the end of the dt ring (its first half would be overwritten before it is read back)
         const bool ring_ok = !log_dt || (sim->iterations % DT_LOG) != DT_LOG - 1;
         if (n_steps - k >= 2 && ring_ok && graph_usable(sim, flags, cell_size)) {
@@ -838,15 +968,53 @@ int cdb_step(cdb_sim *sim, uint32_t flags, double cell_size, double dt_min, doub
             k += 1;
         }
         sim->profiling = prof_saved;
-        if (log_dt && (sim->iterations % DT_LOG == 0 || k == n_steps)) {
-            // slots of the steps not yet returned: they end at slot (iterations - 1) % DT_LOG and do not wrap
-            const int64_t cnt = k - copied;
-            const int64_t first_slot = (sim->iterations - cnt) % DT_LOG;
-            CK(cudaMemcpyAsync(dt_out + copied, sim->d_dt_log + first_slot, cnt * sizeof(double), cudaMemcpyDeviceToHost, sim->stream));
-            CK(cudaStreamSynchronize(sim->stream));
-            copied = k;
+        // Synchronisation points: the dt ring is about to wrap, the call is complete, or (variant 3) every 64 steps, so
+        // that steps the device did not apply because the pair list overflowed are noticed and repeated early.
+        const bool ring_point = log_dt && sim->iterations % DT_LOG == 0;
+        const bool pairs_point = sim->pairs_pending && (k == n_steps || (k & 63) == 0);
+        if (ring_point || pairs_point || (log_dt && k == n_steps)) {
+            bool overflow = false;
+            int64_t dev_steps = sim->iterations;
+            CKS(settle_pairs(sim, &overflow, &dev_steps));
+            if (overflow) {
+                if (++regrown > 16) return fail(CDB_ERR_CAPACITY, "pair list keeps overflowing");
+                // steps issued after the overflowing one ran on the unchanged state and were not applied either
+                const int64_t missing = sim->iterations - dev_steps;
+                sim->iterations = dev_steps;
+                k -= missing;
+            }
+            if (log_dt && k > copied) {
+                // slots of the steps not yet returned: they end at slot (iterations - 1) % DT_LOG and do not wrap
+                const int64_t cnt = k - copied;
+                const int64_t first_slot = (sim->iterations - cnt) % DT_LOG;
+                CK(cudaMemcpyAsync(dt_out + copied, sim->d_dt_log + first_slot, cnt * sizeof(double), cudaMemcpyDeviceToHost, sim->stream));
+                CK(cudaStreamSynchronize(sim->stream));
+                copied = k;
+            }
         }
     }
+    return CDB_OK;
+}
+
+int cdb_set_pair_capacity(cdb_sim *sim, int64_t pairs) {
+    SIM_ENTRY();
+    if (pairs < 0) return fail(CDB_ERR_INVALID_VALUE, "negative pair capacity");
+    sim->pair_cap_request = pairs;
+    if (pairs > 0) {
+        CK(cudaStreamSynchronize(sim->stream));
+        sim->pb.cap = 0;                // shrink as well as grow: reallocate at exactly this size
+        CKS(ensure_pairs(sim, pairs));
+    }
+    return CDB_OK;
+}
+
+int cdb_get_pair_stats(cdb_sim *sim, int64_t *capacity, int64_t *found_last, int64_t *overflows) {
+    SIM_ENTRY();
+    bool overflow = false;
+    CKS(settle_pairs(sim, &overflow, nullptr));
+    if (capacity) *capacity = sim->pb.cap;
+    if (found_last) *found_last = sim->h_pctr ? (int64_t)sim->h_pctr[0] : 0;
+    if (overflows) *overflows = sim->pair_overflows;
     return CDB_OK;
 }
 
@@ -858,7 +1026,7 @@ int cdb_set_graphs(cdb_sim *sim, int enable) {
 
 int cdb_set_variant(cdb_sim *sim, int variant) {
     SIM_ENTRY();
-    if (variant != 1 && variant != 2) return fail(CDB_ERR_INVALID_VALUE, "unknown kernel variant %d", variant);
+    if (variant < 1 || variant > 3) return fail(CDB_ERR_INVALID_VALUE, "unknown kernel variant %d", variant);
     sim->variant = variant;
     sim->state_version++;
     return CDB_OK;
@@ -873,19 +1041,27 @@ int cdb_profile_enable(cdb_sim *sim, int enable) {
     return CDB_OK;
 }
 
-int cdb_profile_read(cdb_sim *sim, double ms[3], int64_t *steps) {
+int cdb_profile_read_phases(cdb_sim *sim, double ms[5], int64_t *steps) {
     SIM_ENTRY();
+    if (!ms) return fail(CDB_ERR_INVALID_VALUE, "ms is NULL");
     CK(cudaStreamSynchronize(sim->stream));
-    ms[0] = ms[1] = ms[2] = 0.0;
-    const size_t n = sim->ev_used / 4;
+    for (int j = 0; j < PROF_EVENTS - 1; ++j) ms[j] = 0.0;
+    const size_t n = sim->ev_used / PROF_EVENTS;
     for (size_t k = 0; k < n; ++k)
-        for (int j = 0; j < 3; ++j) {
+        for (int j = 0; j < PROF_EVENTS - 1; ++j) {
             float t = 0.f;
-            CK(cudaEventElapsedTime(&t, sim->ev_pool[4 * k + j], sim->ev_pool[4 * k + j + 1]));
+            CK(cudaEventElapsedTime(&t, sim->ev_pool[PROF_EVENTS * k + j], sim->ev_pool[PROF_EVENTS * k + j + 1]));
             ms[j] += t;
         }
     if (steps) *steps = (int64_t)n;
     sim->ev_used = 0;
+    return CDB_OK;
+}
+
+int cdb_profile_read(cdb_sim *sim, double ms[3], int64_t *steps) {
+    double p[PROF_EVENTS - 1];
+    CKS(cdb_profile_read_phases(sim, p, steps));
+    ms[0] = p[0]; ms[1] = p[1] + p[2] + p[3]; ms[2] = p[4];
     return CDB_OK;
 }
 
@@ -1081,7 +1257,7 @@ int cdb_strip_finish(cdb_sim *sim, uint32_t flags, double dt_min, double dt_max,
     CKS(launch_step_kernel(sim, flags, dt_min, dt_max, nullptr));
     CKS(prof_mark(sim));
     sim->iterations++;
-    LAUNCH(sim, k_step_advance, 1, 32, 0, sim->d_stepctr);
+    LAUNCH(sim, k_step_advance, 1, 32, 0, sim->d_stepctr, (const unsigned long long *)nullptr, 0LL);
     LAUNCH(sim, k_counters_zero, 1, 32, 0, sim->d_counters, 4);
     if (sim->n > 0)
         LAUNCH(sim, k_migrants_pack, cdiv(sim->n, 256), 256, 0, sim->cur, (int)sim->n, sim->dev_counts ? &sim->d_counts->slots : nullptr, sim->n_planes, sim->cell_size, sim->grid.ix_min,

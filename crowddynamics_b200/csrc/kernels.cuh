@@ -608,11 +608,14 @@ __global__ void k_gather(Soa src, Soa dst, int n, int n_planes, int model, const
 // extent = conservative radius of the whole body around the centre (from the STORED shoulder positions), (ox, oy) =
 // r_ts (sin phi, -cos phi), the shoulder displacement of power_law.py:338-350.
 __global__ void k_records(Soa src, int n_host, const int *n_dev, int model, const int *__restrict__ order,
-                         const int *__restrict__ cell_of_slot, int *__restrict__ cell_sorted, double *__restrict__ nbr, double *__restrict__ nbr_sweep, double cell_size) {
+                         const int *__restrict__ cell_of_slot, int *__restrict__ cell_sorted, double *__restrict__ nbr, double *__restrict__ nbr_sweep, double cell_size,
+                         double2 *__restrict__ par) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= eff_n(n_host, n_dev)) return;
     const int o = order[t];
     cell_sorted[t] = cell_of_slot[o];
+    // what the once-per-pair evaluation needs of an agent's parameters: -mass * k_soc and tau_0 (power_law.py:252-255,355-358)
+    if (par) par[t] = make_double2(-src(MASS, o) * src(K_SOC, o), src(TAU_0, o));
     const double x = src(PX, o), y = src(PY, o), vx = src(VX, o), vy = src(VY, o);
     if (model == CDB_MODEL_CIRCULAR) {
         double2 *r = reinterpret_cast<double2 *>(nbr + (size_t)t * 6);
@@ -669,7 +672,10 @@ __global__ void k_export_pairs(const int *__restrict__ id, const int *__restrict
 // per-agent nodes
 // =====================================================================================================================
 // the device-side step index (Philox key of the Fluctuation node, slot of the dt log); one thread, after every step
-__global__ void k_step_advance(unsigned long long *step) { if (threadIdx.x == 0) ++*step; }
+// (a step whose pairs did not fit the pair list was not applied and does not count: pair_ctr[0] > pair_cap)
+__global__ void k_step_advance(unsigned long long *step, const unsigned long long *pair_ctr, long long pair_cap) {
+    if (threadIdx.x == 0 && !(pair_ctr && pair_ctr[0] > (unsigned long long)pair_cap)) ++*step;
+}
 
 __global__ void k_reset(Soa s, int n, int model) {   // logic.py:59-64
     const int i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -1,0 +1,419 @@
+// pair_kernels.cuh -- agent-agent interactions evaluated ONCE per unordered pair, as the reference does
+// (core/interactions.py:53-70,75-104 update both agents of a pair from one evaluation):
+//
+//   k_sweep      (classify)  one thread per cell-sorted agent ("target") sweeps only its FORWARD half stencil -- the rest of
+//                            its own cell column range and the next cell column(s) -- so every unordered pair of adjacent
+//                            cells is tested exactly once (the block list's own pair enumeration, core/block_list.py:28-52 /
+//                            cell_lists.iter_nearest_neighbors).  The ~25-operation branch-free fp64 test of step_kernel.cuh
+//                            decides whether the pair can contribute a force at all; survivors are compacted warp-wide
+//                            (ballot + popc) into a staging buffer in shared memory and appended, coalesced, to a global pair
+//                            list.  Per-agent counts of listed pairs are kept with integer atomics.
+//   k_pair_alloc             gives every agent a private region of the contribution array (warp-aggregated allocation; the
+//                            regions need not be ordered, only disjoint).
+//   k_pair_eval  (evaluate)  one thread per listed pair runs the exact reference arithmetic once, in the reference's (i, j)
+//                            orientation, and produces BOTH agents' force / torque -- bit-identical to evaluating the pair
+//                            from each side (circular: x -> -x is an exact negation; three-circle: the shared quantities
+//                            h_min, tau, gradient are the same numbers for both sides).  Each side's result goes to that
+//                            agent's region, tagged with the partner's position in cell order.
+//   k_step<M, 1> (gather)    adds an agent's contributions in ascending partner order -- the order in which the one-kernel
+//                            variant (step_kernel.cuh, PAIRS = 0) meets them -- so results are run-to-run reproducible and
+//                            bit-identical to that variant, whatever order the atomics resolved in.
+//
+// The pair list has a fixed capacity.  If a step finds more pairs than fit, NOTHING of that step is applied (k_pair_eval and
+// the gather kernel see ctr[0] > cap and leave the state untouched, the device step counter does not advance); the host
+// notices at its next synchronisation point, grows the buffers and re-issues the missing steps (crowd_b200.cu: settle()).
+#pragma once
+#include "kernels.cuh"
+
+constexpr int SW_THREADS = 128;
+constexpr int SW_WARPS = SW_THREADS / 32;
+constexpr int SW_CHUNK = 4;                  // candidates classified per lane between two staging-capacity checks
+constexpr int SW_STAGE = 256;                // staged pairs per warp
+constexpr int GHOST_KEY_SHIFT = 1 << 30;     // ghosts of the left neighbour strip sort before every owned agent
+
+#define PREFILTER_EPS 1e-12
+#define BOUND_EPS 1e-9
+
+// packed neighbour records (doubles per agent)
+constexpr int REC_CIRC = 6;     // px py vx vy r -
+constexpr int REC_THREE = 16;   // px py vx vy ext rt rs - | lsx lsy rsx rsy ox oy cell_x cell_y
+
+struct PairBuf {
+    int2 *pairs;                 // [cap] (target slot, candidate slot), target < candidate in cell order
+    double *cres;                // [2 * cap][4] contributions {partner key (int64 bits), fx, fy, torque}
+    int *cnt;                    // per slot: listed pairs the agent takes part in
+    int *off;                    // per slot: first entry of the agent's region of cres
+    int *fill;                   // per slot: entries written so far (== contributions to add)
+    unsigned long long *ctr;     // [0] pairs found this step (may exceed cap => step not applied), [1] entries allocated
+    long long cap;
+};
+
+__device__ __forceinline__ bool pairs_overflowed(const PairBuf &pb) { return pb.ctr[0] > (unsigned long long)pb.cap; }
+
+struct SweepArgs {
+    const double *nbr_sweep;     // 48 B sweep records {px, py, vx, vy, R, -} in cell order (+ ghost tail)
+    int n;                       // owned targets (host-side bound)
+    const int *n_dev;            // device-side exact count (nullptr: n is exact)
+    const Grid *grid;
+    const int *cell_sorted, *cell_start, *cell_count;
+    int ghost_base;              // first slot of the left ghost column (strips; targets n .. n + n_ghost map there), or -1
+    int n_ghost;                 // launch bound for the left ghost targets
+    int reach;                   // forward columns / rows swept around the target's cell (1 on the cell_size lattice)
+    PairBuf pb;
+};
+
+__device__ __forceinline__ double2 ldg2(const double *p) { return __ldg(reinterpret_cast<const double2 *>(p)); }
+
+template <int MODEL>
+__global__ void __launch_bounds__(SW_THREADS, 8) k_sweep(const SweepArgs A) {
+    __shared__ int2 s_stage[SW_WARPS][SW_STAGE];
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    int2 *stage = s_stage[threadIdx.x >> 5];
+    const int g = blockIdx.x * SW_THREADS + threadIdx.x;
+    const int n_own = eff_n(A.n, A.n_dev);
+    const int ny = (int)A.grid->ny, nxg = (int)A.grid->nx;
+    // targets: owned agents, then (strips) the ghosts of the left neighbour, which only pair with owned candidates
+    int t = -1;
+    bool ghost = false;
+    if (g < A.n) { if (g < n_own) t = g; }
+    else if (A.ghost_base >= 0) {
+        const int k = g - A.n;
+        const int n_gl = A.cell_start[ny - 1] + A.cell_count[ny - 1] - A.ghost_base;   // column 0 is the left ghost column
+        if (k < n_gl) { t = A.ghost_base + k; ghost = true; }
+    }
+    const bool active = t >= 0;
+    const int tt = active ? t : 0;
+    double mpx, mpy, mvx, mvy, mr;
+    {
+        const double *r = A.nbr_sweep + (size_t)tt * REC_CIRC;
+        const double2 p = ldg2(r), v = ldg2(r + 2);
+        mpx = p.x; mpy = p.y; mvx = v.x; mvy = v.y; mr = __ldg(r + 4);
+    }
+    const int c = A.cell_sorted[tt];
+    const int cx = c / ny, cy = c - cx * ny;
+    const int reach = A.reach;
+    const int ylo = max(cy - reach, 0), yhi = min(cy + reach, ny - 1);
+    const int col_min = (int)A.grid->cx_lo;      // ghost targets: candidates in owned columns only
+    int nst = 0, mine = 0;
+
+    auto flush = [&]() {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(&A.pb.ctr[0], (unsigned long long)nst);
+        base = __shfl_sync(FULL, base, 0);
+        __syncwarp();
+        for (int i = lane; i < nst; i += 32) {
+            const unsigned long long p = base + i;
+            if (p < (unsigned long long)A.pb.cap) {
+                const int2 e = stage[i];
+                A.pb.pairs[p] = e;
+                atomicAdd(&A.pb.cnt[e.y], 1);
+            }
+        }
+        __syncwarp();
+        nst = 0;
+    };
+
+    for (int dx = 0; dx <= reach; ++dx) {
+        const int x2 = cx + dx;
+        int b = 0, e = 0;
+        if (active && x2 < nxg && !(ghost && x2 < col_min)) {
+            if (dx == 0) { b = t + 1; e = A.cell_start[x2 * ny + yhi] + A.cell_count[x2 * ny + yhi]; }
+            else { b = A.cell_start[x2 * ny + ylo]; e = A.cell_start[x2 * ny + yhi] + A.cell_count[x2 * ny + yhi]; }
+        }
+        const int maxlen = __reduce_max_sync(FULL, e - b);
+        for (int k0 = 0; k0 < maxlen; k0 += SW_CHUNK) {
+            bool keep[SW_CHUNK];
+#pragma unroll
+            for (int kk = 0; kk < SW_CHUNK; ++kk) {
+                const int u = b + k0 + kk;
+                const bool inr = u < e;
+                const double *r = A.nbr_sweep + (size_t)(inr ? u : tt) * REC_CIRC;
+                const double2 p = ldg2(r), v = ldg2(r + 2);
+                const double ro = __ldg(r + 4);
+                const double x = mpx - p.x, y = mpy - p.y;
+                const double R = mr + ro;                    // r_tot (circular) / sum of body extents (three-circle)
+                const double d2 = x * x + y * y;
+                const double lim = SIGTH_SOC + R;
+                const double RR = R * R;
+                const bool gate = d2 <= lim * lim * (1.0 + PREFILTER_EPS);
+                const bool contact = d2 <= RR * (1.0 + PREFILTER_EPS);
+                const double vx = mvx - v.x, vy = mvy - v.y;
+                const double a = vx * vx + vy * vy;
+                const double bb = -(x * vx + y * vy);
+                bool social;
+                if (MODEL == 0) {
+                    // the reference's own a, b, c, disc in its operation order: exactly the necessary condition for a
+                    // non-zero social force (power_law.py:236-246)
+                    const double cc = d2 - RR;
+                    const double disc = bb * bb - a * cc;
+                    social = disc > 0.0 && bb > 0.0;
+                } else {
+                    // bounding circles (inflated by BOUND_EPS): no real root for them => none for any of the 9 part pairs
+                    // (power_law.py:308-329); all part pairs receding => no positive time-to-collision
+                    const double Rs = R * (1.0 + BOUND_EPS), RRs = Rs * Rs;
+                    const double disc = bb * bb - a * (d2 - RRs);
+                    social = disc >= 0.0 && (bb >= 0.0 || bb * bb <= RRs * a);
+                }
+                keep[kk] = inr && gate && (social || contact);
+            }
+#pragma unroll
+            for (int kk = 0; kk < SW_CHUNK; ++kk) {
+                const unsigned m = __ballot_sync(FULL, keep[kk]);
+                if (keep[kk]) { stage[nst + __popc(m & ((1u << lane) - 1u))] = make_int2(t, b + k0 + kk); ++mine; }
+                nst += __popc(m);
+            }
+            if (nst > SW_STAGE - 32 * SW_CHUNK) flush();
+        }
+    }
+    if (nst) flush();
+    if (mine) atomicAdd(&A.pb.cnt[t], mine);
+}
+
+// private region of the contribution array for every agent (order of the regions is irrelevant)
+__global__ void k_pair_alloc(PairBuf pb, int n_slots) {
+    if (pairs_overflowed(pb)) return;
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int c = a < n_slots ? pb.cnt[a] : 0;
+    int incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int w = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += w; }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    unsigned long long base = 0;
+    if (lane == 31 && total > 0) base = atomicAdd(&pb.ctr[1], (unsigned long long)total);
+    base = __shfl_sync(0xffffffffu, base, 31);
+    if (a < n_slots) { pb.off[a] = (int)base + incl - c; pb.fill[a] = 0; }
+}
+
+// ---- both sides of a circular pair (interactions.py:53-70, distance.py:19-47, power_law.py:215-259) ---------------------
+// Every quantity of the (u, t) evaluation is either equal to or the exact negation of the (t, u) one (differences, products
+// of two negated factors, hypot), so both results are bit-identical to two one-sided evaluations by pair_circular().
+struct PairPar { double mk, tau_0; };          // -mass * k_soc, tau_0
+struct ContactPar { double mu, kappa, damping; };
+
+template <typename LoadContact>
+__device__ __forceinline__ void pair_circular_both(double pxt, double pyt, double vxt, double vyt, double rt, const PairPar &pt,
+                                                   double pxu, double pyu, double vxu, double vyu, double ru, const PairPar &pu,
+                                                   LoadContact load_contact, double ft[2], double fu[2]) {
+    ft[0] = ft[1] = fu[0] = fu[1] = 0.0;
+    const double x = pxt - pxu, y = pyt - pyu;
+    const double d = hypot(x, y);
+    const double r_tot = rt + ru;
+    const double h = d - r_tot;
+    if (!(h < SIGTH_SOC)) return;
+    const double vx = vxt - vxu, vy = vyt - vyu;
+    const double a = vx * vx + vy * vy;
+    const double b = -(x * vx + y * vy);
+    const double c = (x * x + y * y) - r_tot * r_tot;
+    const double dd = sqrt(b * b - a * c);
+    if (!(isnan(dd) || dd == 0.0 || a == 0.0)) {
+        const double tau = (b - dd) / a;
+        if (!(tau <= 0.0 || tau > TAU_MAX)) {
+            const double gx = (vx - (vx * b + x * a) / dd) / a;   // power_law.py:107-126
+            const double gy = (vy - (vy * b + y * a) / dd) / a;
+            const double mag_t = magnitude(tau, pt.tau_0);
+            const double mag_u = pu.tau_0 == pt.tau_0 ? mag_t : magnitude(tau, pu.tau_0);
+            ft[0] = pt.mk * gx * mag_t; ft[1] = pt.mk * gy * mag_t;
+            fu[0] = pu.mk * (0.0 - gx) * mag_u; fu[1] = pu.mk * (0.0 - gy) * mag_u;
+            truncate2(ft[0], ft[1], F_SOC_MAX);
+            truncate2(fu[0], fu[1], F_SOC_MAX);
+        }
+    }
+    if (h < 0.0) {
+        double nx = 0.0, ny = 0.0;
+        if (d != 0.0) { nx = x / d; ny = y / d; }
+        ContactPar ct, cu;
+        load_contact(ct, cu);
+        double cx, cy;
+        force_contact(h, nx, ny, vx, vy, ny, -nx, ct.mu, ct.kappa, ct.damping, cx, cy);   // t = rotate270(n)
+        ft[0] += cx; ft[1] += cy;
+        force_contact(h, 0.0 - nx, 0.0 - ny, 0.0 - vx, 0.0 - vy, 0.0 - ny, nx, cu.mu, cu.kappa, cu.damping, cx, cy);
+        fu[0] += cx; fu[1] += cy;
+    }
+}
+
+// ---- both sides of a three-circle pair in the reference's (i, j) orientation (interactions.py:75-104, distance.py:55-105,
+//      power_law.py:264-363): the body of pair_three_exact() of step_kernel.cuh with the per-side tail run twice ------------
+struct Three {               // kinematics of one three-circle agent as the pair kernels need them
+    double x0, y0, x1, y1, x2, y2;   // torso, left shoulder, right shoulder centres
+    double rt, rs;           // torso / shoulder radius
+    double vx, vy;
+    double ox, oy;           // r_ts * (sin(phi), -cos(phi)): shoulder displacement (power_law.py:338-350, agents.py:483-484)
+};
+
+__device__ __forceinline__ double sel3(int k, double a, double b, double c) { return k == 0 ? a : (k == 1 ? b : c); }
+
+__device__ __forceinline__ void load_three_rec(const double *__restrict__ nbr, int u, Three &k) {
+    const double *r = nbr + (size_t)u * REC_THREE;
+    const double2 a = ldg2(r), b = ldg2(r + 2), c = ldg2(r + 4), d = ldg2(r + 6), e = ldg2(r + 8), f = ldg2(r + 10), g = ldg2(r + 12);
+    k.x0 = a.x; k.y0 = a.y; k.vx = b.x; k.vy = b.y; k.rt = c.y; k.rs = d.x;
+    k.x1 = e.x; k.y1 = e.y; k.x2 = f.x; k.y2 = f.y; k.ox = g.x; k.oy = g.y;
+}
+
+template <typename LoadContact>
+__device__ __forceinline__ void pair_three_both(const Three &I, const Three &J, const PairPar &pi, const PairPar &pj,
+                                                LoadContact load_contact, double fi[3], double fj[3]) {
+    fi[0] = fi[1] = fi[2] = fj[0] = fj[1] = fj[2] = 0.0;
+    const double jx[3] = {J.x0, J.x1, J.x2}, jy[3] = {J.y0, J.y1, J.y2}, rj[3] = {J.rt, J.rs, J.rs};
+    // distance_three_circles (distance.py:55-105): strict '<', first wins, order torso, left, right
+    double h_min = nan(""), sx = 0.0, sy = 0.0, sd = 0.0;
+    int i_min = 0, j_min = 0;
+#pragma unroll 1
+    for (int pi_ = 0; pi_ < 3; ++pi_) {
+        const double xi = sel3(pi_, I.x0, I.x1, I.x2), yi = sel3(pi_, I.y0, I.y1, I.y2), rip = pi_ == 0 ? I.rt : I.rs;
+#pragma unroll
+        for (int pj_ = 0; pj_ < 3; ++pj_) {
+            const double x = xi - jx[pj_], y = yi - jy[pj_];
+            const double d = hypot(x, y);
+            const double h = d - (rip + rj[pj_]);
+            if (h < h_min || isnan(h_min)) { h_min = h; sx = x; sy = y; sd = d; i_min = pi_; j_min = pj_; }
+        }
+    }
+    if (!(h_min < SIGTH_SOC)) return;
+    double nx = 0.0, ny = 0.0;
+    if (sd != 0.0) { nx = sx / sd; ny = sy / sd; }
+    const double vx = I.vx - J.vx, vy = I.vy - J.vy;
+    const double a = vx * vx + vy * vy;
+    double fix = 0.0, fiy = 0.0, fjx = 0.0, fjy = 0.0;
+    if (a != 0.0) {
+        // smallest time-to-collision over the 9 part pairs with the reference's selection rule (power_law.py:308-329):
+        // `isnan(tau) or 0 < tau_new < tau`.  tau_new = (b - d) / a is monotone in its numerator, so the division is only
+        // needed when the numerator is positive and smaller than the selected one -- same decisions, fewer divisions.
+        double tau = nan(""), num_sel = 0.0, b_min = 0.0, d_min = 0.0;
+        int contact_i = 0, contact_j = 0;
+#pragma unroll 1
+        for (int pi_ = 0; pi_ < 3; ++pi_) {
+            const double xi = sel3(pi_, I.x0, I.x1, I.x2), yi = sel3(pi_, I.y0, I.y1, I.y2), rip = pi_ == 0 ? I.rt : I.rs;
+#pragma unroll
+            for (int pj_ = 0; pj_ < 3; ++pj_) {
+                const double x = xi - jx[pj_], y = yi - jy[pj_];
+                const double r_tot = rip + rj[pj_];
+                const double b = -(x * vx + y * vy);
+                const double c = (x * x + y * y) - r_tot * r_tot;
+                const double disc = b * b - a * c;
+                if (!(disc > 0.0)) continue;         // sqrt gives NaN (disc < 0 or NaN) or 0
+                const double dd = sqrt(disc);
+                const double num = b - dd;
+                bool take = false;
+                double tau_new = 0.0;
+                if (isnan(tau)) { tau_new = num / a; take = true; }
+                else if (num > 0.0 && num < num_sel) { tau_new = num / a; take = 0.0 < tau_new && tau_new < tau; }
+                if (take) { tau = tau_new; num_sel = num; b_min = b; d_min = dd; contact_i = pi_; contact_j = pj_; }
+            }
+        }
+        if (!(isnan(tau) || tau <= 0.0)) {
+            // shoulder displacement of the contacting parts: 0 for the torso, +o for left, -o for right
+            const double oix = sel3(contact_i, 0.0, I.ox, 0.0 - I.ox), oiy = sel3(contact_i, 0.0, I.oy, 0.0 - I.oy);
+            const double ojx = sel3(contact_j, 0.0, J.ox, 0.0 - J.ox), ojy = sel3(contact_j, 0.0, J.oy, 0.0 - J.oy);
+            const double xr = I.x0 - J.x0, yr = I.y0 - J.y0;
+            const double ox = oix - ojx, oy = oiy - ojy;
+            const double gx = (vx - (a * (xr + 2 * ox) + b_min * vx) / d_min) / a;   // power_law.py:131-149
+            const double gy = (vy - (a * (yr + 2 * oy) + b_min * vy) / d_min) / a;
+            const double mag_i = magnitude(tau, pi.tau_0);
+            const double mag_j = pj.tau_0 == pi.tau_0 ? mag_i : magnitude(tau, pj.tau_0);
+            fix = pi.mk * gx * mag_i; fiy = pi.mk * gy * mag_i;
+            fjx = 0.0 - pj.mk * gx * mag_j; fjy = 0.0 - pj.mk * gy * mag_j;   // force_j[:] -= ... (power_law.py:358)
+            truncate2(fix, fiy, F_SOC_MAX);
+            truncate2(fjx, fjy, F_SOC_MAX);
+        }
+    }
+    if (h_min < 0.0) {
+        ContactPar ci, cj;
+        load_contact(ci, cj);
+        double cx, cy;
+        force_contact(h_min, nx, ny, vx, vy, ny, -nx, ci.mu, ci.kappa, ci.damping, cx, cy);
+        fix += cx; fiy += cy;
+        force_contact(h_min, nx, ny, vx, vy, ny, -nx, cj.mu, cj.kappa, cj.damping, cx, cy);
+        fjx -= cx; fjy -= cy;
+    }
+    // moment arms, distance.py:102-103:  i: x0[i_min] + r0[i_min] n - x0[0];  j: x0[j_min] - r1[j_min] n - x1[0]  (sic)
+    const double mir = i_min == 0 ? I.rt : I.rs, mjr = j_min == 0 ? J.rt : J.rs;
+    const double mix = sel3(i_min, I.x0, I.x1, I.x2) + mir * nx - I.x0, miy = sel3(i_min, I.y0, I.y1, I.y2) + mir * ny - I.y0;
+    const double mjx = sel3(j_min, I.x0, I.x1, I.x2) - mjr * nx - J.x0, mjy = sel3(j_min, I.y0, I.y1, I.y2) - mjr * ny - J.y0;
+    fi[0] = fix; fi[1] = fiy; fi[2] = mix * fiy - miy * fix;
+    fj[0] = fjx; fj[1] = fjy; fj[2] = mjx * fjy - mjy * fjx;
+}
+
+struct EvalArgs {
+    const double *nbr;           // packed neighbour records in cell order (+ ghost tail)
+    const double2 *par;          // {-mass * k_soc, tau_0} in cell order (+ ghost tail)
+    Soa in;                      // planes (contact parameters, read through `order` only when a pair overlaps)
+    const int *order;            // sorted slot -> plane slot (nullptr: planes are in cell order)
+    int ghost_base;              // slots >= ghost_base are ghosts: their side of a pair is not stored (INT_MAX: none)
+    int ghost_left_end;          // ghost_base <= slot < ghost_left_end: left ghost column (sorts first)
+    PairBuf pb;
+};
+
+__device__ __forceinline__ void store_contribution(const PairBuf &pb, int a, int partner_key, double fx, double fy, double tq) {
+    const int k = atomicAdd(&pb.fill[a], 1);
+    double *e = pb.cres + ((size_t)pb.off[a] + k) * 4;
+    reinterpret_cast<double2 *>(e)[0] = make_double2(__longlong_as_double((long long)partner_key), fx);
+    reinterpret_cast<double2 *>(e)[1] = make_double2(fy, tq);
+}
+
+template <int MODEL>
+__global__ void __launch_bounds__(128, MODEL == 0 ? 6 : 4) k_pair_eval(const EvalArgs A) {
+    if (pairs_overflowed(A.pb)) return;
+    const long long np = (long long)A.pb.ctr[0];
+    const Soa &s = A.in;
+    for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < np; p += (long long)gridDim.x * blockDim.x) {
+        const int2 e = A.pb.pairs[p];
+        const int t = e.x, u = e.y;
+        const double2 qt = __ldg(A.par + t), qu = __ldg(A.par + u);
+        const PairPar pt = {qt.x, qt.y}, pu = {qu.x, qu.y};
+        double ft[3] = {0.0, 0.0, 0.0}, fu[3] = {0.0, 0.0, 0.0};
+        if (MODEL == 0) {
+            const double *rt = A.nbr + (size_t)t * REC_CIRC, *ru = A.nbr + (size_t)u * REC_CIRC;
+            const double2 p0 = ldg2(rt), v0 = ldg2(rt + 2), p1 = ldg2(ru), v1 = ldg2(ru + 2);
+            auto contact = [&](ContactPar &ct, ContactPar &cu) {
+                ct = ContactPar{0.0, 0.0, 0.0}; cu = ct;
+                if (t < A.ghost_base) { const int o = A.order ? A.order[t] : t; ct = ContactPar{s(MU, o), s(KAPPA, o), s(DAMPING, o)}; }
+                if (u < A.ghost_base) { const int o = A.order ? A.order[u] : u; cu = ContactPar{s(MU, o), s(KAPPA, o), s(DAMPING, o)}; }
+            };
+            pair_circular_both(p0.x, p0.y, v0.x, v0.y, __ldg(rt + 4), pt, p1.x, p1.y, v1.x, v1.y, __ldg(ru + 4), pu, contact, ft, fu);
+        } else {
+            // reference pair orientation: i is the lexicographically smaller (cell_x, cell_y, agent index).  The TRUE cell
+            // coordinates floor(p / c) (last two slots of the neighbour record) are compared, not the flat ids of the search
+            // lattice, so the convention does not depend on how the lattice was chosen (padded, fixed, clamped, per-strip).
+            // Agents of the same true cell share a flat cell, inside which the slots are ordered by agent index.
+            const double2 ca = ldg2(A.nbr + (size_t)t * REC_THREE + 14), cb = ldg2(A.nbr + (size_t)u * REC_THREE + 14);
+            const bool t_is_i = ca.x != cb.x ? ca.x < cb.x : (ca.y != cb.y ? ca.y < cb.y : true);
+            const int si = t_is_i ? t : u, sj = t_is_i ? u : t;
+            Three I, J;
+            load_three_rec(A.nbr, si, I);
+            load_three_rec(A.nbr, sj, J);
+            auto contact = [&](ContactPar &ci, ContactPar &cj) {
+                ci = ContactPar{0.0, 0.0, 0.0}; cj = ci;
+                if (si < A.ghost_base) { const int o = A.order ? A.order[si] : si; ci = ContactPar{s(MU, o), s(KAPPA, o), s(DAMPING, o)}; }
+                if (sj < A.ghost_base) { const int o = A.order ? A.order[sj] : sj; cj = ContactPar{s(MU, o), s(KAPPA, o), s(DAMPING, o)}; }
+            };
+            if (t_is_i) pair_three_both(I, J, pt, pu, contact, ft, fu);
+            else pair_three_both(I, J, pu, pt, contact, fu, ft);
+        }
+        // a side whose result is exactly zero adds nothing: not stored
+        const int key_t = (t >= A.ghost_base && t < A.ghost_left_end) ? t - GHOST_KEY_SHIFT : t;
+        const int key_u = (u >= A.ghost_base && u < A.ghost_left_end) ? u - GHOST_KEY_SHIFT : u;
+        if (t < A.ghost_base && (ft[0] != 0.0 || ft[1] != 0.0 || ft[2] != 0.0)) store_contribution(A.pb, t, key_u, ft[0], ft[1], ft[2]);
+        if (u < A.ghost_base && (fu[0] != 0.0 || fu[1] != 0.0 || fu[2] != 0.0)) store_contribution(A.pb, u, key_t, fu[0], fu[1], fu[2]);
+    }
+}
+
+// adds the contributions of agent `a` in ascending partner order (selection: the lists are a handful of entries long)
+__device__ __forceinline__ void gather_contributions(const PairBuf &pb, int a, bool torque, double &fx, double &fy, double &tq) {
+    const int n = pb.fill[a];
+    const double *e = pb.cres + (size_t)pb.off[a] * 4;
+    long long last = -0x7fffffffffffffffLL - 1;
+    for (int r = 0; r < n; ++r) {
+        long long best = 0x7fffffffffffffffLL;
+        int bi = 0;
+        for (int k = 0; k < n; ++k) {
+            const long long key = __double_as_longlong(e[(size_t)k * 4]);
+            if (key > last && key < best) { best = key; bi = k; }
+        }
+        const double2 v0 = *reinterpret_cast<const double2 *>(e + (size_t)bi * 4), v1 = *reinterpret_cast<const double2 *>(e + (size_t)bi * 4 + 2);
+        fx += v0.y; fy += v1.x;
+        if (torque) tq += v1.y;
+        last = best;
+    }
+}

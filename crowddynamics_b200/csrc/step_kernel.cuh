@@ -22,6 +22,7 @@
 // A pair dropped in phase 1 contributes exactly (0, 0) in the reference too, so results equal evaluating every candidate.
 #pragma once
 #include "kernels.cuh"
+#include "pair_kernels.cuh"
 
 constexpr int STEP_THREADS = 128;
 constexpr int DT_LOG_SLOTS = 1024;
@@ -31,12 +32,6 @@ constexpr int LCAP = 16;     // survivor list entries per lane between two flush
 #define STEP_CHUNK 4
 #endif
 constexpr int CHUNK = STEP_CHUNK;     // candidates classified between two list-capacity checks
-#define PREFILTER_EPS 1e-12
-#define BOUND_EPS 1e-9
-
-// packed neighbour records (doubles per agent)
-constexpr int REC_CIRC = 6;     // px py vx vy r -
-constexpr int REC_THREE = 16;   // px py vx vy ext rt rs - | lsx lsy rsx rsy ox oy cell_x cell_y
 
 struct StepArgs {
     Soa in, out;             // out == in unless integrating (then the new state is written to the other buffer)
@@ -59,6 +54,8 @@ struct StepArgs {
     double *dt_log;          // ring of DT_LOG_SLOTS entries: this step's dt goes to slot step % DT_LOG_SLOTS (or nullptr)
     unsigned long long seed; // Fluctuation: Philox key (with the step index)
     const unsigned long long *step_ptr;   // device-side step index (advanced by k_step_advance after every step)
+    PairBuf pb;              // PAIRS = 1: per-agent contributions written by k_pair_eval (pair_kernels.cuh)
+    int n_planes;            // planes of the model (PAIRS = 1: a step that is not applied still moves them to `out`)
 };
 
 struct WarpSmem {
@@ -67,18 +64,7 @@ struct WarpSmem {
     double res[3][32];       // results of one dealt round
 };
 
-__device__ __forceinline__ double2 ldg2(const double *p) { return __ldg(reinterpret_cast<const double2 *>(p)); }
-
 // ---- exact three-circle pair in the reference's (i, j) orientation, register-only (no dynamic indexing) ---------------
-struct Three {               // kinematics of one three-circle agent as the pair kernels need them
-    double x0, y0, x1, y1, x2, y2;   // torso, left shoulder, right shoulder centres
-    double rt, rs;           // torso / shoulder radius
-    double vx, vy;
-    double ox, oy;           // r_ts * (sin(phi), -cos(phi)): shoulder displacement (power_law.py:338-350, agents.py:483-484)
-};
-
-__device__ __forceinline__ double sel3(int k, double a, double b, double c) { return k == 0 ? a : (k == 1 ? b : c); }
-
 __device__ __forceinline__ void pair_three_exact(const Three &I, const Three &J, bool me_is_i, const ThreePar &me,
                                                  double &fx, double &fy, double &torque) {
     const double jx[3] = {J.x0, J.x1, J.x2}, jy[3] = {J.y0, J.y1, J.y2}, rj[3] = {J.rt, J.rs, J.rs};
@@ -167,13 +153,6 @@ __device__ __forceinline__ void sel_three(bool first, const Three &a, const Thre
     o.vx = first ? a.vx : b.vx; o.vy = first ? a.vy : b.vy; o.ox = first ? a.ox : b.ox; o.oy = first ? a.oy : b.oy;
 }
 
-__device__ __forceinline__ void load_three_rec(const double *__restrict__ nbr, int u, Three &k) {
-    const double *r = nbr + (size_t)u * REC_THREE;
-    const double2 a = ldg2(r), b = ldg2(r + 2), c = ldg2(r + 4), d = ldg2(r + 6), e = ldg2(r + 8), f = ldg2(r + 10), g = ldg2(r + 12);
-    k.x0 = a.x; k.y0 = a.y; k.vx = b.x; k.vy = b.y; k.rt = c.y; k.rs = d.x;
-    k.x1 = e.x; k.y1 = e.y; k.x2 = f.x; k.y2 = f.y; k.ox = g.x; k.oy = g.y;
-}
-
 // =====================================================================================================================
 #ifndef STEP_MINB_CIRC
 #define STEP_MINB_CIRC 8
@@ -181,12 +160,17 @@ __device__ __forceinline__ void load_three_rec(const double *__restrict__ nbr, i
 #ifndef STEP_MINB_THREE
 #define STEP_MINB_THREE 4
 #endif
-template <int MODEL>
-__global__ void __launch_bounds__(STEP_THREADS, MODEL == 0 ? STEP_MINB_CIRC : STEP_MINB_THREE) k_step(const StepArgs A) {
-    __shared__ WarpSmem s_warp[STEP_WARPS];
-    const int t = blockIdx.x * STEP_THREADS + threadIdx.x;
+// PAIRS = 0: agent-agent interactions classified and evaluated inside this kernel, from every agent's side (full 3x3
+//            stencil; the one-kernel variant, kept as an independent cross-check and for cdb_set_variant(2));
+// PAIRS = 1: the interactions were evaluated once per pair by k_sweep / k_pair_eval; this kernel adds every agent's
+//            contributions in ascending partner order (the order PAIRS = 0 meets them).
+template <int MODEL, int PAIRS>
+__global__ void __launch_bounds__(PAIRS ? 256 : STEP_THREADS, PAIRS ? (MODEL == 0 ? 3 : 2) : (MODEL == 0 ? STEP_MINB_CIRC : STEP_MINB_THREE))
+k_step(const StepArgs A) {
+    __shared__ WarpSmem s_warp[PAIRS ? 1 : STEP_WARPS];
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
-    WarpSmem &W = s_warp[threadIdx.x >> 5];
+    WarpSmem &W = s_warp[PAIRS ? 0 : (threadIdx.x >> 5)];
     const int t0 = t - lane;             // first target of this warp
     const bool active = t < eff_n(A.n, A.n_dev);
     const Soa &s = A.in;
@@ -194,6 +178,16 @@ __global__ void __launch_bounds__(STEP_THREADS, MODEL == 0 ? STEP_MINB_CIRC : ST
     const int tt = active ? t : 0;       // inactive lanes read slot 0 and never write
     const int oo = A.order ? A.order[tt] : tt;   // where this agent's planes live in `in`
     constexpr int REC = MODEL == 0 ? REC_CIRC : REC_THREE;
+    if (PAIRS && (A.flags & CDB_STEP_AGENT_AGENT) && pairs_overflowed(A.pb)) {
+        // the pair list did not hold this step's pairs: the step is NOT applied (the host grows the list and repeats it);
+        // an integrating step still has to leave the unchanged state in `out`, which the host makes current
+        if (active && (A.flags & CDB_STEP_INTEGRATOR)) {
+            for (int k = 0; k < A.n_planes; ++k) A.out(k, t) = s(k, oo);
+            A.out.id[t] = s.id[oo];
+            A.out.target[t] = s.target[oo];
+        }
+        return;
+    }
 
     // ---- Navigation, Orientation, Adjusting (logic.py:149-165,258-261,89-94) --------------------------------------------
     double e0x = s(E0X, oo), e0y = s(E0Y, oo);
@@ -215,7 +209,9 @@ __global__ void __launch_bounds__(STEP_THREADS, MODEL == 0 ? STEP_MINB_CIRC : ST
     }
 
     // ---- AgentAgentInteractions (interactions.py:191-205) -----------------------------------------------------------------
-    if (A.flags & CDB_STEP_AGENT_AGENT) {
+    if (PAIRS) {
+        if (active && (A.flags & CDB_STEP_AGENT_AGENT)) gather_contributions(A.pb, t, MODEL == 1, fx, fy, tq);
+    } else if (A.flags & CDB_STEP_AGENT_AGENT) {
         const double *__restrict__ nbr = A.nbr;
         // what phase 1 needs of the target: centre, velocity, radius (circular) / body extent (three-circle)
         double mpx, mpy, mvx, mvy, mr;

@@ -157,6 +157,23 @@ class DeviceAgents:
         _lib.check(self.lib.cdb_profile_read(self.handle, ms, C.byref(steps)))
         return ms[0], ms[1], ms[2], steps.value
 
+    def profile_read_phases(self):
+        """-> (ms_blocklist_and_pre, ms_pair_sweep, ms_pair_eval, ms_step_kernel, ms_post, steps) summed since the last read."""
+        ms = (C.c_double * 5)()
+        steps = C.c_int64()
+        _lib.check(self.lib.cdb_profile_read_phases(self.handle, ms, C.byref(steps)))
+        return ms[0], ms[1], ms[2], ms[3], ms[4], steps.value
+
+    def set_pair_capacity(self, pairs):
+        """Fix the capacity of the pair list of kernel variant 3 (0 = automatic); a test hook for the repeat path."""
+        _lib.check(self.lib.cdb_set_pair_capacity(self.handle, int(pairs)))
+
+    def pair_stats(self):
+        """-> (capacity, pairs listed by the last step, steps repeated after an overflow)."""
+        a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
+        _lib.check(self.lib.cdb_get_pair_stats(self.handle, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
     # -- block list exports ------------------------------------------------------------------------------------------
     def build_block_list(self, cell_size):
         _lib.check(self.lib.cdb_build_block_list(self.handle, float(cell_size)))

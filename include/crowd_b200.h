@@ -127,13 +127,28 @@ int cdb_get_time(cdb_sim *sim, double *time_tot, int64_t *iterations);
 int cdb_set_graphs(cdb_sim *sim, int enable);
 
 /* ---- instrumentation (no reference counterpart) -------------------------------------------------------------------- */
-/* agent-agent kernel variant: 2 (default) = two-phase fused step kernel, 1 = one-phase kernels, kept as a cross-check */
+/* agent-agent kernel variant:
+ *   3 (default) = every unordered pair of the block list classified and evaluated ONCE, as the reference's pair loop does
+ *       (core/interactions.py:69-70,100-104 update both agents from one evaluation): forward-half-stencil sweep -> pair
+ *       list -> one evaluation per pair -> per-agent sums in a fixed order;
+ *   2 = two-phase fused step kernel that evaluates every pair from both agents' sides (bit-identical results to 3);
+ *   1 = one-phase kernels.  2 and 1 are kept as independent cross-checks. */
 int cdb_set_variant(cdb_sim *sim, int variant);
+/* Variant 3 keeps the listed pairs of one step in a buffer that grows on demand: a step that finds more pairs than fit is
+ * not applied on the device and is transparently repeated after growing the buffer.  cdb_set_pair_capacity fixes the
+ * capacity (0 = automatic, 8 pairs per agent to start with) -- a test hook for the repeat path; cdb_get_pair_stats reports
+ * the capacity, the pairs listed by the most recent step and how many steps had to be repeated so far. */
+int cdb_set_pair_capacity(cdb_sim *sim, int64_t pairs);
+int cdb_get_pair_stats(cdb_sim *sim, int64_t *capacity, int64_t *found_last, int64_t *overflows);
 int64_t cdb_launch_count(const cdb_sim *sim);            /* kernels launched by this sim so far */
 int cdb_profile_enable(cdb_sim *sim, int enable);        /* CUDA-event timing of the phases of cdb_step on the sim's stream */
 /* ms[0] = per-agent nodes before + block list build, ms[1] = agent-agent kernel, ms[2] = obstacle + integrator + reset;
  * summed over the profiled steps since the last read (at most 4096 steps are recorded). */
 int cdb_profile_read(cdb_sim *sim, double ms[3], int64_t *steps);
+/* finer split of the same events: ms[0] = per-agent nodes before + block list, ms[1] = pair sweep (+ region allocation),
+ * ms[2] = pair evaluation, ms[3] = step kernel (gather of the pair results, walls, integrator, reset), ms[4] = rest.
+ * Variants 1 / 2 report their whole agent-agent (+ fused step) kernel in ms[3]. */
+int cdb_profile_read_phases(cdb_sim *sim, double ms[5], int64_t *steps);
 
 /* ---- block list: debug / parity exports (cell_lists.add_to_cells & iter_nearest_neighbors, call sites
  * core/interactions.py:191-205; spec core/block_list.py:28-52) ---------------------------------------------------- */

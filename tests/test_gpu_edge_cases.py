@@ -19,7 +19,7 @@ def _mid(model):
     return MODEL_CIRCULAR if model == 'circular' else MODEL_THREE_CIRCLE
 
 
-def _one_step_forces(agents, obstacles, variant=2):
+def _one_step_forces(agents, obstacles, variant=3):
     dev = DeviceAgents(_mid('circular' if agents.dtype.itemsize == 228 else 'three_circle'))
     dev.set_variant(variant)
     dev.upload(agents)
@@ -40,7 +40,7 @@ def _oracle_forces(agents, obstacles):
 
 def _check(agents, obstacles, tol=1e-9):
     ref = _oracle_forces(agents, obstacles)
-    for variant in (2, 1):
+    for variant in (3, 2, 1):
         got = _one_step_forces(agents, obstacles, variant)
         assert vec_rel_err(got['force'], ref['force']) <= tol, variant
         if 'torque' in agents.dtype.names:

@@ -64,7 +64,7 @@ def test_equal_velocities_mean_no_social_force_1m(crowd):
 def test_two_gpu_implementations_agree_and_are_deterministic_1m(crowd):
     model, agents, obstacles, side = crowd
     out = []
-    for variant in (2, 2, 1):
+    for variant in (3, 3, 1, 2):
         dev = DeviceAgents(_mid(model))
         dev.set_variant(variant)
         dev.upload(agents)
@@ -74,11 +74,13 @@ def test_two_gpu_implementations_agree_and_are_deterministic_1m(crowd):
         dev.download(f)
         dev.close()
         out.append(f)
-    assert (out[0]['force'] == out[1]['force']).all()                 # bit-reproducible
-    assert vec_rel_err(out[0]['force'], out[2]['force']) <= 1e-10     # fused two-phase kernel vs one-phase kernels
+    assert (out[0]['force'] == out[1]['force']).all()                 # bit-reproducible (whatever order the atomics resolved in)
+    assert vec_rel_err(out[0]['force'], out[2]['force']) <= 1e-10     # once-per-pair pipeline vs one-phase kernels
+    assert (out[0]['force'] == out[3]['force']).all()                 # ... and bit-identical to the both-sides fused kernel
     if model == 'three_circle':
         assert (out[0]['torque'] == out[1]['torque']).all()
         assert vec_rel_err(out[0]['torque'], out[2]['torque']) <= 1e-10
+        assert (out[0]['torque'] == out[3]['torque']).all()
 
 
 def test_window_against_oracle_1m(crowd):

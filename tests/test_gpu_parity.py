@@ -281,7 +281,7 @@ def test_fused_kernel_matches_one_phase_kernel(model, density):
     a, obs, side = S.uniform_crowd(n, model, density=density, seed=7, overlap_fraction=0.03 if density > 1 else 0.0)
     mid = MODEL_CIRCULAR if model == 'circular' else MODEL_THREE_CIRCLE
     out = {}
-    for variant in (1, 2):
+    for variant in (1, 2, 3):
         dev = DeviceAgents(mid)
         dev.set_variant(variant)
         dev.upload(a)
@@ -296,6 +296,10 @@ def test_fused_kernel_matches_one_phase_kernel(model, density):
     _assert_forces(out[2][0], out[1][0], model, tol=1e-10)
     np.testing.assert_allclose(out[1][2], out[2][2], rtol=1e-9, atol=0)
     assert np.abs(out[1][1]['position'] - out[2][1]['position']).max() <= 1e-9
+    # the once-per-pair pipeline (variant 3, the default) adds the same per-pair numbers in the same order as variant 2
+    assert rel_err_fields(out[3][0], out[2][0])[0] == 0
+    assert (out[3][2] == out[2][2]).all()
+    assert rel_err_fields(out[3][1], out[2][1])[0] == 0
     # and the one-phase path against the oracle on the same crowd (single step forces)
     ref = a.copy()
     O.navigation(ref, [S.direction_field(0.5, (0, 0, side, side), 'swirl')]); O.orientation(ref); O.adjusting(ref)
