@@ -216,6 +216,8 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-fp64-peak', action='store_true', help='skip the DFMA peak micro-benchmark (used under ncu)')
     ap.add_argument('--e2e-steps', type=int, default=3)
+    ap.add_argument('--refinement', type=int, default=0, help='search lattice: 0 automatic (cell_size / 2 where valid), 1 cell_size')
+    ap.add_argument('--variant', type=int, default=3, help='agent-agent kernel variant (3 once-per-pair, 2 both-sides fused kernel)')
     args = ap.parse_args()
 
     rank = int(os.environ.get('RANK', '0'))
@@ -256,6 +258,8 @@ def main():
             field = make_field(side)
         dev = DeviceAgents(mid, capacity=n, device=local_rank)
         dev.set_stream(torch.cuda.current_stream().cuda_stream)
+        dev.set_variant(args.variant)
+        dev.set_search_refinement(args.refinement)
         dev.set_obstacles(obstacles)
         dev.set_navigation_field(0, *field)
         # pinned host image of simulation.agents.array (packed records), the e2e leg copies it every step

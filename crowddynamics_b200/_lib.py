@@ -74,6 +74,8 @@ def _signatures(L):
         'cdb_profile_read': (i32, [vp, pf64, pi64]),
         'cdb_profile_read_phases': (i32, [vp, pf64, pi64]),
         'cdb_set_pair_capacity': (i32, [vp, i64]),
+        'cdb_set_search_refinement': (i32, [vp, i32]),
+        'cdb_get_ext_max': (i32, [vp, pf64]),
         'cdb_get_pair_stats': (i32, [vp, pi64, pi64, pi64]),
         'cdb_build_block_list': (i32, [vp, f64]),
         'cdb_get_grid': (i32, [vp, pi64]),

@@ -22,6 +22,7 @@
 
 #include "kernels.cuh"
 #include "step_kernel.cuh"
+#include "finish_kernel.cuh"
 #include "strip_kernels.cuh"
 #include "collective_kernels.cuh"
 
@@ -106,6 +107,11 @@ struct cdb_sim {
     Grid *d_grid = nullptr;
     double cell_size = 0.0;
     double cell_size_lattice = 0.0;
+    int fine = 1;                    // the current tables bin on cell_size / fine (1, or 2: the twice finer search lattice)
+    int fine_lattice = 1;            // refinement the kept padded lattice was derived for
+    int fine_request = 0;            // cdb_set_search_refinement: 0 automatic, 1 / 2 forced (2 only where it is valid)
+    double ext_max = 1e300;          // bound on any agent's radius / body extent (k_ext_max at upload)
+    unsigned long long *d_extmax = nullptr, *h_extmax = nullptr;
     bool tables_valid = false;
     int64_t cell_capacity = 0;
     int *d_cell_count = nullptr, *d_cell_start = nullptr, *d_cell_fill = nullptr;
@@ -153,6 +159,8 @@ struct cdb_sim {
     // strip decomposition
     bool strip = false;
     int has_left = 0, has_right = 0;
+    int strip_fine = 1;              // search refinement of the strip lattice (fixed by cdb_set_strip)
+    long long strip_ix0 = 0, strip_col_lo = 0, strip_col_hi = 0;   // cell_size columns: lattice origin, owned range
     int64_t halo_cap = 0, mig_cap = 0;
     int64_t n_dead = 0;              // slots vacated by migrants (dropped at the next sort)
     int *d_counters = nullptr;       // [0] migrants left, [1] migrants right, [2] appended
@@ -266,6 +274,7 @@ int check_device_error(cdb_sim *sim) {
     CK(cudaMemsetAsync(sim->d_error, 0, sizeof(int), sim->stream));
     if (e == ERR_NONFINITE) return fail(CDB_ERR_INVALID_VALUE, "non-finite agent position encountered on device");
     if (e == ERR_CELL_RANGE) return fail(CDB_ERR_CAPACITY, "cell lattice too large (more than 2^31 cells)");
+    if (e == ERR_PAIR_OVERFLOW) return fail(CDB_ERR_CAPACITY, "pair list overflow in strip mode (a strip step cannot be repeated): raise cdb_set_pair_capacity");
     return fail(CDB_ERR_CUDA, "device error flag %d", e);
 }
 
@@ -282,8 +291,25 @@ int prof_mark(cdb_sim *sim) {
 }
 
 // ---- block list --------------------------------------------------------------------------------------------------
-int build_block_list(cdb_sim *sim, double cell_size, bool padded_lattice = false, unsigned long long *vmax = nullptr, bool physical = true) {
+// Search lattice refinement for the pair search.  Cells of cell_size / 2 (exact in binary: floor(p / (c/2)) >> 1 ==
+// floor(p / c)) with a reach of 2 cells cover every pair closer than cell_size, all of which lie in the same or in adjacent
+// cell_size cells -- so when no pair can interact beyond cell_size (3 + 2 max R < cell_size; true for every body type of the
+// reference with its default cell_size = 3.6) the swept area drops from 9 c^2 to 6.25 c^2 with the same pair set.  The debug
+// exports always report the cell_size lattice (core/block_list.py:28-52).
+int search_refinement(const cdb_sim *sim, double cell_size) {
+    if (sim->strip) return sim->strip_fine;
+    if (sim->fine_request == 1 || sim->lattice_fixed || sim->variant == 1) return 1;
+    // automatic: circular agents only -- measured (profiles/, round 2): the finer lattice takes 15 % off the sweep for both
+    // models, but its pair list is less coherent (neighbouring list entries belong to different targets) and the branchy
+    // three-circle evaluation loses more to divergence (21 -> 14 of 32 lanes active) than the sweep gains
+    if (sim->fine_request == 0 && sim->model != CDB_MODEL_CIRCULAR) return 1;
+    return (SIGTH_SOC + 2.0 * sim->ext_max) * (1.0 + 1e-9) < cell_size ? 2 : 1;
+}
+
+int build_block_list(cdb_sim *sim, double cell_size, bool padded_lattice = false, unsigned long long *vmax = nullptr, bool physical = true,
+                     int fine = 1) {
     if (!(cell_size > 0.0) || !std::isfinite(cell_size)) return fail(CDB_ERR_INVALID_VALUE, "cell_size must be > 0");
+    const double cs = cell_size / fine;          // bin size of the search lattice
     const int64_t n = sim->n;                   // slots in use, including the ones vacated by migrants (upper bound with dev_counts)
     const int64_t live = sim->dev_counts ? sim->n : sim->n - sim->n_dead;
     const int *slots_dev = sim->dev_counts ? &sim->d_counts->slots : nullptr;
@@ -303,11 +329,13 @@ int build_block_list(cdb_sim *sim, double cell_size, bool padded_lattice = false
     // padded_lattice (fused steps): derive the lattice from the bounding box once, pad it by one cell and keep it for the
     // next steps -- cells stay anchored at multiples of cell_size and agents that leave the lattice are binned into its
     // border cells (adjacency is preserved by clamping), so neighbour sets and forces do not depend on this choice.
-    const bool reuse = padded_lattice && sim->auto_lattice_valid && sim->cell_size_lattice == cell_size && sim->auto_lattice_age < 64;
+    const bool reuse = padded_lattice && sim->auto_lattice_valid && sim->cell_size_lattice == cell_size && sim->fine_lattice == fine &&
+                       sim->auto_lattice_age < 64;
+    sim->fine = fine;
     if (reuse) sim->auto_lattice_age++;
     if (!sim->lattice_fixed && !reuse) {
         LAUNCH(sim, k_bbox_init, 1, 32, 0, sim->d_bbox);
-        LAUNCH(sim, k_bbox, (cdiv(n, T * 4) < 1184 ? cdiv(n, T * 4) : 1184), T, 0, sim->cur, (int)n, cell_size, sim->d_bbox, sim->d_error);
+        LAUNCH(sim, k_bbox, (cdiv(n, T * 4) < 1184 ? cdiv(n, T * 4) : 1184), T, 0, sim->cur, (int)n, cs, sim->d_bbox, sim->d_error);
         CK(cudaMemcpyAsync(sim->h_bbox, sim->d_bbox, 4 * sizeof(long long), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         CKS(check_device_error(sim));
@@ -315,18 +343,19 @@ int build_block_list(cdb_sim *sim, double cell_size, bool padded_lattice = false
         long long nx = x1 - x0 + 1, ny = y1 - y0 + 1;
         if (nx <= 0 || ny <= 0 || (double)nx * (double)ny > 2.0e9)
             return fail(CDB_ERR_CAPACITY, "block list of %lld x %lld cells is too large", nx, ny);
-        if (padded_lattice) { x0 -= 1; y0 -= 1; nx += 2; ny += 2; }
+        if (padded_lattice) { x0 -= fine; y0 -= fine; nx += 2 * fine; ny += 2 * fine; }
         sim->grid = Grid{x0, y0, nx, ny, nx * ny, 0, nx - 1};
         sim->auto_lattice_valid = padded_lattice;
         sim->auto_lattice_age = 0;
         sim->cell_size_lattice = cell_size;
+        sim->fine_lattice = fine;
         CK(cudaMemcpyAsync(sim->d_grid, &sim->grid, sizeof(Grid), cudaMemcpyHostToDevice, st));
     }
     const int64_t ncell = sim->grid.ncell;
     CKS(ensure_cells(sim, ncell));
     CK(cudaMemsetAsync(sim->d_cell_count, 0, ncell * sizeof(int), st));
     CK(cudaMemsetAsync(sim->d_cell_fill, 0, ncell * sizeof(int), st));
-    if (n > 0) LAUNCH(sim, k_cell_count, cdiv(n, T), T, 0, sim->cur, (int)n, cell_size, sim->d_grid, sim->d_cell_of_slot, sim->d_cell_count, sim->d_error, vmax, slots_dev);
+    if (n > 0) LAUNCH(sim, k_cell_count, cdiv(n, T), T, 0, sim->cur, (int)n, cs, sim->d_grid, sim->d_cell_of_slot, sim->d_cell_count, sim->d_error, vmax, slots_dev);
     // exclusive scan count -> start
     const int nblk = cdiv(ncell, SCAN_TILE);
     LAUNCH(sim, k_scan_tiles, nblk, SCAN_THREADS, 0, sim->d_cell_count, sim->d_cell_start, (int)ncell, sim->d_scan_partials);
@@ -409,7 +438,7 @@ StepArgs step_args(cdb_sim *sim, unsigned flags, double dt_min, double dt_max, d
     return a;
 }
 
-inline bool use_pairs(const cdb_sim *sim) { return sim->variant == 3 && !sim->strip; }
+inline bool use_pairs(const cdb_sim *sim) { return sim->variant == 3; }
 
 // allocations of variant 3, made OUTSIDE stream capture (before steps are issued): 8 pairs per agent to start with, grown
 // by settle_pairs() when a step gets close to or beyond the capacity
@@ -421,7 +450,7 @@ int prepare_pairs(cdb_sim *sim) {
         sim->h_pctr[0] = sim->h_pctr[1] = sim->h_pctr[2] = 0;
     }
     if (sim->pair_cap_request > 0) return ensure_pairs(sim, sim->pair_cap_request);
-    const int64_t want = std::max<int64_t>(8 * sim->n, 1 << 16);
+    const int64_t want = std::max<int64_t>((sim->strip ? 16 : 8) * std::max(sim->n, sim->capacity / 2), 1 << 16);
     if (!sim->pb.pairs || sim->pb.cap < want / 2) CKS(ensure_pairs(sim, want));
     return CDB_OK;
 }
@@ -440,18 +469,25 @@ int launch_pairs(cdb_sim *sim) {
     a.n_dev = sim->dev_counts ? &sim->d_counts->live : nullptr;
     a.grid = sim->d_grid;
     a.cell_sorted = sim->d_cell_of_slot; a.cell_start = sim->d_cell_start; a.cell_count = sim->d_cell_count;
-    a.ghost_base = -1; a.n_ghost = 0;
-    a.reach = 1;
+    a.ghost_base = -1; a.n_ghost = 0; a.ghost_cells = 0;
+    if (sim->strip) {
+        a.ghost_base = (int)sim->capacity;
+        a.n_ghost = sim->has_left ? (int)sim->halo_cap : 0;
+        a.ghost_cells = (int)(sim->grid.cx_lo * sim->grid.ny);
+    }
+    a.reach = sim->fine;
     a.pb = sim->pb;
+    a.pb.fatal = sim->strip ? sim->d_error : nullptr;
     const int blocks = cdiv(n + a.n_ghost, SW_THREADS);
     if (sim->model == CDB_MODEL_CIRCULAR) LAUNCH(sim, k_sweep<0>, blocks, SW_THREADS, 0, a);
     else LAUNCH(sim, k_sweep<1>, blocks, SW_THREADS, 0, a);
-    LAUNCH(sim, k_pair_alloc, cdiv(n, 256), 256, 0, sim->pb, (int)n);
+    LAUNCH(sim, k_pair_alloc, cdiv(n, 256), 256, 0, a.pb, (int)n);
     CKS(prof_mark(sim));
     EvalArgs e{};
     e.nbr = sim->d_nbr; e.par = sim->d_par; e.in = sim->cur;
     e.order = sim->perm_valid ? sim->d_order : nullptr;
     e.ghost_base = 0x7fffffff; e.ghost_left_end = 0x7fffffff;
+    if (sim->strip) { e.ghost_base = (int)sim->capacity; e.ghost_left_end = (int)(sim->capacity + sim->halo_cap); }
     e.pb = sim->pb;
     // persistent grid-stride launch: the number of pairs is only known on the device
     const int eval_blocks = (int)std::min<int64_t>(cdiv(std::max<int64_t>(4 * n, 128), 128), (int64_t)sim->sm_count * (sim->model == CDB_MODEL_CIRCULAR ? 16 : 8));
@@ -471,18 +507,15 @@ int launch_step_kernel(cdb_sim *sim, unsigned flags, double dt_min, double dt_ma
     StepArgs a = step_args(sim, flags, dt_min, dt_max, dt_log);
     a.pb = sim->pb;
     a.n_planes = sim->n_planes;
+    a.reach = sim->fine;
     const int smem = 0;
     if (a.n > 0) {
         if (pairs) {
-            auto k0 = k_step<0, 1>;
-            auto k1 = k_step<1, 1>;
-            if (sim->model == CDB_MODEL_CIRCULAR) LAUNCH(sim, k0, cdiv(a.n, 256), 256, smem, a);
-            else LAUNCH(sim, k1, cdiv(a.n, 256), 256, smem, a);
+            if (sim->model == CDB_MODEL_CIRCULAR) LAUNCH(sim, k_finish<0>, cdiv(a.n, FIN_THREADS), FIN_THREADS, smem, a);
+            else LAUNCH(sim, k_finish<1>, cdiv(a.n, FIN_THREADS), FIN_THREADS, smem, a);
         } else {
-            auto k0 = k_step<0, 0>;
-            auto k1 = k_step<1, 0>;
-            if (sim->model == CDB_MODEL_CIRCULAR) LAUNCH(sim, k0, cdiv(a.n, STEP_THREADS), STEP_THREADS, smem, a);
-            else LAUNCH(sim, k1, cdiv(a.n, STEP_THREADS), STEP_THREADS, smem, a);
+            if (sim->model == CDB_MODEL_CIRCULAR) LAUNCH(sim, k_step<0>, cdiv(a.n, STEP_THREADS), STEP_THREADS, smem, a);
+            else LAUNCH(sim, k_step<1>, cdiv(a.n, STEP_THREADS), STEP_THREADS, smem, a);
         }
     } else if (flags & CDB_STEP_INTEGRATOR) {
         LAUNCH(sim, k_integrate, 1, 32, 0, sim->cur, 0, sim->model, dt_min, dt_max, sim->d_vmax, sim->d_dt);
@@ -539,7 +572,7 @@ int launch_agent_agent(cdb_sim *sim) {
 }
 int node_agent_agent(cdb_sim *sim, double cell_size) {
     CKS(prepare_pairs(sim));
-    CKS(build_block_list(sim, cell_size, false, nullptr, sim->variant == 1));
+    CKS(build_block_list(sim, cell_size, false, nullptr, sim->variant == 1, search_refinement(sim, cell_size)));
     for (int attempt = 0; attempt < 8; ++attempt) {
         CKS(launch_agent_agent(sim));
         if (!use_pairs(sim)) return CDB_OK;
@@ -626,6 +659,8 @@ int cdb_create(int device, int model, int64_t capacity, cdb_sim **out) {
         CKS(dev_alloc(&sim->d_dt, 2));
         CKS(dev_alloc(&sim->d_dt_log, DT_LOG));
         CKS(dev_alloc(&sim->d_stepctr, 1));
+        CKS(dev_alloc(&sim->d_extmax, 1));
+        CK(cudaMallocHost((void **)&sim->h_extmax, sizeof(unsigned long long)));
         CK(cudaMemset(sim->d_stepctr, 0, sizeof(unsigned long long)));
         CKS(dev_alloc(&sim->d_error, 1));
         CKS(dev_alloc(&sim->d_pair_count, 1));
@@ -668,7 +703,7 @@ int cdb_destroy(cdb_sim *sim) {
     cudaFree(sim->d_nav); cudaFree(sim->d_vmax); cudaFree(sim->d_dt); cudaFree(sim->d_dt_log); cudaFreeHost(sim->h_dt);
     for (auto e : sim->ev_pool) cudaEventDestroy(e);
     if (sim->graph_exec) cudaGraphExecDestroy(sim->graph_exec);
-    cudaFree(sim->d_stepctr);
+    cudaFree(sim->d_stepctr); cudaFree(sim->d_extmax); cudaFreeHost(sim->h_extmax);
     cudaFree(sim->d_error); cudaFreeHost(sim->h_error); cudaFree(sim->d_pair_count);
     cudaFree(sim->d_counters); cudaFreeHost(sim->h_counters); cudaFree(sim->d_counts); cudaFreeHost(sim->h_counts);
     if (sim->own_stream && sim->stream) cudaStreamDestroy(sim->stream);
@@ -720,8 +755,18 @@ int cdb_upload_agents_aos(cdb_sim *sim, const void *agents, int64_t n, int64_t i
         LAUNCH(sim, k_unpack_aos<1>, cdiv(n, AOS_REC_PER_BLOCK), AOS_REC_PER_BLOCK, smem, sim->d_aos, (int)n, sim->cur);
     CK(cudaGetLastError());
     if (sim->dev_counts) LAUNCH(sim, k_counts_set, 1, 32, 0, sim->d_counts, (int)n);
+    // bound on the radii / body extents: decides whether the finer search lattice is valid (search_refinement)
+    CK(cudaMemsetAsync(sim->d_extmax, 0, sizeof(unsigned long long), sim->stream));
+    LAUNCH(sim, k_ext_max, (cdiv(n, 1024) < 1184 ? cdiv(n, 1024) : 1184), 256, 0, sim->cur, (int)n, sim->model, sim->d_extmax);
+    CK(cudaMemcpyAsync(sim->h_extmax, sim->d_extmax, sizeof(unsigned long long), cudaMemcpyDeviceToHost, sim->stream));
     // the host buffer may be pageable and reused by the caller right away
     CK(cudaStreamSynchronize(sim->stream));
+    {
+        const unsigned long long k = *sim->h_extmax;
+        const unsigned long long b = (k & 0x8000000000000000ULL) ? (k & 0x7fffffffffffffffULL) : ~k;
+        double e; memcpy(&e, &b, sizeof(e));
+        sim->ext_max = k == 0 ? 0.0 : e;
+    }
     return CDB_OK;
 }
 
@@ -883,7 +928,7 @@ static int issue_step(cdb_sim *sim, uint32_t flags, double cell_size, double dt_
     } else {
         const bool need_vmax = flags & CDB_STEP_INTEGRATOR;
         if (need_vmax) LAUNCH(sim, k_vmax_init, 1, 32, 0, sim->d_vmax);
-        if (flags & CDB_STEP_AGENT_AGENT) CKS(build_block_list(sim, cell_size, true, need_vmax ? sim->d_vmax : nullptr, false));
+        if (flags & CDB_STEP_AGENT_AGENT) CKS(build_block_list(sim, cell_size, true, need_vmax ? sim->d_vmax : nullptr, false, search_refinement(sim, cell_size)));
         else if (need_vmax && sim->n > 0) LAUNCH(sim, k_vmax, (cdiv(sim->n, 1024) < 1184 ? cdiv(sim->n, 1024) : 1184), 256, 0, sim->cur, (int)sim->n, sim->d_vmax);
         CKS(prof_mark(sim));
         CKS(launch_step_kernel(sim, flags, dt_min, dt_max, log));
@@ -906,7 +951,7 @@ static bool graph_usable(cdb_sim *sim, uint32_t flags, double cell_size) {
     if (!(flags & CDB_STEP_AGENT_AGENT) || !(flags & CDB_STEP_INTEGRATOR)) return false;
     if (sim->lattice_fixed) return sim->cell_capacity >= sim->grid.ncell;
     return sim->auto_lattice_valid && sim->cell_size_lattice == cell_size && sim->auto_lattice_age + 2 <= 64 &&
-           sim->cell_capacity >= sim->grid.ncell;
+           sim->fine_lattice == search_refinement(sim, cell_size) && sim->cell_capacity >= sim->grid.ncell;
 }
 
 static int run_graph_pair(cdb_sim *sim, uint32_t flags, double cell_size, double dt_min, double dt_max, bool log_dt) {
@@ -996,6 +1041,23 @@ int cdb_step(cdb_sim *sim, uint32_t flags, double cell_size, double dt_min, doub
     return CDB_OK;
 }
 
+int cdb_set_search_refinement(cdb_sim *sim, int refinement) {
+    SIM_ENTRY();
+    if (refinement < 0 || refinement > 2) return fail(CDB_ERR_INVALID_VALUE, "refinement must be 0 (automatic), 1 or 2");
+    sim->fine_request = refinement;
+    sim->tables_valid = false;
+    sim->auto_lattice_valid = false;
+    sim->state_version++;
+    return CDB_OK;
+}
+
+int cdb_get_ext_max(cdb_sim *sim, double *ext_max) {
+    SIM_ENTRY();
+    if (!ext_max) return fail(CDB_ERR_INVALID_VALUE, "ext_max is NULL");
+    *ext_max = sim->ext_max;
+    return CDB_OK;
+}
+
 int cdb_set_pair_capacity(cdb_sim *sim, int64_t pairs) {
     SIM_ENTRY();
     if (pairs < 0) return fail(CDB_ERR_INVALID_VALUE, "negative pair capacity");
@@ -1077,8 +1139,15 @@ int cdb_get_time(cdb_sim *sim, double *time_tot, int64_t *iterations) {
 // ---- block list exports -------------------------------------------------------------------------------------------
 int cdb_build_block_list(cdb_sim *sim, double cell_size) { SIM_ENTRY(); return build_block_list(sim, cell_size, false, nullptr, false); }
 
+// the exports describe the cell_size lattice of the reference; tables built on the finer search lattice are rebuilt
+static int coarse_tables(cdb_sim *sim) {
+    if (sim->tables_valid && sim->fine != 1) return build_block_list(sim, sim->cell_size, false, nullptr, false, 1);
+    return CDB_OK;
+}
+
 int cdb_get_grid(cdb_sim *sim, int64_t grid[4]) {
     SIM_ENTRY();
+    CKS(coarse_tables(sim));
     if (!sim->tables_valid) return fail(CDB_ERR_STATE, "no block list has been built for the current positions");
     grid[0] = sim->grid.ix_min; grid[1] = sim->grid.iy_min; grid[2] = sim->grid.nx; grid[3] = sim->grid.ny;
     return CDB_OK;
@@ -1086,6 +1155,7 @@ int cdb_get_grid(cdb_sim *sim, int64_t grid[4]) {
 
 int cdb_get_cell_ids(cdb_sim *sim, int64_t *cell_of_agent, int64_t n) {
     SIM_ENTRY();
+    CKS(coarse_tables(sim));
     if (!sim->tables_valid) return fail(CDB_ERR_STATE, "no block list has been built for the current positions");
     if (n != sim->n) return fail(CDB_ERR_INVALID_VALUE, "size mismatch");
     if (n == 0) return CDB_OK;
@@ -1100,6 +1170,7 @@ int cdb_get_cell_ids(cdb_sim *sim, int64_t *cell_of_agent, int64_t n) {
 
 int cdb_get_cell_tables(cdb_sim *sim, int64_t *points_indices, int64_t n, int64_t *cells_count, int64_t *cells_offset, int64_t n_cells) {
     SIM_ENTRY();
+    CKS(coarse_tables(sim));
     if (!sim->tables_valid) return fail(CDB_ERR_STATE, "no block list has been built for the current positions");
     if (n != sim->n || n_cells != sim->grid.ncell) return fail(CDB_ERR_INVALID_VALUE, "size mismatch (n %lld vs %lld, cells %lld vs %lld)", (long long)n, (long long)sim->n, (long long)n_cells, (long long)sim->grid.ncell);
     if (n == 0) return CDB_OK;
@@ -1119,6 +1190,7 @@ int cdb_get_cell_tables(cdb_sim *sim, int64_t *points_indices, int64_t n, int64_
 
 int cdb_get_neighbor_pairs(cdb_sim *sim, int64_t *pairs, int64_t cap, int64_t *count) {
     SIM_ENTRY();
+    CKS(coarse_tables(sim));
     if (!sim->tables_valid) return fail(CDB_ERR_STATE, "no block list has been built for the current positions");
     if (!count) return fail(CDB_ERR_INVALID_VALUE, "count is NULL");
     *count = 0;
@@ -1172,7 +1244,11 @@ int cdb_set_strip(cdb_sim *sim, int64_t ix_min, int64_t iy_min, int64_t nx_owned
     sim->halo_cap = halo_cap;
     sim->mig_cap = migrant_cap;
     const int64_t nx = nx_owned + sim->has_left + sim->has_right;
-    sim->grid = Grid{ix_min - sim->has_left, iy_min, nx, ny, nx * ny, sim->has_left, nx - 1 - sim->has_right};
+    // the strip lattice in search cells (cell_size / f): every cell_size column is f columns wide; ghost blocks first / last
+    const int f = sim->fine_request == 2 && sim->variant != 1 ? 2 : 1;
+    sim->strip_fine = f;
+    sim->strip_ix0 = ix_min - sim->has_left; sim->strip_col_lo = sim->has_left; sim->strip_col_hi = nx - 1 - sim->has_right;
+    sim->grid = Grid{f * (ix_min - sim->has_left), f * iy_min, f * nx, f * ny, f * nx * f * ny, f * sim->has_left, f * (nx - sim->has_right) - 1};
     sim->lattice_fixed = true;
     sim->tables_valid = false;
     CK(cudaMemcpy(sim->d_grid, &sim->grid, sizeof(Grid), cudaMemcpyHostToDevice));
@@ -1199,24 +1275,27 @@ int cdb_set_agent_ids(cdb_sim *sim, const int64_t *ids, int64_t n) {
 int64_t cdb_halo_buffer_doubles(const cdb_sim *sim) {
     if (!sim) return -1;
     const int rec = sim->model == CDB_MODEL_CIRCULAR ? REC_CIRC : REC_THREE;
-    return MSG_HEADER + halo_counts_doubles(sim->grid.ny) + sim->halo_cap * rec;
+    return MSG_HEADER + halo_counts_doubles(sim->grid.ny * sim->strip_fine) + sim->halo_cap * rec;
 }
 int64_t cdb_migrant_buffer_doubles(const cdb_sim *sim) { return sim ? MSG_HEADER + sim->mig_cap * (sim->n_planes + 2) : -1; }
 
 int cdb_strip_begin(cdb_sim *sim, uint32_t flags, double cell_size, double *halo_left_out, double *halo_right_out) {
     SIM_ENTRY();
     if (!sim->strip) return fail(CDB_ERR_STATE, "cdb_set_strip has not been called");
-    if (sim->variant == 1) return fail(CDB_ERR_STATE, "the strip decomposition needs the fused step kernel (variant 2)");
+    if (sim->variant == 1) return fail(CDB_ERR_STATE, "the strip decomposition needs kernel variant 2 or 3");
+    if (flags & CDB_STEP_AGENT_AGENT) CKS(prepare_pairs(sim));
     CKS(prof_mark(sim));
     LAUNCH(sim, k_vmax_init, 1, 32, 0, sim->d_vmax);
-    CKS(build_block_list(sim, cell_size, false, sim->d_vmax, false));
+    const int f = sim->strip_fine;
+    CKS(build_block_list(sim, cell_size, false, sim->d_vmax, false, f));
     const int rec = sim->model == CDB_MODEL_CIRCULAR ? REC_CIRC : REC_THREE;
-    const int ny = (int)sim->grid.ny;
+    // a halo message is one cell_size column = f consecutive columns of the search lattice = f * ny consecutive cells
+    const int nyb = (int)sim->grid.ny * f;
     if (sim->has_left && halo_left_out)
-        LAUNCH(sim, k_halo_pack, 32, 256, 0, sim->d_nbr, rec, sim->d_cell_start, sim->d_cell_count, (int)sim->grid.cx_lo, ny, halo_left_out,
+        LAUNCH(sim, k_halo_pack, 32, 256, 0, sim->d_nbr, rec, sim->d_cell_start, sim->d_cell_count, (int)sim->strip_col_lo, nyb, halo_left_out,
                (long long)sim->halo_cap, sim->d_error);
     if (sim->has_right && halo_right_out)
-        LAUNCH(sim, k_halo_pack, 32, 256, 0, sim->d_nbr, rec, sim->d_cell_start, sim->d_cell_count, (int)sim->grid.cx_hi, ny, halo_right_out,
+        LAUNCH(sim, k_halo_pack, 32, 256, 0, sim->d_nbr, rec, sim->d_cell_start, sim->d_cell_count, (int)sim->strip_col_hi, nyb, halo_right_out,
                (long long)sim->halo_cap, sim->d_error);
     CK(cudaGetLastError());
     return CDB_OK;
@@ -1240,7 +1319,7 @@ int cdb_strip_finish(cdb_sim *sim, uint32_t flags, double dt_min, double dt_max,
     SIM_ENTRY();
     if (!sim->strip || !sim->tables_valid) return fail(CDB_ERR_STATE, "cdb_strip_begin must precede cdb_strip_finish");
     const int rec = sim->model == CDB_MODEL_CIRCULAR ? REC_CIRC : REC_THREE;
-    const int ny = (int)sim->grid.ny;
+    const int ny = (int)sim->grid.ny * sim->strip_fine;      // cells of one cell_size column
     const int base_l = (int)sim->capacity, base_r = (int)(sim->capacity + sim->halo_cap);
     if (sim->has_left) {
         if (halo_left_in) LAUNCH(sim, k_halo_unpack, 1, 1024, 0, halo_left_in, rec, sim->d_nbr, sim->d_nbr_sweep, sim->d_cell_of_slot, sim->d_cell_start, sim->d_cell_count,
@@ -1248,7 +1327,7 @@ int cdb_strip_finish(cdb_sim *sim, uint32_t flags, double dt_min, double dt_max,
         else LAUNCH(sim, k_ghost_clear, 4, 256, 0, sim->d_cell_start, sim->d_cell_count, 0, ny, base_l);
     }
     if (sim->has_right) {
-        const int col = (int)sim->grid.nx - 1;
+        const int col = (int)sim->strip_col_hi + 1;
         if (halo_right_in) LAUNCH(sim, k_halo_unpack, 1, 1024, 0, halo_right_in, rec, sim->d_nbr, sim->d_nbr_sweep, sim->d_cell_of_slot, sim->d_cell_start, sim->d_cell_count,
                                   col, ny, base_r, (long long)sim->halo_cap, sim->d_error);
         else LAUNCH(sim, k_ghost_clear, 4, 256, 0, sim->d_cell_start, sim->d_cell_count, col, ny, base_r);
@@ -1260,8 +1339,8 @@ int cdb_strip_finish(cdb_sim *sim, uint32_t flags, double dt_min, double dt_max,
     LAUNCH(sim, k_step_advance, 1, 32, 0, sim->d_stepctr, (const unsigned long long *)nullptr, 0LL);
     LAUNCH(sim, k_counters_zero, 1, 32, 0, sim->d_counters, 4);
     if (sim->n > 0)
-        LAUNCH(sim, k_migrants_pack, cdiv(sim->n, 256), 256, 0, sim->cur, (int)sim->n, sim->dev_counts ? &sim->d_counts->slots : nullptr, sim->n_planes, sim->cell_size, sim->grid.ix_min,
-               (int)sim->grid.cx_lo, (int)sim->grid.cx_hi, sim->has_left, sim->has_right, mig_left_out, mig_right_out, (long long)sim->mig_cap,
+        LAUNCH(sim, k_migrants_pack, cdiv(sim->n, 256), 256, 0, sim->cur, (int)sim->n, sim->dev_counts ? &sim->d_counts->slots : nullptr, sim->n_planes, sim->cell_size, sim->strip_ix0,
+               (int)sim->strip_col_lo, (int)sim->strip_col_hi, sim->has_left, sim->has_right, mig_left_out, mig_right_out, (long long)sim->mig_cap,
                sim->d_counters, sim->d_error);
     LAUNCH(sim, k_migrants_header, 1, 32, 0, sim->has_left ? mig_left_out : nullptr, sim->has_right ? mig_right_out : nullptr, sim->d_counters,
            (long long)sim->mig_cap);
@@ -1278,6 +1357,7 @@ static int strip_refresh(cdb_sim *sim) {
     sim->n = sim->h_counts->slots;
     sim->n_dead = std::min<int64_t>(sim->h_counters[0], sim->mig_cap) + std::min<int64_t>(sim->h_counters[1], sim->mig_cap);
     sim->steps_since_refresh = 0;
+    if (sim->pairs_pending) { bool overflow = false; CKS(settle_pairs(sim, &overflow, nullptr)); }   // grows the pair list early
     return CDB_OK;
 }
 

@@ -1,0 +1,110 @@
+// finish_kernel.cuh -- last kernel of a step of the once-per-pair pipeline (variant 3): everything of the step that is
+// per agent.  Fluctuation, navigation sample, orientation, adjusting (logic.py:78-94,149-165,258-261), the sum of the
+// agent's pair contributions written by k_pair_eval (pair_kernels.cuh) in ascending partner order, agent-obstacle
+// (interactions.py:208-214), adaptive-dt velocity Verlet + shoulders (integrator.py:209-256, agents.py:473-486) and reset
+// (logic.py:59-64).  The new state goes to the other ping-pong buffer in cell order (the physical re-sort is a by-product).
+//
+// This kernel is bound by memory LATENCY, not bandwidth or arithmetic (ncu, round 2: 71 % of the stall samples of its first
+// version were long-scoreboard with DRAM at 30 %), so it is written in phases: (0) the three index loads, (1) every plane of
+// the agent in one batch of independent loads, (2) the dependent gathers (navigation field, contributions) and the
+// arithmetic, (3) the stores.  `in` and `out` are not restrict-qualified (node-wise use passes the same buffer), hence no
+// load may follow a store.
+#pragma once
+#include "kernels.cuh"
+#include "pair_kernels.cuh"
+#include "step_kernel.cuh"
+
+constexpr int FIN_THREADS = 256;
+
+template <int MODEL>
+__global__ void __launch_bounds__(FIN_THREADS, MODEL == 0 ? 3 : 2) k_finish(const StepArgs A) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= eff_n(A.n, A.n_dev)) return;
+    const Soa &s = A.in;
+    const Soa &o = A.out;
+    const bool pairs = A.flags & CDB_STEP_AGENT_AGENT;
+    // ---- phase 0: where the agent's planes and contributions live ---------------------------------------------------------
+    const int oo = A.order ? A.order[t] : t;
+    const int n_con = pairs ? A.pb.fill[t] : 0;
+    const int con_off = pairs ? A.pb.off[t] : 0;
+    if (pairs && pairs_overflowed(A.pb)) {
+        // the pair list did not hold this step's pairs: the step is NOT applied (the host grows the list and repeats it);
+        // an integrating step still has to leave the unchanged state in `out`, which the host makes current
+        if (A.flags & CDB_STEP_INTEGRATOR) {
+            for (int k = 0; k < A.n_planes; ++k) o(k, t) = s(k, oo);
+            o.id[t] = s.id[oo];
+            o.target[t] = s.target[oo];
+        }
+        return;
+    }
+    // ---- phase 1: the agent (one batch of independent loads) --------------------------------------------------------------
+    const double px = s(PX, oo), py = s(PY, oo), vx = s(VX, oo), vy = s(VY, oo);
+    double e0x = s(E0X, oo), e0y = s(E0Y, oo), fx = s(FX, oo), fy = s(FY, oo);
+    const double fpx = s(FPX, oo), fpy = s(FPY, oo);
+    const double radius = s(RADIUS, oo), mass = s(MASS, oo), v0 = s(V0, oo), tau_adj = s(TAU_ADJ, oo), k_soc = s(K_SOC, oo), tau_0 = s(TAU_0, oo);
+    const double mu = s(MU, oo), kappa = s(KAPPA, oo), damping = s(DAMPING, oo), srf = s(STD_RAND_FORCE, oo);
+    const int id = s.id[oo];
+    const long long target = s.target[oo];
+    double lsx = 0, lsy = 0, rsx = 0, rsy = 0, r_t = 0, r_s = 0, r_ts = 0, inertia = 0, omega0 = 0, phi = 0, w = 0, phi0 = 0, tq = 0,
+           tq_prev = 0, tau_rot = 0, srt = 0;
+    if (MODEL == 1) {
+        lsx = s(LSX, oo); lsy = s(LSY, oo); rsx = s(RSX, oo); rsy = s(RSY, oo);
+        r_t = s(R_T, oo); r_s = s(R_S, oo); r_ts = s(R_TS, oo); inertia = s(INERTIA, oo); omega0 = s(OMEGA0, oo);
+        phi = s(PHI, oo); w = s(OMEGA, oo); phi0 = s(PHI0, oo); tq = s(TORQUE, oo); tq_prev = s(TORQUE_PREV, oo);
+        tau_rot = s(TAU_ROT, oo); srt = s(STD_RAND_TORQUE, oo);
+    }
+    // ---- phase 2: the nodes, in the reference's post-order ----------------------------------------------------------------
+    if (A.flags & CDB_STEP_FLUCTUATION) fluctuation(A.seed, *A.step_ptr, id, mass, srf, inertia, srt, MODEL == 1, fx, fy, tq);
+    if (A.flags & CDB_STEP_NAVIGATION) navigation_sample(A.nav, A.n_nav, target, px, py, e0x, e0y);
+    if (MODEL == 1 && (A.flags & CDB_STEP_ORIENTATION)) phi0 = atan2(e0y, e0x);
+    if (A.flags & CDB_STEP_ADJUSTING) {
+        double ax, ay;
+        adjust_force(mass, tau_adj, v0, e0x, e0y, vx, vy, ax, ay);
+        fx += ax; fy += ay;
+        if (MODEL == 1) tq += adjust_torque(inertia, tau_rot, phi0, phi, omega0, w);
+    }
+    if (n_con > 0) gather_contributions(A.pb.cres + (size_t)con_off * 4, n_con, MODEL == 1, fx, fy, tq);
+    if ((A.flags & CDB_STEP_AGENT_OBSTACLE) && A.n_obs > 0) {
+        if (MODEL == 0) walls_circular(px, py, radius, vx, vy, mu, kappa, damping, A.obs, A.n_obs, fx, fy);
+        else walls_three_circle(px, py, lsx, lsy, rsx, rsy, r_t, r_s, vx, vy, mu, kappa, damping, A.obs, A.n_obs, fx, fy, tq);
+    }
+    const bool rst = A.flags & CDB_STEP_RESET;
+    if (!(A.flags & CDB_STEP_INTEGRATOR)) {
+        // node-wise use: publish what the selected nodes wrote, in place
+        o(E0X, oo) = e0x; o(E0Y, oo) = e0y;
+        o(FX, oo) = rst ? 0.0 : fx; o(FY, oo) = rst ? 0.0 : fy;
+        if (MODEL == 1) { o(PHI0, oo) = phi0; o(TORQUE, oo) = rst ? 0.0 : tq; }
+        return;
+    }
+    const double dt = adaptive_timestep(A.vmax, A.dt_min, A.dt_max);
+    double nvx = vx, nvy = vy, npx = px, npy = py;
+    verlet(fx, fpx, mass, dt, nvx, npx);
+    verlet(fy, fpy, mass, dt, nvy, npy);
+    double ox = 0.0, oy = 0.0;
+    if (MODEL == 1) {
+        verlet(tq, tq_prev, inertia, dt, w, phi);
+        phi = wrap_to_pi(phi);
+        ox = sin(phi) * r_ts; oy = -cos(phi) * r_ts;   // shoulders(), agents.py:473-486
+    }
+    // ---- phase 3: the new state, in cell order ----------------------------------------------------------------------------
+    if (t == 0) {
+        A.dt_out[0] = dt; A.dt_out[1] += dt;
+        if (A.dt_log) A.dt_log[*A.step_ptr % DT_LOG_SLOTS] = dt;
+    }
+    o(PX, t) = npx; o(PY, t) = npy; o(VX, t) = nvx; o(VY, t) = nvy;
+    o(E0X, t) = e0x; o(E0Y, t) = e0y;
+    o(FX, t) = rst ? 0.0 : fx; o(FY, t) = rst ? 0.0 : fy;
+    o(FPX, t) = fx; o(FPY, t) = fy;
+    o(RADIUS, t) = radius; o(MASS, t) = mass; o(V0, t) = v0; o(TAU_ADJ, t) = tau_adj;
+    o(K_SOC, t) = k_soc; o(TAU_0, t) = tau_0; o(MU, t) = mu; o(KAPPA, t) = kappa; o(DAMPING, t) = damping;
+    o(STD_RAND_FORCE, t) = srf;
+    o.id[t] = id;
+    o.target[t] = target;
+    if (MODEL == 1) {
+        o(LSX, t) = npx - ox; o(LSY, t) = npy - oy; o(RSX, t) = npx + ox; o(RSY, t) = npy + oy;
+        o(R_T, t) = r_t; o(R_S, t) = r_s; o(R_TS, t) = r_ts; o(INERTIA, t) = inertia; o(OMEGA0, t) = omega0;
+        o(PHI, t) = phi; o(OMEGA, t) = w; o(PHI0, t) = phi0;
+        o(TORQUE, t) = rst ? 0.0 : tq; o(TORQUE_PREV, t) = tq; o(TAU_ROT, t) = tau_rot;
+        o(STD_RAND_TORQUE, t) = srt;
+    }
+}

@@ -37,7 +37,7 @@ struct NavField { const double *U, *V; long long ny, nx; double minx, miny, step
 
 struct FieldMap { short plane; short offset; unsigned bit; };
 
-enum { ERR_NONE = 0, ERR_NONFINITE = 1, ERR_CELL_RANGE = 2 };
+enum { ERR_NONE = 0, ERR_NONFINITE = 1, ERR_CELL_RANGE = 2, ERR_PAIR_OVERFLOW = 100 };
 constexpr int MAX_NAV_TARGETS = 64;
 constexpr int AOS_REC_PER_BLOCK = 128;
 constexpr int SCAN_THREADS = 256;
@@ -568,9 +568,27 @@ __global__ void k_rank_fix(const int *__restrict__ order_tmp, int n_host, const 
     order[b + rank] = src;
 }
 
+// Largest radius / body extent any agent can present to the pair search, now (stored shoulder positions) and after any
+// later integrator step (shoulders re-derived from r_ts): decides whether the twice finer search lattice may be used.
+__global__ void k_ext_max(Soa s, int n, int model, unsigned long long *out) {
+    double m = 0.0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        double e;
+        if (model == CDB_MODEL_CIRCULAR) e = s(RADIUS, i);
+        else {
+            const double x = s(PX, i), y = s(PY, i), r_t = s(R_T, i), r_s = s(R_S, i), r_ts = s(R_TS, i);
+            const double dl = hypot(s(LSX, i) - x, s(LSY, i) - y), dr = hypot(s(RSX, i) - x, s(RSY, i) - y);
+            e = fmax(r_t, fmax(fmax(dl, dr), fabs(r_ts) * (1.0 + 1e-9)) + r_s);
+        }
+        if (!(e <= m)) m = isnan(e) ? __longlong_as_double(0x7ff0000000000000LL) : e;   // NaN => +inf: never refine
+    }
+    const unsigned long long b = warp_max_u64(ordered_bits(m));
+    if ((threadIdx.x & 31) == 0) atomicMax(out, b);
+}
+
 // physical reorder into cell order (all record planes) + the packed neighbour records the pair kernel sweeps:
 //   circular      {px, py, vx, vy, radius, -}                                                   48 B
-//   three-circle  {px, py, vx, vy, extent, r_t, r_s, - | lsx, lsy, rsx, rsy, ox, oy, cell_x, cell_y}     128 B (one line)
+//   three-circle  {px, py, vx, vy, extent, r_t, r_s, id | lsx, lsy, rsx, rsy, ox, oy, cell_x, cell_y}    128 B (one line)
 // extent = conservative radius of the whole body around the centre (from the STORED shoulder positions), (ox, oy) =
 // r_ts (sin phi, -cos phi), the shoulder displacement of power_law.py:338-350.
 __global__ void k_gather(Soa src, Soa dst, int n, int n_planes, int model, const int *__restrict__ order,
@@ -585,26 +603,27 @@ __global__ void k_gather(Soa src, Soa dst, int n, int n_planes, int model, const
     const double x = src(PX, o), y = src(PY, o), vx = src(VX, o), vy = src(VY, o);
     if (model == CDB_MODEL_CIRCULAR) {
         double2 *r = reinterpret_cast<double2 *>(nbr + (size_t)t * 6);
-        r[0] = make_double2(x, y); r[1] = make_double2(vx, vy); r[2] = make_double2(src(RADIUS, o), 0.0);
+        const double rad = src(RADIUS, o);
+        r[0] = make_double2(x, y); r[1] = make_double2(vx, vy); r[2] = make_double2(rad, rad * (1.0 + 1e-12));
     } else {
         const double phi = src(PHI, o), r_ts = src(R_TS, o), r_t = src(R_T, o), r_s = src(R_S, o);
         const double lsx = src(LSX, o), lsy = src(LSY, o), rsx = src(RSX, o), rsy = src(RSY, o);
         const double dl = hypot(lsx - x, lsy - y), dr = hypot(rsx - x, rsy - y);
         const double ext = fmax(r_t, fmax(dl, dr) + r_s) * (1.0 + 1e-12);
         double2 *r = reinterpret_cast<double2 *>(nbr + (size_t)t * 16);
-        r[0] = make_double2(x, y); r[1] = make_double2(vx, vy); r[2] = make_double2(ext, r_t); r[3] = make_double2(r_s, 0.0);
+        r[0] = make_double2(x, y); r[1] = make_double2(vx, vy); r[2] = make_double2(ext, r_t); r[3] = make_double2(r_s, (double)src.id[o]);
         r[4] = make_double2(lsx, lsy); r[5] = make_double2(rsx, rsy);
         r[6] = make_double2(r_ts * sin(phi), r_ts * -cos(phi));
         r[7] = make_double2(floor(x / cell_size), floor(y / cell_size));   // true cell coordinates: pair orientation
         double2 *q = reinterpret_cast<double2 *>(nbr_sweep + (size_t)t * 6);   // compact record for the phase-1 sweep
-        q[0] = make_double2(x, y); q[1] = make_double2(vx, vy); q[2] = make_double2(ext, 0.0);
+        q[0] = make_double2(x, y); q[1] = make_double2(vx, vy); q[2] = make_double2(ext, ext * (1.0 + 1e-9));
     }
 }
 
 // packed neighbour records in cell order WITHOUT moving the planes (the fused step kernel reads its own agent through
 // `order` and writes the new state in cell order, so the physical sort happens as a by-product of the step):
 //   circular      {px, py, vx, vy, radius, -}                                                   48 B
-//   three-circle  {px, py, vx, vy, extent, r_t, r_s, - | lsx, lsy, rsx, rsy, ox, oy, cell_x, cell_y}     128 B (one line)
+//   three-circle  {px, py, vx, vy, extent, r_t, r_s, id | lsx, lsy, rsx, rsy, ox, oy, cell_x, cell_y}    128 B (one line)
 // extent = conservative radius of the whole body around the centre (from the STORED shoulder positions), (ox, oy) =
 // r_ts (sin phi, -cos phi), the shoulder displacement of power_law.py:338-350.
 __global__ void k_records(Soa src, int n_host, const int *n_dev, int model, const int *__restrict__ order,
@@ -619,19 +638,20 @@ __global__ void k_records(Soa src, int n_host, const int *n_dev, int model, cons
     const double x = src(PX, o), y = src(PY, o), vx = src(VX, o), vy = src(VY, o);
     if (model == CDB_MODEL_CIRCULAR) {
         double2 *r = reinterpret_cast<double2 *>(nbr + (size_t)t * 6);
-        r[0] = make_double2(x, y); r[1] = make_double2(vx, vy); r[2] = make_double2(src(RADIUS, o), 0.0);
+        const double rad = src(RADIUS, o);
+        r[0] = make_double2(x, y); r[1] = make_double2(vx, vy); r[2] = make_double2(rad, rad * (1.0 + 1e-12));
     } else {
         const double phi = src(PHI, o), r_ts = src(R_TS, o), r_t = src(R_T, o), r_s = src(R_S, o);
         const double lsx = src(LSX, o), lsy = src(LSY, o), rsx = src(RSX, o), rsy = src(RSY, o);
         const double dl = hypot(lsx - x, lsy - y), dr = hypot(rsx - x, rsy - y);
         const double ext = fmax(r_t, fmax(dl, dr) + r_s) * (1.0 + 1e-12);
         double2 *r = reinterpret_cast<double2 *>(nbr + (size_t)t * 16);
-        r[0] = make_double2(x, y); r[1] = make_double2(vx, vy); r[2] = make_double2(ext, r_t); r[3] = make_double2(r_s, 0.0);
+        r[0] = make_double2(x, y); r[1] = make_double2(vx, vy); r[2] = make_double2(ext, r_t); r[3] = make_double2(r_s, (double)src.id[o]);
         r[4] = make_double2(lsx, lsy); r[5] = make_double2(rsx, rsy);
         r[6] = make_double2(r_ts * sin(phi), r_ts * -cos(phi));
         r[7] = make_double2(floor(x / cell_size), floor(y / cell_size));   // true cell coordinates: pair orientation
         double2 *q = reinterpret_cast<double2 *>(nbr_sweep + (size_t)t * 6);   // compact record for the phase-1 sweep
-        q[0] = make_double2(x, y); q[1] = make_double2(vx, vy); q[2] = make_double2(ext, 0.0);
+        q[0] = make_double2(x, y); q[1] = make_double2(vx, vy); q[2] = make_double2(ext, ext * (1.0 + 1e-9));
     }
 }
 

@@ -36,7 +36,7 @@ constexpr int GHOST_KEY_SHIFT = 1 << 30;     // ghosts of the left neighbour str
 
 // packed neighbour records (doubles per agent)
 constexpr int REC_CIRC = 6;     // px py vx vy r -
-constexpr int REC_THREE = 16;   // px py vx vy ext rt rs - | lsx lsy rsx rsy ox oy cell_x cell_y
+constexpr int REC_THREE = 16;   // px py vx vy ext rt rs id | lsx lsy rsx rsy ox oy cell_x cell_y
 
 struct PairBuf {
     int2 *pairs;                 // [cap] (target slot, candidate slot), target < candidate in cell order
@@ -46,6 +46,7 @@ struct PairBuf {
     int *fill;                   // per slot: entries written so far (== contributions to add)
     unsigned long long *ctr;     // [0] pairs found this step (may exceed cap => step not applied), [1] entries allocated
     long long cap;
+    int *fatal;                  // strips: an unapplied step cannot be repeated (the other ranks went on) => device error flag
 };
 
 __device__ __forceinline__ bool pairs_overflowed(const PairBuf &pb) { return pb.ctr[0] > (unsigned long long)pb.cap; }
@@ -56,9 +57,11 @@ struct SweepArgs {
     const int *n_dev;            // device-side exact count (nullptr: n is exact)
     const Grid *grid;
     const int *cell_sorted, *cell_start, *cell_count;
-    int ghost_base;              // first slot of the left ghost column (strips; targets n .. n + n_ghost map there), or -1
+    int ghost_base;              // first slot of the left ghost columns (strips; targets n .. n + n_ghost map there), or -1
     int n_ghost;                 // launch bound for the left ghost targets
-    int reach;                   // forward columns / rows swept around the target's cell (1 on the cell_size lattice)
+    int ghost_cells;             // cells of the left ghost block (its columns come first in the lattice)
+    int reach;                   // forward columns / rows swept around the target's cell: 1 on the cell_size lattice, 2 on the
+                                 // twice finer search lattice (chosen by the host when 3 + 2 max R < cell_size, see build_block_list)
     PairBuf pb;
 };
 
@@ -79,16 +82,20 @@ __global__ void __launch_bounds__(SW_THREADS, 8) k_sweep(const SweepArgs A) {
     if (g < A.n) { if (g < n_own) t = g; }
     else if (A.ghost_base >= 0) {
         const int k = g - A.n;
-        const int n_gl = A.cell_start[ny - 1] + A.cell_count[ny - 1] - A.ghost_base;   // column 0 is the left ghost column
+        const int n_gl = A.cell_start[A.ghost_cells - 1] + A.cell_count[A.ghost_cells - 1] - A.ghost_base;
         if (k < n_gl) { t = A.ghost_base + k; ghost = true; }
     }
     const bool active = t >= 0;
     const int tt = active ? t : 0;
-    double mpx, mpy, mvx, mvy, mr;
+    // the stored radii / body extents are inflated by SWEEP_EPS (slot 5 of the sweep record), which makes every comparison
+    // below conservative under any rounding: a pair the exact arithmetic of k_pair_eval would give a force is never dropped
+    constexpr double SWEEP_EPS = MODEL == 0 ? PREFILTER_EPS : BOUND_EPS;
+    double mpx, mpy, mvx, mvy, mr, lim_t;
     {
         const double *r = A.nbr_sweep + (size_t)tt * REC_CIRC;
         const double2 p = ldg2(r), v = ldg2(r + 2);
-        mpx = p.x; mpy = p.y; mvx = v.x; mvy = v.y; mr = __ldg(r + 4);
+        mpx = p.x; mpy = p.y; mvx = v.x; mvy = v.y; mr = __ldg(r + 5);
+        lim_t = SIGTH_SOC * (1.0 + SWEEP_EPS) + mr;
     }
     const int c = A.cell_sorted[tt];
     const int cx = c / ny, cy = c - cx * ny;
@@ -96,6 +103,7 @@ __global__ void __launch_bounds__(SW_THREADS, 8) k_sweep(const SweepArgs A) {
     const int ylo = max(cy - reach, 0), yhi = min(cy + reach, ny - 1);
     const int col_min = (int)A.grid->cx_lo;      // ghost targets: candidates in owned columns only
     int nst = 0, mine = 0;
+    const int own_limit = A.ghost_base >= 0 ? A.ghost_base : 0x7fffffff;   // slots beyond are ghosts: nothing is stored for them
 
     auto flush = [&]() {
         unsigned long long base = 0;
@@ -107,7 +115,7 @@ __global__ void __launch_bounds__(SW_THREADS, 8) k_sweep(const SweepArgs A) {
             if (p < (unsigned long long)A.pb.cap) {
                 const int2 e = stage[i];
                 A.pb.pairs[p] = e;
-                atomicAdd(&A.pb.cnt[e.y], 1);
+                if (e.y < own_limit) atomicAdd(&A.pb.cnt[e.y], 1);
             }
         }
         __syncwarp();
@@ -130,30 +138,29 @@ __global__ void __launch_bounds__(SW_THREADS, 8) k_sweep(const SweepArgs A) {
                 const bool inr = u < e;
                 const double *r = A.nbr_sweep + (size_t)(inr ? u : tt) * REC_CIRC;
                 const double2 p = ldg2(r), v = ldg2(r + 2);
-                const double ro = __ldg(r + 4);
+                const double ro = __ldg(r + 5);
+                // fused multiply-adds are fine here (this is a filter, not the reference arithmetic): ~24 fp64 operations
                 const double x = mpx - p.x, y = mpy - p.y;
-                const double R = mr + ro;                    // r_tot (circular) / sum of body extents (three-circle)
-                const double d2 = x * x + y * y;
-                const double lim = SIGTH_SOC + R;
+                const double d2 = fma(x, x, y * y);
+                const double lim = lim_t + ro;               // >= (3 + R)(1 + eps): conservative form of h < SIGTH_SOC
+                const bool gate = d2 <= lim * lim;
+                const double R = mr + ro;                    // inflated r_tot (circular) / sum of body extents (three-circle)
                 const double RR = R * R;
-                const bool gate = d2 <= lim * lim * (1.0 + PREFILTER_EPS);
-                const bool contact = d2 <= RR * (1.0 + PREFILTER_EPS);
+                const double cc = d2 - RR;
+                const bool contact = cc <= 1e-9;             // conservative form of h < 0
                 const double vx = mvx - v.x, vy = mvy - v.y;
-                const double a = vx * vx + vy * vy;
-                const double bb = -(x * vx + y * vy);
+                const double a = fma(vx, vx, vy * vy);
+                const double bb = -fma(x, vx, y * vy);
                 bool social;
                 if (MODEL == 0) {
-                    // the reference's own a, b, c, disc in its operation order: exactly the necessary condition for a
-                    // non-zero social force (power_law.py:236-246)
-                    const double cc = d2 - RR;
-                    const double disc = bb * bb - a * cc;
-                    social = disc > 0.0 && bb > 0.0;
+                    // necessary for a non-zero social force (power_law.py:236-246): a real time-to-collision
+                    // (b^2 - a c > 0) that is positive (b > 0); margins cover the different rounding of the reference's own
+                    // evaluation order
+                    social = bb > -1e-12 && fma(bb * (1.0 + PREFILTER_EPS), bb, -(a * cc)) > 0.0;
                 } else {
-                    // bounding circles (inflated by BOUND_EPS): no real root for them => none for any of the 9 part pairs
-                    // (power_law.py:308-329); all part pairs receding => no positive time-to-collision
-                    const double Rs = R * (1.0 + BOUND_EPS), RRs = Rs * Rs;
-                    const double disc = bb * bb - a * (d2 - RRs);
-                    social = disc >= 0.0 && (bb >= 0.0 || bb * bb <= RRs * a);
+                    // bounding circles: no real root for them => none for any of the 9 part pairs (power_law.py:308-329);
+                    // all part pairs receding (b_k <= b + R |v| <= 0) => no positive time-to-collision
+                    social = fma(bb, bb, -(a * cc)) >= 0.0 && (bb >= -1e-12 || bb * bb <= RR * a);
                 }
                 keep[kk] = inr && gate && (social || contact);
             }
@@ -167,12 +174,15 @@ __global__ void __launch_bounds__(SW_THREADS, 8) k_sweep(const SweepArgs A) {
         }
     }
     if (nst) flush();
-    if (mine) atomicAdd(&A.pb.cnt[t], mine);
+    if (mine && !ghost) atomicAdd(&A.pb.cnt[t], mine);
 }
 
 // private region of the contribution array for every agent (order of the regions is irrelevant)
 __global__ void k_pair_alloc(PairBuf pb, int n_slots) {
-    if (pairs_overflowed(pb)) return;
+    if (pairs_overflowed(pb)) {
+        if (pb.fatal && blockIdx.x == 0 && threadIdx.x == 0) atomicExch(pb.fatal, ERR_PAIR_OVERFLOW);
+        return;
+    }
     const int a = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     const int c = a < n_slots ? pb.cnt[a] : 0;
@@ -376,9 +386,11 @@ __global__ void __launch_bounds__(128, MODEL == 0 ? 6 : 4) k_pair_eval(const Eva
             // reference pair orientation: i is the lexicographically smaller (cell_x, cell_y, agent index).  The TRUE cell
             // coordinates floor(p / c) (last two slots of the neighbour record) are compared, not the flat ids of the search
             // lattice, so the convention does not depend on how the lattice was chosen (padded, fixed, clamped, per-strip).
-            // Agents of the same true cell share a flat cell, inside which the slots are ordered by agent index.
             const double2 ca = ldg2(A.nbr + (size_t)t * REC_THREE + 14), cb = ldg2(A.nbr + (size_t)u * REC_THREE + 14);
-            const bool t_is_i = ca.x != cb.x ? ca.x < cb.x : (ca.y != cb.y ? ca.y < cb.y : true);
+            // Inside one true cell the agent index decides (slot 7 of the record; on the finer search lattice two agents of a
+            // cell_size cell may sit in different search cells, so the slot order does not tell).
+            const bool t_is_i = ca.x != cb.x ? ca.x < cb.x : (ca.y != cb.y ? ca.y < cb.y :
+                                __ldg(A.nbr + (size_t)t * REC_THREE + 7) < __ldg(A.nbr + (size_t)u * REC_THREE + 7));
             const int si = t_is_i ? t : u, sj = t_is_i ? u : t;
             Three I, J;
             load_three_rec(A.nbr, si, I);
@@ -399,10 +411,8 @@ __global__ void __launch_bounds__(128, MODEL == 0 ? 6 : 4) k_pair_eval(const Eva
     }
 }
 
-// adds the contributions of agent `a` in ascending partner order (selection: the lists are a handful of entries long)
-__device__ __forceinline__ void gather_contributions(const PairBuf &pb, int a, bool torque, double &fx, double &fy, double &tq) {
-    const int n = pb.fill[a];
-    const double *e = pb.cres + (size_t)pb.off[a] * 4;
+// adds the `n` contributions at `e` in ascending partner order (selection: the lists are a handful of entries long)
+__device__ __forceinline__ void gather_contributions(const double *__restrict__ e, int n, bool torque, double &fx, double &fy, double &tq) {
     long long last = -0x7fffffffffffffffLL - 1;
     for (int r = 0; r < n; ++r) {
         long long best = 0x7fffffffffffffffLL;

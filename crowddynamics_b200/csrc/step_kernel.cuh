@@ -54,8 +54,9 @@ struct StepArgs {
     double *dt_log;          // ring of DT_LOG_SLOTS entries: this step's dt goes to slot step % DT_LOG_SLOTS (or nullptr)
     unsigned long long seed; // Fluctuation: Philox key (with the step index)
     const unsigned long long *step_ptr;   // device-side step index (advanced by k_step_advance after every step)
-    PairBuf pb;              // PAIRS = 1: per-agent contributions written by k_pair_eval (pair_kernels.cuh)
-    int n_planes;            // planes of the model (PAIRS = 1: a step that is not applied still moves them to `out`)
+    PairBuf pb;              // k_finish: per-agent contributions written by k_pair_eval (pair_kernels.cuh)
+    int n_planes;            // planes of the model (k_finish: a step that is not applied still moves them to `out`)
+    int reach;               // k_step: cell columns / rows swept on either side of the target's cell (1, or 2 on the finer lattice)
 };
 
 struct WarpSmem {
@@ -160,17 +161,15 @@ __device__ __forceinline__ void sel_three(bool first, const Three &a, const Thre
 #ifndef STEP_MINB_THREE
 #define STEP_MINB_THREE 4
 #endif
-// PAIRS = 0: agent-agent interactions classified and evaluated inside this kernel, from every agent's side (full 3x3
-//            stencil; the one-kernel variant, kept as an independent cross-check and for cdb_set_variant(2));
-// PAIRS = 1: the interactions were evaluated once per pair by k_sweep / k_pair_eval; this kernel adds every agent's
-//            contributions in ascending partner order (the order PAIRS = 0 meets them).
-template <int MODEL, int PAIRS>
-__global__ void __launch_bounds__(PAIRS ? 256 : STEP_THREADS, PAIRS ? (MODEL == 0 ? 3 : 2) : (MODEL == 0 ? STEP_MINB_CIRC : STEP_MINB_THREE))
-k_step(const StepArgs A) {
-    __shared__ WarpSmem s_warp[PAIRS ? 1 : STEP_WARPS];
+// Variant 2: agent-agent interactions classified and evaluated inside this kernel, from every agent's side (full stencil).
+// Kept as an independent cross-check of the once-per-pair pipeline (pair_kernels.cuh + finish_kernel.cuh), which adds the same
+// per-pair numbers in the same order.
+template <int MODEL>
+__global__ void __launch_bounds__(STEP_THREADS, MODEL == 0 ? STEP_MINB_CIRC : STEP_MINB_THREE) k_step(const StepArgs A) {
+    __shared__ WarpSmem s_warp[STEP_WARPS];
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
-    WarpSmem &W = s_warp[PAIRS ? 0 : (threadIdx.x >> 5)];
+    WarpSmem &W = s_warp[threadIdx.x >> 5];
     const int t0 = t - lane;             // first target of this warp
     const bool active = t < eff_n(A.n, A.n_dev);
     const Soa &s = A.in;
@@ -178,16 +177,6 @@ k_step(const StepArgs A) {
     const int tt = active ? t : 0;       // inactive lanes read slot 0 and never write
     const int oo = A.order ? A.order[tt] : tt;   // where this agent's planes live in `in`
     constexpr int REC = MODEL == 0 ? REC_CIRC : REC_THREE;
-    if (PAIRS && (A.flags & CDB_STEP_AGENT_AGENT) && pairs_overflowed(A.pb)) {
-        // the pair list did not hold this step's pairs: the step is NOT applied (the host grows the list and repeats it);
-        // an integrating step still has to leave the unchanged state in `out`, which the host makes current
-        if (active && (A.flags & CDB_STEP_INTEGRATOR)) {
-            for (int k = 0; k < A.n_planes; ++k) A.out(k, t) = s(k, oo);
-            A.out.id[t] = s.id[oo];
-            A.out.target[t] = s.target[oo];
-        }
-        return;
-    }
 
     // ---- Navigation, Orientation, Adjusting (logic.py:149-165,258-261,89-94) --------------------------------------------
     double e0x = s(E0X, oo), e0y = s(E0Y, oo);
@@ -209,9 +198,7 @@ k_step(const StepArgs A) {
     }
 
     // ---- AgentAgentInteractions (interactions.py:191-205) -----------------------------------------------------------------
-    if (PAIRS) {
-        if (active && (A.flags & CDB_STEP_AGENT_AGENT)) gather_contributions(A.pb, t, MODEL == 1, fx, fy, tq);
-    } else if (A.flags & CDB_STEP_AGENT_AGENT) {
+    if (A.flags & CDB_STEP_AGENT_AGENT) {
         const double *__restrict__ nbr = A.nbr;
         // what phase 1 needs of the target: centre, velocity, radius (circular) / body extent (three-circle)
         double mpx, mpy, mvx, mvy, mr;
@@ -223,7 +210,8 @@ k_step(const StepArgs A) {
         const int ny = (int)A.grid->ny, nxg = (int)A.grid->nx;
         const int c = A.cell_sorted[tt];
         const int cx = c / ny, cy = c - cx * ny;
-        const int ylo = cy > 0 ? cy - 1 : 0, yhi = cy + 1 < ny ? cy + 1 : ny - 1;
+        const int reach = A.reach;
+        const int ylo = max(cy - reach, 0), yhi = min(cy + reach, ny - 1);
         int cnt = 0;
 
         auto flush = [&]() {
@@ -262,7 +250,8 @@ k_step(const StepArgs A) {
                         // (padded, fixed, clamped, per-strip).  Agents of the same true cell share a flat cell, inside which
                         // the slots are ordered by agent index.
                         const double2 ca = ldg2(nbr + (size_t)tg * REC + 14), cb = ldg2(nbr + (size_t)u * REC + 14);
-                        const bool me_is_i = ca.x != cb.x ? ca.x < cb.x : (ca.y != cb.y ? ca.y < cb.y : tg < u);
+                        const bool me_is_i = ca.x != cb.x ? ca.x < cb.x : (ca.y != cb.y ? ca.y < cb.y :
+                                             __ldg(nbr + (size_t)tg * REC + 7) < __ldg(nbr + (size_t)u * REC + 7));   // agent index
                         Three I, J;     // loaded straight into their roles: one inlined copy of the pair arithmetic, no selects
                         load_three_rec(nbr, me_is_i ? tg : u, I);
                         load_three_rec(nbr, me_is_i ? u : tg, J);
@@ -287,12 +276,12 @@ k_step(const StepArgs A) {
 
         // classify until some list is nearly full or all three cell-columns are done, then evaluate; repeat.
         // (one flush call site: the pair arithmetic is inlined exactly once)
-        int dx = -1, b = 0, e = 0, maxlen = 0, k0 = 0;
+        int dx = -reach, b = 0, e = 0, maxlen = 0, k0 = 0;
         bool have_col = false, done = false;
         do {
             while (true) {
                 if (!have_col) {
-                    if (dx > 1) { done = true; break; }
+                    if (dx > reach) { done = true; break; }
                     const int x2 = cx + dx;
                     b = 0; e = 0;
                     if (active && x2 >= 0 && x2 < nxg) {
@@ -373,33 +362,46 @@ k_step(const StepArgs A) {
     }
 
     // ---- Integrator (integrator.py:209-256) + Reset (logic.py:59-64); new state goes to the other buffer --------------------
+    // Every load is issued BEFORE the first store: `in` and `out` are not restrict-qualified (they are the same buffer in
+    // the node-wise path), so a load placed after a store would have to wait for it -- one DRAM round trip per plane.
     const double dt = adaptive_timestep(A.vmax, A.dt_min, A.dt_max);
+    const double fpx = s(FPX, oo), fpy = s(FPY, oo);
+    const double c_radius = s(RADIUS, oo), c_v0 = s(V0, oo), c_tau_adj = s(TAU_ADJ, oo), c_k_soc = s(K_SOC, oo), c_tau_0 = s(TAU_0, oo);
+    const double c_srf = s(STD_RAND_FORCE, oo);
+    const int c_id = s.id[oo];
+    const long long c_target = s.target[oo];
+    double inertia = 0.0, r_ts = 0.0, w = 0.0, phi = 0.0, tq_prev = 0.0, c_r_t = 0.0, c_r_s = 0.0, c_omega0 = 0.0, c_tau_rot = 0.0, c_srt = 0.0;
+    if (MODEL == 1) {
+        inertia = s(INERTIA, oo); r_ts = s(R_TS, oo); w = s(OMEGA, oo); phi = s(PHI, oo); tq_prev = s(TORQUE_PREV, oo);
+        c_r_t = s(R_T, oo); c_r_s = s(R_S, oo); c_omega0 = s(OMEGA0, oo); c_tau_rot = s(TAU_ROT, oo); c_srt = s(STD_RAND_TORQUE, oo);
+    }
     if (t == 0) {
         A.dt_out[0] = dt; A.dt_out[1] += dt;
         if (A.dt_log) A.dt_log[*A.step_ptr % DT_LOG_SLOTS] = dt;
     }
     double nvx = vx, nvy = vy, npx = px, npy = py;
-    verlet(fx, s(FPX, oo), mass, dt, nvx, npx);
-    verlet(fy, s(FPY, oo), mass, dt, nvy, npy);
+    verlet(fx, fpx, mass, dt, nvx, npx);
+    verlet(fy, fpy, mass, dt, nvy, npy);
+    double ox = 0.0, oy = 0.0;
+    if (MODEL == 1) {
+        verlet(tq, tq_prev, inertia, dt, w, phi);
+        phi = wrap_to_pi(phi);
+        ox = sin(phi) * r_ts; oy = -cos(phi) * r_ts;   // shoulders(), agents.py:473-486
+    }
     o(PX, t) = npx; o(PY, t) = npy; o(VX, t) = nvx; o(VY, t) = nvy;
     o(E0X, t) = e0x; o(E0Y, t) = e0y;
     o(FX, t) = rst ? 0.0 : fx; o(FY, t) = rst ? 0.0 : fy;
     o(FPX, t) = fx; o(FPY, t) = fy;
-    o(RADIUS, t) = s(RADIUS, oo); o(MASS, t) = mass; o(V0, t) = s(V0, oo); o(TAU_ADJ, t) = s(TAU_ADJ, oo);
-    o(K_SOC, t) = s(K_SOC, oo); o(TAU_0, t) = s(TAU_0, oo); o(MU, t) = mu; o(KAPPA, t) = kappa; o(DAMPING, t) = damping;
-    o(STD_RAND_FORCE, t) = s(STD_RAND_FORCE, oo);
-    o.id[t] = s.id[oo];
-    o.target[t] = s.target[oo];
+    o(RADIUS, t) = c_radius; o(MASS, t) = mass; o(V0, t) = c_v0; o(TAU_ADJ, t) = c_tau_adj;
+    o(K_SOC, t) = c_k_soc; o(TAU_0, t) = c_tau_0; o(MU, t) = mu; o(KAPPA, t) = kappa; o(DAMPING, t) = damping;
+    o(STD_RAND_FORCE, t) = c_srf;
+    o.id[t] = c_id;
+    o.target[t] = c_target;
     if (MODEL == 1) {
-        const double inertia = s(INERTIA, oo), r_ts = s(R_TS, oo);
-        double w = s(OMEGA, oo), phi = s(PHI, oo);
-        verlet(tq, s(TORQUE_PREV, oo), inertia, dt, w, phi);
-        phi = wrap_to_pi(phi);
-        const double ox = sin(phi) * r_ts, oy = -cos(phi) * r_ts;   // shoulders(), agents.py:473-486
         o(LSX, t) = npx - ox; o(LSY, t) = npy - oy; o(RSX, t) = npx + ox; o(RSY, t) = npy + oy;
-        o(R_T, t) = s(R_T, oo); o(R_S, t) = s(R_S, oo); o(R_TS, t) = r_ts; o(INERTIA, t) = inertia; o(OMEGA0, t) = s(OMEGA0, oo);
+        o(R_T, t) = c_r_t; o(R_S, t) = c_r_s; o(R_TS, t) = r_ts; o(INERTIA, t) = inertia; o(OMEGA0, t) = c_omega0;
         o(PHI, t) = phi; o(OMEGA, t) = w; o(PHI0, t) = phi0;
-        o(TORQUE, t) = rst ? 0.0 : tq; o(TORQUE_PREV, t) = tq; o(TAU_ROT, t) = s(TAU_ROT, oo);
-        o(STD_RAND_TORQUE, t) = s(STD_RAND_TORQUE, oo);
+        o(TORQUE, t) = rst ? 0.0 : tq; o(TORQUE_PREV, t) = tq; o(TAU_ROT, t) = c_tau_rot;
+        o(STD_RAND_TORQUE, t) = c_srt;
     }
 }

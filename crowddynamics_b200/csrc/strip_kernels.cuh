@@ -68,7 +68,7 @@ __global__ void k_halo_unpack(const double *__restrict__ msg, int rec, double *_
     if (nbr_sweep != nbr)     // three-circle: compact sweep records of the ghosts {px, py, vx, vy, extent, -}
         for (long long i = threadIdx.x; i < (long long)count * 6; i += blockDim.x) {
             const long long a = i / 6, f = i % 6;
-            nbr_sweep[(size_t)base * 6 + i] = f < 5 ? src[a * rec + f] : 0.0;
+            nbr_sweep[(size_t)base * 6 + i] = f < 5 ? src[a * rec + f] : src[a * rec + 4] * (1.0 + 1e-9);
         }
 }
 

@@ -168,6 +168,16 @@ class DeviceAgents:
         """Fix the capacity of the pair list of kernel variant 3 (0 = automatic); a test hook for the repeat path."""
         _lib.check(self.lib.cdb_set_pair_capacity(self.handle, int(pairs)))
 
+    def set_search_refinement(self, refinement):
+        """0 = automatic (search on cell_size / 2 where valid), 1 = always search on the cell_size lattice."""
+        _lib.check(self.lib.cdb_set_search_refinement(self.handle, int(refinement)))
+
+    def ext_max(self):
+        """Bound on the radius / body extent of the uploaded agents (the refined search needs 3 + 2 ext_max < cell_size)."""
+        v = C.c_double()
+        _lib.check(self.lib.cdb_get_ext_max(self.handle, C.byref(v)))
+        return v.value
+
     def pair_stats(self):
         """-> (capacity, pairs listed by the last step, steps repeated after an overflow)."""
         a, b, c = C.c_int64(), C.c_int64(), C.c_int64()

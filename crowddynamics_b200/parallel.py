@@ -57,6 +57,12 @@ class CudaStripDevice:
         ids = np.ascontiguousarray(ids, dtype=np.int64)
         _lib.check(self.lib.cdb_set_agent_ids(self.handle, C.c_void_p(ids.ctypes.data), len(ids)))
 
+    def ext_max(self):
+        return self.dev.ext_max()
+
+    def set_search_refinement(self, refinement):
+        self.dev.set_search_refinement(refinement)
+
     def set_strip(self, ix_min, iy_min, nx_owned, ny, has_left, has_right, halo_cap, mig_cap):
         _lib.check(self.lib.cdb_set_strip(self.handle, ix_min, iy_min, nx_owned, ny, int(has_left), int(has_right),
                                           halo_cap, mig_cap))
@@ -118,7 +124,7 @@ class StripSimulation:
     """One rank's strip of a crowd that is decomposed along x."""
 
     def __init__(self, dev, rank, world, bounds, lattice, cell_size, halo_cap, mig_cap, tensor_device, n_owned,
-                 dist=None, flags=_lib.STEP_ALL, dt_min=0.01, dt_max=0.01):
+                 dist=None, flags=_lib.STEP_ALL, dt_min=0.01, dt_max=0.01, model=None, ext_max=None):
         import torch
         self.torch = torch
         self.dist = dist
@@ -130,6 +136,21 @@ class StripSimulation:
         self.left = rank - 1 if rank > 0 else None
         self.right = rank + 1 if rank < world - 1 else None
         ix_min, iy_min, nx, ny = lattice
+        # Search lattice: every rank must bin on the same one, and the choice mirrors what a single device does on its own
+        # (circular agents: cells of cell_size / 2 whenever no pair can interact beyond cell_size, which needs the largest
+        # radius of the WHOLE crowd), so that the strips reproduce the single-device run bit for bit.
+        self.refinement = 1
+        if model == MODEL_CIRCULAR and hasattr(dev, 'set_search_refinement'):
+            if ext_max is None:
+                ext_max = dev.ext_max()
+                if dist is not None and world > 1:
+                    tmax = torch.tensor([ext_max], dtype=torch.float64, device=tensor_device)
+                    dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+                    ext_max = float(tmax.item())
+            if (3.0 + 2.0 * ext_max) * (1.0 + 1e-9) < self.cell_size:
+                self.refinement = 2
+        if hasattr(dev, 'set_search_refinement'):
+            dev.set_search_refinement(self.refinement)
         halo_doubles, mig_doubles = dev.set_strip(self.bounds[rank], iy_min, self.bounds[rank + 1] - self.bounds[rank], ny,
                                                   self.left is not None, self.right is not None, halo_cap, mig_cap)
 
@@ -233,8 +254,11 @@ class StripSimulation:
         dev.set_obstacles(obstacles)
         for t, (mg, uv) in enumerate(fields or ()):
             dev.set_navigation_field(t, mg, uv)
+        ext = None
+        if model == MODEL_CIRCULAR and len(agents):
+            ext = float(np.max(agents['radius']))       # the whole crowd is known to every rank here
         return cls(dev, rank, world, bounds, lattice, cell_size, halo_cap, mig_cap, tensor_device, len(local), dist=dist,
-                   flags=flags, dt_min=dt_min, dt_max=dt_max)
+                   flags=flags, dt_min=dt_min, dt_max=dt_max, model=model, ext_max=ext)
 
     @classmethod
     def synthetic(cls, model, n_per_rank, density, rank, world, device_index, seed=0, cell_size=3.6, dist=None,
@@ -265,7 +289,7 @@ class StripSimulation:
         mg, uv = S.direction_field(1.0, (x0 - 8.0, 0.0, x0 + side + 8.0, side), 'exit', point=(world * side, side / 2))
         dev.set_navigation_field(0, mg, uv)
         sim = cls(dev, rank, world, bounds, (ix_min, iy_min, nx, ny), cell_size, halo_cap, mig_cap,
-                  torch.device('cuda', device_index), n_per_rank, dist=dist, dt_min=dt_min, dt_max=dt_max)
+                  torch.device('cuda', device_index), n_per_rank, dist=dist, dt_min=dt_min, dt_max=dt_max, model=mid)
         sim.settle()
         return sim
 

@@ -116,3 +116,62 @@ def test_dense_jam_grows_the_list_on_its_own(model):
     assert vec_rel_err(got['force'], ref['force']) <= 1e-9
     if model == 'three_circle':
         assert vec_rel_err(got['torque'], ref['torque']) <= 1e-9
+
+
+# ---- search lattice refinement (cells of cell_size / 2, reach 2) -----------------------------------------------------------
+def _forces(model, agents, obstacles, cell, refinement, variant=3):
+    dev = DeviceAgents(_mid(model))
+    dev.set_variant(variant)
+    dev.set_search_refinement(refinement)
+    dev.upload(agents)
+    dev.set_obstacles(obstacles)
+    dev.step(1, _lib.STEP_ADJUSTING | _lib.STEP_ORIENTATION | _lib.STEP_AGENT_AGENT | _lib.STEP_AGENT_OBSTACLE, cell, 0.01, 0.01,
+             want_dt=False)
+    out = agents.copy()
+    dev.download(out)
+    # the exports keep describing the cell_size lattice, whatever the search used
+    dev.build_block_list(cell)
+    grid = dev.grid()
+    dev.close()
+    return out, grid
+
+
+@pytest.mark.parametrize('model', MODELS)
+@pytest.mark.parametrize('cell', [3.6, 5.0])
+def test_refined_search_lattice_finds_the_same_pairs(model, cell):
+    agents, obstacles, side = S.uniform_crowd(7000, model, density=1.3, seed=41, overlap_fraction=0.03)
+    ref = agents.copy()
+    O.orientation(ref); O.adjusting(ref); O.agent_agent_block_list(ref, cell); O.agent_obstacle(ref, obstacles)
+    coarse, g1 = _forces(model, agents, obstacles, cell, 1)
+    fine, g2 = _forces(model, agents, obstacles, cell, 0)
+    both_sides, _ = _forces(model, agents, obstacles, cell, 0, variant=2)
+    assert g1 == g2
+    for got in (coarse, fine):
+        assert vec_rel_err(got['force'], ref['force']) <= 1e-9
+        if model == 'three_circle':
+            assert vec_rel_err(got['torque'], ref['torque']) <= 1e-9
+    # same pair set, only the summation order differs between the two lattices
+    assert vec_rel_err(fine['force'], coarse['force']) <= 1e-12
+    assert rel_err_fields(fine, both_sides)[0] == 0
+
+
+@pytest.mark.parametrize('model', MODELS)
+def test_refinement_is_refused_when_pairs_can_interact_beyond_a_cell(model):
+    """Agents twice as wide (3 + 2 R > cell_size) or a small cell_size: pairs of non-adjacent cells can be closer than the
+    interaction range, the reference's block list does not see them, and neither may we -- the search must stay on the
+    cell_size lattice."""
+    agents, obstacles, side = S.uniform_crowd(3000, model, density=0.5, seed=42)
+    for f in ('radius', 'r_t', 'r_s', 'r_ts'):
+        if f in agents.dtype.names:
+            agents[f] *= 2.2
+    if model == 'three_circle':
+        S.set_shoulders(agents)
+    for cell in (3.6, 2.0):
+        ref = agents.copy()
+        O.adjusting(ref); O.agent_agent_block_list(ref, cell); O.agent_obstacle(ref, obstacles)
+        brute = agents.copy()
+        O.adjusting(brute); O.agent_agent_brute(brute); O.agent_obstacle(brute, obstacles)
+        got, _ = _forces(model, agents, obstacles, cell, 0)
+        assert vec_rel_err(got['force'], ref['force']) <= 1e-9
+        if cell == 2.0:
+            assert vec_rel_err(ref['force'], brute['force']) > 1e-6     # the block list really misses pairs here
