@@ -30,27 +30,33 @@ CELL = 3.6
 
 
 def profile_counters(model, n_agents, density):
-    """DRAM traffic and fp64 instruction count of ONE launch of the dominant kernel from the committed ncu --set full
-    summary (profiles/ncu_full_<model>_<tag>.txt) -- only valid for the workload that was profiled (1 M agents, 1 /m^2)."""
+    """Per-kernel counters of ONE launch from the committed ncu --set full summary (profiles/ncu_full_<model>_<tag>.txt,
+    the newest tag) -- only valid for the workload that was profiled (1 M agents, 1 /m^2).
+    -> {'source': path, 'kernels': {base kernel name: {metric: value}}}"""
     if n_agents != 1000000 or abs(density - 1.0) > 1e-12:
         return None
     import glob
-    files = sorted(glob.glob(os.path.join(ROOT, 'profiles', 'ncu_full_%s_*.txt' % model)))
+    files = sorted(glob.glob(os.path.join(ROOT, 'profiles', 'ncu_full_%s_r*.txt' % model)), key=os.path.getmtime)
     if not files:
         return None
-    out = {'source': os.path.relpath(files[-1], ROOT)}
-    unit_scale = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
+    out = {'source': os.path.relpath(files[-1], ROOT), 'kernels': {}}
+    unit_scale = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9, 'ns': 1e-6, 'us': 1e-3, 'ms': 1.0, 's': 1e3}
+    cur = None
     with open(files[-1]) as f:
         for line in f:
+            if line.startswith('kernel:'):
+                name = line.split(':', 1)[1].strip()
+                name = name.replace('void ', '').split('<')[0].split('(')[0].strip()
+                cur = out['kernels'].setdefault(name, {})
+                continue
             c = line.split()
-            if len(c) < 2:
+            if cur is None or len(c) < 2:
                 continue
             try:
-                if c[0] in ('dram__bytes_read.sum', 'dram__bytes_write.sum'):
-                    out[c[0]] = float(c[-1].replace(',', '')) * unit_scale.get(c[1], 1.0)
-                elif c[0] in ('smsp__inst_executed_pipe_fp64.sum', 'sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active',
-                              'gpu__time_duration.sum'):
-                    out[c[0]] = float(c[-1].replace(',', ''))
+                if c[0] in ('dram__bytes_read.sum', 'dram__bytes_write.sum', 'gpu__time_duration.sum'):
+                    cur[c[0]] = float(c[-1].replace(',', '')) * unit_scale.get(c[1], 1.0)
+                elif c[0] in ('smsp__inst_executed_pipe_fp64.sum', 'sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active'):
+                    cur[c[0]] = float(c[-1].replace(',', ''))
             except ValueError:
                 pass
     return out
@@ -333,44 +339,49 @@ def main():
     peak, peak_src = measured_peaks()
     n_rank0 = agents_total // world if world > 1 else n
     roofline = None
+    fp64 = None
     if prof[3] > 0:
-        k_ms = prof[1] / prof[3]                      # dominant kernel: agent-agent (+ fused epilogue)
+        # One step = block list + three kernels of the once-per-pair pipeline.  The longest of them, k_finish, streams every
+        # agent's state once (the SURVEY 8(d) algorithmic bytes) and is the HBM-bound one: it carries `roofline`.  k_sweep is
+        # bound by the fp64 pipe: `roofline_fp64`.  Durations: CUDA events on the sim's stream around each phase.
+        steps_p = ph[5]
+        phases = {'pre_and_block_list': ph[0] / steps_p, 'pair_sweep': ph[1] / steps_p, 'pair_eval': ph[2] / steps_p,
+                  'finish': ph[3] / steps_p, 'post': ph[4] / steps_p}
+        k_ms = phases['finish']
         algo_bytes = ALGO_BYTES[args.model] * n_rank0
         achieved = algo_bytes / (k_ms * 1e-3) / 1e9
         pc = profile_counters(args.model, n_rank0, args.density)
         traffic = None
-        if pc and 'dram__bytes_read.sum' in pc:
-            traffic = pc['dram__bytes_read.sum'] + pc['dram__bytes_write.sum']
-        roofline = {'bound': 'hbm', 'kernel': 'k_step<%s> (fused agent-agent + walls + integrator)' % args.model,
+        kf = (pc or {}).get('kernels', {}).get('k_finish', {})
+        if 'dram__bytes_read.sum' in kf:
+            traffic = kf['dram__bytes_read.sum'] + kf['dram__bytes_write.sum']
+        roofline = {'bound': 'hbm', 'kernel': 'k_finish<%s> (per-agent nodes, ordered sum of the pair contributions, walls, '
+                                              'integrator, reset; the dominant kernel of the step)' % args.model,
                     'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                     'frac': achieved / peak, 'peak_source': peak_src, 'traffic': traffic,
                     'traffic_source': pc['source'] if pc else None,
                     'kernel_ms': k_ms, 'algorithmic_bytes_per_launch': algo_bytes,
-                    'phase_ms_per_step': {'pre_and_block_list': prof[0] / prof[3], 'agent_agent': k_ms,
-                                          'pair_sweep': ph[1] / ph[5], 'pair_eval': ph[2] / ph[5],
-                                          'step_kernel': ph[3] / ph[5], 'post': prof[2] / prof[3]},
-                    'note': 'the pair kernel is FP64-pipe bound at this density (SURVEY 7): HBM fraction is low by '
-                            'construction; see DESIGN.md for the FP64 roofline'}
-    # fp64 roofline of the same kernel: DFMA peak measured live, fp64 warp-instructions per launch from the committed profile
-    fp64 = None
-    try:
-        if args.no_fp64_peak:
-            raise RuntimeError('skipped (--no-fp64-peak)')
-        import ctypes as C
-        tf = C.c_double()
-        _lib.check(_lib.load().cdb_measure_fp64_peak(local_rank, C.byref(tf)))
-        fp64 = {'peak_tflops_measured_dfma': tf.value}
-        key = 'sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active'
-        if roofline and pc and key in pc and 'gpu__time_duration.sum' in pc:
-            # fp64-pipe utilisation of the profiled launch, rescaled to the live kernel duration (same instruction count)
-            with open(os.path.join(ROOT, pc['source'])) as f:
-                unit = [l.split()[1] for l in f if l.startswith('gpu__time_duration.sum')][0]
-            t_ncu_ms = pc['gpu__time_duration.sum'] * {'us': 1e-3, 'ms': 1.0, 'ns': 1e-6, 's': 1e3}.get(unit, 1.0)
-            fp64.update({'pipe_frac_ncu': pc[key] / 100.0, 'kernel_ms_ncu': t_ncu_ms,
-                         'pipe_frac_live': pc[key] / 100.0 * t_ncu_ms / roofline['kernel_ms'],
-                         'source': pc['source']})
-    except Exception as exc:   # pragma: no cover
-        fp64 = {'note': str(exc)}
+                    'phase_ms_per_step': phases,
+                    'whole_step': {'ms': ms / args.steps, 'achieved': algo_bytes / (ms / args.steps * 1e-3) / 1e9,
+                                   'frac': algo_bytes / (ms / args.steps * 1e-3) / 1e9 / peak},
+                    'note': 'the step is split over an fp64-bound kernel (k_sweep), a latency/divergence-bound one '
+                            '(k_pair_eval) and this HBM-streaming one; see roofline_fp64 and DESIGN.md section 4'}
+        # fp64 roofline of the sweep: DFMA peak measured live, fp64 warp-instructions per launch from the committed profile
+        try:
+            if args.no_fp64_peak:
+                raise RuntimeError('skipped (--no-fp64-peak)')
+            import ctypes as C
+            tf = C.c_double()
+            _lib.check(_lib.load().cdb_measure_fp64_peak(local_rank, C.byref(tf)))
+            fp64 = {'kernel': 'k_sweep<%s> (forward-half-stencil pair classification)' % args.model,
+                    'peak_tflops_measured_dfma': tf.value, 'phase_ms': phases['pair_sweep']}
+            ks = (pc or {}).get('kernels', {}).get('k_sweep', {})
+            key = 'sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active'
+            if key in ks and 'gpu__time_duration.sum' in ks:
+                fp64.update({'pipe_frac_ncu': ks[key] / 100.0, 'kernel_ms_ncu': ks['gpu__time_duration.sum'],
+                             'source': pc['source']})
+        except Exception as exc:   # pragma: no cover
+            fp64 = {'note': str(exc)}
     line = {
         'metric': 'agent-steps/sec', 'value': value, 'unit': 'agent-steps/s', 'n_gpus': world, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',

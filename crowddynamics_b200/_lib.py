@@ -53,6 +53,10 @@ def _signatures(L):
         'cdb_num_agents': (i64, [vp]),
         'cdb_upload_agents_aos': (i32, [vp, vp, i64, i64]),
         'cdb_download_agents_aos': (i32, [vp, vp, i64, i64, u32]),
+        'cdb_host_register': (i32, [vp, vp, i64, i64]),
+        'cdb_host_unregister': (i32, [vp, vp]),
+        'cdb_upload_agents_fields': (i32, [vp, vp, i64, i64, u32]),
+        'cdb_transfer_stats': (i32, [vp, pi64, pi64, i32]),
         'cdb_set_obstacles': (i32, [vp, vp, i64]),
         'cdb_set_navigation_field': (i32, [vp, i64, vp, vp, i64, i64, f64, f64, f64]),
         'cdb_clear_navigation': (i32, [vp]),

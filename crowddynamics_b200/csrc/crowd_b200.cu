@@ -23,6 +23,7 @@
 #include "kernels.cuh"
 #include "step_kernel.cuh"
 #include "finish_kernel.cuh"
+#include "transfer_kernels.cuh"
 #include "strip_kernels.cuh"
 #include "collective_kernels.cuh"
 
@@ -100,6 +101,10 @@ struct cdb_sim {
     int64_t aos_capacity = 0;
     uint8_t *h_bounce = nullptr;   // pinned host bounce buffer for field-wise downloads
     int64_t bounce_bytes = 0;
+    std::vector<std::pair<void *, size_t>> registered;   // host ranges pinned by cdb_host_register
+    int *d_rec_slot = nullptr;     // record index -> slot (field-masked uploads into a re-sorted state)
+    int64_t rec_slot_cap = 0;
+    int64_t h2d_bytes = 0, d2h_bytes = 0;   // bytes moved over PCIe by the transfer entry points (cdb_transfer_stats)
 
     // block list
     bool lattice_fixed = false;
@@ -204,6 +209,7 @@ namespace {
 
 int alloc_soa(Soa &s, int n_planes, int64_t capacity) {
     s.stride = (capacity + 31) / 32 * 32;
+    s.np = n_planes;
     CKS(dev_alloc(&s.p, (size_t)n_planes * s.stride));
     CKS(dev_alloc(&s.id, s.stride));
     CKS(dev_alloc(&s.target, s.stride));
@@ -688,10 +694,13 @@ int cdb_destroy(cdb_sim *sim) {
     cudaSetDevice(sim->device);
     if (sim->stream) cudaStreamSynchronize(sim->stream);
     free_soa(sim->cur); free_soa(sim->alt);
-    cudaFree(sim->d_aos); cudaFreeHost(sim->h_bounce);
+    cudaFree(sim->d_aos); cudaFreeHost(sim->h_bounce); cudaFree(sim->d_rec_slot);
+    for (auto &r : sim->registered) cudaHostUnregister(r.first);
     cudaFree(sim->d_grid); cudaFree(sim->d_cell_count); cudaFree(sim->d_cell_start); cudaFree(sim->d_cell_fill);
     cudaFree(sim->d_cell_of_slot); cudaFree(sim->d_order_tmp); cudaFree(sim->d_order); if (sim->d_nbr_sweep != sim->d_nbr) cudaFree(sim->d_nbr_sweep); cudaFree(sim->d_nbr); cudaFree(sim->d_scan_partials);
     cudaFree(sim->d_bbox); cudaFreeHost(sim->h_bbox);
+    cudaFree(sim->d_par); cudaFree(sim->pb.pairs); cudaFree(sim->pb.cres); cudaFree(sim->pb.cnt); cudaFree(sim->pb.off); cudaFree(sim->pb.fill);
+    cudaFree(sim->pb.ctr); cudaFreeHost(sim->h_pctr);
     cudaFree(sim->d_obstacles);
     for (auto &f : sim->nav) { cudaFree((void *)f.U); cudaFree((void *)f.V); }
     cudaFree(sim->d_is_leader); cudaFree(sim->d_is_follower); cudaFree(sim->d_has_a); cudaFree(sim->d_has_detected);
@@ -730,6 +739,38 @@ int cdb_synchronize(cdb_sim *sim) {
 
 int64_t cdb_num_agents(const cdb_sim *sim) { return sim ? sim->n : -1; }
 
+}  // extern "C" (helpers follow)
+
+namespace {
+// selected fields of a record as 32-bit words in record order (transfer_kernels.cuh)
+WordMap word_map(const cdb_sim *sim, uint32_t mask, int *bytes) {
+    int nf = 0;
+    const FieldMap *fm = host_field_map(sim->model, &nf);
+    std::vector<std::pair<int, int>> sel;   // (offset, plane)
+    for (int f = 0; f < nf; ++f) if (fm[f].bit & mask) sel.emplace_back(fm[f].offset, fm[f].plane);
+    std::sort(sel.begin(), sel.end());
+    WordMap m{};
+    for (const auto &e : sel) {
+        for (int h = 0; h < 2; ++h) {
+            m.word[m.n_words] = (short)(e.first / 4 + h); m.plane[m.n_words] = (short)e.second; m.hi[m.n_words] = (unsigned char)h;
+            ++m.n_words;
+        }
+    }
+    *bytes = 4 * m.n_words;
+    return m;
+}
+
+// device-visible alias of a pinned / registered host range (nullptr: pageable memory)
+void *mapped_host(const void *p) {
+    cudaPointerAttributes a{};
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (a.type != cudaMemoryTypeHost || !a.devicePointer) return nullptr;
+    return a.devicePointer;
+}
+}  // namespace
+
+extern "C" {
+
 int cdb_upload_agents_aos(cdb_sim *sim, const void *agents, int64_t n, int64_t itemsize) {
     if (!sim) return fail(CDB_ERR_INVALID_VALUE, "sim is NULL");
     sim->state_version++;
@@ -748,6 +789,7 @@ int cdb_upload_agents_aos(cdb_sim *sim, const void *agents, int64_t n, int64_t i
     sim->auto_lattice_valid = false;
     if (n == 0) return CDB_OK;
     CK(cudaMemcpyAsync(sim->d_aos, agents, n * itemsize, cudaMemcpyHostToDevice, sim->stream));
+    sim->h2d_bytes += n * itemsize;
     const int smem = AOS_REC_PER_BLOCK * (int)itemsize;
     if (sim->model == CDB_MODEL_CIRCULAR)
         LAUNCH(sim, k_unpack_aos<0>, cdiv(n, AOS_REC_PER_BLOCK), AOS_REC_PER_BLOCK, smem, sim->d_aos, (int)n, sim->cur);
@@ -779,6 +821,22 @@ int cdb_download_agents_aos(cdb_sim *sim, void *agents, int64_t n, int64_t items
     CK(cudaSetDevice(sim->device));
     const uint32_t mask = field_mask & CDB_F_ALL_MUTABLE;
     const uint32_t pack_mask = (field_mask & CDB_F_WHOLE_RECORD) ? (uint32_t)CDB_F_ALL_MUTABLE : mask;
+    if (!(field_mask & CDB_F_WHOLE_RECORD)) {
+        // selected fields straight into the caller's records when they are pinned / registered (zero-copy over PCIe)
+        void *hm = mapped_host(agents);
+        int bytes = 0;
+        const WordMap m = word_map(sim, mask, &bytes);
+        if (hm && m.n_words > 0) {
+            const long long threads = (long long)n * m.n_words;
+            LAUNCH(sim, k_fields_to_host, cdiv(threads, 256), 256, 0, sim->cur, (int)n, (uint32_t *)hm, (int)(itemsize / 4), m);
+            CK(cudaGetLastError());
+            CK(cudaStreamSynchronize(sim->stream));
+            sim->d2h_bytes += (int64_t)bytes * n;
+            return check_device_error(sim);
+        }
+        if (m.n_words == 0) return check_device_error(sim);
+    }
+    sim->d2h_bytes += n * itemsize;
     if (sim->model == CDB_MODEL_CIRCULAR)
         LAUNCH(sim, k_pack_aos<0>, cdiv(n, 128), 128, 0, sim->cur, (int)n, sim->d_aos, pack_mask);
     else
@@ -816,6 +874,84 @@ int cdb_download_agents_aos(cdb_sim *sim, void *agents, int64_t n, int64_t items
     for (int64_t i = 0; i < n; ++i, dst += itemsize, src += itemsize)
         for (const auto &r : runs) memcpy(dst + r.first, src + r.first, (size_t)r.second);
     return check_device_error(sim);
+}
+
+int cdb_host_register(cdb_sim *sim, void *agents, int64_t n, int64_t itemsize) {
+    if (!sim) return fail(CDB_ERR_INVALID_VALUE, "sim is NULL");
+    if (!agents || n <= 0) return CDB_OK;
+    CK(cudaSetDevice(sim->device));
+    if (mapped_host(agents)) return CDB_OK;          // already pinned (cudaHostAlloc / registered before)
+    CK(cudaHostRegister(agents, (size_t)(n * itemsize), cudaHostRegisterMapped));
+    sim->registered.emplace_back(agents, (size_t)(n * itemsize));
+    return CDB_OK;
+}
+
+int cdb_host_unregister(cdb_sim *sim, void *agents) {
+    if (!sim) return fail(CDB_ERR_INVALID_VALUE, "sim is NULL");
+    CK(cudaSetDevice(sim->device));
+    CK(cudaStreamSynchronize(sim->stream));
+    for (size_t k = 0; k < sim->registered.size(); ++k)
+        if (sim->registered[k].first == agents) {
+            cudaHostUnregister(agents);
+            sim->registered.erase(sim->registered.begin() + k);
+            return CDB_OK;
+        }
+    return CDB_OK;
+}
+
+int cdb_upload_agents_fields(cdb_sim *sim, const void *agents, int64_t n, int64_t itemsize, uint32_t field_mask) {
+    if (!sim) return fail(CDB_ERR_INVALID_VALUE, "sim is NULL");
+    if (itemsize != sim->itemsize) return fail(CDB_ERR_INVALID_TYPE, "agent itemsize %lld does not match the model (%lld)", (long long)itemsize, (long long)sim->itemsize);
+    if (n != sim->n || sim->n_dead != 0 || sim->strip)
+        return fail(CDB_ERR_STATE, "cdb_upload_agents_fields updates the %lld agents uploaded before (got %lld)", (long long)sim->n, (long long)n);
+    const uint32_t mask = field_mask & CDB_F_ALL_MUTABLE;
+    if (n == 0 || mask == 0) return CDB_OK;
+    if (!agents) return fail(CDB_ERR_INVALID_VALUE, "agents is NULL");
+    CK(cudaSetDevice(sim->device));
+    sim->state_version++;
+    int bytes = 0;
+    const WordMap m = word_map(sim, mask, &bytes);
+    void *hm = mapped_host(agents);
+    // the planes may have been re-sorted by fused steps since the upload: record index -> slot
+    if (n > sim->rec_slot_cap) { CKS(dev_alloc(&sim->d_rec_slot, (size_t)n)); sim->rec_slot_cap = n; }
+    LAUNCH(sim, k_slot_of_id, cdiv(n, 256), 256, 0, sim->cur, (int)n, sim->d_rec_slot);
+    if (hm && bytes <= TRANSFER_ZERO_COPY_MAX) {
+        const long long threads = (long long)n * (m.n_words / 2);
+        LAUNCH(sim, k_fields_from_host, cdiv(threads, 256), 256, 0, (const uint32_t *)hm, (int)(itemsize / 4), sim->cur, (int)n, sim->d_rec_slot, m);
+        sim->h2d_bytes += (int64_t)bytes * n;
+    } else {
+        // whole-record DMA into the device image (55 GB/s from pinned memory), then the same field kernel from device memory
+        CK(cudaMemcpyAsync(sim->d_aos, agents, n * itemsize, cudaMemcpyHostToDevice, sim->stream));
+        const long long threads = (long long)n * (m.n_words / 2);
+        LAUNCH(sim, k_fields_from_host, cdiv(threads, 256), 256, 0, (const uint32_t *)sim->d_aos, (int)(itemsize / 4), sim->cur, (int)n, sim->d_rec_slot, m);
+        sim->h2d_bytes += n * itemsize;
+    }
+    CK(cudaGetLastError());
+    sim->tables_valid = false;
+    if (mask & (CDB_F_POSITION | CDB_F_SHOULDERS)) {
+        sim->auto_lattice_valid = false;
+        if (sim->model == CDB_MODEL_THREE_CIRCLE && (mask & (CDB_F_POSITION | CDB_F_SHOULDERS))) {
+            // new positions / shoulders can change the body extents the search refinement relies on
+            CK(cudaMemsetAsync(sim->d_extmax, 0, sizeof(unsigned long long), sim->stream));
+            LAUNCH(sim, k_ext_max, (cdiv(n, 1024) < 1184 ? cdiv(n, 1024) : 1184), 256, 0, sim->cur, (int)n, sim->model, sim->d_extmax);
+            CK(cudaMemcpyAsync(sim->h_extmax, sim->d_extmax, sizeof(unsigned long long), cudaMemcpyDeviceToHost, sim->stream));
+            CK(cudaStreamSynchronize(sim->stream));
+            const unsigned long long k = *sim->h_extmax;
+            const unsigned long long b = (k & 0x8000000000000000ULL) ? (k & 0x7fffffffffffffffULL) : ~k;
+            double e; memcpy(&e, &b, sizeof(e));
+            sim->ext_max = k == 0 ? 0.0 : e;
+        }
+    }
+    CK(cudaStreamSynchronize(sim->stream));      // the host buffer may be reused by the caller right away
+    return CDB_OK;
+}
+
+int cdb_transfer_stats(cdb_sim *sim, int64_t *h2d_bytes, int64_t *d2h_bytes, int reset) {
+    if (!sim) return fail(CDB_ERR_INVALID_VALUE, "sim is NULL");
+    if (h2d_bytes) *h2d_bytes = sim->h2d_bytes;
+    if (d2h_bytes) *d2h_bytes = sim->d2h_bytes;
+    if (reset) sim->h2d_bytes = sim->d2h_bytes = 0;
+    return CDB_OK;
 }
 
 int cdb_set_obstacles(cdb_sim *sim, const double *segments, int64_t n_segments) {
@@ -1322,14 +1458,14 @@ int cdb_strip_finish(cdb_sim *sim, uint32_t flags, double dt_min, double dt_max,
     const int ny = (int)sim->grid.ny * sim->strip_fine;      // cells of one cell_size column
     const int base_l = (int)sim->capacity, base_r = (int)(sim->capacity + sim->halo_cap);
     if (sim->has_left) {
-        if (halo_left_in) LAUNCH(sim, k_halo_unpack, 1, 1024, 0, halo_left_in, rec, sim->d_nbr, sim->d_nbr_sweep, sim->d_cell_of_slot, sim->d_cell_start, sim->d_cell_count,
-                                 0, ny, base_l, (long long)sim->halo_cap, sim->d_error);
+        if (halo_left_in) LAUNCH(sim, k_halo_unpack, 32, 1024, 0, halo_left_in, rec, sim->d_nbr, sim->d_nbr_sweep, sim->d_cell_of_slot, sim->d_cell_start, sim->d_cell_count,
+                                 0, ny, base_l, (long long)sim->halo_cap, sim->d_error, sim->d_par);
         else LAUNCH(sim, k_ghost_clear, 4, 256, 0, sim->d_cell_start, sim->d_cell_count, 0, ny, base_l);
     }
     if (sim->has_right) {
         const int col = (int)sim->strip_col_hi + 1;
-        if (halo_right_in) LAUNCH(sim, k_halo_unpack, 1, 1024, 0, halo_right_in, rec, sim->d_nbr, sim->d_nbr_sweep, sim->d_cell_of_slot, sim->d_cell_start, sim->d_cell_count,
-                                  col, ny, base_r, (long long)sim->halo_cap, sim->d_error);
+        if (halo_right_in) LAUNCH(sim, k_halo_unpack, 32, 1024, 0, halo_right_in, rec, sim->d_nbr, sim->d_nbr_sweep, sim->d_cell_of_slot, sim->d_cell_start, sim->d_cell_count,
+                                  col, ny, base_r, (long long)sim->halo_cap, sim->d_error, sim->d_par);
         else LAUNCH(sim, k_ghost_clear, 4, 256, 0, sim->d_cell_start, sim->d_cell_count, col, ny, base_r);
     }
     CKS(prof_mark(sim));

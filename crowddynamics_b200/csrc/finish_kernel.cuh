@@ -14,10 +14,19 @@
 #include "pair_kernels.cuh"
 #include "step_kernel.cuh"
 
-constexpr int FIN_THREADS = 256;
+#ifndef FIN_THREADS_N
+#define FIN_THREADS_N 256
+#endif
+#ifndef FIN_MINB_THREE
+#define FIN_MINB_THREE 2
+#endif
+#ifndef FIN_MINB_CIRC
+#define FIN_MINB_CIRC 3
+#endif
+constexpr int FIN_THREADS = FIN_THREADS_N;
 
 template <int MODEL>
-__global__ void __launch_bounds__(FIN_THREADS, MODEL == 0 ? 3 : 2) k_finish(const StepArgs A) {
+__global__ void __launch_bounds__(FIN_THREADS, MODEL == 0 ? FIN_MINB_CIRC : FIN_MINB_THREE) k_finish(const StepArgs A) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= eff_n(A.n, A.n_dev)) return;
     const Soa &s = A.in;

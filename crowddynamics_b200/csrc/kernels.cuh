@@ -20,12 +20,27 @@ enum Plane {
     NP_THREE
 };
 
+// Tiled struct-of-arrays: the agents are grouped in tiles of 32 consecutive slots; inside a tile plane k holds its 32 values
+// contiguously (256 B: one coalesced warp access) and the np planes of the tile follow each other.  A warp working on 32
+// consecutive agents therefore streams ONE contiguous block of np * 256 B instead of np segments that lie a whole plane
+// (megabytes) apart -- measured (round 2, profiles/): the plane-major layout left k_finish / k_records at ~3.3 TB/s with
+// ~75 concurrent DRAM streams.
+#ifndef SOA_TILED
+#define SOA_TILED 1
+#endif
 struct Soa {
     double *p;
-    long long stride;
+    long long stride;    // slots allocated (multiple of 32)
     int *id;             // original agent index (row in the host array) of the agent in this slot
     long long *target;   // States.target (simulation/agents.py:41-45)
-    __device__ __forceinline__ double &operator()(int plane, int i) const { return p[(long long)plane * stride + i]; }
+    int np;              // planes per agent
+    __device__ __forceinline__ double &operator()(int plane, int i) const {
+#if SOA_TILED
+        return p[((long long)(i >> 5) * np + plane) * 32 + (i & 31)];
+#else
+        return p[(long long)plane * stride + i];
+#endif
+    }
 };
 
 struct Grid {

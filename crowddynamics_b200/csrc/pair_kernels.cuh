@@ -177,23 +177,32 @@ __global__ void __launch_bounds__(SW_THREADS, 8) k_sweep(const SweepArgs A) {
     if (mine && !ghost) atomicAdd(&A.pb.cnt[t], mine);
 }
 
-// private region of the contribution array for every agent (order of the regions is irrelevant)
-__global__ void k_pair_alloc(PairBuf pb, int n_slots) {
+// private region of the contribution array for every agent (order of the regions is irrelevant); one atomic per block
+__global__ void __launch_bounds__(256) k_pair_alloc(PairBuf pb, int n_slots) {
+    __shared__ int s_warp[8];
+    __shared__ unsigned long long s_base;
     if (pairs_overflowed(pb)) {
         if (pb.fatal && blockIdx.x == 0 && threadIdx.x == 0) atomicExch(pb.fatal, ERR_PAIR_OVERFLOW);
         return;
     }
-    const int a = blockIdx.x * blockDim.x + threadIdx.x;
-    const int lane = threadIdx.x & 31;
+    const int a = blockIdx.x * 256 + threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int c = a < n_slots ? pb.cnt[a] : 0;
     int incl = c;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const int w = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += w; }
-    const int total = __shfl_sync(0xffffffffu, incl, 31);
-    unsigned long long base = 0;
-    if (lane == 31 && total > 0) base = atomicAdd(&pb.ctr[1], (unsigned long long)total);
-    base = __shfl_sync(0xffffffffu, base, 31);
-    if (a < n_slots) { pb.off[a] = (int)base + incl - c; pb.fill[a] = 0; }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        const int ws = lane < 8 ? s_warp[lane] : 0;
+        int wi = ws;
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) { const int w = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += w; }
+        if (lane < 8) s_warp[lane] = wi - ws;
+        if (lane == 7) s_base = wi > 0 ? atomicAdd(&pb.ctr[1], (unsigned long long)wi) : 0ULL;
+    }
+    __syncthreads();
+    if (a < n_slots) { pb.off[a] = (int)s_base + s_warp[warp] + incl - c; pb.fill[a] = 0; }
 }
 
 // ---- both sides of a circular pair (interactions.py:53-70, distance.py:19-47, power_law.py:215-259) ---------------------

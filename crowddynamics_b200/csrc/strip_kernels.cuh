@@ -26,16 +26,29 @@ __global__ void k_halo_pack(const double *__restrict__ nbr, int rec, const int *
 }
 
 // message -> ghost column `col` of the local lattice; ghost records live at slots [base, base + count) of nbr.
+// Block 0 scans the per-cell counts into the cell tables; every block copies a share of the records (the copy does not
+// depend on the scan: ghosts arrive in cell order, so record k simply goes to slot base + k).
 __global__ void k_halo_unpack(const double *__restrict__ msg, int rec, double *__restrict__ nbr, double *__restrict__ nbr_sweep,
                               int *__restrict__ cell_sorted,
                               int *__restrict__ cell_start, int *__restrict__ cell_count, int col, int ny, int base, long long cap,
-                              int *error) {
-    // single block: exclusive scan of the per-cell counts
+                              int *error, double2 *__restrict__ par) {
     __shared__ int warp_sums[32];
     __shared__ int carry_s;
     const int *counts = reinterpret_cast<const int *>(msg + MSG_HEADER);
     const int count = (int)msg[0];
-    if ((int)msg[1] != ny || count > cap) { if (threadIdx.x == 0) atomicExch(error, ERR_CELL_RANGE + 2); return; }
+    if ((int)msg[1] != ny || count > cap) { if (threadIdx.x == 0 && blockIdx.x == 0) atomicExch(error, ERR_CELL_RANGE + 2); return; }
+    const double *src = msg + MSG_HEADER + halo_counts_doubles(ny);
+    double *dst = nbr + (size_t)base * rec;
+    const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x, nth = (long long)gridDim.x * blockDim.x;
+    for (long long i = tid; i < (long long)count * rec; i += nth) dst[i] = src[i];
+    if (nbr_sweep != nbr)     // three-circle: compact sweep records of the ghosts {px, py, vx, vy, extent, inflated extent}
+        for (long long i = tid; i < (long long)count * 6; i += nth) {
+            const long long a = i / 6, f = i % 6;
+            nbr_sweep[(size_t)base * 6 + i] = f < 5 ? src[a * rec + f] : src[a * rec + 4] * (1.0 + 1e-9);
+        }
+    // pair parameters of ghosts are never used for a stored result, but k_pair_eval reads them: keep them defined
+    if (par) for (long long i = tid; i < count; i += nth) par[base + i] = make_double2(0.0, 1.0);
+    if (blockIdx.x != 0) return;
     if (threadIdx.x == 0) carry_s = 0;
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -62,14 +75,6 @@ __global__ void k_halo_unpack(const double *__restrict__ msg, int rec, double *_
         if (threadIdx.x == blockDim.x - 1) carry_s = excl + v;
         __syncthreads();
     }
-    const double *src = msg + MSG_HEADER + halo_counts_doubles(ny);
-    double *dst = nbr + (size_t)base * rec;
-    for (long long i = threadIdx.x; i < (long long)count * rec; i += blockDim.x) dst[i] = src[i];
-    if (nbr_sweep != nbr)     // three-circle: compact sweep records of the ghosts {px, py, vx, vy, extent, -}
-        for (long long i = threadIdx.x; i < (long long)count * 6; i += blockDim.x) {
-            const long long a = i / 6, f = i % 6;
-            nbr_sweep[(size_t)base * 6 + i] = f < 5 ? src[a * rec + f] : src[a * rec + 4] * (1.0 + 1e-9);
-        }
 }
 
 // no neighbour on this side / nothing received: empty ghost column

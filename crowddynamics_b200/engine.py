@@ -70,6 +70,28 @@ class DeviceAgents:
         _lib.check(self.lib.cdb_upload_agents_aos(self.handle, C.c_void_p(int(ptr)), int(n), self.itemsize))
         self.n = int(n)
 
+    def upload_fields(self, agents, mask):
+        """Refresh only the fields in ``mask`` of the agents uploaded before (same array, same order)."""
+        if _check_agents(agents) != self.model:
+            raise InvalidType('agents dtype does not match the device model')
+        _lib.check(self.lib.cdb_upload_agents_fields(self.handle, _ptr(agents), len(agents), agents.dtype.itemsize, int(mask)))
+
+    def upload_fields_raw(self, ptr, n, mask):
+        _lib.check(self.lib.cdb_upload_agents_fields(self.handle, C.c_void_p(int(ptr)), int(n), self.itemsize, int(mask)))
+
+    def host_register(self, agents):
+        """Pin + map the host array so that field-masked transfers run as zero-copy kernels (see include/crowd_b200.h)."""
+        _lib.check(self.lib.cdb_host_register(self.handle, _ptr(agents), len(agents), agents.dtype.itemsize))
+
+    def host_unregister(self, agents):
+        _lib.check(self.lib.cdb_host_unregister(self.handle, _ptr(agents)))
+
+    def transfer_stats(self, reset=False):
+        """-> (h2d_bytes, d2h_bytes) moved over PCIe by upload / download calls so far."""
+        a, b = C.c_int64(), C.c_int64()
+        _lib.check(self.lib.cdb_transfer_stats(self.handle, C.byref(a), C.byref(b), 1 if reset else 0))
+        return a.value, b.value
+
     def download(self, agents, mask=_lib.F_ALL_MUTABLE):
         if _check_agents(agents) != self.model:
             raise InvalidType('agents dtype does not match the device model')

@@ -9,9 +9,11 @@ duck-typed tree (``LogicNodeBase`` below) provides the same surface.
 State handling: all nodes of one simulation share a ``DeviceState`` that mirrors
 ``simulation.agents.array`` on the GPU.
 
-* ``mode='strict'``   -- each ``update()`` uploads the host array, runs its kernel(s) and downloads the fields the
-  node writes: bit-for-bit the reference's contract (the host array is always coherent; host-side nodes such as
-  ``Fluctuation`` / ``InsideDomain`` / ``SaveSimulationData`` can sit anywhere in the tree).
+* ``mode='strict'``   -- each ``update()`` uploads the DIRTY fields of the host array (everything the first time; afterwards
+  only what host-side nodes declared with ``mark_dirty`` / ``HostNode(writes=...)``), runs its kernel(s) and downloads the
+  fields the node writes, field-granular over PCIe: the reference's contract (the host array is always coherent; host-side
+  nodes such as ``InsideDomain`` / ``SaveSimulationData`` can sit anywhere in the tree).  ``upload='always'`` re-sends the
+  whole array before every node, for trees that mix in host code which does not declare its writes.
 * ``mode='resident'`` -- the array is uploaded once; nodes only launch kernels; ``DeviceState.sync_host()`` refreshes
   the host array on demand (call it before any host-side node reads agents).  ``FusedStep`` runs the whole replaced
   sub-tree for many iterations in one C-ABI call.
@@ -20,7 +22,7 @@ import numpy as np
 
 from . import _lib
 from .engine import DeviceAgents
-from .exceptions import InvalidValue
+from .exceptions import InvalidValue, CrowdDynamicsException
 from .structures import is_model, model_of, as_obstacles, MODEL_THREE_CIRCLE
 
 try:  # pragma: no cover - reference package not installable here
@@ -118,35 +120,61 @@ class _Params:
 
 
 class DeviceState:
-    """GPU mirror of ``simulation.agents.array`` shared by all nodes of one simulation."""
+    """GPU mirror of ``simulation.agents.array`` shared by all nodes of one simulation.
 
-    def __init__(self, simulation, mode='strict', device=0):
-        assert mode in ('strict', 'resident')
+    Field-granular bookkeeping (masks of ``_lib.F_*`` bits over the mutable fields):
+
+    * ``host_dirty`` -- fields the HOST changed since the device last saw them.  The first node uploads the whole array
+      (constants included; they then stay on the device, keyed on the identity of the host array); afterwards ``begin()``
+      uploads only ``host_dirty``.  Host-side nodes declare their writes with ``mark_dirty(mask)`` (see ``HostNode``);
+      ``upload='always'`` restores the conservative behaviour (whole array before every node) for trees that mix in host
+      code which does not declare anything.
+    * ``dev_ahead`` -- fields the DEVICE changed that the host array has not received yet.  Strict mode downloads what a
+      node wrote right away (``end(mask)``), resident mode accumulates it until ``sync_host()``.
+    """
+
+    def __init__(self, simulation, mode='strict', device=0, upload='dirty'):
+        assert mode in ('strict', 'resident') and upload in ('dirty', 'always')
         self.simulation = simulation
         self.mode = mode
+        self.upload_policy = upload
         self.device = device
         self.dev = None
         self._host_id = None
         self._obstacles_key = None
         self._nav_key = None
-        self.dirty_host = False     # device is ahead of the host array (resident mode)
-        self.dirty_states = False   # ... and of its States fields target / is_follower / index_leader
+        self.host_dirty = 0
+        self.dev_ahead = 0
+        self.dirty_states = False   # device is ahead of the States fields target / is_follower / index_leader
         self.dirty_active = False   # ... and of States.active
         self._active_id = None
         self._states_id = None
+        self._registered = None
+
+    @property
+    def dirty_host(self):
+        """device is ahead of the host array (some mutable field has not been downloaded yet)"""
+        return bool(self.dev_ahead)
+
+    @dirty_host.setter
+    def dirty_host(self, value):
+        self.dev_ahead = _lib.F_ALL_MUTABLE if value else 0
 
     @classmethod
-    def of(cls, simulation, mode=None, device=0):
+    def of(cls, simulation, mode=None, device=0, upload=None):
         st = getattr(simulation, '_b200_state', None)
         if st is None:
-            st = cls(simulation, mode or 'strict', device)
+            st = cls(simulation, mode or 'strict', device, upload or 'dirty')
             try:
                 simulation._b200_state = st
             except Exception:  # traitlets HasTraits accept new attributes; be defensive anyway
                 object.__setattr__(simulation, '_b200_state', st)
-        elif mode is not None and mode != st.mode:
-            st.sync_host()
-            st.mode = mode
+        else:
+            if mode is not None and mode != st.mode:
+                st.sync_host()
+                st.mode = mode
+            if upload is not None:
+                st.upload_policy = upload
         return st
 
     @property
@@ -158,23 +186,45 @@ class DeviceState:
         model = model_of(agents)      # raises InvalidType for an unknown dtype, like interactions.py:204-205
         if self.dev is None or self.dev.model != model:
             self.dev = DeviceAgents(model, capacity=len(agents), device=self.device)
+            # nothing the old device held is on the new one: walls, fields, seed, States, flags are all sent again
             self._host_id = None
+            self._obstacles_key = None
+            self._nav_key = None
+            self._states_id = None
+            self._active_id = None
+            self._registered = None
+            self._seed = None
+            self.host_dirty = 0
+            self.dev_ahead = 0
+            self.dirty_states = self.dirty_active = False
         return agents
 
     def begin(self):
         """Make the device state current before a node runs."""
         agents = self._ensure()
-        if self.mode == 'strict' or self._host_id != (id(agents), len(agents)):
+        key = (id(agents), len(agents))
+        if self._host_id != key or (self.mode == 'strict' and self.upload_policy == 'always'):
             self.dev.upload(agents)
-            self._host_id = (id(agents), len(agents))
-            self.dirty_host = False
+            if self._host_id != key and self.upload_policy == 'dirty' and len(agents) and hasattr(self.dev, 'host_register'):
+                # pinned + mapped: field-masked transfers then run as zero-copy kernels over PCIe
+                try:
+                    self.dev.host_register(agents)
+                    self._registered = key
+                except CrowdDynamicsException:
+                    self._registered = None      # e.g. memory that cannot be pinned: the bounce-buffer path still works
+            self._host_id = key
+            self.host_dirty = 0
+            self.dev_ahead = 0
+        elif self.host_dirty:
+            self.dev.upload_fields(agents, self.host_dirty)
+            self.host_dirty = 0
         return self.dev
 
     def begin_states(self):
         """``begin()`` for the collective-motion nodes, which also read the States fields (agents.py:33-60)."""
         dev = self.begin()
         agents = self.agents
-        if self.mode == 'strict' or self._states_id != self._host_id:
+        if (self.mode == 'strict' and self.upload_policy == 'always') or self._states_id != self._host_id:
             dev.set_states(agents, target=False)      # target travels with the records
             self._states_id = self._host_id
         return dev
@@ -187,14 +237,15 @@ class DeviceState:
             if states:
                 self.dev.get_states(self.agents)
         else:
-            self.dirty_host = self.dirty_host or bool(mask)
+            self.dev_ahead |= int(mask)
             self.dirty_states = self.dirty_states or states
 
     def sync_host(self, mask=_lib.F_ALL_MUTABLE):
         """Resident mode: refresh the host array from the device (before host-side nodes / IO read it)."""
-        if self.dev is not None and self.dirty_host:
-            self.dev.download(self.agents, mask)
-            self.dirty_host = False
+        pending = self.dev_ahead & int(mask)
+        if self.dev is not None and pending:
+            self.dev.download(self.agents, pending)
+            self.dev_ahead &= ~pending
         if self.dev is not None and self.dirty_states:
             self.dev.get_states(self.agents)
             self.dirty_states = False
@@ -202,12 +253,29 @@ class DeviceState:
             self.agents['active'] = self.dev.get_active()
             self.dirty_active = False
 
-    def invalidate(self):
-        """Resident mode: the host array was modified by a host-side node; re-upload at the next node."""
-        self.sync_host()
+    def mark_dirty(self, mask=_lib.F_ALL_MUTABLE):
+        """A host-side node wrote the mutable fields in ``mask`` of the host array: the next GPU node uploads them (and only
+        them).  The host's values win over device-side changes of the same fields that were never downloaded."""
+        mask = int(mask) & _lib.F_ALL_MUTABLE
+        self.host_dirty |= mask
+        self.dev_ahead &= ~mask
+
+    def invalidate(self, mask=None):
+        """The host array was modified by host code.  ``mask``: the mutable fields that were edited (same as
+        ``mark_dirty``); ``None``: anything may have changed, constants and States fields included -- the whole array is
+        uploaded again at the next node.  That discards whatever the device has not published yet, so it is refused while the
+        device is ahead: call ``sync_host()`` BEFORE editing the array (downloading now would overwrite the edits)."""
+        if mask is not None:
+            return self.mark_dirty(mask)
+        if self.dev_ahead or self.dirty_states or self.dirty_active:
+            raise CrowdDynamicsException(
+                'invalidate(): the device holds results that were never downloaded (fields 0x%x%s%s); call sync_host() '
+                'before editing the host array, or pass the mask of the edited fields'
+                % (self.dev_ahead, ', States' if self.dirty_states else '', ', active' if self.dirty_active else ''))
         self._host_id = None
         self._states_id = None
         self._active_id = None
+        self.host_dirty = 0
 
     # -- geometry / fields -------------------------------------------------------------------------------------------
     def ensure_obstacles(self):
@@ -247,16 +315,37 @@ class LogicNode(_Base, _Params):
     def __init__(self, simulation, *args, **kwargs):
         mode = kwargs.pop('mode', None)
         device = kwargs.pop('device', 0)
+        upload = kwargs.pop('upload', None)
         self._init_params(kwargs)
         if _HAVE_REFERENCE:
             super().__init__(simulation, *args, **kwargs)
         else:
             super().__init__(*args, **kwargs)
             self.simulation = simulation
-        self.state = DeviceState.of(simulation, mode, device)
+        self.state = DeviceState.of(simulation, mode, device, upload)
 
     def update(self):
         raise NotImplementedError
+
+
+class HostNode(LogicNode):
+    """Wraps a host-side node of the reference (anything with ``update()``) in a tree of GPU nodes: the host array is made
+    current before it runs (``reads``: the mutable fields it looks at; resident mode only downloads those that are pending)
+    and the fields it ``writes`` are sent to the device before the next GPU node -- the "upload dirty fields" half of strict
+    mode.  Example: ``HostNode(sim, node=reference_fluctuation, reads=0, writes=F_FORCE | F_TORQUE)``."""
+    _params = dict(node=None, reads=_lib.F_ALL_MUTABLE, writes=0, name=None)
+
+    def __init__(self, simulation, *args, **kwargs):
+        super().__init__(simulation, *args, **kwargs)
+        if self.node is None or not hasattr(self.node, 'update'):
+            raise InvalidValue('HostNode needs node=<object with update()>')
+
+    def update(self):
+        if self.reads:
+            self.state.sync_host(self.reads)
+        self.node.update()
+        if self.writes:
+            self.state.mark_dirty(self.writes)
 
 
 class Reset(LogicNode):
@@ -424,7 +513,7 @@ class InsideDomain(LogicNode):
             dev.set_polygons(_lib.POLY_DOMAIN, [self._vertices])
             self._sent_to = dev
         agents = self.state.agents
-        if self.state.mode == 'strict' or self.state._active_id != self.state._host_id:
+        if (self.state.mode == 'strict' and self.state.upload_policy == 'always') or self.state._active_id != self.state._host_id:
             dev.set_active(agents['active'])
             self.state._active_id = self.state._host_id
         self.simulation.data['inactive'] += dev.inside_domain()
@@ -498,7 +587,7 @@ class FusedStep(LogicNode):
                 dev.set_seed(self.seed)
                 self.state._seed = self.seed
         dts = dev.step(self.steps_per_update, flags, self.cell_size, self.dt_min, self.dt_max)
-        self.state.dirty_host = True
+        self.state.dev_ahead |= _lib.F_ALL_MUTABLE
         if len(dts):
             self.simulation.data['dt'] = float(dts[-1])
             self.simulation.data['time_tot'] += float(dts.sum())

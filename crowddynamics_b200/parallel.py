@@ -116,6 +116,9 @@ class CudaStripDevice:
     def profile_read(self):
         return self.dev.profile_read()
 
+    def profile_read_phases(self):
+        return self.dev.profile_read_phases()
+
     def launch_count(self):
         return self.dev.launch_count()
 

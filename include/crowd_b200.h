@@ -92,6 +92,19 @@ int64_t cdb_num_agents(const cdb_sim *sim);
  * (in the original agent order, whatever the device-side cell ordering is). */
 int cdb_upload_agents_aos(cdb_sim *sim, const void *agents, int64_t n, int64_t itemsize);
 int cdb_download_agents_aos(cdb_sim *sim, void *agents, int64_t n, int64_t itemsize, uint32_t field_mask);
+/* Field-granular traffic for the strict mode of the nodes ("upload dirty fields -> kernel -> download written fields"):
+ *   cdb_host_register      pins + maps the host array (simulation.agents.array is ordinary pageable numpy memory) so that
+ *                          kernels can read / write the selected fields of the packed records in place, over PCIe;
+ *   cdb_upload_agents_fields  refreshes only the fields in field_mask of the n agents uploaded before (same array order),
+ *                          wherever the fused steps have moved them on the device since;
+ *   cdb_download_agents_aos   without CDB_F_WHOLE_RECORD writes only the fields in field_mask into the caller's records.
+ * Masks of at most 120 B per agent travel by zero-copy kernels (time proportional to the bytes selected), larger ones by one
+ * DMA of the whole records (55 GB/s); pageable, unregistered memory falls back to a pinned bounce buffer + host merge.
+ * cdb_transfer_stats reports the bytes these entry points moved over PCIe. */
+int cdb_host_register(cdb_sim *sim, void *agents, int64_t n, int64_t itemsize);
+int cdb_host_unregister(cdb_sim *sim, void *agents);
+int cdb_upload_agents_fields(cdb_sim *sim, const void *agents, int64_t n, int64_t itemsize, uint32_t field_mask);
+int cdb_transfer_stats(cdb_sim *sim, int64_t *h2d_bytes, int64_t *d2h_bytes, int reset);
 
 /* obstacles: (W, 4) doubles p0x,p0y,p1x,p1y == obstacle_type_linear (core/structures.py:6-9), the output format of
  * geom_to_linear_obstacles (core/geometry.py:99-102) that AgentObstacleInteractions.update builds (logic.py:122-130). */

@@ -22,6 +22,12 @@ class Recorder:
         self.n = len(agents)
         self._rec('upload')
 
+    def upload_fields(self, agents, mask):
+        self._rec('upload_fields', mask)
+
+    def host_register(self, agents):
+        self._rec('host_register')
+
     def download(self, agents, mask=_lib.F_ALL_MUTABLE):
         self._rec('download', mask)
 
@@ -50,6 +56,10 @@ class Recorder:
         self._rec('integrate')
         return dt_max
 
+    def step(self, n_steps, flags, cell_size, dt_min, dt_max, want_dt=True):
+        self._rec('step', n_steps)
+        return np.full(n_steps, dt_max)
+
     def __getattr__(self, name):            # every other node entry point: just record it
         if name.startswith('_'):
             raise AttributeError(name)
@@ -66,11 +76,11 @@ def recorder(monkeypatch):
     return Recorder
 
 
-def _sim(mode):
+def _sim(mode, upload=None):
     agents, obstacles, doors, side = S.leader_follower_crowd(50, 'circular', seed=1)
     domain = np.array([(0, 0), (side, 0), (side, side), (0, side)])
     sim = L.MultiAgentSimulation(agents, obstacles, (), domain=domain)
-    sim.logic = L.Reset(sim, mode=mode) << (
+    sim.logic = L.Reset(sim, mode=mode, upload=upload) << (
         L.InsideDomain(sim), L.TargetReached(sim, polygons=[domain, None, domain * 0.5]),
         L.Integrator(sim) << (L.Adjusting(sim) << (L.ExitDetection(sim, center_door=doors) << L.LeaderFollowerWithHerding(sim)),
                               L.AgentAgentInteractions(sim)))
@@ -78,7 +88,7 @@ def _sim(mode):
 
 
 def test_strict_mode_moves_exactly_what_each_node_touches(recorder):
-    sim = _sim('strict')
+    sim = _sim('strict', upload='always')
     assert sim.data['inactive'] == 0 and sim.data['target_0'] == 0 and sim.data['target_2'] == 0 and 'target_1' not in sim.data
     sim.update()
     dev, = recorder.instances
@@ -104,6 +114,83 @@ def test_strict_mode_moves_exactly_what_each_node_touches(recorder):
     assert sim.data['inactive'] == 6 and sim.data['iterations'] == 2
 
 
+def test_strict_mode_uploads_only_dirty_fields(recorder):
+    """strict = upload dirty fields -> kernel -> download written fields.  The first node sends the whole array
+    (constants stay on the device afterwards, keyed on the array identity), the following ones nothing -- until a host-side
+    node declares what it wrote."""
+    sim = _sim('strict')
+    sim.update()
+    dev, = recorder.instances
+    names = dev.names()
+    assert names.count('upload') == 1 and names.count('host_register') == 1 and 'upload_fields' not in names
+    assert names.count('set_states') == 1 and names.count('set_active') == 1
+    # every node still publishes exactly what it wrote
+    assert ('download', _lib.F_FORCE | _lib.F_TORQUE) in dev.calls and names.count('download') >= 4
+    st = sim.logic.state
+    assert st.host_dirty == 0 and st.dev_ahead == 0
+    # a host-side node (here: a stand-in for the reference's Fluctuation) writes force: only force travels up
+    class HostFluctuation:
+        def update(self_inner):
+            sim.agents.array['force'] += 1.0
+    sim.logic['Adjusting'].inject_after(L.HostNode(sim, node=HostFluctuation(), reads=0, writes=_lib.F_FORCE))
+    n0 = len(dev.calls)
+    sim.update()
+    new = dev.calls[n0:]
+    assert [c for c in new if c[0] == 'upload'] == [] and [c for c in new if c[0] == 'upload_fields'] == [('upload_fields', _lib.F_FORCE)]
+    # the array object was replaced: everything is sent again
+    sim.agents.array = sim.agents.array.copy()
+    n0 = len(dev.calls)
+    sim.update()
+    assert [c[0] for c in dev.calls[n0:]].count('upload') == 1
+
+
+def test_invalidate_never_overwrites_host_edits(recorder):
+    """invalidate() used to download first, which overwrote the very edits it was meant to publish."""
+    from crowddynamics_b200.exceptions import CrowdDynamicsException
+    sim = _sim('resident')
+    sim.update()
+    dev, = recorder.instances
+    st = sim.logic.state
+    assert st.dev_ahead and st.dirty_states and st.dirty_active
+    n0 = len(dev.calls)
+    with pytest.raises(CrowdDynamicsException):
+        st.invalidate()                      # the device is ahead: refusing beats silently losing either side
+    assert len(dev.calls) == n0              # ... and nothing was downloaded over the host array
+    # the supported ways: say what was edited (the rest of the pending fields is still fetched later) ...
+    st.invalidate(_lib.F_VELOCITY)
+    assert st.host_dirty == _lib.F_VELOCITY and not (st.dev_ahead & _lib.F_VELOCITY) and st.dev_ahead
+    st.sync_host()
+    assert ('download', st_mask_without(_lib.F_VELOCITY, dev)) in dev.calls
+    # ... or sync first, edit, then invalidate everything
+    st.invalidate()
+    sim.update()
+    assert dev.names().count('upload') == 2
+
+
+def st_mask_without(mask, dev):
+    last = [c for c in dev.calls if c[0] == 'download'][-1][1]
+    assert not (last & mask)
+    return last
+
+
+def test_a_new_device_gets_walls_fields_and_states_again(recorder):
+    """when the agent model changes a new DeviceAgents is created; the keys that say 'already sent' described the
+    old device and must be dropped with it."""
+    agents, obstacles, side = S.uniform_crowd(30, 'circular', density=1.0, seed=3)
+    fields = [S.direction_field(0.5, (0, 0, side, side), 'swirl')]
+    sim = L.MultiAgentSimulation(agents, obstacles, fields)
+    sim.logic = L.FusedStep(sim, seed=11, fluctuation=True)
+    sim.update()
+    first, = recorder.instances
+    assert {'set_obstacles', 'set_navigation_field', 'set_seed'} <= set(first.names())
+    three, _, _ = S.uniform_crowd(30, 'three_circle', density=1.0, seed=3)
+    sim.agents.array = three                 # another agent model: the state is rebuilt on a new device object
+    sim.update()
+    second = recorder.instances[-1]
+    assert second is not first
+    assert {'upload', 'set_obstacles', 'set_navigation_field', 'set_seed'} <= set(second.names())
+
+
 def test_resident_mode_uploads_once_and_syncs_on_demand(recorder):
     sim = _sim('resident')
     for _ in range(3):
@@ -120,7 +207,7 @@ def test_resident_mode_uploads_once_and_syncs_on_demand(recorder):
     assert not (st.dirty_host or st.dirty_states or st.dirty_active)
     st.sync_host()
     assert dev.names()[-3:] == ['download', 'get_states', 'get_active']  # nothing new to fetch
-    # a host-side node edited the array: everything is sent again at the next node
+    # a host-side node edited the array (after the sync above): everything is sent again at the next node
     st.invalidate()
     sim.update()
     names = dev.names()
