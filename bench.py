@@ -314,7 +314,13 @@ def main():
     value = agents_total * args.steps / (ms * 1e-3)
 
     # ---- end to end through the public boundary with HOST buffers (rank-local, aggregated like `value`) -------------
+    # `e2e`: the full round trip of simulation.agents.array -- H2D of the whole packed records, one step, D2H of the whole
+    # records.  PCIe-bound by construction: profiles/pcie_probe_r2.txt measures 55.6 / 52.6 GB/s for whole-record DMA and
+    # 18 - 26 GB/s for any strided subset of the 316-byte records, so moving only the 152 mutable bytes per direction is NOT
+    # faster than moving the record; what the field masks buy is shown by the other legs (`e2e_variants`), where the bytes a
+    # real node tree needs per update are a fraction of the record.
     e2e = None
+    e2e_variants = None
     if world == 1:
         e2e_steps = max(1, args.e2e_steps)
         for _ in range(1):    # warm-up
@@ -330,6 +336,44 @@ def main():
         e2e = {'value': n * e2e_steps / e2e_s, 'unit': 'agent-steps/s', 'h2d_bytes_per_step': n * itemsize,
                'd2h_bytes_per_step': n * itemsize, 'steps': e2e_steps,
                'path': 'cdb_upload_agents_aos -> cdb_step(1) -> cdb_download_agents_aos on a pinned host array'}
+
+        def leg(name, body, what):
+            body()                                       # warm-up
+            torch.cuda.synchronize()
+            dev.transfer_stats(reset=True)
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                body()
+            torch.cuda.synchronize()
+            secs = time.perf_counter() - t0
+            up, down = dev.transfer_stats()
+            return {'value': n * e2e_steps / secs, 'unit': 'agent-steps/s', 'h2d_bytes_per_step': up // e2e_steps,
+                    'd2h_bytes_per_step': down // e2e_steps, 'steps': e2e_steps, 'path': what}
+
+        F = _lib
+        observer = F.F_POSITION | F.F_VELOCITY | (F.F_ORIENTATION if args.model == 'three_circle' else 0)
+        force = F.F_FORCE | (F.F_TORQUE if args.model == 'three_circle' else 0)
+
+        def strict_fused():
+            step_fn(1); dev.download_raw(host.data_ptr(), n, F.F_ALL_MUTABLE)
+
+        def strict_fused_with_host_force_node():
+            dev.upload_fields_raw(host.data_ptr(), n, force); step_fn(1); dev.download_raw(host.data_ptr(), n, F.F_ALL_MUTABLE)
+
+        def resident_observer():
+            step_fn(1); dev.download_raw(host.data_ptr(), n, observer)
+
+        e2e_variants = {
+            'strict_fused_step': leg('strict', strict_fused,
+                                     'FusedStep in strict mode, steady state: nothing dirty on the host, one step, every '
+                                     'mutable field written back into the pinned host records (zero-copy kernel)'),
+            'strict_fused_step_host_force_node': leg('strict+host', strict_fused_with_host_force_node,
+                                                     'the same with a host-side node that writes force (/ torque) every '
+                                                     'update: only those fields are uploaded (cdb_upload_agents_fields)'),
+            'resident_with_observer': leg('observer', resident_observer,
+                                          'resident step + download of what an observer / SaveSimulationData-style node '
+                                          'reads (position, velocity, orientation)'),
+        }
 
     if rank != 0:
         if world > 1:
@@ -387,6 +431,7 @@ def main():
         'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic', 'config': workload_config(args, n, world),
         'gpu_launches': launches, 'clocks': clocks, 'roofline': roofline, 'roofline_fp64': fp64, 'e2e': e2e,
+        'e2e_variants': e2e_variants,
         'hbm_fraction_whole_step': value / world * ALGO_BYTES[args.model] / 1e9 / peak,
     }
     if world == 1 and not args.no_cpu_baseline:

@@ -60,6 +60,7 @@ def _signatures(L):
         'cdb_set_obstacles': (i32, [vp, vp, i64]),
         'cdb_set_navigation_field': (i32, [vp, i64, vp, vp, i64, i64, f64, f64, f64]),
         'cdb_clear_navigation': (i32, [vp]),
+        'cdb_build_navigation_field': (i32, [vp, i64, vp, i64, vp, i64, i64, i64, f64, f64, f64, f64, f64, vp, vp, vp, pi64]),
         'cdb_reset': (i32, [vp]),
         'cdb_set_seed': (i32, [vp, C.c_uint64]),
         'cdb_fluctuation': (i32, [vp]),

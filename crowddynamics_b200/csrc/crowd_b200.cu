@@ -24,6 +24,7 @@
 #include "step_kernel.cuh"
 #include "finish_kernel.cuh"
 #include "transfer_kernels.cuh"
+#include "field_kernels.cuh"
 #include "strip_kernels.cuh"
 #include "collective_kernels.cuh"
 
@@ -993,6 +994,114 @@ int cdb_set_navigation_field(cdb_sim *sim, int64_t target, const double *U, cons
         CK(cudaMemcpy(dV, V, ny * nx * sizeof(double), cudaMemcpyHostToDevice));
     }
     f.U = dU; f.V = dV; f.ny = ny; f.nx = nx; f.minx = minx; f.miny = miny; f.step = step; f.valid = 1;
+    sim->n_nav = (int)sim->nav.size();
+    CK(cudaMemcpy(sim->d_nav, sim->nav.data(), sim->nav.size() * sizeof(NavField), cudaMemcpyHostToDevice));
+    return CDB_OK;
+}
+
+// ---- navigation-field construction (field_kernels.cuh) -------------------------------------------------------------------
+namespace {
+struct FieldScratch {
+    uint8_t *target = nullptr, *obst = nullptr, *mask = nullptr, *state = nullptr, *dirmask = nullptr, *act[2] = {nullptr, nullptr};
+    double *Tt = nullptr, *To = nullptr, *U = nullptr, *V = nullptr, *seg_t = nullptr, *seg_o = nullptr;
+    unsigned *changed = nullptr;
+    ~FieldScratch() {
+        cudaFree(target); cudaFree(obst); cudaFree(mask); cudaFree(state); cudaFree(dirmask); cudaFree(act[0]); cudaFree(act[1]);
+        cudaFree(Tt); cudaFree(To); cudaFree(U); cudaFree(V); cudaFree(seg_t); cudaFree(seg_o); cudaFree(changed);
+    }
+};
+
+// iterate the upwind update to its fixed point; *rounds_out = rounds launched
+int eikonal_solve(cdb_sim *sim, FieldScratch &f, double *T, const uint8_t *raster, const uint8_t *mask, int ny, int nx, double h, int *rounds_out) {
+    cudaStream_t st = sim->stream;
+    const int tiles_x = cdiv(nx, ET), tiles_y = cdiv(ny, ET);
+    const long long cells = (long long)ny * nx;
+    CK(cudaMemsetAsync(f.act[0], 0, (size_t)tiles_x * tiles_y, st));
+    LAUNCH(sim, k_eik_init, cdiv(cells, 256), 256, 0, raster, mask, ny, nx, h, T, f.state, f.act[0], tiles_x, tiles_y);
+    const int max_rounds = 64 * (tiles_x + tiles_y) + 1024;
+    unsigned h_changed = 1;
+    int r = 0, cur = 0;
+    CK(cudaMemsetAsync(f.changed, 0, sizeof(unsigned), st));
+    for (; r < max_rounds; ++r) {
+        CK(cudaMemsetAsync(f.act[cur ^ 1], 0, (size_t)tiles_x * tiles_y, st));
+        LAUNCH(sim, k_eik_fim, dim3(tiles_x, tiles_y), dim3(ET, ET), 0, T, f.state, ny, nx, h, f.act[cur], f.act[cur ^ 1], tiles_x, tiles_y, f.changed);
+        cur ^= 1;
+        if ((r & 15) == 15) {
+            CK(cudaMemcpyAsync(&h_changed, f.changed, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            if (h_changed == 0) { ++r; break; }
+            CK(cudaMemsetAsync(f.changed, 0, sizeof(unsigned), st));
+        }
+    }
+    CK(cudaGetLastError());
+    if (h_changed != 0) return fail(CDB_ERR_STATE, "eikonal solver did not converge in %d rounds", max_rounds);
+    LAUNCH(sim, k_eik_sign, cdiv(cells, 256), 256, 0, T, raster, f.state, cells);
+    if (rounds_out) *rounds_out = r;
+    return CDB_OK;
+}
+}  // namespace
+
+int cdb_build_navigation_field(cdb_sim *sim, int64_t target, const double *target_segments, int64_t n_target_segments,
+                               const double *obstacle_segments, int64_t n_obstacle_segments, int64_t ny, int64_t nx, double minx,
+                               double miny, double step, double radius, double strength, double *distance_map_out, double *U_out,
+                               double *V_out, int64_t *rounds_out) {
+    if (!sim) return fail(CDB_ERR_INVALID_VALUE, "sim is NULL");
+    if (target < 0 || target >= MAX_NAV_TARGETS) return fail(CDB_ERR_INVALID_VALUE, "target index %lld out of range [0, %d)", (long long)target, MAX_NAV_TARGETS);
+    if (ny <= 0 || nx <= 0 || (double)ny * (double)nx > 2.0e9 || !(step > 0.0)) return fail(CDB_ERR_INVALID_VALUE, "bad grid");
+    if (n_target_segments <= 0 || !target_segments) return fail(CDB_ERR_INVALID_VALUE, "a navigation field needs target geometry");
+    if (n_obstacle_segments < 0 || (n_obstacle_segments > 0 && !obstacle_segments)) return fail(CDB_ERR_INVALID_VALUE, "bad obstacle buffer");
+    CK(cudaSetDevice(sim->device));
+    sim->state_version++;
+    cudaStream_t st = sim->stream;
+    CK(cudaStreamSynchronize(st));
+    const long long cells = (long long)ny * nx;
+    const int tiles = cdiv(nx, ET) * cdiv(ny, ET);
+    const bool walls = n_obstacle_segments > 0;
+    FieldScratch f;
+    CKS(dev_alloc(&f.target, (size_t)cells)); CKS(dev_alloc(&f.state, (size_t)cells)); CKS(dev_alloc(&f.dirmask, (size_t)cells));
+    CKS(dev_alloc(&f.act[0], (size_t)tiles)); CKS(dev_alloc(&f.act[1], (size_t)tiles)); CKS(dev_alloc(&f.changed, 1));
+    CKS(dev_alloc(&f.Tt, (size_t)cells)); CKS(dev_alloc(&f.U, (size_t)cells)); CKS(dev_alloc(&f.V, (size_t)cells));
+    CKS(dev_alloc(&f.seg_t, (size_t)n_target_segments * 4));
+    CK(cudaMemcpyAsync(f.seg_t, target_segments, n_target_segments * 4 * sizeof(double), cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(f.target, 0, (size_t)cells, st));
+    LAUNCH(sim, k_raster_lines, cdiv(n_target_segments, 64), 64, 0, f.seg_t, (int)n_target_segments, minx, miny, step, (int)ny, (int)nx, f.target);
+    if (walls) {
+        CKS(dev_alloc(&f.obst, (size_t)cells)); CKS(dev_alloc(&f.mask, (size_t)cells)); CKS(dev_alloc(&f.To, (size_t)cells));
+        CKS(dev_alloc(&f.seg_o, (size_t)n_obstacle_segments * 4));
+        CK(cudaMemcpyAsync(f.seg_o, obstacle_segments, n_obstacle_segments * 4 * sizeof(double), cudaMemcpyHostToDevice, st));
+        CK(cudaMemsetAsync(f.obst, 0, (size_t)cells, st));
+        LAUNCH(sim, k_raster_lines, cdiv(n_obstacle_segments, 64), 64, 0, f.seg_o, (int)n_obstacle_segments, minx, miny, step, (int)ny, (int)nx, f.obst);
+        LAUNCH(sim, k_buffer_mask, cdiv(cells, 256), 256, 0, f.seg_o, (int)n_obstacle_segments, radius, minx, miny, step, (int)ny, (int)nx, f.mask);
+    }
+    // shortest_path: distance to the targets around the buffered obstacles, its normalised gradient, buffer zone filled
+    int rounds_t = 0, rounds_o = 0;
+    CKS(eikonal_solve(sim, f, f.Tt, f.target, f.mask, (int)ny, (int)nx, step, &rounds_t));
+    LAUNCH(sim, k_direction_map, cdiv(cells, 256), 256, 0, f.Tt, f.mask, (int)ny, (int)nx, f.U, f.V, f.dirmask);
+    double *dU = nullptr, *dV = nullptr;          // the installed maps (owned by the sim afterwards)
+    CKS(dev_alloc(&dU, (size_t)cells));
+    if (dev_alloc(&dV, (size_t)cells) != CDB_OK) { cudaFree(dU); return CDB_ERR_CUDA; }
+    if (walls) {
+        const int reach = (int)std::ceil(radius / step) + 3;
+        LAUNCH(sim, k_fill_missing, cdiv(cells, 256), 256, 0, f.dirmask, f.obst, (int)ny, (int)nx, reach, f.U, f.V, dU, dV);
+        // obstacle_handling: distance from the walls (no mask), blend within `radius`, normalise
+        CKS(eikonal_solve(sim, f, f.To, f.obst, nullptr, (int)ny, (int)nx, step, &rounds_o));
+        LAUNCH(sim, k_obstacle_handling, cdiv(cells, 256), 256, 0, f.To, (int)ny, (int)nx, radius, strength, dU, dV);
+    } else {
+        CK(cudaMemcpyAsync(dU, f.U, cells * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        CK(cudaMemcpyAsync(dV, f.V, cells * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    }
+    CK(cudaGetLastError());
+    if (distance_map_out) CK(cudaMemcpyAsync(distance_map_out, f.Tt, cells * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (U_out) CK(cudaMemcpyAsync(U_out, dU, cells * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (V_out) CK(cudaMemcpyAsync(V_out, dV, cells * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (rounds_out) *rounds_out = rounds_t + rounds_o;
+    // install as the navigation field of `target` (what cdb_set_navigation_field does with host maps)
+    if ((int64_t)sim->nav.size() <= target) sim->nav.resize(target + 1, NavField{});
+    NavField &nf = sim->nav[target];
+    cudaFree((void *)nf.U); cudaFree((void *)nf.V);
+    nf = NavField{};
+    nf.U = dU; nf.V = dV; nf.ny = ny; nf.nx = nx; nf.minx = minx; nf.miny = miny; nf.step = step; nf.valid = 1;
     sim->n_nav = (int)sim->nav.size();
     CK(cudaMemcpy(sim->d_nav, sim->nav.data(), sim->nav.size() * sizeof(NavField), cudaMemcpyHostToDevice));
     return CDB_OK;

@@ -104,6 +104,31 @@ class DeviceAgents:
         seg = as_obstacles(obstacles)
         _lib.check(self.lib.cdb_set_obstacles(self.handle, _ptr(seg) if len(seg) else None, len(seg)))
 
+    def build_navigation_field(self, target, target_segments, obstacle_segments, bounds, step, radius=0.5, strength=0.3,
+                               want_maps=False):
+        """Field.navigation_to_target (reference simulation/field.py:155-164) computed on the device from line-segment
+        geometry and installed as the navigation field of ``target``: eikonal distance map around the obstacles buffered by
+        ``radius``, normalised gradient, fill of the buffer zone, blend away from the walls (``strength``).
+        ``bounds`` = (minx, miny, maxx, maxy) of the domain, ``step`` the grid spacing (quickest_path.meshgrid).
+        -> mgrid, or (mgrid, distance_map, (U, V)) as the reference returns when ``want_maps`` (host copies; a 2000 m room at
+        step 0.1 is 3 x 3.2 GB -- leave it off and nothing of that size ever exists on the host)."""
+        from .synthetic import MeshGrid
+        mg = MeshGrid(float(step), *[float(b) for b in bounds])
+        ny, nx = mg.shape
+        tseg = np.ascontiguousarray(np.asarray(target_segments, dtype=np.float64).reshape(-1, 4))
+        oseg = as_obstacles(obstacle_segments) if obstacle_segments is not None else np.zeros((0, 4))
+        oseg = np.ascontiguousarray(oseg, dtype=np.float64)
+        dmap = np.empty((ny, nx)) if want_maps else None
+        U = np.empty((ny, nx)) if want_maps else None
+        V = np.empty((ny, nx)) if want_maps else None
+        rounds = C.c_int64()
+        _lib.check(self.lib.cdb_build_navigation_field(
+            self.handle, int(target), _ptr(tseg), len(tseg), _ptr(oseg) if len(oseg) else None, len(oseg), ny, nx, float(bounds[0]),
+            float(bounds[1]), float(step), float(radius), float(strength), _ptr(dmap) if want_maps else None,
+            _ptr(U) if want_maps else None, _ptr(V) if want_maps else None, C.byref(rounds)))
+        self.last_field_rounds = rounds.value
+        return (mg, dmap, (U, V)) if want_maps else mg
+
     def set_navigation_field(self, target, mgrid, direction_map):
         """(mgrid, (U, V)) as returned by Field.navigation_to_target (reference field.py:155-164)."""
         U = np.ascontiguousarray(np.asarray(direction_map[0]), dtype=np.float64)

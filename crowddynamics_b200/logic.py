@@ -300,9 +300,16 @@ class DeviceState:
         key = (id(field), n_targets, step, radius, strength)
         if key != self._nav_key:
             self.dev.clear_navigation()
+            geometry = getattr(field, 'navigation_geometry', None)
             for target in range(n_targets):
-                mgrid, distance_map, direction_map = field.navigation_to_target(target, step, radius, strength)
-                self.dev.set_navigation_field(target, mgrid, direction_map)
+                if geometry is not None:
+                    # line-segment geometry: the field is BUILT on the device (eikonal solver + gradient + wall blend,
+                    # csrc/field_kernels.cuh) -- what Field.navigation_to_target does on the host with skfmm (field.py:155-164)
+                    tseg, oseg, bounds = geometry(target)
+                    self.dev.build_navigation_field(target, tseg, oseg, bounds, step, radius, strength)
+                else:
+                    mgrid, distance_map, direction_map = field.navigation_to_target(target, step, radius, strength)
+                    self.dev.set_navigation_field(target, mgrid, direction_map)
             self._nav_key = key
 
 
@@ -617,9 +624,22 @@ class MultiAgentSimulation:
             mgrid, direction_map = self._fields[target]
             return mgrid, None, direction_map
 
-    def __init__(self, agents, obstacles=None, fields=(), logic=None, domain=None):
+    class GeometryField:
+        """Field given as geometry, like the reference's ``Field`` (simulation/field.py): obstacle segments, one list of
+        target line segments per target (doors), the bounds of the domain.  The navigation fields are built on the device."""
+
+        def __init__(self, obstacles, targets, bounds, domain=None):
+            self.obstacles = obstacles
+            self.targets = [np.asarray(t, dtype=np.float64).reshape(-1, 4) for t in targets]
+            self.bounds = tuple(float(b) for b in bounds)
+            self.domain = domain
+
+        def navigation_geometry(self, target):
+            return self.targets[target], self.obstacles, self.bounds
+
+    def __init__(self, agents, obstacles=None, fields=(), logic=None, domain=None, field=None):
         self.agents = self._Agents(agents)
-        self.field = self.ArrayField(obstacles, fields, domain)
+        self.field = field if field is not None else self.ArrayField(obstacles, fields, domain)
         self.logic = logic
         self.data = {'iterations': 0, 'time_tot': 0.0, 'dt': 0.0}
 

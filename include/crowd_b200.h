@@ -115,6 +115,19 @@ int cdb_set_obstacles(cdb_sim *sim, const double *segments, int64_t n_segments);
 int cdb_set_navigation_field(cdb_sim *sim, int64_t target, const double *U, const double *V, int64_t ny, int64_t nx,
                              double minx, double miny, double step);
 int cdb_clear_navigation(cdb_sim *sim);
+/* Builds the navigation field of one target ON THE DEVICE and installs it like cdb_set_navigation_field -- what
+ * Field.navigation_to_target (simulation/field.py:155-164) computes on the host with skfmm / shapely / skimage:
+ * shortest_path (core/steering/quickest_path.py:184-197: eikonal distance to the target around the obstacles buffered by
+ * `radius`, distance_map :54-117; normalised gradient, direction_map :144-163; fill_missing :168-181), the distance /
+ * direction from the walls (core/steering/obstacle_handling.py:106+) and obstacle_handling (:15-74, `strength`).
+ * Geometry: target and obstacle line segments (p0x, p0y, p1x, p1y), rasterised like draw_geom does for LineStrings
+ * (core/geometry.py:105-116); grid of (ny, nx) points from (minx, miny) with spacing `step` (quickest_path.meshgrid :21-48).
+ * Optional host outputs (may be NULL): the signed target distance map (NaN inside the buffered obstacles) and (U, V), each
+ * (ny, nx) doubles; rounds_out = relaxation rounds of the eikonal solver.  Nothing of size (ny, nx) is needed on the host. */
+int cdb_build_navigation_field(cdb_sim *sim, int64_t target, const double *target_segments, int64_t n_target_segments,
+                               const double *obstacle_segments, int64_t n_obstacle_segments, int64_t ny, int64_t nx, double minx,
+                               double miny, double step, double radius, double strength, double *distance_map_out, double *U_out,
+                               double *V_out, int64_t *rounds_out);
 
 /* ---- per-node entry points (one per replaced LogicNode.update) ------------------------------------------------------ */
 int cdb_reset(cdb_sim *sim);                 /* Reset.update, logic.py:59-64 */

@@ -47,7 +47,7 @@ def test_masked_download_writes_only_the_selected_fields(model, registered):
         for name in agents.dtype.names:
             bit = FIELDS.get(name, 0)
             want = full[name] if bit & mask else (np.zeros_like(got[name]) if name == 'active' else agents[name])
-            assert (got[name] == want).all() | (np.isnan(got[name]).all() if got[name].dtype.kind == 'f' else False), (name, hex(mask))
+            assert (got[name] == want).all(), (name, hex(mask))
         nbytes = sum(agents.dtype[n].itemsize for n in agents.dtype.names if FIELDS.get(n, 0) & mask)
         if registered:
             assert up == 0 and down == nbytes * len(agents)          # exactly the selected bytes crossed PCIe
@@ -139,5 +139,5 @@ def test_strict_dirty_tree_equals_strict_always_tree(model):
     up_d, down_d = out['dirty'][1][-1]
     up_a, down_a = out['always'][1][-1]
     assert up_d == 16 * n                        # steady state: only the kicked force goes up ...
-    assert up_a >= 7 * item * n                  # ... where 'always' re-sends the whole array per node
+    assert up_a >= 5 * item * n                  # ... where 'always' re-sends the whole array per GPU node
     assert down_d < down_a
