@@ -222,6 +222,9 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-fp64-peak', action='store_true', help='skip the DFMA peak micro-benchmark (used under ncu)')
     ap.add_argument('--e2e-steps', type=int, default=3)
+    ap.add_argument('--field-step', type=float, default=0.0,
+                    help='room_exit: build the exit navigation field ON THE DEVICE from the wall / door geometry at this grid '
+                         'step (reference default 0.1) instead of uploading a synthetic host field')
     ap.add_argument('--refinement', type=int, default=0, help='search lattice: 0 automatic (cell_size / 2 where valid), 1 cell_size')
     ap.add_argument('--variant', type=int, default=3, help='agent-agent kernel variant (3 once-per-pair, 2 both-sides fused kernel)')
     args = ap.parse_args()
@@ -267,7 +270,20 @@ def main():
         dev.set_variant(args.variant)
         dev.set_search_refinement(args.refinement)
         dev.set_obstacles(obstacles)
-        dev.set_navigation_field(0, *field)
+        field_build = None
+        if args.workload == 'room_exit' and args.field_step > 0:
+            # Field.navigation_to_target on the device (cdb_build_navigation_field): nothing of grid size on the host
+            door = [(side + 5.0, side / 2 - 2.6, side + 5.0, side / 2 + 2.6)]
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            mg = dev.build_navigation_field(0, door, obstacles, (0.0, 0.0, side + 5.0, side), args.field_step, 0.5, 0.3)
+            torch.cuda.synchronize()
+            field_build = {'seconds': time.perf_counter() - t0, 'grid': list(mg.shape), 'cells': int(mg.shape[0] * mg.shape[1]),
+                           'step': args.field_step, 'relaxation_rounds': dev.last_field_rounds,
+                           'what': 'eikonal distance to the exit around the walls buffered by 0.5 m (fast iterative method), '
+                                   'normalised gradient, buffer fill, wall blend; two eikonal solves'}
+        else:
+            dev.set_navigation_field(0, *field)
         # pinned host image of simulation.agents.array (packed records), the e2e leg copies it every step
         host = torch.empty(n * itemsize, dtype=torch.uint8).pin_memory()
         host.numpy()[:] = agents.view(np.uint8).reshape(-1)
@@ -431,7 +447,7 @@ def main():
         'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic', 'config': workload_config(args, n, world),
         'gpu_launches': launches, 'clocks': clocks, 'roofline': roofline, 'roofline_fp64': fp64, 'e2e': e2e,
-        'e2e_variants': e2e_variants,
+        'e2e_variants': e2e_variants, 'field_build': field_build if world == 1 else None,
         'hbm_fraction_whole_step': value / world * ALGO_BYTES[args.model] / 1e9 / peak,
     }
     if world == 1 and not args.no_cpu_baseline:

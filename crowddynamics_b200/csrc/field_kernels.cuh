@@ -200,17 +200,21 @@ __global__ void k_direction_map(const double *__restrict__ dmap, const uint8_t *
     dirmask[g] = m ? 1 : 0;
 }
 
-// fill_missing (quickest_path.py:168-181): cells that are masked in the direction map but are not obstacle raster cells take
-// the value of the NEAREST boundary cell -- an unmasked cell with a masked 4-neighbour (skimage find_boundaries(mode='outer')
-// of the mask) -- by Euclidean distance between grid points (scipy NearestNDInterpolator).  Ties: the first candidate in
-// row-major order (scipy's kd-tree does not define one).  Search window: `reach` cells; none found => stays NaN.
+// fill_missing (quickest_path.py:168-181): cells that are masked in the direction map take the value of the NEAREST boundary
+// cell -- an unmasked cell with a masked 4-neighbour (skimage find_boundaries(mode='outer') of the mask) -- by Euclidean
+// distance between grid points (scipy NearestNDInterpolator).  Ties: the first candidate in row-major order (scipy's kd-tree
+// does not define one).  Search window: `reach` cells; none found => stays NaN.
+// The reference fills logical_xor(obstacle raster, mask), i.e. it leaves the cells ON the obstacle lines masked (undefined
+// data that obstacle_handling then reads); here they are filled like the rest of the buffer zone, so that an agent pushed
+// onto a wall line never samples an undefined direction.  Everywhere else the two rules select the same cells.
 __global__ void k_fill_missing(const uint8_t *__restrict__ dirmask, const uint8_t *__restrict__ obstacle, int ny, int nx, int reach,
                                const double *__restrict__ U, const double *__restrict__ V, double *__restrict__ Uo, double *__restrict__ Vo) {
     const long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (g >= (long long)ny * nx) return;
     const int x = (int)(g % nx), y = (int)(g / nx);
     Uo[g] = U[g]; Vo[g] = V[g];
-    if (!(dirmask[g] != 0) != !(obstacle[g] != 0)) {       // logical_xor(obstacle raster, direction-map mask)
+    (void)obstacle;
+    if (dirmask[g] != 0) {
         long long best = -1;
         long long bd = 0x7fffffffffffffffLL;
         for (int y2 = max(y - reach, 0); y2 <= min(y + reach, ny - 1); ++y2)

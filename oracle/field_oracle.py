@@ -148,8 +148,7 @@ def obstacle_handling(dmap_obs, dir_map_obs, dir_map_targets, radius, strength):
 
 
 def navigation_to_target(target_segments, obstacle_segments, bounds, step, radius, strength):
-    """field.py:155-164 for line-segment geometry -> (dmap_targets, (U, V)); dmap NaN inside the buffered obstacles, (U, V)
-    NaN inside the obstacle rasters."""
+    """field.py:155-164 for line-segment geometry -> (dmap_targets, (U, V)); dmap NaN inside the buffered obstacles."""
     minx, miny, maxx, maxy = bounds
     ny, nx = grid_shape(step, *bounds)
     target = raster_segments(target_segments, ny, nx, minx, miny, step)
@@ -163,7 +162,9 @@ def navigation_to_target(target_segments, obstacle_segments, bounds, step, radiu
     dirmask = np.ma.getmaskarray(U)
     Ud, Vd = np.where(dirmask, np.nan, U.data), np.where(dirmask, np.nan, V.data)
     obst = raster_segments(obstacle_segments, ny, nx, minx, miny, step).astype(bool)
-    Ud, Vd = fill_missing(np.logical_xor(obst, dirmask), dirmask, Ud, Vd)
+    # the reference fills logical_xor(obst, dirmask) and leaves the cells ON the obstacle lines masked (undefined data);
+    # they are filled here as well -- the one deliberate difference, see csrc/field_kernels.cuh k_fill_missing
+    Ud, Vd = fill_missing(dirmask, dirmask, Ud, Vd)
     dmap_obs = distance_map(obst.astype(np.uint8), None, step)
     dir_obs = direction_map(dmap_obs)
     return dmap, obstacle_handling(dmap_obs, dir_obs, (Ud, Vd), radius, strength)

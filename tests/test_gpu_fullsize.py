@@ -112,6 +112,41 @@ def test_window_against_oracle_1m(crowd):
             assert vec_rel_err(mine['torque'], ref['torque']) <= 1e-9
 
 
+def test_every_agent_against_oracle_1m(crowd):
+    """ALL 1 M agents: forces / torques after the force nodes of one step, and the state after the integrator, against the
+    serial C oracle on the whole crowd (~10 s of CPU; the headline workload of bench.py itself, not a window of it)."""
+    model, agents, obstacles, side = crowd
+    fields = [S.direction_field(1.0, (0.0, 0.0, side, side), 'exit', point=(side, side / 2))]
+    ref = agents.copy()
+    O.navigation(ref, fields); O.orientation(ref); O.adjusting(ref)
+    O.agent_agent_block_list(ref, CELL); O.agent_obstacle(ref, obstacles)
+    dev = DeviceAgents(_mid(model))
+    dev.upload(agents)
+    dev.set_obstacles(obstacles)
+    dev.set_navigation_field(0, *fields[0])
+    dev.step(1, _lib.STEP_ALL & ~(_lib.STEP_INTEGRATOR | _lib.STEP_RESET), CELL, 0.001, 0.01, want_dt=False)
+    got = agents.copy()
+    dev.download(got)
+    assert vec_rel_err(got['force'], ref['force']) <= 1e-9
+    assert (got['target_direction'] == ref['target_direction']).all()
+    if model == 'three_circle':
+        assert vec_rel_err(got['torque'], ref['torque']) <= 1e-9
+        assert (got['target_orientation'] == ref['target_orientation']).all() or \
+            np.abs(got['target_orientation'] - ref['target_orientation']).max() <= 1e-15
+    interacting = (np.abs(ref['force'] - agents['force']).sum(axis=1) > 0).mean()
+    assert interacting > 0.9                                   # the comparison is about real pair forces
+    dt = dev.step(1, _lib.STEP_INTEGRATOR | _lib.STEP_RESET, CELL, 0.001, 0.01)[0]
+    dt_ref = O.velocity_verlet_integrator(ref, 0.001, 0.01)
+    O.reset(ref)
+    dev.download(got)
+    dev.close()
+    assert abs(dt - dt_ref) <= 1e-15
+    assert np.abs(got['position'] - ref['position']).max() <= 1e-12 and np.abs(got['velocity'] - ref['velocity']).max() <= 1e-11
+    if model == 'three_circle':
+        assert np.abs(got['orientation'] - ref['orientation']).max() <= 1e-11
+        assert np.abs(got['position_ls'] - ref['position_ls']).max() <= 1e-11
+
+
 def test_relabelling_invariance_circular():
     """Shuffling the agent order leaves every agent's force unchanged up to summation order (circular pairs are exactly
     swap symmetric, so pair orientation does not matter)."""
