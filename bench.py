@@ -195,15 +195,58 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def strip_parity_check(model, rank, world, local_rank, dist):
+    """N > 1: before the timed run, every rank steps its strip of a small crowd over NCCL (halo + migrants + adaptive-dt
+    all-reduce); rank 0 gathers the agents and compares them with a single-device run of the same crowd.
+    -> {'status': 'ok' | 'mismatch', ...} on rank 0, None elsewhere.  The strips must reproduce the single device bit for bit
+    (same pairs, same arithmetic, same summation order)."""
+    import torch
+    from crowddynamics_b200 import _lib, synthetic as S
+    from crowddynamics_b200.engine import DeviceAgents
+    from crowddynamics_b200.parallel import StripSimulation
+    from crowddynamics_b200.structures import MODEL_CIRCULAR, MODEL_THREE_CIRCLE
+    steps, n = 12, 40000
+    agents, obstacles, side = S.uniform_crowd(n, model, density=1.0, seed=3, overlap_fraction=0.02)
+    agents['velocity'] *= 3.0                           # plenty of migrants across the strip borders
+    fields = [S.direction_field(0.5, (0, 0, side, side), 'swirl')]
+    sim = StripSimulation.from_global(agents, obstacles, fields, CELL, rank, world, device_index=local_rank, dist=dist,
+                                      dt_min=0.001, dt_max=0.01)
+    sim.step(steps)
+    torch.cuda.synchronize()
+    rec, ids = sim.export(agents.dtype)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (rec.view(np.uint8).reshape(len(rec), -1), ids))
+    if rank != 0:
+        return None
+    got = np.zeros_like(agents)
+    seen = np.zeros(len(agents), dtype=int)
+    for raw, i in gathered:
+        got[i] = np.ascontiguousarray(raw).view(agents.dtype).reshape(-1)
+        seen[i] += 1
+    dev = DeviceAgents(MODEL_CIRCULAR if model == 'circular' else MODEL_THREE_CIRCLE, device=local_rank)
+    dev.upload(agents); dev.set_obstacles(obstacles); dev.set_navigation_field(0, *fields[0])
+    dev.step(steps, _lib.STEP_ALL, CELL, 0.001, 0.01, want_dt=False)
+    ref = agents.copy(); dev.download(ref); dev.close()
+    err = float(np.abs(got['position'] - ref['position']).max())
+    migrated = int(sum(len(i) for _, i in gathered)) == n and bool((seen == 1).all())
+    ok = migrated and err == 0.0
+    return {'status': 'ok' if ok else 'mismatch', 'agents': n, 'steps': steps, 'ranks': world, 'every_agent_owned_once': migrated,
+            'max_abs_position_diff_vs_single_device': err, 'adaptive_dt': True}
+
+
 def workload_config(args, n_per_gpu, world):
     geom = ('a room with a door (11 wall segments)' if getattr(args, 'workload', 'room') == 'room_exit'
             else 'a walled square room, 4 wall segments')
-    return {'workload': 'synthetic %d %s agents per GPU, uniform %.3g agents/m^2 in %s, static exit direction field '
-                        '(step 1 m), cell 3.6 m, dt_min=dt_max=0.01' % (n_per_gpu, args.model, args.density, geom),
-            'agents_per_gpu': n_per_gpu, 'agent_model': args.model, 'density': args.density,
+    strong = world > 1 and getattr(args, 'scaling', 'weak') == 'strong'
+    per = n_per_gpu // world if strong else n_per_gpu
+    field = ('exit navigation field built on the device from the geometry (step %g m)' % args.field_step
+             if getattr(args, 'field_step', 0) > 0 and args.workload == 'room_exit' else 'static exit direction field (step 1 m)')
+    return {'workload': 'synthetic %d %s agents %s, uniform %.3g agents/m^2 in %s, %s, cell 3.6 m, dt_min=dt_max=0.01'
+                        % (n_per_gpu, args.model, 'in total (one room, %d strips)' % world if strong else 'per GPU', args.density, geom, field),
+            'agents_per_gpu': per, 'agents_total': per * world, 'agent_model': args.model, 'density': args.density,
             'parallelism': 'strips%d' % world if world > 1 else 'single',
             'l2_policy': 'inputs larger than L2 (%d MB of SoA state streamed per step)'
-                         % (n_per_gpu * (34 if args.model == 'three_circle' else 19) * 8 // 2 ** 20)}
+                         % (per * (36 if args.model == 'three_circle' else 20) * 8 // 2 ** 20)}
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -225,6 +268,12 @@ def main():
     ap.add_argument('--field-step', type=float, default=0.0,
                     help='room_exit: build the exit navigation field ON THE DEVICE from the wall / door geometry at this grid '
                          'step (reference default 0.1) instead of uploading a synthetic host field')
+    ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'],
+                    help='N > 1: weak = --agents per GPU (a row of rooms); strong = --agents in total, ONE room split into strips '
+                         '(BASELINE configs 4 / 5)')
+    ap.add_argument('--exchange', default='peer', choices=['peer', 'nccl'],
+                    help='N > 1: halo / migrant exchange by one-sided writes over NVLink peer memory (CUDA IPC; falls back to '
+                         'NCCL send/recv when IPC is unavailable) or by NCCL send/recv')
     ap.add_argument('--refinement', type=int, default=0, help='search lattice: 0 automatic (cell_size / 2 where valid), 1 cell_size')
     ap.add_argument('--variant', type=int, default=3, help='agent-agent kernel variant (3 once-per-pair, 2 both-sides fused kernel)')
     args = ap.parse_args()
@@ -252,9 +301,19 @@ def main():
     mid = MODEL_CIRCULAR if args.model == 'circular' else MODEL_THREE_CIRCLE
     itemsize = 228 if args.model == 'circular' else 316
 
+    strip_parity = None
     if world > 1:
         from crowddynamics_b200.parallel import StripSimulation
-        sim = StripSimulation.synthetic(args.model, n, args.density, rank, world, local_rank, seed=rank, dist=dist)
+        strip_parity = strip_parity_check(args.model, rank, world, local_rank, dist)
+        if args.scaling == 'strong':
+            from crowddynamics_b200.parallel import strong_scaling_strip
+            sim = strong_scaling_strip(args.model, n, args.density, rank, world, local_rank,
+                                       geometry='room_exit' if args.workload == 'room_exit' else 'room', dist=dist)
+        else:
+            sim = StripSimulation.synthetic(args.model, n, args.density, rank, world, local_rank, seed=rank, dist=dist)
+        exchange = 'nccl send/recv'
+        if args.exchange == 'peer' and sim.connect_direct():
+            exchange = 'one-sided writes over NVLink peer memory (CUDA IPC) + sequence flags'
         step_fn, dev = sim.step, sim.dev
         n_local = sim.n_owned
     else:
@@ -304,6 +363,8 @@ def main():
         sampler.start()
     step_fn(args.warmup)
     sync()
+    if world > 1:
+        sim.profile_phases(True)
     dev.profile(True)
     launches0 = dev.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -319,6 +380,7 @@ def main():
     ph = dev.profile_read_phases()       # pre + block list, pair sweep, pair evaluation, step kernel, post, steps
     prof = (ph[0], ph[1] + ph[2] + ph[3], ph[4], ph[5])
     dev.profile(False)
+    exchange_ms = sim.phase_ms() if world > 1 else None
     agents_total = n_local() if callable(n_local) else n_local
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device='cuda')
@@ -444,10 +506,11 @@ def main():
             fp64 = {'note': str(exc)}
     line = {
         'metric': 'agent-steps/sec', 'value': value, 'unit': 'agent-steps/s', 'n_gpus': world, 'steps': args.steps,
-        'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+        'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': args.scaling if world > 1 else 'weak',
         'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic', 'config': workload_config(args, n, world),
         'gpu_launches': launches, 'clocks': clocks, 'roofline': roofline, 'roofline_fp64': fp64, 'e2e': e2e,
-        'e2e_variants': e2e_variants, 'field_build': field_build if world == 1 else None,
+        'e2e_variants': e2e_variants, 'field_build': field_build if world == 1 else None, 'strip_parity': strip_parity,
+        'strip_phase_ms_rank0': exchange_ms, 'strip_exchange': exchange if world > 1 else None,
         'hbm_fraction_whole_step': value / world * ALGO_BYTES[args.model] / 1e9 / peak,
     }
     if world == 1 and not args.no_cpu_baseline:

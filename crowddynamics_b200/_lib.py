@@ -99,6 +99,14 @@ def _signatures(L):
         'cdb_strip_finish': (i32, [vp, u32, f64, f64, vp, vp, vp, vp]),
         'cdb_strip_absorb': (i32, [vp, vp, vp, pi64]),
         'cdb_strip_count': (i32, [vp, pi64]),
+        'cdb_strip_exchange_alloc': (i32, [vp]),
+        'cdb_strip_exchange_handle_bytes': (i64, []),
+        'cdb_strip_exchange_handles': (i32, [vp, vp]),
+        'cdb_strip_exchange_connect_ipc': (i32, [vp, vp, vp]),
+        'cdb_strip_exchange_connect_local': (i32, [vp, vp, vp]),
+        'cdb_strip_begin_direct': (i32, [vp, u32, f64, i32]),
+        'cdb_strip_finish_direct': (i32, [vp, u32, f64, f64, i32]),
+        'cdb_strip_absorb_direct': (i32, [vp, pi64]),
         'cdb_export_agents': (i32, [vp, vp, vp, i64, pi64]),
         'cdb_set_states': (i32, [vp, vp, vp, vp, vp, vp, i64]),
         'cdb_get_states': (i32, [vp, vp, vp, vp, i64]),

@@ -165,6 +165,14 @@ struct cdb_sim {
     // strip decomposition
     bool strip = false;
     int has_left = 0, has_right = 0;
+    // one-sided exchange over peer memory (cdb_strip_exchange_*): my receive buffers [0] from the left, [1] from the right
+    double *x_halo_in[2] = {nullptr, nullptr}, *x_mig_in[2] = {nullptr, nullptr};
+    unsigned long long *x_flags = nullptr;       // [0] halo from left, [1] halo from right, [2] migrants from left, [3] from right
+    unsigned int *x_done = nullptr;              // arrival counters of my two halo-pack grids
+    double *p_halo[2] = {nullptr, nullptr}, *p_mig[2] = {nullptr, nullptr};   // where I write: the neighbours' receive buffers
+    unsigned long long *p_flags[2] = {nullptr, nullptr};                      // the neighbours' flag arrays
+    void *p_opened[2][5] = {{nullptr}};          // IPC mappings to close
+    bool x_connected = false;
     int strip_fine = 1;              // search refinement of the strip lattice (fixed by cdb_set_strip)
     long long strip_ix0 = 0, strip_col_lo = 0, strip_col_hi = 0;   // cell_size columns: lattice origin, owned range
     int64_t halo_cap = 0, mig_cap = 0;
@@ -281,6 +289,7 @@ int check_device_error(cdb_sim *sim) {
     CK(cudaMemsetAsync(sim->d_error, 0, sizeof(int), sim->stream));
     if (e == ERR_NONFINITE) return fail(CDB_ERR_INVALID_VALUE, "non-finite agent position encountered on device");
     if (e == ERR_CELL_RANGE) return fail(CDB_ERR_CAPACITY, "cell lattice too large (more than 2^31 cells)");
+    if (e == ERR_CELL_RANGE + 5) return fail(CDB_ERR_CAPACITY, "more migrants arrived in one step than the host-side slot bound allows; ask for the exact count (cdb_strip_count / n_out) after bursts");
     if (e == ERR_PAIR_OVERFLOW) return fail(CDB_ERR_CAPACITY, "pair list overflow in strip mode (a strip step cannot be repeated): raise cdb_set_pair_capacity");
     return fail(CDB_ERR_CUDA, "device error flag %d", e);
 }
@@ -507,7 +516,7 @@ int launch_pairs(cdb_sim *sim) {
 }
 
 // the fused kernel; requires a current block list when CDB_STEP_AGENT_AGENT is selected
-int launch_step_kernel(cdb_sim *sim, unsigned flags, double dt_min, double dt_max, double *dt_log) {
+int launch_step_kernel(cdb_sim *sim, unsigned flags, double dt_min, double dt_max, double *dt_log, const MigrantArgs *mig = nullptr) {
     const bool pairs = use_pairs(sim);
     if (pairs && (flags & CDB_STEP_AGENT_AGENT)) CKS(launch_pairs(sim));
     else { CKS(prof_mark(sim)); CKS(prof_mark(sim)); }
@@ -515,6 +524,8 @@ int launch_step_kernel(cdb_sim *sim, unsigned flags, double dt_min, double dt_ma
     a.pb = sim->pb;
     a.n_planes = sim->n_planes;
     a.reach = sim->fine;
+    a.mig = MigrantArgs{};
+    if (mig && pairs && (flags & CDB_STEP_INTEGRATOR)) a.mig = *mig;
     const int smem = 0;
     if (a.n > 0) {
         if (pairs) {
@@ -697,6 +708,11 @@ int cdb_destroy(cdb_sim *sim) {
     free_soa(sim->cur); free_soa(sim->alt);
     cudaFree(sim->d_aos); cudaFreeHost(sim->h_bounce); cudaFree(sim->d_rec_slot);
     for (auto &r : sim->registered) cudaHostUnregister(r.first);
+    for (int k = 0; k < 2; ++k) {
+        for (int j = 0; j < 5; ++j) if (sim->p_opened[k][j]) cudaIpcCloseMemHandle(sim->p_opened[k][j]);
+        cudaFree(sim->x_halo_in[k]); cudaFree(sim->x_mig_in[k]);
+    }
+    cudaFree(sim->x_flags); cudaFree(sim->x_done);
     cudaFree(sim->d_grid); cudaFree(sim->d_cell_count); cudaFree(sim->d_cell_start); cudaFree(sim->d_cell_fill);
     cudaFree(sim->d_cell_of_slot); cudaFree(sim->d_order_tmp); cudaFree(sim->d_order); if (sim->d_nbr_sweep != sim->d_nbr) cudaFree(sim->d_nbr_sweep); cudaFree(sim->d_nbr); cudaFree(sim->d_scan_partials);
     cudaFree(sim->d_bbox); cudaFreeHost(sim->h_bbox);
@@ -1524,26 +1540,38 @@ int64_t cdb_halo_buffer_doubles(const cdb_sim *sim) {
 }
 int64_t cdb_migrant_buffer_doubles(const cdb_sim *sim) { return sim ? MSG_HEADER + sim->mig_cap * (sim->n_planes + 2) : -1; }
 
-int cdb_strip_begin(cdb_sim *sim, uint32_t flags, double cell_size, double *halo_left_out, double *halo_right_out) {
-    SIM_ENTRY();
+static int strip_begin_impl(cdb_sim *sim, uint32_t flags, double cell_size, double *halo_left_out, double *halo_right_out, bool direct) {
     if (!sim->strip) return fail(CDB_ERR_STATE, "cdb_set_strip has not been called");
     if (sim->variant == 1) return fail(CDB_ERR_STATE, "the strip decomposition needs kernel variant 2 or 3");
+    if (direct && !sim->x_connected) return fail(CDB_ERR_STATE, "cdb_strip_exchange_connect_* has not been called");
     if (flags & CDB_STEP_AGENT_AGENT) CKS(prepare_pairs(sim));
     CKS(prof_mark(sim));
     LAUNCH(sim, k_vmax_init, 1, 32, 0, sim->d_vmax);
+    LAUNCH(sim, k_counters_zero, 1, 32, 0, sim->d_counters, 4);      // migrant counters of this step
     const int f = sim->strip_fine;
     CKS(build_block_list(sim, cell_size, false, sim->d_vmax, false, f));
     const int rec = sim->model == CDB_MODEL_CIRCULAR ? REC_CIRC : REC_THREE;
     // a halo message is one cell_size column = f consecutive columns of the search lattice = f * ny consecutive cells
     const int nyb = (int)sim->grid.ny * f;
+    const unsigned long long seq = (unsigned long long)sim->iterations + 1;
     if (sim->has_left && halo_left_out)
         LAUNCH(sim, k_halo_pack, 32, 256, 0, sim->d_nbr, rec, sim->d_cell_start, sim->d_cell_count, (int)sim->strip_col_lo, nyb, halo_left_out,
-               (long long)sim->halo_cap, sim->d_error);
+               (long long)sim->halo_cap, sim->d_error, sim->x_done, direct ? sim->p_flags[0] + 1 : nullptr, seq);   // I am its right neighbour
     if (sim->has_right && halo_right_out)
         LAUNCH(sim, k_halo_pack, 32, 256, 0, sim->d_nbr, rec, sim->d_cell_start, sim->d_cell_count, (int)sim->strip_col_hi, nyb, halo_right_out,
-               (long long)sim->halo_cap, sim->d_error);
+               (long long)sim->halo_cap, sim->d_error, sim->x_done ? sim->x_done + 1 : nullptr, direct ? sim->p_flags[1] + 0 : nullptr, seq);
     CK(cudaGetLastError());
     return CDB_OK;
+}
+
+int cdb_strip_begin(cdb_sim *sim, uint32_t flags, double cell_size, double *halo_left_out, double *halo_right_out) {
+    SIM_ENTRY();
+    return strip_begin_impl(sim, flags, cell_size, halo_left_out, halo_right_out, false);
+}
+
+int cdb_strip_begin_direct(cdb_sim *sim, uint32_t flags, double cell_size, int send_halo) {
+    SIM_ENTRY();
+    return strip_begin_impl(sim, flags, cell_size, send_halo ? sim->p_halo[0] : nullptr, send_halo ? sim->p_halo[1] : nullptr, true);
 }
 
 int cdb_strip_export_vmax(cdb_sim *sim, double *dev_vmax2) {
@@ -1559,39 +1587,59 @@ int cdb_strip_import_vmax(cdb_sim *sim, const double *dev_vmax2) {
     return CDB_OK;
 }
 
-int cdb_strip_finish(cdb_sim *sim, uint32_t flags, double dt_min, double dt_max, const double *halo_left_in,
-                     const double *halo_right_in, double *mig_left_out, double *mig_right_out) {
-    SIM_ENTRY();
+static int strip_finish_impl(cdb_sim *sim, uint32_t flags, double dt_min, double dt_max, const double *halo_left_in,
+                             const double *halo_right_in, double *mig_left_out, double *mig_right_out, bool direct) {
     if (!sim->strip || !sim->tables_valid) return fail(CDB_ERR_STATE, "cdb_strip_begin must precede cdb_strip_finish");
     const int rec = sim->model == CDB_MODEL_CIRCULAR ? REC_CIRC : REC_THREE;
     const int ny = (int)sim->grid.ny * sim->strip_fine;      // cells of one cell_size column
     const int base_l = (int)sim->capacity, base_r = (int)(sim->capacity + sim->halo_cap);
+    const unsigned long long seq = (unsigned long long)sim->iterations + 1;
     if (sim->has_left) {
         if (halo_left_in) LAUNCH(sim, k_halo_unpack, 32, 1024, 0, halo_left_in, rec, sim->d_nbr, sim->d_nbr_sweep, sim->d_cell_of_slot, sim->d_cell_start, sim->d_cell_count,
-                                 0, ny, base_l, (long long)sim->halo_cap, sim->d_error, sim->d_par);
+                                 0, ny, base_l, (long long)sim->halo_cap, sim->d_error, sim->d_par, direct ? sim->x_flags + 0 : nullptr, seq);
         else LAUNCH(sim, k_ghost_clear, 4, 256, 0, sim->d_cell_start, sim->d_cell_count, 0, ny, base_l);
     }
     if (sim->has_right) {
         const int col = (int)sim->strip_col_hi + 1;
         if (halo_right_in) LAUNCH(sim, k_halo_unpack, 32, 1024, 0, halo_right_in, rec, sim->d_nbr, sim->d_nbr_sweep, sim->d_cell_of_slot, sim->d_cell_start, sim->d_cell_count,
-                                  col, ny, base_r, (long long)sim->halo_cap, sim->d_error, sim->d_par);
+                                  col, ny, base_r, (long long)sim->halo_cap, sim->d_error, sim->d_par, direct ? sim->x_flags + 1 : nullptr, seq);
         else LAUNCH(sim, k_ghost_clear, 4, 256, 0, sim->d_cell_start, sim->d_cell_count, col, ny, base_r);
     }
     CKS(prof_mark(sim));
-    CKS(launch_step_kernel(sim, flags, dt_min, dt_max, nullptr));
+    // variant 3, integrating step: the finish kernel itself hands over the agents that left the owned columns
+    const bool fused_migrants = use_pairs(sim) && (flags & CDB_STEP_INTEGRATOR) && sim->n_sorted > 0;
+    MigrantArgs mig{};
+    mig.enabled = 1; mig.cell_size = sim->cell_size; mig.ix0 = sim->strip_ix0;
+    mig.col_lo = (int)sim->strip_col_lo; mig.col_hi = (int)sim->strip_col_hi; mig.has_left = sim->has_left; mig.has_right = sim->has_right;
+    mig.msg_left = mig_left_out; mig.msg_right = mig_right_out; mig.cap = sim->mig_cap; mig.counters = sim->d_counters; mig.error = sim->d_error;
+    if (mig.has_left && !mig_left_out) mig.has_left = 0;
+    if (mig.has_right && !mig_right_out) mig.has_right = 0;
+    CKS(launch_step_kernel(sim, flags, dt_min, dt_max, nullptr, fused_migrants ? &mig : nullptr));
     CKS(prof_mark(sim));
     sim->iterations++;
     LAUNCH(sim, k_step_advance, 1, 32, 0, sim->d_stepctr, (const unsigned long long *)nullptr, 0LL);
-    LAUNCH(sim, k_counters_zero, 1, 32, 0, sim->d_counters, 4);
-    if (sim->n > 0)
+    if (sim->n > 0 && !fused_migrants)
         LAUNCH(sim, k_migrants_pack, cdiv(sim->n, 256), 256, 0, sim->cur, (int)sim->n, sim->dev_counts ? &sim->d_counts->slots : nullptr, sim->n_planes, sim->cell_size, sim->strip_ix0,
                (int)sim->strip_col_lo, (int)sim->strip_col_hi, sim->has_left, sim->has_right, mig_left_out, mig_right_out, (long long)sim->mig_cap,
                sim->d_counters, sim->d_error);
     LAUNCH(sim, k_migrants_header, 1, 32, 0, sim->has_left ? mig_left_out : nullptr, sim->has_right ? mig_right_out : nullptr, sim->d_counters,
-           (long long)sim->mig_cap);
+           (long long)sim->mig_cap, direct && sim->has_left ? sim->p_flags[0] + 3 : nullptr, direct && sim->has_right ? sim->p_flags[1] + 2 : nullptr, seq);
     CK(cudaGetLastError());
     CKS(prof_mark(sim));
     return CDB_OK;
+}
+
+int cdb_strip_finish(cdb_sim *sim, uint32_t flags, double dt_min, double dt_max, const double *halo_left_in,
+                     const double *halo_right_in, double *mig_left_out, double *mig_right_out) {
+    SIM_ENTRY();
+    return strip_finish_impl(sim, flags, dt_min, dt_max, halo_left_in, halo_right_in, mig_left_out, mig_right_out, false);
+}
+
+int cdb_strip_finish_direct(cdb_sim *sim, uint32_t flags, double dt_min, double dt_max, int recv_halo) {
+    SIM_ENTRY();
+    if (!sim->x_connected) return fail(CDB_ERR_STATE, "cdb_strip_exchange_connect_* has not been called");
+    return strip_finish_impl(sim, flags, dt_min, dt_max, recv_halo ? sim->x_halo_in[0] : nullptr, recv_halo ? sim->x_halo_in[1] : nullptr,
+                             sim->p_mig[0], sim->p_mig[1], true);
 }
 
 // exact counts back on the host (one sync): slots in use, slots vacated by the last step's migrants; also surfaces device errors
@@ -1606,27 +1654,104 @@ static int strip_refresh(cdb_sim *sim) {
     return CDB_OK;
 }
 
-int cdb_strip_absorb(cdb_sim *sim, const double *mig_left_in, const double *mig_right_in, int64_t *n_out) {
-    SIM_ENTRY();
+static int strip_absorb_impl(cdb_sim *sim, const double *mig_left_in, const double *mig_right_in, int64_t *n_out, bool direct) {
     if (!sim->strip) return fail(CDB_ERR_STATE, "cdb_set_strip has not been called");
     const int g = cdiv(sim->mig_cap > 0 ? sim->mig_cap : 1, 128);
     const int *slots_dev = &sim->d_counts->slots;
+    const unsigned long long seq = (unsigned long long)sim->iterations;      // the step cdb_strip_finish just completed
     if (sim->has_left && mig_left_in)
-        LAUNCH(sim, k_migrants_unpack, g, 128, 0, mig_left_in, sim->cur, (int)sim->n, slots_dev, sim->n_planes, (long long)sim->capacity, sim->d_counters, sim->d_error);
+        LAUNCH(sim, k_migrants_unpack, g, 128, 0, mig_left_in, sim->cur, (int)sim->n, slots_dev, sim->n_planes, (long long)sim->capacity, sim->d_counters, sim->d_error,
+               direct ? sim->x_flags + 2 : nullptr, seq);
     if (sim->has_right && mig_right_in)
-        LAUNCH(sim, k_migrants_unpack, g, 128, 0, mig_right_in, sim->cur, (int)sim->n, slots_dev, sim->n_planes, (long long)sim->capacity, sim->d_counters, sim->d_error);
-    LAUNCH(sim, k_counts_after_absorb, 1, 32, 0, sim->d_counts, sim->d_counters);
-    CK(cudaGetLastError());
-    sim->tables_valid = false;
+        LAUNCH(sim, k_migrants_unpack, g, 128, 0, mig_right_in, sim->cur, (int)sim->n, slots_dev, sim->n_planes, (long long)sim->capacity, sim->d_counters, sim->d_error,
+               direct ? sim->x_flags + 3 : nullptr, seq);
     // The exact counts stay on the device; the host keeps an upper bound for its launch sizes and only synchronises every
     // STRIP_REFRESH steps (or when the bound would not fit the allocation, or when the caller asks for the exact count).
-    const int64_t bound = sim->n + 2 * sim->mig_cap;
-    if (++sim->steps_since_refresh >= STRIP_REFRESH || bound > sim->capacity || n_out) {
+    // The bound grows by what can plausibly arrive in one step (agents move ~1 cm per step: a few per km of border), not by
+    // the capacity of the migrant messages; a burst beyond it raises a device error instead of being skipped silently.
+    const int64_t grow = 2 * std::min<int64_t>(sim->mig_cap, std::max<int64_t>(64, sim->n / 2048));
+    const int64_t bound = sim->n + grow;
+    const bool refresh = ++sim->steps_since_refresh >= STRIP_REFRESH || bound > sim->capacity || n_out;
+    LAUNCH(sim, k_counts_after_absorb, 1, 32, 0, sim->d_counts, sim->d_counters, refresh ? -1LL : (long long)bound, sim->d_error);
+    CK(cudaGetLastError());
+    sim->tables_valid = false;
+    if (refresh) {
         CKS(strip_refresh(sim));
         if (n_out) *n_out = sim->n - sim->n_dead;
     } else {
         sim->n = bound;
     }
+    return CDB_OK;
+}
+
+int cdb_strip_absorb(cdb_sim *sim, const double *mig_left_in, const double *mig_right_in, int64_t *n_out) {
+    SIM_ENTRY();
+    return strip_absorb_impl(sim, mig_left_in, mig_right_in, n_out, false);
+}
+
+int cdb_strip_absorb_direct(cdb_sim *sim, int64_t *n_out) {
+    SIM_ENTRY();
+    if (!sim->x_connected) return fail(CDB_ERR_STATE, "cdb_strip_exchange_connect_* has not been called");
+    return strip_absorb_impl(sim, sim->x_mig_in[0], sim->x_mig_in[1], n_out, true);
+}
+
+// ---- one-sided exchange: receive buffers + flags, exported as CUDA IPC handles (one process per GPU) or raw pointers -------
+int cdb_strip_exchange_alloc(cdb_sim *sim) {
+    SIM_ENTRY();
+    if (!sim->strip) return fail(CDB_ERR_STATE, "cdb_set_strip has not been called");
+    const size_t hb = (size_t)cdb_halo_buffer_doubles(sim), mb = (size_t)cdb_migrant_buffer_doubles(sim);
+    for (int k = 0; k < 2; ++k) {
+        CKS(dev_alloc(&sim->x_halo_in[k], hb)); CKS(dev_alloc(&sim->x_mig_in[k], mb));
+        CK(cudaMemset(sim->x_halo_in[k], 0, hb * sizeof(double))); CK(cudaMemset(sim->x_mig_in[k], 0, mb * sizeof(double)));
+    }
+    CKS(dev_alloc(&sim->x_flags, 8)); CKS(dev_alloc(&sim->x_done, 4));
+    CK(cudaMemset(sim->x_flags, 0, 8 * sizeof(unsigned long long))); CK(cudaMemset(sim->x_done, 0, 4 * sizeof(unsigned int)));
+    return CDB_OK;
+}
+
+int64_t cdb_strip_exchange_handle_bytes(void) { return 5 * (int64_t)sizeof(cudaIpcMemHandle_t); }
+
+int cdb_strip_exchange_handles(cdb_sim *sim, void *out) {
+    SIM_ENTRY();
+    if (!sim->x_flags || !out) return fail(CDB_ERR_STATE, "cdb_strip_exchange_alloc has not been called");
+    cudaIpcMemHandle_t *h = (cudaIpcMemHandle_t *)out;
+    CK(cudaIpcGetMemHandle(&h[0], sim->x_halo_in[0])); CK(cudaIpcGetMemHandle(&h[1], sim->x_halo_in[1]));
+    CK(cudaIpcGetMemHandle(&h[2], sim->x_mig_in[0])); CK(cudaIpcGetMemHandle(&h[3], sim->x_mig_in[1]));
+    CK(cudaIpcGetMemHandle(&h[4], sim->x_flags));
+    return CDB_OK;
+}
+
+// left / right: the 5 handles of the neighbour's cdb_strip_exchange_handles (NULL: no neighbour on that side)
+int cdb_strip_exchange_connect_ipc(cdb_sim *sim, const void *left, const void *right) {
+    SIM_ENTRY();
+    if (!sim->x_flags) return fail(CDB_ERR_STATE, "cdb_strip_exchange_alloc has not been called");
+    const void *side[2] = {left, right};
+    for (int k = 0; k < 2; ++k) {
+        if (!side[k]) continue;
+        const cudaIpcMemHandle_t *h = (const cudaIpcMemHandle_t *)side[k];
+        for (int j = 0; j < 5; ++j) CK(cudaIpcOpenMemHandle(&sim->p_opened[k][j], h[j], cudaIpcMemLazyEnablePeerAccess));
+        // I write into the buffer the neighbour reads from MY side: its "from right" buffers if it is my left neighbour
+        sim->p_halo[k] = (double *)sim->p_opened[k][k == 0 ? 1 : 0];
+        sim->p_mig[k] = (double *)sim->p_opened[k][k == 0 ? 3 : 2];
+        sim->p_flags[k] = (unsigned long long *)sim->p_opened[k][4];
+    }
+    sim->x_connected = true;
+    return CDB_OK;
+}
+
+// the same inside one process (all strips on one device, or peer-accessible devices): the neighbours' sims directly
+int cdb_strip_exchange_connect_local(cdb_sim *sim, cdb_sim *left, cdb_sim *right) {
+    SIM_ENTRY();
+    if (!sim->x_flags) return fail(CDB_ERR_STATE, "cdb_strip_exchange_alloc has not been called");
+    cdb_sim *side[2] = {left, right};
+    for (int k = 0; k < 2; ++k) {
+        if (!side[k]) continue;
+        if (!side[k]->x_flags) return fail(CDB_ERR_STATE, "the neighbour has no exchange buffers");
+        sim->p_halo[k] = side[k]->x_halo_in[k == 0 ? 1 : 0];
+        sim->p_mig[k] = side[k]->x_mig_in[k == 0 ? 1 : 0];
+        sim->p_flags[k] = side[k]->x_flags;
+    }
+    sim->x_connected = true;
     return CDB_OK;
 }
 

@@ -107,7 +107,6 @@ __global__ void __launch_bounds__(FIN_THREADS, MODEL == 0 ? FIN_MINB_CIRC : FIN_
     o(RADIUS, t) = radius; o(MASS, t) = mass; o(V0, t) = v0; o(TAU_ADJ, t) = tau_adj;
     o(K_SOC, t) = k_soc; o(TAU_0, t) = tau_0; o(MU, t) = mu; o(KAPPA, t) = kappa; o(DAMPING, t) = damping;
     o(STD_RAND_FORCE, t) = srf;
-    o.id[t] = id;
     o.target[t] = target;
     if (MODEL == 1) {
         o(LSX, t) = npx - ox; o(LSY, t) = npy - oy; o(RSX, t) = npx + ox; o(RSY, t) = npy + oy;
@@ -116,4 +115,31 @@ __global__ void __launch_bounds__(FIN_THREADS, MODEL == 0 ? FIN_MINB_CIRC : FIN_
         o(TORQUE, t) = rst ? 0.0 : tq; o(TORQUE_PREV, t) = tq; o(TAU_ROT, t) = tau_rot;
         o(STD_RAND_TORQUE, t) = srt;
     }
+    // ---- strips: did the agent leave the owned columns?  Then its new state goes into the neighbour's migrant message ------
+    int side = -1;
+    if (A.mig.enabled) {
+        const double col = floor(npx / A.mig.cell_size) - (double)A.mig.ix0;
+        if (A.mig.has_left && col < (double)A.mig.col_lo) side = 0;
+        else if (A.mig.has_right && col > (double)A.mig.col_hi) side = 1;
+    }
+    if (side >= 0) {
+        const int k = atomicAdd(&A.mig.counters[side], 1);
+        if (k >= A.mig.cap) { atomicExch(A.mig.error, ERR_CELL_RANGE + 3); side = -1; }
+        else {
+            double *d = (side == 0 ? A.mig.msg_left : A.mig.msg_right) + MSG_HEADER + (size_t)k * (A.n_planes + 2);
+            d[PX] = npx; d[PY] = npy; d[VX] = nvx; d[VY] = nvy; d[E0X] = e0x; d[E0Y] = e0y;
+            d[FX] = rst ? 0.0 : fx; d[FY] = rst ? 0.0 : fy; d[FPX] = fx; d[FPY] = fy;
+            d[RADIUS] = radius; d[MASS] = mass; d[V0] = v0; d[TAU_ADJ] = tau_adj; d[K_SOC] = k_soc; d[TAU_0] = tau_0;
+            d[MU] = mu; d[KAPPA] = kappa; d[DAMPING] = damping; d[STD_RAND_FORCE] = srf;
+            if (MODEL == 1) {
+                d[LSX] = npx - ox; d[LSY] = npy - oy; d[RSX] = npx + ox; d[RSY] = npy + oy;
+                d[R_T] = r_t; d[R_S] = r_s; d[R_TS] = r_ts; d[INERTIA] = inertia; d[OMEGA0] = omega0;
+                d[PHI] = phi; d[OMEGA] = w; d[PHI0] = phi0; d[TORQUE] = rst ? 0.0 : tq; d[TORQUE_PREV] = tq; d[TAU_ROT] = tau_rot;
+                d[STD_RAND_TORQUE] = srt;
+            }
+            d[A.n_planes] = (double)id;
+            d[A.n_planes + 1] = (double)target;
+        }
+    }
+    o.id[t] = side >= 0 ? -1 : id;
 }

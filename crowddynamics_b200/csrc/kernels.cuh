@@ -54,6 +54,7 @@ struct FieldMap { short plane; short offset; unsigned bit; };
 
 enum { ERR_NONE = 0, ERR_NONFINITE = 1, ERR_CELL_RANGE = 2, ERR_PAIR_OVERFLOW = 100 };
 constexpr int MAX_NAV_TARGETS = 64;
+constexpr int MSG_HEADER = 4;   // doubles at the head of a halo / migrant message (strip_kernels.cuh)
 constexpr int AOS_REC_PER_BLOCK = 128;
 constexpr int SCAN_THREADS = 256;
 constexpr int SCAN_ITEMS = 8;

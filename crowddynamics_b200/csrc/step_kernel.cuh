@@ -33,6 +33,19 @@ constexpr int LCAP = 16;     // survivor list entries per lane between two flush
 #endif
 constexpr int CHUNK = STEP_CHUNK;     // candidates classified between two list-capacity checks
 
+// strips: an agent whose new position lies in a cell_size column outside the owned range is handed to the neighbour --
+// the finish kernel appends its whole new state to that side's migrant message and vacates the slot (id = -1)
+struct MigrantArgs {
+    int enabled;
+    double cell_size;
+    long long ix0;           // cell_size column of the local lattice origin
+    int col_lo, col_hi, has_left, has_right;
+    double *msg_left, *msg_right;
+    long long cap;
+    int *counters;           // [0] left, [1] right
+    int *error;
+};
+
 struct StepArgs {
     Soa in, out;             // out == in unless integrating (then the new state is written to the other buffer)
     const double *nbr;       // packed neighbour records of `in`
@@ -56,6 +69,7 @@ struct StepArgs {
     const unsigned long long *step_ptr;   // device-side step index (advanced by k_step_advance after every step)
     PairBuf pb;              // k_finish: per-agent contributions written by k_pair_eval (pair_kernels.cuh)
     int n_planes;            // planes of the model (k_finish: a step that is not applied still moves them to `out`)
+    MigrantArgs mig;         // k_finish in strip mode
     int reach;               // k_step: cell columns / rows swept on either side of the target's cell (1, or 2 on the finer lattice)
 };
 

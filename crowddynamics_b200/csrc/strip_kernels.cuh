@@ -5,13 +5,43 @@
 #pragma once
 #include "kernels.cuh"
 
-constexpr int MSG_HEADER = 4;   // doubles
+// ---- one-sided exchange over peer memory (NVLink): the producer writes the message straight into the consumer's receive
+// buffer and then publishes a sequence number in the consumer's memory; the consumer's kernel spins on that number.
+// Single buffers suffice: halo and migrant messages alternate, and each one can only be produced after the other one of the
+// previous phase was consumed ("Multi-GPU").
+__device__ __forceinline__ void signal_store(unsigned long long *flag, unsigned long long seq) {
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag), "l"(seq) : "memory");
+}
+__device__ __forceinline__ unsigned long long signal_load(const unsigned long long *flag) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
+    return v;
+}
+// all threads of the block return once *flag >= seq (flag == nullptr: nothing to wait for)
+__device__ __forceinline__ void signal_wait(const unsigned long long *flag, unsigned long long seq) {
+    if (flag) {
+        if (threadIdx.x == 0) while (signal_load(flag) < seq) __nanosleep(64);
+        __syncthreads();
+    }
+}
+// last block of a grid to arrive publishes the flag (done: a zero-initialised counter, reset for the next use)
+__device__ __forceinline__ void signal_when_grid_done(unsigned int *done, unsigned long long *flag, unsigned long long seq) {
+    if (!flag) return;
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int prev = atomicAdd(done, 1u);
+        if (prev == gridDim.x - 1) { *done = 0u; signal_store(flag, seq); }
+    }
+}
 
 __host__ __device__ inline long long halo_counts_doubles(long long ny) { return (ny + 1) / 2; }
 
 // column `col` of the local lattice -> message.  One block; the column's agents are contiguous in cell order.
 __global__ void k_halo_pack(const double *__restrict__ nbr, int rec, const int *__restrict__ cell_start,
-                            const int *__restrict__ cell_count, int col, int ny, double *__restrict__ msg, long long cap, int *error) {
+                            const int *__restrict__ cell_count, int col, int ny, double *__restrict__ msg, long long cap, int *error,
+                            unsigned int *done, unsigned long long *peer_flag, unsigned long long seq) {
     const int b = cell_start[col * ny];
     const int e = cell_start[col * ny + ny - 1] + cell_count[col * ny + ny - 1];
     int count = e - b;
@@ -23,6 +53,7 @@ __global__ void k_halo_pack(const double *__restrict__ nbr, int rec, const int *
     const double *src = nbr + (size_t)b * rec;
     for (long long i = blockIdx.x * blockDim.x + threadIdx.x; i < (long long)count * rec; i += (long long)gridDim.x * blockDim.x)
         dst[i] = src[i];
+    signal_when_grid_done(done, peer_flag, seq);
 }
 
 // message -> ghost column `col` of the local lattice; ghost records live at slots [base, base + count) of nbr.
@@ -31,9 +62,10 @@ __global__ void k_halo_pack(const double *__restrict__ nbr, int rec, const int *
 __global__ void k_halo_unpack(const double *__restrict__ msg, int rec, double *__restrict__ nbr, double *__restrict__ nbr_sweep,
                               int *__restrict__ cell_sorted,
                               int *__restrict__ cell_start, int *__restrict__ cell_count, int col, int ny, int base, long long cap,
-                              int *error, double2 *__restrict__ par) {
+                              int *error, double2 *__restrict__ par, const unsigned long long *flag, unsigned long long seq) {
     __shared__ int warp_sums[32];
     __shared__ int carry_s;
+    signal_wait(flag, seq);
     const int *counts = reinterpret_cast<const int *>(msg + MSG_HEADER);
     const int count = (int)msg[0];
     if ((int)msg[1] != ny || count > cap) { if (threadIdx.x == 0 && blockIdx.x == 0) atomicExch(error, ERR_CELL_RANGE + 2); return; }
@@ -89,7 +121,14 @@ __global__ void k_counters_zero(int *c, int n) { if (threadIdx.x < n) c[threadId
 // device-side bookkeeping of the strip step (no host round trip): after the integrating step the live agents are compact
 // in [0, live); after absorbing migrants the slot count grows by the number appended
 __global__ void k_counts_after_step(DevCounts *c) { if (threadIdx.x == 0) c->slots = c->live; }
-__global__ void k_counts_after_absorb(DevCounts *c, const int *counters) { if (threadIdx.x == 0) c->slots += counters[2]; }
+// host_bound: the slot count the host will assume for its next launches (it only synchronises every few steps); more
+// arrivals than that in one step would be silently skipped by those launches => device error instead
+__global__ void k_counts_after_absorb(DevCounts *c, const int *counters, long long host_bound, int *error) {
+    if (threadIdx.x == 0) {
+        c->slots += counters[2];
+        if (host_bound >= 0 && c->slots > host_bound) atomicExch(error, ERR_CELL_RANGE + 5);
+    }
+}
 __global__ void k_counts_set(DevCounts *c, int slots) { if (threadIdx.x == 0) { c->slots = slots; c->live = slots; } }
 
 // agents whose cell column left the owned range [col_lo, col_hi] move to the neighbour: append the whole agent to the
@@ -113,16 +152,21 @@ __global__ void k_migrants_pack(Soa s, int n_host, const int *n_dev, int n_plane
     s.id[i] = -1;
 }
 
-__global__ void k_migrants_header(double *msg_left, double *msg_right, const int *counters, long long cap) {
+__global__ void k_migrants_header(double *msg_left, double *msg_right, const int *counters, long long cap,
+                                  unsigned long long *flag_left, unsigned long long *flag_right, unsigned long long seq) {
     if (threadIdx.x == 0) {
         if (msg_left) { msg_left[0] = (double)min((long long)counters[0], cap); msg_left[1] = msg_left[2] = msg_left[3] = 0.0; }
         if (msg_right) { msg_right[0] = (double)min((long long)counters[1], cap); msg_right[1] = msg_right[2] = msg_right[3] = 0.0; }
+        // (the migrant records were written by the previous kernel of this stream: complete, made visible by the fence)
+        if (flag_left) signal_store(flag_left, seq);
+        if (flag_right) signal_store(flag_right, seq);
     }
 }
 
 // append received migrants after the current slots; counters[2] = number appended so far
 __global__ void k_migrants_unpack(const double *__restrict__ msg, Soa s, int n_slots_host, const int *n_slots_dev, int n_planes,
-                                  long long capacity, int *counters, int *error) {
+                                  long long capacity, int *counters, int *error, const unsigned long long *flag, unsigned long long seq) {
+    signal_wait(flag, seq);
     const int m = (int)msg[0];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= m) return;

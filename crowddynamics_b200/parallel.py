@@ -74,6 +74,35 @@ class CudaStripDevice:
     def set_navigation_field(self, target, mgrid, direction_map):
         self.dev.set_navigation_field(target, mgrid, direction_map)
 
+    # -- one-sided exchange over peer memory (NVLink) ---------------------------------------------------------------------
+    def exchange_alloc(self):
+        _lib.check(self.lib.cdb_strip_exchange_alloc(self.handle))
+
+    def exchange_handles(self):
+        buf = C.create_string_buffer(int(self.lib.cdb_strip_exchange_handle_bytes()))
+        _lib.check(self.lib.cdb_strip_exchange_handles(self.handle, buf))
+        return buf.raw
+
+    def connect_ipc(self, left, right):
+        lb = C.create_string_buffer(left, len(left)) if left is not None else None
+        rb = C.create_string_buffer(right, len(right)) if right is not None else None
+        _lib.check(self.lib.cdb_strip_exchange_connect_ipc(self.handle, lb, rb))
+
+    def connect_local(self, left, right):
+        _lib.check(self.lib.cdb_strip_exchange_connect_local(self.handle, left.handle if left is not None else None,
+                                                             right.handle if right is not None else None))
+
+    def begin_direct(self, flags, cell_size, send_halo=True):
+        _lib.check(self.lib.cdb_strip_begin_direct(self.handle, flags, cell_size, 1 if send_halo else 0))
+
+    def finish_direct(self, flags, dt_min, dt_max, recv_halo=True):
+        _lib.check(self.lib.cdb_strip_finish_direct(self.handle, flags, dt_min, dt_max, 1 if recv_halo else 0))
+
+    def absorb_direct(self, exact=False):
+        n = C.c_int64()
+        _lib.check(self.lib.cdb_strip_absorb_direct(self.handle, C.byref(n) if exact else None))
+        return n.value if exact else None
+
     def begin(self, flags, cell_size, halo_left_out, halo_right_out):
         _lib.check(self.lib.cdb_strip_begin(self.handle, flags, cell_size, self._p(halo_left_out), self._p(halo_right_out)))
 
@@ -87,10 +116,12 @@ class CudaStripDevice:
         _lib.check(self.lib.cdb_strip_finish(self.handle, flags, dt_min, dt_max, self._p(halo_left_in),
                                              self._p(halo_right_in), self._p(mig_left_out), self._p(mig_right_out)))
 
-    def absorb(self, mig_left_in, mig_right_in):
-        """Appends the received migrants; returns None: the exact count stays on the device (see count())."""
-        _lib.check(self.lib.cdb_strip_absorb(self.handle, self._p(mig_left_in), self._p(mig_right_in), None))
-        return None
+    def absorb(self, mig_left_in, mig_right_in, exact=False):
+        """Appends the received migrants; returns None: the exact count stays on the device (see count()) unless ``exact``
+        (one host synchronisation; required after bursts such as the initial settle())."""
+        n = C.c_int64()
+        _lib.check(self.lib.cdb_strip_absorb(self.handle, self._p(mig_left_in), self._p(mig_right_in), C.byref(n) if exact else None))
+        return n.value if exact else None
 
     def count(self):
         n = C.c_int64()
@@ -165,6 +196,31 @@ class StripSimulation:
         self.mig_in = {s: buf(mig_doubles) for s in ('l', 'r')}
         self.vmax = buf(2)
         self._n_owned = n_owned
+        self.direct = False          # True: halo / migrants travel by one-sided writes into the neighbours' buffers
+
+    def connect_direct(self):
+        """One process per GPU: replace the two NCCL send/recv rounds of a step by one-sided writes over NVLink peer memory
+        (CUDA IPC).  Collective: every rank must call it.  Falls back to NCCL (returns False) where IPC is not possible."""
+        ok = 1
+        handles = None
+        try:
+            self.dev.exchange_alloc()
+            handles = self.dev.exchange_handles()
+        except Exception:
+            ok = 0
+        gathered = [None] * self.world
+        self.dist.all_gather_object(gathered, (ok, handles))
+        if not all(g[0] for g in gathered):
+            return False
+        try:
+            self.dev.connect_ipc(gathered[self.left][1] if self.left is not None else None,
+                                 gathered[self.right][1] if self.right is not None else None)
+        except Exception:
+            ok = 0
+        flags = [None] * self.world
+        self.dist.all_gather_object(flags, ok)
+        self.direct = all(flags)
+        return self.direct
 
     def n_owned(self):
         """Agents currently owned by this rank (asks the device when the last step did not report it)."""
@@ -175,7 +231,7 @@ class StripSimulation:
     # -- neighbour exchange ---------------------------------------------------------------------------------------------
     def _exchange(self, out, inn):
         """Send out['l'] to the left neighbour and out['r'] to the right one; receive into inn['l'] / inn['r']."""
-        if self.world == 1:
+        if self.world == 1 or self.direct:
             return
         dist = self.dist
         ops = []
@@ -189,42 +245,82 @@ class StripSimulation:
             req.wait()
 
     # -- the phases of one step (driven by step() over torch.distributed, or by LocalGroup in one process) ---------------
-    def phase_begin(self):
+    def phase_begin(self, flags=None, send_halo=True):
         L, R = self.left is not None, self.right is not None
-        self.dev.begin(self.flags, self.cell_size, self.halo_out['l'] if L else None, self.halo_out['r'] if R else None)
+        flags = self.flags if flags is None else flags
+        if self.direct:
+            return self.dev.begin_direct(flags, self.cell_size, send_halo)
+        self.dev.begin(flags, self.cell_size, self.halo_out['l'] if L and send_halo else None, self.halo_out['r'] if R and send_halo else None)
 
     def phase_finish(self, flags=None, use_halo=True):
         L, R = self.left is not None, self.right is not None
-        self.dev.finish(self.flags if flags is None else flags, self.dt_min, self.dt_max,
+        flags = self.flags if flags is None else flags
+        if self.direct:
+            return self.dev.finish_direct(flags, self.dt_min, self.dt_max, use_halo)
+        self.dev.finish(flags, self.dt_min, self.dt_max,
                         self.halo_in['l'] if L and use_halo else None, self.halo_in['r'] if R and use_halo else None,
                         self.mig_out['l'] if L else None, self.mig_out['r'] if R else None)
 
-    def phase_absorb(self):
+    def phase_absorb(self, exact=False):
         L, R = self.left is not None, self.right is not None
-        self._n_owned = self.dev.absorb(self.mig_in['l'] if L else None, self.mig_in['r'] if R else None)
+        if self.direct:
+            self._n_owned = self.dev.absorb_direct(exact)
+            return
+        self._n_owned = self.dev.absorb(self.mig_in['l'] if L else None, self.mig_in['r'] if R else None, exact)
 
     @property
     def adaptive(self):
         return self.dt_min != self.dt_max and bool(self.flags & _lib.STEP_INTEGRATOR)
 
+    PHASES = ('block_list_and_halo_pack', 'halo_exchange', 'halo_unpack_pairs_finish_migrant_pack', 'migrant_exchange', 'absorb')
+
+    def profile_phases(self, enable=True):
+        """CUDA-event timing of the five phases of step() on the current stream (bench.py, N > 1)."""
+        self._phase_events = [] if enable else None
+
+    def phase_ms(self):
+        """-> {phase: mean ms per step} over the steps recorded since profile_phases(True)."""
+        ev = getattr(self, '_phase_events', None) or []
+        self.torch.cuda.synchronize()
+        out = {}
+        for k, name in enumerate(self.PHASES):
+            out[name] = float(np.mean([e[k].elapsed_time(e[k + 1]) for e in ev])) if ev else 0.0
+        return out
+
+    def _mark(self, marks):
+        if marks is not None:
+            e = self.torch.cuda.Event(enable_timing=True)
+            e.record()
+            marks.append(e)
+
     def step(self, n_steps=1):
+        rec = getattr(self, '_phase_events', None)
         for _ in range(n_steps):
+            marks = [] if rec is not None and len(rec) < 2048 else None
+            self._mark(marks)
             self.phase_begin()
+            self._mark(marks)
             self._exchange(self.halo_out, self.halo_in)
             if self.adaptive and self.world > 1:
                 self.dev.export_vmax(self.vmax)
                 self.dist.all_reduce(self.vmax, op=self.dist.ReduceOp.MAX)
                 self.dev.import_vmax(self.vmax)
+            self._mark(marks)
             self.phase_finish()
+            self._mark(marks)
             self._exchange(self.mig_out, self.mig_in)
+            self._mark(marks)
             self.phase_absorb()
+            self._mark(marks)
+            if marks is not None:
+                rec.append(marks)
 
     def settle(self):
         """Move agents that were generated outside this rank's columns to their owner (one hop), without stepping."""
-        self.dev.begin(0, self.cell_size, None, None)
+        self.phase_begin(flags=0, send_halo=False)
         self.phase_finish(flags=0, use_halo=False)
         self._exchange(self.mig_out, self.mig_in)
-        self.phase_absorb()
+        self.phase_absorb(exact=True)
 
     def export(self, dtype):
         return self.dev.export_agents(dtype)
@@ -297,14 +393,64 @@ class StripSimulation:
         return sim
 
 
+def strong_scaling_strip(model, n_total, density, rank, world, device_index, geometry='room', seed=0, cell_size=3.6, dist=None,
+                         dt_min=0.01, dt_max=0.01):
+    """Strong-scaling benchmark crowd (BASELINE configs 4 and 5): ONE square room of n_total agents split into `world` strips
+    of (almost) equal width; every rank generates the lattice columns of its own strip (``synthetic.uniform_slab``).
+    geometry: 'room' = four walls (config 5), 'room_exit' = a door in the right wall + exit hall, 11 wall segments (config 4).
+    Static exit direction field (step 1 m) over the rank's x range."""
+    import torch
+    from . import synthetic as S
+    m = int(math.ceil(math.sqrt(n_total)))
+    side = m / math.sqrt(density)
+    ix_min, iy_min = -1, -1
+    nx = int(math.floor((side + (5.0 if geometry == 'room_exit' else 0.0)) / cell_size)) + 3
+    ny = int(math.floor(side / cell_size)) + 3
+    inner = int(math.floor(side / cell_size)) + 1          # columns that hold agents initially
+    bounds = [ix_min] + [int(round(inner * g / world)) for g in range(1, world)] + [ix_min + nx]
+    x_lo = -np.inf if rank == 0 else bounds[rank] * cell_size
+    x_hi = np.inf if rank == world - 1 else bounds[rank + 1] * cell_size
+    agents, ids, _ = S.uniform_slab(n_total, model, density=density, seed=seed, x_lo=x_lo, x_hi=x_hi)
+    if geometry == 'room_exit':
+        obstacles = S.room_exit_walls(side)
+        agents['target'] = 0
+    else:
+        obstacles = S.walls_of_box(0.0, 0.0, side, side)
+    mid = MODEL_CIRCULAR if model == 'circular' else MODEL_THREE_CIRCLE
+    per_col = int(1.3 * density * cell_size * side) + 256
+    halo_cap, mig_cap = per_col, per_col
+    capacity = int(1.05 * len(agents)) + 4 * mig_cap
+    dev = CudaStripDevice(mid, capacity, device_index, stream=torch.cuda.current_stream().cuda_stream)
+    dev.upload(agents, ids)
+    dev.set_obstacles(obstacles)
+    fx0 = max(0.0, (bounds[rank] if rank else 0) * cell_size - 8.0)
+    fx1 = min(side + 5.0, (bounds[rank + 1] if rank < world - 1 else nx) * cell_size + 8.0)
+    mg, uv = S.direction_field(1.0, (fx0, 0.0, fx1, side), 'exit', point=(side + 0.15, side / 2))
+    dev.set_navigation_field(0, mg, uv)
+    sim = StripSimulation(dev, rank, world, bounds, (ix_min, iy_min, nx, ny), cell_size, halo_cap, mig_cap,
+                          torch.device('cuda', device_index), len(agents), dist=dist, dt_min=dt_min, dt_max=dt_max, model=mid)
+    sim.settle()
+    return sim
+
+
 class LocalGroup:
     """All strips of a decomposition inside ONE process (message exchange by tensor copies instead of send/recv).
     Functionally identical to one process per GPU; used to validate the strip kernels on a single device."""
 
-    def __init__(self, sims):
+    def __init__(self, sims, direct=False):
         self.sims = list(sims)
+        if direct:
+            # the one-sided exchange inside one process: every strip writes straight into its neighbours' receive buffers
+            for s in self.sims:
+                s.dev.exchange_alloc()
+            for g, s in enumerate(self.sims):
+                s.dev.connect_local(self.sims[g - 1].dev if s.left is not None else None,
+                                    self.sims[g + 1].dev if s.right is not None else None)
+                s.direct = True
 
     def _exchange(self, out_name, in_name):
+        if self.sims[0].direct:
+            return
         for g, s in enumerate(self.sims):
             if s.right is not None:
                 r = self.sims[g + 1]
@@ -313,11 +459,12 @@ class LocalGroup:
 
     def settle(self):
         for s in self.sims:
-            s.dev.begin(0, s.cell_size, None, None)
+            s.phase_begin(flags=0, send_halo=False)
+        for s in self.sims:
             s.phase_finish(flags=0, use_halo=False)
         self._exchange('mig_out', 'mig_in')
         for s in self.sims:
-            s.phase_absorb()
+            s.phase_absorb(exact=True)
 
     def step(self, n_steps=1):
         torch = self.sims[0].torch

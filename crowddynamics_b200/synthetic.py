@@ -97,6 +97,54 @@ def uniform_crowd(n, model='circular', density=1.0, seed=0, origin=(0.0, 0.0), j
     return agents, obstacles, side
 
 
+def uniform_slab(n_total, model='circular', density=1.0, seed=0, x_lo=-np.inf, x_hi=np.inf):
+    """The agents of ``uniform_crowd(n_total, ...)``'s lattice whose lattice column centre lies in [x_lo, x_hi) -- what one
+    rank of a strong-scaling strip run generates for itself (same lattice and body distributions; its own random stream).
+    Returns (agents, ids, side): ids = position of each agent in the full lattice (global agent index)."""
+    dtype = agent_type_circular if model == 'circular' else agent_type_three_circle
+    pitch = 1.0 / np.sqrt(density)
+    m = int(np.ceil(np.sqrt(n_total)))
+    side = m * pitch
+    centres = (np.arange(m) + 0.5) * pitch
+    cols = np.nonzero((centres >= x_lo) & (centres < x_hi))[0]
+    ids = (cols[:, None] * m + np.arange(m)[None, :]).reshape(-1)
+    ids = ids[ids < n_total]
+    n = len(ids)
+    rng = np.random.default_rng([seed, int(cols[0]) if len(cols) else 0])
+    agents = np.zeros(n, dtype=dtype)
+    fill_adult_bodies(agents, rng)
+    jitter = max(0.0, 0.5 * (pitch - 0.6))
+    gx, gy = ids // m, ids % m
+    pos = np.stack(((gx + 0.5) * pitch, (gy + 0.5) * pitch), axis=1) + rng.uniform(-jitter, jitter, size=(n, 2))
+    agents['position'] = pos
+    phi = rng.uniform(-np.pi, np.pi, n)
+    e = np.stack((np.cos(phi), np.sin(phi)), axis=1)
+    agents['velocity'] = e * rng.uniform(0.0, 1.3, n)[:, None]
+    agents['target_direction'] = e
+    if model != 'circular':
+        agents['orientation'] = phi
+        agents['target_orientation'] = phi
+        agents['angular_velocity'] = rng.uniform(-1.0, 1.0, n)
+        set_shoulders(agents)
+    return agents, ids.astype(np.int64), side
+
+
+def room_exit_walls(side, door_width=1.2):
+    """The 11 wall segments of ``room_with_exit`` for a room of the given side."""
+    y_lo, y_hi = side / 2 - door_width / 2, side / 2 + door_width / 2
+    t = 0.3
+    segs = [((side, 0.0), (0.0, 0.0)), ((0.0, 0.0), (0.0, side)), ((0.0, side), (side, side))]
+
+    def rect(x0, y0, x1, y1):
+        c = [(x0, y0), (x1, y0), (x1, y1), (x0, y1)]
+        return [(c[k], c[(k + 1) % 4]) for k in range(4)]
+    segs += rect(side, 0.0, side + t, y_lo) + rect(side, y_hi, side + t, side)
+    obstacles = np.zeros(len(segs), dtype=obstacle_type_linear)
+    for k, (p0, p1) in enumerate(segs):
+        obstacles[k]['p0'], obstacles[k]['p1'] = p0, p1
+    return obstacles
+
+
 def random_crowd(n, model='circular', half_width=None, seed=0):
     """The reference benchmark's own workload (core/tests/test_interactions_benchmark.py:10-33): positions uniform in
     [-sqrt(2N), sqrt(2N)]^2 (0.125 agents/m^2), overlaps allowed."""

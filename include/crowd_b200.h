@@ -228,6 +228,19 @@ int cdb_strip_finish(cdb_sim *sim, uint32_t node_flags, double dt_min, double dt
                      const double *halo_right_in, double *mig_left_out, double *mig_right_out);
 int cdb_strip_absorb(cdb_sim *sim, const double *mig_left_in, const double *mig_right_in, int64_t *n_out);
 int cdb_strip_count(cdb_sim *sim, int64_t *n_out);   /* agents currently owned (one host sync) */
+/* One-sided exchange over NVLink peer memory instead of NCCL send / recv: every sim owns its receive buffers and a flag
+ * array (cdb_strip_exchange_alloc), the neighbours map them (CUDA IPC handles between processes -- one process per GPU --
+ * or directly inside one process) and the *_direct variants of begin / finish / absorb make the producer's kernels write
+ * the halo / migrant messages straight into the consumer's buffers and publish a sequence number there, on which the
+ * consumer's kernels spin: no collective kernel, no host-side handshake per step. */
+int cdb_strip_exchange_alloc(cdb_sim *sim);
+int64_t cdb_strip_exchange_handle_bytes(void);
+int cdb_strip_exchange_handles(cdb_sim *sim, void *handles_out);
+int cdb_strip_exchange_connect_ipc(cdb_sim *sim, const void *left_handles, const void *right_handles);
+int cdb_strip_exchange_connect_local(cdb_sim *sim, cdb_sim *left, cdb_sim *right);
+int cdb_strip_begin_direct(cdb_sim *sim, uint32_t node_flags, double cell_size, int send_halo);
+int cdb_strip_finish_direct(cdb_sim *sim, uint32_t node_flags, double dt_min, double dt_max, int recv_halo);
+int cdb_strip_absorb_direct(cdb_sim *sim, int64_t *n_out);
 /* Live agents in device order: packed records rebuilt from the device state (record fields the kernels never touch are
  * zero) and their global ids. */
 int cdb_export_agents(cdb_sim *sim, void *agents, int64_t *ids, int64_t cap, int64_t *count);

@@ -21,6 +21,7 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     ok = True
+    exchange = os.environ.get('STRIP_EXCHANGE', 'nccl')      # 'peer': one-sided writes over NVLink peer memory (CUDA IPC)
     for model in ('circular', 'three_circle'):
         for dts in ((0.01, 0.01), (0.001, 0.01)):
             agents, obstacles, side = S.uniform_crowd(40000, model, density=1.0, seed=3, overlap_fraction=0.02)
@@ -28,8 +29,11 @@ def main():
             fields = [S.direction_field(0.5, (0, 0, side, side), 'swirl')]
             sim = StripSimulation.from_global(agents, obstacles, fields, 3.6, rank, world, device_index=local, dist=dist,
                                               dt_min=dts[0], dt_max=dts[1])
+            if exchange == 'peer':
+                assert sim.connect_direct(), 'CUDA IPC not available'
             sim.step(20)
             torch.cuda.synchronize()
+            dist.barrier()
             rec, ids = sim.export(agents.dtype)
             gathered = [None] * world
             dist.all_gather_object(gathered, (rec.view(np.uint8).reshape(len(rec), -1), ids))
@@ -46,8 +50,8 @@ def main():
                 err = np.abs(got['position'] - ref['position']).max()
                 good = (seen == 1).all() and err <= 1e-12
                 ok &= bool(good)
-                print('strips nccl world=%d %-12s dt=%s: owners ok=%s max |dx|=%.3e %s' % (
-                    world, model, dts, (seen == 1).all(), err, 'OK' if good else 'FAIL'), flush=True)
+                print('strips %s world=%d %-12s dt=%s: owners ok=%s max |dx|=%.3e %s' % (
+                    exchange, world, model, dts, (seen == 1).all(), err, 'OK' if good else 'FAIL'), flush=True)
     dist.barrier()
     dist.destroy_process_group()
     if rank == 0 and not ok:

@@ -124,7 +124,7 @@ class NumpyStripDevice:
         keep = ~(go_l | go_r)
         self.agents, self.ids = np.ascontiguousarray(self.agents[keep]), self.ids[keep]
 
-    def absorb(self, mig_left_in, mig_right_in):
+    def absorb(self, mig_left_in, mig_right_in, exact=False):
         for b in (mig_left_in, mig_right_in):
             if b is not None:
                 recs, ids = self._unpack(b)

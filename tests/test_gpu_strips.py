@@ -35,7 +35,8 @@ def _single(agents, obstacles, fields, steps, dt_min, dt_max):
 @pytest.mark.parametrize('model', ['circular', 'three_circle'])
 @pytest.mark.parametrize('world', [2, 3])
 @pytest.mark.parametrize('dts', [(0.01, 0.01), (0.001, 0.01)])
-def test_strips_reproduce_single_device(model, world, dts):
+@pytest.mark.parametrize('direct', [False, True], ids=['messages', 'peer-memory'])
+def test_strips_reproduce_single_device(model, world, dts, direct):
     import torch
     agents, obstacles, side = S.uniform_crowd(6000, model, density=1.0, seed=3, overlap_fraction=0.02)
     agents['velocity'] *= 6.0                  # agents cross strip borders within the horizon
@@ -44,7 +45,7 @@ def test_strips_reproduce_single_device(model, world, dts):
     ref = _single(agents, obstacles, fields, steps, *dts)
     sims = [StripSimulation.from_global(agents, obstacles, fields, 3.6, r, world, device_index=0, dt_min=dts[0], dt_max=dts[1])
             for r in range(world)]
-    group = LocalGroup(sims)
+    group = LocalGroup(sims, direct=direct)      # direct: one-sided writes into the neighbours' buffers + sequence flags
     owned0 = [set(s.export(agents.dtype)[1].tolist()) for s in sims]
     group.step(steps)
     torch.cuda.synchronize()
@@ -100,9 +101,11 @@ def _gpu_count():
 
 
 @pytest.mark.skipif(_gpu_count() < 2, reason='needs >= 2 GPUs (one process per GPU over NCCL)')
-def test_nccl_strips_one_process_per_gpu():
-    """torchrun with one rank per visible GPU (at most 4): halo + migrant exchange over NCCL, gathered result must equal
-    the single-GPU trajectory bit for bit (tests/run_strips_nccl.py)."""
+@pytest.mark.parametrize('exchange', ['nccl', 'peer'])
+def test_nccl_strips_one_process_per_gpu(exchange):
+    """torchrun with one rank per visible GPU (at most 4): halo + migrant exchange over NCCL send / recv, or by one-sided
+    writes over NVLink peer memory; the gathered result must equal the single-GPU trajectory bit for bit
+    (tests/run_strips_nccl.py)."""
     n = min(_gpu_count(), 4)
     s = socket.socket()
     s.bind(('127.0.0.1', 0))
@@ -110,6 +113,6 @@ def test_nccl_strips_one_process_per_gpu():
     s.close()
     cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', str(n), '--master-addr', '127.0.0.1',
            '--master-port', str(port), os.path.join(ROOT, 'tests', 'run_strips_nccl.py')]
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, STRIP_EXCHANGE=exchange))
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert out.stdout.count(' OK') == 4 and 'FAIL' not in out.stdout
