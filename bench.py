@@ -195,6 +195,82 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def run_hallway(args):
+    """BASELINE config 1: examples.simulations.Hallway, 50 Circular agents, 1000 update() iterations -- the launch-bound end of
+    the path.  Three ways through the boundary: (a) one resident FusedStep node per update(), dt read back every update like
+    the reference's Integrator node does (a host synchronisation per update); (b) the same 1000 iterations as ONE cdb_step
+    call (pairs of steps replayed as a CUDA graph on the sim's own stream); (c) the seven strict nodes per update.  Beside
+    them the serial C port of the reference on one host core (the numba original is ~10x slower than the port)."""
+    import torch
+    from crowddynamics_b200 import _lib, logic as L, synthetic as S
+    from crowddynamics_b200.engine import DeviceAgents
+    from crowddynamics_b200.structures import MODEL_CIRCULAR
+    from oracle import crowd_oracle as O
+    updates = 1000
+
+    def fused_nodes():
+        agents, obstacles, fields = S.hallway(seed=0)
+        sim = L.MultiAgentSimulation(agents, obstacles, fields)
+        sim.logic = L.FusedStep(sim, step=0.1)
+        sim.update()
+        t0 = time.perf_counter()
+        for _ in range(updates):
+            sim.update()
+        sim.logic.state.sync_host()
+        return time.perf_counter() - t0, agents
+
+    def one_call():
+        agents, obstacles, fields = S.hallway(seed=0)
+        dev = DeviceAgents(MODEL_CIRCULAR)
+        dev.upload(agents); dev.set_obstacles(obstacles)
+        for t, f in enumerate(fields):
+            dev.set_navigation_field(t, *f)
+        dev.step(2, _lib.STEP_ALL, CELL, 0.01, 0.01, want_dt=False)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        dev.step(updates, _lib.STEP_ALL, CELL, 0.01, 0.01, want_dt=False)
+        dev.download(agents)
+        secs = time.perf_counter() - t0
+        dev.close()
+        return secs, agents
+
+    def strict_nodes():
+        agents, obstacles, fields = S.hallway(seed=0)
+        sim = L.MultiAgentSimulation(agents, obstacles, fields)
+        sim.logic = L.hallway_logic(sim, mode='strict')
+        sim.update()
+        t0 = time.perf_counter()
+        for _ in range(updates):
+            sim.update()
+        return time.perf_counter() - t0, agents
+
+    def cpu_port():
+        agents, obstacles, fields = S.hallway(seed=0)
+        O.lib()
+        O.step(agents, obstacles, fields, CELL, 0.01, 0.01)
+        t0 = time.perf_counter()
+        for _ in range(updates):
+            O.step(agents, obstacles, fields, CELL, 0.01, 0.01)
+        return time.perf_counter() - t0, agents
+
+    out = {}
+    for name, fn in (('fused_node_per_update', fused_nodes), ('one_cdb_step_call_cuda_graphs', one_call),
+                     ('strict_seven_nodes_per_update', strict_nodes), ('cpu_port_1_core', cpu_port)):
+        secs, agents = fn()
+        out[name] = {'seconds': secs, 'updates_per_s': updates / secs, 'agent_steps_per_s': 50 * updates / secs,
+                     'us_per_update': 1e6 * secs / updates}
+    best = out['one_cdb_step_call_cuda_graphs']
+    line = {'metric': 'agent-steps/sec', 'value': best['agent_steps_per_s'], 'unit': 'agent-steps/s', 'n_gpus': 1, 'steps': updates,
+            'warmup': 2, 'ms_per_step': best['us_per_update'] * 1e-3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f64', 'data': 'synthetic',
+            'config': {'workload': 'BASELINE config 1: Hallway, 50 Circular agents, 40 x 5 m, 2 walls, 2 targets (constant +-x fields '
+                                   'instead of the FMM field), dt 0.01, 1000 updates; launch-latency bound on a GPU'},
+            'hallway': out,
+            'cpu_baseline': {'value': out['cpu_port_1_core']['agent_steps_per_s'], 'unit': 'agent-steps/s', 'cores': 1, 'kind': 'port',
+                             'sample': 'the whole workload: 1000 updates of the 50-agent Hallway, serial C port of the reference'}}
+    print(json.dumps(line), flush=True)
+
+
 def strip_parity_check(model, rank, world, local_rank, dist):
     """N > 1: before the timed run, every rank steps its strip of a small crowd over NCCL (halo + migrants + adaptive-dt
     all-reduce); rank 0 gathers the agents and compares them with a single-device run of the same crowd.
@@ -259,8 +335,9 @@ def main():
     ap.add_argument('--model', default='three_circle', choices=['circular', 'three_circle'])
     ap.add_argument('--agents', type=int, default=1000000, help='agents per GPU')
     ap.add_argument('--density', type=float, default=1.0)
-    ap.add_argument('--workload', default='room', choices=['room', 'room_exit'],
-                    help="room: walled square (configs 2/3/5); room_exit: room with a door, 11 wall segments, exit field (config 4)")
+    ap.add_argument('--workload', default='room', choices=['room', 'room_exit', 'hallway'],
+                    help="room: walled square (configs 2/3/5); room_exit: room with a door, 11 wall segments, exit field (config 4); "
+                         "hallway: BASELINE config 1 (50 agents x 1000 updates, launch-bound)")
     ap.add_argument('--cpu-agents', type=int, default=0, help='agents in the CPU baseline sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-fp64-peak', action='store_true', help='skip the DFMA peak micro-benchmark (used under ncu)')
@@ -296,6 +373,8 @@ def main():
     if world > 1:
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
     _lib.load()
+    if args.workload == 'hallway':
+        return run_hallway(args)
 
     n = args.agents
     mid = MODEL_CIRCULAR if args.model == 'circular' else MODEL_THREE_CIRCLE
@@ -514,12 +593,14 @@ def main():
         'hbm_fraction_whole_step': value / world * ALGO_BYTES[args.model] / 1e9 / peak,
     }
     if world == 1 and not args.no_cpu_baseline:
-        n_sample = args.cpu_agents or (50000 if args.model == 'three_circle' else 200000)
-        rate, secs = cpu_port_rate(args.model, n_sample, 3, args.density, threads=1)
+        # the workload itself where one step of it fits the budget (1 M agents: ~8 s per three-circle step on one core)
+        n_sample = args.cpu_agents or min(n, 1000000 if args.model == 'three_circle' else 2000000)
+        cpu_steps = 2 if n_sample * (8e-6 if args.model == 'three_circle' else 1.5e-6) > 3 else 3
+        rate, secs = cpu_port_rate(args.model, n_sample, cpu_steps, args.density, threads=1)
         line['cpu_baseline'] = {'value': rate, 'unit': 'agent-steps/s', 'cores': 1, 'kind': 'port',
-                                'sample': '%d %s agents (density %.3g /m^2) x 3 steps after 1 warm-up step, serial C '
+                                'sample': '%d %s agents (density %.3g /m^2) x %d steps after 1 warm-up step, serial C '
                                           'port of the numba reference (bit-identical on the golden vectors), %.1f s'
-                                          % (n_sample, args.model, args.density, secs),
+                                          % (n_sample, args.model, args.density, cpu_steps, secs),
                                 'host_cores': os.cpu_count()}
     print(json.dumps(line), flush=True)
     if world > 1:

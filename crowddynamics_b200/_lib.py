@@ -73,6 +73,12 @@ def _signatures(L):
         'cdb_step': (i32, [vp, u32, f64, f64, f64, i64, vp]),
         'cdb_get_time': (i32, [vp, pf64, pi64]),
         'cdb_set_graphs': (i32, [vp, i32]),
+        'cdb_snapshot_begin': (i32, [vp, pi64]),
+        'cdb_snapshot_wait': (i32, [vp, i64, C.POINTER(vp), pi64]),
+        'cdb_scalars_begin': (i32, [vp, pi64]),
+        'cdb_scalars_wait': (i32, [vp, i64, pf64, pf64, pi64, vp, i64]),
+        'cdb_set_deferred_sync': (i32, [vp, i32]),
+        'cdb_sync_count': (i64, [vp]),
         'cdb_set_variant': (i32, [vp, i32]),
         'cdb_launch_count': (i64, [vp]),
         'cdb_profile_enable': (i32, [vp, i32]),

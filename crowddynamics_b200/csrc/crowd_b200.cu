@@ -72,6 +72,9 @@ inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
 }  // namespace
 
+struct cdb_sim;
+static cudaError_t sync_stream(cdb_sim *sim);   // cudaStreamSynchronize(sim->stream), counted (cdb_sync_count)
+
 // every kernel launch of the library goes through here (counted: cdb_launch_count)
 #define LAUNCH(sim, kernel, grid, block, smem, ...)                          \
     do {                                                                     \
@@ -106,6 +109,18 @@ struct cdb_sim {
     int *d_rec_slot = nullptr;     // record index -> slot (field-masked uploads into a re-sorted state)
     int64_t rec_slot_cap = 0;
     int64_t h2d_bytes = 0, d2h_bytes = 0;   // bytes moved over PCIe by the transfer entry points (cdb_transfer_stats)
+    int64_t syncs = 0;             // blocking host synchronisations so far (cdb_sync_count)
+    // asynchronous snapshots (cdb_snapshot_* / cdb_scalars_*): side stream, two pinned slots each
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_main = nullptr, ev_snap[2] = {nullptr, nullptr}, ev_scal[2] = {nullptr, nullptr}, ev_pairs = nullptr;
+    uint8_t *d_snap[2] = {nullptr, nullptr}, *h_snap[2] = {nullptr, nullptr};
+    int64_t snap_bytes[2] = {0, 0}, snap_n[2] = {0, 0};
+    int snap_next = 0, scal_next = 0;
+    unsigned long long *d_scal = nullptr, *h_scal[2] = {nullptr, nullptr};   // [0] dt bits, [1] time_tot bits, [2] inside-domain changes, [3..] target counts
+    int64_t scal_n[2] = {0, 0};
+    bool defer_sync = false;       // cdb_set_deferred_sync: cdb_step does not wait for its own pair-count check
+    int64_t pairs_known_found = -1; int pairs_known_age = 1 << 30;
+    bool pairs_inflight = false;   // a non-blocking pair-count check has been issued and not read yet
 
     // block list
     bool lattice_fixed = false;
@@ -158,7 +173,7 @@ struct cdb_sim {
     cudaGraphExec_t graph_exec = nullptr;
     int64_t graph_launches = 0;      // kernel launches inside one replay
     uint64_t state_version = 0;      // bumped by everything that invalidates a captured graph
-    struct GraphKey { uint32_t flags; double cell_size, dt_min, dt_max; bool log; int64_t n; long long ncell, nx, ny; uint64_t version; const void *cur; } graph_key{};
+    struct GraphKey { uint32_t flags; double cell_size, dt_min, dt_max; bool log; int64_t n; long long ncell, nx, ny; uint64_t version; const void *cur, *cells; } graph_key{};
     unsigned long long seed = 0x9E3779B97F4A7C15ULL;   // Fluctuation
     unsigned long long fluct_calls = 0;               // per-node Fluctuation calls (keeps successive calls independent)
 
@@ -214,6 +229,8 @@ struct cdb_sim {
     size_t ev_used = 0;
 };
 
+static cudaError_t sync_stream(cdb_sim *sim) { sim->syncs++; return cudaStreamSynchronize(sim->stream); }
+
 namespace {
 
 int alloc_soa(Soa &s, int n_planes, int64_t capacity) {
@@ -262,7 +279,7 @@ int alloc_ghost_tail(cdb_sim *sim) {
 // pair list + contribution array for `cap` pairs (contents are per-step scratch: nothing to preserve)
 int ensure_pairs(cdb_sim *sim, int64_t cap) {
     if (cap <= sim->pb.cap && sim->pb.pairs) return CDB_OK;
-    CK(cudaStreamSynchronize(sim->stream));
+    CK(sync_stream(sim));
     CKS(dev_alloc(&sim->pb.pairs, (size_t)cap));
     CKS(dev_alloc(&sim->pb.cres, (size_t)cap * 8));
     sim->pb.cap = cap;
@@ -283,7 +300,7 @@ int ensure_cells(cdb_sim *sim, int64_t ncell) {
 
 int check_device_error(cdb_sim *sim) {
     CK(cudaMemcpyAsync(sim->h_error, sim->d_error, sizeof(int), cudaMemcpyDeviceToHost, sim->stream));
-    CK(cudaStreamSynchronize(sim->stream));
+    CK(sync_stream(sim));
     int e = *sim->h_error;
     if (e == 0) return CDB_OK;
     CK(cudaMemsetAsync(sim->d_error, 0, sizeof(int), sim->stream));
@@ -353,7 +370,7 @@ int build_block_list(cdb_sim *sim, double cell_size, bool padded_lattice = false
         LAUNCH(sim, k_bbox_init, 1, 32, 0, sim->d_bbox);
         LAUNCH(sim, k_bbox, (cdiv(n, T * 4) < 1184 ? cdiv(n, T * 4) : 1184), T, 0, sim->cur, (int)n, cs, sim->d_bbox, sim->d_error);
         CK(cudaMemcpyAsync(sim->h_bbox, sim->d_bbox, 4 * sizeof(long long), cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
+        CK(sync_stream(sim));
         CKS(check_device_error(sim));
         long long x0 = sim->h_bbox[0], x1 = sim->h_bbox[1], y0 = sim->h_bbox[2], y1 = sim->h_bbox[3];
         long long nx = x1 - x0 + 1, ny = y1 - y0 + 1;
@@ -466,7 +483,7 @@ int prepare_pairs(cdb_sim *sim) {
         sim->h_pctr[0] = sim->h_pctr[1] = sim->h_pctr[2] = 0;
     }
     if (sim->pair_cap_request > 0) return ensure_pairs(sim, sim->pair_cap_request);
-    const int64_t want = std::max<int64_t>((sim->strip ? 16 : 8) * std::max(sim->n, sim->capacity / 2), 1 << 16);
+    const int64_t want = std::max<int64_t>((sim->strip || sim->defer_sync ? 16 : 8) * std::max(sim->n, sim->capacity / 2), 1 << 16);
     if (!sim->pb.pairs || sim->pb.cap < want / 2) CKS(ensure_pairs(sim, want));
     return CDB_OK;
 }
@@ -554,16 +571,11 @@ int launch_step_kernel(cdb_sim *sim, unsigned flags, double dt_min, double dt_ma
 // Host side of the "a step whose pairs did not fit is not applied" protocol: one synchronisation; *overflow says whether
 // the most recent step found more pairs than the list holds (then the list has been grown), *dev_steps is the number of
 // integrating steps the device has really applied.
-int settle_pairs(cdb_sim *sim, bool *overflow, int64_t *dev_steps) {
-    *overflow = false;
-    if (dev_steps) *dev_steps = sim->iterations;
-    if (!sim->pairs_pending || !sim->pb.ctr) return CDB_OK;
-    CK(cudaMemcpyAsync(sim->h_pctr, sim->pb.ctr, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, sim->stream));
-    CK(cudaMemcpyAsync(sim->h_pctr + 2, sim->d_stepctr, sizeof(unsigned long long), cudaMemcpyDeviceToHost, sim->stream));
-    CK(cudaStreamSynchronize(sim->stream));
-    sim->pairs_pending = false;
+int analyze_pairs(cdb_sim *sim, bool *overflow, int64_t *dev_steps) {
     const int64_t found = (int64_t)sim->h_pctr[0];
     if (dev_steps) *dev_steps = (int64_t)sim->h_pctr[2];
+    sim->pairs_known_found = found;
+    sim->pairs_known_age = 0;
     if (found > sim->pb.cap) {
         *overflow = true;
         sim->pair_overflows++;
@@ -573,6 +585,44 @@ int settle_pairs(cdb_sim *sim, bool *overflow, int64_t *dev_steps) {
         CKS(ensure_pairs(sim, 2 * sim->pb.cap));     // the crowd is getting denser: grow before it overflows
     }
     return CDB_OK;
+}
+
+// deferred mode: pick up a check whose copy has completed since it was issued (never waits)
+int harvest_pairs(cdb_sim *sim, bool *overflow, int64_t *dev_steps) {
+    if (!sim->pairs_inflight) return CDB_OK;
+    if (cudaEventQuery(sim->ev_pairs) != cudaSuccess) { cudaGetLastError(); return CDB_OK; }
+    sim->pairs_inflight = false;
+    return analyze_pairs(sim, overflow, dev_steps);
+}
+
+int settle_pairs(cdb_sim *sim, bool *overflow, int64_t *dev_steps, bool may_defer = false) {
+    *overflow = false;
+    if (dev_steps) *dev_steps = sim->iterations;
+    if (!sim->pairs_pending || !sim->pb.ctr) return CDB_OK;
+    if (sim->defer_sync && may_defer) {
+        // Deferred mode (cdb_set_deferred_sync): do not wait for this call's own check while the list is known to have
+        // ample room -- a recent check found it at most a quarter full, and a crowd cannot get four times denser within a
+        // few steps (agents move about a centimetre per step).  The check is read once its copy has completed.
+        CKS(harvest_pairs(sim, overflow, dev_steps));
+        if (*overflow) { CK(sync_stream(sim)); sim->pairs_pending = false; sim->pairs_inflight = false; return CDB_OK; }
+        const bool safe = sim->pairs_known_found >= 0 && sim->pairs_known_found <= sim->pb.cap / 4 && sim->pairs_known_age < 16;
+        if (safe) {
+            if (!sim->pairs_inflight) {
+                CK(cudaMemcpyAsync(sim->h_pctr, sim->pb.ctr, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, sim->stream));
+                CK(cudaMemcpyAsync(sim->h_pctr + 2, sim->d_stepctr, sizeof(unsigned long long), cudaMemcpyDeviceToHost, sim->stream));
+                CK(cudaEventRecord(sim->ev_pairs, sim->stream));
+                sim->pairs_inflight = true;
+            }
+            sim->pairs_known_age++;
+            return CDB_OK;
+        }
+    }
+    if (sim->pairs_inflight) { CK(sync_stream(sim)); sim->pairs_inflight = false; }     // its slot is reused below
+    CK(cudaMemcpyAsync(sim->h_pctr, sim->pb.ctr, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, sim->stream));
+    CK(cudaMemcpyAsync(sim->h_pctr + 2, sim->d_stepctr, sizeof(unsigned long long), cudaMemcpyDeviceToHost, sim->stream));
+    CK(sync_stream(sim));
+    sim->pairs_pending = false;
+    return analyze_pairs(sim, overflow, dev_steps);
 }
 
 int launch_agent_agent(cdb_sim *sim) {
@@ -677,6 +727,15 @@ int cdb_create(int device, int model, int64_t capacity, cdb_sim **out) {
         CKS(dev_alloc(&sim->d_dt, 2));
         CKS(dev_alloc(&sim->d_dt_log, DT_LOG));
         CKS(dev_alloc(&sim->d_stepctr, 1));
+        CK(cudaStreamCreateWithFlags(&sim->side, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&sim->ev_main, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&sim->ev_pairs, cudaEventDisableTiming));
+        for (int k = 0; k < 2; ++k) {
+            CK(cudaEventCreateWithFlags(&sim->ev_snap[k], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&sim->ev_scal[k], cudaEventDisableTiming));
+            CK(cudaMallocHost((void **)&sim->h_scal[k], (2 + 1 + 64) * sizeof(unsigned long long)));
+        }
+        CKS(dev_alloc(&sim->d_scal, 2 + 1 + 64));
         CKS(dev_alloc(&sim->d_extmax, 1));
         CK(cudaMallocHost((void **)&sim->h_extmax, sizeof(unsigned long long)));
         CK(cudaMemset(sim->d_stepctr, 0, sizeof(unsigned long long)));
@@ -713,6 +772,15 @@ int cdb_destroy(cdb_sim *sim) {
         cudaFree(sim->x_halo_in[k]); cudaFree(sim->x_mig_in[k]);
     }
     cudaFree(sim->x_flags); cudaFree(sim->x_done);
+    if (sim->side) { cudaStreamSynchronize(sim->side); cudaStreamDestroy(sim->side); }
+    for (int k = 0; k < 2; ++k) {
+        if (sim->ev_snap[k]) cudaEventDestroy(sim->ev_snap[k]);
+        if (sim->ev_scal[k]) cudaEventDestroy(sim->ev_scal[k]);
+        cudaFree(sim->d_snap[k]); cudaFreeHost(sim->h_snap[k]); cudaFreeHost(sim->h_scal[k]);
+    }
+    if (sim->ev_main) cudaEventDestroy(sim->ev_main);
+    if (sim->ev_pairs) cudaEventDestroy(sim->ev_pairs);
+    cudaFree(sim->d_scal);
     cudaFree(sim->d_grid); cudaFree(sim->d_cell_count); cudaFree(sim->d_cell_start); cudaFree(sim->d_cell_fill);
     cudaFree(sim->d_cell_of_slot); cudaFree(sim->d_order_tmp); cudaFree(sim->d_order); if (sim->d_nbr_sweep != sim->d_nbr) cudaFree(sim->d_nbr_sweep); cudaFree(sim->d_nbr); cudaFree(sim->d_scan_partials);
     cudaFree(sim->d_bbox); cudaFreeHost(sim->h_bbox);
@@ -741,7 +809,7 @@ int cdb_set_stream(cdb_sim *sim, void *cuda_stream) {
     if (!sim) return fail(CDB_ERR_INVALID_VALUE, "sim is NULL");
     sim->state_version++;
     CK(cudaSetDevice(sim->device));
-    CK(cudaStreamSynchronize(sim->stream));
+    CK(sync_stream(sim));
     if (sim->own_stream) { cudaStreamDestroy(sim->stream); sim->own_stream = false; }
     sim->stream = (cudaStream_t)cuda_stream;
     return CDB_OK;
@@ -750,7 +818,7 @@ int cdb_set_stream(cdb_sim *sim, void *cuda_stream) {
 int cdb_synchronize(cdb_sim *sim) {
     if (!sim) return fail(CDB_ERR_INVALID_VALUE, "sim is NULL");
     CK(cudaSetDevice(sim->device));
-    CK(cudaStreamSynchronize(sim->stream));
+    CK(sync_stream(sim));
     return CDB_OK;
 }
 
@@ -819,7 +887,7 @@ int cdb_upload_agents_aos(cdb_sim *sim, const void *agents, int64_t n, int64_t i
     LAUNCH(sim, k_ext_max, (cdiv(n, 1024) < 1184 ? cdiv(n, 1024) : 1184), 256, 0, sim->cur, (int)n, sim->model, sim->d_extmax);
     CK(cudaMemcpyAsync(sim->h_extmax, sim->d_extmax, sizeof(unsigned long long), cudaMemcpyDeviceToHost, sim->stream));
     // the host buffer may be pageable and reused by the caller right away
-    CK(cudaStreamSynchronize(sim->stream));
+    CK(sync_stream(sim));
     {
         const unsigned long long k = *sim->h_extmax;
         const unsigned long long b = (k & 0x8000000000000000ULL) ? (k & 0x7fffffffffffffffULL) : ~k;
@@ -847,7 +915,7 @@ int cdb_download_agents_aos(cdb_sim *sim, void *agents, int64_t n, int64_t items
             const long long threads = (long long)n * m.n_words;
             LAUNCH(sim, k_fields_to_host, cdiv(threads, 256), 256, 0, sim->cur, (int)n, (uint32_t *)hm, (int)(itemsize / 4), m);
             CK(cudaGetLastError());
-            CK(cudaStreamSynchronize(sim->stream));
+            CK(sync_stream(sim));
             sim->d2h_bytes += (int64_t)bytes * n;
             return check_device_error(sim);
         }
@@ -861,7 +929,7 @@ int cdb_download_agents_aos(cdb_sim *sim, void *agents, int64_t n, int64_t items
     CK(cudaGetLastError());
     if (field_mask & CDB_F_WHOLE_RECORD) {
         CK(cudaMemcpyAsync(agents, sim->d_aos, n * itemsize, cudaMemcpyDeviceToHost, sim->stream));
-        CK(cudaStreamSynchronize(sim->stream));
+        CK(sync_stream(sim));
         return check_device_error(sim);
     }
     if (n * itemsize > sim->bounce_bytes) {
@@ -871,7 +939,7 @@ int cdb_download_agents_aos(cdb_sim *sim, void *agents, int64_t n, int64_t items
         sim->bounce_bytes = n * itemsize;
     }
     CK(cudaMemcpyAsync(sim->h_bounce, sim->d_aos, n * itemsize, cudaMemcpyDeviceToHost, sim->stream));
-    CK(cudaStreamSynchronize(sim->stream));
+    CK(sync_stream(sim));
     // merge the selected fields into the caller's records (plumbing: byte copies only); adjacent selected fields are
     // copied as one run per record (position .. force_prev are contiguous in the record)
     int nf = 0;
@@ -893,6 +961,94 @@ int cdb_download_agents_aos(cdb_sim *sim, void *agents, int64_t n, int64_t items
     return check_device_error(sim);
 }
 
+// ---- asynchronous snapshots: nothing here makes the host wait for the step that is being copied --------------------------
+int cdb_set_deferred_sync(cdb_sim *sim, int enable) {
+    if (!sim) return fail(CDB_ERR_INVALID_VALUE, "sim is NULL");
+    sim->defer_sync = enable != 0;
+    return CDB_OK;
+}
+
+int64_t cdb_sync_count(const cdb_sim *sim) { return sim ? sim->syncs : -1; }
+
+int cdb_snapshot_begin(cdb_sim *sim, int64_t *slot_out) {
+    if (!sim || !slot_out) return fail(CDB_ERR_INVALID_VALUE, "sim / slot_out is NULL");
+    CK(cudaSetDevice(sim->device));
+    if (sim->strip) return fail(CDB_ERR_STATE, "snapshots are not available in strip mode");
+    const int slot = sim->snap_next;
+    const int64_t n = sim->n, bytes = n * sim->itemsize;
+    if (bytes > sim->snap_bytes[slot]) {
+        // (re)allocation: the slot may still be in flight from an earlier snapshot
+        if (sim->ev_snap[slot]) { sim->syncs++; CK(cudaEventSynchronize(sim->ev_snap[slot])); }
+        cudaFree(sim->d_snap[slot]); cudaFreeHost(sim->h_snap[slot]);
+        sim->d_snap[slot] = nullptr; sim->h_snap[slot] = nullptr;
+        CKS(dev_alloc(&sim->d_snap[slot], (size_t)bytes + 16));
+        CK(cudaMallocHost((void **)&sim->h_snap[slot], (size_t)bytes + 16));
+        sim->snap_bytes[slot] = bytes;
+    }
+    sim->snap_n[slot] = n;
+    if (n > 0) {
+        // whole records: the uploaded image (constants, States bytes) with every mutable field, target, active and the
+        // follower fields as the device has them NOW -- what cdb_download_agents_aos + cdb_get_states + cdb_get_active return
+        CK(cudaMemcpyAsync(sim->d_snap[slot], sim->d_aos, bytes, cudaMemcpyDeviceToDevice, sim->stream));
+        const uint8_t *active = sim->d_active && sim->active_n == n ? sim->d_active : nullptr;
+        const bool states = sim->states_n == n;
+        if (sim->model == CDB_MODEL_CIRCULAR)
+            LAUNCH(sim, k_snapshot_records<0>, cdiv(n, 128), 128, 0, sim->cur, (int)n, sim->d_snap[slot], active, states ? sim->d_is_follower : nullptr,
+                   states ? sim->d_index_leader : nullptr);
+        else
+            LAUNCH(sim, k_snapshot_records<1>, cdiv(n, 128), 128, 0, sim->cur, (int)n, sim->d_snap[slot], active, states ? sim->d_is_follower : nullptr,
+                   states ? sim->d_index_leader : nullptr);
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(sim->ev_main, sim->stream));
+        CK(cudaStreamWaitEvent(sim->side, sim->ev_main, 0));
+        CK(cudaMemcpyAsync(sim->h_snap[slot], sim->d_snap[slot], bytes, cudaMemcpyDeviceToHost, sim->side));
+        sim->d2h_bytes += bytes;
+    }
+    CK(cudaEventRecord(sim->ev_snap[slot], sim->side));
+    *slot_out = slot;
+    sim->snap_next ^= 1;
+    return CDB_OK;
+}
+
+int cdb_snapshot_wait(cdb_sim *sim, int64_t slot, const void **records, int64_t *n) {
+    if (!sim || slot < 0 || slot > 1 || !records) return fail(CDB_ERR_INVALID_VALUE, "bad snapshot slot");
+    CK(cudaSetDevice(sim->device));
+    if (cudaEventQuery(sim->ev_snap[slot]) != cudaSuccess) { cudaGetLastError(); sim->syncs++; CK(cudaEventSynchronize(sim->ev_snap[slot])); }
+    *records = sim->h_snap[slot];
+    if (n) *n = sim->snap_n[slot];
+    return CDB_OK;
+}
+
+// the scalars host-side bookkeeping wants every update: dt, time_tot, InsideDomain's change count, TargetReached's counts
+int cdb_scalars_begin(cdb_sim *sim, int64_t *slot_out) {
+    if (!sim || !slot_out) return fail(CDB_ERR_INVALID_VALUE, "sim / slot_out is NULL");
+    CK(cudaSetDevice(sim->device));
+    const int slot = sim->scal_next;
+    const int64_t np = std::min<int64_t>(sim->n_polygons[CDB_POLY_TARGETS], 64);
+    CK(cudaMemcpyAsync(sim->d_scal, sim->d_dt, 2 * sizeof(double), cudaMemcpyDeviceToDevice, sim->stream));
+    if (sim->d_poly_counts) CK(cudaMemcpyAsync(sim->d_scal + 2, sim->d_poly_counts, (size_t)(1 + np) * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, sim->stream));
+    CK(cudaEventRecord(sim->ev_main, sim->stream));
+    CK(cudaStreamWaitEvent(sim->side, sim->ev_main, 0));
+    CK(cudaMemcpyAsync(sim->h_scal[slot], sim->d_scal, (size_t)(3 + np) * sizeof(unsigned long long), cudaMemcpyDeviceToHost, sim->side));
+    CK(cudaEventRecord(sim->ev_scal[slot], sim->side));
+    sim->scal_n[slot] = 3 + np;
+    *slot_out = slot;
+    sim->scal_next ^= 1;
+    return CDB_OK;
+}
+
+int cdb_scalars_wait(cdb_sim *sim, int64_t slot, double *dt, double *time_tot, int64_t *inside_changes, int64_t *target_counts, int64_t n_targets) {
+    if (!sim || slot < 0 || slot > 1) return fail(CDB_ERR_INVALID_VALUE, "bad scalars slot");
+    CK(cudaSetDevice(sim->device));
+    if (cudaEventQuery(sim->ev_scal[slot]) != cudaSuccess) { cudaGetLastError(); sim->syncs++; CK(cudaEventSynchronize(sim->ev_scal[slot])); }
+    const unsigned long long *h = sim->h_scal[slot];
+    if (dt) memcpy(dt, &h[0], sizeof(double));
+    if (time_tot) memcpy(time_tot, &h[1], sizeof(double));
+    if (inside_changes) *inside_changes = (int64_t)h[2];
+    for (int64_t p = 0; target_counts && p < n_targets && 3 + p < sim->scal_n[slot]; ++p) target_counts[p] = (int64_t)h[3 + p];
+    return CDB_OK;
+}
+
 int cdb_host_register(cdb_sim *sim, void *agents, int64_t n, int64_t itemsize) {
     if (!sim) return fail(CDB_ERR_INVALID_VALUE, "sim is NULL");
     if (!agents || n <= 0) return CDB_OK;
@@ -906,7 +1062,7 @@ int cdb_host_register(cdb_sim *sim, void *agents, int64_t n, int64_t itemsize) {
 int cdb_host_unregister(cdb_sim *sim, void *agents) {
     if (!sim) return fail(CDB_ERR_INVALID_VALUE, "sim is NULL");
     CK(cudaSetDevice(sim->device));
-    CK(cudaStreamSynchronize(sim->stream));
+    CK(sync_stream(sim));
     for (size_t k = 0; k < sim->registered.size(); ++k)
         if (sim->registered[k].first == agents) {
             cudaHostUnregister(agents);
@@ -952,14 +1108,14 @@ int cdb_upload_agents_fields(cdb_sim *sim, const void *agents, int64_t n, int64_
             CK(cudaMemsetAsync(sim->d_extmax, 0, sizeof(unsigned long long), sim->stream));
             LAUNCH(sim, k_ext_max, (cdiv(n, 1024) < 1184 ? cdiv(n, 1024) : 1184), 256, 0, sim->cur, (int)n, sim->model, sim->d_extmax);
             CK(cudaMemcpyAsync(sim->h_extmax, sim->d_extmax, sizeof(unsigned long long), cudaMemcpyDeviceToHost, sim->stream));
-            CK(cudaStreamSynchronize(sim->stream));
+            CK(sync_stream(sim));
             const unsigned long long k = *sim->h_extmax;
             const unsigned long long b = (k & 0x8000000000000000ULL) ? (k & 0x7fffffffffffffffULL) : ~k;
             double e; memcpy(&e, &b, sizeof(e));
             sim->ext_max = k == 0 ? 0.0 : e;
         }
     }
-    CK(cudaStreamSynchronize(sim->stream));      // the host buffer may be reused by the caller right away
+    CK(sync_stream(sim));      // the host buffer may be reused by the caller right away
     return CDB_OK;
 }
 
@@ -976,7 +1132,7 @@ int cdb_set_obstacles(cdb_sim *sim, const double *segments, int64_t n_segments) 
     sim->state_version++;
     if (n_segments < 0 || (n_segments > 0 && !segments)) return fail(CDB_ERR_INVALID_VALUE, "bad obstacle buffer");
     CK(cudaSetDevice(sim->device));
-    CK(cudaStreamSynchronize(sim->stream));
+    CK(sync_stream(sim));
     CKS(dev_alloc(&sim->d_obstacles, (size_t)n_segments * SEG));
     sim->n_obstacles = n_segments;
     if (n_segments) {
@@ -984,7 +1140,7 @@ int cdb_set_obstacles(cdb_sim *sim, const double *segments, int64_t n_segments) 
         CKS(dev_alloc(&raw, (size_t)n_segments * 4));
         CK(cudaMemcpy(raw, segments, n_segments * 4 * sizeof(double), cudaMemcpyHostToDevice));
         LAUNCH(sim, k_obstacle_prep, cdiv(n_segments, 128), 128, 0, raw, (int)n_segments, sim->d_obstacles);
-        CK(cudaStreamSynchronize(sim->stream));
+        CK(sync_stream(sim));
         cudaFree(raw);
     }
     return CDB_OK;
@@ -997,7 +1153,7 @@ int cdb_set_navigation_field(cdb_sim *sim, int64_t target, const double *U, cons
     if (target < 0 || target >= MAX_NAV_TARGETS) return fail(CDB_ERR_INVALID_VALUE, "target index %lld out of range [0, %d)", (long long)target, MAX_NAV_TARGETS);
     if (ny < 0 || nx < 0 || ((ny * nx) > 0 && (!U || !V))) return fail(CDB_ERR_INVALID_VALUE, "bad navigation field");
     CK(cudaSetDevice(sim->device));
-    CK(cudaStreamSynchronize(sim->stream));
+    CK(sync_stream(sim));
     if ((int64_t)sim->nav.size() <= target) sim->nav.resize(target + 1, NavField{});
     NavField &f = sim->nav[target];
     cudaFree((void *)f.U); cudaFree((void *)f.V);
@@ -1044,7 +1200,7 @@ int eikonal_solve(cdb_sim *sim, FieldScratch &f, double *T, const uint8_t *raste
         cur ^= 1;
         if ((r & 15) == 15) {
             CK(cudaMemcpyAsync(&h_changed, f.changed, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
-            CK(cudaStreamSynchronize(st));
+            CK(sync_stream(sim));
             if (h_changed == 0) { ++r; break; }
             CK(cudaMemsetAsync(f.changed, 0, sizeof(unsigned), st));
         }
@@ -1069,7 +1225,7 @@ int cdb_build_navigation_field(cdb_sim *sim, int64_t target, const double *targe
     CK(cudaSetDevice(sim->device));
     sim->state_version++;
     cudaStream_t st = sim->stream;
-    CK(cudaStreamSynchronize(st));
+    CK(sync_stream(sim));
     const long long cells = (long long)ny * nx;
     const int tiles = cdiv(nx, ET) * cdiv(ny, ET);
     const bool walls = n_obstacle_segments > 0;
@@ -1110,7 +1266,7 @@ int cdb_build_navigation_field(cdb_sim *sim, int64_t target, const double *targe
     if (distance_map_out) CK(cudaMemcpyAsync(distance_map_out, f.Tt, cells * sizeof(double), cudaMemcpyDeviceToHost, st));
     if (U_out) CK(cudaMemcpyAsync(U_out, dU, cells * sizeof(double), cudaMemcpyDeviceToHost, st));
     if (V_out) CK(cudaMemcpyAsync(V_out, dV, cells * sizeof(double), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    CK(sync_stream(sim));
     if (rounds_out) *rounds_out = rounds_t + rounds_o;
     // install as the navigation field of `target` (what cdb_set_navigation_field does with host maps)
     if ((int64_t)sim->nav.size() <= target) sim->nav.resize(target + 1, NavField{});
@@ -1127,7 +1283,7 @@ int cdb_clear_navigation(cdb_sim *sim) {
     if (!sim) return fail(CDB_ERR_INVALID_VALUE, "sim is NULL");
     sim->state_version++;
     CK(cudaSetDevice(sim->device));
-    CK(cudaStreamSynchronize(sim->stream));
+    CK(sync_stream(sim));
     for (auto &f : sim->nav) { cudaFree((void *)f.U); cudaFree((void *)f.V); }
     sim->nav.clear();
     sim->n_nav = 0;
@@ -1137,29 +1293,33 @@ int cdb_clear_navigation(cdb_sim *sim) {
 #define SIM_ENTRY()                                               \
     if (!sim) return fail(CDB_ERR_INVALID_VALUE, "sim is NULL"); \
     CK(cudaSetDevice(sim->device))
+// node-wise entry points that launch work on the buffers a captured pair of steps refers to: the graph is re-captured
+#define SIM_ENTRY_NODE() \
+    SIM_ENTRY();         \
+    sim->state_version++
 
-int cdb_reset(cdb_sim *sim) { SIM_ENTRY(); return node_reset(sim); }
+int cdb_reset(cdb_sim *sim) { SIM_ENTRY_NODE(); return node_reset(sim); }
 int cdb_set_seed(cdb_sim *sim, uint64_t seed) { SIM_ENTRY(); sim->seed = seed; sim->fluct_calls = 0; sim->state_version++; return CDB_OK; }
 int cdb_fluctuation(cdb_sim *sim) {
-    SIM_ENTRY();
+    SIM_ENTRY_NODE();
     // key the stream on a private call counter in the high half, so that node-wise calls never reuse a fused step's stream
     const unsigned long long step = (1ULL << 63) | sim->fluct_calls++;
     if (sim->n) LAUNCH(sim, k_fluctuation, cdiv(sim->n, 256), 256, 0, sim->cur, (int)sim->n, sim->model, sim->seed, step);
     CK(cudaGetLastError());
     return CDB_OK;
 }
-int cdb_navigation(cdb_sim *sim) { SIM_ENTRY(); return node_navigation(sim); }
-int cdb_orientation(cdb_sim *sim) { SIM_ENTRY(); return node_orientation(sim); }
-int cdb_adjust(cdb_sim *sim) { SIM_ENTRY(); return node_adjust(sim); }
-int cdb_agent_agent(cdb_sim *sim, double cell_size) { SIM_ENTRY(); return node_agent_agent(sim, cell_size); }
-int cdb_agent_obstacle(cdb_sim *sim) { SIM_ENTRY(); return node_agent_obstacle(sim); }
+int cdb_navigation(cdb_sim *sim) { SIM_ENTRY_NODE(); return node_navigation(sim); }
+int cdb_orientation(cdb_sim *sim) { SIM_ENTRY_NODE(); return node_orientation(sim); }
+int cdb_adjust(cdb_sim *sim) { SIM_ENTRY_NODE(); return node_adjust(sim); }
+int cdb_agent_agent(cdb_sim *sim, double cell_size) { SIM_ENTRY_NODE(); return node_agent_agent(sim, cell_size); }
+int cdb_agent_obstacle(cdb_sim *sim) { SIM_ENTRY_NODE(); return node_agent_obstacle(sim); }
 
 int cdb_integrate(cdb_sim *sim, double dt_min, double dt_max, double *dt_out) {
-    SIM_ENTRY();
+    SIM_ENTRY_NODE();
     CKS(node_integrate(sim, dt_min, dt_max));
     if (dt_out) {
         CK(cudaMemcpyAsync(sim->h_dt, sim->d_dt, 2 * sizeof(double), cudaMemcpyDeviceToHost, sim->stream));
-        CK(cudaStreamSynchronize(sim->stream));
+        CK(sync_stream(sim));
         *dt_out = sim->h_dt[0];
     }
     return CDB_OK;
@@ -1217,11 +1377,11 @@ static bool graph_usable(cdb_sim *sim, uint32_t flags, double cell_size) {
 
 static int run_graph_pair(cdb_sim *sim, uint32_t flags, double cell_size, double dt_min, double dt_max, bool log_dt) {
     const cdb_sim::GraphKey key{flags, cell_size, dt_min, dt_max, log_dt, sim->n, sim->grid.ncell, sim->grid.nx, sim->grid.ny,
-                                sim->state_version, sim->cur.p};
+                                sim->state_version, sim->cur.p, sim->d_cell_of_slot};
     const cdb_sim::GraphKey &k0 = sim->graph_key;
     const bool same = sim->graph_exec && k0.flags == key.flags && k0.cell_size == key.cell_size && k0.dt_min == key.dt_min &&
                       k0.dt_max == key.dt_max && k0.log == key.log && k0.n == key.n && k0.ncell == key.ncell && k0.nx == key.nx &&
-                      k0.ny == key.ny && k0.version == key.version && k0.cur == key.cur;
+                      k0.ny == key.ny && k0.version == key.version && k0.cur == key.cur && k0.cells == key.cells;
     if (same) {
         CK(cudaGraphLaunch(sim->graph_exec, sim->stream));
         sim->launches += sim->graph_launches;
@@ -1239,15 +1399,35 @@ static int run_graph_pair(cdb_sim *sim, uint32_t flags, double cell_size, double
         CKS(issue_step(sim, flags, cell_size, dt_min, dt_max, log_dt));
         return issue_step(sim, flags, cell_size, dt_min, dt_max, log_dt);
     }
+    // The two issue_step calls below only RECORD device work but advance the host bookkeeping (step counter, lattice age,
+    // ping-pong and index-array roles).  If the capture cannot be turned into an executable graph, that bookkeeping is put
+    // back and the two steps are issued as plain launches, so host and device never disagree about what has run.
+    const int64_t it0 = sim->iterations, n0 = sim->n, dead0 = sim->n_dead, sorted0 = sim->n_sorted;
+    const int age0 = sim->auto_lattice_age;
+    const Soa cur0 = sim->cur, alt0 = sim->alt;
+    int *const cos0 = sim->d_cell_of_slot, *const tmp0 = sim->d_order_tmp;
+    const bool perm0 = sim->perm_valid, tables0 = sim->tables_valid, pending0 = sim->pairs_pending;
+    const size_t ev0 = sim->ev_used;
     int rc = issue_step(sim, flags, cell_size, dt_min, dt_max, log_dt);
     if (rc == CDB_OK) rc = issue_step(sim, flags, cell_size, dt_min, dt_max, log_dt);
     cudaError_t e = cudaStreamEndCapture(sim->stream, &graph);
-    if (rc != CDB_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
-    if (e != cudaSuccess) return fail(CDB_ERR_CUDA, "stream capture failed: %s", cudaGetErrorString(e));
-    sim->graph_launches = sim->launches - launches0;
-    e = cudaGraphInstantiate(&sim->graph_exec, graph, 0);
-    cudaGraphDestroy(graph);
-    if (e != cudaSuccess) { sim->graph_exec = nullptr; return fail(CDB_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e)); }
+    if (rc == CDB_OK && e == cudaSuccess) {
+        sim->graph_launches = sim->launches - launches0;
+        e = cudaGraphInstantiate(&sim->graph_exec, graph, 0);
+    }
+    if (graph) cudaGraphDestroy(graph);
+    if (rc != CDB_OK || e != cudaSuccess) {
+        cudaGetLastError();
+        sim->graph_exec = nullptr;
+        sim->iterations = it0; sim->n = n0; sim->n_dead = dead0; sim->n_sorted = sorted0; sim->auto_lattice_age = age0;
+        sim->cur = cur0; sim->alt = alt0; sim->d_cell_of_slot = cos0; sim->d_order_tmp = tmp0;
+        sim->perm_valid = perm0; sim->tables_valid = tables0; sim->pairs_pending = pending0; sim->ev_used = ev0;
+        sim->launches = launches0;
+        if (rc != CDB_OK) return rc;                 // an argument / allocation error of the step itself: report it
+        sim->use_graphs = false;                     // capture or instantiation refused: plain launches from now on
+        CKS(issue_step(sim, flags, cell_size, dt_min, dt_max, log_dt));
+        return issue_step(sim, flags, cell_size, dt_min, dt_max, log_dt);
+    }
     sim->graph_key = key;
     // the capture issued the two steps on the host side (counters, buffer roles); run them
     CK(cudaGraphLaunch(sim->graph_exec, sim->stream));
@@ -1262,6 +1442,20 @@ int cdb_step(cdb_sim *sim, uint32_t flags, double cell_size, double dt_min, doub
     const bool prof_saved = sim->profiling;
     int regrown = 0;
     if (flags & CDB_STEP_AGENT_AGENT) CKS(prepare_pairs(sim));
+    if (sim->defer_sync && sim->pairs_inflight) {
+        // a check of an earlier call may have completed meanwhile: steps it reports as not applied are repeated first
+        bool overflow = false;
+        int64_t dev_steps = sim->iterations;
+        CKS(harvest_pairs(sim, &overflow, &dev_steps));
+        if (overflow) {
+            CK(sync_stream(sim));
+            const int64_t missing = sim->iterations - dev_steps;
+            sim->iterations = dev_steps;
+            sim->pairs_pending = false;
+            sim->pairs_inflight = false;
+            k -= missing;
+        }
+    }
     while (k < n_steps) {
         sim->profiling = prof_saved && sim->ev_used + 2 * PROF_EVENTS <= (size_t)PROFILE_MAX_STEPS * PROF_EVENTS;
         // a pair must not straddle the end of the dt ring (its first half would be overwritten before it is read back)
@@ -1281,7 +1475,7 @@ int cdb_step(cdb_sim *sim, uint32_t flags, double cell_size, double dt_min, doub
         if (ring_point || pairs_point || (log_dt && k == n_steps)) {
             bool overflow = false;
             int64_t dev_steps = sim->iterations;
-            CKS(settle_pairs(sim, &overflow, &dev_steps));
+            CKS(settle_pairs(sim, &overflow, &dev_steps, !log_dt && k == n_steps));
             if (overflow) {
                 if (++regrown > 16) return fail(CDB_ERR_CAPACITY, "pair list keeps overflowing");
                 // steps issued after the overflowing one ran on the unchanged state and were not applied either
@@ -1294,7 +1488,7 @@ int cdb_step(cdb_sim *sim, uint32_t flags, double cell_size, double dt_min, doub
                 const int64_t cnt = k - copied;
                 const int64_t first_slot = (sim->iterations - cnt) % DT_LOG;
                 CK(cudaMemcpyAsync(dt_out + copied, sim->d_dt_log + first_slot, cnt * sizeof(double), cudaMemcpyDeviceToHost, sim->stream));
-                CK(cudaStreamSynchronize(sim->stream));
+                CK(sync_stream(sim));
                 copied = k;
             }
         }
@@ -1324,7 +1518,7 @@ int cdb_set_pair_capacity(cdb_sim *sim, int64_t pairs) {
     if (pairs < 0) return fail(CDB_ERR_INVALID_VALUE, "negative pair capacity");
     sim->pair_cap_request = pairs;
     if (pairs > 0) {
-        CK(cudaStreamSynchronize(sim->stream));
+        CK(sync_stream(sim));
         sim->pb.cap = 0;                // shrink as well as grow: reallocate at exactly this size
         CKS(ensure_pairs(sim, pairs));
     }
@@ -1367,7 +1561,7 @@ int cdb_profile_enable(cdb_sim *sim, int enable) {
 int cdb_profile_read_phases(cdb_sim *sim, double ms[5], int64_t *steps) {
     SIM_ENTRY();
     if (!ms) return fail(CDB_ERR_INVALID_VALUE, "ms is NULL");
-    CK(cudaStreamSynchronize(sim->stream));
+    CK(sync_stream(sim));
     for (int j = 0; j < PROF_EVENTS - 1; ++j) ms[j] = 0.0;
     const size_t n = sim->ev_used / PROF_EVENTS;
     for (size_t k = 0; k < n; ++k)
@@ -1391,14 +1585,14 @@ int cdb_profile_read(cdb_sim *sim, double ms[3], int64_t *steps) {
 int cdb_get_time(cdb_sim *sim, double *time_tot, int64_t *iterations) {
     SIM_ENTRY();
     CK(cudaMemcpyAsync(sim->h_dt, sim->d_dt, 2 * sizeof(double), cudaMemcpyDeviceToHost, sim->stream));
-    CK(cudaStreamSynchronize(sim->stream));
+    CK(sync_stream(sim));
     if (time_tot) *time_tot = sim->h_dt[1];
     if (iterations) *iterations = sim->iterations;
     return check_device_error(sim);
 }
 
 // ---- block list exports -------------------------------------------------------------------------------------------
-int cdb_build_block_list(cdb_sim *sim, double cell_size) { SIM_ENTRY(); return build_block_list(sim, cell_size, false, nullptr, false); }
+int cdb_build_block_list(cdb_sim *sim, double cell_size) { SIM_ENTRY_NODE(); return build_block_list(sim, cell_size, false, nullptr, false); }
 
 // the exports describe the cell_size lattice of the reference; tables built on the finer search lattice are rebuilt
 static int coarse_tables(cdb_sim *sim) {
@@ -1424,7 +1618,7 @@ int cdb_get_cell_ids(cdb_sim *sim, int64_t *cell_of_agent, int64_t n) {
     CKS(dev_alloc(&d, (size_t)n));
     LAUNCH(sim, k_export_cell_ids, cdiv(n, 256), 256, 0, sim->cur.id, sim->perm_valid ? sim->d_order : nullptr, sim->d_cell_of_slot, (int)n, d);
     CK(cudaMemcpyAsync(cell_of_agent, d, n * sizeof(long long), cudaMemcpyDeviceToHost, sim->stream));
-    CK(cudaStreamSynchronize(sim->stream));
+    CK(sync_stream(sim));
     cudaFree(d);
     return CDB_OK;
 }
@@ -1444,7 +1638,7 @@ int cdb_get_cell_tables(cdb_sim *sim, int64_t *points_indices, int64_t n, int64_
     CK(cudaMemcpyAsync(cells_count, d, n_cells * sizeof(long long), cudaMemcpyDeviceToHost, sim->stream));
     LAUNCH(sim, k_widen, cdiv(n_cells, 256), 256, 0, sim->d_cell_start, nullptr, (int)n_cells, d);
     CK(cudaMemcpyAsync(cells_offset, d, n_cells * sizeof(long long), cudaMemcpyDeviceToHost, sim->stream));
-    CK(cudaStreamSynchronize(sim->stream));
+    CK(sync_stream(sim));
     cudaFree(d);
     return CDB_OK;
 }
@@ -1463,7 +1657,7 @@ int cdb_get_neighbor_pairs(cdb_sim *sim, int64_t *pairs, int64_t cap, int64_t *c
                                                              sim->d_cell_count, d, cap > 0 && pairs ? cap : 0, sim->d_pair_count);
     unsigned long long c = 0;
     CK(cudaMemcpyAsync(&c, sim->d_pair_count, sizeof(c), cudaMemcpyDeviceToHost, sim->stream));
-    CK(cudaStreamSynchronize(sim->stream));
+    CK(sync_stream(sim));
     *count = (int64_t)c;
     if (pairs && cap > 0) {
         int64_t m = (int64_t)c < cap ? (int64_t)c : cap;
@@ -1477,7 +1671,7 @@ int cdb_get_neighbor_pairs(cdb_sim *sim, int64_t *pairs, int64_t cap, int64_t *c
 int cdb_set_lattice(cdb_sim *sim, int64_t ix_min, int64_t iy_min, int64_t nx, int64_t ny) {
     SIM_ENTRY();
     if (nx <= 0 || ny <= 0 || (double)nx * (double)ny > 2.0e9) return fail(CDB_ERR_INVALID_VALUE, "bad lattice shape");
-    CK(cudaStreamSynchronize(sim->stream));
+    CK(sync_stream(sim));
     sim->grid = Grid{ix_min, iy_min, nx, ny, nx * ny, 0, nx - 1};
     sim->lattice_fixed = true;
     sim->tables_valid = false;
@@ -1498,7 +1692,7 @@ int cdb_set_strip(cdb_sim *sim, int64_t ix_min, int64_t iy_min, int64_t nx_owned
                   int64_t halo_cap, int64_t migrant_cap) {
     SIM_ENTRY();
     if (nx_owned <= 0 || ny <= 0 || halo_cap < 0 || migrant_cap < 0) return fail(CDB_ERR_INVALID_VALUE, "bad strip shape");
-    CK(cudaStreamSynchronize(sim->stream));
+    CK(sync_stream(sim));
     sim->strip = true;
     sim->has_left = has_left ? 1 : 0;
     sim->has_right = has_right ? 1 : 0;
@@ -1516,7 +1710,7 @@ int cdb_set_strip(cdb_sim *sim, int64_t ix_min, int64_t iy_min, int64_t nx_owned
     sim->dev_counts = true;
     sim->steps_since_refresh = 0;
     LAUNCH(sim, k_counts_set, 1, 32, 0, sim->d_counts, (int)sim->n);
-    CK(cudaStreamSynchronize(sim->stream));
+    CK(sync_stream(sim));
     return alloc_ghost_tail(sim);
 }
 
@@ -1528,7 +1722,7 @@ int cdb_set_agent_ids(cdb_sim *sim, const int64_t *ids, int64_t n) {
     CKS(dev_alloc(&d, (size_t)n));
     CK(cudaMemcpyAsync(d, ids, n * sizeof(long long), cudaMemcpyHostToDevice, sim->stream));
     LAUNCH(sim, k_set_ids, cdiv(n, 256), 256, 0, sim->cur, d, (int)n);
-    CK(cudaStreamSynchronize(sim->stream));
+    CK(sync_stream(sim));
     cudaFree(d);
     return CDB_OK;
 }
@@ -1574,15 +1768,15 @@ int cdb_strip_begin_direct(cdb_sim *sim, uint32_t flags, double cell_size, int s
     return strip_begin_impl(sim, flags, cell_size, send_halo ? sim->p_halo[0] : nullptr, send_halo ? sim->p_halo[1] : nullptr, true);
 }
 
-int cdb_strip_export_vmax(cdb_sim *sim, double *dev_vmax2) {
+int cdb_strip_export_vmax(cdb_sim *sim, double *dev_vmax4) {
     SIM_ENTRY();
-    LAUNCH(sim, k_vmax_export, 1, 32, 0, sim->d_vmax, dev_vmax2);
+    LAUNCH(sim, k_vmax_export, 1, 32, 0, sim->d_vmax, dev_vmax4);
     CK(cudaGetLastError());
     return CDB_OK;
 }
-int cdb_strip_import_vmax(cdb_sim *sim, const double *dev_vmax2) {
+int cdb_strip_import_vmax(cdb_sim *sim, const double *dev_vmax4) {
     SIM_ENTRY();
-    LAUNCH(sim, k_vmax_import, 1, 32, 0, dev_vmax2, sim->d_vmax);
+    LAUNCH(sim, k_vmax_import, 1, 32, 0, dev_vmax4, sim->d_vmax);
     CK(cudaGetLastError());
     return CDB_OK;
 }
@@ -1780,7 +1974,7 @@ int cdb_export_agents(cdb_sim *sim, void *agents, int64_t *ids, int64_t cap, int
     else LAUNCH(sim, k_export_records<1>, cdiv(sim->n, 128), 128, 0, sim->cur, (int)sim->n, d_rec, d_ids, sim->d_counters + 3);
     CK(cudaMemcpyAsync(agents, d_rec, live * sim->itemsize, cudaMemcpyDeviceToHost, sim->stream));
     CK(cudaMemcpyAsync(ids, d_ids, live * sizeof(long long), cudaMemcpyDeviceToHost, sim->stream));
-    CK(cudaStreamSynchronize(sim->stream));
+    CK(sync_stream(sim));
     cudaFree(d_rec); cudaFree(d_ids);
     return CDB_OK;
 }
@@ -1850,7 +2044,7 @@ int launch_herding(cdb_sim *sim, double sight, int64_t k, bool all_agents, doubl
         LAUNCH(sim, k_bbox_init, 1, 32, 0, sim->d_bbox);
         LAUNCH(sim, k_bbox, (cdiv(sim->n, 1024) < 1184 ? cdiv(sim->n, 1024) : 1184), 256, 0, sim->cur, (int)sim->n, sight, sim->d_bbox, sim->d_error);
         CK(cudaMemcpyAsync(sim->h_bbox, sim->d_bbox, 4 * sizeof(long long), cudaMemcpyDeviceToHost, sim->stream));
-        CK(cudaStreamSynchronize(sim->stream));
+        CK(sync_stream(sim));
         CKS(check_device_error(sim));
         const double area = (double)(sim->h_bbox[1] - sim->h_bbox[0] + 1) * (double)(sim->h_bbox[3] - sim->h_bbox[2] + 1) * sight * sight;
         const double r0 = std::sqrt(3.0 * (double)k * area / (3.141592653589793 * (double)sim->n));
@@ -1887,8 +2081,7 @@ int cdb_set_states(cdb_sim *sim, const int64_t *target, const uint8_t *is_leader
     if (sim->strip) return fail(CDB_ERR_STATE, "the collective-motion nodes are not available in strip mode");
     if (n != sim->n) return fail(CDB_ERR_INVALID_VALUE, "cdb_set_states: n = %lld but the device holds %lld agents", (long long)n, (long long)sim->n);
     CKS(ensure_states(sim, n));
-    cudaStream_t st = sim->stream;
-    CK(cudaStreamSynchronize(st));
+    CK(sync_stream(sim));
     if (n > 0) {
         if (is_follower) CK(cudaMemcpy(sim->d_is_follower, is_follower, n, cudaMemcpyHostToDevice));
         if (index_leader) CK(cudaMemcpy(sim->d_index_leader, index_leader, n * sizeof(int64_t), cudaMemcpyHostToDevice));
@@ -1903,7 +2096,7 @@ int cdb_set_states(cdb_sim *sim, const int64_t *target, const uint8_t *is_leader
         if (target) {
             CK(cudaMemcpy(sim->d_target_by_id, target, n * sizeof(int64_t), cudaMemcpyHostToDevice));
             LAUNCH(sim, k_target_scatter, cdiv(n, 256), 256, 0, sim->cur, (int)n, sim->d_target_by_id);
-            CK(cudaStreamSynchronize(st));
+            CK(sync_stream(sim));
         }
     }
     sim->states_n = n;
@@ -1917,7 +2110,7 @@ int cdb_get_states(cdb_sim *sim, int64_t *target, uint8_t *is_follower, int64_t 
     if (n != sim->n) return fail(CDB_ERR_INVALID_VALUE, "cdb_get_states: n = %lld but the device holds %lld agents", (long long)n, (long long)sim->n);
     if (n == 0) return CDB_OK;
     if (target) LAUNCH(sim, k_slot_map, cdiv(n, 256), 256, 0, sim->cur, (int)n, sim->d_slot_of_id, sim->d_target_by_id);
-    CK(cudaStreamSynchronize(sim->stream));
+    CK(sync_stream(sim));
     if (target) CK(cudaMemcpy(target, sim->d_target_by_id, n * sizeof(int64_t), cudaMemcpyDeviceToHost));
     if (is_follower) CK(cudaMemcpy(is_follower, sim->d_is_follower, n, cudaMemcpyDeviceToHost));
     if (index_leader) CK(cudaMemcpy(index_leader, sim->d_index_leader, n * sizeof(int64_t), cudaMemcpyDeviceToHost));
@@ -1934,7 +2127,7 @@ int cdb_exit_detection(cdb_sim *sim, const double *center_door, int64_t n_doors,
         LAUNCH(sim, k_exit_detection, cdiv(sim->n, 128), 128, 0, sim->cur, (int)sim->n, sim->d_doors, (int)n_doors, sim->d_obstacles, (int)sim->n_obstacles,
                detection_range, sim->d_detected, sim->d_has_detected, sim->d_is_follower, apply ? 1 : 0);
     CK(cudaGetLastError());
-    CK(cudaStreamSynchronize(sim->stream));   // center_door is the caller's (pageable) memory
+    CK(sync_stream(sim));   // center_door is the caller's (pageable) memory
     sim->detection_valid = true;
     if (apply) sim->state_version++;
     return CDB_OK;
@@ -1943,7 +2136,7 @@ int cdb_exit_detection(cdb_sim *sim, const double *center_door, int64_t n_doors,
 int cdb_get_exit_detection(cdb_sim *sim, int64_t *detected_exit, uint8_t *has_detected, int64_t n) {
     SIM_ENTRY();
     if (!sim->detection_valid || n != sim->n) return fail(CDB_ERR_STATE, "cdb_exit_detection must run first (on the same %lld agents)", (long long)sim->n);
-    CK(cudaStreamSynchronize(sim->stream));
+    CK(sync_stream(sim));
     if (n && detected_exit) CK(cudaMemcpy(detected_exit, sim->d_detected, n * sizeof(int64_t), cudaMemcpyDeviceToHost));
     if (n && has_detected) CK(cudaMemcpy(has_detected, sim->d_has_detected, n, cudaMemcpyDeviceToHost));
     return CDB_OK;
@@ -1956,7 +2149,7 @@ int cdb_nearest_neighbors(cdb_sim *sim, double sight, int64_t k, int64_t *neighb
     if (!neighbors && sim->n) return fail(CDB_ERR_INVALID_VALUE, "neighbors is NULL");
     if (sim->n == 0) return CDB_OK;
     CKS(launch_herding(sim, sight, k, true, 0.0, 0.0, false));
-    CK(cudaStreamSynchronize(sim->stream));
+    CK(sync_stream(sim));
     CKS(check_device_error(sim));
     CK(cudaMemcpy(neighbors, sim->d_knn, (size_t)sim->n * k * sizeof(int64_t), cudaMemcpyDeviceToHost));
     return CDB_OK;
@@ -1983,7 +2176,7 @@ int cdb_leader_follower_with_herding(cdb_sim *sim, double sight, int64_t size_ne
 int cdb_get_direction(cdb_sim *sim, double *direction, int64_t n) {
     SIM_ENTRY();
     if (!sim->direction_valid || n != sim->n) return fail(CDB_ERR_STATE, "no direction computed for these %lld agents", (long long)sim->n);
-    CK(cudaStreamSynchronize(sim->stream));
+    CK(sync_stream(sim));
     if (n && direction) CK(cudaMemcpy(direction, sim->d_direction, 2 * n * sizeof(double), cudaMemcpyDeviceToHost));
     return CDB_OK;
 }
@@ -2006,7 +2199,7 @@ int cdb_set_polygons(cdb_sim *sim, int which, const double *xy, const int64_t *o
         off[(size_t)p] = (int)offsets[p];
     }
     const int64_t nv = n_polygons > 0 ? offsets[n_polygons] : 0;
-    CK(cudaStreamSynchronize(sim->stream));
+    CK(sync_stream(sim));
     CKS(dev_alloc(&sim->d_poly_xy[which], (size_t)(2 * nv)));
     CKS(dev_alloc(&sim->d_poly_off[which], (size_t)n_polygons + 1));
     if (nv) CK(cudaMemcpy(sim->d_poly_xy[which], xy, 2 * nv * sizeof(double), cudaMemcpyHostToDevice));
@@ -2028,7 +2221,7 @@ int cdb_set_active(cdb_sim *sim, const uint8_t *active, int64_t n) {
     SIM_ENTRY();
     if (sim->strip) return fail(CDB_ERR_STATE, "InsideDomain is not available in strip mode");
     if (n != sim->n || (n > 0 && !active)) return fail(CDB_ERR_INVALID_VALUE, "cdb_set_active: n = %lld but the device holds %lld agents", (long long)n, (long long)sim->n);
-    CK(cudaStreamSynchronize(sim->stream));
+    CK(sync_stream(sim));
     if (n > sim->active_n || !sim->d_active) CKS(dev_alloc(&sim->d_active, (size_t)std::max<int64_t>(n, 1024)));
     if (n) CK(cudaMemcpy(sim->d_active, active, n, cudaMemcpyHostToDevice));
     sim->active_n = n;
@@ -2038,7 +2231,7 @@ int cdb_set_active(cdb_sim *sim, const uint8_t *active, int64_t n) {
 int cdb_get_active(cdb_sim *sim, uint8_t *active, int64_t n) {
     SIM_ENTRY();
     if (!sim->d_active || n != sim->active_n || n != sim->n) return fail(CDB_ERR_STATE, "cdb_set_active must describe the %lld agents on the device first", (long long)sim->n);
-    CK(cudaStreamSynchronize(sim->stream));
+    CK(sync_stream(sim));
     if (n && active) CK(cudaMemcpy(active, sim->d_active, n, cudaMemcpyDeviceToHost));
     return CDB_OK;
 }
@@ -2056,7 +2249,7 @@ int cdb_inside_domain(cdb_sim *sim, int64_t *n_changed) {
     if (n_changed) {
         unsigned long long c = 0;
         CK(cudaMemcpyAsync(&c, sim->d_poly_counts, sizeof(c), cudaMemcpyDeviceToHost, sim->stream));
-        CK(cudaStreamSynchronize(sim->stream));
+        CK(sync_stream(sim));
         *n_changed = (int64_t)c;
     }
     return CDB_OK;
@@ -2082,7 +2275,7 @@ int cdb_target_reached(cdb_sim *sim, int64_t *counts, int64_t n_polygons) {
         std::vector<unsigned long long> c((size_t)np, 0ULL);
         if (sim->n > 0) {
             CK(cudaMemcpyAsync(c.data(), sim->d_poly_counts + 1, np * sizeof(unsigned long long), cudaMemcpyDeviceToHost, sim->stream));
-            CK(cudaStreamSynchronize(sim->stream));
+            CK(sync_stream(sim));
         }
         for (int64_t p = 0; p < np; ++p) counts[p] = (int64_t)c[(size_t)p];
     }
@@ -2093,7 +2286,7 @@ int cdb_get_target_reached(cdb_sim *sim, uint8_t *reached_by, int64_t n_polygons
     SIM_ENTRY();
     if (n_polygons != sim->n_polygons[CDB_POLY_TARGETS] || n != sim->n || sim->reached_n != sim->n)
         return fail(CDB_ERR_STATE, "cdb_target_reached must run first (on the same agents and polygons)");
-    CK(cudaStreamSynchronize(sim->stream));
+    CK(sync_stream(sim));
     if (n_polygons * n > 0 && reached_by) CK(cudaMemcpy(reached_by, sim->d_reached, (size_t)(n_polygons * n), cudaMemcpyDeviceToHost));
     return CDB_OK;
 }

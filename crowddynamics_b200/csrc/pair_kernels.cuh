@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(SW_THREADS, 8) k_sweep(const SweepArgs A) {
     int t = -1;
     bool ghost = false;
     if (g < A.n) { if (g < n_own) t = g; }
-    else if (A.ghost_base >= 0) {
+    else if (A.ghost_base >= 0 && A.ghost_cells > 0) {      // no left neighbour: no ghost targets (and no cell -1 to look at)
         const int k = g - A.n;
         const int n_gl = A.cell_start[A.ghost_cells - 1] + A.cell_count[A.ghost_cells - 1] - A.ghost_base;
         if (k < n_gl) { t = A.ghost_base + k; ghost = true; }

@@ -179,16 +179,26 @@ __global__ void k_migrants_unpack(const double *__restrict__ msg, Soa s, int n_s
     s.target[slot] = (long long)src[n_planes + 1];
 }
 
+// Adaptive dt across strips: the two maxima travel as {max |v|, max v0, NaN flag of the first, NaN flag of the second}.  The
+// reference's np.max propagates NaN (integrator.py:25-60); an all_reduce(MAX) over NCCL / gloo does not promise to, so a NaN is
+// replaced by a neutral value plus a flag that survives the MAX and is turned back into NaN on import: every rank sees the
+// same dt whatever the collective does with NaN payloads.
 __global__ void k_vmax_export(const unsigned long long *vmax, double *out) {
     if (threadIdx.x == 0) {
-        out[0] = from_ordered_bits(vmax[0]);
-        out[1] = vmax[1] == 0xffffffffffffffffULL ? nan("") : (vmax[1] == 0ULL ? -__longlong_as_double(0x7ff0000000000000LL) : from_ordered_bits(vmax[1]));
+        const double ninf = -__longlong_as_double(0x7ff0000000000000LL);
+        const double a = from_ordered_bits(vmax[0]);
+        const double b = vmax[1] == 0xffffffffffffffffULL ? nan("") : (vmax[1] == 0ULL ? ninf : from_ordered_bits(vmax[1]));
+        out[0] = isnan(a) ? 0.0 : a;
+        out[1] = isnan(b) ? ninf : b;
+        out[2] = isnan(a) ? 1.0 : 0.0;
+        out[3] = isnan(b) ? 1.0 : 0.0;
     }
 }
 __global__ void k_vmax_import(const double *in, unsigned long long *vmax) {
     if (threadIdx.x == 0) {
-        vmax[0] = ordered_bits(in[0]);
-        vmax[1] = isnan(in[1]) ? 0xffffffffffffffffULL : ordered_bits(in[1]);
+        const double a = in[2] > 0.0 ? nan("") : in[0];
+        vmax[0] = ordered_bits(a);
+        vmax[1] = in[3] > 0.0 || isnan(in[1]) ? 0xffffffffffffffffULL : ordered_bits(in[1]);
     }
 }
 

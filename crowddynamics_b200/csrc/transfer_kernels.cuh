@@ -51,3 +51,38 @@ __global__ void k_slot_of_id(Soa s, int n, int *__restrict__ slot_of_id) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t < n && s.id[t] >= 0) slot_of_id[s.id[t]] = t;
 }
+
+// whole-record snapshot (cdb_snapshot_begin): `aos` already holds a copy of the uploaded image; every mutable field, the
+// States.target and -- where the device owns them -- active / is_follower / index_leader are overwritten with current values
+template <int MODEL>
+__global__ void k_snapshot_records(Soa s, int n, uint8_t *__restrict__ aos, const uint8_t *__restrict__ active,
+                                   const uint8_t *__restrict__ is_follower, const long long *__restrict__ index_leader) {
+    constexpr int ITEM = MODEL == 0 ? 228 : 316;
+    constexpr int B = MODEL == 0 ? 0 : 32;          // offset of the States block (agents.py:33-60 field order)
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n || s.id[t] < 0) return;
+    const int rec_i = s.id[t];
+    uint8_t *rb = aos + (size_t)rec_i * ITEM;
+    uint32_t *rec = reinterpret_cast<uint32_t *>(rb);
+    constexpr FieldMap fmc[] = {CIRC_FIELDS(0)};
+    constexpr FieldMap fmt[] = {CIRC_FIELDS(32), THREE_FIELDS};
+    constexpr int NF = MODEL == 0 ? N_FIELDS_CIRC : N_FIELDS_THREE;
+#pragma unroll
+    for (int f = 0; f < NF; ++f) {
+        const unsigned bit = MODEL == 0 ? fmc[f < N_FIELDS_CIRC ? f : 0].bit : fmt[f].bit;
+        if (bit == 0u) continue;
+        const int w = (MODEL == 0 ? fmc[f < N_FIELDS_CIRC ? f : 0].offset : fmt[f].offset) >> 2;
+        const int plane = MODEL == 0 ? fmc[f < N_FIELDS_CIRC ? f : 0].plane : fmt[f].plane;
+        const double v = s(plane, t);
+        rec[w] = (uint32_t)__double2loint(v);
+        rec[w + 1] = (uint32_t)__double2hiint(v);
+    }
+    const unsigned long long tv = (unsigned long long)s.target[t];      // target: i8 at byte B + 2
+    for (int b = 0; b < 8; ++b) rb[B + 2 + b] = (uint8_t)(tv >> (8 * b));
+    if (active) rb[B + 0] = active[rec_i];
+    if (is_follower) {
+        rb[B + 11] = is_follower[rec_i];
+        const unsigned long long lv = (unsigned long long)index_leader[rec_i];
+        for (int b = 0; b < 8; ++b) rb[B + 12 + b] = (uint8_t)(lv >> (8 * b));
+    }
+}

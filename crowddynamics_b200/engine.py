@@ -179,6 +179,42 @@ class DeviceAgents:
                                      int(n_steps), _ptr(dts) if want_dt and n_steps else None))
         return dts
 
+    # -- asynchronous host-visible state ---------------------------------------------------------------------------------
+    def set_deferred_sync(self, enable=True):
+        _lib.check(self.lib.cdb_set_deferred_sync(self.handle, 1 if enable else 0))
+
+    def sync_count(self):
+        """Blocking host synchronisations the library has performed for this sim so far."""
+        return int(self.lib.cdb_sync_count(self.handle))
+
+    def snapshot_begin(self):
+        """Queue a copy of the whole packed records (current device state) into a pinned host buffer; returns the slot."""
+        slot = C.c_int64()
+        _lib.check(self.lib.cdb_snapshot_begin(self.handle, C.byref(slot)))
+        return slot.value
+
+    def snapshot_wait(self, slot, dtype):
+        """-> structured array VIEW of the slot's pinned buffer (valid until the slot is reused two snapshots later)."""
+        ptr, n = C.c_void_p(), C.c_int64()
+        _lib.check(self.lib.cdb_snapshot_wait(self.handle, int(slot), C.byref(ptr), C.byref(n)))
+        if n.value == 0:
+            return np.zeros(0, dtype=dtype)
+        buf = (C.c_uint8 * (n.value * dtype.itemsize)).from_address(ptr.value)
+        return np.frombuffer(buf, dtype=dtype, count=n.value)
+
+    def scalars_begin(self):
+        slot = C.c_int64()
+        _lib.check(self.lib.cdb_scalars_begin(self.handle, C.byref(slot)))
+        return slot.value
+
+    def scalars_wait(self, slot, n_targets=0):
+        """-> (dt, time_tot, inside_domain_changes, target_counts) as they were when scalars_begin(slot) was queued."""
+        dt, tt, ch = C.c_double(), C.c_double(), C.c_int64()
+        counts = np.zeros(int(n_targets), dtype=np.int64)
+        _lib.check(self.lib.cdb_scalars_wait(self.handle, int(slot), C.byref(dt), C.byref(tt), C.byref(ch),
+                                             _ptr(counts) if n_targets else None, int(n_targets)))
+        return dt.value, tt.value, ch.value, counts
+
     def set_graphs(self, enable):
         _lib.check(self.lib.cdb_set_graphs(self.handle, 1 if enable else 0))
 

@@ -150,6 +150,7 @@ class DeviceState:
         self._active_id = None
         self._states_id = None
         self._registered = None
+        self.pending_scalars = set()   # deferred nodes waiting for this update's scalars (ScalarsSync)
 
     @property
     def dirty_host(self):
@@ -506,7 +507,7 @@ def _exterior(geom):
 class InsideDomain(LogicNode):
     """logic.py:343-357 -- sets agents not inside the domain inactive.  ``domain``: (nv, 2) vertices or a shapely Polygon;
     default ``simulation.field.domain``."""
-    _params = dict(domain=None)
+    _params = dict(domain=None, deferred=False)
 
     def __init__(self, simulation, *args, **kwargs):
         super().__init__(simulation, *args, **kwargs)
@@ -523,11 +524,21 @@ class InsideDomain(LogicNode):
         if (self.state.mode == 'strict' and self.state.upload_policy == 'always') or self.state._active_id != self.state._host_id:
             dev.set_active(agents['active'])
             self.state._active_id = self.state._host_id
+        if self.deferred and self.state.mode == 'resident':
+            # no read-back now: the change count of THIS update is collected by the tree's scalar snapshot one update later
+            dev.inside_domain(want_count=False)
+            self.state.pending_scalars.add(self)
+            self.state.dirty_active = True
+            return
         self.simulation.data['inactive'] += dev.inside_domain()
         if self.state.mode == 'strict':
             agents['active'] = dev.get_active()
         else:
             self.state.dirty_active = True
+
+    def collect(self, scalars):
+        """deferred mode: ``scalars`` = (dt, time_tot, inside changes, target counts) of the update before"""
+        self.simulation.data['inactive'] += int(scalars[2])
 
 
 class TargetReached(LogicNode):
@@ -535,7 +546,7 @@ class TargetReached(LogicNode):
     (``simulation.data['target_<i>']``).  ``polygons``: list of (nv, 2) vertex arrays / shapely Polygons, or None for an index
     to be skipped; default ``simulation.field.targets`` (non-polygon targets are skipped, as in the reference)."""
     prefix = 'target_{index}'
-    _params = dict(polygons=None)
+    _params = dict(polygons=None, deferred=False)
 
     def __init__(self, simulation, *args, **kwargs):
         super().__init__(simulation, *args, **kwargs)
@@ -564,7 +575,15 @@ class TargetReached(LogicNode):
         if self._sent_to is not dev:
             dev.set_polygons(_lib.POLY_TARGETS, self._polys)
             self._sent_to = dev
+        if self.deferred and self.state.mode == 'resident':
+            dev.target_reached(len(self._polys), want_counts=False)
+            self.state.pending_scalars.add(self)
+            return
         for name, count in zip(self.names, dev.target_reached(len(self._polys))):
+            self.simulation.data[name] = int(count)
+
+    def collect(self, scalars):
+        for name, count in zip(self.names, scalars[3]):
             self.simulation.data[name] = int(count)
 
 
@@ -573,7 +592,7 @@ class FusedStep(LogicNode):
     agent-agent -> agent-obstacle -> integrator -> reset (post-order of examples/simulations.py:123-136), resident on
     the device.  ``steps_per_update`` > 1 advances several iterations per call."""
     _params = dict(dt_min=0.01, dt_max=0.01, cell_size=3.6, step=0.1, radius=0.5, strength=0.3, steps_per_update=1,
-                   navigation=True, fluctuation=False, seed=None, sync_every_update=False)
+                   navigation=True, fluctuation=False, seed=None, sync_every_update=False, deferred=False)
 
     def __init__(self, simulation, *args, **kwargs):
         kwargs.setdefault('mode', 'resident')
@@ -593,6 +612,16 @@ class FusedStep(LogicNode):
             if self.seed is not None and getattr(self.state, '_seed', None) != self.seed:
                 dev.set_seed(self.seed)
                 self.state._seed = self.seed
+        if self.deferred and self.state.mode == 'resident':
+            # nothing is read back here: simulation.data['dt'] / ['time_tot'] follow one update later (collect), the
+            # library does not wait for its own bookkeeping either (cdb_set_deferred_sync)
+            if not getattr(self.state, '_deferred_on', False):
+                dev.set_deferred_sync(True)
+                self.state._deferred_on = True
+            dev.step(self.steps_per_update, flags, self.cell_size, self.dt_min, self.dt_max, want_dt=False)
+            self.state.dev_ahead |= _lib.F_ALL_MUTABLE
+            self.state.pending_scalars.add(self)
+            return
         dts = dev.step(self.steps_per_update, flags, self.cell_size, self.dt_min, self.dt_max)
         self.state.dev_ahead |= _lib.F_ALL_MUTABLE
         if len(dts):
@@ -600,6 +629,92 @@ class FusedStep(LogicNode):
             self.simulation.data['time_tot'] += float(dts.sum())
         if self.sync_every_update or self.state.mode == 'strict':
             self.state.sync_host()
+
+
+    def collect(self, scalars):
+        self.simulation.data['dt'] = float(scalars[0])
+        self.simulation.data['time_tot'] = float(scalars[1])
+
+
+class ScalarsSync(LogicNode):
+    """Last node of a resident tree whose nodes run ``deferred``: queues ONE small asynchronous copy of this update's
+    scalars (dt, time_tot, InsideDomain's change count, TargetReached's counts) and hands the copy queued by the PREVIOUS
+    update -- complete by now -- to the nodes that asked for it.  ``simulation.data`` therefore trails the device by one
+    update and no node ever waits; ``flush()`` (or ``DeviceState.sync_host()``) settles the last update."""
+
+    def update(self):
+        st = self.state
+        if st.dev is None:
+            return
+        prev = getattr(st, '_scalar_slot', None)
+        if prev is not None:
+            self._deliver(prev)
+        st._scalar_slot = (st.dev.scalars_begin(), tuple(st.pending_scalars))
+        st.pending_scalars.clear()
+
+    def _deliver(self, prev):
+        slot, nodes = prev
+        n_targets = max([len(getattr(n, '_polys', ())) for n in nodes] + [0])
+        scalars = self.state.dev.scalars_wait(slot, n_targets)
+        for node in nodes:
+            node.collect(scalars)
+
+    def flush(self):
+        prev = getattr(self.state, '_scalar_slot', None)
+        if prev is not None:
+            self._deliver(prev)
+            self.state._scalar_slot = None
+
+
+class SaveSimulationData(LogicNode):
+    """logic.py:266-337 (+ io.py:19-45 ``save_npy``): every update the agents array goes into a buffer, and when
+    ``save_condition(simulation)`` holds the buffer is stacked and written to ``<directory>/agents_<index>.npy``.
+
+    The reference appends ``simulation.agents.array`` itself (a reference to the one live array, so a dumped file holds
+    copies of the LAST state -- evidently a bug); the evident intent, one record array per update, is what is stored here.
+    Resident mode: the array is not downloaded synchronously.  Each update queues an asynchronous snapshot of the whole
+    packed records (``cdb_snapshot_begin``: device-side copy, then D2H on a side stream into one of two pinned buffers) and
+    collects the snapshot queued one update earlier, which has arrived by then; only an update that dumps waits for its own
+    snapshot.  Strict mode (host array always coherent) copies the host array like the reference."""
+    _params = dict(save_condition=None, base_directory='.', save_directory='simulation', basename='agents')
+
+    def __init__(self, simulation, *args, **kwargs):
+        super().__init__(simulation, *args, **kwargs)
+        import os
+        self.full_path = os.path.join(os.path.abspath(self.base_directory), self.save_directory)
+        os.makedirs(self.full_path, exist_ok=True)
+        self.buffer = []
+        self.index = 0
+        self._slot = None
+        self.files = []
+
+    def _collect(self):
+        if self._slot is not None:
+            view = self.state.dev.snapshot_wait(self._slot, self.state.agents.dtype)
+            self.buffer.append(np.array(view))         # out of the pinned slot before it is reused
+            self._slot = None
+
+    def update(self):
+        import os
+        save = bool(self.save_condition(self.simulation)) if self.save_condition is not None else False
+        if self.state.mode == 'resident' and self.state.dev is not None:
+            self._collect()
+            self._slot = self.state.dev.snapshot_begin()
+            if save:
+                self._collect()
+        else:
+            self.buffer.append(self.state.agents.copy())
+        if save and self.buffer:
+            path = os.path.join(self.full_path, '%s_%d.npy' % (self.basename, self.index))
+            np.save(path, np.vstack(self.buffer))
+            self.files.append(path)
+            self.buffer.clear()
+            self.index += 1
+
+    def flush(self):
+        """collect the snapshot still in flight (end of the run)"""
+        if self.state.mode == 'resident' and self.state.dev is not None:
+            self._collect()
 
 
 class MultiAgentSimulation:

@@ -194,7 +194,7 @@ class StripSimulation:
         self.halo_in = {s: buf(halo_doubles) for s in ('l', 'r')}
         self.mig_out = {s: buf(mig_doubles) for s in ('l', 'r')}
         self.mig_in = {s: buf(mig_doubles) for s in ('l', 'r')}
-        self.vmax = buf(2)
+        self.vmax = buf(4)           # {max |v|, max v0, NaN flags of the two}: see k_vmax_export
         self._n_owned = n_owned
         self.direct = False          # True: halo / migrants travel by one-sided writes into the neighbours' buffers
 
@@ -475,9 +475,9 @@ class LocalGroup:
             if self.sims[0].adaptive and len(self.sims) > 1:
                 for s in self.sims:
                     s.dev.export_vmax(s.vmax)
-                v = torch.stack([s.vmax for s in self.sims])
-                # NaN-propagating maximum, like np.max in the reference's adaptive_timestep
-                m = torch.where(torch.isnan(v).any(0), torch.full_like(v[0], float('nan')), v.max(0).values)
+                # plain maximum, like the all_reduce(MAX) of the multi-process path: NaN (np.max in the reference's
+                # adaptive_timestep propagates it) travels as a flag, see k_vmax_export
+                m = torch.stack([s.vmax for s in self.sims]).max(0).values
                 for s in self.sims:
                     s.vmax.copy_(m)
                     s.dev.import_vmax(s.vmax)

@@ -152,6 +152,24 @@ int cdb_get_time(cdb_sim *sim, double *time_tot, int64_t *iterations);
  * not in strip mode).  Results are identical either way; this only removes launch latency for small crowds. */
 int cdb_set_graphs(cdb_sim *sim, int enable);
 
+/* ---- asynchronous host-visible state (SaveSimulationData, logic.py:266-337 + io.py:19-45; the per-update scalars of
+ * Integrator / InsideDomain / TargetReached, logic.py:71-75,343-387) -- a fully resident tree never waits for the device:
+ *   cdb_snapshot_begin   queues, behind the work already issued, a copy of the WHOLE packed records (as
+ *                        cdb_download_agents_aos + cdb_get_states + cdb_get_active would return them) into one of two pinned
+ *                        host buffers, on a side stream; returns at once with the slot;
+ *   cdb_snapshot_wait    pointer to that slot's records; blocks only if its copy has not finished (one update later it has);
+ *   cdb_scalars_begin / cdb_scalars_wait   the same for {dt, time_tot, InsideDomain change count, TargetReached counts};
+ *   cdb_set_deferred_sync  lets cdb_step return without waiting for its own pair-list check while the list is at most a
+ *                        quarter full (see cdb_set_pair_capacity); the check is read when a later call finds it complete;
+ *   cdb_sync_count       blocking host synchronisations the library has performed so far (the tests count them). */
+int cdb_snapshot_begin(cdb_sim *sim, int64_t *slot_out);
+int cdb_snapshot_wait(cdb_sim *sim, int64_t slot, const void **records, int64_t *n);
+int cdb_scalars_begin(cdb_sim *sim, int64_t *slot_out);
+int cdb_scalars_wait(cdb_sim *sim, int64_t slot, double *dt, double *time_tot, int64_t *inside_changes, int64_t *target_counts,
+                     int64_t n_targets);
+int cdb_set_deferred_sync(cdb_sim *sim, int enable);
+int64_t cdb_sync_count(const cdb_sim *sim);
+
 /* ---- instrumentation (no reference counterpart) -------------------------------------------------------------------- */
 /* agent-agent kernel variant:
  *   3 (default) = every unordered pair of the block list classified and evaluated ONCE, as the reference's pair loop does
@@ -215,15 +233,16 @@ int64_t cdb_migrant_buffer_doubles(const cdb_sim *sim);
 /* One strip step is split around the two exchanges:
  *   begin   block list of the owned agents; packs the first / last owned cell column (neighbour records + per-cell
  *           counts) into halo_left_out / halo_right_out (NULL where there is no neighbour)
- *   -- caller exchanges halos, and MAX-reduces the two doubles of export_vmax across ranks when dt_min != dt_max --
+ *   -- caller exchanges halos, and MAX-reduces the FOUR doubles of export_vmax {max |v|, max v0, NaN flag, NaN flag}
+ *      across ranks when dt_min != dt_max (NaN travels as a flag: a MAX collective need not propagate it) --
  *   finish  installs the received ghost columns, runs the fused step kernel on the owned agents, then packs the agents
  *           that left the strip into mig_left_out / mig_right_out
  *   -- caller exchanges migrants --
  *   absorb  appends the received migrants.  The exact agent counts stay on the device: the host keeps upper bounds for its
  *           launch sizes and synchronises only every 16th step -- or when n_out is non-NULL (*n_out = agents now owned). */
 int cdb_strip_begin(cdb_sim *sim, uint32_t node_flags, double cell_size, double *halo_left_out, double *halo_right_out);
-int cdb_strip_export_vmax(cdb_sim *sim, double *dev_vmax2);
-int cdb_strip_import_vmax(cdb_sim *sim, const double *dev_vmax2);
+int cdb_strip_export_vmax(cdb_sim *sim, double *dev_vmax4);
+int cdb_strip_import_vmax(cdb_sim *sim, const double *dev_vmax4);
 int cdb_strip_finish(cdb_sim *sim, uint32_t node_flags, double dt_min, double dt_max, const double *halo_left_in,
                      const double *halo_right_in, double *mig_left_out, double *mig_right_out);
 int cdb_strip_absorb(cdb_sim *sim, const double *mig_left_in, const double *mig_right_in, int64_t *n_out);

@@ -76,10 +76,13 @@ class NumpyStripDevice:
                                self.agents['target_velocity'].max() if len(v) else -np.inf])
 
     def export_vmax(self, buf):
-        buf.numpy()[:] = self._vmax
+        # {max |v|, max v0, NaN flags}: NaN travels as a flag because all_reduce(MAX) need not propagate it (k_vmax_export)
+        v = self._vmax
+        buf.numpy()[:] = [0.0 if np.isnan(v[0]) else v[0], -np.inf if np.isnan(v[1]) else v[1], float(np.isnan(v[0])), float(np.isnan(v[1]))]
 
     def import_vmax(self, buf):
-        self._vmax = buf.numpy().copy()
+        b = buf.numpy()
+        self._vmax = np.array([np.nan if b[2] > 0 else b[0], np.nan if b[3] > 0 else b[1]])
 
     def finish(self, flags, dt_min, dt_max, halo_left_in, halo_right_in, mig_left_out, mig_right_out):
         ghosts = [self._unpack(b) for b in (halo_left_in, halo_right_in) if b is not None]

@@ -98,3 +98,49 @@ def test_errors():
     dev.set_active(np.ones(100, dtype=bool))
     assert dev.inside_domain() == 100 - sum(O.point_in_polygon([(0, 0), (1, 0), (1, 1)], *p) for p in agents['position'])
     assert list(dev.target_reached(0)) == []
+
+
+# ---- a fully resident tree never waits for the device (SaveSimulationData, deferred counters) ----------------------------------
+def test_resident_tree_with_io_nodes_never_blocks(tmp_path):
+    """FusedStep + InsideDomain + TargetReached + SaveSimulationData, all resident and deferred: in steady state an update
+    performs ZERO blocking host synchronisations (counted inside the library), the saved chunks equal the oracle trajectory
+    update by update, and the counters equal the oracle's once flushed."""
+    from crowddynamics_b200 import logic as L
+    agents, obstacles, fields = S.hallway(seed=4)
+    domain = np.array([(1.0, -1.0), (39.0, -1.0), (39.0, 6.0), (1.0, 6.0)])       # agents walk out of it at both ends
+    goal = np.array([(30.0, -1.0), (41.0, -1.0), (41.0, 6.0), (30.0, 6.0)])
+    ref = agents.copy()
+    sim = L.MultiAgentSimulation(agents, obstacles, fields, domain=domain)
+    updates, every = 60, 25
+    step = L.FusedStep(sim, step=0.1, deferred=True)
+    inside = L.InsideDomain(sim, deferred=True)
+    reached = L.TargetReached(sim, polygons=[goal], deferred=True)
+    saver = L.SaveSimulationData(sim, save_condition=lambda s: (s.data['iterations'] + 1) % every == 0, base_directory=str(tmp_path),
+                                 save_directory='run')
+    scal = L.ScalarsSync(sim)
+    sim.logic = scal << (saver << (reached << (inside << step)))
+    assert [n.name for n in L.post_order_iter(sim.logic.root)] == ['FusedStep', 'InsideDomain', 'TargetReached', 'SaveSimulationData', 'ScalarsSync']
+    syncs, traj, inactive_ref, reached_ref = [], [], 0, np.zeros(len(ref), dtype=bool)
+    act = ref['active'].copy()
+    for it in range(updates):
+        before = sim.logic.state.dev.sync_count() if sim.logic.state.dev is not None else None
+        sim.update()
+        if before is not None:
+            syncs.append(sim.logic.state.dev.sync_count() - before)
+        O.step(ref, obstacles, fields, 3.6, 0.01, 0.01)
+        inactive_ref += O.inside_domain(ref, domain)
+        O.target_reached(ref, goal, reached_ref)
+        traj.append(ref.copy())
+    dumping = [(it + 1) % every == 0 for it in range(1, updates)]
+    steady = [s for s, d in zip(syncs, dumping) if not d][5:]
+    assert steady and max(steady) == 0, syncs                     # nothing waits outside the dumping updates
+    saver.flush(); scal.flush()
+    assert sim.data['inactive'] == inactive_ref and sim.data['target_0'] == int(reached_ref.sum())
+    assert abs(sim.data['time_tot'] - 0.01 * updates) < 1e-12
+    assert len(saver.files) == updates // every
+    saved = np.concatenate([np.load(f) for f in saver.files] + ([np.vstack(saver.buffer)] if saver.buffer else []))
+    assert saved.shape == (updates, len(ref))
+    for it in range(updates):
+        assert np.abs(saved[it]['position'] - traj[it]['position']).max() <= 1e-9, it
+        assert (saved[it]['active'] == traj[it]['active']).all(), it
+        assert (saved[it]['radius'] == ref['radius']).all()

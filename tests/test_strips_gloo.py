@@ -72,6 +72,35 @@ def test_two_rank_strips_match_single_domain(tmp_path, model, dts):
     assert np.abs(got['velocity'] - ref['velocity']).max() <= 1e-7
 
 
+def _nan_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from strip_mock import NumpyStripDevice
+    agents, obstacles, side = S.uniform_crowd(400, 'circular', density=1.0, seed=2)
+    agents['velocity'][np.argmin(agents['position'][:, 0])] = np.nan          # owned by rank 0 only
+    sim = StripSimulation.from_global(agents, obstacles, [], 3.6, rank, world, dist=dist, dt_min=0.001, dt_max=0.01,
+                                      make_device=lambda m, cap: NumpyStripDevice(m, cap), tensor_device=torch.device('cpu'))
+    sim.phase_begin()
+    sim.dev.export_vmax(sim.vmax)
+    local = sim.vmax.numpy().copy()
+    dist.all_reduce(sim.vmax, op=dist.ReduceOp.MAX)
+    sim.dev.import_vmax(sim.vmax)
+    np.savez(os.path.join(out_dir, 'nan%d.npz' % rank), local=local, merged=sim.dev._vmax)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_nan_velocity_reaches_every_rank(tmp_path):
+    """np.max in the reference's adaptive_timestep propagates NaN (integrator.py:25-60); all_reduce(MAX) does not promise to.
+    The exchanged vector carries NaN as a flag (k_vmax_export / strip_mock.export_vmax), so both ranks end up with NaN."""
+    port = _free_port()
+    mp.spawn(_nan_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    d0, d1 = (np.load(os.path.join(str(tmp_path), 'nan%d.npz' % r)) for r in range(2))
+    assert d0['local'][2] == 1.0 and d1['local'][2] == 0.0 and not np.isnan(d0['local']).any()
+    assert np.isnan(d0['merged'][0]) and np.isnan(d1['merged'][0])
+    assert d0['merged'][1] == d1['merged'][1] and np.isfinite(d0['merged'][1])
+
+
 def test_partition_helpers():
     b = partition_columns(-3, 20, 4)
     assert b[0] == -3 and b[-1] == 17 and all(b[i] < b[i + 1] for i in range(4))
