@@ -352,6 +352,10 @@ def main():
                     help='N > 1: halo / migrant exchange by one-sided writes over NVLink peer memory (CUDA IPC; falls back to '
                          'NCCL send/recv when IPC is unavailable) or by NCCL send/recv')
     ap.add_argument('--refinement', type=int, default=0, help='search lattice: 0 automatic (cell_size / 2 where valid), 1 cell_size')
+    ap.add_argument('--rebuild-max', type=int, default=16,
+                    help='N = 1: rebuild the block list at most every this many steps (resident-order steps, include/crowd_b200.h); '
+                         '1 = rebuild at every step like the reference')
+    ap.add_argument('--skin', type=float, default=0.10, help='widening of the search cells that the kept block list relies on')
     ap.add_argument('--variant', type=int, default=3, help='agent-agent kernel variant (3 once-per-pair, 2 both-sides fused kernel)')
     args = ap.parse_args()
 
@@ -407,6 +411,7 @@ def main():
         dev.set_stream(torch.cuda.current_stream().cuda_stream)
         dev.set_variant(args.variant)
         dev.set_search_refinement(args.refinement)
+        dev.set_rebuild_policy(args.skin, args.rebuild_max)
         dev.set_obstacles(obstacles)
         field_build = None
         if args.workload == 'room_exit' and args.field_step > 0:
@@ -456,6 +461,7 @@ def main():
     clocks = sampler.stop(t_begin, time.time()) if rank == 0 else None
     ms = ev0.elapsed_time(ev1)
     launches = dev.launch_count() - launches0
+    rebuild_stats = dev.rebuild_stats() if world == 1 else None
     ph = dev.profile_read_phases()       # pre + block list, pair sweep, pair evaluation, step kernel, post, steps
     prof = (ph[0], ph[1] + ph[2] + ph[3], ph[4], ph[5])
     dev.profile(False)
@@ -589,6 +595,8 @@ def main():
         'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic', 'config': workload_config(args, n, world),
         'gpu_launches': launches, 'clocks': clocks, 'roofline': roofline, 'roofline_fp64': fp64, 'e2e': e2e,
         'e2e_variants': e2e_variants, 'field_build': field_build if world == 1 else None, 'strip_parity': strip_parity,
+        'block_list_policy': ({'skin_fraction': args.skin, 'max_interval': args.rebuild_max, 'since_upload': rebuild_stats} if world == 1 else
+                              'rebuilt at every step (strips)'),
         'strip_phase_ms_rank0': exchange_ms, 'strip_exchange': exchange if world > 1 else None,
         'hbm_fraction_whole_step': value / world * ALGO_BYTES[args.model] / 1e9 / peak,
     }

@@ -121,6 +121,7 @@ struct cdb_sim {
     bool defer_sync = false;       // cdb_set_deferred_sync: cdb_step does not wait for its own pair-count check
     int64_t pairs_known_found = -1; int pairs_known_age = 1 << 30;
     bool pairs_inflight = false;   // a non-blocking pair-count check has been issued and not read yet
+    int64_t iterations_at_check = 0;   // sim->iterations when that check was queued
 
     // block list
     bool lattice_fixed = false;
@@ -130,6 +131,7 @@ struct cdb_sim {
     double cell_size_lattice = 0.0;
     int fine = 1;                    // the current tables bin on cell_size / fine (1, or 2: the twice finer search lattice)
     int fine_lattice = 1;            // refinement the kept padded lattice was derived for
+    double scale_lattice = 1.0;      // ... and the widening of its cells (resident-order steps)
     int fine_request = 0;            // cdb_set_search_refinement: 0 automatic, 1 / 2 forced (2 only where it is valid)
     double ext_max = 1e300;          // bound on any agent's radius / body extent (k_ext_max at upload)
     unsigned long long *d_extmax = nullptr, *h_extmax = nullptr;
@@ -144,12 +146,30 @@ struct cdb_sim {
     // once-per-pair evaluation (variant 3, pair_kernels.cuh)
     PairBuf pb{};                    // device pointers + capacity
     double2 *d_par = nullptr;        // {-mass * k_soc, tau_0} in cell order (+ ghost tail)
-    unsigned long long *h_pctr = nullptr;   // pinned: [0] pairs found by the last step, [1] entries allocated, [2] device step counter
+    unsigned long long *h_pctr = nullptr;   // pinned: [0] pairs found by the last step, [1] entries allocated, [2] device step counter,
+                                            // [3] bits of ChainState::disp_last
     bool pairs_pending = false;      // steps were issued whose pair count has not been checked yet
     int64_t pair_cap_request = 0;    // cdb_set_pair_capacity (0: automatic)
     int64_t pair_overflows = 0;      // steps that had to be repeated after growing the list
     long long *d_bbox = nullptr;     // min ix, max ix, min iy, max iy
     long long *h_bbox = nullptr;     // pinned
+
+    // resident-order steps (fused steps of variant 3 on one device, see ChainState in kernels.cuh): the block list is rebuilt
+    // every `rebuild_every` steps only; in between the agents keep their slots and the step works in place
+    bool chain_enabled = true;       // cdb_set_rebuild_policy
+    double skin_frac = 0.10;         // search cells are (1 + skin_frac) * cell_size / fine wide
+    int rebuild_max = 16;            // upper bound of the rebuild interval (1: rebuild every step, the round-1 behaviour)
+    int rebuild_every = 1;           // current interval, adapted to the observed per-step displacement
+    int since_rebuild = 0;           // steps issued on the current block list
+    bool chain_step = false;         // the step being issued runs in resident-order mode (set by issue_step)
+    bool chain_inplace = false;      // ... on the kept order, in place
+    bool chain_valid = false;        // `cur` is in the slot order of the tables; records and ChainState describe it
+    double chain_cell_size = 0.0, chain_scale = 1.0;
+    uint64_t chain_version = 0;      // state_version the kept order belongs to (uploads, node-wise calls ... end it)
+    int64_t chain_min_agents = 16384;   // smaller crowds are launch-bound: they keep the CUDA-graph path
+    int64_t chain_rebuilds = 0, chain_kept = 0, chain_stale = 0;   // statistics (cdb_get_rebuild_stats)
+    ChainState *d_chain = nullptr;
+    double drift_limit = 0.0;        // of the current block list: (coverage of the search cells - interaction range) / 2
 
     // obstacles / navigation
     double *d_obstacles = nullptr;
@@ -340,9 +360,12 @@ int search_refinement(const cdb_sim *sim, double cell_size) {
 }
 
 int build_block_list(cdb_sim *sim, double cell_size, bool padded_lattice = false, unsigned long long *vmax = nullptr, bool physical = true,
-                     int fine = 1) {
+                     int fine = 1, double scale = 1.0) {
     if (!(cell_size > 0.0) || !std::isfinite(cell_size)) return fail(CDB_ERR_INVALID_VALUE, "cell_size must be > 0");
-    const double cs = cell_size / fine;          // bin size of the search lattice
+    // bin size of the search lattice; scale > 1 (resident-order steps): wider cells, so that the list stays complete while the
+    // agents drift -- the pair set is decided by distances, not by the lattice, whenever 3 + 2 max R < cell_size
+    const double cs = cell_size * scale / fine;
+    sim->chain_valid = false;                    // whoever rebuilds the tables ends a run of resident-order steps
     const int64_t n = sim->n;                   // slots in use, including the ones vacated by migrants (upper bound with dev_counts)
     const int64_t live = sim->dev_counts ? sim->n : sim->n - sim->n_dead;
     const int *slots_dev = sim->dev_counts ? &sim->d_counts->slots : nullptr;
@@ -363,7 +386,7 @@ int build_block_list(cdb_sim *sim, double cell_size, bool padded_lattice = false
     // next steps -- cells stay anchored at multiples of cell_size and agents that leave the lattice are binned into its
     // border cells (adjacency is preserved by clamping), so neighbour sets and forces do not depend on this choice.
     const bool reuse = padded_lattice && sim->auto_lattice_valid && sim->cell_size_lattice == cell_size && sim->fine_lattice == fine &&
-                       sim->auto_lattice_age < 64;
+                       sim->scale_lattice == scale && sim->auto_lattice_age < 64;
     sim->fine = fine;
     if (reuse) sim->auto_lattice_age++;
     if (!sim->lattice_fixed && !reuse) {
@@ -382,6 +405,7 @@ int build_block_list(cdb_sim *sim, double cell_size, bool padded_lattice = false
         sim->auto_lattice_age = 0;
         sim->cell_size_lattice = cell_size;
         sim->fine_lattice = fine;
+        sim->scale_lattice = scale;
         CK(cudaMemcpyAsync(sim->d_grid, &sim->grid, sizeof(Grid), cudaMemcpyHostToDevice, st));
     }
     const int64_t ncell = sim->grid.ncell;
@@ -479,8 +503,8 @@ int prepare_pairs(cdb_sim *sim) {
     if (!use_pairs(sim)) return CDB_OK;
     if (!sim->pb.ctr) {
         CKS(dev_alloc(&sim->pb.ctr, 2));
-        CK(cudaMallocHost((void **)&sim->h_pctr, 3 * sizeof(unsigned long long)));
-        sim->h_pctr[0] = sim->h_pctr[1] = sim->h_pctr[2] = 0;
+        CK(cudaMallocHost((void **)&sim->h_pctr, 4 * sizeof(unsigned long long)));
+        sim->h_pctr[0] = sim->h_pctr[1] = sim->h_pctr[2] = sim->h_pctr[3] = 0;
     }
     if (sim->pair_cap_request > 0) return ensure_pairs(sim, sim->pair_cap_request);
     const int64_t want = std::max<int64_t>((sim->strip || sim->defer_sync ? 16 : 8) * std::max(sim->n, sim->capacity / 2), 1 << 16);
@@ -511,6 +535,8 @@ int launch_pairs(cdb_sim *sim) {
     a.reach = sim->fine;
     a.pb = sim->pb;
     a.pb.fatal = sim->strip ? sim->d_error : nullptr;
+    a.chain = sim->chain_step ? sim->d_chain : nullptr;
+    a.drift_limit = sim->drift_limit;
     const int blocks = cdiv(n + a.n_ghost, SW_THREADS);
     if (sim->model == CDB_MODEL_CIRCULAR) LAUNCH(sim, k_sweep<0>, blocks, SW_THREADS, 0, a);
     else LAUNCH(sim, k_sweep<1>, blocks, SW_THREADS, 0, a);
@@ -543,6 +569,11 @@ int launch_step_kernel(cdb_sim *sim, unsigned flags, double dt_min, double dt_ma
     a.reach = sim->fine;
     a.mig = MigrantArgs{};
     if (mig && pairs && (flags & CDB_STEP_INTEGRATOR)) a.mig = *mig;
+    a.chain = nullptr; a.rec_nbr = nullptr; a.rec_sweep = nullptr; a.inplace = 0;
+    if (sim->chain_step) {
+        a.chain = sim->d_chain; a.rec_nbr = sim->d_nbr; a.rec_sweep = sim->d_nbr_sweep;
+        if (sim->chain_inplace) { a.inplace = 1; a.out = sim->cur; a.order = nullptr; }
+    }
     const int smem = 0;
     if (a.n > 0) {
         if (pairs) {
@@ -557,10 +588,12 @@ int launch_step_kernel(cdb_sim *sim, unsigned flags, double dt_min, double dt_ma
     }
     CK(cudaGetLastError());
     if (flags & CDB_STEP_INTEGRATOR) {
-        std::swap(sim->cur, sim->alt);
-        if (a.order) {   // the step wrote the live agents compacted, in cell order
-            sim->n = a.n; sim->n_dead = 0;
-            if (sim->dev_counts) LAUNCH(sim, k_counts_after_step, 1, 32, 0, sim->d_counts);
+        if (!a.inplace) {
+            std::swap(sim->cur, sim->alt);
+            if (a.order) {   // the step wrote the live agents compacted, in cell order
+                sim->n = a.n; sim->n_dead = 0;
+                if (sim->dev_counts) LAUNCH(sim, k_counts_after_step, 1, 32, 0, sim->d_counts);
+            }
         }
         sim->perm_valid = false;
         sim->tables_valid = false;
@@ -574,10 +607,30 @@ int launch_step_kernel(cdb_sim *sim, unsigned flags, double dt_min, double dt_ma
 int analyze_pairs(cdb_sim *sim, bool *overflow, int64_t *dev_steps) {
     const int64_t found = (int64_t)sim->h_pctr[0];
     if (dev_steps) *dev_steps = (int64_t)sim->h_pctr[2];
+    // resident-order steps: size the rebuild interval so that the drift bound (sum of the per-step maximum displacements)
+    // stays below the slack of the search cells, with a margin for crowds that speed up
+    {
+        double last; memcpy(&last, &sim->h_pctr[3], sizeof(last));
+        if (sim->drift_limit > 0.0 && last > 0.0 && std::isfinite(last)) {
+            const double k = sim->drift_limit / (1.25 * last);
+            sim->rebuild_every = (int)std::max(1.0, std::min((double)sim->rebuild_max, std::floor(k)));
+        } else if (!(last >= 0.0) || !std::isfinite(last)) {
+            sim->rebuild_every = 1;
+        }
+    }
+    if ((unsigned long long)found >= CHAIN_STALE) {
+        // a step on the kept order found the search lattice stale and was not applied: rebuild, and more often from now on
+        *overflow = true;
+        sim->chain_valid = false;
+        sim->chain_stale++;
+        sim->rebuild_every = std::max(1, sim->rebuild_every / 2);
+        return CDB_OK;
+    }
     sim->pairs_known_found = found;
     sim->pairs_known_age = 0;
     if (found > sim->pb.cap) {
         *overflow = true;
+        sim->chain_valid = false;
         sim->pair_overflows++;
         sim->pair_cap_request = 0;
         CKS(ensure_pairs(sim, std::max<int64_t>(2 * sim->pb.cap, found + found / 2)));
@@ -587,12 +640,33 @@ int analyze_pairs(cdb_sim *sim, bool *overflow, int64_t *dev_steps) {
     return CDB_OK;
 }
 
-// deferred mode: pick up a check whose copy has completed since it was issued (never waits)
+// blocking read of the pair counters, the device step counter and the last displacement (one synchronisation)
+int read_counters(cdb_sim *sim) {
+    CK(cudaMemcpyAsync(sim->h_pctr, sim->pb.ctr, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, sim->stream));
+    CK(cudaMemcpyAsync(sim->h_pctr + 2, sim->d_stepctr, sizeof(unsigned long long), cudaMemcpyDeviceToHost, sim->stream));
+    CK(cudaMemcpyAsync(sim->h_pctr + 3, &sim->d_chain->disp_last, sizeof(double), cudaMemcpyDeviceToHost, sim->stream));
+    return CDB_OK;
+}
+
+// deferred mode: pick up a check whose copy has completed since it was issued (never waits).  *overflow also reports a step
+// that was refused before the check was queued (fewer steps applied than the host had issued by then); the caller then
+// synchronises and reads the counters again.
 int harvest_pairs(cdb_sim *sim, bool *overflow, int64_t *dev_steps) {
     if (!sim->pairs_inflight) return CDB_OK;
     if (cudaEventQuery(sim->ev_pairs) != cudaSuccess) { cudaGetLastError(); return CDB_OK; }
     sim->pairs_inflight = false;
-    return analyze_pairs(sim, overflow, dev_steps);
+    int64_t seen = sim->iterations_at_check;
+    CKS(analyze_pairs(sim, overflow, &seen));
+    if (seen < sim->iterations_at_check) *overflow = true;
+    if (*overflow) {
+        // what has been applied by NOW (steps issued after the check may or may not have been)
+        CKS(read_counters(sim));
+        CK(sync_stream(sim));
+        if (dev_steps) *dev_steps = (int64_t)sim->h_pctr[2];
+        sim->chain_valid = false;
+        sim->pairs_pending = false;
+    }
+    return CDB_OK;
 }
 
 int settle_pairs(cdb_sim *sim, bool *overflow, int64_t *dev_steps, bool may_defer = false) {
@@ -604,22 +678,21 @@ int settle_pairs(cdb_sim *sim, bool *overflow, int64_t *dev_steps, bool may_defe
         // ample room -- a recent check found it at most a quarter full, and a crowd cannot get four times denser within a
         // few steps (agents move about a centimetre per step).  The check is read once its copy has completed.
         CKS(harvest_pairs(sim, overflow, dev_steps));
-        if (*overflow) { CK(sync_stream(sim)); sim->pairs_pending = false; sim->pairs_inflight = false; return CDB_OK; }
+        if (*overflow) return CDB_OK;
         const bool safe = sim->pairs_known_found >= 0 && sim->pairs_known_found <= sim->pb.cap / 4 && sim->pairs_known_age < 16;
         if (safe) {
             if (!sim->pairs_inflight) {
-                CK(cudaMemcpyAsync(sim->h_pctr, sim->pb.ctr, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, sim->stream));
-                CK(cudaMemcpyAsync(sim->h_pctr + 2, sim->d_stepctr, sizeof(unsigned long long), cudaMemcpyDeviceToHost, sim->stream));
+                CKS(read_counters(sim));
                 CK(cudaEventRecord(sim->ev_pairs, sim->stream));
                 sim->pairs_inflight = true;
+                sim->iterations_at_check = sim->iterations;
             }
             sim->pairs_known_age++;
             return CDB_OK;
         }
     }
     if (sim->pairs_inflight) { CK(sync_stream(sim)); sim->pairs_inflight = false; }     // its slot is reused below
-    CK(cudaMemcpyAsync(sim->h_pctr, sim->pb.ctr, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, sim->stream));
-    CK(cudaMemcpyAsync(sim->h_pctr + 2, sim->d_stepctr, sizeof(unsigned long long), cudaMemcpyDeviceToHost, sim->stream));
+    CKS(read_counters(sim));
     CK(sync_stream(sim));
     sim->pairs_pending = false;
     return analyze_pairs(sim, overflow, dev_steps);
@@ -727,6 +800,8 @@ int cdb_create(int device, int model, int64_t capacity, cdb_sim **out) {
         CKS(dev_alloc(&sim->d_dt, 2));
         CKS(dev_alloc(&sim->d_dt_log, DT_LOG));
         CKS(dev_alloc(&sim->d_stepctr, 1));
+        CKS(dev_alloc(&sim->d_chain, 1));
+        CK(cudaMemset(sim->d_chain, 0, sizeof(ChainState)));
         CK(cudaStreamCreateWithFlags(&sim->side, cudaStreamNonBlocking));
         CK(cudaEventCreateWithFlags(&sim->ev_main, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&sim->ev_pairs, cudaEventDisableTiming));
@@ -780,7 +855,7 @@ int cdb_destroy(cdb_sim *sim) {
     }
     if (sim->ev_main) cudaEventDestroy(sim->ev_main);
     if (sim->ev_pairs) cudaEventDestroy(sim->ev_pairs);
-    cudaFree(sim->d_scal);
+    cudaFree(sim->d_scal); cudaFree(sim->d_chain);
     cudaFree(sim->d_grid); cudaFree(sim->d_cell_count); cudaFree(sim->d_cell_start); cudaFree(sim->d_cell_fill);
     cudaFree(sim->d_cell_of_slot); cudaFree(sim->d_order_tmp); cudaFree(sim->d_order); if (sim->d_nbr_sweep != sim->d_nbr) cudaFree(sim->d_nbr_sweep); cudaFree(sim->d_nbr); cudaFree(sim->d_scan_partials);
     cudaFree(sim->d_bbox); cudaFreeHost(sim->h_bbox);
@@ -1325,6 +1400,14 @@ int cdb_integrate(cdb_sim *sim, double dt_min, double dt_max, double *dt_out) {
     return CDB_OK;
 }
 
+// Resident-order steps apply to whole fused steps of the once-per-pair pipeline on one device, for crowds large enough that
+// the step is not launch-bound, and only where the pair set does not depend on the lattice (3 + 2 max R < cell_size).
+static bool chain_usable(const cdb_sim *sim, uint32_t flags, double cell_size) {
+    return sim->chain_enabled && sim->rebuild_max > 1 && sim->skin_frac > 0.0 && sim->variant == 3 && !sim->strip && !sim->lattice_fixed &&
+           (flags & CDB_STEP_AGENT_AGENT) && (flags & CDB_STEP_INTEGRATOR) && sim->n >= sim->chain_min_agents && sim->n_dead == 0 &&
+           !sim->dev_counts && sim->pb.ctr && (SIGTH_SOC + 2.0 * sim->ext_max) * (1.0 + 1e-9) < cell_size;
+}
+
 // launches of ONE step of the selected nodes (no host synchronisation unless the search lattice has to be re-derived)
 static int issue_step(cdb_sim *sim, uint32_t flags, double cell_size, double dt_min, double dt_max, bool log_dt) {
     double *log = log_dt && (flags & CDB_STEP_INTEGRATOR) ? sim->d_dt_log : nullptr;
@@ -1348,11 +1431,46 @@ static int issue_step(cdb_sim *sim, uint32_t flags, double cell_size, double dt_
         if (flags & CDB_STEP_RESET) CKS(node_reset(sim));
     } else {
         const bool need_vmax = flags & CDB_STEP_INTEGRATOR;
-        if (need_vmax) LAUNCH(sim, k_vmax_init, 1, 32, 0, sim->d_vmax);
-        if (flags & CDB_STEP_AGENT_AGENT) CKS(build_block_list(sim, cell_size, true, need_vmax ? sim->d_vmax : nullptr, false, search_refinement(sim, cell_size)));
-        else if (need_vmax && sim->n > 0) LAUNCH(sim, k_vmax, (cdiv(sim->n, 1024) < 1184 ? cdiv(sim->n, 1024) : 1184), 256, 0, sim->cur, (int)sim->n, sim->d_vmax);
+        const bool chain = chain_usable(sim, flags, cell_size);
+        sim->chain_step = chain;
+        sim->chain_inplace = false;
+        if (chain) {
+            // resident-order step: rebuild the block list only every `rebuild_every` steps (ChainState in kernels.cuh)
+            const double scale = 1.0 + sim->skin_frac;
+            const bool keep = sim->chain_valid && sim->chain_version == sim->state_version && sim->chain_cell_size == cell_size &&
+                              sim->chain_scale == scale && sim->since_rebuild < sim->rebuild_every && sim->n_sorted == sim->n;
+            LAUNCH(sim, k_chain_begin, 1, 32, 0, sim->d_chain, sim->d_vmax, keep ? 0 : 1);
+            if (keep) {
+                sim->chain_inplace = true;
+                sim->chain_kept++;
+            } else {
+                LAUNCH(sim, k_vmax_init, 1, 32, 0, sim->d_vmax);
+                CKS(build_block_list(sim, cell_size, true, sim->d_vmax, false, search_refinement(sim, cell_size), scale));
+                sim->since_rebuild = 0;
+                sim->chain_rebuilds++;
+                sim->chain_cell_size = cell_size;
+                sim->chain_scale = scale;
+                // every pair closer than the interaction range is swept while both agents together have drifted less than
+                // the slack between the cells' reach (cell_size * scale) and that range
+                sim->drift_limit = 0.5 * (cell_size * scale - (SIGTH_SOC + 2.0 * sim->ext_max) * (1.0 + 1e-9)) * (1.0 - 1e-9);
+            }
+        } else if (flags & CDB_STEP_AGENT_AGENT) {
+            if (need_vmax) LAUNCH(sim, k_vmax_init, 1, 32, 0, sim->d_vmax);
+            CKS(build_block_list(sim, cell_size, true, need_vmax ? sim->d_vmax : nullptr, false, search_refinement(sim, cell_size)));
+        } else if (need_vmax) {
+            LAUNCH(sim, k_vmax_init, 1, 32, 0, sim->d_vmax);
+            if (sim->n > 0) LAUNCH(sim, k_vmax, (cdiv(sim->n, 1024) < 1184 ? cdiv(sim->n, 1024) : 1184), 256, 0, sim->cur, (int)sim->n, sim->d_vmax);
+        }
         CKS(prof_mark(sim));
-        CKS(launch_step_kernel(sim, flags, dt_min, dt_max, log));
+        const int rc = launch_step_kernel(sim, flags, dt_min, dt_max, log);
+        sim->chain_step = false;
+        CKS(rc);
+        if (chain) {
+            LAUNCH(sim, k_chain_end, 1, 32, 0, sim->d_chain, sim->pb.ctr, (long long)sim->pb.cap);
+            sim->since_rebuild++;
+            sim->chain_valid = true;
+            sim->chain_version = sim->state_version;
+        }
         CKS(prof_mark(sim));
     }
     const bool checked = use_pairs(sim) && sim->variant != 1 && (flags & CDB_STEP_AGENT_AGENT) && sim->n_sorted > 0;
@@ -1370,6 +1488,7 @@ static bool graph_usable(cdb_sim *sim, uint32_t flags, double cell_size) {
     // the legacy / per-thread default streams cannot be captured (e.g. torch's default current stream)
     if (sim->stream == nullptr || sim->stream == cudaStreamLegacy || sim->stream == cudaStreamPerThread) return false;
     if (!(flags & CDB_STEP_AGENT_AGENT) || !(flags & CDB_STEP_INTEGRATOR)) return false;
+    if (chain_usable(sim, flags, cell_size)) return false;      // large crowds: resident-order steps instead
     if (sim->lattice_fixed) return sim->cell_capacity >= sim->grid.ncell;
     return sim->auto_lattice_valid && sim->cell_size_lattice == cell_size && sim->auto_lattice_age + 2 <= 64 &&
            sim->fine_lattice == search_refinement(sim, cell_size) && sim->cell_capacity >= sim->grid.ncell;
@@ -1448,11 +1567,8 @@ int cdb_step(cdb_sim *sim, uint32_t flags, double cell_size, double dt_min, doub
         int64_t dev_steps = sim->iterations;
         CKS(harvest_pairs(sim, &overflow, &dev_steps));
         if (overflow) {
-            CK(sync_stream(sim));
             const int64_t missing = sim->iterations - dev_steps;
             sim->iterations = dev_steps;
-            sim->pairs_pending = false;
-            sim->pairs_inflight = false;
             k -= missing;
         }
     }
@@ -1472,14 +1588,20 @@ int cdb_step(cdb_sim *sim, uint32_t flags, double cell_size, double dt_min, doub
         // that steps the device did not apply because the pair list overflowed are noticed and repeated early.
         const bool ring_point = log_dt && sim->iterations % DT_LOG == 0;
         const bool pairs_point = sim->pairs_pending && (k == n_steps || (k & 63) == 0);
-        if (ring_point || pairs_point || (log_dt && k == n_steps)) {
+        // resident-order steps start with a rebuild interval of 1: look at the displacement of the first steps early
+        const bool chain_probe = sim->pairs_pending && k == 2 && sim->rebuild_every == 1 && chain_usable(sim, flags, cell_size);
+        if (ring_point || pairs_point || chain_probe || (log_dt && k == n_steps)) {
             bool overflow = false;
             int64_t dev_steps = sim->iterations;
             CKS(settle_pairs(sim, &overflow, &dev_steps, !log_dt && k == n_steps));
-            if (overflow) {
-                if (++regrown > 16) return fail(CDB_ERR_CAPACITY, "pair list keeps overflowing");
-                // steps issued after the overflowing one ran on the unchanged state and were not applied either
-                const int64_t missing = sim->iterations - dev_steps;
+            // The device counts the steps it really applied.  Steps issued after an overflowing one ran on the unchanged
+            // state and were not applied either; a step refused because its search lattice had gone stale may be followed
+            // by applied ones (the next scheduled rebuild clears the condition), so the count decides, not the last step.
+            const int64_t missing = sim->iterations - dev_steps;
+            if (overflow || missing > 0) {
+                if (++regrown > 64) return fail(CDB_ERR_CAPACITY, "steps keep being refused (pair list overflow / stale search lattice)");
+                if (!overflow) { sim->chain_stale++; sim->rebuild_every = std::max(1, sim->rebuild_every / 2); }
+                sim->chain_valid = false;
                 sim->iterations = dev_steps;
                 k -= missing;
             }
@@ -1532,6 +1654,30 @@ int cdb_get_pair_stats(cdb_sim *sim, int64_t *capacity, int64_t *found_last, int
     if (capacity) *capacity = sim->pb.cap;
     if (found_last) *found_last = sim->h_pctr ? (int64_t)sim->h_pctr[0] : 0;
     if (overflows) *overflows = sim->pair_overflows;
+    return CDB_OK;
+}
+
+int cdb_set_rebuild_policy(cdb_sim *sim, double skin_fraction, int64_t max_interval, int64_t min_agents) {
+    SIM_ENTRY();
+    if (!(skin_fraction >= 0.0) || skin_fraction > 1.0 || max_interval < 1 || min_agents < 0)
+        return fail(CDB_ERR_INVALID_VALUE, "rebuild policy: 0 <= skin_fraction <= 1, max_interval >= 1, min_agents >= 0");
+    sim->skin_frac = skin_fraction;
+    sim->rebuild_max = (int)std::min<int64_t>(max_interval, 1024);
+    sim->rebuild_every = std::min(sim->rebuild_every, sim->rebuild_max);
+    sim->chain_min_agents = min_agents;
+    sim->chain_enabled = max_interval > 1 && skin_fraction > 0.0;
+    sim->chain_valid = false;
+    sim->auto_lattice_valid = false;
+    sim->state_version++;
+    return CDB_OK;
+}
+
+int cdb_get_rebuild_stats(cdb_sim *sim, int64_t *rebuilds, int64_t *kept, int64_t *stale, int64_t *interval) {
+    SIM_ENTRY();
+    if (rebuilds) *rebuilds = sim->chain_rebuilds;
+    if (kept) *kept = sim->chain_kept;
+    if (stale) *stale = sim->chain_stale;
+    if (interval) *interval = sim->rebuild_every;
     return CDB_OK;
 }
 

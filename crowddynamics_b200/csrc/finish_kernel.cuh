@@ -27,8 +27,11 @@ constexpr int FIN_THREADS = FIN_THREADS_N;
 
 template <int MODEL>
 __global__ void __launch_bounds__(FIN_THREADS, MODEL == 0 ? FIN_MINB_CIRC : FIN_MINB_THREE) k_finish(const StepArgs A) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= eff_n(A.n, A.n_dev)) return;
+    const int t0 = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = t0 < eff_n(A.n, A.n_dev);
+    // resident-order steps end with block-wide reductions: there every thread stays (idle ones shadow slot 0, store nothing)
+    if (!live && !A.chain) return;
+    const int t = live ? t0 : 0;
     const Soa &s = A.in;
     const Soa &o = A.out;
     const bool pairs = A.flags & CDB_STEP_AGENT_AGENT;
@@ -37,9 +40,10 @@ __global__ void __launch_bounds__(FIN_THREADS, MODEL == 0 ? FIN_MINB_CIRC : FIN_
     const int n_con = pairs ? A.pb.fill[t] : 0;
     const int con_off = pairs ? A.pb.off[t] : 0;
     if (pairs && pairs_overflowed(A.pb)) {
-        // the pair list did not hold this step's pairs: the step is NOT applied (the host grows the list and repeats it);
-        // an integrating step still has to leave the unchanged state in `out`, which the host makes current
-        if (A.flags & CDB_STEP_INTEGRATOR) {
+        // the pair list did not hold this step's pairs (or the search lattice had gone stale): the step is NOT applied (the
+        // host grows the list / rebuilds the block list and repeats it); an integrating step that moves the agents to the
+        // other buffer still has to leave the unchanged state there, because the host makes that buffer current
+        if ((A.flags & CDB_STEP_INTEGRATOR) && !A.inplace && live) {
             for (int k = 0; k < A.n_planes; ++k) o(k, t) = s(k, oo);
             o.id[t] = s.id[oo];
             o.target[t] = s.target[oo];
@@ -95,26 +99,75 @@ __global__ void __launch_bounds__(FIN_THREADS, MODEL == 0 ? FIN_MINB_CIRC : FIN_
         phi = wrap_to_pi(phi);
         ox = sin(phi) * r_ts; oy = -cos(phi) * r_ts;   // shoulders(), agents.py:473-486
     }
-    // ---- phase 3: the new state, in cell order ----------------------------------------------------------------------------
-    if (t == 0) {
+    // ---- phase 3: the new state, in cell order (in place: only what the step changes) -------------------------------------
+    if (t0 == 0) {
         A.dt_out[0] = dt; A.dt_out[1] += dt;
         if (A.dt_log) A.dt_log[*A.step_ptr % DT_LOG_SLOTS] = dt;
     }
-    o(PX, t) = npx; o(PY, t) = npy; o(VX, t) = nvx; o(VY, t) = nvy;
-    o(E0X, t) = e0x; o(E0Y, t) = e0y;
-    o(FX, t) = rst ? 0.0 : fx; o(FY, t) = rst ? 0.0 : fy;
-    o(FPX, t) = fx; o(FPY, t) = fy;
-    o(RADIUS, t) = radius; o(MASS, t) = mass; o(V0, t) = v0; o(TAU_ADJ, t) = tau_adj;
-    o(K_SOC, t) = k_soc; o(TAU_0, t) = tau_0; o(MU, t) = mu; o(KAPPA, t) = kappa; o(DAMPING, t) = damping;
-    o(STD_RAND_FORCE, t) = srf;
-    o.target[t] = target;
-    if (MODEL == 1) {
-        o(LSX, t) = npx - ox; o(LSY, t) = npy - oy; o(RSX, t) = npx + ox; o(RSY, t) = npy + oy;
-        o(R_T, t) = r_t; o(R_S, t) = r_s; o(R_TS, t) = r_ts; o(INERTIA, t) = inertia; o(OMEGA0, t) = omega0;
-        o(PHI, t) = phi; o(OMEGA, t) = w; o(PHI0, t) = phi0;
-        o(TORQUE, t) = rst ? 0.0 : tq; o(TORQUE_PREV, t) = tq; o(TAU_ROT, t) = tau_rot;
-        o(STD_RAND_TORQUE, t) = srt;
+    if (live) {
+        o(PX, t) = npx; o(PY, t) = npy; o(VX, t) = nvx; o(VY, t) = nvy;
+        o(E0X, t) = e0x; o(E0Y, t) = e0y;
+        o(FX, t) = rst ? 0.0 : fx; o(FY, t) = rst ? 0.0 : fy;
+        o(FPX, t) = fx; o(FPY, t) = fy;
+        if (!A.inplace) {
+            o(RADIUS, t) = radius; o(MASS, t) = mass; o(V0, t) = v0; o(TAU_ADJ, t) = tau_adj;
+            o(K_SOC, t) = k_soc; o(TAU_0, t) = tau_0; o(MU, t) = mu; o(KAPPA, t) = kappa; o(DAMPING, t) = damping;
+            o(STD_RAND_FORCE, t) = srf;
+            o.target[t] = target;
+        }
+        if (MODEL == 1) {
+            o(LSX, t) = npx - ox; o(LSY, t) = npy - oy; o(RSX, t) = npx + ox; o(RSY, t) = npy + oy;
+            o(PHI, t) = phi; o(OMEGA, t) = w; o(PHI0, t) = phi0;
+            o(TORQUE, t) = rst ? 0.0 : tq; o(TORQUE_PREV, t) = tq;
+            if (!A.inplace) {
+                o(R_T, t) = r_t; o(R_S, t) = r_s; o(R_TS, t) = r_ts; o(INERTIA, t) = inertia; o(OMEGA0, t) = omega0;
+                o(TAU_ROT, t) = tau_rot; o(STD_RAND_TORQUE, t) = srt;
+            }
+        }
     }
+    if (A.chain) {
+        // ---- resident-order steps: the next step sweeps THESE slots again, so its neighbour records are written here -- the
+        // same values k_records would derive from the stored state -- and the maxima adaptive_timestep needs of the new
+        // state plus the largest displacement of this step are reduced block-wide
+        if (live) {
+            if (MODEL == 0) {
+                double2 *r = reinterpret_cast<double2 *>(A.rec_nbr + (size_t)t * REC_CIRC);
+                r[0] = make_double2(npx, npy); r[1] = make_double2(nvx, nvy); r[2] = make_double2(radius, radius * (1.0 + 1e-12));
+            } else {
+                const double nlx = npx - ox, nly = npy - oy, nrx = npx + ox, nry = npy + oy;
+                const double dl = hypot(nlx - npx, nly - npy), dr = hypot(nrx - npx, nry - npy);
+                const double ext = fmax(r_t, fmax(dl, dr) + r_s) * (1.0 + 1e-12);
+                double2 *r = reinterpret_cast<double2 *>(A.rec_nbr + (size_t)t * REC_THREE);
+                r[0] = make_double2(npx, npy); r[1] = make_double2(nvx, nvy); r[2] = make_double2(ext, r_t); r[3] = make_double2(r_s, (double)id);
+                r[4] = make_double2(nlx, nly); r[5] = make_double2(nrx, nry);
+                r[6] = make_double2(ox, oy);
+                r[7] = make_double2(floor(npx / A.cell_size), floor(npy / A.cell_size));
+                double2 *q = reinterpret_cast<double2 *>(A.rec_sweep + (size_t)t * REC_CIRC);
+                q[0] = make_double2(npx, npy); q[1] = make_double2(nvx, nvy); q[2] = make_double2(ext, ext * (1.0 + 1e-9));
+            }
+        }
+        const double ninf = -__longlong_as_double(0x7ff0000000000000LL);
+        const double sp = live ? hypot(nvx, nvy) : 0.0;
+        unsigned long long vm = ordered_bits(sp > 0.0 ? sp : 0.0);               // NaN speeds are skipped (k_cell_count)
+        unsigned long long vb = !live ? ordered_bits(ninf) : (isnan(v0) ? 0xffffffffffffffffULL : ordered_bits(v0));
+        double dd = live ? hypot(npx - px, npy - py) : 0.0;
+        if (isnan(dd)) dd = -ninf;                                              // unknown drift: never trust the kept order
+        unsigned long long db = (unsigned long long)__double_as_longlong(dd);
+        __shared__ unsigned long long s_red[3][FIN_THREADS / 32];
+        vm = warp_max_u64(vm); vb = warp_max_u64(vb); db = warp_max_u64(db);
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        if (lane == 0) { s_red[0][warp] = vm; s_red[1][warp] = vb; s_red[2][warp] = db; }
+        __syncthreads();
+        if (warp == 0) {
+            constexpr int NW = FIN_THREADS / 32;
+            vm = lane < NW ? s_red[0][lane] : 0ULL; vb = lane < NW ? s_red[1][lane] : 0ULL; db = lane < NW ? s_red[2][lane] : 0ULL;
+            vm = warp_max_u64(vm); vb = warp_max_u64(vb); db = warp_max_u64(db);
+            if (lane == 0) { atomicMax(&A.chain->vmax_next[0], vm); atomicMax(&A.chain->vmax_next[1], vb); atomicMax(&A.chain->disp_step, db); }
+        }
+        if (live) o.id[t] = id;
+        return;
+    }
+    if (!live) return;
     // ---- strips: did the agent leave the owned columns?  Then its new state goes into the neighbour's migrant message ------
     int side = -1;
     if (A.mig.enabled) {

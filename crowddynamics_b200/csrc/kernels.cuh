@@ -713,6 +713,39 @@ __global__ void k_step_advance(unsigned long long *step, const unsigned long lon
     if (threadIdx.x == 0 && !(pair_ctr && pair_ctr[0] > (unsigned long long)pair_cap)) ++*step;
 }
 
+// ---- resident-order steps (crowd_b200.cu: issue_step) -----------------------------------------------------------------
+// Between two rebuilds of the block list the agents keep their slots: the step works in place (constants are not
+// rewritten), k_finish writes the next step's neighbour records itself, and the search lattice -- cells a little wider than
+// the interaction range needs -- stays valid while no agent has moved further than half that slack.  ChainState is the
+// device-side bookkeeping of this; every kernel that touches it runs on the sim's stream.
+struct ChainState {
+    unsigned long long disp_step;     // max |dx| over the agents of the running step (bits of a non-negative double: ordered)
+    double disp_acc;                  // sum of the per-step maxima since the block list was built: bound on any agent's drift
+    double disp_last;                 // max |dx| of the last applied step (the host sizes the rebuild interval with it)
+    unsigned long long vmax_next[2];  // max |v|, max v0 of the state the last applied step wrote (adaptive_timestep of the next)
+};
+constexpr unsigned long long CHAIN_STALE = 1ULL << 62;   // pair counter value: "the search lattice is stale, step not applied"
+
+// start of a step: a rebuilding step starts the drift bound afresh (its k_cell_count reduces the two maxima itself); a step
+// on the kept order takes the maxima its predecessor's k_finish left
+__global__ void k_chain_begin(ChainState *c, unsigned long long *vmax, int rebuild) {
+    if (threadIdx.x == 0) {
+        if (rebuild) c->disp_acc = 0.0;
+        else { vmax[0] = c->vmax_next[0]; vmax[1] = c->vmax_next[1]; }
+        c->vmax_next[0] = ordered_bits(0.0);
+        c->vmax_next[1] = ordered_bits(-__longlong_as_double(0x7ff0000000000000LL));
+        c->disp_step = 0ULL;
+    }
+}
+// end of a step (after k_finish): an applied step adds its largest displacement to the drift bound
+__global__ void k_chain_end(ChainState *c, const unsigned long long *pair_ctr, long long pair_cap) {
+    if (threadIdx.x == 0 && !(pair_ctr[0] > (unsigned long long)pair_cap)) {
+        const double d = __longlong_as_double((long long)c->disp_step);
+        c->disp_acc += d;
+        c->disp_last = d;
+    }
+}
+
 __global__ void k_reset(Soa s, int n, int model) {   // logic.py:59-64
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;

@@ -63,6 +63,8 @@ struct SweepArgs {
     int reach;                   // forward columns / rows swept around the target's cell: 1 on the cell_size lattice, 2 on the
                                  // twice finer search lattice (chosen by the host when 3 + 2 max R < cell_size, see build_block_list)
     PairBuf pb;
+    const ChainState *chain;     // resident-order steps: drift bound since the block list was built (nullptr: list is fresh)
+    double drift_limit;          // the sweep is complete while chain->disp_acc <= drift_limit (half the slack of the cells)
 };
 
 __device__ __forceinline__ double2 ldg2(const double *p) { return __ldg(reinterpret_cast<const double2 *>(p)); }
@@ -76,6 +78,13 @@ __global__ void __launch_bounds__(SW_THREADS, 8) k_sweep(const SweepArgs A) {
     const int g = blockIdx.x * SW_THREADS + threadIdx.x;
     const int n_own = eff_n(A.n, A.n_dev);
     const int ny = (int)A.grid->ny, nxg = (int)A.grid->nx;
+    if (A.chain && !(A.chain->disp_acc <= A.drift_limit)) {
+        // some agent may have drifted out of the cells this sweep relies on: the step is NOT applied (same protocol as a
+        // pair list that is too small -- every later kernel of the step sees the counter above the capacity); the host
+        // rebuilds the block list and repeats it
+        if (g == 0) A.pb.ctr[0] = CHAIN_STALE;
+        return;
+    }
     // targets: owned agents, then (strips) the ghosts of the left neighbour, which only pair with owned candidates
     int t = -1;
     bool ghost = false;
@@ -297,9 +306,14 @@ __device__ __forceinline__ void pair_three_both(const Three &I, const Three &J, 
     double fix = 0.0, fiy = 0.0, fjx = 0.0, fjy = 0.0;
     if (a != 0.0) {
         // smallest time-to-collision over the 9 part pairs with the reference's selection rule (power_law.py:308-329):
-        // `isnan(tau) or 0 < tau_new < tau`.  tau_new = (b - d) / a is monotone in its numerator, so the division is only
-        // needed when the numerator is positive and smaller than the selected one -- same decisions, fewer divisions.
-        double tau = nan(""), num_sel = 0.0, b_min = 0.0, d_min = 0.0;
+        // `isnan(tau) or 0 < tau_new < tau` with tau_new = (b - d) / a.  `a` is the same for all nine, so the rule is decided
+        // on the numerators: num < num_sel (1 - 1e-15) implies fl(num / a) < fl(num_sel / a) whenever both quotients are
+        // normal numbers (each is within 2^-53 relative of the exact value), and num > 0 then implies tau_new > 0.  Only
+        // near-ties and extreme magnitudes take the two divisions; the selected tau itself is formed once, after the loop --
+        // the same quotient of the same operands the reference forms at selection time.
+        const bool a_ok = a > 1e-100 && a < 1e100;
+        bool have = false;
+        double num_sel = 0.0, b_min = 0.0, d_min = 0.0;
         int contact_i = 0, contact_j = 0;
 #pragma unroll 1
         for (int pi_ = 0; pi_ < 3; ++pi_) {
@@ -314,13 +328,15 @@ __device__ __forceinline__ void pair_three_both(const Three &I, const Three &J, 
                 if (!(disc > 0.0)) continue;         // sqrt gives NaN (disc < 0 or NaN) or 0
                 const double dd = sqrt(disc);
                 const double num = b - dd;
-                bool take = false;
-                double tau_new = 0.0;
-                if (isnan(tau)) { tau_new = num / a; take = true; }
-                else if (num > 0.0 && num < num_sel) { tau_new = num / a; take = 0.0 < tau_new && tau_new < tau; }
-                if (take) { tau = tau_new; num_sel = num; b_min = b; d_min = dd; contact_i = pi_; contact_j = pj_; }
+                bool take = !have;
+                if (have && num > 0.0 && num < num_sel) {
+                    if (a_ok && num > 1e-200 && num_sel < 1e100 && num < num_sel * (1.0 - 1e-15)) take = true;
+                    else { const double tau_new = num / a; take = 0.0 < tau_new && tau_new < num_sel / a; }
+                }
+                if (take) { have = true; num_sel = num; b_min = b; d_min = dd; contact_i = pi_; contact_j = pj_; }
             }
         }
+        const double tau = have ? num_sel / a : nan("");
         if (!(isnan(tau) || tau <= 0.0)) {
             // shoulder displacement of the contacting parts: 0 for the torso, +o for left, -o for right
             const double oix = sel3(contact_i, 0.0, I.ox, 0.0 - I.ox), oiy = sel3(contact_i, 0.0, I.oy, 0.0 - I.oy);
@@ -409,8 +425,13 @@ __global__ void __launch_bounds__(128, MODEL == 0 ? 6 : 4) k_pair_eval(const Eva
                 if (si < A.ghost_base) { const int o = A.order ? A.order[si] : si; ci = ContactPar{s(MU, o), s(KAPPA, o), s(DAMPING, o)}; }
                 if (sj < A.ghost_base) { const int o = A.order ? A.order[sj] : sj; cj = ContactPar{s(MU, o), s(KAPPA, o), s(DAMPING, o)}; }
             };
-            if (t_is_i) pair_three_both(I, J, pt, pu, contact, ft, fu);
-            else pair_three_both(I, J, pu, pt, contact, fu, ft);
+            // ONE call site: with two (one per orientation) the warp splits and each half runs the whole evaluation at half
+            // occupancy of its lanes (ncu, round 2: 17.5 of 32 lanes active throughout pair_three_both)
+            const PairPar pI = t_is_i ? pt : pu, pJ = t_is_i ? pu : pt;
+            double fI[3], fJ[3];
+            pair_three_both(I, J, pI, pJ, contact, fI, fJ);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { ft[k] = t_is_i ? fI[k] : fJ[k]; fu[k] = t_is_i ? fJ[k] : fI[k]; }
         }
         // a side whose result is exactly zero adds nothing: not stored
         const int key_t = (t >= A.ghost_base && t < A.ghost_left_end) ? t - GHOST_KEY_SHIFT : t;

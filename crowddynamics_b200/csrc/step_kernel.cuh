@@ -71,6 +71,10 @@ struct StepArgs {
     int n_planes;            // planes of the model (k_finish: a step that is not applied still moves them to `out`)
     MigrantArgs mig;         // k_finish in strip mode
     int reach;               // k_step: cell columns / rows swept on either side of the target's cell (1, or 2 on the finer lattice)
+    // resident-order steps (k_finish): see ChainState in kernels.cuh
+    ChainState *chain;       // non-null: reduce max |v|, max v0, max |dx| of the new state and write the next step's records
+    double *rec_nbr, *rec_sweep;   // where those records go (the buffers this step's sweep / evaluation read)
+    int inplace;             // 1: the agents keep their slots (in == out, order == nullptr): only mutable planes are written
 };
 
 struct WarpSmem {

@@ -215,6 +215,17 @@ class DeviceAgents:
                                              _ptr(counts) if n_targets else None, int(n_targets)))
         return dt.value, tt.value, ch.value, counts
 
+    def set_rebuild_policy(self, skin_fraction=0.10, max_interval=16, min_agents=16384):
+        """Resident-order steps (include/crowd_b200.h): rebuild the block list at most every ``max_interval`` steps, on search
+        cells ``1 + skin_fraction`` times wider; ``max_interval=1`` rebuilds at every step."""
+        _lib.check(self.lib.cdb_set_rebuild_policy(self.handle, float(skin_fraction), int(max_interval), int(min_agents)))
+
+    def rebuild_stats(self):
+        """-> dict(rebuilds, kept, stale, interval)"""
+        v = [C.c_int64() for _ in range(4)]
+        _lib.check(self.lib.cdb_get_rebuild_stats(self.handle, *[C.byref(x) for x in v]))
+        return dict(zip(('rebuilds', 'kept', 'stale', 'interval'), (x.value for x in v)))
+
     def set_graphs(self, enable):
         _lib.check(self.lib.cdb_set_graphs(self.handle, 1 if enable else 0))
 

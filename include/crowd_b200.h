@@ -170,6 +170,20 @@ int cdb_scalars_wait(cdb_sim *sim, int64_t slot, double *dt, double *time_tot, i
 int cdb_set_deferred_sync(cdb_sim *sim, int enable);
 int64_t cdb_sync_count(const cdb_sim *sim);
 
+/* ---- resident-order steps (no reference counterpart; the reference re-bins every agent at every update,
+ * core/interactions.py:191-205).  For crowds of at least `min_agents` agents cdb_step rebuilds its block list only every few steps:
+ * the search cells are (1 + skin_fraction) times wider than the interaction range needs, the agents keep their slots in between,
+ * the step then works in place (constant fields are not rewritten) and writes the next step's neighbour records itself.  A
+ * device-side bound on how far any agent has drifted since the last rebuild guards every sweep; a step that finds the bound
+ * exceeded is not applied, and the host rebuilds and repeats it (same protocol as a pair list that is too small).  The interval
+ * adapts to the observed displacement, at most `max_interval` steps; max_interval = 1 rebuilds at every step.  Forces are the
+ * same numbers up to the order in which an agent's pair contributions are added (<= 1e-15 relative).
+ * Defaults: skin_fraction 0.10, max_interval 16, min_agents 16384.  Not used in strip mode, with a fixed lattice, or when
+ * 3 + 2 max R >= cell_size (then the pair set depends on the lattice itself). */
+int cdb_set_rebuild_policy(cdb_sim *sim, double skin_fraction, int64_t max_interval, int64_t min_agents);
+/* steps that rebuilt the block list / ran on the kept order / were refused as stale so far, and the current interval */
+int cdb_get_rebuild_stats(cdb_sim *sim, int64_t *rebuilds, int64_t *kept, int64_t *stale, int64_t *interval);
+
 /* ---- instrumentation (no reference counterpart) -------------------------------------------------------------------- */
 /* agent-agent kernel variant:
  *   3 (default) = every unordered pair of the block list classified and evaluated ONCE, as the reference's pair loop does
