@@ -352,10 +352,8 @@ int prof_mark(cdb_sim *sim) {
 int search_refinement(const cdb_sim *sim, double cell_size) {
     if (sim->strip) return sim->strip_fine;
     if (sim->fine_request == 1 || sim->lattice_fixed || sim->variant == 1) return 1;
-    // automatic: circular agents only -- measured (profiles/, round 2): the finer lattice takes 15 % off the sweep for both
-    // models, but its pair list is less coherent (neighbouring list entries belong to different targets) and the branchy
-    // three-circle evaluation loses more to divergence (21 -> 14 of 32 lanes active) than the sweep gains
-    if (sim->fine_request == 0 && sim->model != CDB_MODEL_CIRCULAR) return 1;
+    // automatic: both models (round 2: with one call site per pair in k_pair_eval the less coherent pair list of the finer
+    // lattice no longer costs the three-circle evaluation more than the sweep gains: 0.684 vs 0.711 ms / step at 1 M agents)
     return (SIGTH_SOC + 2.0 * sim->ext_max) * (1.0 + 1e-9) < cell_size ? 2 : 1;
 }
 

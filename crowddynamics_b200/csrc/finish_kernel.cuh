@@ -132,18 +132,22 @@ __global__ void __launch_bounds__(FIN_THREADS, MODEL == 0 ? FIN_MINB_CIRC : FIN_
         if (live) {
             if (MODEL == 0) {
                 double2 *r = reinterpret_cast<double2 *>(A.rec_nbr + (size_t)t * REC_CIRC);
-                r[0] = make_double2(npx, npy); r[1] = make_double2(nvx, nvy); r[2] = make_double2(radius, radius * (1.0 + 1e-12));
+                r[0] = make_double2(npx, npy); r[1] = make_double2(nvx, nvy);
+                if (!A.inplace) r[2] = make_double2(radius, radius * (1.0 + 1e-12));
             } else {
+                // body extent: a rigid body's is constant, r_ts + r_s around the centre (the stored shoulder positions differ
+                // from centre -+ o by one rounding of the coordinate, which the sweep's 1e-9 inflation of the extent covers)
                 const double nlx = npx - ox, nly = npy - oy, nrx = npx + ox, nry = npy + oy;
-                const double dl = hypot(nlx - npx, nly - npy), dr = hypot(nrx - npx, nry - npy);
-                const double ext = fmax(r_t, fmax(dl, dr) + r_s) * (1.0 + 1e-12);
+                const double ext = fmax(r_t, r_ts * (1.0 + 1e-12) + r_s) * (1.0 + 1e-12);
                 double2 *r = reinterpret_cast<double2 *>(A.rec_nbr + (size_t)t * REC_THREE);
-                r[0] = make_double2(npx, npy); r[1] = make_double2(nvx, nvy); r[2] = make_double2(ext, r_t); r[3] = make_double2(r_s, (double)id);
+                r[0] = make_double2(npx, npy); r[1] = make_double2(nvx, nvy);
+                if (!A.inplace) { r[2] = make_double2(ext, r_t); r[3] = make_double2(r_s, (double)id); }   // kept slot: unchanged
                 r[4] = make_double2(nlx, nly); r[5] = make_double2(nrx, nry);
                 r[6] = make_double2(ox, oy);
                 r[7] = make_double2(floor(npx / A.cell_size), floor(npy / A.cell_size));
                 double2 *q = reinterpret_cast<double2 *>(A.rec_sweep + (size_t)t * REC_CIRC);
-                q[0] = make_double2(npx, npy); q[1] = make_double2(nvx, nvy); q[2] = make_double2(ext, ext * (1.0 + 1e-9));
+                q[0] = make_double2(npx, npy); q[1] = make_double2(nvx, nvy);
+                if (!A.inplace) q[2] = make_double2(ext, ext * (1.0 + 1e-9));
             }
         }
         const double ninf = -__longlong_as_double(0x7ff0000000000000LL);

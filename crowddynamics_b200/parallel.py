@@ -171,10 +171,10 @@ class StripSimulation:
         self.right = rank + 1 if rank < world - 1 else None
         ix_min, iy_min, nx, ny = lattice
         # Search lattice: every rank must bin on the same one, and the choice mirrors what a single device does on its own
-        # (circular agents: cells of cell_size / 2 whenever no pair can interact beyond cell_size, which needs the largest
-        # radius of the WHOLE crowd), so that the strips reproduce the single-device run bit for bit.
+        # (cells of cell_size / 2 whenever no pair can interact beyond cell_size, which needs the largest radius / body
+        # extent of the WHOLE crowd), so that the strips reproduce the single-device run bit for bit.
         self.refinement = 1
-        if model == MODEL_CIRCULAR and hasattr(dev, 'set_search_refinement'):
+        if model is not None and hasattr(dev, 'set_search_refinement'):
             if ext_max is None:
                 ext_max = dev.ext_max()
                 if dist is not None and world > 1:
@@ -353,9 +353,14 @@ class StripSimulation:
         dev.set_obstacles(obstacles)
         for t, (mg, uv) in enumerate(fields or ()):
             dev.set_navigation_field(t, mg, uv)
-        ext = None
+        ext = None                                      # the whole crowd is known to every rank here (k_ext_max's formula)
         if model == MODEL_CIRCULAR and len(agents):
-            ext = float(np.max(agents['radius']))       # the whole crowd is known to every rank here
+            ext = float(np.max(agents['radius']))
+        elif len(agents):
+            p = agents['position']
+            arm = np.maximum(np.hypot(*(agents['position_ls'] - p).T), np.hypot(*(agents['position_rs'] - p).T))
+            arm = np.maximum(arm, np.abs(agents['r_ts']) * (1.0 + 1e-9))
+            ext = float(np.max(np.maximum(agents['r_t'], arm + agents['r_s'])))
         return cls(dev, rank, world, bounds, lattice, cell_size, halo_cap, mig_cap, tensor_device, len(local), dist=dist,
                    flags=flags, dt_min=dt_min, dt_max=dt_max, model=model, ext_max=ext)
 
