@@ -36,7 +36,7 @@ def profile_counters(model, n_agents, density):
     if n_agents != 1000000 or abs(density - 1.0) > 1e-12:
         return None
     import glob
-    files = sorted(glob.glob(os.path.join(ROOT, 'profiles', 'ncu_full_%s_r*.txt' % model)), key=os.path.getmtime)
+    files = sorted(glob.glob(os.path.join(ROOT, 'profiles', 'ncu_full_%s_r*.txt' % model)))     # tags sort by round
     if not files:
         return None
     out = {'source': os.path.relpath(files[-1], ROOT), 'kernels': {}}

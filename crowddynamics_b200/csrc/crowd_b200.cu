@@ -575,8 +575,14 @@ int launch_step_kernel(cdb_sim *sim, unsigned flags, double dt_min, double dt_ma
     const int smem = 0;
     if (a.n > 0) {
         if (pairs) {
-            if (sim->model == CDB_MODEL_CIRCULAR) LAUNCH(sim, k_finish<0>, cdiv(a.n, FIN_THREADS), FIN_THREADS, smem, a);
-            else LAUNCH(sim, k_finish<1>, cdiv(a.n, FIN_THREADS), FIN_THREADS, smem, a);
+            const int fb = cdiv(a.n, FIN_THREADS);
+            if (sim->model == CDB_MODEL_CIRCULAR) {
+                if (a.inplace) LAUNCH(sim, (k_finish<0, true>), fb, FIN_THREADS, smem, a);
+                else LAUNCH(sim, (k_finish<0, false>), fb, FIN_THREADS, smem, a);
+            } else {
+                if (a.inplace) LAUNCH(sim, (k_finish<1, true>), fb, FIN_THREADS, smem, a);
+                else LAUNCH(sim, (k_finish<1, false>), fb, FIN_THREADS, smem, a);
+            }
         } else {
             if (sim->model == CDB_MODEL_CIRCULAR) LAUNCH(sim, k_step<0>, cdiv(a.n, STEP_THREADS), STEP_THREADS, smem, a);
             else LAUNCH(sim, k_step<1>, cdiv(a.n, STEP_THREADS), STEP_THREADS, smem, a);

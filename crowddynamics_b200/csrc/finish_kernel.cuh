@@ -25,8 +25,17 @@
 #endif
 constexpr int FIN_THREADS = FIN_THREADS_N;
 
-template <int MODEL>
-__global__ void __launch_bounds__(FIN_THREADS, MODEL == 0 ? FIN_MINB_CIRC : FIN_MINB_THREE) k_finish(const StepArgs A) {
+#ifndef FIN_MINB_THREE_INPLACE
+#define FIN_MINB_THREE_INPLACE 3
+#endif
+#ifndef FIN_MINB_CIRC_INPLACE
+#define FIN_MINB_CIRC_INPLACE 4
+#endif
+// INPLACE: the agents keep their slots (resident-order steps, A.inplace == 1) -- a separate instantiation, so that the constants
+// the other variant carries from `in` to `out` cost neither loads nor registers here
+template <int MODEL, bool INPLACE>
+__global__ void __launch_bounds__(FIN_THREADS, MODEL == 0 ? (INPLACE ? FIN_MINB_CIRC_INPLACE : FIN_MINB_CIRC) : (INPLACE ? FIN_MINB_THREE_INPLACE : FIN_MINB_THREE))
+k_finish(const StepArgs A) {
     const int t0 = blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = t0 < eff_n(A.n, A.n_dev);
     // resident-order steps end with block-wide reductions: there every thread stays (idle ones shadow slot 0, store nothing)
@@ -43,7 +52,7 @@ __global__ void __launch_bounds__(FIN_THREADS, MODEL == 0 ? FIN_MINB_CIRC : FIN_
         // the pair list did not hold this step's pairs (or the search lattice had gone stale): the step is NOT applied (the
         // host grows the list / rebuilds the block list and repeats it); an integrating step that moves the agents to the
         // other buffer still has to leave the unchanged state there, because the host makes that buffer current
-        if ((A.flags & CDB_STEP_INTEGRATOR) && !A.inplace && live) {
+        if ((A.flags & CDB_STEP_INTEGRATOR) && !INPLACE && live) {
             for (int k = 0; k < A.n_planes; ++k) o(k, t) = s(k, oo);
             o.id[t] = s.id[oo];
             o.target[t] = s.target[oo];
@@ -54,8 +63,14 @@ __global__ void __launch_bounds__(FIN_THREADS, MODEL == 0 ? FIN_MINB_CIRC : FIN_
     const double px = s(PX, oo), py = s(PY, oo), vx = s(VX, oo), vy = s(VY, oo);
     double e0x = s(E0X, oo), e0y = s(E0Y, oo), fx = s(FX, oo), fy = s(FY, oo);
     const double fpx = s(FPX, oo), fpy = s(FPY, oo);
-    const double radius = s(RADIUS, oo), mass = s(MASS, oo), v0 = s(V0, oo), tau_adj = s(TAU_ADJ, oo), k_soc = s(K_SOC, oo), tau_0 = s(TAU_0, oo);
-    const double mu = s(MU, oo), kappa = s(KAPPA, oo), damping = s(DAMPING, oo), srf = s(STD_RAND_FORCE, oo);
+    // constants the step only carries along (k_soc, tau_0 are in the pair parameters; the contact parameters matter for an
+    // agent that overlaps a wall; the fluctuation scales for that node) are not even read when the agents keep their slots
+    constexpr bool carry = !INPLACE;
+    const bool fluct = A.flags & CDB_STEP_FLUCTUATION;
+    const double radius = s(RADIUS, oo), mass = s(MASS, oo), v0 = s(V0, oo), tau_adj = s(TAU_ADJ, oo);
+    const double k_soc = carry ? s(K_SOC, oo) : 0.0, tau_0 = carry ? s(TAU_0, oo) : 0.0;
+    const double mu = carry ? s(MU, oo) : 0.0, kappa = carry ? s(KAPPA, oo) : 0.0, damping = carry ? s(DAMPING, oo) : 0.0;
+    const double srf = carry || fluct ? s(STD_RAND_FORCE, oo) : 0.0;
     const int id = s.id[oo];
     const long long target = s.target[oo];
     double lsx = 0, lsy = 0, rsx = 0, rsy = 0, r_t = 0, r_s = 0, r_ts = 0, inertia = 0, omega0 = 0, phi = 0, w = 0, phi0 = 0, tq = 0,
@@ -64,7 +79,7 @@ __global__ void __launch_bounds__(FIN_THREADS, MODEL == 0 ? FIN_MINB_CIRC : FIN_
         lsx = s(LSX, oo); lsy = s(LSY, oo); rsx = s(RSX, oo); rsy = s(RSY, oo);
         r_t = s(R_T, oo); r_s = s(R_S, oo); r_ts = s(R_TS, oo); inertia = s(INERTIA, oo); omega0 = s(OMEGA0, oo);
         phi = s(PHI, oo); w = s(OMEGA, oo); phi0 = s(PHI0, oo); tq = s(TORQUE, oo); tq_prev = s(TORQUE_PREV, oo);
-        tau_rot = s(TAU_ROT, oo); srt = s(STD_RAND_TORQUE, oo);
+        tau_rot = s(TAU_ROT, oo); srt = carry || fluct ? s(STD_RAND_TORQUE, oo) : 0.0;
     }
     // ---- phase 2: the nodes, in the reference's post-order ----------------------------------------------------------------
     if (A.flags & CDB_STEP_FLUCTUATION) fluctuation(A.seed, *A.step_ptr, id, mass, srf, inertia, srt, MODEL == 1, fx, fy, tq);
@@ -78,8 +93,12 @@ __global__ void __launch_bounds__(FIN_THREADS, MODEL == 0 ? FIN_MINB_CIRC : FIN_
     }
     if (n_con > 0) gather_contributions(A.pb.cres + (size_t)con_off * 4, n_con, MODEL == 1, fx, fy, tq);
     if ((A.flags & CDB_STEP_AGENT_OBSTACLE) && A.n_obs > 0) {
-        if (MODEL == 0) walls_circular(px, py, radius, vx, vy, mu, kappa, damping, A.obs, A.n_obs, fx, fy);
-        else walls_three_circle(px, py, lsx, lsy, rsx, rsy, r_t, r_s, vx, vy, mu, kappa, damping, A.obs, A.n_obs, fx, fy, tq);
+        auto contact = [&](double &m, double &k, double &d) {
+            if (carry) { m = mu; k = kappa; d = damping; }
+            else { m = s(MU, oo); k = s(KAPPA, oo); d = s(DAMPING, oo); }      // in place: no store to these planes anywhere
+        };
+        if (MODEL == 0) walls_circular(px, py, radius, vx, vy, contact, A.obs, A.n_obs, fx, fy);
+        else walls_three_circle(px, py, lsx, lsy, rsx, rsy, r_t, r_s, vx, vy, contact, A.obs, A.n_obs, fx, fy, tq);
     }
     const bool rst = A.flags & CDB_STEP_RESET;
     if (!(A.flags & CDB_STEP_INTEGRATOR)) {
@@ -109,7 +128,7 @@ __global__ void __launch_bounds__(FIN_THREADS, MODEL == 0 ? FIN_MINB_CIRC : FIN_
         o(E0X, t) = e0x; o(E0Y, t) = e0y;
         o(FX, t) = rst ? 0.0 : fx; o(FY, t) = rst ? 0.0 : fy;
         o(FPX, t) = fx; o(FPY, t) = fy;
-        if (!A.inplace) {
+        if (!INPLACE) {
             o(RADIUS, t) = radius; o(MASS, t) = mass; o(V0, t) = v0; o(TAU_ADJ, t) = tau_adj;
             o(K_SOC, t) = k_soc; o(TAU_0, t) = tau_0; o(MU, t) = mu; o(KAPPA, t) = kappa; o(DAMPING, t) = damping;
             o(STD_RAND_FORCE, t) = srf;
@@ -119,7 +138,7 @@ __global__ void __launch_bounds__(FIN_THREADS, MODEL == 0 ? FIN_MINB_CIRC : FIN_
             o(LSX, t) = npx - ox; o(LSY, t) = npy - oy; o(RSX, t) = npx + ox; o(RSY, t) = npy + oy;
             o(PHI, t) = phi; o(OMEGA, t) = w; o(PHI0, t) = phi0;
             o(TORQUE, t) = rst ? 0.0 : tq; o(TORQUE_PREV, t) = tq;
-            if (!A.inplace) {
+            if (!INPLACE) {
                 o(R_T, t) = r_t; o(R_S, t) = r_s; o(R_TS, t) = r_ts; o(INERTIA, t) = inertia; o(OMEGA0, t) = omega0;
                 o(TAU_ROT, t) = tau_rot; o(STD_RAND_TORQUE, t) = srt;
             }
@@ -133,7 +152,8 @@ __global__ void __launch_bounds__(FIN_THREADS, MODEL == 0 ? FIN_MINB_CIRC : FIN_
             if (MODEL == 0) {
                 double2 *r = reinterpret_cast<double2 *>(A.rec_nbr + (size_t)t * REC_CIRC);
                 r[0] = make_double2(npx, npy); r[1] = make_double2(nvx, nvy);
-                if (!A.inplace) r[2] = make_double2(radius, radius * (1.0 + 1e-12));
+                r[2] = make_double2(radius, radius * (1.0 + 1e-12));   // (constant, but a 48 B record left partly unwritten costs
+                                                                      // the L2 a read-modify-write of its straddling sectors)
             } else {
                 // body extent: a rigid body's is constant, r_ts + r_s around the centre (the stored shoulder positions differ
                 // from centre -+ o by one rounding of the coordinate, which the sweep's 1e-9 inflation of the extent covers)
@@ -141,13 +161,13 @@ __global__ void __launch_bounds__(FIN_THREADS, MODEL == 0 ? FIN_MINB_CIRC : FIN_
                 const double ext = fmax(r_t, r_ts * (1.0 + 1e-12) + r_s) * (1.0 + 1e-12);
                 double2 *r = reinterpret_cast<double2 *>(A.rec_nbr + (size_t)t * REC_THREE);
                 r[0] = make_double2(npx, npy); r[1] = make_double2(nvx, nvy);
-                if (!A.inplace) { r[2] = make_double2(ext, r_t); r[3] = make_double2(r_s, (double)id); }   // kept slot: unchanged
+                if (!INPLACE) { r[2] = make_double2(ext, r_t); r[3] = make_double2(r_s, (double)id); }   // kept slot: unchanged
                 r[4] = make_double2(nlx, nly); r[5] = make_double2(nrx, nry);
                 r[6] = make_double2(ox, oy);
                 r[7] = make_double2(floor(npx / A.cell_size), floor(npy / A.cell_size));
                 double2 *q = reinterpret_cast<double2 *>(A.rec_sweep + (size_t)t * REC_CIRC);
                 q[0] = make_double2(npx, npy); q[1] = make_double2(nvx, nvy);
-                if (!A.inplace) q[2] = make_double2(ext, ext * (1.0 + 1e-9));
+                q[2] = make_double2(ext, ext * (1.0 + 1e-9));          // whole 48 B record: no partially written sectors
             }
         }
         const double ninf = -__longlong_as_double(0x7ff0000000000000LL);
@@ -168,7 +188,7 @@ __global__ void __launch_bounds__(FIN_THREADS, MODEL == 0 ? FIN_MINB_CIRC : FIN_
             vm = warp_max_u64(vm); vb = warp_max_u64(vb); db = warp_max_u64(db);
             if (lane == 0) { atomicMax(&A.chain->vmax_next[0], vm); atomicMax(&A.chain->vmax_next[1], vb); atomicMax(&A.chain->disp_step, db); }
         }
-        if (live) o.id[t] = id;
+        if (live && !INPLACE) o.id[t] = id;
         return;
     }
     if (!live) return;

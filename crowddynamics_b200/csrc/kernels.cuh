@@ -815,7 +815,10 @@ __global__ void k_adjust(Soa s, int n, int model) {
 }
 
 // interactions.py:107-141,169-186
-__device__ __forceinline__ void walls_circular(double px, double py, double r, double vx, double vy, double mu, double kappa, double damping,
+// `contact(mu, kappa, damping)` delivers the agent's contact parameters; it is only called for a wall the agent overlaps
+// (rare), so a caller that does not hold them in registers anyway can fetch them there
+template <typename Contact>
+__device__ __forceinline__ void walls_circular(double px, double py, double r, double vx, double vy, Contact contact,
                                                const double *__restrict__ obs, int n_obs, double &fx, double &fy) {
     for (int w = 0; w < n_obs; ++w) {
         const double *s = obs + (size_t)w * SEG;
@@ -823,15 +826,17 @@ __device__ __forceinline__ void walls_circular(double px, double py, double r, d
         double nx, ny;
         double h = distance_circle_line(px, py, r, s, nx, ny);
         if (h < 0.0) {
-            double cx, cy;
+            double cx, cy, mu, kappa, damping;
+            contact(mu, kappa, damping);
             force_contact(h, nx, ny, vx, vy, ny, -nx, mu, kappa, damping, cx, cy);
             fx += cx; fy += cy;
         }
     }
 }
 
+template <typename Contact>
 __device__ __forceinline__ void walls_three_circle(double px, double py, double lsx, double lsy, double rsx, double rsy, double r_t,
-                                                   double r_s, double vx, double vy, double mu, double kappa, double damping,
+                                                   double r_s, double vx, double vy, Contact contact,
                                                    const double *__restrict__ obs, int n_obs, double &fx, double &fy, double &torque) {
     for (int w = 0; w < n_obs; ++w) {
         const double *s = obs + (size_t)w * SEG;
@@ -849,24 +854,29 @@ __device__ __forceinline__ void walls_three_circle(double px, double py, double 
         if (h_min < 0.0) {
             double mx = sx - sr * nx - px;
             double my = sy - sr * ny - py;
-            double cx, cy;
+            double cx, cy, mu, kappa, damping;
+            contact(mu, kappa, damping);
             force_contact(h_min, nx, ny, vx, vy, ny, -nx, mu, kappa, damping, cx, cy);
             fx += cx; fy += cy;
             torque += mx * cy - my * cx;
         }
     }
 }
+struct ContactValues {
+    double mu, kappa, damping;
+    __device__ __forceinline__ void operator()(double &m, double &k, double &d) const { m = mu; k = kappa; d = damping; }
+};
 
 __global__ void k_agent_obstacle(Soa s, int n, int model, const double *__restrict__ obs, int n_obs) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     double fx = s(FX, i), fy = s(FY, i);
     if (model == CDB_MODEL_CIRCULAR) {
-        walls_circular(s(PX, i), s(PY, i), s(RADIUS, i), s(VX, i), s(VY, i), s(MU, i), s(KAPPA, i), s(DAMPING, i), obs, n_obs, fx, fy);
+        walls_circular(s(PX, i), s(PY, i), s(RADIUS, i), s(VX, i), s(VY, i), ContactValues{s(MU, i), s(KAPPA, i), s(DAMPING, i)}, obs, n_obs, fx, fy);
     } else {
         double tq = s(TORQUE, i);
         walls_three_circle(s(PX, i), s(PY, i), s(LSX, i), s(LSY, i), s(RSX, i), s(RSY, i), s(R_T, i), s(R_S, i), s(VX, i), s(VY, i),
-                           s(MU, i), s(KAPPA, i), s(DAMPING, i), obs, n_obs, fx, fy, tq);
+                           ContactValues{s(MU, i), s(KAPPA, i), s(DAMPING, i)}, obs, n_obs, fx, fy, tq);
         s(TORQUE, i) = tq;
     }
     s(FX, i) = fx; s(FY, i) = fy;

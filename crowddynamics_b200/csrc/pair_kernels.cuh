@@ -388,7 +388,13 @@ __device__ __forceinline__ void store_contribution(const PairBuf &pb, int a, int
 }
 
 template <int MODEL>
-__global__ void __launch_bounds__(128, MODEL == 0 ? 6 : 4) k_pair_eval(const EvalArgs A) {
+#ifndef EVAL_MINB_THREE
+#define EVAL_MINB_THREE 4
+#endif
+#ifndef EVAL_MINB_CIRC
+#define EVAL_MINB_CIRC 8
+#endif
+__global__ void __launch_bounds__(128, MODEL == 0 ? EVAL_MINB_CIRC : EVAL_MINB_THREE) k_pair_eval(const EvalArgs A) {
     if (pairs_overflowed(A.pb)) return;
     const long long np = (long long)A.pb.ctr[0];
     const Soa &s = A.in;

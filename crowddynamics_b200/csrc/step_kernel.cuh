@@ -362,9 +362,9 @@ __global__ void __launch_bounds__(STEP_THREADS, MODEL == 0 ? STEP_MINB_CIRC : ST
     // ---- AgentObstacleInteractions (interactions.py:208-214) ---------------------------------------------------------------
     if ((A.flags & CDB_STEP_AGENT_OBSTACLE) && A.n_obs > 0) {
         if (MODEL == 0) {
-            walls_circular(px, py, s(RADIUS, oo), vx, vy, mu, kappa, damping, A.obs, A.n_obs, fx, fy);
+            walls_circular(px, py, s(RADIUS, oo), vx, vy, ContactValues{mu, kappa, damping}, A.obs, A.n_obs, fx, fy);
         } else {
-            walls_three_circle(px, py, s(LSX, oo), s(LSY, oo), s(RSX, oo), s(RSY, oo), s(R_T, oo), s(R_S, oo), vx, vy, mu, kappa, damping,
+            walls_three_circle(px, py, s(LSX, oo), s(LSY, oo), s(RSX, oo), s(RSY, oo), s(R_T, oo), s(R_S, oo), vx, vy, ContactValues{mu, kappa, damping},
                                A.obs, A.n_obs, fx, fy, tq);
         }
     }

@@ -27,8 +27,8 @@ def main(tag):
     for model in ('three_circle', 'circular'):
         rep = 'gpurun_out/prof_%s_%s.ncu-rep' % (model, tag)
         hdr, units, rows = raw(rep)
-        lines = ['# ncu --set full --clock-control none, kernel k_step<%d> (%s), one launch, 1M agents, 1 agent/m^2' % (
-            0 if model == 'circular' else 1, model), '# source: %s (not committed: binary); metric, unit, value' % rep]
+        lines = ['# ncu --set full --clock-control none, the kernels of the step (%s), 1M agents, 1 agent/m^2; one section per captured launch'
+                 % model, '# source: %s (not committed: binary); metric, unit, value' % rep]
         for r in rows:
             d = dict(zip(hdr, r))
             lines.append('kernel: %s' % d.get('Kernel Name'))
@@ -43,7 +43,11 @@ def main(tag):
         open('profiles/ncu_full_%s_%s.txt' % (model, tag), 'w').write('\n'.join(lines) + '\n')
         # launch list: per-kernel totals over the profiled launches
         agg = {}
-        with open('gpurun_out/launches_%s_%s.csv' % (model, tag[:2])) as f:
+        import os
+        csv_path = 'gpurun_out/launches_%s_%s.csv' % (model, tag)
+        if not os.path.exists(csv_path):
+            csv_path = 'gpurun_out/launches_%s_%s.csv' % (model, tag[:2])
+        with open(csv_path) as f:
             rd = csv.reader(l for l in f if not l.startswith('=='))
             h = next(rd)
             ki, vi, mi = h.index('Kernel Name'), h.index('Metric Value'), h.index('Metric Name')
@@ -55,7 +59,7 @@ def main(tag):
                 a[0] += 1
                 a[1] += float(r[vi].replace(',', ''))
         tot = sum(a[1] for a in agg.values())
-        lines = ['# ncu --metrics gpu__time_duration.sum --clock-control none: all launches of `bench.py --model %s --steps 3 --warmup 3`' % model,
+        lines = ['# ncu --metrics gpu__time_duration.sum --clock-control none: all launches of one short `bench.py --model %s` run (see capture_*.sh)' % model,
                  '# (cold-cache, serialised: compare SHARES; includes upload/download kernels of the e2e leg)',
                  '%-40s %8s %14s %8s' % ('kernel', 'launches', 'total ns', 'share')]
         for name, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
