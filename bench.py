@@ -300,6 +300,7 @@ def strip_parity_check(model, rank, world, local_rank, dist):
         got[i] = np.ascontiguousarray(raw).view(agents.dtype).reshape(-1)
         seen[i] += 1
     dev = DeviceAgents(MODEL_CIRCULAR if model == 'circular' else MODEL_THREE_CIRCLE, device=local_rank)
+    dev.set_rebuild_policy(0.10, 1)      # block list rebuilt at every step, like these strips: same summation order, bit for bit
     dev.upload(agents); dev.set_obstacles(obstacles); dev.set_navigation_field(0, *fields[0])
     dev.step(steps, _lib.STEP_ALL, CELL, 0.001, 0.01, want_dt=False)
     ref = agents.copy(); dev.download(ref); dev.close()
