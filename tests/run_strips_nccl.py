@@ -44,6 +44,7 @@ def main():
                     got[i] = np.ascontiguousarray(raw).view(agents.dtype).reshape(-1)
                     seen[i] += 1
                 dev = DeviceAgents(MODEL_CIRCULAR if model == 'circular' else MODEL_THREE_CIRCLE, device=local)
+                dev.set_rebuild_policy(0.10, 1)       # rebuild at every step, like the strips: same summation order
                 dev.upload(agents); dev.set_obstacles(obstacles); dev.set_navigation_field(0, *fields[0])
                 dev.step(20, _lib.STEP_ALL, 3.6, dts[0], dts[1], want_dt=False)
                 ref = agents.copy(); dev.download(ref); dev.close()
