@@ -311,6 +311,47 @@ def strip_parity_check(model, rank, world, local_rank, dist):
             'max_abs_position_diff_vs_single_device': err, 'adaptive_dt': True}
 
 
+def strip_kept_check(model, rank, world, local_rank, dist):
+    """N > 1: the strips with KEPT block lists (resident-order steps) against one device with the same policy.  The rebuild
+    schedules differ (each adapts on its own), so the two agree up to summation order: 1e-16 per step, doubled per step by the
+    dynamics -- 10 steps, bar 1e-9 m."""
+    import torch
+    from crowddynamics_b200 import _lib, synthetic as S
+    from crowddynamics_b200.engine import DeviceAgents
+    from crowddynamics_b200.parallel import StripSimulation
+    from crowddynamics_b200.structures import MODEL_CIRCULAR, MODEL_THREE_CIRCLE
+    steps, n = 10, 60000
+    agents, obstacles, side = S.uniform_crowd(n, model, density=1.0, seed=5)
+    agents['velocity'] *= 1.5
+    fields = [S.direction_field(0.5, (0, 0, side, side), 'swirl')]
+    sim = StripSimulation.from_global(agents, obstacles, fields, CELL, rank, world, device_index=local_rank, dist=dist,
+                                      skin=0.10, max_interval=16)
+    sim.step(steps)
+    torch.cuda.synchronize()
+    stats = sim.dev.rebuild_stats()
+    rec, ids = sim.export(agents.dtype)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (rec.view(np.uint8).reshape(len(rec), -1), ids))
+    if rank != 0:
+        return None
+    got = np.zeros_like(agents)
+    seen = np.zeros(len(agents), dtype=int)
+    for raw, i in gathered:
+        got[i] = np.ascontiguousarray(raw).view(agents.dtype).reshape(-1)
+        seen[i] += 1
+    dev = DeviceAgents(MODEL_CIRCULAR if model == 'circular' else MODEL_THREE_CIRCLE, device=local_rank)
+    dev.set_rebuild_policy(0.10, 16, 0)
+    dev.upload(agents); dev.set_obstacles(obstacles); dev.set_navigation_field(0, *fields[0])
+    dev.step(2, _lib.STEP_ALL, CELL, 0.01, 0.01, want_dt=False)
+    dev.step(steps - 2, _lib.STEP_ALL, CELL, 0.01, 0.01, want_dt=False)
+    ref = agents.copy(); dev.download(ref); dev.close()
+    err = float(np.abs(got['position'] - ref['position']).max())
+    owned = bool((seen == 1).all())
+    return {'status': 'ok' if owned and err <= 1e-9 and stats['kept'] > 0 else 'mismatch', 'agents': n, 'steps': steps,
+            'kept_steps_rank0': stats['kept'], 'rebuilds_rank0': stats['rebuilds'], 'interval': sim.interval,
+            'every_agent_owned_once': owned, 'max_abs_position_diff_vs_single_device': err, 'bar': 1e-9}
+
+
 def workload_config(args, n_per_gpu, world):
     geom = ('a room with a door (11 wall segments)' if getattr(args, 'workload', 'room') == 'room_exit'
             else 'a walled square room, 4 wall segments')
@@ -354,7 +395,7 @@ def main():
                          'NCCL send/recv when IPC is unavailable) or by NCCL send/recv')
     ap.add_argument('--refinement', type=int, default=0, help='search lattice: 0 automatic (cell_size / 2 where valid), 1 cell_size')
     ap.add_argument('--rebuild-max', type=int, default=16,
-                    help='N = 1: rebuild the block list at most every this many steps (resident-order steps, include/crowd_b200.h); '
+                    help='rebuild the block list at most every this many steps (resident-order steps, include/crowd_b200.h); '
                          '1 = rebuild at every step like the reference')
     ap.add_argument('--skin', type=float, default=0.10, help='widening of the search cells that the kept block list relies on')
     ap.add_argument('--variant', type=int, default=3, help='agent-agent kernel variant (3 once-per-pair, 2 both-sides fused kernel)')
@@ -385,16 +426,19 @@ def main():
     mid = MODEL_CIRCULAR if args.model == 'circular' else MODEL_THREE_CIRCLE
     itemsize = 228 if args.model == 'circular' else 316
 
-    strip_parity = None
+    strip_parity = strip_kept = None
     if world > 1:
         from crowddynamics_b200.parallel import StripSimulation
         strip_parity = strip_parity_check(args.model, rank, world, local_rank, dist)
+        strip_kept = strip_kept_check(args.model, rank, world, local_rank, dist) if args.rebuild_max > 1 else None
         if args.scaling == 'strong':
             from crowddynamics_b200.parallel import strong_scaling_strip
             sim = strong_scaling_strip(args.model, n, args.density, rank, world, local_rank,
-                                       geometry='room_exit' if args.workload == 'room_exit' else 'room', dist=dist)
+                                       geometry='room_exit' if args.workload == 'room_exit' else 'room', dist=dist,
+                                       skin=args.skin if args.rebuild_max > 1 else 0.0, max_interval=args.rebuild_max)
         else:
-            sim = StripSimulation.synthetic(args.model, n, args.density, rank, world, local_rank, seed=rank, dist=dist)
+            sim = StripSimulation.synthetic(args.model, n, args.density, rank, world, local_rank, seed=rank, dist=dist,
+                                            skin=args.skin if args.rebuild_max > 1 else 0.0, max_interval=args.rebuild_max)
         exchange = 'nccl send/recv'
         if args.exchange == 'peer' and sim.connect_direct():
             exchange = 'one-sided writes over NVLink peer memory (CUDA IPC) + sequence flags'
@@ -462,7 +506,9 @@ def main():
     clocks = sampler.stop(t_begin, time.time()) if rank == 0 else None
     ms = ev0.elapsed_time(ev1)
     launches = dev.launch_count() - launches0
-    rebuild_stats = dev.rebuild_stats() if world == 1 else None
+    rebuild_stats = dev.rebuild_stats()
+    if world > 1:
+        rebuild_stats['interval'] = sim.interval      # agreed across ranks (all-reduced displacement)
     ph = dev.profile_read_phases()       # pre + block list, pair sweep, pair evaluation, step kernel, post, steps
     prof = (ph[0], ph[1] + ph[2] + ph[3], ph[4], ph[5])
     dev.profile(False)
@@ -595,9 +641,8 @@ def main():
         'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': args.scaling if world > 1 else 'weak',
         'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic', 'config': workload_config(args, n, world),
         'gpu_launches': launches, 'clocks': clocks, 'roofline': roofline, 'roofline_fp64': fp64, 'e2e': e2e,
-        'e2e_variants': e2e_variants, 'field_build': field_build if world == 1 else None, 'strip_parity': strip_parity,
-        'block_list_policy': ({'skin_fraction': args.skin, 'max_interval': args.rebuild_max, 'since_upload': rebuild_stats} if world == 1 else
-                              'rebuilt at every step (strips)'),
+        'e2e_variants': e2e_variants, 'field_build': field_build if world == 1 else None, 'strip_parity': strip_parity, 'strip_kept_block_lists': strip_kept,
+        'block_list_policy': {'skin_fraction': args.skin, 'max_interval': args.rebuild_max, 'since_upload': rebuild_stats},
         'strip_phase_ms_rank0': exchange_ms, 'strip_exchange': exchange if world > 1 else None,
         'hbm_fraction_whole_step': value / world * ALGO_BYTES[args.model] / 1e9 / peak,
     }

@@ -157,6 +157,7 @@ struct cdb_sim {
     // resident-order steps (fused steps of variant 3 on one device, see ChainState in kernels.cuh): the block list is rebuilt
     // every `rebuild_every` steps only; in between the agents keep their slots and the step works in place
     bool chain_enabled = true;       // cdb_set_rebuild_policy
+    bool policy_explicit = false;    // ... has been called (strips keep block lists only on request: every rank must agree)
     double skin_frac = 0.10;         // search cells are (1 + skin_frac) * cell_size / fine wide
     int rebuild_max = 16;            // upper bound of the rebuild interval (1: rebuild every step, the round-1 behaviour)
     int rebuild_every = 1;           // current interval, adapted to the observed per-step displacement
@@ -209,6 +210,8 @@ struct cdb_sim {
     void *p_opened[2][5] = {{nullptr}};          // IPC mappings to close
     bool x_connected = false;
     int strip_fine = 1;              // search refinement of the strip lattice (fixed by cdb_set_strip)
+    double strip_scale = 1.0;        // widening of the strip's search cells (1 + skin when block lists are kept, cdb_set_strip)
+    int strip_kind = 0;              // cdb_strip_set_kind: what the step being issued is (see include/crowd_b200.h)
     long long strip_ix0 = 0, strip_col_lo = 0, strip_col_hi = 0;   // cell_size columns: lattice origin, owned range
     int64_t halo_cap = 0, mig_cap = 0;
     int64_t n_dead = 0;              // slots vacated by migrants (dropped at the next sort)
@@ -1670,6 +1673,7 @@ int cdb_set_rebuild_policy(cdb_sim *sim, double skin_fraction, int64_t max_inter
     sim->rebuild_every = std::min(sim->rebuild_every, sim->rebuild_max);
     sim->chain_min_agents = min_agents;
     sim->chain_enabled = max_interval > 1 && skin_fraction > 0.0;
+    sim->policy_explicit = true;
     sim->chain_valid = false;
     sim->auto_lattice_valid = false;
     sim->state_version++;
@@ -1852,6 +1856,11 @@ int cdb_set_strip(cdb_sim *sim, int64_t ix_min, int64_t iy_min, int64_t nx_owned
     // the strip lattice in search cells (cell_size / f): every cell_size column is f columns wide; ghost blocks first / last
     const int f = sim->fine_request == 2 && sim->variant != 1 ? 2 : 1;
     sim->strip_fine = f;
+    // kept block lists (cdb_set_rebuild_policy before cdb_set_strip): the columns the caller partitions are columns of the
+    // WIDENED cells, cell_size * (1 + skin) -- every rank bins, owns and hands over agents on that lattice
+    sim->strip_scale = sim->policy_explicit && sim->chain_enabled && sim->rebuild_max > 1 && sim->skin_frac > 0.0 && sim->variant == 3 ? 1.0 + sim->skin_frac : 1.0;
+    sim->strip_kind = 0;
+    sim->chain_valid = false;
     sim->strip_ix0 = ix_min - sim->has_left; sim->strip_col_lo = sim->has_left; sim->strip_col_hi = nx - 1 - sim->has_right;
     sim->grid = Grid{f * (ix_min - sim->has_left), f * iy_min, f * nx, f * ny, f * nx * f * ny, f * sim->has_left, f * (nx - sim->has_right) - 1};
     sim->lattice_fixed = true;
@@ -1888,21 +1897,44 @@ static int strip_begin_impl(cdb_sim *sim, uint32_t flags, double cell_size, doub
     if (!sim->strip) return fail(CDB_ERR_STATE, "cdb_set_strip has not been called");
     if (sim->variant == 1) return fail(CDB_ERR_STATE, "the strip decomposition needs kernel variant 2 or 3");
     if (direct && !sim->x_connected) return fail(CDB_ERR_STATE, "cdb_strip_exchange_connect_* has not been called");
+    const int kind = sim->strip_kind;
+    const bool chain = kind != 0, kept = kind == 2 || kind == 3;
+    if (chain && (sim->strip_scale <= 1.0 || !use_pairs(sim) || !(flags & CDB_STEP_AGENT_AGENT) || !(flags & CDB_STEP_INTEGRATOR)))
+        return fail(CDB_ERR_STATE, "kept block lists need cdb_set_rebuild_policy before cdb_set_strip and whole integrating steps");
+    if (sim->strip_scale > 1.0 && !((SIGTH_SOC + 2.0 * sim->ext_max) * (1.0 + 1e-9) < cell_size))
+        return fail(CDB_ERR_STATE, "widened search cells need 3 + 2 max R < cell_size");
+    if (kept && !(sim->chain_valid && sim->chain_version == sim->state_version && sim->chain_cell_size == cell_size))
+        return fail(CDB_ERR_STATE, "a kept step must follow a step of the same run of kept block lists");
     if (flags & CDB_STEP_AGENT_AGENT) CKS(prepare_pairs(sim));
     CKS(prof_mark(sim));
-    LAUNCH(sim, k_vmax_init, 1, 32, 0, sim->d_vmax);
+    if (!kept) LAUNCH(sim, k_vmax_init, 1, 32, 0, sim->d_vmax);
     LAUNCH(sim, k_counters_zero, 1, 32, 0, sim->d_counters, 4);      // migrant counters of this step
+    if (chain) LAUNCH(sim, k_chain_begin, 1, 32, 0, sim->d_chain, sim->d_vmax, kept ? 0 : 1);
     const int f = sim->strip_fine;
-    CKS(build_block_list(sim, cell_size, false, sim->d_vmax, false, f));
+    if (!kept) {
+        CKS(build_block_list(sim, cell_size, false, sim->d_vmax, false, f, sim->strip_scale));
+        if (chain) {
+            sim->chain_rebuilds++;
+            sim->chain_cell_size = cell_size;
+            sim->drift_limit = 0.5 * (cell_size * sim->strip_scale - (SIGTH_SOC + 2.0 * sim->ext_max) * (1.0 + 1e-9)) * (1.0 - 1e-9);
+        }
+    } else {
+        sim->tables_valid = true;        // of the kept order: same slots, same cells, same ghost columns
+        sim->chain_kept++;
+    }
     const int rec = sim->model == CDB_MODEL_CIRCULAR ? REC_CIRC : REC_THREE;
-    // a halo message is one cell_size column = f consecutive columns of the search lattice = f * ny consecutive cells
+    // a halo message is one column of the strip lattice = f consecutive columns of the search lattice = f * ny consecutive
+    // cells; on a kept step it is the SAME slice of slots, with the records k_finish wrote in place
     const int nyb = (int)sim->grid.ny * f;
     const unsigned long long seq = (unsigned long long)sim->iterations + 1;
+    // direct exchange: two receive buffers per side, alternating with the step -- on kept steps no migrant handshake
+    // separates my next halo from the neighbour's reading of the previous one
+    const size_t par_off = direct ? (size_t)(seq & 1ULL) * (size_t)cdb_halo_buffer_doubles(sim) : 0;
     if (sim->has_left && halo_left_out)
-        LAUNCH(sim, k_halo_pack, 32, 256, 0, sim->d_nbr, rec, sim->d_cell_start, sim->d_cell_count, (int)sim->strip_col_lo, nyb, halo_left_out,
+        LAUNCH(sim, k_halo_pack, 32, 256, 0, sim->d_nbr, rec, sim->d_cell_start, sim->d_cell_count, (int)sim->strip_col_lo, nyb, halo_left_out + par_off,
                (long long)sim->halo_cap, sim->d_error, sim->x_done, direct ? sim->p_flags[0] + 1 : nullptr, seq);   // I am its right neighbour
     if (sim->has_right && halo_right_out)
-        LAUNCH(sim, k_halo_pack, 32, 256, 0, sim->d_nbr, rec, sim->d_cell_start, sim->d_cell_count, (int)sim->strip_col_hi, nyb, halo_right_out,
+        LAUNCH(sim, k_halo_pack, 32, 256, 0, sim->d_nbr, rec, sim->d_cell_start, sim->d_cell_count, (int)sim->strip_col_hi, nyb, halo_right_out + par_off,
                (long long)sim->halo_cap, sim->d_error, sim->x_done ? sim->x_done + 1 : nullptr, direct ? sim->p_flags[1] + 0 : nullptr, seq);
     CK(cudaGetLastError());
     return CDB_OK;
@@ -1950,24 +1982,40 @@ static int strip_finish_impl(cdb_sim *sim, uint32_t flags, double dt_min, double
         else LAUNCH(sim, k_ghost_clear, 4, 256, 0, sim->d_cell_start, sim->d_cell_count, col, ny, base_r);
     }
     CKS(prof_mark(sim));
-    // variant 3, integrating step: the finish kernel itself hands over the agents that left the owned columns
-    const bool fused_migrants = use_pairs(sim) && (flags & CDB_STEP_INTEGRATOR) && sim->n_sorted > 0;
+    const int kind = sim->strip_kind;
+    const bool chain = kind != 0, kept = kind == 2 || kind == 3;
+    const bool migrate = kind == 0 || kind == 3 || kind == 4;   // steps whose successor rebuilds the block list hand their leavers over
+    // variant 3, integrating step (every step rebuilds): the finish kernel itself hands over the agents that left the owned columns
+    const bool fused_migrants = use_pairs(sim) && (flags & CDB_STEP_INTEGRATOR) && sim->n_sorted > 0 && kind == 0;
     MigrantArgs mig{};
-    mig.enabled = 1; mig.cell_size = sim->cell_size; mig.ix0 = sim->strip_ix0;
+    mig.enabled = 1; mig.cell_size = sim->cell_size * sim->strip_scale; mig.ix0 = sim->strip_ix0;
     mig.col_lo = (int)sim->strip_col_lo; mig.col_hi = (int)sim->strip_col_hi; mig.has_left = sim->has_left; mig.has_right = sim->has_right;
     mig.msg_left = mig_left_out; mig.msg_right = mig_right_out; mig.cap = sim->mig_cap; mig.counters = sim->d_counters; mig.error = sim->d_error;
     if (mig.has_left && !mig_left_out) mig.has_left = 0;
     if (mig.has_right && !mig_right_out) mig.has_right = 0;
-    CKS(launch_step_kernel(sim, flags, dt_min, dt_max, nullptr, fused_migrants ? &mig : nullptr));
+    sim->chain_step = chain;
+    sim->chain_inplace = kept;
+    const int rc = launch_step_kernel(sim, flags, dt_min, dt_max, nullptr, fused_migrants ? &mig : nullptr);
+    sim->chain_step = false;
+    sim->chain_inplace = false;
+    CKS(rc);
+    if (chain) {
+        LAUNCH(sim, k_chain_end, 1, 32, 0, sim->d_chain, sim->pb.ctr, (long long)sim->pb.cap);
+        sim->chain_valid = true;
+        sim->chain_version = sim->state_version;
+    }
     CKS(prof_mark(sim));
     sim->iterations++;
     LAUNCH(sim, k_step_advance, 1, 32, 0, sim->d_stepctr, (const unsigned long long *)nullptr, 0LL);
-    if (sim->n > 0 && !fused_migrants)
-        LAUNCH(sim, k_migrants_pack, cdiv(sim->n, 256), 256, 0, sim->cur, (int)sim->n, sim->dev_counts ? &sim->d_counts->slots : nullptr, sim->n_planes, sim->cell_size, sim->strip_ix0,
-               (int)sim->strip_col_lo, (int)sim->strip_col_hi, sim->has_left, sim->has_right, mig_left_out, mig_right_out, (long long)sim->mig_cap,
-               sim->d_counters, sim->d_error);
-    LAUNCH(sim, k_migrants_header, 1, 32, 0, sim->has_left ? mig_left_out : nullptr, sim->has_right ? mig_right_out : nullptr, sim->d_counters,
-           (long long)sim->mig_cap, direct && sim->has_left ? sim->p_flags[0] + 3 : nullptr, direct && sim->has_right ? sim->p_flags[1] + 2 : nullptr, seq);
+    if (migrate) {
+        if (sim->n > 0 && !fused_migrants)
+            LAUNCH(sim, k_migrants_pack, cdiv(sim->n, 256), 256, 0, sim->cur, (int)sim->n, sim->dev_counts ? &sim->d_counts->slots : nullptr, sim->n_planes,
+                   sim->cell_size * sim->strip_scale, sim->strip_ix0, (int)sim->strip_col_lo, (int)sim->strip_col_hi, sim->has_left, sim->has_right,
+                   mig_left_out, mig_right_out, (long long)sim->mig_cap, sim->d_counters, sim->d_error);
+        LAUNCH(sim, k_migrants_header, 1, 32, 0, sim->has_left ? mig_left_out : nullptr, sim->has_right ? mig_right_out : nullptr, sim->d_counters,
+               (long long)sim->mig_cap, direct && sim->has_left ? sim->p_flags[0] + 3 : nullptr, direct && sim->has_right ? sim->p_flags[1] + 2 : nullptr, seq);
+        if (chain) sim->chain_valid = false;         // slots were vacated: the next step has to rebuild
+    }
     CK(cudaGetLastError());
     CKS(prof_mark(sim));
     return CDB_OK;
@@ -1982,8 +2030,9 @@ int cdb_strip_finish(cdb_sim *sim, uint32_t flags, double dt_min, double dt_max,
 int cdb_strip_finish_direct(cdb_sim *sim, uint32_t flags, double dt_min, double dt_max, int recv_halo) {
     SIM_ENTRY();
     if (!sim->x_connected) return fail(CDB_ERR_STATE, "cdb_strip_exchange_connect_* has not been called");
-    return strip_finish_impl(sim, flags, dt_min, dt_max, recv_halo ? sim->x_halo_in[0] : nullptr, recv_halo ? sim->x_halo_in[1] : nullptr,
-                             sim->p_mig[0], sim->p_mig[1], true);
+    const size_t par_off = (size_t)(((unsigned long long)sim->iterations + 1) & 1ULL) * (size_t)cdb_halo_buffer_doubles(sim);
+    return strip_finish_impl(sim, flags, dt_min, dt_max, recv_halo ? sim->x_halo_in[0] + par_off : nullptr,
+                             recv_halo ? sim->x_halo_in[1] + par_off : nullptr, sim->p_mig[0], sim->p_mig[1], true);
 }
 
 // exact counts back on the host (one sync): slots in use, slots vacated by the last step's migrants; also surfaces device errors
@@ -2045,8 +2094,8 @@ int cdb_strip_exchange_alloc(cdb_sim *sim) {
     if (!sim->strip) return fail(CDB_ERR_STATE, "cdb_set_strip has not been called");
     const size_t hb = (size_t)cdb_halo_buffer_doubles(sim), mb = (size_t)cdb_migrant_buffer_doubles(sim);
     for (int k = 0; k < 2; ++k) {
-        CKS(dev_alloc(&sim->x_halo_in[k], hb)); CKS(dev_alloc(&sim->x_mig_in[k], mb));
-        CK(cudaMemset(sim->x_halo_in[k], 0, hb * sizeof(double))); CK(cudaMemset(sim->x_mig_in[k], 0, mb * sizeof(double)));
+        CKS(dev_alloc(&sim->x_halo_in[k], 2 * hb)); CKS(dev_alloc(&sim->x_mig_in[k], mb));     // halo: one buffer per step parity
+        CK(cudaMemset(sim->x_halo_in[k], 0, 2 * hb * sizeof(double))); CK(cudaMemset(sim->x_mig_in[k], 0, mb * sizeof(double)));
     }
     CKS(dev_alloc(&sim->x_flags, 8)); CKS(dev_alloc(&sim->x_done, 4));
     CK(cudaMemset(sim->x_flags, 0, 8 * sizeof(unsigned long long))); CK(cudaMemset(sim->x_done, 0, 4 * sizeof(unsigned int)));
@@ -2096,6 +2145,26 @@ int cdb_strip_exchange_connect_local(cdb_sim *sim, cdb_sim *left, cdb_sim *right
         sim->p_flags[k] = side[k]->x_flags;
     }
     sim->x_connected = true;
+    return CDB_OK;
+}
+
+int cdb_strip_set_kind(cdb_sim *sim, int kind) {
+    SIM_ENTRY();
+    if (!sim->strip) return fail(CDB_ERR_STATE, "cdb_set_strip has not been called");
+    if (kind < 0 || kind > 4) return fail(CDB_ERR_INVALID_VALUE, "step kind must be 0 .. 4");
+    if (kind != 0 && sim->strip_scale <= 1.0) return fail(CDB_ERR_STATE, "kept block lists need cdb_set_rebuild_policy before cdb_set_strip");
+    sim->strip_kind = kind;
+    return CDB_OK;
+}
+
+int cdb_strip_drift(cdb_sim *sim, double *disp_last, double *disp_acc, double *drift_limit) {
+    SIM_ENTRY();
+    ChainState h;
+    CK(cudaMemcpyAsync(&h, sim->d_chain, sizeof(ChainState), cudaMemcpyDeviceToHost, sim->stream));
+    CKS(check_device_error(sim));     // synchronizes; a sweep that found its block list stale surfaces here
+    if (disp_last) *disp_last = h.disp_last;
+    if (disp_acc) *disp_acc = h.disp_acc;
+    if (drift_limit) *drift_limit = sim->drift_limit;
     return CDB_OK;
 }
 

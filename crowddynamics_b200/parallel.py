@@ -63,6 +63,21 @@ class CudaStripDevice:
     def set_search_refinement(self, refinement):
         self.dev.set_search_refinement(refinement)
 
+    def set_rebuild_policy(self, skin_fraction, max_interval, min_agents=0):
+        self.dev.set_rebuild_policy(skin_fraction, max_interval, min_agents)
+
+    def set_kind(self, kind):
+        _lib.check(self.lib.cdb_strip_set_kind(self.handle, int(kind)))
+
+    def drift(self):
+        """-> (largest displacement of the last step, drift bound since the last rebuild, its limit); one synchronisation"""
+        a, b, c = C.c_double(), C.c_double(), C.c_double()
+        _lib.check(self.lib.cdb_strip_drift(self.handle, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
+    def rebuild_stats(self):
+        return self.dev.rebuild_stats()
+
     def set_strip(self, ix_min, iy_min, nx_owned, ny, has_left, has_right, halo_cap, mig_cap):
         _lib.check(self.lib.cdb_set_strip(self.handle, ix_min, iy_min, nx_owned, ny, int(has_left), int(has_right),
                                           halo_cap, mig_cap))
@@ -158,7 +173,9 @@ class StripSimulation:
     """One rank's strip of a crowd that is decomposed along x."""
 
     def __init__(self, dev, rank, world, bounds, lattice, cell_size, halo_cap, mig_cap, tensor_device, n_owned,
-                 dist=None, flags=_lib.STEP_ALL, dt_min=0.01, dt_max=0.01, model=None, ext_max=None):
+                 dist=None, flags=_lib.STEP_ALL, dt_min=0.01, dt_max=0.01, model=None, ext_max=None, skin=0.0, max_interval=16):
+        """``bounds`` / ``lattice`` are in columns of ``cell_size * (1 + skin)``.  ``skin`` > 0: block lists are kept for up to
+        ``max_interval`` steps (cdb_strip_set_kind); every rank must pass the same values."""
         import torch
         self.torch = torch
         self.dist = dist
@@ -185,6 +202,17 @@ class StripSimulation:
                 self.refinement = 2
         if hasattr(dev, 'set_search_refinement'):
             dev.set_search_refinement(self.refinement)
+        # kept block lists: the same interval on every rank, sized from the all-reduced displacement (adapt_interval)
+        self.skin = float(skin) if hasattr(dev, 'set_kind') else 0.0
+        self.max_interval = int(max_interval)
+        self.interval = 1
+        self._since = 0               # steps issued on the current block list
+        self._steps = 0
+        self._force_rebuild = True    # the first step, and the first one after settle(), rebuild
+        if self.skin > 0.0:
+            if ext_max is None or not (3.0 + 2.0 * ext_max) * (1.0 + 1e-9) < self.cell_size:
+                raise ValueError('kept block lists need 3 + 2 max R < cell_size (the pair set must not depend on the lattice)')
+            dev.set_rebuild_policy(self.skin, max(2, self.max_interval))
         halo_doubles, mig_doubles = dev.set_strip(self.bounds[rank], iy_min, self.bounds[rank + 1] - self.bounds[rank], ny,
                                                   self.left is not None, self.right is not None, halo_cap, mig_cap)
 
@@ -293,11 +321,39 @@ class StripSimulation:
             e.record()
             marks.append(e)
 
+    # -- kept block lists: which kind of step comes next (cdb_strip_set_kind); identical on every rank ---------------------
+    def plan_step(self):
+        """-> (kind, migrate): 0 rebuild + migrants (no kept lists at all), 1 rebuild, 2 kept, 3 kept + migrants, 4 rebuild + migrants"""
+        if self.skin <= 0.0:
+            return 0, True
+        rebuild = self._force_rebuild or self._since == 0
+        last = self._since + 1 >= self.interval          # the next step rebuilds
+        kind = (4 if last else 1) if rebuild else (3 if last else 2)
+        self.dev.set_kind(kind)
+        return kind, last
+
+    def end_step(self, migrate):
+        self._force_rebuild = False
+        self._since = 0 if migrate else self._since + 1
+        self._steps += 1
+
+    def adapt_due(self):
+        return self.skin > 0.0 and (self._steps == 2 or self._steps % 32 == 0)
+
+    def adapt_interval(self, disp_max, limit):
+        """Common rebuild interval from the largest per-step displacement over ALL ranks (margin 1.5; the device refuses to
+        sweep a stale list, which in strip mode is an error rather than a repeat)."""
+        if disp_max > 0.0 and np.isfinite(disp_max) and limit > 0.0:
+            self.interval = int(max(1, min(self.max_interval, np.floor(limit / (1.5 * disp_max)))))
+        else:
+            self.interval = 1
+
     def step(self, n_steps=1):
         rec = getattr(self, '_phase_events', None)
         for _ in range(n_steps):
             marks = [] if rec is not None and len(rec) < 2048 else None
             self._mark(marks)
+            kind, migrate = self.plan_step()
             self.phase_begin()
             self._mark(marks)
             self._exchange(self.halo_out, self.halo_in)
@@ -308,15 +364,28 @@ class StripSimulation:
             self._mark(marks)
             self.phase_finish()
             self._mark(marks)
-            self._exchange(self.mig_out, self.mig_in)
+            if migrate:
+                self._exchange(self.mig_out, self.mig_in)
             self._mark(marks)
-            self.phase_absorb()
+            if migrate:
+                self.phase_absorb()
             self._mark(marks)
+            self.end_step(migrate)
             if marks is not None:
                 rec.append(marks)
+            if self.adapt_due():
+                last, _, limit = self.dev.drift()
+                if self.dist is not None and self.world > 1:
+                    t = self.torch.tensor([last], dtype=self.torch.float64, device=self.vmax.device)
+                    self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+                    last = float(t.item())
+                self.adapt_interval(last, limit)
 
     def settle(self):
         """Move agents that were generated outside this rank's columns to their owner (one hop), without stepping."""
+        if self.skin > 0.0:
+            self.dev.set_kind(0)
+        self._force_rebuild, self._since = True, 0
         self.phase_begin(flags=0, send_halo=False)
         self.phase_finish(flags=0, use_halo=False)
         self._exchange(self.mig_out, self.mig_in)
@@ -328,14 +397,16 @@ class StripSimulation:
     # -- construction helpers ---------------------------------------------------------------------------------------------
     @classmethod
     def from_global(cls, agents, obstacles, fields, cell_size, rank, world, device_index=0, dist=None, lattice=None,
-                    flags=_lib.STEP_ALL, dt_min=0.01, dt_max=0.01, make_device=None, tensor_device=None, slack=1.5):
+                    flags=_lib.STEP_ALL, dt_min=0.01, dt_max=0.01, make_device=None, tensor_device=None, slack=1.5,
+                    skin=0.0, max_interval=16):
         """Every rank holds the same global `agents` array and keeps the agents of its own cell columns
         (global id = row index).  Used by the tests: the union over ranks must reproduce the single-GPU result."""
         model = model_of(agents)
-        lattice = lattice or lattice_of(agents['position'], cell_size)
+        bin_size = cell_size * (1.0 + skin)            # columns of the (possibly widened) strip lattice
+        lattice = lattice or lattice_of(agents['position'], bin_size)
         ix_min, iy_min, nx, ny = lattice
         bounds = partition_columns(ix_min, nx, world)
-        cols = np.floor(agents['position'][:, 0] / cell_size).astype(np.int64)
+        cols = np.floor(agents['position'][:, 0] / bin_size).astype(np.int64)
         mine = owner_of_columns(cols, bounds) == rank
         ids = np.nonzero(mine)[0].astype(np.int64)
         local = np.ascontiguousarray(agents[mine])
@@ -362,11 +433,11 @@ class StripSimulation:
             arm = np.maximum(arm, np.abs(agents['r_ts']) * (1.0 + 1e-9))
             ext = float(np.max(np.maximum(agents['r_t'], arm + agents['r_s'])))
         return cls(dev, rank, world, bounds, lattice, cell_size, halo_cap, mig_cap, tensor_device, len(local), dist=dist,
-                   flags=flags, dt_min=dt_min, dt_max=dt_max, model=model, ext_max=ext)
+                   flags=flags, dt_min=dt_min, dt_max=dt_max, model=model, ext_max=ext, skin=skin, max_interval=max_interval)
 
     @classmethod
     def synthetic(cls, model, n_per_rank, density, rank, world, device_index, seed=0, cell_size=3.6, dist=None,
-                  dt_min=0.01, dt_max=0.01):
+                  dt_min=0.01, dt_max=0.01, skin=0.0, max_interval=16):
         """Weak-scaling benchmark crowd: every rank generates its own n_per_rank agents in its own square of a
         world x 1 row of rooms without inner walls (one walled rectangle); strips are aligned to cell columns, so agents a
         rank generated beyond its last column are handed to the neighbour before the first step."""
@@ -377,12 +448,13 @@ class StripSimulation:
         agents, _, _ = S.uniform_crowd(n_per_rank, model, density=density, seed=seed, origin=(rank * side, 0.0))
         obstacles = S.walls_of_box(0.0, 0.0, world * side, side)
         ix_min, iy_min = -1, -1
-        nx = int(math.floor(world * side / cell_size)) + 3
-        ny = int(math.floor(side / cell_size)) + 3
+        bin_size = cell_size * (1.0 + skin)
+        nx = int(math.floor(world * side / bin_size)) + 3
+        ny = int(math.floor(side / bin_size)) + 3
         # column boundaries follow the rooms: rank g owns the columns whose left edge lies in [g * side, (g + 1) * side)
-        bounds = [ix_min] + [int(math.ceil(g * side / cell_size)) for g in range(1, world)] + [ix_min + nx]
+        bounds = [ix_min] + [int(math.ceil(g * side / bin_size)) for g in range(1, world)] + [ix_min + nx]
         mid = MODEL_CIRCULAR if model == 'circular' else MODEL_THREE_CIRCLE
-        per_col = int(1.3 * density * cell_size * side) + 256
+        per_col = int(1.3 * density * bin_size * side) + 256
         halo_cap, mig_cap = per_col, per_col
         capacity = int(1.05 * n_per_rank) + 4 * mig_cap
         dev = CudaStripDevice(mid, capacity, device_index, stream=torch.cuda.current_stream().cuda_stream)
@@ -393,13 +465,14 @@ class StripSimulation:
         mg, uv = S.direction_field(1.0, (x0 - 8.0, 0.0, x0 + side + 8.0, side), 'exit', point=(world * side, side / 2))
         dev.set_navigation_field(0, mg, uv)
         sim = cls(dev, rank, world, bounds, (ix_min, iy_min, nx, ny), cell_size, halo_cap, mig_cap,
-                  torch.device('cuda', device_index), n_per_rank, dist=dist, dt_min=dt_min, dt_max=dt_max, model=mid)
+                  torch.device('cuda', device_index), n_per_rank, dist=dist, dt_min=dt_min, dt_max=dt_max, model=mid,
+                  skin=skin, max_interval=max_interval)
         sim.settle()
         return sim
 
 
 def strong_scaling_strip(model, n_total, density, rank, world, device_index, geometry='room', seed=0, cell_size=3.6, dist=None,
-                         dt_min=0.01, dt_max=0.01):
+                         dt_min=0.01, dt_max=0.01, skin=0.0, max_interval=16):
     """Strong-scaling benchmark crowd (BASELINE configs 4 and 5): ONE square room of n_total agents split into `world` strips
     of (almost) equal width; every rank generates the lattice columns of its own strip (``synthetic.uniform_slab``).
     geometry: 'room' = four walls (config 5), 'room_exit' = a door in the right wall + exit hall, 11 wall segments (config 4).
@@ -409,12 +482,13 @@ def strong_scaling_strip(model, n_total, density, rank, world, device_index, geo
     m = int(math.ceil(math.sqrt(n_total)))
     side = m / math.sqrt(density)
     ix_min, iy_min = -1, -1
-    nx = int(math.floor((side + (5.0 if geometry == 'room_exit' else 0.0)) / cell_size)) + 3
-    ny = int(math.floor(side / cell_size)) + 3
-    inner = int(math.floor(side / cell_size)) + 1          # columns that hold agents initially
+    bin_size = cell_size * (1.0 + skin)
+    nx = int(math.floor((side + (5.0 if geometry == 'room_exit' else 0.0)) / bin_size)) + 3
+    ny = int(math.floor(side / bin_size)) + 3
+    inner = int(math.floor(side / bin_size)) + 1           # columns that hold agents initially
     bounds = [ix_min] + [int(round(inner * g / world)) for g in range(1, world)] + [ix_min + nx]
-    x_lo = -np.inf if rank == 0 else bounds[rank] * cell_size
-    x_hi = np.inf if rank == world - 1 else bounds[rank + 1] * cell_size
+    x_lo = -np.inf if rank == 0 else bounds[rank] * bin_size
+    x_hi = np.inf if rank == world - 1 else bounds[rank + 1] * bin_size
     agents, ids, _ = S.uniform_slab(n_total, model, density=density, seed=seed, x_lo=x_lo, x_hi=x_hi)
     if geometry == 'room_exit':
         obstacles = S.room_exit_walls(side)
@@ -422,18 +496,19 @@ def strong_scaling_strip(model, n_total, density, rank, world, device_index, geo
     else:
         obstacles = S.walls_of_box(0.0, 0.0, side, side)
     mid = MODEL_CIRCULAR if model == 'circular' else MODEL_THREE_CIRCLE
-    per_col = int(1.3 * density * cell_size * side) + 256
+    per_col = int(1.3 * density * bin_size * side) + 256
     halo_cap, mig_cap = per_col, per_col
     capacity = int(1.05 * len(agents)) + 4 * mig_cap
     dev = CudaStripDevice(mid, capacity, device_index, stream=torch.cuda.current_stream().cuda_stream)
     dev.upload(agents, ids)
     dev.set_obstacles(obstacles)
-    fx0 = max(0.0, (bounds[rank] if rank else 0) * cell_size - 8.0)
-    fx1 = min(side + 5.0, (bounds[rank + 1] if rank < world - 1 else nx) * cell_size + 8.0)
+    fx0 = max(0.0, (bounds[rank] if rank else 0) * bin_size - 8.0)
+    fx1 = min(side + 5.0, (bounds[rank + 1] if rank < world - 1 else nx) * bin_size + 8.0)
     mg, uv = S.direction_field(1.0, (fx0, 0.0, fx1, side), 'exit', point=(side + 0.15, side / 2))
     dev.set_navigation_field(0, mg, uv)
     sim = StripSimulation(dev, rank, world, bounds, (ix_min, iy_min, nx, ny), cell_size, halo_cap, mig_cap,
-                          torch.device('cuda', device_index), len(agents), dist=dist, dt_min=dt_min, dt_max=dt_max, model=mid)
+                          torch.device('cuda', device_index), len(agents), dist=dist, dt_min=dt_min, dt_max=dt_max, model=mid,
+                          skin=skin, max_interval=max_interval)
     sim.settle()
     return sim
 
@@ -464,6 +539,9 @@ class LocalGroup:
 
     def settle(self):
         for s in self.sims:
+            if s.skin > 0.0:
+                s.dev.set_kind(0)
+            s._force_rebuild, s._since = True, 0
             s.phase_begin(flags=0, send_halo=False)
         for s in self.sims:
             s.phase_finish(flags=0, use_halo=False)
@@ -474,6 +552,9 @@ class LocalGroup:
     def step(self, n_steps=1):
         torch = self.sims[0].torch
         for _ in range(n_steps):
+            plans = [s.plan_step() for s in self.sims]
+            assert len(set(plans)) == 1                # every strip issues the same kind of step
+            migrate = plans[0][1]
             for s in self.sims:
                 s.phase_begin()
             self._exchange('halo_out', 'halo_in')
@@ -488,9 +569,16 @@ class LocalGroup:
                     s.dev.import_vmax(s.vmax)
             for s in self.sims:
                 s.phase_finish()
-            self._exchange('mig_out', 'mig_in')
+            if migrate:
+                self._exchange('mig_out', 'mig_in')
+                for s in self.sims:
+                    s.phase_absorb()
             for s in self.sims:
-                s.phase_absorb()
+                s.end_step(migrate)
+            if self.sims[0].adapt_due():
+                drifts = [s.dev.drift() for s in self.sims]
+                for s in self.sims:
+                    s.adapt_interval(max(d[0] for d in drifts), min(d[2] for d in drifts))
 
     def export(self, dtype):
         """-> (agents, ids) of the whole crowd ordered by global id."""

@@ -255,6 +255,22 @@ int64_t cdb_migrant_buffer_doubles(const cdb_sim *sim);
  *   absorb  appends the received migrants.  The exact agent counts stay on the device: the host keeps upper bounds for its
  *           launch sizes and synchronises only every 16th step -- or when n_out is non-NULL (*n_out = agents now owned). */
 int cdb_strip_begin(cdb_sim *sim, uint32_t node_flags, double cell_size, double *halo_left_out, double *halo_right_out);
+/* Kept block lists in strip mode (resident-order steps, see cdb_set_rebuild_policy; the policy has to be set BEFORE
+ * cdb_set_strip, whose columns are then columns of the widened cells cell_size * (1 + skin_fraction)).  The caller -- every
+ * rank alike -- announces what the step it is about to issue is:
+ *   0  rebuilds the block list and hands its leavers over at its end (every step rebuilds: the default);
+ *   1  rebuilds; the next step keeps the order: no migrant messages, no absorb;
+ *   2  keeps the order of the last rebuild: begin only packs the halo records (same slice of slots, same per-cell counts),
+ *      finish works in place; no migrant messages, no absorb;
+ *   3  like 2, and the next step rebuilds: finish fills the migrant messages, the caller exchanges them and calls absorb;
+ *   4  like 1, but the next step rebuilds as well (an interval of one step, with the drift bookkeeping of kept lists running).
+ * An agent that drifts across the strip border between two rebuilds stays with its rank until then; the ghost column still
+ * shows it every partner within reach because it is as wide as the widened cells.  All ranks must use the same sequence of
+ * kinds; a step that finds its block list stale raises a device error (a strip cannot repeat a step on its own).
+ * cdb_strip_drift (one synchronisation): largest displacement of the last step, drift bound since the last rebuild and its
+ * limit -- what the caller sizes the common rebuild interval with. */
+int cdb_strip_set_kind(cdb_sim *sim, int kind);
+int cdb_strip_drift(cdb_sim *sim, double *disp_last, double *disp_acc, double *drift_limit);
 int cdb_strip_export_vmax(cdb_sim *sim, double *dev_vmax4);
 int cdb_strip_import_vmax(cdb_sim *sim, const double *dev_vmax4);
 int cdb_strip_finish(cdb_sim *sim, uint32_t node_flags, double dt_min, double dt_max, const double *halo_left_in,

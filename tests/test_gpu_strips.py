@@ -60,6 +60,57 @@ def test_strips_reproduce_single_device(model, world, dts, direct):
         assert np.abs(got['orientation'] - ref['orientation']).max() <= 1e-10
 
 
+@pytest.mark.parametrize('model', ['circular', 'three_circle'])
+@pytest.mark.parametrize('world', [2, 3])
+@pytest.mark.parametrize('dts', [(0.01, 0.01), (0.001, 0.01)], ids=['fixed-dt', 'adaptive-dt'])
+@pytest.mark.parametrize('direct', [False, True], ids=['messages', 'peer-memory'])
+def test_strips_with_kept_block_lists(model, world, dts, direct):
+    """Resident-order steps in strip mode (cdb_strip_set_kind): block lists kept for several steps on widened cells, halo
+    records only on kept steps, migrants on the step before a rebuild.  Against one device with the same policy -- the two
+    rebuild on different schedules, so they agree up to summation order (14 steps: bar 1e-8 m)."""
+    import torch
+    agents, obstacles, side = S.uniform_crowd(30000, model, density=1.0, seed=6)
+    agents['velocity'] *= 3.0
+    # make sure some agents cross every strip border within the horizon, whatever dt the adaptive rule picks
+    from crowddynamics_b200.parallel import lattice_of, partition_columns
+    bin_size = 3.6 * 1.10
+    lat = lattice_of(agents['position'], bin_size)
+    for col in partition_columns(lat[0], lat[2], world)[1:-1]:
+        near = np.abs(agents['position'][:, 0] - col * bin_size) < 0.25
+        agents['velocity'][near] = np.where(agents['position'][near, :1] < col * bin_size, 1.0, -1.0) * np.array([[4.0, 0.0]])
+    fields = [S.direction_field(0.5, (0, 0, side, side), 'swirl')]
+    steps = 14
+    dev = DeviceAgents(MODEL_CIRCULAR if model == 'circular' else MODEL_THREE_CIRCLE)
+    dev.set_rebuild_policy(0.10, 16, 0)
+    dev.upload(agents)
+    dev.set_obstacles(obstacles)
+    dev.set_navigation_field(0, *fields[0])
+    dev.step(2, _lib.STEP_ALL, 3.6, *dts, want_dt=False)
+    dev.step(steps - 2, _lib.STEP_ALL, 3.6, *dts, want_dt=False)
+    ref = agents.copy()
+    dev.download(ref)
+    assert dev.rebuild_stats()['kept'] > 0
+    dev.close()
+    sims = [StripSimulation.from_global(agents, obstacles, fields, 3.6, r, world, device_index=0, dt_min=dts[0], dt_max=dts[1],
+                                        skin=0.10, max_interval=16) for r in range(world)]
+    group = LocalGroup(sims, direct=direct)
+    owned0 = [set(s.export(agents.dtype)[1].tolist()) for s in sims]
+    group.step(steps)
+    torch.cuda.synchronize()
+    stats = [s.dev.rebuild_stats() for s in sims]
+    assert all(st['kept'] >= 3 and st['rebuilds'] >= 2 for st in stats), stats
+    assert sims[0].interval > 1
+    got, ids = group.export(agents.dtype)
+    assert (ids == np.arange(len(agents))).all()          # every agent owned by exactly one strip
+    owned1 = [set(s.export(agents.dtype)[1].tolist()) for s in sims]
+    if dts[0] == dts[1]:       # (adaptive dt caps the displacement at 1.4 cm per step: too little to cross within the horizon)
+        assert any(a != b for a, b in zip(owned0, owned1))   # migration happened (on the steps before a rebuild)
+    d = {k: float(np.abs(got[k] - ref[k]).max()) for k in ('position', 'velocity')}
+    assert d['position'] <= 1e-8 and d['velocity'] <= 1e-6, d
+    if model == 'three_circle':
+        assert np.abs(got['orientation'] - ref['orientation']).max() <= 1e-7
+
+
 def test_settle_moves_misplaced_agents():
     """Set-up path of the weak-scaling benchmark: ranks generate agents by coordinate, strips are aligned to cell columns,
     settle() hands the misplaced ones to their owner."""
