@@ -197,10 +197,12 @@ def run_reference(args, rank, world):
 
 def run_hallway(args):
     """BASELINE config 1: examples.simulations.Hallway, 50 Circular agents, 1000 update() iterations -- the launch-bound end of
-    the path.  Three ways through the boundary: (a) one resident FusedStep node per update(), dt read back every update like
-    the reference's Integrator node does (a host synchronisation per update); (b) the same 1000 iterations as ONE cdb_step
-    call (pairs of steps replayed as a CUDA graph on the sim's own stream); (c) the seven strict nodes per update.  Beside
-    them the serial C port of the reference on one host core (the numba original is ~10x slower than the port)."""
+    the path.  Ways through the boundary: (a) one resident FusedStep node per update(), dt read back every update like the
+    reference's Integrator node does (a host synchronisation per update), and (a') the same with deferred scalars (no
+    synchronisation); (b) the same 1000 iterations as ONE cdb_step call -- one launch of the single-block small-crowd kernel
+    (csrc/small_kernel.cuh) -- and (b') on the general pipeline (pairs of steps replayed as a CUDA graph); (c) the seven
+    strict nodes per update.  Beside them the serial C port of the reference on one host core (the numba original is ~10x
+    slower than the port)."""
     import torch
     from crowddynamics_b200 import _lib, logic as L, synthetic as S
     from crowddynamics_b200.engine import DeviceAgents
@@ -208,20 +210,24 @@ def run_hallway(args):
     from oracle import crowd_oracle as O
     updates = 1000
 
-    def fused_nodes():
+    def fused_nodes(deferred=False):
         agents, obstacles, fields = S.hallway(seed=0)
         sim = L.MultiAgentSimulation(agents, obstacles, fields)
-        sim.logic = L.FusedStep(sim, step=0.1)
+        step = L.FusedStep(sim, step=0.1, deferred=deferred)
+        sim.logic = (L.ScalarsSync(sim) << step) if deferred else step
         sim.update()
         t0 = time.perf_counter()
         for _ in range(updates):
             sim.update()
+        if deferred:
+            sim.logic.flush()
         sim.logic.state.sync_host()
         return time.perf_counter() - t0, agents
 
-    def one_call():
+    def one_call(small=True):
         agents, obstacles, fields = S.hallway(seed=0)
         dev = DeviceAgents(MODEL_CIRCULAR)
+        dev.set_small_crowd_max(256 if small else 0)
         dev.upload(agents); dev.set_obstacles(obstacles)
         for t, f in enumerate(fields):
             dev.set_navigation_field(t, *f)
@@ -254,17 +260,18 @@ def run_hallway(args):
         return time.perf_counter() - t0, agents
 
     out = {}
-    for name, fn in (('fused_node_per_update', fused_nodes), ('one_cdb_step_call_cuda_graphs', one_call),
+    for name, fn in (('fused_node_per_update', fused_nodes), ('fused_node_per_update_deferred_scalars', lambda: fused_nodes(True)),
+                     ('one_cdb_step_call', one_call), ('one_cdb_step_call_general_pipeline_cuda_graphs', lambda: one_call(False)),
                      ('strict_seven_nodes_per_update', strict_nodes), ('cpu_port_1_core', cpu_port)):
         secs, agents = fn()
         out[name] = {'seconds': secs, 'updates_per_s': updates / secs, 'agent_steps_per_s': 50 * updates / secs,
                      'us_per_update': 1e6 * secs / updates}
-    best = out['one_cdb_step_call_cuda_graphs']
+    best = out['one_cdb_step_call']
     line = {'metric': 'agent-steps/sec', 'value': best['agent_steps_per_s'], 'unit': 'agent-steps/s', 'n_gpus': 1, 'steps': updates,
             'warmup': 2, 'ms_per_step': best['us_per_update'] * 1e-3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'f64', 'data': 'synthetic',
             'config': {'workload': 'BASELINE config 1: Hallway, 50 Circular agents, 40 x 5 m, 2 walls, 2 targets (constant +-x fields '
-                                   'instead of the FMM field), dt 0.01, 1000 updates; launch-latency bound on a GPU'},
+                                   'instead of the FMM field), dt 0.01, 1000 updates; latency bound on a GPU: one thread block holds the crowd'},
             'hallway': out,
             'cpu_baseline': {'value': out['cpu_port_1_core']['agent_steps_per_s'], 'unit': 'agent-steps/s', 'cores': 1, 'kind': 'port',
                              'sample': 'the whole workload: 1000 updates of the 50-agent Hallway, serial C port of the reference'}}

@@ -73,6 +73,7 @@ def _signatures(L):
         'cdb_step': (i32, [vp, u32, f64, f64, f64, i64, vp]),
         'cdb_get_time': (i32, [vp, pf64, pi64]),
         'cdb_set_graphs': (i32, [vp, i32]),
+        'cdb_set_small_crowd_max': (i32, [vp, i64]),
         'cdb_snapshot_begin': (i32, [vp, pi64]),
         'cdb_snapshot_wait': (i32, [vp, i64, C.POINTER(vp), pi64]),
         'cdb_scalars_begin': (i32, [vp, pi64]),

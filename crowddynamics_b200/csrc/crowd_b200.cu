@@ -23,6 +23,7 @@
 #include "kernels.cuh"
 #include "step_kernel.cuh"
 #include "finish_kernel.cuh"
+#include "small_kernel.cuh"
 #include "transfer_kernels.cuh"
 #include "field_kernels.cuh"
 #include "strip_kernels.cuh"
@@ -171,6 +172,8 @@ struct cdb_sim {
     int64_t chain_rebuilds = 0, chain_kept = 0, chain_stale = 0;   // statistics (cdb_get_rebuild_stats)
     ChainState *d_chain = nullptr;
     double drift_limit = 0.0;        // of the current block list: (coverage of the search cells - interaction range) / 2
+
+    int64_t small_max = SMALL_MAX;   // crowds up to this size are stepped by one thread block (small_kernel.cuh); 0: never
 
     // obstacles / navigation
     double *d_obstacles = nullptr;
@@ -1560,6 +1563,35 @@ static int run_graph_pair(cdb_sim *sim, uint32_t flags, double cell_size, double
     return CDB_OK;
 }
 
+// Small crowds: the whole crowd in one thread block, many steps per launch (small_kernel.cuh).  The all-pairs loop adds the
+// same terms as the block list only where the pair set does not depend on the lattice (3 + 2 max R < cell_size).
+static bool small_usable(const cdb_sim *sim, uint32_t flags, double cell_size) {
+    return sim->small_max > 0 && sim->n > 0 && sim->n <= sim->small_max && sim->n <= SMALL_MAX && sim->variant == 3 && !sim->strip &&
+           !sim->lattice_fixed && !sim->profiling && sim->n_dead == 0 && cell_size > 0.0 && std::isfinite(cell_size) &&
+           (!(flags & CDB_STEP_AGENT_AGENT) || (SIGTH_SOC + 2.0 * sim->ext_max) * (1.0 + 1e-9) < cell_size);
+}
+
+static int issue_small_steps(cdb_sim *sim, uint32_t flags, double cell_size, double dt_min, double dt_max, bool log_dt, int64_t m) {
+    SmallArgs a{};
+    a.s = sim->cur; a.n = (int)sim->n;
+    a.nav = sim->d_nav; a.n_nav = sim->n_nav;
+    a.obs = sim->d_obstacles; a.n_obs = (int)sim->n_obstacles;
+    a.flags = flags; a.cell_size = cell_size; a.dt_min = dt_min; a.dt_max = dt_max;
+    a.dt_out = sim->d_dt; a.dt_log = log_dt && (flags & CDB_STEP_INTEGRATOR) ? sim->d_dt_log : nullptr;
+    a.seed = sim->seed; a.step_ptr = sim->d_stepctr; a.n_steps = (int)m;
+    a.group = 1;
+    while (a.group < 16 && 2 * a.group * sim->n <= SMALL_MAX) a.group *= 2;
+    if (sim->model == CDB_MODEL_CIRCULAR) LAUNCH(sim, k_small_steps<0>, 1, SMALL_MAX, 0, a);
+    else LAUNCH(sim, k_small_steps<1>, 1, SMALL_MAX, 0, a);
+    CK(cudaGetLastError());
+    sim->cell_size = cell_size;
+    sim->iterations += m;
+    sim->tables_valid = false;
+    sim->perm_valid = false;
+    sim->chain_valid = false;
+    return CDB_OK;
+}
+
 int cdb_step(cdb_sim *sim, uint32_t flags, double cell_size, double dt_min, double dt_max, int64_t n_steps, double *dt_out) {
     SIM_ENTRY();
     if (n_steps < 0) return fail(CDB_ERR_INVALID_VALUE, "negative n_steps");
@@ -1583,7 +1615,12 @@ int cdb_step(cdb_sim *sim, uint32_t flags, double cell_size, double dt_min, doub
         sim->profiling = prof_saved && sim->ev_used + 2 * PROF_EVENTS <= (size_t)PROFILE_MAX_STEPS * PROF_EVENTS;
         // a pair must not straddle the end of the dt ring (its first half would be overwritten before it is read back)
         const bool ring_ok = !log_dt || (sim->iterations % DT_LOG) != DT_LOG - 1;
-        if (n_steps - k >= 2 && ring_ok && graph_usable(sim, flags, cell_size)) {
+        if (small_usable(sim, flags, cell_size)) {
+            int64_t m = std::min<int64_t>(n_steps - k, 8192);
+            if (log_dt) m = std::min<int64_t>(m, DT_LOG - (sim->iterations % DT_LOG));    // up to the end of the dt ring
+            CKS(issue_small_steps(sim, flags, cell_size, dt_min, dt_max, log_dt, m));
+            k += m;
+        } else if (n_steps - k >= 2 && ring_ok && graph_usable(sim, flags, cell_size)) {
             CKS(run_graph_pair(sim, flags, cell_size, dt_min, dt_max, log_dt));
             k += 2;
         } else {
@@ -1686,6 +1723,13 @@ int cdb_get_rebuild_stats(cdb_sim *sim, int64_t *rebuilds, int64_t *kept, int64_
     if (kept) *kept = sim->chain_kept;
     if (stale) *stale = sim->chain_stale;
     if (interval) *interval = sim->rebuild_every;
+    return CDB_OK;
+}
+
+int cdb_set_small_crowd_max(cdb_sim *sim, int64_t max_agents) {
+    SIM_ENTRY();
+    if (max_agents < 0) return fail(CDB_ERR_INVALID_VALUE, "negative size");
+    sim->small_max = std::min<int64_t>(max_agents, SMALL_MAX);
     return CDB_OK;
 }
 

@@ -226,6 +226,10 @@ class DeviceAgents:
         _lib.check(self.lib.cdb_get_rebuild_stats(self.handle, *[C.byref(x) for x in v]))
         return dict(zip(('rebuilds', 'kept', 'stale', 'interval'), (x.value for x in v)))
 
+    def set_small_crowd_max(self, max_agents):
+        """Crowds up to this size are stepped by one thread block, all steps of a call in one launch (0: never)."""
+        _lib.check(self.lib.cdb_set_small_crowd_max(self.handle, int(max_agents)))
+
     def set_graphs(self, enable):
         _lib.check(self.lib.cdb_set_graphs(self.handle, 1 if enable else 0))
 

@@ -151,6 +151,12 @@ int cdb_get_time(cdb_sim *sim, double *time_tot, int64_t *iterations);
 /* cdb_step replays pairs of steps as one CUDA graph when nothing it captured changes (default on; not while profiling and
  * not in strip mode).  Results are identical either way; this only removes launch latency for small crowds. */
 int cdb_set_graphs(cdb_sim *sim, int enable);
+/* Crowds of at most max_agents agents (default and upper limit 256) are advanced by cdb_step with ONE thread block that keeps
+ * the crowd in shared memory and runs all the requested steps in one launch (the reference's example simulations are of this
+ * size: Hallway, 50 agents, examples/simulations.py:74-163).  All pairs are tested instead of a block list, which adds the
+ * same terms whenever 3 + 2 max R < cell_size (otherwise, and with max_agents = 0, the general path is used).  Contributions
+ * are added in ascending slot order: results equal the general path's up to summation order. */
+int cdb_set_small_crowd_max(cdb_sim *sim, int64_t max_agents);
 
 /* ---- asynchronous host-visible state (SaveSimulationData, logic.py:266-337 + io.py:19-45; the per-update scalars of
  * Integrator / InsideDomain / TargetReached, logic.py:71-75,343-387) -- a fully resident tree never waits for the device:
