@@ -83,3 +83,64 @@ def test_synthetic_workloads_are_seeded_and_sane():
     assert mg.indicer(np.array([[0.05, 0.19], [39.99, 4.99]])).tolist() == [[0, 1], [399, 49]]
     ar, obr, fr, side = S.room_with_exit(300, 'circular')
     assert len(obr) == 11 and (ar['target'] == 0).all()
+
+
+# ---- strips: the step schedule of kept block lists is pure host logic (crowddynamics_b200/parallel.py) -------------------------
+class _KindRecorder:
+    def __init__(self):
+        self.kinds = []
+
+    def set_kind(self, kind):
+        self.kinds.append(kind)
+
+
+def _bare_strip(skin, interval):
+    from crowddynamics_b200.parallel import StripSimulation
+    sim = StripSimulation.__new__(StripSimulation)
+    sim.dev = _KindRecorder()
+    sim.skin, sim.max_interval, sim.interval = skin, 16, interval
+    sim._since, sim._steps, sim._force_rebuild = 0, 0, True
+    return sim
+
+
+def test_strip_step_schedule():
+    """cdb_strip_set_kind: 4 = rebuild + migrants, 1 = rebuild, 2 = kept, 3 = kept + migrants (the step before a rebuild)."""
+    sim = _bare_strip(0.0, 1)                      # no kept lists at all: classic steps, nothing announced to the device
+    for _ in range(3):
+        kind, migrate = sim.plan_step()
+        assert (kind, migrate) == (0, True)
+        sim.end_step(migrate)
+    assert sim.dev.kinds == []
+    sim = _bare_strip(0.1, 1)                      # interval 1: every step rebuilds and migrates, drift bookkeeping running
+    seq = []
+    for _ in range(3):
+        kind, migrate = sim.plan_step(); seq.append((kind, migrate)); sim.end_step(migrate)
+    assert seq == [(4, True)] * 3
+    sim = _bare_strip(0.1, 4)
+    seq = []
+    for _ in range(9):
+        kind, migrate = sim.plan_step(); seq.append(kind); sim.end_step(migrate)
+    assert seq == [1, 2, 2, 3, 1, 2, 2, 3, 1] and sim.dev.kinds == seq
+    # the interval shrinks in the middle of a run of kept steps: the next step is the last one on this list
+    sim = _bare_strip(0.1, 8)
+    for _ in range(3):
+        kind, migrate = sim.plan_step(); sim.end_step(migrate)
+    sim.adapt_interval(disp_max=0.05, limit=0.21)          # floor(0.21 / 0.075) = 2
+    assert sim.interval == 2
+    kind, migrate = sim.plan_step()
+    assert (kind, migrate) == (3, True)
+    sim.end_step(migrate)
+    assert sim.plan_step() == (1, False)
+    # adapt cadence and degenerate inputs
+    sim = _bare_strip(0.1, 1)
+    due = []
+    for k in range(1, 70):
+        sim._steps = k
+        if sim.adapt_due():
+            due.append(k)
+    assert due == [2, 32, 64]
+    for bad in (0.0, float('nan'), float('inf')):
+        sim.adapt_interval(bad, 0.21)
+        assert sim.interval == 1
+    sim.adapt_interval(1e-6, 0.21)
+    assert sim.interval == 16                       # capped at max_interval
