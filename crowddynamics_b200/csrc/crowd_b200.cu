@@ -123,6 +123,7 @@ struct cdb_sim {
     int64_t pairs_known_found = -1; int pairs_known_age = 1 << 30;
     bool pairs_inflight = false;   // a non-blocking pair-count check has been issued and not read yet
     int64_t iterations_at_check = 0;   // sim->iterations when that check was queued
+    uint32_t last_flags = 0; double last_cell_size = 0.0, last_dt_min = 0.0, last_dt_max = 0.0;   // of the last cdb_step call (catch_up)
 
     // block list
     bool lattice_fixed = false;
@@ -900,9 +901,33 @@ int cdb_set_stream(cdb_sim *sim, void *cuda_stream) {
     return CDB_OK;
 }
 
+// Deferred synchronisation (cdb_set_deferred_sync) leaves the check of the last cdb_step call unread.  Entry points that hand
+// state to the host read it first and, if the device refused steps (pair list too small, search lattice stale), issue them
+// again with the parameters of that call -- the host never sees a state that is behind the step count it was told.
+static int catch_up(cdb_sim *sim) {
+    if (!sim->defer_sync || !(sim->pairs_pending || sim->pairs_inflight) || !sim->pb.ctr) return CDB_OK;
+    if (sim->pairs_inflight) { CK(sync_stream(sim)); sim->pairs_inflight = false; }
+    CKS(read_counters(sim));
+    CK(sync_stream(sim));
+    sim->pairs_pending = false;
+    bool overflow = false;
+    int64_t dev_steps = sim->iterations;
+    CKS(analyze_pairs(sim, &overflow, &dev_steps));
+    const int64_t missing = sim->iterations - dev_steps;
+    if (!overflow && missing <= 0) return CDB_OK;
+    if (!overflow) { sim->chain_stale++; sim->rebuild_every = std::max(1, sim->rebuild_every / 2); }
+    sim->chain_valid = false;
+    sim->iterations = dev_steps;
+    sim->defer_sync = false;             // the repeated steps are checked before this returns
+    const int rc = cdb_step(sim, sim->last_flags, sim->last_cell_size, sim->last_dt_min, sim->last_dt_max, missing, nullptr);
+    sim->defer_sync = true;
+    return rc;
+}
+
 int cdb_synchronize(cdb_sim *sim) {
     if (!sim) return fail(CDB_ERR_INVALID_VALUE, "sim is NULL");
     CK(cudaSetDevice(sim->device));
+    CKS(catch_up(sim));
     CK(sync_stream(sim));
     return CDB_OK;
 }
@@ -989,6 +1014,7 @@ int cdb_download_agents_aos(cdb_sim *sim, void *agents, int64_t n, int64_t items
     if (n == 0) return CDB_OK;
     if (!agents) return fail(CDB_ERR_INVALID_VALUE, "agents is NULL");
     CK(cudaSetDevice(sim->device));
+    CKS(catch_up(sim));
     const uint32_t mask = field_mask & CDB_F_ALL_MUTABLE;
     const uint32_t pack_mask = (field_mask & CDB_F_WHOLE_RECORD) ? (uint32_t)CDB_F_ALL_MUTABLE : mask;
     if (!(field_mask & CDB_F_WHOLE_RECORD)) {
@@ -1595,6 +1621,7 @@ static int issue_small_steps(cdb_sim *sim, uint32_t flags, double cell_size, dou
 int cdb_step(cdb_sim *sim, uint32_t flags, double cell_size, double dt_min, double dt_max, int64_t n_steps, double *dt_out) {
     SIM_ENTRY();
     if (n_steps < 0) return fail(CDB_ERR_INVALID_VALUE, "negative n_steps");
+    sim->last_flags = flags; sim->last_cell_size = cell_size; sim->last_dt_min = dt_min; sim->last_dt_max = dt_max;
     const bool log_dt = dt_out && (flags & CDB_STEP_INTEGRATOR);
     int64_t k = 0, copied = 0;      // steps done / dt values already returned
     const bool prof_saved = sim->profiling;
@@ -1782,6 +1809,7 @@ int cdb_profile_read(cdb_sim *sim, double ms[3], int64_t *steps) {
 
 int cdb_get_time(cdb_sim *sim, double *time_tot, int64_t *iterations) {
     SIM_ENTRY();
+    CKS(catch_up(sim));
     CK(cudaMemcpyAsync(sim->h_dt, sim->d_dt, 2 * sizeof(double), cudaMemcpyDeviceToHost, sim->stream));
     CK(sync_stream(sim));
     if (time_tot) *time_tot = sim->h_dt[1];
