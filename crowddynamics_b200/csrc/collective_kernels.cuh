@@ -408,9 +408,10 @@ __device__ __forceinline__ bool point_in_polygon(const double *__restrict__ v, i
 }
 
 // InsideDomain.update: active[id] = contains(position); counter[0] += number of flags that changed
-__global__ void k_inside_domain(Soa s, int n, const double *__restrict__ verts, int nv, uint8_t *__restrict__ active_by_id,
+__global__ void k_inside_domain(Soa s, int n_host, const int *n_dev, const double *__restrict__ verts, int nv, uint8_t *__restrict__ active_by_id,
                                 unsigned long long *counter) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = eff_n(n_host, n_dev);
     bool changed = false;
     if (t < n && s.id[t] >= 0) {
         const int id = s.id[t];
@@ -423,10 +424,10 @@ __global__ void k_inside_domain(Soa s, int n, const double *__restrict__ verts, 
 }
 
 // TargetReached.update: reached[p][id] |= contains_p(position); counts[p] = number of agents that ever reached polygon p
-__global__ void k_target_reached(Soa s, int n, const double *__restrict__ verts, const int *__restrict__ offsets, int n_polygons,
+__global__ void k_target_reached(Soa s, int n_host, const int *n_dev, const double *__restrict__ verts, const int *__restrict__ offsets, int n_polygons,
                                  uint8_t *__restrict__ reached, long long stride, unsigned long long *counts) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool live = t < n && s.id[t] >= 0;
+    const bool live = t < eff_n(n_host, n_dev) && s.id[t] >= 0;
     const int id = live ? s.id[t] : 0;
     const double px = live ? s(PX, t) : 0.0, py = live ? s(PY, t) : 0.0;
     for (int p = 0; p < n_polygons; ++p) {

@@ -219,6 +219,7 @@ struct cdb_sim {
     long long strip_ix0 = 0, strip_col_lo = 0, strip_col_hi = 0;   // cell_size columns: lattice origin, owned range
     int64_t halo_cap = 0, mig_cap = 0;
     int64_t n_dead = 0;              // slots vacated by migrants (dropped at the next sort)
+    int64_t n_global = 0;            // agents of the WHOLE crowd (cdb_strip_set_global_agents): size of the per-id flag arrays
     int *d_counters = nullptr;       // [0] migrants left, [1] migrants right, [2] appended
     DevCounts *d_counts = nullptr;   // device-side slot / live counts: in strip mode the host only keeps upper bounds in n
     DevCounts *h_counts = nullptr;   // pinned
@@ -1965,6 +1966,17 @@ int64_t cdb_halo_buffer_doubles(const cdb_sim *sim) {
 }
 int64_t cdb_migrant_buffer_doubles(const cdb_sim *sim) { return sim ? MSG_HEADER + sim->mig_cap * (sim->n_planes + 2) : -1; }
 
+// the flag arrays that travel with migrating agents (strip mode: indexed by global agent id, see AgentFlags)
+static AgentFlags strip_flags(const cdb_sim *sim) {
+    AgentFlags f{};
+    if (!sim->strip || sim->n_global <= 0) return f;
+    if (sim->d_active && sim->active_n == sim->n_global) f.active = sim->d_active;
+    if (sim->d_reached && sim->reached_n == sim->n_global && sim->n_polygons[CDB_POLY_TARGETS] > 0) {
+        f.reached = sim->d_reached; f.stride = sim->n_global; f.np = (int)sim->n_polygons[CDB_POLY_TARGETS];
+    }
+    return f;
+}
+
 static int strip_begin_impl(cdb_sim *sim, uint32_t flags, double cell_size, double *halo_left_out, double *halo_right_out, bool direct) {
     if (!sim->strip) return fail(CDB_ERR_STATE, "cdb_set_strip has not been called");
     if (sim->variant == 1) return fail(CDB_ERR_STATE, "the strip decomposition needs kernel variant 2 or 3");
@@ -2063,6 +2075,7 @@ static int strip_finish_impl(cdb_sim *sim, uint32_t flags, double dt_min, double
     mig.enabled = 1; mig.cell_size = sim->cell_size * sim->strip_scale; mig.ix0 = sim->strip_ix0;
     mig.col_lo = (int)sim->strip_col_lo; mig.col_hi = (int)sim->strip_col_hi; mig.has_left = sim->has_left; mig.has_right = sim->has_right;
     mig.msg_left = mig_left_out; mig.msg_right = mig_right_out; mig.cap = sim->mig_cap; mig.counters = sim->d_counters; mig.error = sim->d_error;
+    mig.flags = strip_flags(sim);
     if (mig.has_left && !mig_left_out) mig.has_left = 0;
     if (mig.has_right && !mig_right_out) mig.has_right = 0;
     sim->chain_step = chain;
@@ -2083,7 +2096,7 @@ static int strip_finish_impl(cdb_sim *sim, uint32_t flags, double dt_min, double
         if (sim->n > 0 && !fused_migrants)
             LAUNCH(sim, k_migrants_pack, cdiv(sim->n, 256), 256, 0, sim->cur, (int)sim->n, sim->dev_counts ? &sim->d_counts->slots : nullptr, sim->n_planes,
                    sim->cell_size * sim->strip_scale, sim->strip_ix0, (int)sim->strip_col_lo, (int)sim->strip_col_hi, sim->has_left, sim->has_right,
-                   mig_left_out, mig_right_out, (long long)sim->mig_cap, sim->d_counters, sim->d_error);
+                   mig_left_out, mig_right_out, (long long)sim->mig_cap, sim->d_counters, sim->d_error, strip_flags(sim));
         LAUNCH(sim, k_migrants_header, 1, 32, 0, sim->has_left ? mig_left_out : nullptr, sim->has_right ? mig_right_out : nullptr, sim->d_counters,
                (long long)sim->mig_cap, direct && sim->has_left ? sim->p_flags[0] + 3 : nullptr, direct && sim->has_right ? sim->p_flags[1] + 2 : nullptr, seq);
         if (chain) sim->chain_valid = false;         // slots were vacated: the next step has to rebuild
@@ -2126,10 +2139,10 @@ static int strip_absorb_impl(cdb_sim *sim, const double *mig_left_in, const doub
     const unsigned long long seq = (unsigned long long)sim->iterations;      // the step cdb_strip_finish just completed
     if (sim->has_left && mig_left_in)
         LAUNCH(sim, k_migrants_unpack, g, 128, 0, mig_left_in, sim->cur, (int)sim->n, slots_dev, sim->n_planes, (long long)sim->capacity, sim->d_counters, sim->d_error,
-               direct ? sim->x_flags + 2 : nullptr, seq);
+               direct ? sim->x_flags + 2 : nullptr, seq, strip_flags(sim));
     if (sim->has_right && mig_right_in)
         LAUNCH(sim, k_migrants_unpack, g, 128, 0, mig_right_in, sim->cur, (int)sim->n, slots_dev, sim->n_planes, (long long)sim->capacity, sim->d_counters, sim->d_error,
-               direct ? sim->x_flags + 3 : nullptr, seq);
+               direct ? sim->x_flags + 3 : nullptr, seq, strip_flags(sim));
     // The exact counts stay on the device; the host keeps an upper bound for its launch sizes and only synchronises every
     // STRIP_REFRESH steps (or when the bound would not fit the allocation, or when the caller asks for the exact count).
     // The bound grows by what can plausibly arrive in one step (agents move ~1 cm per step: a few per km of border), not by
@@ -2508,10 +2521,27 @@ int cdb_set_polygons(cdb_sim *sim, int which, const double *xy, const int64_t *o
     return CDB_OK;
 }
 
+// Strip mode: the per-agent flag arrays of these nodes are indexed by GLOBAL agent id on every rank (n = the whole crowd,
+// cdb_strip_set_global_agents); a rank's entries are authoritative for the agents it owns, a migrating agent takes its flags
+// along (AgentFlags).  Counts are per rank: the caller sums them over the ranks.
+static int64_t flag_ids(const cdb_sim *sim) { return sim->strip ? sim->n_global : sim->n; }
+
+int cdb_strip_set_global_agents(cdb_sim *sim, int64_t n_global) {
+    SIM_ENTRY();
+    if (!sim->strip) return fail(CDB_ERR_STATE, "cdb_set_strip has not been called");
+    if (n_global < 0 || n_global > 0x7fffffff) return fail(CDB_ERR_INVALID_VALUE, "bad global agent count");
+    CK(sync_stream(sim));
+    sim->n_global = n_global;
+    sim->active_n = 0;
+    sim->reached_n = 0;
+    return CDB_OK;
+}
+
 int cdb_set_active(cdb_sim *sim, const uint8_t *active, int64_t n) {
     SIM_ENTRY();
-    if (sim->strip) return fail(CDB_ERR_STATE, "InsideDomain is not available in strip mode");
-    if (n != sim->n || (n > 0 && !active)) return fail(CDB_ERR_INVALID_VALUE, "cdb_set_active: n = %lld but the device holds %lld agents", (long long)n, (long long)sim->n);
+    if (sim->strip && sim->n_global <= 0) return fail(CDB_ERR_STATE, "strip mode: cdb_strip_set_global_agents must be called first");
+    const int64_t ids = flag_ids(sim);
+    if (n != ids || (n > 0 && !active)) return fail(CDB_ERR_INVALID_VALUE, "cdb_set_active: n = %lld but the flags describe %lld agents", (long long)n, (long long)ids);
     CK(sync_stream(sim));
     if (n > sim->active_n || !sim->d_active) CKS(dev_alloc(&sim->d_active, (size_t)std::max<int64_t>(n, 1024)));
     if (n) CK(cudaMemcpy(sim->d_active, active, n, cudaMemcpyHostToDevice));
@@ -2521,7 +2551,7 @@ int cdb_set_active(cdb_sim *sim, const uint8_t *active, int64_t n) {
 
 int cdb_get_active(cdb_sim *sim, uint8_t *active, int64_t n) {
     SIM_ENTRY();
-    if (!sim->d_active || n != sim->active_n || n != sim->n) return fail(CDB_ERR_STATE, "cdb_set_active must describe the %lld agents on the device first", (long long)sim->n);
+    if (!sim->d_active || n != sim->active_n || n != flag_ids(sim)) return fail(CDB_ERR_STATE, "cdb_set_active must describe the %lld agents first", (long long)flag_ids(sim));
     CK(sync_stream(sim));
     if (n && active) CK(cudaMemcpy(active, sim->d_active, n, cudaMemcpyDeviceToHost));
     return CDB_OK;
@@ -2529,13 +2559,13 @@ int cdb_get_active(cdb_sim *sim, uint8_t *active, int64_t n) {
 
 int cdb_inside_domain(cdb_sim *sim, int64_t *n_changed) {
     SIM_ENTRY();
-    if (sim->strip) return fail(CDB_ERR_STATE, "InsideDomain is not available in strip mode");
     if (sim->n_polygons[CDB_POLY_DOMAIN] != 1) return fail(CDB_ERR_STATE, "cdb_set_polygons(CDB_POLY_DOMAIN) must be called first");
-    if (!sim->d_active || sim->active_n != sim->n) return fail(CDB_ERR_STATE, "cdb_set_active must describe the %lld agents on the device first", (long long)sim->n);
+    if (!sim->d_active || sim->active_n != flag_ids(sim) || sim->active_n <= 0 && sim->n > 0)
+        return fail(CDB_ERR_STATE, "cdb_set_active must describe the %lld agents first", (long long)flag_ids(sim));
     CK(cudaMemsetAsync(sim->d_poly_counts, 0, sizeof(unsigned long long), sim->stream));
     if (sim->n)
-        LAUNCH(sim, k_inside_domain, cdiv(sim->n, 128), 128, 0, sim->cur, (int)sim->n, sim->d_poly_xy[CDB_POLY_DOMAIN], (int)sim->poly_nv[CDB_POLY_DOMAIN],
-               sim->d_active, sim->d_poly_counts);
+        LAUNCH(sim, k_inside_domain, cdiv(sim->n, 128), 128, 0, sim->cur, (int)sim->n, sim->dev_counts ? &sim->d_counts->slots : nullptr,
+               sim->d_poly_xy[CDB_POLY_DOMAIN], (int)sim->poly_nv[CDB_POLY_DOMAIN], sim->d_active, sim->d_poly_counts);
     CK(cudaGetLastError());
     if (n_changed) {
         unsigned long long c = 0;
@@ -2548,23 +2578,26 @@ int cdb_inside_domain(cdb_sim *sim, int64_t *n_changed) {
 
 int cdb_target_reached(cdb_sim *sim, int64_t *counts, int64_t n_polygons) {
     SIM_ENTRY();
-    if (sim->strip) return fail(CDB_ERR_STATE, "TargetReached is not available in strip mode");
     const int64_t np = sim->n_polygons[CDB_POLY_TARGETS];
     if (n_polygons != np) return fail(CDB_ERR_INVALID_VALUE, "n_polygons = %lld but %lld target polygons are set", (long long)n_polygons, (long long)np);
-    if (np > 0 && sim->n > 0) {
-        if (sim->reached_n != sim->n || np * sim->n > sim->reached_cap) {     // first call for this crowd: nobody has arrived yet
-            if (np * sim->n > sim->reached_cap) { CKS(dev_alloc(&sim->d_reached, (size_t)(np * sim->n))); sim->reached_cap = np * sim->n; }
-            CK(cudaMemsetAsync(sim->d_reached, 0, (size_t)(np * sim->n), sim->stream));
+    if (sim->strip && sim->n_global <= 0) return fail(CDB_ERR_STATE, "strip mode: cdb_strip_set_global_agents must be called first");
+    if (sim->strip && np > FLAG_POLYGONS) return fail(CDB_ERR_CAPACITY, "strip mode: at most %d target polygons (their flags travel with migrating agents)", FLAG_POLYGONS);
+    const int64_t ids = flag_ids(sim);
+    if (np > 0 && ids > 0) {
+        if (sim->reached_n != ids || np * ids > sim->reached_cap) {     // first call for this crowd: nobody has arrived yet
+            if (np * ids > sim->reached_cap) { CKS(dev_alloc(&sim->d_reached, (size_t)(np * ids))); sim->reached_cap = np * ids; }
+            CK(cudaMemsetAsync(sim->d_reached, 0, (size_t)(np * ids), sim->stream));
             CK(cudaMemsetAsync(sim->d_poly_counts + 1, 0, np * sizeof(unsigned long long), sim->stream));
-            sim->reached_n = sim->n;
+            sim->reached_n = ids;
         }
-        LAUNCH(sim, k_target_reached, cdiv(sim->n, 128), 128, 0, sim->cur, (int)sim->n, sim->d_poly_xy[CDB_POLY_TARGETS], sim->d_poly_off[CDB_POLY_TARGETS], (int)np,
-               sim->d_reached, (long long)sim->n, sim->d_poly_counts + 1);
+        if (sim->n > 0)
+            LAUNCH(sim, k_target_reached, cdiv(sim->n, 128), 128, 0, sim->cur, (int)sim->n, sim->dev_counts ? &sim->d_counts->slots : nullptr,
+                   sim->d_poly_xy[CDB_POLY_TARGETS], sim->d_poly_off[CDB_POLY_TARGETS], (int)np, sim->d_reached, (long long)ids, sim->d_poly_counts + 1);
         CK(cudaGetLastError());
     }
     if (counts && np > 0) {
         std::vector<unsigned long long> c((size_t)np, 0ULL);
-        if (sim->n > 0) {
+        if (ids > 0) {
             CK(cudaMemcpyAsync(c.data(), sim->d_poly_counts + 1, np * sizeof(unsigned long long), cudaMemcpyDeviceToHost, sim->stream));
             CK(sync_stream(sim));
         }
@@ -2575,7 +2608,7 @@ int cdb_target_reached(cdb_sim *sim, int64_t *counts, int64_t n_polygons) {
 
 int cdb_get_target_reached(cdb_sim *sim, uint8_t *reached_by, int64_t n_polygons, int64_t n) {
     SIM_ENTRY();
-    if (n_polygons != sim->n_polygons[CDB_POLY_TARGETS] || n != sim->n || sim->reached_n != sim->n)
+    if (n_polygons != sim->n_polygons[CDB_POLY_TARGETS] || n != flag_ids(sim) || sim->reached_n != n)
         return fail(CDB_ERR_STATE, "cdb_target_reached must run first (on the same agents and polygons)");
     CK(sync_stream(sim));
     if (n_polygons * n > 0 && reached_by) CK(cudaMemcpy(reached_by, sim->d_reached, (size_t)(n_polygons * n), cudaMemcpyDeviceToHost));

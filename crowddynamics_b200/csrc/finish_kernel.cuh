@@ -214,7 +214,7 @@ k_finish(const StepArgs A) {
                 d[PHI] = phi; d[OMEGA] = w; d[PHI0] = phi0; d[TORQUE] = rst ? 0.0 : tq; d[TORQUE_PREV] = tq; d[TAU_ROT] = tau_rot;
                 d[STD_RAND_TORQUE] = srt;
             }
-            d[A.n_planes] = (double)id;
+            d[A.n_planes] = pack_id_flags(id, A.mig.flags);
             d[A.n_planes + 1] = (double)target;
         }
     }

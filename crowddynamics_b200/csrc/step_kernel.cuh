@@ -35,6 +35,32 @@ constexpr int CHUNK = STEP_CHUNK;     // candidates classified between two list-
 
 // strips: an agent whose new position lies in a cell_size column outside the owned range is handed to the neighbour --
 // the finish kernel appends its whole new state to that side's migrant message and vacates the slot (id = -1)
+// Per-agent flags of the host-visible state nodes (InsideDomain: active; TargetReached: reached_by of up to FLAG_POLYGONS
+// polygons), kept in arrays indexed by GLOBAL agent id on every rank.  A rank's entries are authoritative for the agents it
+// owns; when an agent migrates its flags travel in the upper bits of the id slot of the migrant record (the id itself takes
+// the low 32 bits of the 53-bit mantissa) and are written into the receiver's arrays.
+constexpr int FLAG_POLYGONS = 20;
+struct AgentFlags {
+    uint8_t *active;         // [n_global] or nullptr
+    uint8_t *reached;        // [np][stride] or nullptr
+    long long stride;
+    int np;
+};
+__device__ __forceinline__ double pack_id_flags(int id, const AgentFlags &f) {
+    unsigned long long bits = 0ULL;
+    if (f.active && f.active[id]) bits |= 1ULL;
+    if (f.reached) for (int p = 0; p < f.np; ++p) if (f.reached[(size_t)p * f.stride + id]) bits |= 2ULL << p;
+    return (double)(((unsigned long long)(unsigned int)id) | (bits << 32));
+}
+__device__ __forceinline__ int unpack_id_flags(double v, const AgentFlags &f) {
+    const unsigned long long w = (unsigned long long)v;
+    const int id = (int)(unsigned int)(w & 0xffffffffULL);
+    const unsigned long long bits = w >> 32;
+    if (f.active) f.active[id] = (uint8_t)(bits & 1ULL);
+    if (f.reached) for (int p = 0; p < f.np; ++p) f.reached[(size_t)p * f.stride + id] = (uint8_t)((bits >> (p + 1)) & 1ULL);
+    return id;
+}
+
 struct MigrantArgs {
     int enabled;
     double cell_size;
@@ -44,6 +70,7 @@ struct MigrantArgs {
     long long cap;
     int *counters;           // [0] left, [1] right
     int *error;
+    AgentFlags flags;        // flags that travel with a migrant (all null: none)
 };
 
 struct StepArgs {

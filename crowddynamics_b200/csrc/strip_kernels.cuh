@@ -4,6 +4,7 @@
 // + global id + target.
 #pragma once
 #include "kernels.cuh"
+#include "step_kernel.cuh"
 
 // ---- one-sided exchange over peer memory (NVLink): the producer writes the message straight into the consumer's receive
 // buffer and then publishes a sequence number in the consumer's memory; the consumer's kernel spins on that number.
@@ -135,7 +136,7 @@ __global__ void k_counts_set(DevCounts *c, int slots) { if (threadIdx.x == 0) { 
 // message of that side and vacate the slot (id = -1).  counters: [0] left, [1] right.
 __global__ void k_migrants_pack(Soa s, int n_host, const int *n_dev, int n_planes, double cell_size, long long ix_min_local, int col_lo,
                                 int col_hi, int has_left, int has_right, double *__restrict__ msg_left, double *__restrict__ msg_right,
-                                long long cap, int *counters, int *error) {
+                                long long cap, int *counters, int *error, AgentFlags flags) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= eff_n(n_host, n_dev) || s.id[i] < 0) return;
     const double col = floor(s(PX, i) / cell_size) - (double)ix_min_local;
@@ -147,7 +148,7 @@ __global__ void k_migrants_pack(Soa s, int n_host, const int *n_dev, int n_plane
     if (k >= cap) { atomicExch(error, ERR_CELL_RANGE + 3); return; }
     double *dst = (side == 0 ? msg_left : msg_right) + MSG_HEADER + (size_t)k * (n_planes + 2);
     for (int p = 0; p < n_planes; ++p) dst[p] = s(p, i);
-    dst[n_planes] = (double)s.id[i];
+    dst[n_planes] = pack_id_flags(s.id[i], flags);
     dst[n_planes + 1] = (double)s.target[i];
     s.id[i] = -1;
 }
@@ -165,7 +166,8 @@ __global__ void k_migrants_header(double *msg_left, double *msg_right, const int
 
 // append received migrants after the current slots; counters[2] = number appended so far
 __global__ void k_migrants_unpack(const double *__restrict__ msg, Soa s, int n_slots_host, const int *n_slots_dev, int n_planes,
-                                  long long capacity, int *counters, int *error, const unsigned long long *flag, unsigned long long seq) {
+                                  long long capacity, int *counters, int *error, const unsigned long long *flag, unsigned long long seq,
+                                  AgentFlags flags) {
     signal_wait(flag, seq);
     const int m = (int)msg[0];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -175,7 +177,7 @@ __global__ void k_migrants_unpack(const double *__restrict__ msg, Soa s, int n_s
     if (slot >= capacity) { atomicExch(error, ERR_CELL_RANGE + 4); return; }
     const double *src = msg + MSG_HEADER + (size_t)i * (n_planes + 2);
     for (int p = 0; p < n_planes; ++p) s(p, slot) = src[p];
-    s.id[slot] = (int)src[n_planes];
+    s.id[slot] = unpack_id_flags(src[n_planes], flags);
     s.target[slot] = (long long)src[n_planes + 1];
 }
 
