@@ -82,6 +82,7 @@ def _signatures(L):
         'cdb_sync_count': (i64, [vp]),
         'cdb_set_rebuild_policy': (i32, [vp, f64, i64, i64]),
         'cdb_strip_set_kind': (i32, [vp, i32]),
+        'cdb_strip_set_global_agents': (i32, [vp, i64]),
         'cdb_strip_drift': (i32, [vp, pf64, pf64, pf64]),
         'cdb_get_rebuild_stats': (i32, [vp, pi64, pi64, pi64, pi64]),
         'cdb_set_variant': (i32, [vp, i32]),

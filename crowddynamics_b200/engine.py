@@ -386,9 +386,11 @@ class DeviceAgents:
         a = np.ascontiguousarray(active).view(np.uint8)
         _lib.check(self.lib.cdb_set_active(self.handle, _ptr(a) if len(a) else None, len(a)))
 
-    def get_active(self):
-        out = np.zeros(self.n, dtype=np.uint8)
-        _lib.check(self.lib.cdb_get_active(self.handle, _ptr(out) if self.n else None, self.n))
+    def get_active(self, n=None):
+        """``n``: size of the flag array -- the uploaded agents, or the whole crowd in strip mode (cdb_strip_set_global_agents)"""
+        n = self.n if n is None else int(n)
+        out = np.zeros(n, dtype=np.uint8)
+        _lib.check(self.lib.cdb_get_active(self.handle, _ptr(out) if n else None, n))
         return out.astype(bool)
 
     def inside_domain(self, want_count=True):
@@ -401,9 +403,10 @@ class DeviceAgents:
         _lib.check(self.lib.cdb_target_reached(self.handle, _ptr(counts) if want_counts and n_polygons else None, int(n_polygons)))
         return counts if want_counts else None
 
-    def target_reached_by(self, n_polygons):
-        out = np.zeros((int(n_polygons), self.n), dtype=np.uint8)
-        _lib.check(self.lib.cdb_get_target_reached(self.handle, _ptr(out) if out.size else None, int(n_polygons), self.n))
+    def target_reached_by(self, n_polygons, n=None):
+        n = self.n if n is None else int(n)
+        out = np.zeros((int(n_polygons), n), dtype=np.uint8)
+        _lib.check(self.lib.cdb_get_target_reached(self.handle, _ptr(out) if out.size else None, int(n_polygons), n))
         return out.astype(bool)
 
     def set_lattice(self, ix_min, iy_min, nx, ny):

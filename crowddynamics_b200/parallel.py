@@ -78,6 +78,29 @@ class CudaStripDevice:
     def rebuild_stats(self):
         return self.dev.rebuild_stats()
 
+    # -- host-visible state nodes in strip mode: flag arrays indexed by GLOBAL agent id --------------------------------------
+    def set_global_agents(self, n_global):
+        self.n_global = int(n_global)
+        _lib.check(self.lib.cdb_strip_set_global_agents(self.handle, int(n_global)))
+
+    def set_polygons(self, which, polygons):
+        self.dev.set_polygons(which, polygons)
+
+    def set_active(self, active):
+        self.dev.set_active(active)
+
+    def get_active(self):
+        return self.dev.get_active(self.n_global)
+
+    def inside_domain(self):
+        return self.dev.inside_domain()
+
+    def target_reached(self, n_polygons):
+        return self.dev.target_reached(n_polygons)
+
+    def target_reached_by(self, n_polygons):
+        return self.dev.target_reached_by(n_polygons, self.n_global)
+
     def set_strip(self, ix_min, iy_min, nx_owned, ny, has_left, has_right, halo_cap, mig_cap):
         _lib.check(self.lib.cdb_set_strip(self.handle, ix_min, iy_min, nx_owned, ny, int(has_left), int(has_right),
                                           halo_cap, mig_cap))
@@ -380,6 +403,45 @@ class StripSimulation:
                     self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
                     last = float(t.item())
                 self.adapt_interval(last, limit)
+
+    # -- InsideDomain / TargetReached on strips (simulation/logic.py:343-387) ---------------------------------------------
+    def set_domain(self, polygon, n_global, active=None):
+        """``polygon``: (nv, 2) vertices of the domain; ``n_global``: agents of the whole crowd; ``active``: the initial
+        States.active flags by global id (default: all active).  Every rank calls it with the same arguments."""
+        self._n_global = int(n_global)
+        self.dev.set_global_agents(n_global)
+        self.dev.set_polygons(_lib.POLY_DOMAIN, [np.asarray(polygon, dtype=np.float64)])
+        self.dev.set_active(np.ones(n_global, dtype=bool) if active is None else np.ascontiguousarray(active, dtype=bool))
+
+    def set_targets(self, polygons, n_global):
+        if getattr(self, '_n_global', 0) != int(n_global):
+            self._n_global = int(n_global)
+            self.dev.set_global_agents(n_global)
+        self._n_targets = len(polygons)
+        self.dev.set_polygons(_lib.POLY_TARGETS, [np.asarray(p, dtype=np.float64) for p in polygons])
+
+    def _sum_over_ranks(self, values):
+        values = np.asarray(values, dtype=np.int64)
+        if self.dist is None or self.world == 1:
+            return values
+        t = self.torch.tensor(values, dtype=self.torch.int64, device=self.vmax.device)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return t.cpu().numpy()
+
+    def inside_domain(self):
+        """InsideDomain.update on the owned agents -> number of ``active`` flags that changed in the WHOLE crowd"""
+        return int(self._sum_over_ranks([self.dev.inside_domain()])[0])
+
+    def target_reached(self):
+        """TargetReached.update on the owned agents -> per polygon, agents of the whole crowd that have ever been inside it"""
+        return self._sum_over_ranks(self.dev.target_reached(self._n_targets))
+
+    def owned_flags(self, dtype):
+        """-> (ids, active, reached_by[np, len(ids)]) of the agents this rank owns now (authoritative entries only)"""
+        _, ids = self.export(dtype)
+        active = self.dev.get_active()[ids] if getattr(self, '_n_global', 0) else None
+        reached = self.dev.target_reached_by(self._n_targets)[:, ids] if getattr(self, '_n_targets', 0) else None
+        return ids, active, reached
 
     def settle(self):
         """Move agents that were generated outside this rank's columns to their owner (one hop), without stepping."""

@@ -276,6 +276,12 @@ int cdb_strip_begin(cdb_sim *sim, uint32_t node_flags, double cell_size, double 
  * cdb_strip_drift (one synchronisation): largest displacement of the last step, drift bound since the last rebuild and its
  * limit -- what the caller sizes the common rebuild interval with. */
 int cdb_strip_set_kind(cdb_sim *sim, int kind);
+/* InsideDomain / TargetReached in strip mode (logic.py:343-387): their per-agent flags (`active`, `reached_by`) live in arrays
+ * indexed by GLOBAL agent id on every rank -- n of cdb_set_active / cdb_get_active / cdb_get_target_reached is then the size of
+ * the whole crowd, announced here.  A rank's entries are authoritative for the agents it currently owns (cdb_export_agents
+ * lists them); a migrating agent takes its flags along inside the migrant message.  cdb_inside_domain / cdb_target_reached
+ * return this rank's counts: the caller adds them up over the ranks.  At most 20 target polygons in strip mode. */
+int cdb_strip_set_global_agents(cdb_sim *sim, int64_t n_global);
 int cdb_strip_drift(cdb_sim *sim, double *disp_last, double *disp_acc, double *drift_limit);
 int cdb_strip_export_vmax(cdb_sim *sim, double *dev_vmax4);
 int cdb_strip_import_vmax(cdb_sim *sim, const double *dev_vmax4);

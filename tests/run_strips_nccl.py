@@ -12,6 +12,7 @@ ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), '..'))
 sys.path.insert(0, ROOT)
 from crowddynamics_b200 import _lib, synthetic as S  # noqa: E402
 from crowddynamics_b200.engine import DeviceAgents  # noqa: E402
+from oracle import crowd_oracle as O  # noqa: E402
 from crowddynamics_b200.parallel import StripSimulation  # noqa: E402
 from crowddynamics_b200.structures import MODEL_CIRCULAR, MODEL_THREE_CIRCLE  # noqa: E402
 
@@ -31,7 +32,16 @@ def main():
                                               dt_min=dts[0], dt_max=dts[1])
             if exchange == 'peer':
                 assert sim.connect_direct(), 'CUDA IPC not available'
-            sim.step(20)
+            # InsideDomain / TargetReached over the strips: flags by global id, counts all-reduced over the ranks
+            domain = np.array([(0.2 * side, 0.15 * side), (0.85 * side, 0.1 * side), (0.9 * side, 0.8 * side), (0.1 * side, 0.7 * side)])
+            goal = np.array([(0.4 * side, 0.4 * side), (0.6 * side, 0.4 * side), (0.6 * side, 0.6 * side), (0.4 * side, 0.6 * side)])
+            sim.set_domain(domain, len(agents), agents['active'])
+            sim.set_targets([goal], len(agents))
+            inactive, reached = 0, None
+            for _ in range(4):
+                sim.step(5)
+                inactive += sim.inside_domain()
+                reached = sim.target_reached()
             torch.cuda.synchronize()
             dist.barrier()
             rec, ids = sim.export(agents.dtype)
@@ -46,10 +56,16 @@ def main():
                 dev = DeviceAgents(MODEL_CIRCULAR if model == 'circular' else MODEL_THREE_CIRCLE, device=local)
                 dev.set_rebuild_policy(0.10, 1)       # rebuild at every step, like the strips: same summation order
                 dev.upload(agents); dev.set_obstacles(obstacles); dev.set_navigation_field(0, *fields[0])
-                dev.step(20, _lib.STEP_ALL, 3.6, dts[0], dts[1], want_dt=False)
-                ref = agents.copy(); dev.download(ref); dev.close()
+                ref = agents.copy()
+                inactive_ref, reached_ref = 0, np.zeros(len(agents), dtype=bool)
+                for _ in range(4):
+                    dev.step(5, _lib.STEP_ALL, 3.6, dts[0], dts[1], want_dt=False)
+                    dev.download(ref)
+                    inactive_ref += O.inside_domain(ref, domain)
+                    O.target_reached(ref, goal, reached_ref)
+                dev.close()
                 err = np.abs(got['position'] - ref['position']).max()
-                good = (seen == 1).all() and err <= 1e-12
+                good = (seen == 1).all() and err <= 1e-12 and inactive == inactive_ref and int(reached[0]) == int(reached_ref.sum())
                 ok &= bool(good)
                 print('strips %s world=%d %-12s dt=%s: owners ok=%s max |dx|=%.3e %s' % (
                     exchange, world, model, dts, (seen == 1).all(), err, 'OK' if good else 'FAIL'), flush=True)

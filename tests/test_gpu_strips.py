@@ -111,6 +111,63 @@ def test_strips_with_kept_block_lists(model, world, dts, direct):
         assert np.abs(got['orientation'] - ref['orientation']).max() <= 1e-7
 
 
+@pytest.mark.parametrize('model', ['circular', 'three_circle'])
+@pytest.mark.parametrize('world', [2, 3])
+@pytest.mark.parametrize('skin', [0.0, 0.10], ids=['rebuild-every-step', 'kept-block-lists'])
+def test_domain_nodes_on_strips(model, world, skin):
+    """InsideDomain / TargetReached (simulation/logic.py:343-387) with the crowd split into strips: the flags live in arrays
+    indexed by global agent id, migrating agents take theirs along, counts are summed over the strips.  Against the oracle
+    applied to the single-device trajectory, update by update."""
+    import torch
+    from oracle import crowd_oracle as O
+    agents, obstacles, side = S.uniform_crowd(20000 if skin else 6000, model, density=1.0, seed=9)
+    agents['velocity'] *= 6.0 if not skin else 2.5
+    n = len(agents)
+    c = side / 2
+    domain = np.array([(0.2 * side, 0.15 * side), (0.85 * side, 0.1 * side), (0.9 * side, 0.8 * side), (c, 0.95 * side), (0.1 * side, 0.7 * side)])
+    goals = [np.array([(c - 9, c - 9), (c + 9, c - 9), (c + 9, c + 9), (c - 9, c + 9)]),
+             np.array([(0.0, 0.0), (0.3 * side, 0.0), (0.0, 0.3 * side)])]
+    fields = [S.direction_field(0.5, (0, 0, side, side), 'swirl')]
+    sims = [StripSimulation.from_global(agents, obstacles, fields, 3.6, r, world, device_index=0, skin=skin) for r in range(world)]
+    group = LocalGroup(sims)
+    for s in sims:
+        s.set_domain(domain, n, agents['active'])
+        s.set_targets(goals, n)
+    ref_dev = DeviceAgents(MODEL_CIRCULAR if model == 'circular' else MODEL_THREE_CIRCLE)
+    ref_dev.set_rebuild_policy(0.10, 16 if skin else 1, 0)
+    ref_dev.upload(agents)
+    ref_dev.set_obstacles(obstacles)
+    ref_dev.set_navigation_field(0, *fields[0])
+    ref = agents.copy()
+    reached_ref = [np.zeros(n, dtype=bool) for _ in goals]
+    inactive_ref = inactive = 0
+    updates = 10
+    for it in range(updates):
+        group.step(1)
+        ref_dev.step(1, _lib.STEP_ALL, 3.6, 0.01, 0.01, want_dt=False)
+        ref_dev.download(ref)
+        inactive += sum(s.dev.inside_domain() for s in sims)              # what StripSimulation.inside_domain() all-reduces
+        counts = np.sum([s.dev.target_reached(len(goals)) for s in sims], axis=0)
+        inactive_ref += O.inside_domain(ref, domain)
+        for g, r in zip(goals, reached_ref):
+            O.target_reached(ref, g, r)
+        assert inactive == inactive_ref, it
+        assert counts.tolist() == [int(r.sum()) for r in reached_ref], it
+    torch.cuda.synchronize()
+    assert inactive_ref > 0 and all(r.any() for r in reached_ref)
+    # every agent's flags, read from the strip that owns it now, equal the oracle's
+    seen = np.zeros(n, dtype=int)
+    moved = 0
+    for r, s in enumerate(sims):
+        ids, active, reached = s.owned_flags(agents.dtype)
+        seen[ids] += 1
+        assert (active == ref['active'][ids]).all()
+        for p in range(len(goals)):
+            assert (reached[p] == reached_ref[p][ids]).all()
+    assert (seen == 1).all()
+    ref_dev.close()
+
+
 def test_settle_moves_misplaced_agents():
     """Set-up path of the weak-scaling benchmark: ranks generate agents by coordinate, strips are aligned to cell columns,
     settle() hands the misplaced ones to their owner."""
