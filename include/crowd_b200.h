@@ -184,7 +184,7 @@ int64_t cdb_sync_count(const cdb_sim *sim);
  * exceeded is not applied, and the host rebuilds and repeats it (same protocol as a pair list that is too small).  The interval
  * adapts to the observed displacement, at most `max_interval` steps; max_interval = 1 rebuilds at every step.  Forces are the
  * same numbers up to the order in which an agent's pair contributions are added (<= 1e-15 relative).
- * Defaults: skin_fraction 0.10, max_interval 16, min_agents 16384.  Not used in strip mode, with a fixed lattice, or when
+ * Defaults: skin_fraction 0.10, max_interval 16, min_agents 16384.  In strip mode only on request (cdb_strip_set_kind below); not used with a fixed lattice, or when
  * 3 + 2 max R >= cell_size (then the pair set depends on the lattice itself). */
 int cdb_set_rebuild_policy(cdb_sim *sim, double skin_fraction, int64_t max_interval, int64_t min_agents);
 /* steps that rebuilt the block list / ran on the kept order / were refused as stale so far, and the current interval */
@@ -340,7 +340,7 @@ int cdb_get_direction(cdb_sim *sim, double *direction, int64_t n);
  * InsideDomain / TargetReached (simulation/logic.py:343-387) = matplotlib Path(vertices).contains_points(position).
  * Polygons: (x, y) vertex pairs back to back, offsets[n_polygons + 1] in vertices, implicitly closed (do not repeat the first
  * vertex).  which = CDB_POLY_DOMAIN takes exactly one polygon (field.domain.exterior), CDB_POLY_TARGETS one per measured
- * target; setting the target polygons clears their reached_by state.  Not available in strip mode. */
+ * target; setting the target polygons clears their reached_by state.  In strip mode: see cdb_strip_set_global_agents. */
 #define CDB_POLY_DOMAIN 0
 #define CDB_POLY_TARGETS 1
 int cdb_set_polygons(cdb_sim *sim, int which, const double *xy, const int64_t *offsets, int64_t n_polygons);
