@@ -1606,10 +1606,11 @@ static int issue_small_steps(cdb_sim *sim, uint32_t flags, double cell_size, dou
     a.flags = flags; a.cell_size = cell_size; a.dt_min = dt_min; a.dt_max = dt_max;
     a.dt_out = sim->d_dt; a.dt_log = log_dt && (flags & CDB_STEP_INTEGRATOR) ? sim->d_dt_log : nullptr;
     a.seed = sim->seed; a.step_ptr = sim->d_stepctr; a.n_steps = (int)m;
+    const int threads = sim->model == CDB_MODEL_CIRCULAR ? SmallThreads<0>::value : SmallThreads<1>::value;
     a.group = 1;
-    while (a.group < 16 && 2 * a.group * sim->n <= SMALL_MAX) a.group *= 2;
-    if (sim->model == CDB_MODEL_CIRCULAR) LAUNCH(sim, k_small_steps<0>, 1, SMALL_MAX, 0, a);
-    else LAUNCH(sim, k_small_steps<1>, 1, SMALL_MAX, 0, a);
+    while (a.group < 16 && 2 * a.group * sim->n <= threads) a.group *= 2;
+    if (sim->model == CDB_MODEL_CIRCULAR) LAUNCH(sim, k_small_steps<0>, 1, threads, 0, a);
+    else LAUNCH(sim, k_small_steps<1>, 1, threads, 0, a);
     CK(cudaGetLastError());
     sim->cell_size = cell_size;
     sim->iterations += m;

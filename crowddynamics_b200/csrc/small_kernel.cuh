@@ -3,7 +3,7 @@
 // crowd in shared memory and runs MANY steps per launch.  The general pipeline costs ~16 dependent launches of single-CTA
 // kernels per step for such a crowd (45 us / step even replayed as a CUDA graph); here a step costs two block barriers.
 //
-// A group of G = 1 .. 16 threads per agent (G the largest power of two with n G <= 256): every thread of a group carries the
+// A group of G = 1 .. 16 threads per agent (G the largest power of two with n G <= 512 circular / 256 three-circle threads): every thread of a group carries the
 // agent's state and runs the per-agent nodes redundantly (same inputs, same results); the pair loop is split G ways and its
 // partial sums are combined by a butterfly, which gives every thread of the group the same bits -- the single-thread
 // critical path of a step is what a small crowd costs.  Per step, in the reference's post-order (logic.py:59-165,258-261):
@@ -22,7 +22,9 @@
 #include "pair_kernels.cuh"
 #include "step_kernel.cuh"
 
-constexpr int SMALL_MAX = 256;          // agents (= threads of the one block)
+constexpr int SMALL_MAX = 256;          // agents
+// threads of the one block: the circular kernel needs half the registers and takes twice the threads (more threads per agent)
+template <int MODEL> struct SmallThreads { static constexpr int value = MODEL == 0 ? 512 : 256; };
 
 struct SmallArgs {
     Soa s;                  // the state, updated in place (slot order is irrelevant here and left alone)
@@ -38,13 +40,14 @@ struct SmallArgs {
     unsigned long long seed;
     unsigned long long *step_ptr;   // device-side step index, advanced here
     int n_steps;
-    int group;              // threads per agent (power of two, <= 16, n * group <= SMALL_MAX)
+    int group;              // threads per agent (power of two, <= 16, n * group <= threads of the block)
 };
 
 template <int MODEL>
-__global__ void __launch_bounds__(SMALL_MAX, 1) k_small_steps(const SmallArgs A) {
+__global__ void __launch_bounds__(SmallThreads<MODEL>::value, 1) k_small_steps(const SmallArgs A) {
+    constexpr int THREADS = SmallThreads<MODEL>::value;
     __shared__ double s_rec[SMALL_MAX][MODEL == 0 ? 5 : 16];     // kinematics of every agent for the pair loop
-    __shared__ unsigned long long s_vm[SMALL_MAX / 32], s_v0[SMALL_MAX / 32];
+    __shared__ unsigned long long s_vm[THREADS / 32], s_v0[THREADS / 32];
     __shared__ double s_dt;
     const int t = threadIdx.x;
     const int G = A.group, ag = t / G, sub = t - ag * G;      // agent of this thread, its place in the agent's group
