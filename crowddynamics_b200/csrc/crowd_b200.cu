@@ -583,13 +583,14 @@ int launch_step_kernel(cdb_sim *sim, unsigned flags, double dt_min, double dt_ma
     const int smem = 0;
     if (a.n > 0) {
         if (pairs) {
-            const int fb = cdiv(a.n, FIN_THREADS);
+            const int ft = a.inplace ? FIN_THREADS_INPLACE : FIN_THREADS;
+            const int fb = cdiv(a.n, ft);
             if (sim->model == CDB_MODEL_CIRCULAR) {
-                if (a.inplace) LAUNCH(sim, (k_finish<0, true>), fb, FIN_THREADS, smem, a);
-                else LAUNCH(sim, (k_finish<0, false>), fb, FIN_THREADS, smem, a);
+                if (a.inplace) LAUNCH(sim, (k_finish<0, true>), fb, ft, smem, a);
+                else LAUNCH(sim, (k_finish<0, false>), fb, ft, smem, a);
             } else {
-                if (a.inplace) LAUNCH(sim, (k_finish<1, true>), fb, FIN_THREADS, smem, a);
-                else LAUNCH(sim, (k_finish<1, false>), fb, FIN_THREADS, smem, a);
+                if (a.inplace) LAUNCH(sim, (k_finish<1, true>), fb, ft, smem, a);
+                else LAUNCH(sim, (k_finish<1, false>), fb, ft, smem, a);
             }
         } else {
             if (sim->model == CDB_MODEL_CIRCULAR) LAUNCH(sim, k_step<0>, cdiv(a.n, STEP_THREADS), STEP_THREADS, smem, a);

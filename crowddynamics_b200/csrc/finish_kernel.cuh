@@ -28,13 +28,17 @@ constexpr int FIN_THREADS = FIN_THREADS_N;
 #ifndef FIN_MINB_THREE_INPLACE
 #define FIN_MINB_THREE_INPLACE 3
 #endif
+#ifndef FIN_THREADS_INPLACE_N
+#define FIN_THREADS_INPLACE_N FIN_THREADS_N
+#endif
+constexpr int FIN_THREADS_INPLACE = FIN_THREADS_INPLACE_N;
 #ifndef FIN_MINB_CIRC_INPLACE
 #define FIN_MINB_CIRC_INPLACE 4
 #endif
 // INPLACE: the agents keep their slots (resident-order steps, A.inplace == 1) -- a separate instantiation, so that the constants
 // the other variant carries from `in` to `out` cost neither loads nor registers here
 template <int MODEL, bool INPLACE>
-__global__ void __launch_bounds__(FIN_THREADS, MODEL == 0 ? (INPLACE ? FIN_MINB_CIRC_INPLACE : FIN_MINB_CIRC) : (INPLACE ? FIN_MINB_THREE_INPLACE : FIN_MINB_THREE))
+__global__ void __launch_bounds__(INPLACE ? FIN_THREADS_INPLACE : FIN_THREADS, MODEL == 0 ? (INPLACE ? FIN_MINB_CIRC_INPLACE : FIN_MINB_CIRC) : (INPLACE ? FIN_MINB_THREE_INPLACE : FIN_MINB_THREE))
 k_finish(const StepArgs A) {
     const int t0 = blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = t0 < eff_n(A.n, A.n_dev);
@@ -177,13 +181,14 @@ k_finish(const StepArgs A) {
         double dd = live ? hypot(npx - px, npy - py) : 0.0;
         if (isnan(dd)) dd = -ninf;                                              // unknown drift: never trust the kept order
         unsigned long long db = (unsigned long long)__double_as_longlong(dd);
-        __shared__ unsigned long long s_red[3][FIN_THREADS / 32];
+        constexpr int BT = INPLACE ? FIN_THREADS_INPLACE : FIN_THREADS;
+        __shared__ unsigned long long s_red[3][BT / 32];
         vm = warp_max_u64(vm); vb = warp_max_u64(vb); db = warp_max_u64(db);
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
         if (lane == 0) { s_red[0][warp] = vm; s_red[1][warp] = vb; s_red[2][warp] = db; }
         __syncthreads();
         if (warp == 0) {
-            constexpr int NW = FIN_THREADS / 32;
+            constexpr int NW = BT / 32;
             vm = lane < NW ? s_red[0][lane] : 0ULL; vb = lane < NW ? s_red[1][lane] : 0ULL; db = lane < NW ? s_red[2][lane] : 0ULL;
             vm = warp_max_u64(vm); vb = warp_max_u64(vb); db = warp_max_u64(db);
             if (lane == 0) { atomicMax(&A.chain->vmax_next[0], vm); atomicMax(&A.chain->vmax_next[1], vb); atomicMax(&A.chain->disp_step, db); }
