@@ -182,8 +182,9 @@ def run_reference(args, rank, world):
     # warm-up steps are run inside cpu_port_rate (1 per replica); `steps` timed steps per replica
     steps = max(1, min(args.steps, 5))
     rate, secs = cpu_port_rate(args.model, n_sample, steps, args.density, threads=cores)
-    sample = '%d independent replicas of %d %s agents (density %.3g /m^2) x %d steps, C port of the numba reference' % (
-        cores, n_sample, args.model, args.density, steps)
+    sample = ('%d independent replicas of %d %s agents (density %.3g /m^2) x %d steps, C port of the numba reference (bit-identical to it; '
+              'the numba original is 8 - 10x slower than this port: profiles/reference_numba_vs_port_container_cpu.json)' % (
+                  cores, n_sample, args.model, args.density, steps))
     line = {
         'impl': 'reference', 'metric': 'agent-steps/sec', 'value': rate, 'unit': 'agent-steps/s', 'n_gpus': args.gpus,
         'steps': steps, 'warmup': 1, 'ms_per_step': 1e3 * secs / steps, 'higher_is_better': True, 'scaling': 'weak',
