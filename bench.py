@@ -405,6 +405,7 @@ def main():
     ap.add_argument('--rebuild-max', type=int, default=16,
                     help='rebuild the block list at most every this many steps (resident-order steps, include/crowd_b200.h); '
                          '1 = rebuild at every step like the reference')
+    ap.add_argument('--rebuild-min-agents', type=int, default=16384, help='crowds below this size rebuild at every step (and replay CUDA graphs)')
     ap.add_argument('--skin', type=float, default=0.10, help='widening of the search cells that the kept block list relies on')
     ap.add_argument('--variant', type=int, default=3, help='agent-agent kernel variant (3 once-per-pair, 2 both-sides fused kernel)')
     args = ap.parse_args()
@@ -464,7 +465,7 @@ def main():
         dev.set_stream(torch.cuda.current_stream().cuda_stream)
         dev.set_variant(args.variant)
         dev.set_search_refinement(args.refinement)
-        dev.set_rebuild_policy(args.skin, args.rebuild_max)
+        dev.set_rebuild_policy(args.skin, args.rebuild_max, args.rebuild_min_agents)
         dev.set_obstacles(obstacles)
         field_build = None
         if args.workload == 'room_exit' and args.field_step > 0:
