@@ -1658,6 +1658,28 @@ int cdb_step(cdb_sim *sim, uint32_t flags, double cell_size, double dt_min, doub
             k += 1;
         }
         sim->profiling = prof_saved;
+        // Long calls on kept block lists: look at the counters every 16 steps WITHOUT waiting (the copy queued at step 16 j + 8 is
+        // read once its event has completed), so that the rebuild interval follows a crowd that speeds up and refused steps are
+        // noticed within a few steps instead of at the next synchronisation point.
+        if (!sim->defer_sync && sim->pairs_pending && n_steps - k > 8 && chain_usable(sim, flags, cell_size)) {
+            if (sim->pairs_inflight) {
+                bool refused = false;
+                int64_t dev_now = sim->iterations;
+                CKS(harvest_pairs(sim, &refused, &dev_now));
+                if (refused) {
+                    if (++regrown > 64) return fail(CDB_ERR_CAPACITY, "steps keep being refused (pair list overflow / stale search lattice)");
+                    const int64_t missing = sim->iterations - dev_now;
+                    sim->chain_valid = false;
+                    sim->iterations = dev_now;
+                    k -= missing;
+                }
+            } else if ((k & 15) == 8) {
+                CKS(read_counters(sim));
+                CK(cudaEventRecord(sim->ev_pairs, sim->stream));
+                sim->pairs_inflight = true;
+                sim->iterations_at_check = sim->iterations;
+            }
+        }
         // Synchronisation points: the dt ring is about to wrap, the call is complete, or (variant 3) every 64 steps, so
         // that steps the device did not apply because the pair list overflowed are noticed and repeated early.
         const bool ring_point = log_dt && sim->iterations % DT_LOG == 0;
