@@ -174,6 +174,12 @@ struct cdb_sim {
     ChainState *d_chain = nullptr;
     double drift_limit = 0.0;        // of the current block list: (coverage of the search cells - interaction range) / 2
 
+    // a kept step is the same launch sequence on the same buffers every time: replayed as a CUDA graph (one per buffer parity)
+    struct KeptGraph { const void *cur, *cells, *pairs; long long cap; uint32_t flags; double cell_size, dt_min, dt_max; const void *log;
+                       int64_t n; uint64_t version; cudaGraphExec_t exec; int64_t launches; } kept_graph[4] = {};
+    int kept_graph_next = 0;
+    bool kept_graph_ok = true;       // false once this stream has refused a capture
+    int64_t kept_graph_max_agents = 200000;   // larger crowds are not launch-bound
     int64_t small_max = SMALL_MAX;   // crowds up to this size are stepped by one thread block (small_kernel.cuh); 0: never
 
     // obstacles / navigation
@@ -869,6 +875,7 @@ int cdb_destroy(cdb_sim *sim) {
     if (sim->ev_main) cudaEventDestroy(sim->ev_main);
     if (sim->ev_pairs) cudaEventDestroy(sim->ev_pairs);
     cudaFree(sim->d_scal); cudaFree(sim->d_chain);
+    for (auto &g : sim->kept_graph) if (g.exec) cudaGraphExecDestroy(g.exec);
     cudaFree(sim->d_grid); cudaFree(sim->d_cell_count); cudaFree(sim->d_cell_start); cudaFree(sim->d_cell_fill);
     cudaFree(sim->d_cell_of_slot); cudaFree(sim->d_order_tmp); cudaFree(sim->d_order); if (sim->d_nbr_sweep != sim->d_nbr) cudaFree(sim->d_nbr_sweep); cudaFree(sim->d_nbr); cudaFree(sim->d_scan_partials);
     cudaFree(sim->d_bbox); cudaFreeHost(sim->h_bbox);
@@ -1446,6 +1453,74 @@ static bool chain_usable(const cdb_sim *sim, uint32_t flags, double cell_size) {
            !sim->dev_counts && sim->pb.ctr && (SIGTH_SOC + 2.0 * sim->ext_max) * (1.0 + 1e-9) < cell_size;
 }
 
+// the launches of a step on the kept order (resident-order steps), in stream order
+static int issue_kept_launches(cdb_sim *sim, uint32_t flags, double dt_min, double dt_max, double *log) {
+    LAUNCH(sim, k_chain_begin, 1, 32, 0, sim->d_chain, sim->d_vmax, 0);
+    CKS(prof_mark(sim));                 // (the phase marks of issue_step; no-ops unless profiling, which rules the graph out)
+    sim->chain_step = true;
+    sim->chain_inplace = true;
+    const int rc = launch_step_kernel(sim, flags, dt_min, dt_max, log);
+    sim->chain_step = false;
+    sim->chain_inplace = false;
+    CKS(rc);
+    LAUNCH(sim, k_chain_end, 1, 32, 0, sim->d_chain, sim->pb.ctr, (long long)sim->pb.cap);
+    CKS(prof_mark(sim));
+    LAUNCH(sim, k_step_advance, 1, 32, 0, sim->d_stepctr, sim->pb.ctr, (long long)sim->pb.cap);
+    CKS(prof_mark(sim));
+    CK(cudaGetLastError());
+    return CDB_OK;
+}
+
+static bool kept_graph_usable(const cdb_sim *sim) {
+    return sim->use_graphs && sim->kept_graph_ok && !sim->profiling && sim->n <= sim->kept_graph_max_agents && sim->stream != nullptr &&
+           sim->stream != cudaStreamLegacy && sim->stream != cudaStreamPerThread;
+}
+
+// a kept step as one graph launch; falls back to plain launches where the stream cannot be captured
+static int issue_kept_step(cdb_sim *sim, uint32_t flags, double cell_size, double dt_min, double dt_max, double *log) {
+    if (!kept_graph_usable(sim)) return issue_kept_launches(sim, flags, dt_min, dt_max, log);
+    cdb_sim::KeptGraph *hit = nullptr;
+    for (auto &g : sim->kept_graph)
+        if (g.exec && g.cur == sim->cur.p && g.cells == sim->d_cell_of_slot && g.pairs == sim->pb.pairs && g.cap == sim->pb.cap && g.flags == flags &&
+            g.cell_size == cell_size && g.dt_min == dt_min && g.dt_max == dt_max && g.log == log && g.n == sim->n_sorted && g.version == sim->state_version)
+            hit = &g;
+    if (!hit) {
+        cdb_sim::KeptGraph &g = sim->kept_graph[sim->kept_graph_next];
+        sim->kept_graph_next = (sim->kept_graph_next + 1) % 4;
+        if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
+        const int64_t launches0 = sim->launches;
+        cudaGraph_t graph = nullptr;
+        if (cudaStreamBeginCapture(sim->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+            cudaGetLastError();
+            sim->kept_graph_ok = false;
+            return issue_kept_launches(sim, flags, dt_min, dt_max, log);
+        }
+        const int rc = issue_kept_launches(sim, flags, dt_min, dt_max, log);      // recorded, not run
+        cudaError_t e = cudaStreamEndCapture(sim->stream, &graph);
+        if (rc == CDB_OK && e == cudaSuccess) e = cudaGraphInstantiate(&g.exec, graph, 0);
+        if (graph) cudaGraphDestroy(graph);
+        g.launches = sim->launches - launches0;
+        sim->launches = launches0;
+        if (rc != CDB_OK || e != cudaSuccess) {
+            cudaGetLastError();
+            g.exec = nullptr;
+            if (rc != CDB_OK) return rc;
+            sim->kept_graph_ok = false;
+            return issue_kept_launches(sim, flags, dt_min, dt_max, log);
+        }
+        g.cur = sim->cur.p; g.cells = sim->d_cell_of_slot; g.pairs = sim->pb.pairs; g.cap = sim->pb.cap; g.flags = flags; g.cell_size = cell_size;
+        g.dt_min = dt_min; g.dt_max = dt_max; g.log = log; g.n = sim->n_sorted; g.version = sim->state_version;
+        hit = &g;
+    }
+    CK(cudaGraphLaunch(hit->exec, sim->stream));
+    sim->launches += hit->launches;
+    // what launch_step_kernel / launch_pairs note on the host for a step on the kept order
+    sim->pairs_pending = true;
+    sim->perm_valid = false;
+    sim->tables_valid = false;
+    return CDB_OK;
+}
+
 // launches of ONE step of the selected nodes (no host synchronisation unless the search lattice has to be re-derived)
 static int issue_step(cdb_sim *sim, uint32_t flags, double cell_size, double dt_min, double dt_max, bool log_dt) {
     double *log = log_dt && (flags & CDB_STEP_INTEGRATOR) ? sim->d_dt_log : nullptr;
@@ -1477,11 +1552,17 @@ static int issue_step(cdb_sim *sim, uint32_t flags, double cell_size, double dt_
             const double scale = 1.0 + sim->skin_frac;
             const bool keep = sim->chain_valid && sim->chain_version == sim->state_version && sim->chain_cell_size == cell_size &&
                               sim->chain_scale == scale && sim->since_rebuild < sim->rebuild_every && sim->n_sorted == sim->n;
-            LAUNCH(sim, k_chain_begin, 1, 32, 0, sim->d_chain, sim->d_vmax, keep ? 0 : 1);
             if (keep) {
-                sim->chain_inplace = true;
+                // the whole step is a fixed launch sequence on fixed buffers
+                sim->chain_step = false;
                 sim->chain_kept++;
+                CKS(issue_kept_step(sim, flags, cell_size, dt_min, dt_max, log));
+                sim->since_rebuild++;
+                sim->chain_version = sim->state_version;
+                sim->iterations++;
+                return CDB_OK;
             } else {
+                LAUNCH(sim, k_chain_begin, 1, 32, 0, sim->d_chain, sim->d_vmax, 1);
                 LAUNCH(sim, k_vmax_init, 1, 32, 0, sim->d_vmax);
                 CKS(build_block_list(sim, cell_size, true, sim->d_vmax, false, search_refinement(sim, cell_size), scale));
                 sim->since_rebuild = 0;
