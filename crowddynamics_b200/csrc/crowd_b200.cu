@@ -65,6 +65,7 @@ int dev_alloc(T **p, size_t count) {
 }
 
 constexpr int DT_LOG = DT_LOG_SLOTS;
+constexpr int HALO_BLOCKS = 32;    // blocks of the halo pack / unpack kernels (128 measured the same: a column of a 1 M-agent strip is ~1 MB)
 constexpr int STRIP_REFRESH = 16;
 constexpr int PROFILE_MAX_STEPS = 4096;
 constexpr int PROF_EVENTS = 6;   // per step: begin, block list, sweep + alloc, pair evaluation, step kernel, end
@@ -2120,10 +2121,10 @@ static int strip_begin_impl(cdb_sim *sim, uint32_t flags, double cell_size, doub
     // separates my next halo from the neighbour's reading of the previous one
     const size_t par_off = direct ? (size_t)(seq & 1ULL) * (size_t)cdb_halo_buffer_doubles(sim) : 0;
     if (sim->has_left && halo_left_out)
-        LAUNCH(sim, k_halo_pack, 32, 256, 0, sim->d_nbr, rec, sim->d_cell_start, sim->d_cell_count, (int)sim->strip_col_lo, nyb, halo_left_out + par_off,
+        LAUNCH(sim, k_halo_pack, HALO_BLOCKS, 256, 0, sim->d_nbr, rec, sim->d_cell_start, sim->d_cell_count, (int)sim->strip_col_lo, nyb, halo_left_out + par_off,
                (long long)sim->halo_cap, sim->d_error, sim->x_done, direct ? sim->p_flags[0] + 1 : nullptr, seq);   // I am its right neighbour
     if (sim->has_right && halo_right_out)
-        LAUNCH(sim, k_halo_pack, 32, 256, 0, sim->d_nbr, rec, sim->d_cell_start, sim->d_cell_count, (int)sim->strip_col_hi, nyb, halo_right_out + par_off,
+        LAUNCH(sim, k_halo_pack, HALO_BLOCKS, 256, 0, sim->d_nbr, rec, sim->d_cell_start, sim->d_cell_count, (int)sim->strip_col_hi, nyb, halo_right_out + par_off,
                (long long)sim->halo_cap, sim->d_error, sim->x_done ? sim->x_done + 1 : nullptr, direct ? sim->p_flags[1] + 0 : nullptr, seq);
     CK(cudaGetLastError());
     return CDB_OK;
@@ -2160,13 +2161,13 @@ static int strip_finish_impl(cdb_sim *sim, uint32_t flags, double dt_min, double
     const int base_l = (int)sim->capacity, base_r = (int)(sim->capacity + sim->halo_cap);
     const unsigned long long seq = (unsigned long long)sim->iterations + 1;
     if (sim->has_left) {
-        if (halo_left_in) LAUNCH(sim, k_halo_unpack, 32, 1024, 0, halo_left_in, rec, sim->d_nbr, sim->d_nbr_sweep, sim->d_cell_of_slot, sim->d_cell_start, sim->d_cell_count,
+        if (halo_left_in) LAUNCH(sim, k_halo_unpack, HALO_BLOCKS, 1024, 0, halo_left_in, rec, sim->d_nbr, sim->d_nbr_sweep, sim->d_cell_of_slot, sim->d_cell_start, sim->d_cell_count,
                                  0, ny, base_l, (long long)sim->halo_cap, sim->d_error, sim->d_par, direct ? sim->x_flags + 0 : nullptr, seq);
         else LAUNCH(sim, k_ghost_clear, 4, 256, 0, sim->d_cell_start, sim->d_cell_count, 0, ny, base_l);
     }
     if (sim->has_right) {
         const int col = (int)sim->strip_col_hi + 1;
-        if (halo_right_in) LAUNCH(sim, k_halo_unpack, 32, 1024, 0, halo_right_in, rec, sim->d_nbr, sim->d_nbr_sweep, sim->d_cell_of_slot, sim->d_cell_start, sim->d_cell_count,
+        if (halo_right_in) LAUNCH(sim, k_halo_unpack, HALO_BLOCKS, 1024, 0, halo_right_in, rec, sim->d_nbr, sim->d_nbr_sweep, sim->d_cell_of_slot, sim->d_cell_start, sim->d_cell_count,
                                   col, ny, base_r, (long long)sim->halo_cap, sim->d_error, sim->d_par, direct ? sim->x_flags + 1 : nullptr, seq);
         else LAUNCH(sim, k_ghost_clear, 4, 256, 0, sim->d_cell_start, sim->d_cell_count, col, ny, base_r);
     }
