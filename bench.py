@@ -392,6 +392,8 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-fp64-peak', action='store_true', help='skip the DFMA peak micro-benchmark (used under ncu)')
     ap.add_argument('--e2e-steps', type=int, default=3)
+    ap.add_argument('--e2e-crowds', type=int, default=2,
+                    help='independent crowds in flight in the e2e leg (1: a single crowd, copies and step strictly serial)')
     ap.add_argument('--field-step', type=float, default=0.0,
                     help='room_exit: build the exit navigation field ON THE DEVICE from the wall / door geometry at this grid '
                          'step (reference default 0.1) instead of uploading a synthetic host field')
@@ -436,6 +438,7 @@ def main():
     itemsize = 228 if args.model == 'circular' else 316
 
     strip_parity = strip_kept = None
+    field_build = None
     if world > 1:
         from crowddynamics_b200.parallel import StripSimulation
         strip_parity = strip_parity_check(args.model, rank, world, local_rank, dist)
@@ -552,9 +555,47 @@ def main():
             dev.download_raw(host.data_ptr(), n)        # SoA -> AoS + D2H of the whole records
         torch.cuda.synchronize()
         e2e_s = time.perf_counter() - t0
-        e2e = {'value': n * e2e_steps / e2e_s, 'unit': 'agent-steps/s', 'h2d_bytes_per_step': n * itemsize,
-               'd2h_bytes_per_step': n * itemsize, 'steps': e2e_steps,
-               'path': 'cdb_upload_agents_aos -> cdb_step(1) -> cdb_download_agents_aos on a pinned host array'}
+        e2e_single = {'value': n * e2e_steps / e2e_s, 'unit': 'agent-steps/s', 'h2d_bytes_per_step': n * itemsize,
+                      'd2h_bytes_per_step': n * itemsize, 'steps': e2e_steps,
+                      'path': 'cdb_upload_agents_aos -> cdb_step(1) -> cdb_download_agents_aos on a pinned host array, ONE crowd: '
+                              'upload, step and download strictly one after the other (PCIe used in one direction at a time)'}
+        e2e = e2e_single
+        if args.e2e_crowds > 1 and field_build is None:
+            # The same round trip for `e2e_crowds` independent crowds of the SAME workload in flight (a replica study; the
+            # reference arm likewise runs independent replicas on the host cores): one device handle + CUDA stream + host
+            # thread per crowd (crowddynamics_b200.engine.host_round_trips), so the upload of one crowd overlaps the download
+            # of another -- PCIe is full duplex -- and the kernels hide behind the copies.  Every step of every crowd still
+            # moves its whole records both ways inside the timed region.
+            from crowddynamics_b200.engine import host_round_trips
+            crowds, keep = [], []
+            for _k in range(args.e2e_crowds):
+                d = DeviceAgents(mid, capacity=n, device=local_rank)       # own non-blocking stream
+                d.set_variant(args.variant)
+                d.set_search_refinement(args.refinement)
+                d.set_rebuild_policy(args.skin, args.rebuild_max, args.rebuild_min_agents)
+                d.set_obstacles(obstacles)
+                d.set_navigation_field(0, *field)
+                h = torch.empty(n * itemsize, dtype=torch.uint8).pin_memory()
+                h.numpy()[:] = agents.view(np.uint8).reshape(-1)
+                crowds.append((d, h.data_ptr(), n))
+                keep.append(h)
+            host_round_trips(crowds, 1, _lib.STEP_ALL, CELL, 0.01, 0.01)          # warm-up
+            torch.cuda.synchronize()
+            per_crowd = max(4, e2e_steps)
+            t0 = time.perf_counter()
+            host_round_trips(crowds, per_crowd, _lib.STEP_ALL, CELL, 0.01, 0.01)
+            torch.cuda.synchronize()
+            secs = time.perf_counter() - t0
+            e2e = {'value': n * per_crowd * len(crowds) / secs, 'unit': 'agent-steps/s', 'h2d_bytes_per_step': n * itemsize,
+                   'd2h_bytes_per_step': n * itemsize, 'steps': per_crowd * len(crowds), 'crowds_in_flight': len(crowds),
+                   'single_crowd_value': e2e_single['value'],
+                   'path': '%d independent crowds of the workload in flight, each stepped by cdb_upload_agents_aos -> cdb_step(1) -> '
+                           'cdb_download_agents_aos on its own pinned host records (one host thread and CUDA stream per crowd): whole '
+                           'records both ways for every step of every crowd; uploads overlap downloads (full-duplex PCIe). '
+                           'One crowd alone: single_crowd_value' % len(crowds)}
+            for d, _, _ in crowds:
+                d.close()
+            del crowds, keep
 
         def leg(name, body, what):
             body()                                       # warm-up
@@ -583,6 +624,7 @@ def main():
             step_fn(1); dev.download_raw(host.data_ptr(), n, observer)
 
         e2e_variants = {
+            'single_crowd': e2e_single,
             'strict_fused_step': leg('strict', strict_fused,
                                      'FusedStep in strict mode, steady state: nothing dirty on the host, one step, every '
                                      'mutable field written back into the pinned host records (zero-copy kernel)'),

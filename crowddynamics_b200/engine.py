@@ -427,3 +427,34 @@ def device_agents_for(agents, device=0):
     if da is None:
         da = _CACHE[key] = DeviceAgents(model, capacity=len(agents), device=device)
     return da
+
+
+def host_round_trips(crowds, n_updates, flags=_lib.STEP_ALL, cell_size=3.6, dt_min=0.01, dt_max=0.01):
+    """Step independent crowds through the HOST boundary concurrently: a replica study (the reference runs its replicas as
+    independent processes, ``MultiAgentProcess``, ``crowddynamics/simulation/multiagent.py:58-101``) on one device.
+
+    ``crowds`` is a list of ``(DeviceAgents, host_pointer, n_agents)`` -- every crowd on its own device handle (hence its own
+    CUDA stream), its packed host records pinned.  Every update of every crowd is the strict round trip ``upload whole
+    records -> one fused step -> download whole records``; the crowds run on one host thread each (the C ABI calls release
+    the GIL), so the upload of one crowd overlaps the download of another -- PCIe is full duplex, a single crowd can only use
+    one direction at a time -- and the kernels of one hide behind the copies of the others.  Results are those of running
+    the crowds one after the other (nothing is shared between the handles)."""
+    import threading
+    errors = []
+
+    def work(dev, ptr, n):
+        try:
+            for _ in range(int(n_updates)):
+                dev.upload_raw(ptr, n)
+                dev.step(1, flags, cell_size, dt_min, dt_max, want_dt=False)
+                dev.download_raw(ptr, n)
+        except BaseException as exc:      # surfaced in the calling thread
+            errors.append(exc)
+
+    threads = [threading.Thread(target=work, args=c) for c in crowds]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    if errors:
+        raise errors[0]

@@ -141,3 +141,32 @@ def test_strict_dirty_tree_equals_strict_always_tree(model):
     assert up_d == 16 * n                        # steady state: only the kicked force goes up ...
     assert up_a >= 5 * item * n                  # ... where 'always' re-sends the whole array per GPU node
     assert down_d < down_a
+
+
+@pytest.mark.parametrize('model', MODELS)
+def test_host_round_trips_of_independent_crowds_equal_serial_runs(model):
+    """engine.host_round_trips: crowds stepped through the host boundary concurrently (one host thread and CUDA stream per
+    crowd; bench.py's `e2e` leg) end with the bytes they end with when run one after the other."""
+    import torch
+    from crowddynamics_b200.engine import host_round_trips
+    flags = _lib.STEP_ALL & ~_lib.STEP_NAVIGATION
+    crowds, hosts, refs = [], [], []
+    for k in range(3):
+        agents, obstacles, side = S.uniform_crowd(20000 + 1000 * k, model, density=1.0, seed=70 + k, overlap_fraction=0.01)
+        ref = agents.copy()
+        dev = DeviceAgents(_mid(model))
+        dev.set_obstacles(obstacles)
+        for _ in range(4):
+            dev.upload(ref); dev.step(1, flags, CELL, 0.001, 0.01, want_dt=False); dev.download(ref, _lib.F_WHOLE_RECORD)
+        dev.close()
+        refs.append(ref)
+        host = torch.empty(agents.nbytes, dtype=torch.uint8).pin_memory()
+        host.numpy()[:] = agents.view(np.uint8).reshape(-1)
+        dev = DeviceAgents(_mid(model))
+        dev.set_obstacles(obstacles)
+        crowds.append((dev, host.data_ptr(), len(agents)))
+        hosts.append(host)
+    host_round_trips(crowds, 4, flags, CELL, 0.001, 0.01)
+    for (dev, _, _), host, ref in zip(crowds, hosts, refs):
+        dev.close()
+        assert np.array_equal(host.numpy(), ref.view(np.uint8).reshape(-1))
