@@ -22,7 +22,7 @@
 #include <vector>
 
 #ifndef SWEEP_MODE_DEFAULT
-#define SWEEP_MODE_DEFAULT 0     // classification sweep: 0 k_sweep, 1 k_sweep_staged, 2 k_sweep_gated (pair_kernels.cuh)
+#define SWEEP_MODE_DEFAULT 0     // classification sweep: 0 k_sweep, 1 k_sweep_staged (pair_kernels.cuh)
 #endif
 
 #include "kernels.cuh"
@@ -96,7 +96,7 @@ struct cdb_sim {
     int64_t itemsize = 0;
     int n_planes = 0;         // planes that mirror record fields
     int n_alloc_planes = 0;   // planes allocated (== n_planes)
-    int sweep_mode = SWEEP_MODE_DEFAULT;   // 0 k_sweep, 1 k_sweep_staged, 2 k_sweep_gated (env CROWD_B200_SWEEP = plain | staged | gated overrides)
+    int sweep_mode = SWEEP_MODE_DEFAULT;   // 0 k_sweep, 1 k_sweep_staged (env CROWD_B200_SWEEP = plain | staged overrides)
     int variant = 3;          // agent-agent: 1 = one-phase reference kernels, 2 = two-phase inside the fused kernel (every pair
                               // evaluated from both sides), 3 = half-stencil sweep + pair list + one evaluation per pair
     bool auto_lattice_valid = false;
@@ -557,12 +557,8 @@ int launch_pairs(cdb_sim *sim) {
     a.chain = sim->chain_step ? sim->d_chain : nullptr;
     a.drift_limit = sim->drift_limit;
     const int blocks = cdiv(n + a.n_ghost, SW_THREADS);
-    // strips have ghost targets: plain kernel; the gated kernel's queue entries hold slot offsets in 27 bits
-    const int mode = sim->strip ? 0 : (sim->sweep_mode == 2 && n >= SWG_MAX_AGENTS ? 1 : sim->sweep_mode);
-    if (mode == 2) {
-        if (sim->model == CDB_MODEL_CIRCULAR) LAUNCH(sim, k_sweep_gated<0>, blocks, SW_THREADS, 0, a);
-        else LAUNCH(sim, k_sweep_gated<1>, blocks, SW_THREADS, 0, a);
-    } else if (mode == 1) {
+    if (sim->sweep_mode == 1 && !sim->strip) {
+        // candidates staged in shared memory by TMA bulk copies (k_sweep_staged); strips have ghost targets: plain kernel
         if (sim->model == CDB_MODEL_CIRCULAR) LAUNCH(sim, k_sweep_staged<0>, blocks, SW_THREADS, 0, a);
         else LAUNCH(sim, k_sweep_staged<1>, blocks, SW_THREADS, 0, a);
     } else if (sim->model == CDB_MODEL_CIRCULAR) LAUNCH(sim, k_sweep<0>, blocks, SW_THREADS, 0, a);
@@ -824,16 +820,10 @@ int cdb_create(int device, int model, int64_t capacity, cdb_sim **out) {
     sim->itemsize = model == CDB_MODEL_CIRCULAR ? 228 : 316;
     sim->n_planes = model == CDB_MODEL_CIRCULAR ? NP_CIRC : NP_THREE;
     sim->n_alloc_planes = sim->n_planes;
-    if (const char *e = getenv("CROWD_B200_SWEEP"))
-        sim->sweep_mode = strcmp(e, "gated") == 0 ? 2 : (strcmp(e, "staged") == 0 ? 1 : (strcmp(e, "plain") == 0 ? 0 : sim->sweep_mode));
-    if (sim->sweep_mode) {     // 36 - 41 KB of static shared memory per CTA: ask for the largest carve-out so that 5 - 6 CTAs fit an SM
-        if (model == CDB_MODEL_CIRCULAR) {
-            cudaFuncSetAttribute(k_sweep_staged<0>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-            cudaFuncSetAttribute(k_sweep_gated<0>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        } else {
-            cudaFuncSetAttribute(k_sweep_staged<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-            cudaFuncSetAttribute(k_sweep_gated<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        }
+    if (const char *e = getenv("CROWD_B200_SWEEP")) sim->sweep_mode = strcmp(e, "staged") == 0 ? 1 : (strcmp(e, "plain") == 0 ? 0 : sim->sweep_mode);
+    if (sim->sweep_mode) {     // 36 KB of static shared memory per CTA: ask for the largest carve-out so that SWS_MINB CTAs fit an SM
+        if (model == CDB_MODEL_CIRCULAR) cudaFuncSetAttribute(k_sweep_staged<0>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        else cudaFuncSetAttribute(k_sweep_staged<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         cudaGetLastError();
     }
     int rc = [&]() -> int {

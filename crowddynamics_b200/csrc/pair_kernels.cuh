@@ -72,20 +72,14 @@ __device__ __forceinline__ double2 ldg2(const double *p) { return __ldg(reinterp
 // The classification of one candidate: can the pair exert a force at all?  The stored radii / body extents are inflated by
 // SWEEP_EPS (slot 5 of the sweep record), which makes every comparison conservative under any rounding: a pair the exact
 // arithmetic of k_pair_eval would give a force is never dropped.  Fused multiply-adds are fine here (this is a filter, not
-// the reference arithmetic).  Two parts: the sight gate (7 fp64 operations) and, behind it, the contact / time-to-collision
-// test (~20); k_sweep and k_sweep_staged run both on every candidate, k_sweep_gated runs the second on the gated ones only.
-__device__ __forceinline__ bool sweep_gate(double mpx, double mpy, double lim_t, const double2 p, double ro) {
+// the reference arithmetic): ~24 fp64 operations, branch-free.
+template <int MODEL>
+__device__ __forceinline__ bool sweep_keep(double mpx, double mpy, double mvx, double mvy, double mr, double lim_t,
+                                           const double2 p, const double2 v, double ro) {
     const double x = mpx - p.x, y = mpy - p.y;
     const double d2 = fma(x, x, y * y);
     const double lim = lim_t + ro;               // >= (3 + R)(1 + eps): conservative form of h < SIGTH_SOC
-    return d2 <= lim * lim;
-}
-
-template <int MODEL>
-__device__ __forceinline__ bool sweep_force_possible(double mpx, double mpy, double mvx, double mvy, double mr,
-                                                     const double2 p, const double2 v, double ro) {
-    const double x = mpx - p.x, y = mpy - p.y;
-    const double d2 = fma(x, x, y * y);
+    const bool gate = d2 <= lim * lim;
     const double R = mr + ro;                    // inflated r_tot (circular) / sum of body extents (three-circle)
     const double RR = R * R;
     const double cc = d2 - RR;
@@ -103,15 +97,7 @@ __device__ __forceinline__ bool sweep_force_possible(double mpx, double mpy, dou
         // all part pairs receding (b_k <= b + R |v| <= 0) => no positive time-to-collision
         social = fma(bb, bb, -(a * cc)) >= 0.0 && (bb >= -1e-12 || bb * bb <= RR * a);
     }
-    return social || contact;
-}
-
-template <int MODEL>
-__device__ __forceinline__ bool sweep_keep(double mpx, double mpy, double mvx, double mvy, double mr, double lim_t,
-                                           const double2 p, const double2 v, double ro) {
-    const bool gate = sweep_gate(mpx, mpy, lim_t, p, ro);
-    const bool force = sweep_force_possible<MODEL>(mpx, mpy, mvx, mvy, mr, p, v, ro);
-    return gate & force;                         // both evaluated: branch-free
+    return gate && (social || contact);
 }
 
 template <int MODEL>
@@ -378,198 +364,6 @@ __global__ void __launch_bounds__(SW_THREADS, SWS_MINB) k_sweep_staged(const Swe
     if (mine) atomicAdd(&A.pb.cnt[t], mine);
 }
 
-// ---- k_sweep_gated: staged candidates + the classification in two stages ----------------------------------------------------
-// Only ~40 % of the swept candidates lie inside the sight radius (the half stencil of the finer lattice covers 49 m^2, the half
-// disc of radius 3 + 2R 19.7 m^2), and lanes past the end of their own range ride along idle, yet k_sweep runs all ~24 fp64
-// operations on every candidate slot.  Here stage A applies the sight gate only (7 operations) and pushes the gated
-// (target lane, candidate) entries into a per-warp queue in shared memory; whenever 32 entries are queued (and at the end of a
-// column) stage B runs the contact / time-to-collision test with every lane busy.  Same predicates on the same operands as
-// sweep_keep(): the listed pair SET is identical, only the order of the list differs (which k_finish's ordered sums ignore).
-#ifndef SWG_MINB
-#define SWG_MINB 5
-#endif
-constexpr int SWG_STAGE = 128;               // staged output pairs per warp
-constexpr int SWG_QUEUE = 32 * SW_CHUNK + 32;
-constexpr int SWG_MAX_AGENTS = 1 << 26;      // queue entries carry (candidate - hull start) in 27 bits
-
-template <int MODEL>
-__global__ void __launch_bounds__(SW_THREADS, SWG_MINB) k_sweep_gated(const SweepArgs A) {
-    __shared__ int2 s_stage[SW_WARPS][SWG_STAGE];
-    __shared__ __align__(128) double s_rec[SWS_COLS][SWS_CAP * REC_CIRC];
-    __shared__ __align__(16) double s_tgt[SW_THREADS][REC_CIRC];          // the CTA's targets: px py vx vy - R(inflated)
-    __shared__ unsigned s_queue[SW_WARPS][SWG_QUEUE];
-    __shared__ int s_mine[SW_THREADS];
-    __shared__ __align__(8) unsigned long long s_bar[SWS_COLS];
-    __shared__ int s_lo[SWS_COLS][SW_WARPS], s_hi[SWS_COLS][SW_WARPS];
-    const unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int2 *stage = s_stage[warp];
-    unsigned *queue = s_queue[warp];
-    const int g = blockIdx.x * SW_THREADS + threadIdx.x;
-    const int n_own = eff_n(A.n, A.n_dev);
-    const int ny = (int)A.grid->ny, nxg = (int)A.grid->nx;
-    if (A.chain && !(A.chain->disp_acc <= A.drift_limit)) {      // stale search lattice: step not applied (see k_sweep)
-        if (g == 0) A.pb.ctr[0] = CHAIN_STALE;
-        return;
-    }
-    if (threadIdx.x == 0) {
-#pragma unroll
-        for (int k = 0; k < SWS_COLS; ++k) mbar_init(&s_bar[k], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    const bool active = g < n_own;
-    const int t = active ? g : -1, tt = active ? g : 0;
-    const int t_warp = g - lane;                                  // target of lane 0 of this warp
-    constexpr double SWEEP_EPS = MODEL == 0 ? PREFILTER_EPS : BOUND_EPS;
-    double mpx, mpy, lim_t;
-    {
-        const double *r = A.nbr_sweep + (size_t)tt * REC_CIRC;
-        const double2 p = ldg2(r), v = ldg2(r + 2), q = ldg2(r + 4);
-        mpx = p.x; mpy = p.y;
-        lim_t = SIGTH_SOC * (1.0 + SWEEP_EPS) + q.y;
-        double2 *d = reinterpret_cast<double2 *>(s_tgt[threadIdx.x]);
-        d[0] = p; d[1] = v; d[2] = q;
-        s_mine[threadIdx.x] = 0;
-    }
-    const int c = A.cell_sorted[tt];
-    const int cx = c / ny, cy = c - cx * ny;
-    const int reach = A.reach;
-    const int ylo = max(cy - reach, 0), yhi = min(cy + reach, ny - 1);
-    auto range = [&](int dx, int &b, int &e) {
-        b = 0; e = 0;
-        const int x2 = cx + dx;
-        if (active && dx <= reach && x2 < nxg) {
-            const int last = x2 * ny + yhi;
-            e = A.cell_start[last] + A.cell_count[last];
-            b = dx == 0 ? t + 1 : A.cell_start[x2 * ny + ylo];
-        }
-    };
-#pragma unroll
-    for (int dx = 0; dx < SWS_COLS; ++dx) {
-        int b, e;
-        range(dx, b, e);
-        const int lo = __reduce_min_sync(FULL, e > b ? b : 0x7fffffff);
-        const int hi = __reduce_max_sync(FULL, e > b ? e : 0);
-        if (lane == 0) { s_lo[dx][warp] = lo; s_hi[dx][warp] = hi; }
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-#pragma unroll
-        for (int dx = 0; dx < SWS_COLS; ++dx) {
-            int lo = 0x7fffffff, hi = 0;
-#pragma unroll
-            for (int w = 0; w < SW_WARPS; ++w) { lo = min(lo, s_lo[dx][w]); hi = max(hi, s_hi[dx][w]); }
-            const int len = hi - lo;
-            if (len > 0 && len <= SWS_CAP) {
-                const unsigned bytes = (unsigned)len * (REC_CIRC * (unsigned)sizeof(double));
-                mbar_expect_tx(&s_bar[dx], bytes);
-                bulk_g2s(s_rec[dx], A.nbr_sweep + (size_t)lo * REC_CIRC, bytes, &s_bar[dx]);
-            }
-        }
-    }
-    int nst = 0, qn = 0;
-    auto flush = [&]() {
-        unsigned long long base = 0;
-        if (lane == 0) base = atomicAdd(&A.pb.ctr[0], (unsigned long long)nst);
-        base = __shfl_sync(FULL, base, 0);
-        __syncwarp();
-        for (int i = lane; i < nst; i += 32) {
-            const unsigned long long p = base + i;
-            if (p < (unsigned long long)A.pb.cap) {
-                const int2 e = stage[i];
-                A.pb.pairs[p] = e;
-                atomicAdd(&A.pb.cnt[e.y], 1);
-            }
-        }
-        __syncwarp();
-        nst = 0;
-    };
-    // stage B: the last m (<= 32) queued entries, one per lane; `lo` is the hull start the entries are relative to
-    auto drain = [&](int m, int lo, auto load) {
-        __syncwarp();
-        const bool val = lane < m;
-        const unsigned en = queue[qn - m + (val ? lane : 0)];
-        const int tl = (int)(en & 31u);
-        const int u = lo + (int)(en >> 5);
-        const double2 *tg = reinterpret_cast<const double2 *>(s_tgt[warp * 32 + tl]);
-        const double2 tp = tg[0], tv = tg[1], tq = tg[2];
-        double2 p, v;
-        double ro;
-        load(u, p, v, ro);
-        const bool keep = val && sweep_force_possible<MODEL>(tp.x, tp.y, tv.x, tv.y, tq.y, p, v, ro);
-        const unsigned mk = __ballot_sync(FULL, keep);
-        if (keep) {
-            stage[nst + __popc(mk & ((1u << lane) - 1u))] = make_int2(t_warp + tl, u);
-            atomicAdd(&s_mine[warp * 32 + tl], 1);
-        }
-        nst += __popc(mk);
-        qn -= m;
-        __syncwarp();
-        if (nst > SWG_STAGE - 32) flush();
-    };
-    // stage A over [b, e): sight gate, gated entries queued; lanes past their range shadow record `idle`
-    auto sweep = [&](int b, int e, int lo, int idle, auto load_gate, auto load) {
-        const int maxlen = __reduce_max_sync(FULL, e - b);
-        for (int k0 = 0; k0 < maxlen; k0 += SW_CHUNK) {
-            bool gate[SW_CHUNK];
-#pragma unroll
-            for (int kk = 0; kk < SW_CHUNK; ++kk) {
-                const int u = b + k0 + kk;
-                const bool inr = u < e;
-                double2 p;
-                double ro;
-                load_gate(inr ? u : idle, p, ro);
-                gate[kk] = inr & sweep_gate(mpx, mpy, lim_t, p, ro);
-            }
-#pragma unroll
-            for (int kk = 0; kk < SW_CHUNK; ++kk) {
-                const unsigned m = __ballot_sync(FULL, gate[kk]);
-                if (gate[kk]) queue[qn + __popc(m & ((1u << lane) - 1u))] = (unsigned)lane | ((unsigned)(b + k0 + kk - lo) << 5);
-                qn += __popc(m);
-            }
-            while (qn >= 32) drain(32, lo, load);
-        }
-        if (qn) drain(qn, lo, load);                             // end of the column: the queue is emptied
-    };
-    for (int dx = 0; dx <= reach; ++dx) {
-        int lo = 0x7fffffff, hi = 0;
-#pragma unroll
-        for (int w = 0; w < SW_WARPS; ++w) { lo = min(lo, s_lo[dx][w]); hi = max(hi, s_hi[dx][w]); }
-        const int len = hi - lo;
-        if (len <= 0) continue;                                  // no candidates for any target of the CTA
-        int b, e;
-        range(dx, b, e);
-        if (len <= SWS_CAP) {
-            unsigned spins = 0;
-            while (!mbar_try_wait(&s_bar[dx], 0)) { if (++spins > (1u << 26)) asm volatile("trap;"); }
-            const double *base = s_rec[dx];
-            sweep(b, e, lo, lo,
-                  [&](int u, double2 &p, double &ro) {
-                      const double *r = base + (u - lo) * REC_CIRC;
-                      p = *reinterpret_cast<const double2 *>(r); ro = r[5];
-                  },
-                  [&](int u, double2 &p, double2 &v, double &ro) {
-                      const double *r = base + (u - lo) * REC_CIRC;
-                      p = *reinterpret_cast<const double2 *>(r); v = *reinterpret_cast<const double2 *>(r + 2); ro = r[5];
-                  });
-        } else {
-            sweep(b, e, lo, tt,
-                  [&](int u, double2 &p, double &ro) {
-                      const double *r = A.nbr_sweep + (size_t)u * REC_CIRC;
-                      p = ldg2(r); ro = __ldg(r + 5);
-                  },
-                  [&](int u, double2 &p, double2 &v, double &ro) {
-                      const double *r = A.nbr_sweep + (size_t)u * REC_CIRC;
-                      p = ldg2(r); v = ldg2(r + 2); ro = __ldg(r + 5);
-                  });
-        }
-    }
-    if (nst) flush();
-    __syncwarp();
-    const int mine = s_mine[threadIdx.x];
-    if (mine) atomicAdd(&A.pb.cnt[t], mine);
-}
-
 // private region of the contribution array for every agent (order of the regions is irrelevant); one atomic per block
 __global__ void __launch_bounds__(256) k_pair_alloc(PairBuf pb, int n_slots) {
     __shared__ int s_warp[8];
@@ -647,6 +441,9 @@ __device__ __forceinline__ void pair_circular_both(double pxt, double pyt, doubl
 
 // ---- both sides of a three-circle pair in the reference's (i, j) orientation (interactions.py:75-104, distance.py:55-105,
 //      power_law.py:264-363): the body of pair_three_exact() of step_kernel.cuh with the per-side tail run twice ------------
+#ifndef PAIR_HMIN_RANKED
+#define PAIR_HMIN_RANKED 1      // distance_three_circles: rank the nine part pairs in fp32, exact hypot for the possible minima only
+#endif
 struct Three {               // kinematics of one three-circle agent as the pair kernels need them
     double x0, y0, x1, y1, x2, y2;   // torso, left shoulder, right shoulder centres
     double rt, rs;           // torso / shoulder radius
@@ -668,9 +465,45 @@ __device__ __forceinline__ void pair_three_both(const Three &I, const Three &J, 
                                                 LoadContact load_contact, double fi[3], double fj[3]) {
     fi[0] = fi[1] = fi[2] = fj[0] = fj[1] = fj[2] = 0.0;
     const double jx[3] = {J.x0, J.x1, J.x2}, jy[3] = {J.y0, J.y1, J.y2}, rj[3] = {J.rt, J.rs, J.rs};
-    // distance_three_circles (distance.py:55-105): strict '<', first wins, order torso, left, right
+    // distance_three_circles (distance.py:55-105): h = hypot(x, y) - (r_i + r_j) over the nine part pairs, strict '<', first
+    // wins, order torso, left, right.  The nine fp64 hypot are most of this kernel's instructions, and all but one lose:
+    // the part pairs are RANKED in fp32 first (error of h below 4e-7 (d_max + radii); the margin is five times that), and
+    // the exact hypot runs only for those that can attain the minimum, in the reference's order with the reference's rule.
+    // Every part pair whose exact h equals the exact minimum is a candidate and every other candidate loses the strict
+    // comparison, so h_min, the winning pair and its (x, y, d) are the very numbers the nine-fold loop produces
+    // (validated on the host against that loop, 24 M pairs incl. exact ties: scripts/validate_hmin_ranking.c).
     double h_min = nan(""), sx = 0.0, sy = 0.0, sd = 0.0;
     int i_min = 0, j_min = 0;
+#if PAIR_HMIN_RANKED
+    {
+        const float rit = (float)I.rt, ris = (float)I.rs, rjt = (float)J.rt, rjs = (float)J.rs;
+        float ha[9], ha_lo = 3.0e38f, d_hi = 0.0f, chk = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+            const int pi_ = k / 3, pj_ = k % 3;
+            const double x = (pi_ == 0 ? I.x0 : (pi_ == 1 ? I.x1 : I.x2)) - jx[pj_];
+            const double y = (pi_ == 0 ? I.y0 : (pi_ == 1 ? I.y1 : I.y2)) - jy[pj_];
+            const float df = __fsqrt_rn((float)fma(x, x, y * y));
+            ha[k] = df - ((pi_ == 0 ? rit : ris) + (pj_ == 0 ? rjt : rjs));
+            ha_lo = fminf(ha_lo, ha[k]); d_hi = fmaxf(d_hi, df); chk += ha[k];
+        }
+        const float thr = ha_lo + 2.0f * (1e-6f * (d_hi + rit + ris + rjt + rjs) + 1e-15f);
+        unsigned cand = 0;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) cand |= ha[k] <= thr ? (1u << k) : 0u;
+        if (!(fabsf(chk) < 1e30f)) cand = 0x1ffu;       // NaN / overflow somewhere: all nine, exactly the reference's loop
+        while (cand) {
+            const int k = __ffs((int)cand) - 1;
+            cand &= cand - 1;
+            const int pi_ = (k >= 3) + (k >= 6), pj_ = k - 3 * pi_;
+            const double x = sel3(pi_, I.x0, I.x1, I.x2) - sel3(pj_, J.x0, J.x1, J.x2);
+            const double y = sel3(pi_, I.y0, I.y1, I.y2) - sel3(pj_, J.y0, J.y1, J.y2);
+            const double d = hypot(x, y);
+            const double h = d - ((pi_ == 0 ? I.rt : I.rs) + (pj_ == 0 ? J.rt : J.rs));
+            if (h < h_min || isnan(h_min)) { h_min = h; sx = x; sy = y; sd = d; i_min = pi_; j_min = pj_; }
+        }
+    }
+#else
 #pragma unroll 1
     for (int pi_ = 0; pi_ < 3; ++pi_) {
         const double xi = sel3(pi_, I.x0, I.x1, I.x2), yi = sel3(pi_, I.y0, I.y1, I.y2), rip = pi_ == 0 ? I.rt : I.rs;
@@ -682,6 +515,7 @@ __device__ __forceinline__ void pair_three_both(const Three &I, const Three &J, 
             if (h < h_min || isnan(h_min)) { h_min = h; sx = x; sy = y; sd = d; i_min = pi_; j_min = pj_; }
         }
     }
+#endif
     if (!(h_min < SIGTH_SOC)) return;
     double nx = 0.0, ny = 0.0;
     if (sd != 0.0) { nx = sx / sd; ny = sy / sd; }

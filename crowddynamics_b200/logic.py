@@ -36,7 +36,11 @@ except Exception:  # noqa
 
 
 class LogicNodeBase:
-    """Minimal stand-in for reference simulation/base.py:27-84 (anytree NodeMixin + traitlets ``name``)."""
+    """Minimal stand-in for reference simulation/base.py:27-84 (anytree NodeMixin + traitlets ``name``), used only where the
+    reference package (hence its real ``LogicNode``) is not importable.  It restates that interface on purpose --
+    ``inject_before / inject_after / add_children``, ``<<`` composition, ``tree['Name']`` lookup and its ``KeyError`` text
+    are the reference's, method for method, so that node trees written for the reference run unchanged; there is no logic
+    of its own here."""
 
     def __init__(self, *args, **kwargs):
         self.name = kwargs.pop('name', self.__class__.__name__)
