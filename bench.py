@@ -392,7 +392,7 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-fp64-peak', action='store_true', help='skip the DFMA peak micro-benchmark (used under ncu)')
     ap.add_argument('--e2e-steps', type=int, default=3)
-    ap.add_argument('--e2e-crowds', type=int, default=2,
+    ap.add_argument('--e2e-crowds', type=int, default=4,
                     help='independent crowds in flight in the e2e leg (1: a single crowd, copies and step strictly serial)')
     ap.add_argument('--field-step', type=float, default=0.0,
                     help='room_exit: build the exit navigation field ON THE DEVICE from the wall / door geometry at this grid '

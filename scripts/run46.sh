@@ -29,8 +29,7 @@ echo "== 3. driver invocation, e2e with 2 / 3 / 4 crowds in flight"
 for c in 2 3 4; do
   timeout 300 python bench.py --gpus 1 --steps 20 --warmup 5 --no-cpu-baseline --e2e-crowds $c > gpurun_out/${T}_bench_c$c.json 2> gpurun_out/${T}_bench_c$c.err; summ gpurun_out/${T}_bench_c$c.json
 done
-echo "== 4. room_exit 4M and density 0.125 (ranked)"
-timeout 200 python bench.py --workload room_exit --agents 4000000 --steps 50 --warmup 10 --no-cpu-baseline --no-fp64-peak --e2e-steps 1 --e2e-crowds 1 > gpurun_out/${T}_room4M.json 2> gpurun_out/${T}_room4M.err; summ gpurun_out/${T}_room4M.json
+echo "== 4. density 0.125 (ranked)"
 timeout 200 python bench.py --density 0.125 $B > gpurun_out/${T}_rho0125.json 2> gpurun_out/${T}_rho0125.err; summ gpurun_out/${T}_rho0125.json
 echo "== 5. ncu: k_pair_eval (ranked), k_sweep_staged"
 timeout 240 ncu --set full --clock-control none --import-source on -k regex:'k_pair_eval' -s 10 -c 2 -o gpurun_out/prof_pair_eval_${T} -f python bench.py --steps 6 --warmup 8 --no-cpu-baseline --no-fp64-peak --e2e-steps 1 --e2e-crowds 1 > gpurun_out/ncu_pair_eval_${T}.log 2>&1
