@@ -14,9 +14,6 @@
 #include "pair_kernels.cuh"
 #include "step_kernel.cuh"
 
-#ifndef FIN_PREFETCH
-#define FIN_PREFETCH 1        // k_finish: request the agent's contribution lines before the plane loads
-#endif
 #ifndef FIN_THREADS_N
 #define FIN_THREADS_N 256
 #endif
@@ -66,16 +63,6 @@ k_finish(const StepArgs A) {
         }
         return;
     }
-#if FIN_PREFETCH
-    // the contributions are gathered after the per-agent nodes, through `con_off`: ask for their lines now, so that they
-    // travel together with the planes instead of after them (32 B per entry, 4 per line)
-    if (n_con > 0) {
-        const double *c0 = A.pb.cres + (size_t)con_off * 4;
-        prefetch_line(c0);
-        if (n_con > 3) prefetch_line(c0 + 16);
-        if (n_con > 7) prefetch_line(c0 + 32);
-    }
-#endif
     // ---- phase 1: the agent (one batch of independent loads) --------------------------------------------------------------
     const double px = s(PX, oo), py = s(PY, oo), vx = s(VX, oo), vy = s(VY, oo);
     double e0x = s(E0X, oo), e0y = s(E0Y, oo), fx = s(FX, oo), fy = s(FY, oo);

@@ -70,7 +70,7 @@ struct SweepArgs {
 __device__ __forceinline__ double2 ldg2(const double *p) { return __ldg(reinterpret_cast<const double2 *>(p)); }
 
 #ifndef PAIR_PREFETCH
-#define PAIR_PREFETCH 1      // k_pair_eval: 0 none, 1 next pair's records -> L1, 2 -> L2
+#define PAIR_PREFETCH 1      // k_pair_eval<three_circle>: 0 none, 1 next pair's records -> L1, 2 -> L2 (measured equal to L1)
 #endif
 __device__ __forceinline__ void prefetch_line(const void *p) {
 #if PAIR_PREFETCH == 2
@@ -628,8 +628,9 @@ __global__ void __launch_bounds__(128, MODEL == 0 ? EVAL_MINB_CIRC : EVAL_MINB_T
     const long long np = (long long)A.pb.ctr[0];
     const Soa &s = A.in;
     // The kernel waits on memory, not on arithmetic (ncu, round 2: long_scoreboard 4 warps per issue at 16 warps per SM, L1 hit
-    // rate 53 %): the pair two iterations ahead is read while this one is evaluated, and the records of the next pair are
-    // requested into L1 (prefetch: no registers are held for them).
+    // rate 53 %): the pair two iterations ahead is read while this one is evaluated, and for three-circle agents the records
+    // of the next pair (one 128-byte line each) are requested into L1 -- a prefetch holds no registers.  Measured (1 M agents,
+    // profiles/prefetch_ab_r4c/): three-circle 0.153 -> 0.1445 ms; the cheap circular evaluation got 5 % slower with it.
     const long long stride = (long long)gridDim.x * blockDim.x;
     long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     int2 e0 = p < np ? A.pb.pairs[p] : make_int2(0, 0);
@@ -638,7 +639,7 @@ __global__ void __launch_bounds__(128, MODEL == 0 ? EVAL_MINB_CIRC : EVAL_MINB_T
         const int2 e = e0;
         e0 = e1;
 #if PAIR_PREFETCH
-        if (p + stride < np) {
+        if (MODEL == 1 && p + stride < np) {
             constexpr int REC = MODEL == 0 ? REC_CIRC : REC_THREE;
             prefetch_line(A.nbr + (size_t)e0.x * REC); prefetch_line(A.nbr + (size_t)e0.y * REC);
             prefetch_line(A.par + e0.x); prefetch_line(A.par + e0.y);
