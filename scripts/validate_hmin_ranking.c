@@ -1,3 +1,10 @@
+/* Host-side validation of the part-pair ranking used by k_pair_eval (csrc/pair_kernels.cuh, pair_three_both, PAIR_HMIN_RANKED):
+ * distance_three_circles (reference core/distance.py:55-105) takes the minimum of h = hypot(x, y) - (r_i + r_j) over nine part
+ * pairs with a strict '<' in a fixed order.  The kernel ranks the nine in fp32 and runs the exact hypot only for those within a
+ * margin of the fp32 minimum.  exact() is the reference's loop, fast() the kernel's selection with the same constants; they must
+ * agree BIT FOR BIT (h_min, the winning pair, x, y, d) -- random pairs, pairs far from the origin, coincident agents, zero radii
+ * and configurations with exact ties.  Usage: validate_hmin_ranking [pairs per mode, default 3000000]; exit status 1 on mismatch.
+ * Test infrastructure (tests/test_hmin_ranking_host.py); nothing in the product links it. */
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -23,8 +30,8 @@ static void fast(const A3*I,const A3*J,double*h_min,double*sx,double*sy,double*s
 }
 static double U(){return rand()/(double)RAND_MAX;}
 static void mk(A3*a,double cx,double cy,double phi,double rt,double rs,double rts){a->x[0]=cx;a->y[0]=cy;double ox=rts*sin(phi),oy=-rts*cos(phi);a->x[1]=cx-ox;a->y[1]=cy-oy;a->x[2]=cx+ox;a->y[2]=cy+oy;a->r[0]=rt;a->r[1]=rs;a->r[2]=rs;}
-int main(){long bad=0,n=0;srand(1);
-  for(int mode=0;mode<8;mode++)for(long it=0;it<3000000;it++){A3 I,J;double base=(mode==3)?1e5*(U()-0.5):(mode==4?1e7:0);
+int main(int argc,char**argv){long bad=0,n=0,iters=argc>1?atol(argv[1]):3000000;srand(1);
+  for(int mode=0;mode<8;mode++)for(long it=0;it<iters;it++){A3 I,J;double base=(mode==3)?1e5*(U()-0.5):(mode==4?1e7:0);
     double rt=0.1+0.1*U(),rs=0.05+0.08*U(),rts=0.1+0.1*U();double rt2=rt,rs2=rs,rts2=rts;if(mode!=1&&mode!=5){rt2=0.1+0.1*U();rs2=0.05+0.08*U();rts2=0.1+0.1*U();}
     double phi=(U()-0.5)*6.283,phi2=(U()-0.5)*6.283;double dist=mode==2?1e-9*U():(mode==6?1e-3*U():4*U());double ang=(U()-0.5)*6.283;
     if(mode==1||mode==5){ /* symmetric / aligned: exact ties */ phi2=phi; if(mode==5){phi=0.5*3.141592653589793*(rand()%4);phi2=phi+3.141592653589793*(rand()%2);ang=0.5*3.141592653589793*(rand()%4);dist=0.25*(rand()%16);} }
