@@ -144,3 +144,37 @@ def test_strip_step_schedule():
         assert sim.interval == 1
     sim.adapt_interval(1e-6, 0.21)
     assert sim.interval == 16                       # capped at max_interval
+
+
+def test_host_round_trips_runs_every_crowd_and_surfaces_errors():
+    """engine.host_round_trips (bench.py's e2e leg): one host thread per crowd, every crowd gets its n updates of
+    upload -> step -> download in that order, an exception in one crowd's thread is re-raised in the caller."""
+    import threading
+    from crowddynamics_b200.engine import host_round_trips
+
+    class FakeDevice:
+        def __init__(self, fail_at=None):
+            self.log, self.threads, self.fail_at = [], set(), fail_at
+
+        def upload_raw(self, ptr, n):
+            self.threads.add(threading.get_ident())
+            self.log.append(('up', ptr, n))
+
+        def step(self, k, flags, cell_size, dt_min, dt_max, want_dt=True):
+            if self.fail_at is not None and len(self.log) // 3 == self.fail_at:
+                raise CrowdDynamicsException('device error')
+            self.log.append(('step', k, flags, cell_size, dt_min, dt_max, want_dt))
+
+        def download_raw(self, ptr, n):
+            self.log.append(('down', ptr, n))
+
+    devs = [FakeDevice() for _ in range(3)]
+    host_round_trips([(d, 1000 + k, 10 * (k + 1)) for k, d in enumerate(devs)], 4, flags=0x7f, cell_size=3.6, dt_min=0.001, dt_max=0.01)
+    for k, d in enumerate(devs):
+        assert len(d.threads) == 1 and threading.get_ident() not in d.threads
+        assert d.log == [('up', 1000 + k, 10 * (k + 1)), ('step', 1, 0x7f, 3.6, 0.001, 0.01, False), ('down', 1000 + k, 10 * (k + 1))] * 4
+    bad = FakeDevice(fail_at=2)
+    good = FakeDevice()
+    with pytest.raises(CrowdDynamicsException):
+        host_round_trips([(good, 1, 5), (bad, 2, 5)], 4)
+    assert len(good.log) == 12 and len(bad.log) == 7      # the healthy crowd finished, the failing one stopped at its third update
